@@ -1,0 +1,643 @@
+/* oracle/m3d_oracle.c — CPU ORACLE: TEST INFRASTRUCTURE, NOT PRODUCT CODE.  See m3d_oracle.h.
+ *
+ * Compile with -ffp-contract=off: every fused multiply-add below is an explicit fmaf() placed
+ * where nvcc 12.9 contracts the reference's expressions (PTX of lesson_16.cu inspected, see
+ * DESIGN.md "FP contraction"), everything else is a separately rounded IEEE operation.
+ * Citations "L16" = src/lesson_16.cu, "CW" = src/cudaWrapper.cpp, "SL" = src/gpu6DSLAM.cpp,
+ * "AXB" = src/CCUDAAXBSolverWrapper.cpp of the reference.
+ */
+#include "m3d_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static int g_threads = 0;
+
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+	return g_threads > 0 ? g_threads : omp_get_max_threads();
+#else
+	return 1;
+#endif
+}
+
+void orc_set_num_threads(int n)
+{
+	g_threads = n;
+#ifdef _OPENMP
+	if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
+static float f32_from_bits(uint32_t u)
+{
+	float f;
+	memcpy(&f, &u, 4);
+	return f;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Grid parameters — L16:23-106 (cudaCalculateGridParams).
+ * thrust::minmax_element per axis (L16:34-45), then on the host (L16:64-91):
+ *   max += ext; min -= ext; nb = int((max-min)/res + 1)  [float arithmetic, truncation]
+ *   number_of_buckets = nbX*nbY*nbZ evaluated in int32 and widened (L16:80).
+ * --------------------------------------------------------------------------------------------- */
+void orc_grid_params_compute(const orc_point *c, int n, float rx, float ry, float rz, float ext, orc_grid_params *out)
+{
+	float mnx = c[0].x, mxx = c[0].x, mny = c[0].y, mxy = c[0].y, mnz = c[0].z, mxz = c[0].z;
+	for (int i = 1; i < n; i++) {
+		if (c[i].x < mnx) mnx = c[i].x;
+		if (mxx < c[i].x) mxx = c[i].x;
+		if (c[i].y < mny) mny = c[i].y;
+		if (mxy < c[i].y) mxy = c[i].y;
+		if (c[i].z < mnz) mnz = c[i].z;
+		if (mxz < c[i].z) mxz = c[i].z;
+	}
+	mxx += ext; mnx -= ext;
+	mxy += ext; mny -= ext;
+	mxz += ext; mnz -= ext;
+	int nbx = (int)(((mxx - mnx) / rx) + 1);
+	int nby = (int)(((mxy - mny) / ry) + 1);
+	int nbz = (int)(((mxz - mnz) / rz) + 1);
+	memset(out, 0, sizeof(*out));
+	out->number_of_buckets_X = nbx;
+	out->number_of_buckets_Y = nby;
+	out->number_of_buckets_Z = nbz;
+	/* int32 product with wrap-around, as the reference's `int*int*int` behaves on the GPU host */
+	out->number_of_buckets = (int64_t)(int32_t)((uint32_t)nbx * (uint32_t)nby * (uint32_t)nbz);
+	out->bounding_box_max_X = mxx; out->bounding_box_min_X = mnx;
+	out->bounding_box_max_Y = mxy; out->bounding_box_min_Y = mny;
+	out->bounding_box_max_Z = mxz; out->bounding_box_min_Z = mnz;
+	out->resolution_X = rx; out->resolution_Y = ry; out->resolution_Z = rz;
+}
+
+/* Bucket key of one coordinate triple — L16:124-127 (and L16:578-583 for queries):
+ * sub.f32, div.rn.f32, cvt.rzi.s32.f32, then int32 mul-add. */
+static inline int32_t bucket_key(float x, float y, float z, const orc_grid_params *p, int *ix_o, int *iy_o, int *iz_o)
+{
+	int ix = (int)((x - p->bounding_box_min_X) / p->resolution_X);
+	int iy = (int)((y - p->bounding_box_min_Y) / p->resolution_Y);
+	int iz = (int)((z - p->bounding_box_min_Z) / p->resolution_Z);
+	if (ix_o) { *ix_o = ix; *iy_o = iy; *iz_o = iz; }
+	return (int32_t)((uint32_t)ix * (uint32_t)p->number_of_buckets_Y * (uint32_t)p->number_of_buckets_Z +
+			(uint32_t)iy * (uint32_t)p->number_of_buckets_Z + (uint32_t)iz);
+}
+
+void orc_bucket_keys(const orc_point *c, int n, const orc_grid_params *p, int32_t *keys)
+{
+#pragma omp parallel for schedule(static)
+	for (int i = 0; i < n; i++) keys[i] = bucket_key(c[i].x, c[i].y, c[i].z, p, 0, 0, 0);
+}
+
+/* Stable LSD radix sort of (key, index) by key: the permutation thrust::sort produces for the
+ * key-only comparator compareHashElements (lesson_16.cuh:6-13) — CUB merge sort, stable, so
+ * equal buckets keep ascending original index (L16:213-227). */
+static void stable_sort_by_key(orc_hash_element *t, int n)
+{
+	orc_hash_element *tmp = (orc_hash_element *)malloc((size_t)(n > 0 ? n : 1) * sizeof(*tmp));
+	orc_hash_element *src = t, *dst = tmp;
+	for (int pass = 0; pass < 4; pass++) {
+		size_t cnt[257];
+		memset(cnt, 0, sizeof(cnt));
+		int shift = pass * 8;
+		for (int i = 0; i < n; i++) {
+			uint32_t k = (uint32_t)src[i].index_of_bucket ^ 0x80000000u;
+			cnt[((k >> shift) & 255u) + 1]++;
+		}
+		for (int d = 0; d < 256; d++) cnt[d + 1] += cnt[d];
+		for (int i = 0; i < n; i++) {
+			uint32_t k = (uint32_t)src[i].index_of_bucket ^ 0x80000000u;
+			dst[cnt[(k >> shift) & 255u]++] = src[i];
+		}
+		orc_hash_element *s = src; src = dst; dst = s;
+	}
+	/* 4 passes: result is back in t */
+	free(tmp);
+}
+
+/* cudaCalculateGrid — L16:200-243.
+ *  initializeIndByKey (L16:109) + getIndexOfBucketForPoints (L16:119) -> table
+ *  thrust::sort by bucket (L16:216)
+ *  initializeBuckets (L16:131): {-1,-1,0}
+ *  updateBuckets (L16:142-174): run boundaries, INCLUDING the ind==0 behaviour: when element 0 is
+ *     alone in its bucket the next bucket gets index_end=1 instead of index_begin=1 (L16:154-158),
+ *     so that bucket keeps index_begin=-1.  Its index_end is a write race in the reference
+ *     (thread 0 writes 1, the thread at the end of that run writes the run end); this restatement
+ *     applies the writes in ascending thread order, so the run end wins.  number_of_points stays 0
+ *     for it either way, which is all the NN kernel reads before skipping (L16:615-616).
+ *  countNumberOfPointsForBuckets (L16:176-189): n = end-begin iff both != -1
+ *  copyKeys (L16:191): table out. */
+void orc_build_grid(const orc_point *c, int n, const orc_grid_params *p, orc_bucket *buckets, orc_hash_element *table)
+{
+	int64_t nb = p->number_of_buckets;
+#pragma omp parallel for schedule(static)
+	for (int i = 0; i < n; i++) {
+		table[i].index_of_point = i;
+		table[i].index_of_bucket = bucket_key(c[i].x, c[i].y, c[i].z, p, 0, 0, 0);
+	}
+	stable_sort_by_key(table, n);
+#pragma omp parallel for schedule(static)
+	for (int64_t b = 0; b < nb; b++) {
+		buckets[b].index_begin = -1;
+		buckets[b].index_end = -1;
+		buckets[b].number_of_points = 0;
+	}
+	for (int ind = 0; ind < n; ind++) {
+		if (ind == 0) {
+			int b0 = table[0].index_of_bucket;
+			buckets[b0].index_begin = 0;
+			if (n > 1) { /* the reference reads table[1] unconditionally (out of bounds for n==1) */
+				int b1 = table[1].index_of_bucket;
+				if (b0 != b1) {
+					buckets[b0].index_end = 1;
+					buckets[b1].index_end = 1;
+				}
+			}
+			if (n == 1) buckets[b0].index_end = 1; /* the `else if (ind == n-1)` branch is shadowed; n==1 is UB upstream, see DESIGN.md */
+		} else if (ind == n - 1) {
+			buckets[table[ind].index_of_bucket].index_end = ind + 1;
+		} else {
+			int b0 = table[ind].index_of_bucket;
+			int b1 = table[ind + 1].index_of_bucket;
+			if (b0 != b1) {
+				buckets[b0].index_end = ind + 1;
+				buckets[b1].index_begin = ind + 1;
+			}
+		}
+	}
+#pragma omp parallel for schedule(static)
+	for (int64_t b = 0; b < nb; b++) {
+		if (buckets[b].index_begin != -1 && buckets[b].index_end != -1)
+			buckets[b].number_of_points = buckets[b].index_end - buckets[b].index_begin;
+	}
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Angle gate — L16:666-676:  angle = acos(dot) [float overload -> acosf], angled = angle*180.0f/M_PI
+ * (f32 multiply, f64 divide, rounded back to f32), |angled| < 90.0f.
+ *
+ * acosf here is the CUDA device function.  Its code as inlined by nvcc 12.9 (PTX of the NN kernel):
+ *   a = |d|;   if a > 0.56 (0x3F0F5C29): t = sqrt((1-a)/2) via rsqrt.approx + one Newton step, sign of d
+ *              else                      t = d
+ *   s = t + t*(t2*poly(t2))   (asin polynomial, 6 fmaf)
+ *   a <= 0.56 : acos = fma(0x3F6EE581, 0x3FD774EB, -s)            (pi/2 - asin d)
+ *   d >  0.56 : acos = 2*s                      in [0, 0.98 rad]   -> angled <= 56.1 deg -> gate TRUE
+ *   d < -0.56 : acos = 2*fma(c1,c2,s) = pi-2|s| in [2.16, pi]      -> angled >= 123 deg -> gate FALSE
+ *   |d| > 1 or NaN: rsqrt of a negative -> NaN -> every compare false -> gate FALSE
+ * Only the |d| <= 0.56 branch decides anything at the bit level, and it contains no approximate
+ * instruction, so it is restated exactly with fmaf.  tests/test_gpu_gate.py proves this function
+ * equal to the reference expression for ALL 2^32 float inputs on the device.
+ * --------------------------------------------------------------------------------------------- */
+int orc_angle_gate(float d)
+{
+	float a = fabsf(d);
+	if (!(a <= 1.0f)) return 0;                     /* NaN or |d| > 1 */
+	if (a > f32_from_bits(0x3F0F5C29u)) return d > 0.0f;
+	float t2 = d * d;
+	float p = fmaf(t2, f32_from_bits(0x3D10ECEFu), f32_from_bits(0x3C8B1ABBu));
+	p = fmaf(p, t2, f32_from_bits(0x3CFC028Cu));
+	p = fmaf(p, t2, f32_from_bits(0x3D372139u));
+	p = fmaf(p, t2, f32_from_bits(0x3D9993DBu));
+	p = fmaf(p, t2, f32_from_bits(0x3E2AAAC6u));
+	float q = t2 * p;
+	float s = fmaf(q, d, d);
+	float ang = fmaf(f32_from_bits(0x3F6EE581u), f32_from_bits(0x3FD774EBu), -s);
+	float deg = ang * 180.0f;
+	float angled = (float)((double)deg / 3.14159265358979323846);
+	if (angled < 0) angled = -angled;
+	return angled < 90.0f;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Semantic nearest neighbour — L16:531-703 (kernel_semanticNearestNeighborSearch), one query per
+ * loop iteration instead of per thread.  FP pattern (PTX): dist = fma(dz,dz, fma(dx,dx, dy*dy)),
+ * dot = fma(nz,nnz, fma(nx,nnx, ny*nny)), r2 = r*r.
+ * --------------------------------------------------------------------------------------------- */
+static inline int32_t nn_one_query(const orc_point *first, int n_first, const orc_point *q,
+		const orc_hash_element *table, const orc_bucket *buckets, const orc_grid_params *p,
+		float r2, int max_inner, int max_outer, int64_t *evals)
+{
+	float x = q->x, y = q->y, z = q->z;
+	float nx = q->normal_x, ny = q->normal_y, nz = q->normal_z;
+	int label = q->label;
+	if (x < p->bounding_box_min_X || x > p->bounding_box_max_X) return -1; /* L16:562-576 */
+	if (y < p->bounding_box_min_Y || y > p->bounding_box_max_Y) return -1;
+	if (z < p->bounding_box_min_Z || z > p->bounding_box_max_Z) return -1;
+	int ix, iy, iz;
+	int32_t index_bucket = bucket_key(x, y, z, p, &ix, &iy, &iz);           /* L16:578-583 */
+	int32_t nn_index = -1;
+	int isok = 0;
+	if (index_bucket >= 0 && (int64_t)index_bucket < p->number_of_buckets) {
+		int nbY = p->number_of_buckets_Y, nbZ = p->number_of_buckets_Z;
+		int sx = ix == 0 ? 0 : -1, sy = iy == 0 ? 0 : -1, sz = iz == 0 ? 0 : -1;    /* L16:588-595 */
+		int stx = ix == p->number_of_buckets_X - 1 ? 1 : 2;
+		int sty = iy == nbY - 1 ? 1 : 2;
+		int stz = iz == nbZ - 1 ? 1 : 2;
+		float best = 100000000.0f;                                                   /* L16:597 */
+		for (int i = sx; i < stx; i++)
+		for (int j = sy; j < sty; j++)
+		for (int k = sz; k < stz; k++) {
+			int32_t nb = (int32_t)((uint32_t)index_bucket + (uint32_t)(i * nbY * nbZ) + (uint32_t)(j * nbZ) + (uint32_t)k);
+			if (!(nb >= 0 && (int64_t)nb < p->number_of_buckets)) continue;
+			int npts = buckets[nb].number_of_points;
+			if (npts <= 0) continue;                                                 /* L16:615-616 */
+			int cap = nb == index_bucket ? max_inner : max_outer;                    /* L16:618-626 */
+			if (cap <= 0) continue;
+			int iter;
+			if (cap >= npts) iter = 1;
+			else { iter = npts / cap; if (iter <= 0) iter = 1; }                     /* L16:628-635 */
+			int lb = buckets[nb].index_begin, le = buckets[nb].index_end;
+			for (int l = lb; l < le; l += iter) {
+				if (!(l >= 0 && l < n_first)) continue;
+				int hp = table[l].index_of_point;
+				const orc_point *c = &first[hp];
+				float dx = x - c->x, dy = y - c->y, dz = z - c->z;
+				float dist = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+				float dot = fmaf(nz, c->normal_z, fmaf(nx, c->normal_x, ny * c->normal_y));
+				if (evals) (*evals)++;
+				if (c->label == label && orc_angle_gate(dot) && dist <= r2 && dist < best) { /* L16:674-686 */
+					isok = 1;
+					nn_index = hp;
+					best = dist;
+				}
+			}
+		}
+	}
+	return isok ? nn_index : -1;
+}
+
+void orc_nn_search(const orc_point *first, int n_first, const orc_point *second, int n_second,
+		const orc_hash_element *table, const orc_bucket *buckets, const orc_grid_params *p,
+		float search_radius, int max_inner, int max_outer, int32_t *nn_out)
+{
+	float r2 = search_radius * search_radius;
+#pragma omp parallel for schedule(dynamic, 1024)
+	for (int q = 0; q < n_second; q++)
+		nn_out[q] = nn_one_query(first, n_first, &second[q], table, buckets, p, r2, max_inner, max_outer, 0);
+}
+
+int64_t orc_nn_count_evaluations(const orc_point *second, int n_second, const orc_bucket *buckets,
+		const orc_grid_params *p, int max_inner, int max_outer)
+{
+	int64_t total = 0;
+#pragma omp parallel for schedule(static) reduction(+:total)
+	for (int qi = 0; qi < n_second; qi++) {
+		const orc_point *q = &second[qi];
+		if (q->x < p->bounding_box_min_X || q->x > p->bounding_box_max_X) continue;
+		if (q->y < p->bounding_box_min_Y || q->y > p->bounding_box_max_Y) continue;
+		if (q->z < p->bounding_box_min_Z || q->z > p->bounding_box_max_Z) continue;
+		int ix, iy, iz;
+		int32_t ib = bucket_key(q->x, q->y, q->z, p, &ix, &iy, &iz);
+		if (!(ib >= 0 && (int64_t)ib < p->number_of_buckets)) continue;
+		int nbY = p->number_of_buckets_Y, nbZ = p->number_of_buckets_Z;
+		for (int i = (ix == 0 ? 0 : -1); i < (ix == p->number_of_buckets_X - 1 ? 1 : 2); i++)
+		for (int j = (iy == 0 ? 0 : -1); j < (iy == nbY - 1 ? 1 : 2); j++)
+		for (int k = (iz == 0 ? 0 : -1); k < (iz == nbZ - 1 ? 1 : 2); k++) {
+			int32_t nb = ib + i * nbY * nbZ + j * nbZ + k;
+			if (!(nb >= 0 && (int64_t)nb < p->number_of_buckets)) continue;
+			int npts = buckets[nb].number_of_points;
+			if (npts <= 0) continue;
+			int cap = nb == ib ? max_inner : max_outer;
+			if (cap <= 0) continue;
+			int iter = cap >= npts ? 1 : npts / cap;
+			if (iter <= 0) iter = 1;
+			total += (npts + iter - 1) / iter;
+		}
+	}
+	return total;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Host observation assembly — SL:323-398 (duplicated at SL:490-565).
+ * counts per label of the QUERY point (second cloud) over matched queries; obs = {p1-p2 in float
+ * from the TRANSFORMED clouds, x0y0z0 from the UNTRANSFORMED first cloud, P = weight/count}.
+ * Labels outside 0..3 leave P uninitialised upstream; here P = 0 (documented deviation).
+ * --------------------------------------------------------------------------------------------- */
+int orc_build_observations(const orc_point *first_global, const orc_point *first_local,
+		const orc_point *second_global, int n_second, const int32_t *nn, const float *weight4,
+		orc_obs_nn *obs_out)
+{
+	int cnt[4] = {0, 0, 0, 0};
+	for (int i = 0; i < n_second; i++)
+		if (nn[i] != -1) {
+			int l = second_global[i].label;
+			if (l >= 0 && l < 4) cnt[l]++;
+		}
+	int n = 0;
+	for (int i = 0; i < n_second; i++) {
+		if (nn[i] == -1) continue;
+		const orc_point *p1 = &first_global[nn[i]];
+		const orc_point *p2 = &second_global[i];
+		orc_obs_nn o;
+		o.x0 = first_local[nn[i]].x;
+		o.y0 = first_local[nn[i]].y;
+		o.z0 = first_local[nn[i]].z;
+		o.x_diff = p1->x - p2->x;
+		o.y_diff = p1->y - p2->y;
+		o.z_diff = p1->z - p2->z;
+		int l = p2->label;
+		o.P = (l >= 0 && l < 4) ? weight4[l] / (float)cnt[l] : 0.0f;
+		obs_out[n++] = o;
+	}
+	return n;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Normal equations — fill_A_l_cuda (L16:355-428) / fill_A_l_4DOFcuda (L16:441-518), computeR and
+ * compute_a1x..a3x (L16:278-353), cudaCompute_AtP (L16:245-255: AtP = A^T * diag(P)), then
+ * AtPA = AtP*A and AtPl = AtP*l (AXB:420,427, cuBLAS DGEMM).  Here: the same per-observation 3xdof
+ * block, accumulated in long double (the reference's cuBLAS summation order is not specified, so
+ * parity downstream of this point is tolerance-based).  Output column-major dof x dof, like cuBLAS.
+ * --------------------------------------------------------------------------------------------- */
+void orc_normal_equations(const orc_obs_nn *obs, int n_obs, const double *pose6, int dof,
+		double *AtPA_out, double *AtPl_out)
+{
+	double om = pose6[3], fi = pose6[4], ka = pose6[5];
+	double r[9];
+	r[0] = cos(fi) * cos(ka);
+	r[1] = -cos(fi) * sin(ka);
+	r[2] = sin(fi);
+	r[3] = cos(om) * sin(ka) + sin(om) * sin(fi) * cos(ka);
+	r[4] = cos(om) * cos(ka) - sin(om) * sin(fi) * sin(ka);
+	r[5] = -sin(om) * cos(fi);
+	r[6] = sin(om) * sin(ka) - cos(om) * sin(fi) * cos(ka);
+	r[7] = sin(om) * cos(ka) + cos(om) * sin(fi) * sin(ka);
+	r[8] = cos(om) * cos(fi);
+	long double N[36], b[6];
+	for (int i = 0; i < 36; i++) N[i] = 0;
+	for (int i = 0; i < 6; i++) b[i] = 0;
+	for (int k = 0; k < n_obs; k++) {
+		double x0 = obs[k].x0, y0 = obs[k].y0, z0 = obs[k].z0;
+		double a14 = 0.0;
+		double a15 = (-sin(fi) * cos(ka) * x0 + sin(fi) * sin(ka) * y0 + cos(fi) * z0);
+		double a16 = (r[1] * x0 - r[0] * y0);
+		double a24 = (-r[6] * x0 - r[7] * y0 - r[8] * z0);
+		double a25 = (sin(om) * cos(fi) * cos(ka) * x0 - sin(om) * cos(fi) * sin(ka) * y0 + sin(om) * sin(fi) * z0);
+		double a26 = (r[4] * x0 - r[3] * y0);
+		double a34 = (r[3] * x0 + r[4] * y0 + r[5] * z0);
+		double a35 = (-cos(om) * cos(fi) * cos(ka) * x0 + cos(om) * cos(fi) * sin(ka) * y0 - cos(om) * sin(fi) * z0);
+		double a36 = (r[7] * x0 - r[6] * y0);
+		double A[3][6];
+		if (dof == 6) {
+			double t[3][6] = {{-1, 0, 0, -a14, -a15, -a16}, {0, -1, 0, -a24, -a25, -a26}, {0, 0, -1, -a34, -a35, -a36}};
+			memcpy(A, t, sizeof(t));
+		} else {
+			double t[3][6] = {{-1, 0, 0, -a16, 0, 0}, {0, -1, 0, -a26, 0, 0}, {0, 0, -1, -a36, 0, 0}};
+			memcpy(A, t, sizeof(t));
+		}
+		double P = obs[k].P;
+		double l[3] = {obs[k].x_diff, obs[k].y_diff, obs[k].z_diff};
+		for (int rr = 0; rr < 3; rr++)
+			for (int i = 0; i < dof; i++) {
+				double atp = A[rr][i] * P;            /* L16:253 */
+				b[i] += (long double)atp * l[rr];
+				for (int j = 0; j < dof; j++) N[i + j * dof] += (long double)atp * A[rr][j];
+			}
+	}
+	for (int i = 0; i < dof * dof; i++) AtPA_out[i] = (double)N[i];
+	for (int i = 0; i < dof; i++) AtPl_out[i] = (double)b[i];
+}
+
+/* linearSolverCHOL — AXB:484-539: Dpotrf(LOWER) + Dpotrs.  Returns 0, or k>0 when the k-th leading
+ * minor is not positive definite (cuSOLVER's devInfo convention). */
+int orc_chol_solve(const double *A, const double *b, int n, double *x)
+{
+	double L[36];
+	memset(L, 0, sizeof(L));
+	for (int j = 0; j < n; j++) {
+		double d = A[j + j * n];
+		for (int k = 0; k < j; k++) d -= L[j + k * n] * L[j + k * n];
+		if (!(d > 0.0)) return j + 1;
+		d = sqrt(d);
+		L[j + j * n] = d;
+		for (int i = j + 1; i < n; i++) {
+			double s = A[i + j * n];
+			for (int k = 0; k < j; k++) s -= L[i + k * n] * L[j + k * n];
+			L[i + j * n] = s / d;
+		}
+	}
+	double y[6];
+	for (int i = 0; i < n; i++) {
+		double s = b[i];
+		for (int k = 0; k < i; k++) s -= L[i + k * n] * y[k];
+		y[i] = s / L[i + i * n];
+	}
+	for (int i = n - 1; i >= 0; i--) {
+		double s = y[i];
+		for (int k = i + 1; k < n; k++) s -= L[k + i * n] * x[k];
+		x[i] = s / L[i + i * n];
+	}
+	return 0;
+}
+
+/* registerLS (CW:516-581) / registerLS_4DOF (CW:583-648): pose6 = {tx,ty,tz,om,fi,ka}. */
+int orc_register_ls(const orc_obs_nn *obs, int n_obs, double *pose6, int dof, double *x_out)
+{
+	double N[36], b[6], x[6] = {0, 0, 0, 0, 0, 0};
+	orc_normal_equations(obs, n_obs, pose6, dof, N, b);
+	int info = orc_chol_solve(N, b, dof, x);
+	if (info != 0) return -3;
+	pose6[0] += x[0];
+	pose6[1] += x[1];
+	pose6[2] += x[2];
+	if (dof == 6) { pose6[3] += x[3]; pose6[4] += x[4]; pose6[5] += x[5]; }
+	else pose6[5] += x[3];
+	if (x_out) memcpy(x_out, x, sizeof(double) * (size_t)dof);
+	return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Pose helpers.  Matrix4ToEuler(Affine3f) — CW:470-504; EulerToMatrix — CW:506-514.
+ * m4x4 is row-major.  EulerToMatrix upstream is Eigen: AngleAxisf(x)*AngleAxisf(y)*AngleAxisf(z)
+ * (a float quaternion product) converted to a rotation matrix; Eigen is a third-party dependency
+ * absent from /root/reference (unpinned version, find_package(Eigen)), so the published formulae
+ * (half-angle quaternions, Hamilton product, quaternion->matrix) are restated in float.  PARITY
+ * UNPINNED at the last-ulp level; agreement is by tolerance.
+ * --------------------------------------------------------------------------------------------- */
+void orc_matrix4_to_euler(const float *m, float *omfika, float *xyz)
+{
+	double trX, trY;
+	if (m[0] > 0.0) omfika[1] = (float)asin((double)m[2]);
+	else omfika[1] = (float)(M_PI - asin((double)m[2]));
+	double C = cos((double)omfika[1]);
+	if (fabs(C) > 0.005) {
+		trX = m[10] / C;
+		trY = -m[6] / C;
+		omfika[0] = (float)atan2(trY, trX);
+		trX = m[0] / C;
+		trY = -m[1] / C;
+		omfika[2] = (float)atan2(trY, trX);
+	} else {
+		omfika[0] = 0.0f;
+		trX = m[5];
+		trY = m[4];
+		omfika[2] = (float)atan2(trY, trX);
+	}
+	xyz[0] = m[3];
+	xyz[1] = m[7];
+	xyz[2] = m[11];
+}
+
+void orc_euler_to_matrix(const float *omfika, const float *xyz, float *m)
+{
+	float hx = 0.5f * omfika[0], hy = 0.5f * omfika[1], hz = 0.5f * omfika[2];
+	float ax = sinf(hx), aw = cosf(hx);        /* qx = (aw; ax,0,0) */
+	float by = sinf(hy), bw = cosf(hy);        /* qy = (bw; 0,by,0) */
+	float cz = sinf(hz), cw = cosf(hz);        /* qz = (cw; 0,0,cz) */
+	/* q1 = qx*qy */
+	float w1 = aw * bw, x1 = ax * bw, y1 = aw * by, z1 = ax * by;
+	/* q = q1*qz */
+	float w = w1 * cw - z1 * cz;
+	float x = x1 * cw + y1 * cz;
+	float y = y1 * cw - x1 * cz;
+	float z = w1 * cz + z1 * cw;
+	float tx = 2.0f * x, ty = 2.0f * y, tz = 2.0f * z;
+	float twx = tx * w, twy = ty * w, twz = tz * w;
+	float txx = tx * x, txy = ty * x, txz = tz * x;
+	float tyy = ty * y, tyz = tz * y, tzz = tz * z;
+	m[0] = 1.0f - (tyy + tzz); m[1] = txy - twz;          m[2] = txz + twy;           m[3] = xyz[0];
+	m[4] = txy + twz;          m[5] = 1.0f - (txx + tzz); m[6] = tyz - twx;           m[7] = xyz[1];
+	m[8] = txz - twy;          m[9] = tyz + twx;          m[10] = 1.0f - (txx + tyy); m[11] = xyz[2];
+	m[12] = 0.0f; m[13] = 0.0f; m[14] = 0.0f; m[15] = 1.0f;
+}
+
+/* Rigid transform of xyz and normals.  Upstream the ICP loop does this on the CPU with Eigen
+ * (SL:635-663, rounding not reproducible without Eigen); the only transform whose arithmetic can be
+ * pinned is the reference's DEVICE kernel (L16:1341-1367), whose PTX is
+ *   v = fma(r02,z, fma(r00,x, r01*y)) + t     and the same without t for normals,
+ * so that is what is restated here (and what the product's transform kernel implements). */
+void orc_transform_cloud(const orc_point *in, orc_point *out, int n, const float *m)
+{
+#pragma omp parallel for schedule(static)
+	for (int i = 0; i < n; i++) {
+		orc_point p = in[i];
+		float x = p.x, y = p.y, z = p.z;
+		float nx = p.normal_x, ny = p.normal_y, nz = p.normal_z;
+		p.x = m[3] + fmaf(m[2], z, fmaf(m[0], x, m[1] * y));
+		p.y = m[7] + fmaf(m[6], z, fmaf(m[4], x, m[5] * y));
+		p.z = m[11] + fmaf(m[10], z, fmaf(m[8], x, m[9] * y));
+		p.normal_x = fmaf(m[2], nz, fmaf(m[0], nx, m[1] * ny));
+		p.normal_y = fmaf(m[6], nz, fmaf(m[4], nx, m[5] * ny));
+		p.normal_z = fmaf(m[10], nz, fmaf(m[8], nx, m[9] * ny));
+		out[i] = p;
+	}
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * One iteration of registerLastArrivedScan on pair (i=first, j=second) — SL:264-422.
+ *   SL:276-277  Euler round trip of the stored float pose, SL:279-280 transform of cloud i,
+ *   SL:313      semantic NN (grid on cloud i, queries = cloud j), SL:323-398 observations,
+ *   SL:402-413  if n_obs > threshold: registerLS / registerLS_4DOF, pose = EulerToMatrix(float(obs)).
+ * --------------------------------------------------------------------------------------------- */
+int orc_icp_iteration(const orc_point *first_local, int n_first, const orc_point *second_global, int n_second,
+		float *pose, const orc_reg_params *prm, orc_point *scratch_first, int32_t *nn_out,
+		int64_t *n_obs_out, double *x_out)
+{
+	float omfika[3], xyz[3], pose1[16];
+	orc_matrix4_to_euler(pose, omfika, xyz);
+	orc_euler_to_matrix(omfika, xyz, pose1);
+	orc_transform_cloud(first_local, scratch_first, n_first, pose1);
+
+	orc_grid_params gp;
+	orc_grid_params_compute(scratch_first, n_first, prm->bucket_size, prm->bucket_size, prm->bucket_size, prm->bbox_extension, &gp);
+	orc_hash_element *table = (orc_hash_element *)malloc((size_t)n_first * sizeof(*table));
+	orc_bucket *buckets = (orc_bucket *)malloc((size_t)gp.number_of_buckets * sizeof(*buckets));
+	int32_t *nn = nn_out ? nn_out : (int32_t *)malloc((size_t)n_second * sizeof(int32_t));
+	orc_obs_nn *obs = (orc_obs_nn *)malloc((size_t)(n_second > 0 ? n_second : 1) * sizeof(*obs));
+	orc_build_grid(scratch_first, n_first, &gp, buckets, table);
+	orc_nn_search(scratch_first, n_first, second_global, n_second, table, buckets, &gp,
+			prm->search_radius, prm->max_inner, prm->max_outer, nn);
+	int n_obs = orc_build_observations(scratch_first, first_local, second_global, n_second, nn, prm->weight, obs);
+	if (n_obs_out) *n_obs_out = n_obs;
+	int status = -4;
+	if (n_obs > prm->obs_threshold) {
+		double pose6[6] = {xyz[0], xyz[1], xyz[2], omfika[0], omfika[1], omfika[2]};
+		status = orc_register_ls(obs, n_obs, pose6, prm->dof, x_out);
+		if (status == 0) {
+			float of[3] = {(float)pose6[3], (float)pose6[4], (float)pose6[5]};
+			float tf[3] = {(float)pose6[0], (float)pose6[1], (float)pose6[2]};
+			orc_euler_to_matrix(of, tf, pose);
+		}
+	}
+	free(table); free(buckets); free(obs);
+	if (!nn_out) free(nn);
+	return status;
+}
+
+/* 28-double packing of a 6-DOF system: 21 upper-triangular AtPA entries row by row, 6 AtPl, count. */
+static void pack_neq(const double *N6, const double *b6, double count, double *out28)
+{
+	int k = 0;
+	for (int i = 0; i < 6; i++)
+		for (int j = i; j < 6; j++) out28[k++] = N6[i + j * 6];
+	for (int i = 0; i < 6; i++) out28[k++] = b6[i];
+	out28[k] = count;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * One Jacobi sweep of registerAll over all scans — SL:424-597 with number_of_last_EOZ = n_scans
+ * (the service path, SL:599-633).  Every i uses the OLD poses (SL:596); when the observation gate
+ * fails the pose is still replaced by its Euler round trip (SL:586-593).  The 4-DOF system is the
+ * {tx,ty,tz,ka} sub-system of the 6-DOF one, so neq_out always carries the 6-DOF equations.
+ * --------------------------------------------------------------------------------------------- */
+int orc_register_all_sweep(const orc_point *scans, const int64_t *off, int n_scans,
+		float *poses, const orc_reg_params *prm, float pair_thr, double *neq_out, int32_t *status_out)
+{
+	float *newp = (float *)malloc((size_t)n_scans * 16 * sizeof(float));
+	int64_t maxn = 0;
+	for (int i = 0; i < n_scans; i++) if (off[i + 1] - off[i] > maxn) maxn = off[i + 1] - off[i];
+	orc_point *pc1 = (orc_point *)malloc((size_t)maxn * sizeof(orc_point));
+	orc_point *pc2 = (orc_point *)malloc((size_t)maxn * sizeof(orc_point));
+	int32_t *nn = (int32_t *)malloc((size_t)maxn * sizeof(int32_t));
+	for (int i = 0; i < n_scans; i++) {
+		int n1 = (int)(off[i + 1] - off[i]);
+		float of1[3], t1[3], pose1[16];
+		orc_matrix4_to_euler(poses + 16 * i, of1, t1);
+		orc_euler_to_matrix(of1, t1, pose1);
+		orc_transform_cloud(scans + off[i], pc1, n1, pose1);
+		orc_grid_params gp;
+		orc_grid_params_compute(pc1, n1, prm->bucket_size, prm->bucket_size, prm->bucket_size, prm->bbox_extension, &gp);
+		orc_hash_element *table = (orc_hash_element *)malloc((size_t)n1 * sizeof(*table));
+		orc_bucket *buckets = (orc_bucket *)malloc((size_t)gp.number_of_buckets * sizeof(*buckets));
+		orc_build_grid(pc1, n1, &gp, buckets, table);   /* upstream rebuilds this per j (SL:478); same result */
+		size_t obs_cap = 1024, n_obs = 0;
+		orc_obs_nn *obs = (orc_obs_nn *)malloc(obs_cap * sizeof(*obs));
+		for (int j = 0; j < n_scans; j++) {
+			if (j == i) continue;
+			int n2 = (int)(off[j + 1] - off[j]);
+			float of2[3], t2[3], pose2[16];
+			orc_matrix4_to_euler(poses + 16 * j, of2, t2);
+			orc_euler_to_matrix(of2, t2, pose2);
+			float dist = sqrtf((t1[0] - t2[0]) * (t1[0] - t2[0]) + (t1[1] - t2[1]) * (t1[1] - t2[1]) + (t1[2] - t2[2]) * (t1[2] - t2[2]));
+			if (!(dist < pair_thr)) continue;                                     /* SL:469 */
+			orc_transform_cloud(scans + off[j], pc2, n2, pose2);
+			orc_nn_search(pc1, n1, pc2, n2, table, buckets, &gp, prm->search_radius, prm->max_inner, prm->max_outer, nn);
+			if (n_obs + (size_t)n2 > obs_cap) {
+				while (n_obs + (size_t)n2 > obs_cap) obs_cap *= 2;
+				obs = (orc_obs_nn *)realloc(obs, obs_cap * sizeof(*obs));
+			}
+			n_obs += (size_t)orc_build_observations(pc1, scans + off[i], pc2, n2, nn, prm->weight, obs + n_obs);
+		}
+		double pose6[6] = {t1[0], t1[1], t1[2], of1[0], of1[1], of1[2]};
+		if (neq_out) {
+			double N6[36], b6[6];
+			orc_normal_equations(obs, (int)n_obs, pose6, 6, N6, b6);
+			pack_neq(N6, b6, (double)n_obs, neq_out + 28 * (size_t)i);
+		}
+		int status = -4;
+		if ((int64_t)n_obs > prm->obs_threshold) status = orc_register_ls(obs, (int)n_obs, pose6, prm->dof, 0);
+		if (status_out) status_out[i] = status;
+		float of[3] = {(float)pose6[3], (float)pose6[4], (float)pose6[5]};
+		float tf[3] = {(float)pose6[0], (float)pose6[1], (float)pose6[2]};
+		orc_euler_to_matrix(of, tf, newp + 16 * i);                               /* SL:586-593 */
+		free(obs); free(table); free(buckets);
+	}
+	memcpy(poses, newp, (size_t)n_scans * 16 * sizeof(float));
+	free(newp); free(pc1); free(pc2); free(nn);
+	return 0;
+}
