@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py — points/s per ICP iteration of the device-resident registration hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|c3] [--mode icp|ndt]
+
+A "step" is one complete registration iteration over one scan pair: transform of the first scan by the current
+pose + bounding box, bucket keys, radix sort, bucket table, semantic NN over the 27 neighbouring buckets,
+normal-equation reduction, 6-DOF Cholesky solve and pose update — all on the device (m3dreg_icp_step).
+N=1 runs BASELINE config C2 (1M-point rotating-SICK pair, 1.0 m buckets).  N>1 (under torchrun, one rank per
+GPU) is the pair-sharded multi-scan case: every rank registers its own C2-sized pair and the 28-double normal
+equation blocks are all-reduced with NCCL every step (weak scaling).
+
+One JSON line is printed by rank 0; see the task contract for the keys.  `--impl reference` times the UNMODIFIED
+reference kernels (oracle/_ref, its own malloc/copy/sync pattern, cudaWrapper.cpp:344-424,516-581) plus the host
+glue the reference runs on the CPU each iteration; if that library is unavailable it times the CPU oracle port.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (generator kind, kwargs, bucket/radius, description)
+    "c1": ("hdl32", {}, 0.5, "C1 two-scan ICP, 65 536-point HDL-32E-like pair, 0.5 m grid"),
+    "c2": ("sick", {}, 1.0, "C2 two-scan registration, 1 048 576-point rotating-SICK pair, 1.0 m buckets"),
+    "c3": ("sick", {"n_beams": 2048, "n_profiles": 2048}, 0.25, "C3 dense 4 194 304-point pair, 0.25 m grid"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, n in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def alg_bytes(n1, n2, nb, nc):
+    """Algorithmic bytes per ICP iteration: B_alg = 104*N1 + 36*N2 + 24*B + 40*Nc."""
+    return 104 * n1 + 36 * n2 + 24 * nb + 40 * nc
+
+
+def nn_alg_bytes(n1, n2, nb):
+    """NN stage: table 8*N1 + first cloud 28*N1 + bucket table 12*B + queries 28*N2 + nn 4*N2."""
+    return 36 * n1 + 32 * n2 + 12 * nb
+
+
+def make_pair(pkg, workload, seed):
+    kind, kw, res, _ = WORKLOADS[workload]
+    first, second, pose_init, pose2, pose_true = pkg.synth.scan_pair(kind, seed=seed, **kw)
+    return first, second, pose_init, pose2, pose_true, res
+
+
+def cpu_baseline(first, second, pose_init, pose2, res, dof, budget_s=20.0, max_iters=4):
+    """The oracle port (CPU restatement) timed on this box's host cores on a bounded sample of the same workload."""
+    import oracle
+    prm = oracle.default_params(res, dof=dof)
+    sg = oracle.transform_cloud(second, oracle.euler_to_matrix(*oracle.matrix4_to_euler(pose2)))
+    pose = pose_init.copy()
+    t0 = time.perf_counter()
+    iters = 0
+    while iters < max_iters and (time.perf_counter() - t0) < budget_s:
+        _, pose, _, _, _ = oracle.icp_iteration(first, sg, pose, prm)
+        iters += 1
+    dt = time.perf_counter() - t0
+    pts = (len(first) + len(second)) * iters
+    return {"value": pts / dt, "unit": "points/s", "cores": oracle.lib().orc_num_threads(), "kind": "port",
+            "sample": f"{iters} full ICP iterations of the same pair (transform+grid+NN+obs+solve), {dt:.1f} s wall"}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own kernels driven the way cudaWrapper.cpp / gpu6DSLAM.cpp drive them."""
+    if rank != 0:
+        return
+    pkg = importlib.import_module("mandala-mapping_b200")
+    import oracle
+    first, second, pose_init, pose2, _, res = make_pair(pkg, args.workload, args.seed)
+    n_pts = len(first) + len(second)
+    dof = args.dof
+    use_ref = oracle.ref_available()
+    kind = "reference"
+    if use_ref:
+        try:
+            from tests import refwrap
+            if oracle.ref().ref_device_count() <= 0:
+                use_ref = False
+            else:
+                oracle.ref().ref_warm_up(0)
+        except Exception:
+            use_ref = False
+    if not use_ref:
+        kind = "port"
+    prm = oracle.default_params(res, dof=dof)
+    pose = pose_init.copy()
+    weights = (10.0, 1.0, 10.0, 10.0)
+
+    def step(pose):
+        # gpu6DSLAM.cpp:276-307: Euler round trips + CPU transform of BOTH clouds every iteration
+        o1, t1 = oracle.matrix4_to_euler(pose)
+        p1 = oracle.euler_to_matrix(o1, t1)
+        fg = oracle.transform_cloud(first, p1)
+        sg = oracle.transform_cloud(second, oracle.euler_to_matrix(*oracle.matrix4_to_euler(pose2)))
+        if use_ref:
+            nn, *_ = refwrap.nn_search_host(fg, sg, res, res, 1.0, 100, 100, export=False)     # cudaWrapper.cpp:344-424
+        else:
+            nn, *_ = oracle.semantic_nn(fg, sg, res, res, 1.0, 100, 100)
+        obs = oracle.build_observations(fg, first, sg, nn, weights)                              # gpu6DSLAM.cpp:323-398
+        pose6 = [t1[0], t1[1], t1[2], o1[0], o1[1], o1[2]]
+        if len(obs) > 100:
+            if use_ref:
+                st, p6, _ = refwrap.register_ls_host(obs, pose6, dof)                           # cudaWrapper.cpp:516-648
+            else:
+                st, p6, _ = oracle.register_ls(obs, pose6, dof)
+            if st == 0:
+                pose = oracle.euler_to_matrix(np.float32(p6[3:]), np.float32(p6[:3]))
+        return pose
+
+    # bounded: the CPU port needs seconds per step on 1M points
+    steps = args.steps if use_ref else min(args.steps, 3)
+    warm = args.warmup if use_ref else min(args.warmup, 1)
+    for _ in range(warm):
+        pose = step(pose)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pose = step(pose)
+    dt = time.perf_counter() - t0
+    value = n_pts * steps / dt
+    cores = oracle.lib().orc_num_threads()
+    line = {
+        "impl": "reference", "metric": "points/sec per ICP iteration", "value": value, "unit": "points/s", "n_gpus": 1,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 geometry / f64 normal equations", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][3], "mode": "icp", "dof": dof,
+                   "reference_path": ("verbatim reference CUDA kernels (lesson_16.cu, CCUDAAXBSolverWrapper.cpp compiled for sm_100a) through the "
+                                      "reference's per-call malloc/H2D/D2H/free pattern + its per-iteration CPU transform and observation assembly "
+                                      "(the reference has NO CPU implementation of this path)") if use_ref else
+                                     "CPU oracle port (reference kernels unavailable on this box)"},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": kind,
+                         "sample": f"{steps} full iterations of the same pair, host glue on {cores} threads"},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="icp", choices=["icp", "ndt"])
+    ap.add_argument("--dof", type=int, default=6, choices=[4, 6])
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("mandala-mapping_b200")
+    assert torch.cuda.is_available(), "bench.py needs a B200 (the product has no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    peak_gbs, peak_src = load_peaks()
+    first, second, pose_init, pose2, pose_true, res = make_pair(pkg, args.workload, args.seed + rank)
+    n1, n2 = len(first), len(second)
+    prm = pkg.default_params(res, dof=args.dof, mode=pkg.MODE_NDT if args.mode == "ndt" else pkg.MODE_ICP)
+
+    ctx = pkg.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.scan_upload(0, first)
+    ctx.scan_upload(1, second)
+    neq_all = torch.zeros(world * 28, dtype=torch.float64, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        ctx.icp_step(1)
+        if world > 1:
+            neq_all.zero_()
+            ctx.icp_copy_neq(neq_all[rank * 28:])
+            dist.all_reduce(neq_all)
+
+    # ---------------- device-resident timing: value ----------------
+    ctx.icp_begin(0, 1, pose_init, pose2, prm)
+    launches0 = ctx.launch_count
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches1 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        one_step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches1
+    clocks = sampler.stop() if rank == 0 else None
+    pose_out, st = ctx.icp_end()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = world * (n1 + n2) / (ms_per_step * 1e-3)
+    nb = int(st.n_buckets_last)
+    nc = int(st.n_obs_last)
+
+    # ---------------- per-stage event timing: roofline of the dominant kernel ----------------
+    ctx.icp_begin(0, 1, pose_out, pose2, prm)
+    ctx.set_profiling(True)
+    ctx.icp_step(min(args.steps, 10))
+    stage_ms, stage_iters = ctx.get_stage_ms()
+    ctx.set_profiling(False)
+    ctx.icp_end()
+    stage_ms = stage_ms / max(stage_iters, 1)
+    stage_names = ["transform+bounds", "grid (keys, radix sort, bucket table, gather)", "semantic NN (k_nn_search)", "normal equations + solve"]
+    dom = int(np.argmax(stage_ms))
+    nn_ms = float(stage_ms[2])
+    nn_bytes = nn_alg_bytes(n1, n2, nb)
+    nn_gbs = nn_bytes / (nn_ms * 1e-3) / 1e9
+    iter_bytes = alg_bytes(n1, n2, nb, nc)
+    iter_gbs = iter_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---------------- end-to-end through the host-buffer C ABI call (H2D/D2H inside the timed region) ----------------
+    h_first = torch.from_numpy(np.frombuffer(first.tobytes(), dtype=np.uint8).copy()).pin_memory()
+    # second cloud already in the global frame, as the reference hands it over (gpu6DSLAM.cpp:306-307)
+    d_tmp = torch.from_numpy(np.frombuffer(second.tobytes(), dtype=np.uint8).copy()).cuda()
+    d_out = torch.empty_like(d_tmp)
+    o2, t2 = pkg.matrix4_to_euler(pose2)
+    ctx.transform(d_tmp, d_out, n2, pkg.euler_to_matrix(o2, t2))
+    ctx.synchronize()
+    h_second = d_out.cpu().pin_memory()
+    del d_tmp, d_out
+    h_nn = torch.empty(n2, dtype=torch.int32).pin_memory()
+    pose_e2e = np.ascontiguousarray(pose_init, dtype=np.float32).reshape(16).copy()
+    e2e_steps = max(1, args.e2e_steps)
+    for _ in range(2):
+        _e2e_call(ctx, pkg, h_first, n1, h_second, n2, pose_e2e, prm, h_nn)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _e2e_call(ctx, pkg, h_first, n1, h_second, n2, pose_e2e, prm, h_nn)
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    te = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * (n1 + n2) * e2e_steps / float(te.item())
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            try:
+                cpu = cpu_baseline(first, second, pose_init, pose2, res, args.dof)
+            except Exception as ex:  # pragma: no cover
+                cpu = {"value": None, "unit": "points/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+        working_set = n1 * (32 * 3 + 16 + 16) + n2 * (32 + 32 + 4) + nb * 12
+        line = {
+            "metric": "points/sec per ICP iteration", "value": value, "unit": "points/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 geometry / f64 normal equations", "data": "synthetic",
+            "config": {
+                "workload": WORKLOADS[args.workload][3] + (f"; one pair per rank x {world} ranks, NCCL all-reduce of the 28-double normal-equation blocks per step" if world > 1 else ""),
+                "mode": args.mode, "dof": args.dof, "n_first": n1, "n_second": n2, "buckets": nb, "correspondences": nc,
+                "search_radius_m": res, "bucket_m": res, "max_inner": 100, "max_outer": 100,
+                "l2_policy": f"no flush: per-iteration working set {working_set / 1e6:.0f} MB " + ("exceeds" if working_set > 126e6 else "is below") + " the 126 MB L2",
+                "parallelism": f"pairs{world}",
+            },
+            "gpu_launches": int(launches),
+            "launches_per_step": launches / args.steps,
+            "clocks": clocks,
+            "roofline": {
+                "bound": "hbm", "kernel": "k_nn_search", "achieved": nn_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": nn_gbs / peak_gbs,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": nn_bytes, "launch_ms": nn_ms,
+                "dominant_stage": stage_names[dom],
+                "stage_ms": {stage_names[k]: float(stage_ms[k]) for k in range(4)},
+                "iteration": {"algorithmic_bytes": iter_bytes, "achieved": iter_gbs, "frac": iter_gbs / peak_gbs,
+                              "note": "whole iteration (all kernels) vs the HBM roofline, B_alg = 104*N1 + 36*N2 + 24*B + 40*Nc"},
+            },
+            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": 40 * (n1 + n2), "d2h_bytes_per_step": 4 * n2 + 64,
+                    "steps": e2e_steps, "call": "m3dreg_icp_iteration_host (both 40-B clouds H2D from pinned memory, nn + pose D2H, every step)"},
+            "cpu_baseline": cpu,
+            "result": {"status": int(st.last_status), "translation_error_m": float(np.abs(pose_out[:3, 3] - pose_true[:3, 3]).max())},
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _e2e_call(ctx, pkg, h_first, n1, h_second, n2, pose, prm, h_nn):
+    import ctypes as C
+    st = pkg.IcpStats()
+    rc = pkg.lib().m3dreg_icp_iteration_host(ctx._h, C.c_void_p(h_first.data_ptr()), C.c_int(n1), C.c_void_p(h_second.data_ptr()),
+                                             C.c_int(n2), pkg._p(pose), C.byref(prm), C.c_void_p(h_nn.data_ptr()), C.byref(st))
+    if rc != 0:
+        raise pkg.M3dRegError(rc, "m3dreg_icp_iteration_host")
+    return st
+
+
+if __name__ == "__main__":
+    main()

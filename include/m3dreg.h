@@ -145,7 +145,7 @@ int64_t m3dreg_launch_count(const m3dreg_ctx *ctx);
 
 /* ref: cudaCalculateGridParams (include/lesson_16.h:61-62, src/lesson_16.cu:23-106).
  * One fused min/max pass instead of 3 thrust::minmax_element + 6 D2H copies. out is HOST memory. */
-int m3dreg_grid_params(m3dreg_ctx *ctx, const m3dreg_point *d_cloud, int n,
+int m3dreg_calculate_grid_params(m3dreg_ctx *ctx, const m3dreg_point *d_cloud, int n,
 		float resolution_X, float resolution_Y, float resolution_Z,
 		float bounding_box_extension, m3dreg_grid_params *out);
 
@@ -153,7 +153,7 @@ int m3dreg_grid_params(m3dreg_ctx *ctx, const m3dreg_point *d_cloud, int n,
  * Fills d_table (n entries, sorted by bucket then original index) and the dense d_buckets
  * (params->number_of_buckets entries, empty = {-1,-1,0}) bit-identically to the reference,
  * including the first-element quirk of kernel_updateBuckets (src/lesson_16.cu:148-158). */
-int m3dreg_build_grid(m3dreg_ctx *ctx, const m3dreg_point *d_cloud, int n,
+int m3dreg_calculate_grid(m3dreg_ctx *ctx, const m3dreg_point *d_cloud, int n,
 		const m3dreg_grid_params *params, m3dreg_bucket *d_buckets, m3dreg_hash_element *d_table);
 
 /* ref: cudaSemanticNearestNeighborSearch (include/lesson_16.h:76-88, src/lesson_16.cu:531-738).
@@ -221,6 +221,26 @@ int m3dreg_scan_clear(m3dreg_ctx *ctx);
 int m3dreg_icp_pair(m3dreg_ctx *ctx, int first_slot, int second_slot,
 		float *pose_first, const float *pose_second,
 		const m3dreg_reg_params *params, int iterations, m3dreg_icp_stats *stats);
+
+/* The same loop in three steps, for callers that want to enqueue iterations without any host round trip in
+ * between (benchmarks, CUDA-graph style replays, multi-GPU drivers):
+ *   icp_begin   uploads the poses, transforms the queries once and sizes the bucket table (one stream sync);
+ *   icp_step    ENQUEUES `iterations` device-resident iterations on the context's stream and returns at once;
+ *   icp_end     reads pose + statistics back (synchronises).
+ * icp_copy_neq copies the last iteration's 28-double normal-equation block (21 upper-triangular AtPA, 6 AtPl,
+ * count) device-to-device into d_dst, asynchronously on the context's stream (for NCCL all-reduce). */
+int m3dreg_icp_begin(m3dreg_ctx *ctx, int first_slot, int second_slot, const float *pose_first,
+		const float *pose_second, const m3dreg_reg_params *params);
+int m3dreg_icp_step(m3dreg_ctx *ctx, int iterations);
+int m3dreg_icp_end(m3dreg_ctx *ctx, float *pose_first_out, m3dreg_icp_stats *stats);
+int m3dreg_icp_copy_neq(m3dreg_ctx *ctx, double *d_dst);
+
+/* Per-stage CUDA-event timing of the fused iteration (off by default).  Stages: 0 transform+bounds,
+ * 1 grid (params, keys, radix sort, bucket table, gather), 2 semantic NN, 3 normal equations + solve.
+ * get_stage_ms returns the accumulated milliseconds and launch counts since the last reset and resets them. */
+#define M3DREG_STAGE_COUNT 4
+int m3dreg_set_profiling(m3dreg_ctx *ctx, int enabled);
+int m3dreg_get_stage_ms(m3dreg_ctx *ctx, float *ms_out, int *iterations_out);
 
 /* Same iteration, but through HOST clouds every call the way the reference crosses the
  * boundary (both 40-B clouds H2D, nn + pose D2H): first is in its LOCAL frame, second already

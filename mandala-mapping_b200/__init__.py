@@ -1,0 +1,346 @@
+"""m3dreg-b200: B200-native registration hot path of gpu_6dslam behind the reference's CUDA-wrapper surface.
+
+This Python package is only the thin host-side binding used by the tests, ``bench.py`` and the multi-GPU
+driver: the product is ``libm3dreg.so`` (hand-written sm_100a kernels + the C ABI of ``include/m3dreg.h``).
+The package name contains a hyphen (it is mandated by the repository layout), so import it with::
+
+    import importlib
+    m3d = importlib.import_module("mandala-mapping_b200")
+
+There is NO CPU fallback: :func:`lib` raises if the CUDA library is missing, and ``m3dreg_create`` fails
+without an sm_100 device.  Nothing in here imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import synth
+from .synth import BUCKET_DTYPE, GRID_PARAMS_DTYPE, HASH_DTYPE, OBS_DTYPE, POINT_DTYPE  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libm3dreg.so")
+CSRC = os.path.join(_HERE, "csrc")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+# status codes (include/m3dreg.h)
+OK, E_INVALID_ARG, E_TOO_MANY_BUCKETS, E_NOT_SPD, E_TOO_FEW_OBS, E_BAD_SLOT, E_NO_DEVICE, E_SIZE_MISMATCH = 0, -1, -2, -3, -4, -5, -6, -7
+MODE_ICP, MODE_NDT = 0, 1
+
+#: every symbol include/m3dreg.h declares (checked by tests/test_cabi.py against the built library)
+EXPORTS = [
+    "m3dreg_version", "m3dreg_status_string", "m3dreg_create", "m3dreg_destroy", "m3dreg_warm_up",
+    "m3dreg_set_stream", "m3dreg_get_stream", "m3dreg_synchronize", "m3dreg_launch_count",
+    "m3dreg_calculate_grid_params", "m3dreg_calculate_grid", "m3dreg_nn_search", "m3dreg_transform",
+    "m3dreg_normal_equations", "m3dreg_solve_chol", "m3dreg_solve_observations",
+    "m3dreg_semantic_nn_host", "m3dreg_register_ls_host", "m3dreg_matrix4_to_euler", "m3dreg_euler_to_matrix",
+    "m3dreg_scan_upload", "m3dreg_scan_size", "m3dreg_scan_clear", "m3dreg_icp_pair", "m3dreg_icp_iteration_host",
+    "m3dreg_export_last_grid", "m3dreg_export_last_nn", "m3dreg_sweep_zero", "m3dreg_sweep_accumulate",
+    "m3dreg_sweep_solve", "m3dreg_icp_begin", "m3dreg_icp_step", "m3dreg_icp_end", "m3dreg_icp_copy_neq",
+    "m3dreg_set_profiling", "m3dreg_get_stage_ms",
+]
+
+
+class RegParams(C.Structure):
+    """m3dreg_reg_params (include/m3dreg.h) = hot-path subset of the reference's ROS params."""
+    _fields_ = [("search_radius", C.c_float), ("bucket_size", C.c_float), ("bbox_extension", C.c_float),
+                ("max_inner", C.c_int32), ("max_outer", C.c_int32), ("obs_threshold", C.c_int32),
+                ("weight", C.c_float * 4), ("dof", C.c_int32), ("mode", C.c_int32)]
+
+
+class IcpStats(C.Structure):
+    _fields_ = [("iterations_run", C.c_int32), ("last_status", C.c_int32), ("n_obs_last", C.c_int64),
+                ("n_buckets_last", C.c_int64), ("x_last", C.c_double * 6), ("device_ms", C.c_float)]
+
+
+def default_params(radius: float = 0.5, bucket: float | None = None, dof: int = 6, mode: int = MODE_ICP) -> RegParams:
+    """Reference defaults (gpu_6dslam/include/gpu6DSLAM.h:179-210)."""
+    p = RegParams()
+    p.search_radius = radius
+    p.bucket_size = radius if bucket is None else bucket
+    p.bbox_extension = 1.0
+    p.max_inner = 100
+    p.max_outer = 100
+    p.obs_threshold = 100
+    p.weight[:] = [10.0, 1.0, 10.0, 10.0]
+    p.dof = dof
+    p.mode = mode
+    return p
+
+
+def sources() -> list[str]:
+    return [os.path.join(CSRC, "m3dreg.cu")]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libm3dreg.so, in-tree (nvcc cross-compiles without a GPU)."""
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "m3dreg.h")]
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
+    if force or stale:
+        cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+        subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+class M3dRegError(RuntimeError):
+    def __init__(self, status: int, where: str):
+        self.status = status
+        try:
+            msg = lib().m3dreg_status_string(status).decode()
+        except Exception:  # pragma: no cover
+            msg = "?"
+        super().__init__(f"{where}: status {status} ({msg})")
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The CUDA library.  Fails loudly when it has not been built — there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the product has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.m3dreg_status_string.restype = C.c_char_p
+        L.m3dreg_get_stream.restype = C.c_void_p
+        L.m3dreg_launch_count.restype = C.c_int64
+        L.m3dreg_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        for name in EXPORTS:
+            getattr(L, name)
+        _lib = L
+    return _lib
+
+
+def _p(x):
+    """void* of a numpy array / torch tensor / raw int address / None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        if x.dtype.names and "normal_x" in x.dtype.names:
+            assert x.dtype.itemsize == 40, "point array lost its 40-byte layout (np.concatenate re-packs it)"
+        return C.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(int(x))
+
+
+def _check(st: int, where: str, allow=()):
+    if st != 0 and st not in allow:
+        raise M3dRegError(st, where)
+    return st
+
+
+class Context:
+    """Owns one m3dreg_ctx (one per device / per rank)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(lib().m3dreg_create(C.byref(self._h), int(device)), "m3dreg_create")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().m3dreg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- lifecycle -------------------------------------------------------------------------------------
+    def warm_up(self):
+        _check(lib().m3dreg_warm_up(self._h), "m3dreg_warm_up")
+
+    def set_stream(self, cuda_stream: int | None):
+        _check(lib().m3dreg_set_stream(self._h, C.c_void_p(cuda_stream or 0)), "m3dreg_set_stream")
+
+    def synchronize(self):
+        _check(lib().m3dreg_synchronize(self._h), "m3dreg_synchronize")
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().m3dreg_launch_count(self._h))
+
+    # -- stage level (device pointers: torch CUDA tensors or raw addresses) ------------------------------
+    def calculate_grid_params(self, d_cloud, n, rx, ry=None, rz=None, ext=1.0) -> np.ndarray:
+        ry = rx if ry is None else ry
+        rz = rx if rz is None else rz
+        out = np.zeros(1, dtype=GRID_PARAMS_DTYPE)
+        _check(lib().m3dreg_calculate_grid_params(self._h, _p(d_cloud), C.c_int(n), C.c_float(rx), C.c_float(ry),
+                                                  C.c_float(rz), C.c_float(ext), _p(out)), "m3dreg_calculate_grid_params")
+        return out
+
+    def calculate_grid(self, d_cloud, n, gp: np.ndarray, d_buckets, d_table):
+        _check(lib().m3dreg_calculate_grid(self._h, _p(d_cloud), C.c_int(n), _p(gp), _p(d_buckets), _p(d_table)),
+               "m3dreg_calculate_grid")
+
+    def nn_search(self, d_first, n1, d_second, n2, d_table, d_buckets, gp, radius, max_inner, max_outer, d_nn):
+        _check(lib().m3dreg_nn_search(self._h, _p(d_first), C.c_int(n1), _p(d_second), C.c_int(n2), _p(d_table),
+                                      _p(d_buckets), _p(gp), C.c_float(radius), C.c_int(max_inner), C.c_int(max_outer),
+                                      _p(d_nn)), "m3dreg_nn_search")
+
+    def transform(self, d_in, d_out, n, m3x4):
+        m = np.ascontiguousarray(m3x4, dtype=np.float32).reshape(-1)[:12].copy()
+        _check(lib().m3dreg_transform(self._h, _p(d_in), _p(d_out), C.c_int(n), _p(m)), "m3dreg_transform")
+
+    def normal_equations(self, d_obs, n_obs, pose6, dof=6):
+        p = np.asarray(pose6, dtype=np.float64).copy()
+        N = np.zeros(dof * dof)
+        b = np.zeros(dof)
+        _check(lib().m3dreg_normal_equations(self._h, _p(d_obs), C.c_int(n_obs), _p(p), C.c_int(dof), _p(N), _p(b)),
+               "m3dreg_normal_equations")
+        return N.reshape(dof, dof).T.copy(), b
+
+    def solve_chol(self, N, b):
+        dof = len(b)
+        A = np.ascontiguousarray(np.asarray(N, dtype=np.float64).T).reshape(-1)  # column-major buffer
+        bb = np.asarray(b, dtype=np.float64).copy()
+        x = np.zeros(dof)
+        st = lib().m3dreg_solve_chol(self._h, _p(A), _p(bb), C.c_int(dof), _p(x))
+        _check(st, "m3dreg_solve_chol", allow=(E_NOT_SPD,))
+        return st, x
+
+    def solve_observations(self, d_obs, n_obs, pose6, dof=6):
+        p = np.asarray(pose6, dtype=np.float64).copy()
+        x = np.zeros(dof)
+        st = lib().m3dreg_solve_observations(self._h, _p(d_obs), C.c_int(n_obs), _p(p), C.c_int(dof), _p(x))
+        _check(st, "m3dreg_solve_observations", allow=(E_NOT_SPD,))
+        return st, x
+
+    # -- CCudaWrapper level (host buffers) -----------------------------------------------------------------
+    def semantic_nn_host(self, first, second, radius, bucket, ext=1.0, max_inner=100, max_outer=100, nn_out=None):
+        nn = np.empty(len(second), dtype=np.int32) if nn_out is None else nn_out
+        _check(lib().m3dreg_semantic_nn_host(self._h, _p(first), C.c_int(len(first)), _p(second), C.c_int(len(second)),
+                                             C.c_float(radius), C.c_float(bucket), C.c_float(ext), C.c_int(max_inner),
+                                             C.c_int(max_outer), _p(nn)), "m3dreg_semantic_nn_host")
+        return nn
+
+    def register_ls_host(self, obs, pose6, dof=6):
+        p = np.asarray(pose6, dtype=np.float64).copy()
+        x = np.zeros(6)
+        st = lib().m3dreg_register_ls_host(self._h, _p(obs), C.c_int(len(obs)), _p(p), C.c_int(dof), _p(x))
+        _check(st, "m3dreg_register_ls_host", allow=(E_NOT_SPD,))
+        return st, p, x[:dof]
+
+    # -- scan store + fused loops ------------------------------------------------------------------------------
+    def scan_upload(self, slot: int, pts, n: int | None = None, on_device: bool = False):
+        n = len(pts) if n is None else n
+        _check(lib().m3dreg_scan_upload(self._h, C.c_int(slot), _p(pts), C.c_int(n), C.c_int(1 if on_device else 0)),
+               "m3dreg_scan_upload")
+
+    def scan_size(self, slot: int) -> int:
+        return int(lib().m3dreg_scan_size(self._h, C.c_int(slot)))
+
+    def scan_clear(self):
+        _check(lib().m3dreg_scan_clear(self._h), "m3dreg_scan_clear")
+
+    def icp_pair(self, first_slot, second_slot, pose_first, pose_second, params: RegParams, iterations: int):
+        pf = np.ascontiguousarray(pose_first, dtype=np.float32).reshape(16).copy()
+        ps = np.ascontiguousarray(pose_second, dtype=np.float32).reshape(16).copy()
+        st = IcpStats()
+        _check(lib().m3dreg_icp_pair(self._h, C.c_int(first_slot), C.c_int(second_slot), _p(pf), _p(ps), C.byref(params),
+                                     C.c_int(iterations), C.byref(st)), "m3dreg_icp_pair")
+        return pf.reshape(4, 4), st
+
+    def icp_begin(self, first_slot, second_slot, pose_first, pose_second, params: RegParams):
+        pf = np.ascontiguousarray(pose_first, dtype=np.float32).reshape(16).copy()
+        ps = np.ascontiguousarray(pose_second, dtype=np.float32).reshape(16).copy()
+        self._params = params   # keep alive
+        _check(lib().m3dreg_icp_begin(self._h, C.c_int(first_slot), C.c_int(second_slot), _p(pf), _p(ps), C.byref(params)),
+               "m3dreg_icp_begin")
+
+    def icp_step(self, iterations: int = 1):
+        _check(lib().m3dreg_icp_step(self._h, C.c_int(iterations)), "m3dreg_icp_step")
+
+    def icp_end(self):
+        pf = np.zeros(16, dtype=np.float32)
+        st = IcpStats()
+        _check(lib().m3dreg_icp_end(self._h, _p(pf), C.byref(st)), "m3dreg_icp_end")
+        return pf.reshape(4, 4), st
+
+    def icp_copy_neq(self, d_dst):
+        _check(lib().m3dreg_icp_copy_neq(self._h, _p(d_dst)), "m3dreg_icp_copy_neq")
+
+    def set_profiling(self, enabled: bool):
+        _check(lib().m3dreg_set_profiling(self._h, C.c_int(1 if enabled else 0)), "m3dreg_set_profiling")
+
+    def get_stage_ms(self):
+        ms = np.zeros(4, dtype=np.float32)
+        it = C.c_int(0)
+        _check(lib().m3dreg_get_stage_ms(self._h, _p(ms), C.byref(it)), "m3dreg_get_stage_ms")
+        return ms, int(it.value)
+
+    def icp_iteration_host(self, first_local, second_global, pose_first, params: RegParams, nn_out=None,
+                           pose_inout: np.ndarray | None = None):
+        pf = pose_inout if pose_inout is not None else np.ascontiguousarray(pose_first, dtype=np.float32).reshape(16).copy()
+        st = IcpStats()
+        _check(lib().m3dreg_icp_iteration_host(self._h, _p(first_local), C.c_int(len(first_local)), _p(second_global),
+                                               C.c_int(len(second_global)), _p(pf), C.byref(params), _p(nn_out),
+                                               C.byref(st)), "m3dreg_icp_iteration_host")
+        return pf.reshape(4, 4), st
+
+    def export_last_grid(self, n_first: int):
+        gp = np.zeros(1, dtype=GRID_PARAMS_DTYPE)
+        _check(lib().m3dreg_export_last_grid(self._h, _p(gp), None, C.c_int(0), None, C.c_int64(0)), "m3dreg_export_last_grid")
+        nb = int(gp["number_of_buckets"][0])
+        table = np.zeros(n_first, dtype=HASH_DTYPE)
+        buckets = np.zeros(nb, dtype=BUCKET_DTYPE)
+        _check(lib().m3dreg_export_last_grid(self._h, _p(gp), _p(table), C.c_int(n_first), _p(buckets), C.c_int64(nb)),
+               "m3dreg_export_last_grid")
+        return gp, table, buckets
+
+    def export_last_nn(self, n_second: int) -> np.ndarray:
+        nn = np.zeros(n_second, dtype=np.int32)
+        _check(lib().m3dreg_export_last_nn(self._h, _p(nn), C.c_int(n_second)), "m3dreg_export_last_nn")
+        return nn
+
+    # -- multi-scan sweep ----------------------------------------------------------------------------------------
+    def sweep_zero(self, d_neq, n_scans):
+        _check(lib().m3dreg_sweep_zero(self._h, _p(d_neq), C.c_int(n_scans)), "m3dreg_sweep_zero")
+
+    def sweep_accumulate(self, pair_i, pair_j, poses, params: RegParams, d_neq):
+        pi = np.ascontiguousarray(pair_i, dtype=np.int32)
+        pj = np.ascontiguousarray(pair_j, dtype=np.int32)
+        ps = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, 16)
+        _check(lib().m3dreg_sweep_accumulate(self._h, C.c_int(len(pi)), _p(pi), _p(pj), _p(ps), C.c_int(len(ps)),
+                                             C.byref(params), _p(d_neq)), "m3dreg_sweep_accumulate")
+
+    def sweep_solve(self, d_neq, poses, params: RegParams, begin=0, end=None):
+        ps = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, 16).copy()
+        n = len(ps)
+        end = n if end is None else end
+        status = np.zeros(n, dtype=np.int32)
+        _check(lib().m3dreg_sweep_solve(self._h, _p(d_neq), C.c_int(n), C.c_int(begin), C.c_int(end), _p(ps),
+                                        C.byref(params), _p(status)), "m3dreg_sweep_solve")
+        return ps.reshape(-1, 4, 4), status
+
+
+def matrix4_to_euler(m):
+    m = np.ascontiguousarray(m, dtype=np.float32).reshape(16)
+    o = np.zeros(3, dtype=np.float32)
+    t = np.zeros(3, dtype=np.float32)
+    lib().m3dreg_matrix4_to_euler(_p(m), _p(o), _p(t))
+    return o, t
+
+
+def euler_to_matrix(omfika, xyz):
+    o = np.ascontiguousarray(omfika, dtype=np.float32)
+    t = np.ascontiguousarray(xyz, dtype=np.float32)
+    m = np.zeros(16, dtype=np.float32)
+    lib().m3dreg_euler_to_matrix(_p(o), _p(t), _p(m))
+    return m.reshape(4, 4)
+
+
+from .wrapper import CCudaWrapper, Observations  # noqa: E402,F401

@@ -1,0 +1,984 @@
+/* m3dreg.cu — context, persistent arena and the C ABI (include/m3dreg.h) over the sm_100a kernels.
+ *
+ * Host-side structure mirrors the reference's L1 wrapper (src/cudaWrapper.cpp: CCudaWrapper) but
+ *   - device buffers live in a per-context arena that only grows (the reference cudaMalloc/cudaFree's 13+9+18
+ *     times per ICP iteration, cudaWrapper.cpp:360-420,523-572, CCUDAAXBSolverWrapper.cpp:407-539),
+ *   - everything is issued on one stream with no cudaDeviceSynchronize between kernels (45 in lesson_16.cu),
+ *   - the iteration state (pose, bounds, grid parameters, normal equations) stays on the device.
+ * There is no CPU fallback: without an sm_100 device m3dreg_create fails.
+ */
+#include <type_traits>
+#include <vector>
+#include <new>
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+
+#include "m3dreg_kernels.cuh"
+
+using namespace m3d;
+
+#define CK(expr)                                                      \
+	do {                                                              \
+		cudaError_t e__ = (expr);                                     \
+		if (e__ != cudaSuccess) return (int)e__;                      \
+	} while (0)
+
+namespace {
+
+struct Scan {
+	float4 *xyzl = nullptr;
+	float4 *nrm = nullptr;
+	int n = 0;
+	size_t cap = 0;
+};
+
+template <class T>
+struct DevBuf {
+	T *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t n)
+	{
+		if (n <= cap) return 0;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = n + n / 8 + 64;
+		cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+		if (e != cudaSuccess) return (int)e;
+		cap = want;
+		return 0;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostSmall {          /* pinned host mirror of the small device block */
+	PoseState ps;
+	uint32_t bounds[8];
+	m3dreg_grid_params gp;
+	int flags[FLAG_COUNT];
+	unsigned long long label_counts[4];
+	double scratch[64];
+	float mats[32];
+};
+
+} /* namespace */
+
+struct m3dreg_ctx {
+	int dev = 0;
+	int sm_count = 148;
+	cudaStream_t own_stream = nullptr;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	int64_t launches = 0;
+
+	std::vector<Scan> scans;
+
+	/* arena */
+	DevBuf<float4> g_xyzl, g_nrm, s_xyzl, s_nrm, q_xyzl, q_nrm, l_xyzl, l_nrm;
+	DevBuf<uint32_t> keys[2], vals[2], hist;
+	DevBuf<m3dreg_bucket> buckets;
+	DevBuf<int> nn;
+	DevBuf<m3dreg_point> aos_a, aos_b;
+	DevBuf<m3dreg_obs_nn> obs;
+	DevBuf<double> partials;
+	DevBuf<m3dreg_hash_element> table;
+	DevBuf<float> d_poses1;      /* sweep: round-tripped poses, 16 floats per scan */
+	DevBuf<double> d_pose6;      /* sweep: tx,ty,tz,om,fi,ka per scan             */
+
+	/* small device block */
+	PoseState *ps = nullptr;
+	uint32_t *bounds = nullptr;
+	m3dreg_grid_params *gp = nullptr;
+	int *flags = nullptr;
+	unsigned long long *label_counts = nullptr;
+	unsigned int *ticket = nullptr;
+	double *scratch = nullptr;   /* 64 doubles */
+	float *mats = nullptr;       /* 32 floats  */
+	HostSmall *h = nullptr;      /* pinned */
+
+	/* active fused loop (icp_begin .. icp_end) */
+	bool active = false;
+	const float4 *act_lx = nullptr, *act_ln = nullptr;
+	int act_n1 = 0, act_n2 = 0, act_sort_bits = 0;
+	m3dreg_reg_params act_prm;
+
+	/* per-stage profiling */
+	bool profiling = false;
+	cudaEvent_t pev[M3DREG_STAGE_COUNT + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+	float stage_ms[M3DREG_STAGE_COUNT] = {0, 0, 0, 0};
+	int stage_iters = 0;
+
+	/* what the last fused iteration left behind (export hooks) */
+	int last_n_first = 0, last_n_second = 0, last_sorted = 0;
+	bool last_valid = false;
+};
+
+namespace {
+
+inline int grid_for(const m3dreg_ctx *c, long long n, int threads, int per_sm = 8)
+{
+	long long b = (n + threads - 1) / threads;
+	long long cap = (long long)c->sm_count * per_sm;
+	if (b > cap) b = cap;
+	if (b < 1) b = 1;
+	return (int)b;
+}
+
+#define LAUNCH(ctx, kernel, grid, block, ...)                                  \
+	do {                                                                       \
+		kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);            \
+		(ctx)->launches++;                                                     \
+	} while (0)
+
+int bits_for(long long nb)
+{
+	int bits = 1;
+	while (bits < 31 && (1LL << bits) < nb) bits++;
+	return bits;
+}
+
+/* Host replica of the tail of cudaCalculateGridParams (lesson_16.cu:64-91).  volatile stores keep every
+ * operation a separately rounded IEEE float op whatever the host compiler's contraction setting. */
+int grid_params_from_bounds(const float mn[3], const float mx[3], float rx, float ry, float rz, float ext, m3dreg_grid_params *out)
+{
+	volatile float mxx = mx[0], mxy = mx[1], mxz = mx[2], mnx = mn[0], mny = mn[1], mnz = mn[2];
+	mxx = mxx + ext; mnx = mnx - ext;
+	mxy = mxy + ext; mny = mny - ext;
+	mxz = mxz + ext; mnz = mnz - ext;
+	volatile float dx = mxx - mnx, dy = mxy - mny, dz = mxz - mnz;
+	volatile float qx = dx / rx, qy = dy / ry, qz = dz / rz;
+	volatile float fx = qx + 1.0f, fy = qy + 1.0f, fz = qz + 1.0f;
+	int nbx = (int)fx, nby = (int)fy, nbz = (int)fz;
+	memset(out, 0, sizeof(*out));
+	out->bounding_box_min_X = mnx; out->bounding_box_min_Y = mny; out->bounding_box_min_Z = mnz;
+	out->bounding_box_max_X = mxx; out->bounding_box_max_Y = mxy; out->bounding_box_max_Z = mxz;
+	out->number_of_buckets_X = nbx; out->number_of_buckets_Y = nby; out->number_of_buckets_Z = nbz;
+	out->resolution_X = rx; out->resolution_Y = ry; out->resolution_Z = rz;
+	long long nb = (long long)nbx * nby * nbz;
+	out->number_of_buckets = nb;
+	if (nbx <= 0 || nby <= 0 || nbz <= 0 || nb > 2147483647LL) return M3DREG_E_TOO_MANY_BUCKETS;
+	return 0;
+}
+
+float o2f_host(uint32_t o)
+{
+	uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+	float f;
+	memcpy(&f, &u, 4);
+	return f;
+}
+
+int ensure_first(m3dreg_ctx *c, size_t n)
+{
+	int e;
+	if ((e = c->g_xyzl.ensure(n))) return e;
+	if ((e = c->g_nrm.ensure(n))) return e;
+	if ((e = c->s_xyzl.ensure(n))) return e;
+	if ((e = c->s_nrm.ensure(n))) return e;
+	for (int k = 0; k < 2; k++) {
+		if ((e = c->keys[k].ensure(n))) return e;
+		if ((e = c->vals[k].ensure(n))) return e;
+	}
+	size_t tiles = (n + 1023) / 1024 + 1;
+	if ((e = c->hist.ensure(tiles * kRadixSize))) return e;
+	return 0;
+}
+
+int ensure_second(m3dreg_ctx *c, size_t n)
+{
+	int e;
+	if ((e = c->q_xyzl.ensure(n))) return e;
+	if ((e = c->q_nrm.ensure(n))) return e;
+	if ((e = c->nn.ensure(n))) return e;
+	return 0;
+}
+
+int ensure_partials(m3dreg_ctx *c)
+{
+	return c->partials.ensure((size_t)c->sm_count * 8 * kMomentCount);
+}
+
+/* stable LSD radix sort of (keys[0], vals[0]) by the low `bits` bits; returns the index (0/1) of the buffers
+ * holding the result.  gp (device, may be null) lets every pass no-op when the grid was rejected on the device. */
+int sort_by_bucket(m3dreg_ctx *c, int n, int bits, const m3dreg_grid_params *gp)
+{
+	int passes = (bits + kRadixBits - 1) / kRadixBits;
+	if (passes < 1) passes = 1;
+	int cur = 0;
+	bool big = n >= (1 << 19);
+	int items = big ? 16 : 4;
+	int tiles = (n + kSortThreads * items - 1) / (kSortThreads * items);
+	for (int p = 0; p < passes; p++) {
+		int shift = p * kRadixBits;
+		if (big) LAUNCH(c, k_radix_hist<16>, tiles, kSortThreads, c->keys[cur].p, n, shift, tiles, c->hist.p, gp);
+		else LAUNCH(c, k_radix_hist<4>, tiles, kSortThreads, c->keys[cur].p, n, shift, tiles, c->hist.p, gp);
+		LAUNCH(c, k_radix_scan, 1, 1024, c->hist.p, tiles * kRadixSize, gp);
+		if (big) LAUNCH(c, k_radix_scatter<16>, tiles, kSortThreads, c->keys[cur].p, c->vals[cur].p, c->keys[cur ^ 1].p, c->vals[cur ^ 1].p, n, shift, tiles, c->hist.p, gp);
+		else LAUNCH(c, k_radix_scatter<4>, tiles, kSortThreads, c->keys[cur].p, c->vals[cur].p, c->keys[cur ^ 1].p, c->vals[cur ^ 1].p, n, shift, tiles, c->hist.p, gp);
+		cur ^= 1;
+	}
+	return cur;
+}
+
+void host_roundtrip_pose(const float *m, float *pose1, double *pose6)
+{
+	float of[3], t[3];
+	matrix4_to_euler(m, of, t);
+	euler_to_matrix(of, t, pose1);
+	if (pose6) {
+		pose6[0] = t[0]; pose6[1] = t[1]; pose6[2] = t[2];
+		pose6[3] = of[0]; pose6[4] = of[1]; pose6[5] = of[2];
+	}
+}
+
+/* Grid of the (already transformed) first cloud in g_*: params (device) from bounds, keys, sort, dense table,
+ * sorted SoA copy.  bounds must already hold the reduced box. */
+void build_grid_fused(m3dreg_ctx *c, int n1, const m3dreg_reg_params *prm, int sort_bits)
+{
+	LAUNCH(c, k_grid_params, 1, 32, c->bounds, prm->bucket_size, prm->bucket_size, prm->bucket_size, prm->bbox_extension,
+			(long long)c->buckets.cap, c->gp, c->flags);
+	LAUNCH(c, k_keys_soa, grid_for(c, n1, 256), 256, c->g_xyzl.p, n1, c->gp, c->keys[0].p, c->vals[0].p);
+	int cur = sort_by_bucket(c, n1, sort_bits, c->gp);
+	LAUNCH(c, k_init_buckets, grid_for(c, (long long)c->buckets.cap * 3, 256), 256, c->buckets.p, c->gp, 0LL);
+	LAUNCH(c, k_finalize_grid, grid_for(c, n1, 256), 256, c->keys[cur].p, c->vals[cur].p, n1, c->gp, c->buckets.p,
+			c->g_xyzl.p, c->g_nrm.p, c->s_xyzl.p, c->s_nrm.p, (m3dreg_hash_element *)nullptr);
+	c->last_sorted = cur;
+}
+
+/* Reads the reduced bounds back (one sync), sizes the dense bucket table with a margin so the box may drift
+ * while the pose converges, and returns the radix bit count for that capacity. */
+int plan_buckets(m3dreg_ctx *c, const m3dreg_reg_params *prm, int *sort_bits)
+{
+	CK(cudaMemcpyAsync(c->h->bounds, c->bounds, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	float mn[3], mx[3];
+	for (int k = 0; k < 3; k++) { mn[k] = o2f_host(c->h->bounds[k]); mx[k] = o2f_host(c->h->bounds[3 + k]); }
+	m3dreg_grid_params gp;
+	int st = grid_params_from_bounds(mn, mx, prm->bucket_size, prm->bucket_size, prm->bucket_size, prm->bbox_extension, &gp);
+	if (st) return st;
+	long long cap = (long long)(gp.number_of_buckets_X + 4) * (gp.number_of_buckets_Y + 4) * (gp.number_of_buckets_Z + 4);
+	if (cap > 2147483647LL) cap = 2147483647LL;
+	if (gp.number_of_buckets > cap) return M3DREG_E_TOO_MANY_BUCKETS;
+	int e = c->buckets.ensure((size_t)cap);
+	if (e) return e;
+	*sort_bits = bits_for((long long)c->buckets.cap);
+	return 0;
+}
+
+int check_flags(m3dreg_ctx *c)
+{
+	CK(cudaMemcpyAsync(c->h->flags, c->flags, sizeof(int) * FLAG_COUNT, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	int f = c->h->flags[FLAG_ERROR];
+	if (f) {
+		CK(cudaMemsetAsync(c->flags, 0, sizeof(int) * FLAG_COUNT, c->stream));
+	}
+	return f;
+}
+
+bool valid_params(const m3dreg_reg_params *p)
+{
+	if (!p) return false;
+	if (!(p->bucket_size > 0.0f) || !(p->search_radius >= 0.0f)) return false;
+	if (p->dof != 6 && p->dof != 4) return false;
+	if (p->mode != M3DREG_MODE_ICP && p->mode != M3DREG_MODE_NDT) return false;
+	return true;
+}
+
+/* One registerLastArrivedScan iteration, fully on the device.  first local cloud = (lx, ln), queries already in q_*. */
+void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, int n2,
+		const m3dreg_reg_params *prm, int sort_bits)
+{
+	const bool prof = c->profiling;
+	if (prof) cudaEventRecord(c->pev[0], c->stream);
+	LAUNCH(c, k_transform_soa<true>, grid_for(c, n1, 256), 256, lx, ln, n1, c->ps->pose1, c->g_xyzl.p, c->g_nrm.p, c->bounds);
+	if (prof) cudaEventRecord(c->pev[1], c->stream);
+	build_grid_fused(c, n1, prm, sort_bits);
+	if (prof) cudaEventRecord(c->pev[2], c->stream);
+	LAUNCH(c, k_nn_search, (n2 + 255) / 256, 256, c->q_xyzl.p, c->q_nrm.p, n2, c->s_xyzl.p, c->s_nrm.p,
+			c->vals[c->last_sorted].p, n1, c->buckets.p, c->gp, prm->search_radius, prm->max_inner, prm->max_outer, 1,
+			c->nn.p, c->label_counts);
+	ObsFromNN src;
+	src.nn = c->nn.p; src.q_xyzl = c->q_xyzl.p; src.g_xyzl = c->g_xyzl.p; src.l_xyzl = lx; src.label_counts = c->label_counts;
+	for (int k = 0; k < 4; k++) src.weight[k] = prm->weight[k];
+	FinalizeArgs fin;
+	fin.ps = c->ps; fin.neq_out = nullptr; fin.accumulate = 0; fin.solve = 1; fin.dof = prm->dof;
+	fin.obs_threshold = prm->obs_threshold; fin.pose6_in = nullptr; fin.bounds_reset = c->bounds;
+	fin.label_counts_reset = c->label_counts;
+	if (prof) cudaEventRecord(c->pev[3], c->stream);
+	LAUNCH(c, k_normal_equations<ObsFromNN>, grid_for(c, n2, kNeqThreads, 4), kNeqThreads, src, n2, c->partials.p, c->ticket, fin);
+	if (prof) {
+		cudaEventRecord(c->pev[4], c->stream);
+		cudaEventSynchronize(c->pev[4]);
+		for (int k = 0; k < M3DREG_STAGE_COUNT; k++) {
+			float ms = 0.0f;
+			cudaEventElapsedTime(&ms, c->pev[k], c->pev[k + 1]);
+			c->stage_ms[k] += ms;
+		}
+		c->stage_iters++;
+	}
+	c->last_n_first = n1; c->last_n_second = n2; c->last_valid = true;
+}
+
+void fill_stats(m3dreg_ctx *c, m3dreg_icp_stats *stats, float ms)
+{
+	if (!stats) return;
+	const PoseState &ps = c->h->ps;
+	stats->iterations_run = ps.iterations;
+	stats->last_status = ps.status;
+	stats->n_obs_last = ps.n_obs;
+	stats->n_buckets_last = c->h->gp.number_of_buckets;
+	for (int k = 0; k < 6; k++) stats->x_last[k] = ps.x[k];
+	stats->device_ms = ms;
+}
+
+} /* namespace */
+
+extern "C" {
+
+int m3dreg_version(void) { return M3DREG_VERSION; }
+
+const char *m3dreg_status_string(int status)
+{
+	switch (status) {
+	case M3DREG_OK: return "ok";
+	case M3DREG_E_INVALID_ARG: return "invalid argument";
+	case M3DREG_E_TOO_MANY_BUCKETS: return "bucket count exceeds int32 / planned capacity";
+	case M3DREG_E_NOT_SPD: return "normal equations not positive definite";
+	case M3DREG_E_TOO_FEW_OBS: return "too few observations";
+	case M3DREG_E_BAD_SLOT: return "bad scan slot";
+	case M3DREG_E_NO_DEVICE: return "no sm_100 CUDA device";
+	case M3DREG_E_SIZE_MISMATCH: return "size mismatch";
+	default: break;
+	}
+	if (status > 0) return cudaGetErrorString((cudaError_t)status);
+	return "unknown status";
+}
+
+int m3dreg_create(m3dreg_ctx **out, int cuda_device)
+{
+	if (!out) return M3DREG_E_INVALID_ARG;
+	*out = nullptr;
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { cudaGetLastError(); return M3DREG_E_NO_DEVICE; }
+	if (cuda_device < 0 || cuda_device >= count) return M3DREG_E_NO_DEVICE;
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, cuda_device));
+	if (prop.major != 10) return M3DREG_E_NO_DEVICE;     /* the fatbin only carries sm_100a SASS */
+	CK(cudaSetDevice(cuda_device));
+	m3dreg_ctx *c = new (std::nothrow) m3dreg_ctx();
+	if (!c) return (int)cudaErrorMemoryAllocation;
+	c->dev = cuda_device;
+	c->sm_count = prop.multiProcessorCount;
+	cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+	if (e != cudaSuccess) { delete c; return (int)e; }
+	c->stream = c->own_stream;
+	cudaEventCreate(&c->ev0);
+	cudaEventCreate(&c->ev1);
+	size_t small = sizeof(PoseState) + 8 * sizeof(uint32_t) + sizeof(m3dreg_grid_params) + FLAG_COUNT * sizeof(int) +
+			4 * sizeof(unsigned long long) + 16 + 64 * sizeof(double) + 32 * sizeof(float) + 256;
+	char *blk = nullptr;
+	e = cudaMalloc((void **)&blk, small);
+	if (e != cudaSuccess) { m3dreg_destroy(c); return (int)e; }
+	cudaMemset(blk, 0, small);
+	size_t off = 0;
+	auto take = [&](size_t bytes) { char *p = blk + off; off += (bytes + 15) & ~(size_t)15; return p; };
+	c->ps = (PoseState *)take(sizeof(PoseState));
+	c->gp = (m3dreg_grid_params *)take(sizeof(m3dreg_grid_params));
+	c->scratch = (double *)take(64 * sizeof(double));
+	c->label_counts = (unsigned long long *)take(4 * sizeof(unsigned long long));
+	c->bounds = (uint32_t *)take(8 * sizeof(uint32_t));
+	c->flags = (int *)take(FLAG_COUNT * sizeof(int));
+	c->ticket = (unsigned int *)take(16);
+	c->mats = (float *)take(32 * sizeof(float));
+	e = cudaMallocHost((void **)&c->h, sizeof(HostSmall));
+	if (e != cudaSuccess) { m3dreg_destroy(c); return (int)e; }
+	memset(c->h, 0, sizeof(HostSmall));
+	int rc = ensure_partials(c);
+	if (rc) { m3dreg_destroy(c); return rc; }
+	*out = c;
+	return M3DREG_OK;
+}
+
+void m3dreg_destroy(m3dreg_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->dev);
+	if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+	for (auto &s : c->scans) { if (s.xyzl) cudaFree(s.xyzl); if (s.nrm) cudaFree(s.nrm); }
+	c->g_xyzl.release(); c->g_nrm.release(); c->s_xyzl.release(); c->s_nrm.release();
+	c->q_xyzl.release(); c->q_nrm.release(); c->l_xyzl.release(); c->l_nrm.release();
+	for (int k = 0; k < 2; k++) { c->keys[k].release(); c->vals[k].release(); }
+	c->hist.release(); c->buckets.release(); c->nn.release(); c->aos_a.release(); c->aos_b.release();
+	c->obs.release(); c->partials.release(); c->table.release(); c->d_poses1.release(); c->d_pose6.release();
+	if (c->ps) cudaFree(c->ps);   /* base of the small block */
+	if (c->h) cudaFreeHost(c->h);
+	for (int k = 0; k <= M3DREG_STAGE_COUNT; k++) if (c->pev[k]) cudaEventDestroy(c->pev[k]);
+	if (c->ev0) cudaEventDestroy(c->ev0);
+	if (c->ev1) cudaEventDestroy(c->ev1);
+	if (c->own_stream) cudaStreamDestroy(c->own_stream);
+	delete c;
+}
+
+int m3dreg_warm_up(m3dreg_ctx *c)
+{
+	if (!c) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
+	CK(cudaStreamSynchronize(c->stream));
+	return (int)cudaGetLastError();
+}
+
+int m3dreg_set_stream(m3dreg_ctx *c, void *s)
+{
+	if (!c) return M3DREG_E_INVALID_ARG;
+	CK(cudaStreamSynchronize(c->stream));
+	c->stream = s ? (cudaStream_t)s : c->own_stream;
+	return 0;
+}
+
+void *m3dreg_get_stream(m3dreg_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int m3dreg_synchronize(m3dreg_ctx *c)
+{
+	if (!c) return M3DREG_E_INVALID_ARG;
+	CK(cudaStreamSynchronize(c->stream));
+	return (int)cudaGetLastError();
+}
+
+int64_t m3dreg_launch_count(const m3dreg_ctx *c) { return c ? c->launches : 0; }
+
+/* ---- stage-level entry points ------------------------------------------------------------------------ */
+
+int m3dreg_calculate_grid_params(m3dreg_ctx *c, const m3dreg_point *d_cloud, int n, float rx, float ry, float rz, float ext,
+		m3dreg_grid_params *out)
+{
+	if (!c || !d_cloud || n <= 0 || !out || !(rx > 0) || !(ry > 0) || !(rz > 0)) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
+	LAUNCH(c, k_bounds_aos, grid_for(c, n, 256), 256, d_cloud, n, c->bounds);
+	CK(cudaMemcpyAsync(c->h->bounds, c->bounds, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	float mn[3], mx[3];
+	for (int k = 0; k < 3; k++) { mn[k] = o2f_host(c->h->bounds[k]); mx[k] = o2f_host(c->h->bounds[3 + k]); }
+	return grid_params_from_bounds(mn, mx, rx, ry, rz, ext, out);
+}
+
+int m3dreg_calculate_grid(m3dreg_ctx *c, const m3dreg_point *d_cloud, int n, const m3dreg_grid_params *params,
+		m3dreg_bucket *d_buckets, m3dreg_hash_element *d_table)
+{
+	if (!c || !d_cloud || n <= 0 || !params || !d_buckets || !d_table) return M3DREG_E_INVALID_ARG;
+	if (params->number_of_buckets <= 0 || params->number_of_buckets > 2147483647LL) return M3DREG_E_TOO_MANY_BUCKETS;
+	CK(cudaSetDevice(c->dev));
+	int e = ensure_first(c, (size_t)n);
+	if (e) return e;
+	c->h->gp = *params;
+	CK(cudaMemcpyAsync(c->gp, &c->h->gp, sizeof(m3dreg_grid_params), cudaMemcpyHostToDevice, c->stream));
+	LAUNCH(c, k_keys_aos, grid_for(c, n, 256), 256, d_cloud, n, c->gp, c->keys[0].p, c->vals[0].p);
+	int cur = sort_by_bucket(c, n, bits_for(params->number_of_buckets), nullptr);
+	LAUNCH(c, k_init_buckets, grid_for(c, params->number_of_buckets * 3, 256), 256, d_buckets, (const m3dreg_grid_params *)nullptr,
+			(long long)params->number_of_buckets);
+	LAUNCH(c, k_finalize_grid, grid_for(c, n, 256), 256, c->keys[cur].p, c->vals[cur].p, n, (const m3dreg_grid_params *)nullptr, d_buckets,
+			(const float4 *)nullptr, (const float4 *)nullptr, (float4 *)nullptr, (float4 *)nullptr, d_table);
+	c->last_valid = false;
+	CK(cudaStreamSynchronize(c->stream));   /* c->h->gp is reused by the next call */
+	return (int)cudaGetLastError();
+}
+
+int m3dreg_nn_search(m3dreg_ctx *c, const m3dreg_point *d_first, int n1, const m3dreg_point *d_second, int n2,
+		const m3dreg_hash_element *d_table, const m3dreg_bucket *d_buckets, const m3dreg_grid_params *params,
+		float search_radius, int max_inner, int max_outer, int *d_nn)
+{
+	if (!c || !d_first || !d_second || n1 <= 0 || n2 <= 0 || !d_table || !d_buckets || !params || !d_nn) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	int e = ensure_first(c, (size_t)n1);
+	if (e) return e;
+	if ((e = ensure_second(c, (size_t)n2))) return e;
+	c->h->gp = *params;
+	CK(cudaMemcpyAsync(c->gp, &c->h->gp, sizeof(m3dreg_grid_params), cudaMemcpyHostToDevice, c->stream));
+	LAUNCH(c, k_unpack_points, (n1 + 255) / 256, 256, d_first, n1, c->g_xyzl.p, c->g_nrm.p);
+	LAUNCH(c, k_unpack_points, (n2 + 255) / 256, 256, d_second, n2, c->q_xyzl.p, c->q_nrm.p);
+	LAUNCH(c, k_gather_by_table, grid_for(c, n1, 256), 256, d_table, n1, c->g_xyzl.p, c->g_nrm.p, c->s_xyzl.p, c->s_nrm.p, c->vals[0].p);
+	LAUNCH(c, k_nn_search, (n2 + 255) / 256, 256, c->q_xyzl.p, c->q_nrm.p, n2, c->s_xyzl.p, c->s_nrm.p, c->vals[0].p, n1,
+			d_buckets, c->gp, search_radius, max_inner, max_outer, 1, d_nn, (unsigned long long *)nullptr);
+	c->last_valid = false;
+	CK(cudaStreamSynchronize(c->stream));
+	return (int)cudaGetLastError();
+}
+
+int m3dreg_transform(m3dreg_ctx *c, const m3dreg_point *d_in, m3dreg_point *d_out, int n, const float *m)
+{
+	if (!c || !d_in || !d_out || n <= 0 || !m) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	LAUNCH(c, k_transform_aos, (n + 255) / 256, 256, d_in, d_out, n, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11]);
+	return (int)cudaGetLastError();
+}
+
+static int normal_equations_device(m3dreg_ctx *c, const m3dreg_obs_nn *d_obs, int n_obs, const double *pose6)
+{
+	/* result: packed 28 doubles in c->scratch[8..36); pose6 staged in c->scratch[0..6) */
+	memcpy(c->h->scratch, pose6, 6 * sizeof(double));
+	CK(cudaMemcpyAsync(c->scratch, c->h->scratch, 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	ObsFromList src;
+	src.obs = d_obs;
+	FinalizeArgs fin;
+	fin.ps = nullptr; fin.neq_out = c->scratch + 8; fin.accumulate = 0; fin.solve = 0; fin.dof = 6; fin.obs_threshold = 0;
+	fin.pose6_in = c->scratch; fin.bounds_reset = nullptr; fin.label_counts_reset = nullptr;
+	LAUNCH(c, k_normal_equations<ObsFromList>, grid_for(c, n_obs, kNeqThreads, 4), kNeqThreads, src, n_obs, c->partials.p, c->ticket, fin);
+	return 0;
+}
+
+static void unpack_neq(const double *neq, int dof, double *AtPA, double *AtPl)
+{
+	const int sel6[6] = {0, 1, 2, 3, 4, 5}, sel4[4] = {0, 1, 2, 5};
+	const int *sel = dof == 6 ? sel6 : sel4;
+	double full[6][6];
+	int k = 0;
+	for (int i = 0; i < 6; i++)
+		for (int j = i; j < 6; j++) { full[i][j] = neq[k]; full[j][i] = neq[k]; k++; }
+	for (int i = 0; i < dof; i++) {
+		if (AtPl) AtPl[i] = neq[21 + sel[i]];
+		if (AtPA) for (int j = 0; j < dof; j++) AtPA[i + j * dof] = full[sel[i]][sel[j]];
+	}
+}
+
+int m3dreg_normal_equations(m3dreg_ctx *c, const m3dreg_obs_nn *d_obs, int n_obs, const double *pose6, int dof,
+		double *AtPA_out, double *AtPl_out)
+{
+	if (!c || !d_obs || n_obs <= 0 || !pose6 || (dof != 6 && dof != 4)) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	int e = normal_equations_device(c, d_obs, n_obs, pose6);
+	if (e) return e;
+	CK(cudaMemcpyAsync(c->h->scratch + 8, c->scratch + 8, kNeqCount * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	unpack_neq(c->h->scratch + 8, dof, AtPA_out, AtPl_out);
+	return (int)cudaGetLastError();
+}
+
+int m3dreg_solve_chol(m3dreg_ctx *c, const double *AtPA, const double *AtPl, int dof, double *x_out)
+{
+	if (!c || !AtPA || !AtPl || !x_out || (dof != 6 && dof != 4)) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	memcpy(c->h->scratch, AtPA, sizeof(double) * dof * dof);
+	memcpy(c->h->scratch + 36, AtPl, sizeof(double) * dof);
+	CK(cudaMemcpyAsync(c->scratch, c->h->scratch, 42 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	LAUNCH(c, k_solve_dense, 1, 32, c->scratch, c->scratch + 36, dof, c->scratch + 48, c->flags + 1);
+	CK(cudaMemcpyAsync(c->h->scratch + 48, c->scratch + 48, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(c->h->flags, c->flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	memcpy(x_out, c->h->scratch + 48, sizeof(double) * dof);
+	return c->h->flags[1];
+}
+
+int m3dreg_solve_observations(m3dreg_ctx *c, const m3dreg_obs_nn *d_obs, int n_obs, const double *pose6, int dof, double *x_out)
+{
+	if (!c || !d_obs || n_obs <= 0 || !pose6 || !x_out || (dof != 6 && dof != 4)) return M3DREG_E_INVALID_ARG;
+	double N[36], b[6];
+	int e = m3dreg_normal_equations(c, d_obs, n_obs, pose6, dof, N, b);
+	if (e) return e;
+	return m3dreg_solve_chol(c, N, b, dof, x_out);
+}
+
+/* ---- CCudaWrapper-level entry points on host buffers --------------------------------------------------- */
+
+int m3dreg_semantic_nn_host(m3dreg_ctx *c, const m3dreg_point *first, int n1, const m3dreg_point *second, int n2,
+		float search_radius, float bucket_size, float ext, int max_inner, int max_outer, int *nn_out)
+{
+	if (!c || !first || !second || n1 <= 0 || n2 <= 0 || !nn_out || !(bucket_size > 0)) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	int e;
+	if ((e = c->aos_a.ensure((size_t)n1))) return e;
+	if ((e = c->aos_b.ensure((size_t)n2))) return e;
+	if ((e = ensure_first(c, (size_t)n1))) return e;
+	if ((e = ensure_second(c, (size_t)n2))) return e;
+	CK(cudaMemcpyAsync(c->aos_a.p, first, (size_t)n1 * sizeof(m3dreg_point), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->aos_b.p, second, (size_t)n2 * sizeof(m3dreg_point), cudaMemcpyHostToDevice, c->stream));
+	LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
+	LAUNCH(c, k_bounds_aos, grid_for(c, n1, 256), 256, c->aos_a.p, n1, c->bounds);
+	LAUNCH(c, k_unpack_points, (n1 + 255) / 256, 256, c->aos_a.p, n1, c->g_xyzl.p, c->g_nrm.p);
+	LAUNCH(c, k_unpack_points, (n2 + 255) / 256, 256, c->aos_b.p, n2, c->q_xyzl.p, c->q_nrm.p);
+	m3dreg_reg_params prm;
+	memset(&prm, 0, sizeof(prm));
+	prm.bucket_size = bucket_size; prm.bbox_extension = ext; prm.search_radius = search_radius;
+	int sort_bits = 0;
+	if ((e = plan_buckets(c, &prm, &sort_bits))) return e;
+	build_grid_fused(c, n1, &prm, sort_bits);
+	LAUNCH(c, k_nn_search, (n2 + 255) / 256, 256, c->q_xyzl.p, c->q_nrm.p, n2, c->s_xyzl.p, c->s_nrm.p,
+			c->vals[c->last_sorted].p, n1, c->buckets.p, c->gp, search_radius, max_inner, max_outer, 1,
+			c->nn.p, (unsigned long long *)nullptr);
+	CK(cudaMemcpyAsync(nn_out, c->nn.p, (size_t)n2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	c->last_n_first = n1; c->last_n_second = n2; c->last_valid = true;
+	int f = check_flags(c);
+	if (f) return f;
+	return (int)cudaGetLastError();
+}
+
+int m3dreg_register_ls_host(m3dreg_ctx *c, const m3dreg_obs_nn *obs, int n_obs, double *pose6, int dof, double *x_out)
+{
+	if (!c || !obs || n_obs <= 0 || !pose6 || (dof != 6 && dof != 4)) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	int e = c->obs.ensure((size_t)n_obs);
+	if (e) return e;
+	CK(cudaMemcpyAsync(c->obs.p, obs, (size_t)n_obs * sizeof(m3dreg_obs_nn), cudaMemcpyHostToDevice, c->stream));
+	double x[6] = {0, 0, 0, 0, 0, 0};
+	e = m3dreg_solve_observations(c, c->obs.p, n_obs, pose6, dof, x);
+	if (e) return e;
+	/* cudaWrapper.cpp:574-579 / 641-646 */
+	pose6[0] += x[0]; pose6[1] += x[1]; pose6[2] += x[2];
+	if (dof == 6) { pose6[3] += x[3]; pose6[4] += x[4]; pose6[5] += x[5]; }
+	else pose6[5] += x[3];
+	if (x_out) memcpy(x_out, x, sizeof(double) * dof);
+	return 0;
+}
+
+void m3dreg_matrix4_to_euler(const float *m, float *omfika, float *xyz) { matrix4_to_euler(m, omfika, xyz); }
+void m3dreg_euler_to_matrix(const float *omfika, const float *xyz, float *m) { euler_to_matrix(omfika, xyz, m); }
+
+/* ---- scan store ------------------------------------------------------------------------------------------ */
+
+int m3dreg_scan_upload(m3dreg_ctx *c, int slot, const m3dreg_point *src, int n, int src_on_device)
+{
+	if (!c || slot < 0 || !src || n <= 0) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	if ((size_t)slot >= c->scans.size()) c->scans.resize((size_t)slot + 1);
+	Scan &s = c->scans[(size_t)slot];
+	if ((size_t)n > s.cap) {
+		if (s.xyzl) cudaFree(s.xyzl);
+		if (s.nrm) cudaFree(s.nrm);
+		s.xyzl = s.nrm = nullptr; s.cap = 0; s.n = 0;
+		CK(cudaMalloc((void **)&s.xyzl, (size_t)n * sizeof(float4)));
+		CK(cudaMalloc((void **)&s.nrm, (size_t)n * sizeof(float4)));
+		s.cap = (size_t)n;
+	}
+	const m3dreg_point *d_src = src;
+	if (!src_on_device) {
+		int e = c->aos_a.ensure((size_t)n);
+		if (e) return e;
+		CK(cudaMemcpyAsync(c->aos_a.p, src, (size_t)n * sizeof(m3dreg_point), cudaMemcpyHostToDevice, c->stream));
+		d_src = c->aos_a.p;
+	}
+	LAUNCH(c, k_unpack_points, (n + 255) / 256, 256, d_src, n, s.xyzl, s.nrm);
+	s.n = n;
+	CK(cudaStreamSynchronize(c->stream));
+	return (int)cudaGetLastError();
+}
+
+int m3dreg_scan_size(const m3dreg_ctx *c, int slot)
+{
+	if (!c || slot < 0 || (size_t)slot >= c->scans.size()) return M3DREG_E_BAD_SLOT;
+	return c->scans[(size_t)slot].n;
+}
+
+int m3dreg_scan_clear(m3dreg_ctx *c)
+{
+	if (!c) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	CK(cudaStreamSynchronize(c->stream));
+	for (auto &s : c->scans) { if (s.xyzl) cudaFree(s.xyzl); if (s.nrm) cudaFree(s.nrm); }
+	c->scans.clear();
+	return 0;
+}
+
+/* ---- fused loops ------------------------------------------------------------------------------------------- */
+
+static int icp_begin_internal(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, int n2, const float *pose_first,
+		const m3dreg_reg_params *prm)
+{
+	int e;
+	memset(&c->h->ps, 0, sizeof(PoseState));
+	memcpy(c->h->ps.m, pose_first, 16 * sizeof(float));
+	CK(cudaMemcpyAsync(c->ps, &c->h->ps, sizeof(PoseState), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemsetAsync(c->label_counts, 0, 4 * sizeof(unsigned long long), c->stream));
+	CK(cudaMemsetAsync(c->flags, 0, FLAG_COUNT * sizeof(int), c->stream));
+	CK(cudaMemsetAsync(c->ticket, 0, sizeof(unsigned int), c->stream));
+	LAUNCH(c, k_pose_prepare, 1, 32, c->ps);
+	/* size the dense bucket table from the initial box (one sync, outside the iteration loop) */
+	LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
+	LAUNCH(c, k_transform_soa<true>, grid_for(c, n1, 256), 256, lx, ln, n1, c->ps->pose1, c->g_xyzl.p, c->g_nrm.p, c->bounds);
+	int sort_bits = 0;
+	if ((e = plan_buckets(c, prm, &sort_bits))) return e;
+	LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
+	c->act_lx = lx; c->act_ln = ln; c->act_n1 = n1; c->act_n2 = n2; c->act_sort_bits = sort_bits; c->act_prm = *prm;
+	c->active = true;
+	return 0;
+}
+
+static int icp_end_internal(m3dreg_ctx *c, float *pose_first_out, m3dreg_icp_stats *stats, float ms)
+{
+	CK(cudaMemcpyAsync(&c->h->ps, c->ps, sizeof(PoseState), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(&c->h->gp, c->gp, sizeof(m3dreg_grid_params), cudaMemcpyDeviceToHost, c->stream));
+	int f = check_flags(c);
+	fill_stats(c, stats, ms);
+	if (f) return f;
+	if (pose_first_out) memcpy(pose_first_out, c->h->ps.m, 16 * sizeof(float));
+	return (int)cudaGetLastError();
+}
+
+static int icp_loop(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, int n2, float *pose_first,
+		const m3dreg_reg_params *prm, int iterations, m3dreg_icp_stats *stats)
+{
+	int e = icp_begin_internal(c, lx, ln, n1, n2, pose_first, prm);
+	if (e) return e;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	for (int it = 0; it < iterations; it++) icp_iteration_device(c, lx, ln, n1, n2, prm, c->act_sort_bits);
+	CK(cudaEventRecord(c->ev1, c->stream));
+	CK(cudaEventSynchronize(c->ev1));
+	float ms = 0.0f;
+	cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+	return icp_end_internal(c, pose_first, stats, ms);
+}
+
+static int stage_queries(m3dreg_ctx *c, int second_slot, const float *pose_second)
+{
+	const Scan &B = c->scans[(size_t)second_slot];
+	/* queries: second scan transformed once by the Euler round trip of its pose (gpu6DSLAM.cpp:295-307) */
+	host_roundtrip_pose(pose_second, c->h->mats, nullptr);
+	CK(cudaMemcpyAsync(c->mats, c->h->mats, 16 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+	LAUNCH(c, k_transform_soa<false>, grid_for(c, B.n, 256), 256, B.xyzl, B.nrm, B.n, c->mats, c->q_xyzl.p, c->q_nrm.p, (uint32_t *)nullptr);
+	return 0;
+}
+
+int m3dreg_icp_begin(m3dreg_ctx *c, int first_slot, int second_slot, const float *pose_first, const float *pose_second,
+		const m3dreg_reg_params *prm)
+{
+	if (!c || !pose_first || !pose_second || !valid_params(prm)) return M3DREG_E_INVALID_ARG;
+	if (first_slot < 0 || second_slot < 0 || (size_t)first_slot >= c->scans.size() || (size_t)second_slot >= c->scans.size())
+		return M3DREG_E_BAD_SLOT;
+	const Scan &A = c->scans[(size_t)first_slot], &B = c->scans[(size_t)second_slot];
+	if (A.n <= 0 || B.n <= 0) return M3DREG_E_BAD_SLOT;
+	CK(cudaSetDevice(c->dev));
+	int e;
+	if ((e = ensure_first(c, (size_t)A.n))) return e;
+	if ((e = ensure_second(c, (size_t)B.n))) return e;
+	if ((e = stage_queries(c, second_slot, pose_second))) return e;
+	return icp_begin_internal(c, A.xyzl, A.nrm, A.n, B.n, pose_first, prm);
+}
+
+int m3dreg_icp_step(m3dreg_ctx *c, int iterations)
+{
+	if (!c || iterations < 0) return M3DREG_E_INVALID_ARG;
+	if (!c->active) return M3DREG_E_BAD_SLOT;
+	CK(cudaSetDevice(c->dev));
+	for (int it = 0; it < iterations; it++)
+		icp_iteration_device(c, c->act_lx, c->act_ln, c->act_n1, c->act_n2, &c->act_prm, c->act_sort_bits);
+	return (int)cudaGetLastError();
+}
+
+int m3dreg_icp_end(m3dreg_ctx *c, float *pose_first_out, m3dreg_icp_stats *stats)
+{
+	if (!c) return M3DREG_E_INVALID_ARG;
+	if (!c->active) return M3DREG_E_BAD_SLOT;
+	CK(cudaSetDevice(c->dev));
+	c->active = false;
+	return icp_end_internal(c, pose_first_out, stats, 0.0f);
+}
+
+int m3dreg_icp_copy_neq(m3dreg_ctx *c, double *d_dst)
+{
+	if (!c || !d_dst) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	CK(cudaMemcpyAsync(d_dst, c->ps->neq, kNeqCount * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+	return 0;
+}
+
+int m3dreg_set_profiling(m3dreg_ctx *c, int enabled)
+{
+	if (!c) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	if (enabled && !c->pev[0])
+		for (int k = 0; k <= M3DREG_STAGE_COUNT; k++) CK(cudaEventCreate(&c->pev[k]));
+	c->profiling = enabled != 0;
+	for (int k = 0; k < M3DREG_STAGE_COUNT; k++) c->stage_ms[k] = 0.0f;
+	c->stage_iters = 0;
+	return 0;
+}
+
+int m3dreg_get_stage_ms(m3dreg_ctx *c, float *ms_out, int *iterations_out)
+{
+	if (!c || !ms_out) return M3DREG_E_INVALID_ARG;
+	for (int k = 0; k < M3DREG_STAGE_COUNT; k++) { ms_out[k] = c->stage_ms[k]; c->stage_ms[k] = 0.0f; }
+	if (iterations_out) *iterations_out = c->stage_iters;
+	c->stage_iters = 0;
+	return 0;
+}
+
+int m3dreg_icp_pair(m3dreg_ctx *c, int first_slot, int second_slot, float *pose_first, const float *pose_second,
+		const m3dreg_reg_params *prm, int iterations, m3dreg_icp_stats *stats)
+{
+	if (!c || !pose_first || !pose_second || !valid_params(prm) || iterations < 0) return M3DREG_E_INVALID_ARG;
+	if (first_slot < 0 || second_slot < 0 || (size_t)first_slot >= c->scans.size() || (size_t)second_slot >= c->scans.size())
+		return M3DREG_E_BAD_SLOT;
+	const Scan &A = c->scans[(size_t)first_slot], &B = c->scans[(size_t)second_slot];
+	if (A.n <= 0 || B.n <= 0) return M3DREG_E_BAD_SLOT;
+	CK(cudaSetDevice(c->dev));
+	int e;
+	if ((e = ensure_first(c, (size_t)A.n))) return e;
+	if ((e = ensure_second(c, (size_t)B.n))) return e;
+	if ((e = stage_queries(c, second_slot, pose_second))) return e;
+	e = icp_loop(c, A.xyzl, A.nrm, A.n, B.n, pose_first, prm, iterations, stats);
+	c->active = false;
+	return e;
+}
+
+int m3dreg_icp_iteration_host(m3dreg_ctx *c, const m3dreg_point *first_local, int n1, const m3dreg_point *second_global, int n2,
+		float *pose_first, const m3dreg_reg_params *prm, int *nn_out, m3dreg_icp_stats *stats)
+{
+	if (!c || !first_local || !second_global || n1 <= 0 || n2 <= 0 || !pose_first || !valid_params(prm)) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	int e;
+	if ((e = c->aos_a.ensure((size_t)n1))) return e;
+	if ((e = c->aos_b.ensure((size_t)n2))) return e;
+	if ((e = c->l_xyzl.ensure((size_t)n1))) return e;
+	if ((e = c->l_nrm.ensure((size_t)n1))) return e;
+	if ((e = ensure_first(c, (size_t)n1))) return e;
+	if ((e = ensure_second(c, (size_t)n2))) return e;
+	CK(cudaMemcpyAsync(c->aos_a.p, first_local, (size_t)n1 * sizeof(m3dreg_point), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->aos_b.p, second_global, (size_t)n2 * sizeof(m3dreg_point), cudaMemcpyHostToDevice, c->stream));
+	LAUNCH(c, k_unpack_points, (n1 + 255) / 256, 256, c->aos_a.p, n1, c->l_xyzl.p, c->l_nrm.p);
+	LAUNCH(c, k_unpack_points, (n2 + 255) / 256, 256, c->aos_b.p, n2, c->q_xyzl.p, c->q_nrm.p);
+	e = icp_loop(c, c->l_xyzl.p, c->l_nrm.p, n1, n2, pose_first, prm, 1, stats);
+	c->active = false;
+	if (e) return e;
+	if (nn_out) {
+		CK(cudaMemcpyAsync(nn_out, c->nn.p, (size_t)n2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	return (int)cudaGetLastError();
+}
+
+int m3dreg_export_last_grid(m3dreg_ctx *c, m3dreg_grid_params *params_out, m3dreg_hash_element *table_out, int table_cap,
+		m3dreg_bucket *buckets_out, int64_t buckets_cap)
+{
+	if (!c) return M3DREG_E_INVALID_ARG;
+	if (!c->last_valid) return M3DREG_E_BAD_SLOT;
+	CK(cudaSetDevice(c->dev));
+	CK(cudaMemcpyAsync(&c->h->gp, c->gp, sizeof(m3dreg_grid_params), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	if (params_out) *params_out = c->h->gp;
+	int n = c->last_n_first;
+	if (table_out) {
+		if (table_cap < n) return M3DREG_E_SIZE_MISMATCH;
+		std::vector<uint32_t> k((size_t)n), v((size_t)n);
+		CK(cudaMemcpyAsync(k.data(), c->keys[c->last_sorted].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaMemcpyAsync(v.data(), c->vals[c->last_sorted].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		for (int i = 0; i < n; i++) { table_out[i].index_of_point = (int)v[(size_t)i]; table_out[i].index_of_bucket = (int)k[(size_t)i]; }
+	}
+	if (buckets_out) {
+		if (buckets_cap < c->h->gp.number_of_buckets) return M3DREG_E_SIZE_MISMATCH;
+		CK(cudaMemcpyAsync(buckets_out, c->buckets.p, (size_t)c->h->gp.number_of_buckets * sizeof(m3dreg_bucket), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	return 0;
+}
+
+int m3dreg_export_last_nn(m3dreg_ctx *c, int *nn_out, int nn_cap)
+{
+	if (!c || !nn_out) return M3DREG_E_INVALID_ARG;
+	if (!c->last_valid) return M3DREG_E_BAD_SLOT;
+	if (nn_cap < c->last_n_second) return M3DREG_E_SIZE_MISMATCH;
+	CK(cudaSetDevice(c->dev));
+	CK(cudaMemcpyAsync(nn_out, c->nn.p, (size_t)c->last_n_second * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+/* ---- multi-scan sweep (registerAll) ------------------------------------------------------------------------ */
+
+int m3dreg_sweep_zero(m3dreg_ctx *c, double *d_neq, int n_scans)
+{
+	if (!c || !d_neq || n_scans <= 0) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	LAUNCH(c, k_zero_f64, grid_for(c, (long long)n_scans * kNeqCount, 256), 256, d_neq, n_scans * kNeqCount);
+	return (int)cudaGetLastError();
+}
+
+int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const int *pair_j, const float *poses, int n_scans,
+		const m3dreg_reg_params *prm, double *d_neq)
+{
+	if (!c || n_pairs < 0 || (n_pairs && (!pair_i || !pair_j)) || !poses || n_scans <= 0 || !valid_params(prm) || !d_neq)
+		return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	int e;
+	for (int p = 0; p < n_pairs; p++) {
+		int i = pair_i[p], j = pair_j[p];
+		if (i < 0 || j < 0 || i >= n_scans || j >= n_scans || (size_t)i >= c->scans.size() || (size_t)j >= c->scans.size() ||
+				c->scans[(size_t)i].n <= 0 || c->scans[(size_t)j].n <= 0 || i == j)
+			return M3DREG_E_BAD_SLOT;
+	}
+	/* Euler round trip of every (old) pose: gpu6DSLAM.cpp:440-441, 461-462 */
+	std::vector<float> p1((size_t)n_scans * 16);
+	std::vector<double> p6((size_t)n_scans * 6);
+	for (int s = 0; s < n_scans; s++) host_roundtrip_pose(poses + 16 * (size_t)s, p1.data() + 16 * (size_t)s, p6.data() + 6 * (size_t)s);
+	if ((e = c->d_poses1.ensure(p1.size()))) return e;
+	if ((e = c->d_pose6.ensure(p6.size()))) return e;
+	CK(cudaMemcpyAsync(c->d_poses1.p, p1.data(), p1.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->d_pose6.p, p6.data(), p6.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaStreamSynchronize(c->stream));   /* p1/p6 are pageable */
+	CK(cudaMemsetAsync(c->label_counts, 0, 4 * sizeof(unsigned long long), c->stream));
+	CK(cudaMemsetAsync(c->flags, 0, FLAG_COUNT * sizeof(int), c->stream));
+	CK(cudaMemsetAsync(c->ticket, 0, sizeof(unsigned int), c->stream));
+
+	/* process pairs grouped by i so the grid of scan i is built once (the reference rebuilds it per j, gpu6DSLAM.cpp:478) */
+	std::vector<int> order((size_t)n_pairs);
+	for (int p = 0; p < n_pairs; p++) order[(size_t)p] = p;
+	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pair_i[a] < pair_i[b]; });
+	int cur_i = -1, sort_bits = 0;
+	for (int q = 0; q < n_pairs; q++) {
+		int p = order[(size_t)q];
+		int i = pair_i[p], j = pair_j[p];
+		const Scan &A = c->scans[(size_t)i], &B = c->scans[(size_t)j];
+		if (i != cur_i) {
+			if ((e = ensure_first(c, (size_t)A.n))) return e;
+			LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
+			LAUNCH(c, k_transform_soa<true>, grid_for(c, A.n, 256), 256, A.xyzl, A.nrm, A.n, c->d_poses1.p + 16 * (size_t)i,
+					c->g_xyzl.p, c->g_nrm.p, c->bounds);
+			if ((e = plan_buckets(c, prm, &sort_bits))) return e;
+			build_grid_fused(c, A.n, prm, sort_bits);
+			cur_i = i;
+		}
+		if ((e = ensure_second(c, (size_t)B.n))) return e;
+		LAUNCH(c, k_transform_soa<false>, grid_for(c, B.n, 256), 256, B.xyzl, B.nrm, B.n, c->d_poses1.p + 16 * (size_t)j,
+				c->q_xyzl.p, c->q_nrm.p, (uint32_t *)nullptr);
+		LAUNCH(c, k_nn_search, (B.n + 255) / 256, 256, c->q_xyzl.p, c->q_nrm.p, B.n, c->s_xyzl.p, c->s_nrm.p,
+				c->vals[c->last_sorted].p, A.n, c->buckets.p, c->gp, prm->search_radius, prm->max_inner, prm->max_outer, 1,
+				c->nn.p, c->label_counts);
+		ObsFromNN src;
+		src.nn = c->nn.p; src.q_xyzl = c->q_xyzl.p; src.g_xyzl = c->g_xyzl.p; src.l_xyzl = A.xyzl; src.label_counts = c->label_counts;
+		for (int k = 0; k < 4; k++) src.weight[k] = prm->weight[k];
+		FinalizeArgs fin;
+		fin.ps = nullptr; fin.neq_out = d_neq + (size_t)i * kNeqCount; fin.accumulate = 1; fin.solve = 0; fin.dof = prm->dof;
+		fin.obs_threshold = prm->obs_threshold; fin.pose6_in = c->d_pose6.p + 6 * (size_t)i; fin.bounds_reset = nullptr;
+		fin.label_counts_reset = c->label_counts;
+		LAUNCH(c, k_normal_equations<ObsFromNN>, grid_for(c, B.n, kNeqThreads, 4), kNeqThreads, src, B.n, c->partials.p, c->ticket, fin);
+		c->last_n_first = A.n; c->last_n_second = B.n; c->last_valid = true;
+	}
+	int f = check_flags(c);
+	if (f) return f;
+	return (int)cudaGetLastError();
+}
+
+int m3dreg_sweep_solve(m3dreg_ctx *c, const double *d_neq, int n_scans, int scan_begin, int scan_end, float *poses,
+		const m3dreg_reg_params *prm, int *status_out)
+{
+	if (!c || !d_neq || n_scans <= 0 || scan_begin < 0 || scan_end > n_scans || scan_begin > scan_end || !poses || !valid_params(prm))
+		return M3DREG_E_INVALID_ARG;
+	if (scan_begin == scan_end) return 0;
+	CK(cudaSetDevice(c->dev));
+	int e;
+	if ((e = c->d_poses1.ensure((size_t)n_scans * 16))) return e;
+	DevBuf<int> st;
+	if ((e = st.ensure((size_t)n_scans))) return e;
+	CK(cudaMemcpyAsync(c->d_poses1.p, poses, (size_t)n_scans * 16 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+	int cnt = scan_end - scan_begin;
+	LAUNCH(c, k_sweep_solve, (cnt + 63) / 64, 64, d_neq, scan_begin, scan_end, c->d_poses1.p, prm->dof, prm->obs_threshold, st.p);
+	CK(cudaMemcpyAsync(poses + 16 * (size_t)scan_begin, c->d_poses1.p + 16 * (size_t)scan_begin, (size_t)cnt * 16 * sizeof(float),
+			cudaMemcpyDeviceToHost, c->stream));
+	if (status_out)
+		CK(cudaMemcpyAsync(status_out + scan_begin, st.p + scan_begin, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	st.release();
+	return (int)cudaGetLastError();
+}
+
+} /* extern "C" */

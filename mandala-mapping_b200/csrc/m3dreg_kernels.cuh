@@ -1,0 +1,968 @@
+/* m3dreg_kernels.cuh — sm_100a kernels of the registration hot path.
+ *
+ * Data layout in HBM (all device-resident, SoA, 16-byte records so every access is one LDG.128/STG.128):
+ *   xyzl[i] = {x, y, z, label-bits}      nrm[i] = {nx, ny, nz, 0}
+ * for (a) each stored scan in its local frame, (b) the first cloud transformed into the global frame in
+ * original order (g_*), (c) the same in grid-sorted order (s_*), (d) the queries (q_*).
+ * Grid: keys/vals u32 ping-pong buffers for the LSD radix sort, a dense bucket table in the reference's
+ * 12-byte layout, nn[] in query order.
+ *
+ * Arithmetic contract: every float operation that decides an index is written with
+ * explicit round-to-nearest intrinsics in the exact association nvcc 12.9 gives the reference's kernels
+ * (src/lesson_16.cu of the reference, PTX inspected), so results are bit-identical:
+ *   cell    = cvt.rzi( div.rn( sub(v, min), res ) )                       (lesson_16.cu:124-126, 578-580)
+ *   dist    = fma(dz,dz, fma(dx,dx, dy*dy))                               (lesson_16.cu:658-660)
+ *   dot     = fma(nz,nnz, fma(nx,nnx, ny*nny))                            (lesson_16.cu:662-664)
+ *   v'      = t + fma(r02,z, fma(r00,x, r01*y))                           (lesson_16.cu:1354-1356)
+ * No -use_fast_math, no reciprocal multiplication.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/m3dreg.h"
+
+namespace m3d {
+
+constexpr int kMomentCount = 24;   /* S, M1[3], M2[6], L1[3], L2[9], n_obs, (pad) */
+constexpr int kNeqCount = 28;      /* 21 upper-tri AtPA + 6 AtPl + count */
+
+/* flags[] slots */
+enum { FLAG_ERROR = 0, FLAG_COUNT = 4 };
+
+/* Device-resident pose / solve state of the fused loop. */
+struct PoseState {
+	float  m[16];        /* stored pose (row-major 4x4), the reference's vmregistered[i]          */
+	float  pose1[16];    /* Euler round trip of m, used to transform the first cloud this iteration */
+	double pose6[6];     /* tx,ty,tz,om,fi,ka = double(float Euler) that the solve updates          */
+	double x[6];         /* last solution                                                          */
+	double neq[kNeqCount];
+	long long n_obs;
+	int    status;       /* 0 | M3DREG_E_NOT_SPD | M3DREG_E_TOO_FEW_OBS                            */
+	int    iterations;
+};
+
+/* ---- ordered-uint encoding of floats for atomicMin/Max -------------------------------------------- */
+__device__ __forceinline__ uint32_t f2o(float f)
+{
+	uint32_t u = __float_as_uint(f);
+	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float o2f(uint32_t o)
+{
+	return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+__device__ __forceinline__ float warp_min(float v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+/* Block-level min/max of xyz and one atomic per block per bound. blockDim.x multiple of 32, <= 1024. */
+__device__ __forceinline__ void block_bounds_commit(float mnx, float mny, float mnz, float mxx, float mxy, float mxz,
+		uint32_t *bounds)
+{
+	__shared__ float sm[6][32];
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+	mnx = warp_min(mnx); mny = warp_min(mny); mnz = warp_min(mnz);
+	mxx = warp_max(mxx); mxy = warp_max(mxy); mxz = warp_max(mxz);
+	if (lane == 0) { sm[0][w] = mnx; sm[1][w] = mny; sm[2][w] = mnz; sm[3][w] = mxx; sm[4][w] = mxy; sm[5][w] = mxz; }
+	__syncthreads();
+	if (w == 0) {
+		float a = lane < nw ? sm[0][lane] : INFINITY, b = lane < nw ? sm[1][lane] : INFINITY, c = lane < nw ? sm[2][lane] : INFINITY;
+		float d = lane < nw ? sm[3][lane] : -INFINITY, e = lane < nw ? sm[4][lane] : -INFINITY, f = lane < nw ? sm[5][lane] : -INFINITY;
+		a = warp_min(a); b = warp_min(b); c = warp_min(c);
+		d = warp_max(d); e = warp_max(e); f = warp_max(f);
+		if (lane == 0) {
+			atomicMin(&bounds[0], f2o(a)); atomicMin(&bounds[1], f2o(b)); atomicMin(&bounds[2], f2o(c));
+			atomicMax(&bounds[3], f2o(d)); atomicMax(&bounds[4], f2o(e)); atomicMax(&bounds[5], f2o(f));
+		}
+	}
+}
+
+/* ---- AoS (reference 40-byte point) <-> SoA ----------------------------------------------------------- */
+__global__ void k_unpack_points(const m3dreg_point *__restrict__ in, int n, float4 *__restrict__ xyzl, float4 *__restrict__ nrm)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint2 *p = reinterpret_cast<const uint2 *>(in + i);   /* 40-byte records are 8-byte aligned */
+	uint2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4);
+	/* a={x,y} b={z,intensity} c={ring,normal_x} d={normal_y,normal_z} e={label,rgb} */
+	xyzl[i] = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(b.x), __uint_as_float(e.x));
+	nrm[i] = make_float4(__uint_as_float(c.y), __uint_as_float(d.x), __uint_as_float(d.y), 0.0f);
+}
+
+/* min/max straight from an AoS cloud (stage-level m3dreg_grid_params). */
+__global__ void k_bounds_aos(const m3dreg_point *__restrict__ in, int n, uint32_t *bounds)
+{
+	float mnx = INFINITY, mny = INFINITY, mnz = INFINITY, mxx = -INFINITY, mxy = -INFINITY, mxz = -INFINITY;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint2 *p = reinterpret_cast<const uint2 *>(in + i);
+		uint2 a = __ldg(p), b = __ldg(p + 1);
+		float x = __uint_as_float(a.x), y = __uint_as_float(a.y), z = __uint_as_float(b.x);
+		mnx = fminf(mnx, x); mny = fminf(mny, y); mnz = fminf(mnz, z);
+		mxx = fmaxf(mxx, x); mxy = fmaxf(mxy, y); mxz = fmaxf(mxz, z);
+	}
+	block_bounds_commit(mnx, mny, mnz, mxx, mxy, mxz, bounds);
+}
+
+__global__ void k_reset_bounds(uint32_t *bounds)
+{
+	if (threadIdx.x < 3) bounds[threadIdx.x] = 0xFFFFFFFFu;
+	else if (threadIdx.x < 6) bounds[threadIdx.x] = 0u;
+}
+
+/* Rigid transform of an AoS cloud, bit-compatible with the reference's device kernel (lesson_16.cu:1341-1367). */
+__global__ void k_transform_aos(const m3dreg_point *__restrict__ in, m3dreg_point *__restrict__ out, int n,
+		float r00, float r01, float r02, float t0, float r10, float r11, float r12, float t1,
+		float r20, float r21, float r22, float t2)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	m3dreg_point p = in[i];
+	float x = p.x, y = p.y, z = p.z, nx = p.normal_x, ny = p.normal_y, nz = p.normal_z;
+	p.x = __fadd_rn(t0, __fmaf_rn(r02, z, __fmaf_rn(r00, x, __fmul_rn(r01, y))));
+	p.y = __fadd_rn(t1, __fmaf_rn(r12, z, __fmaf_rn(r10, x, __fmul_rn(r11, y))));
+	p.z = __fadd_rn(t2, __fmaf_rn(r22, z, __fmaf_rn(r20, x, __fmul_rn(r21, y))));
+	p.normal_x = __fmaf_rn(r02, nz, __fmaf_rn(r00, nx, __fmul_rn(r01, ny)));
+	p.normal_y = __fmaf_rn(r12, nz, __fmaf_rn(r10, nx, __fmul_rn(r11, ny)));
+	p.normal_z = __fmaf_rn(r22, nz, __fmaf_rn(r20, nx, __fmul_rn(r21, ny)));
+	out[i] = p;
+}
+
+/* Transform a stored scan (SoA) by the 3x4 matrix at `m` (DEVICE memory, row-major 4x4) and, when bounds != 0,
+ * reduce the bounding box of the result in the same pass (replaces 3x thrust::minmax_element, lesson_16.cu:34-45). */
+template <bool WITH_BOUNDS>
+__global__ void k_transform_soa(const float4 *__restrict__ in_xyzl, const float4 *__restrict__ in_nrm, int n,
+		const float *__restrict__ m, float4 *__restrict__ out_xyzl, float4 *__restrict__ out_nrm, uint32_t *bounds)
+{
+	float r00 = __ldg(m + 0), r01 = __ldg(m + 1), r02 = __ldg(m + 2), t0 = __ldg(m + 3);
+	float r10 = __ldg(m + 4), r11 = __ldg(m + 5), r12 = __ldg(m + 6), t1 = __ldg(m + 7);
+	float r20 = __ldg(m + 8), r21 = __ldg(m + 9), r22 = __ldg(m + 10), t2 = __ldg(m + 11);
+	float mnx = INFINITY, mny = INFINITY, mnz = INFINITY, mxx = -INFINITY, mxy = -INFINITY, mxz = -INFINITY;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		float4 p = __ldg(in_xyzl + i), q = __ldg(in_nrm + i);
+		float x = __fadd_rn(t0, __fmaf_rn(r02, p.z, __fmaf_rn(r00, p.x, __fmul_rn(r01, p.y))));
+		float y = __fadd_rn(t1, __fmaf_rn(r12, p.z, __fmaf_rn(r10, p.x, __fmul_rn(r11, p.y))));
+		float z = __fadd_rn(t2, __fmaf_rn(r22, p.z, __fmaf_rn(r20, p.x, __fmul_rn(r21, p.y))));
+		float nx = __fmaf_rn(r02, q.z, __fmaf_rn(r00, q.x, __fmul_rn(r01, q.y)));
+		float ny = __fmaf_rn(r12, q.z, __fmaf_rn(r10, q.x, __fmul_rn(r11, q.y)));
+		float nz = __fmaf_rn(r22, q.z, __fmaf_rn(r20, q.x, __fmul_rn(r21, q.y)));
+		out_xyzl[i] = make_float4(x, y, z, p.w);
+		out_nrm[i] = make_float4(nx, ny, nz, 0.0f);
+		if (WITH_BOUNDS) {
+			mnx = fminf(mnx, x); mny = fminf(mny, y); mnz = fminf(mnz, z);
+			mxx = fmaxf(mxx, x); mxy = fmaxf(mxy, y); mxz = fmaxf(mxz, z);
+		}
+	}
+	if (WITH_BOUNDS) block_bounds_commit(mnx, mny, mnz, mxx, mxy, mxz, bounds);
+}
+
+/* Grid parameters from the reduced bounds, on the device (host part of cudaCalculateGridParams, lesson_16.cu:64-91):
+ * max += ext; min -= ext; nb = int((max-min)/res + 1); B = nbX*nbY*nbZ.  One thread.
+ * Sets flags[FLAG_ERROR] when B overflows int32 or the planned capacity; B is then forced to 0 so that every
+ * later kernel of the iteration is a no-op. */
+__global__ void k_grid_params(const uint32_t *__restrict__ bounds, float rx, float ry, float rz, float ext,
+		long long bucket_cap, m3dreg_grid_params *gp, int *flags)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	float mnx = o2f(bounds[0]), mny = o2f(bounds[1]), mnz = o2f(bounds[2]);
+	float mxx = o2f(bounds[3]), mxy = o2f(bounds[4]), mxz = o2f(bounds[5]);
+	mxx = __fadd_rn(mxx, ext); mnx = __fsub_rn(mnx, ext);
+	mxy = __fadd_rn(mxy, ext); mny = __fsub_rn(mny, ext);
+	mxz = __fadd_rn(mxz, ext); mnz = __fsub_rn(mnz, ext);
+	int nbx = (int)__fadd_rn(__fdiv_rn(__fsub_rn(mxx, mnx), rx), 1.0f);
+	int nby = (int)__fadd_rn(__fdiv_rn(__fsub_rn(mxy, mny), ry), 1.0f);
+	int nbz = (int)__fadd_rn(__fdiv_rn(__fsub_rn(mxz, mnz), rz), 1.0f);
+	long long nb = (long long)nbx * (long long)nby * (long long)nbz;
+	gp->bounding_box_min_X = mnx; gp->bounding_box_min_Y = mny; gp->bounding_box_min_Z = mnz;
+	gp->bounding_box_max_X = mxx; gp->bounding_box_max_Y = mxy; gp->bounding_box_max_Z = mxz;
+	gp->number_of_buckets_X = nbx; gp->number_of_buckets_Y = nby; gp->number_of_buckets_Z = nbz;
+	gp->resolution_X = rx; gp->resolution_Y = ry; gp->resolution_Z = rz;
+	gp->_pad0 = 0; gp->_pad1 = 0;
+	if (nbx <= 0 || nby <= 0 || nbz <= 0 || nb > 2147483647LL || nb > bucket_cap) {
+		gp->number_of_buckets = 0;
+		atomicExch(&flags[FLAG_ERROR], M3DREG_E_TOO_MANY_BUCKETS);
+	} else {
+		gp->number_of_buckets = nb;
+	}
+}
+
+__device__ __forceinline__ int cell_of(float v, float mn, float res)
+{
+	return (int)__fdiv_rn(__fsub_rn(v, mn), res);     /* sub.f32, div.rn.f32, cvt.rzi.s32.f32 */
+}
+
+/* Bucket key of every point (kernel_initializeIndByKey + kernel_getIndexOfBucketForPoints, lesson_16.cu:109-129),
+ * values are the implicit original indices. */
+__global__ void k_keys_soa(const float4 *__restrict__ xyzl, int n, const m3dreg_grid_params *__restrict__ gp,
+		uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+	if (gp->number_of_buckets <= 0) return;
+	float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
+	float rx = gp->resolution_X, ry = gp->resolution_Y, rz = gp->resolution_Z;
+	int nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		float4 p = __ldg(xyzl + i);
+		int ix = cell_of(p.x, mnx, rx), iy = cell_of(p.y, mny, ry), iz = cell_of(p.z, mnz, rz);
+		keys[i] = (uint32_t)(ix * nby * nbz + iy * nbz + iz);
+		vals[i] = (uint32_t)i;
+	}
+}
+
+__global__ void k_keys_aos(const m3dreg_point *__restrict__ in, int n, const m3dreg_grid_params *__restrict__ gp,
+		uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+	float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
+	float rx = gp->resolution_X, ry = gp->resolution_Y, rz = gp->resolution_Z;
+	int nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint2 *p = reinterpret_cast<const uint2 *>(in + i);
+		uint2 a = __ldg(p), b = __ldg(p + 1);
+		int ix = cell_of(__uint_as_float(a.x), mnx, rx), iy = cell_of(__uint_as_float(a.y), mny, ry), iz = cell_of(__uint_as_float(b.x), mnz, rz);
+		keys[i] = (uint32_t)(ix * nby * nbz + iy * nbz + iz);
+		vals[i] = (uint32_t)i;
+	}
+}
+
+/* ---- stable LSD radix sort by bucket key (replaces thrust::sort + compareHashElements, lesson_16.cu:213-227) ----
+ * 8-bit digits, ceil(bits/8) passes where bits = bit width of the bucket capacity.  Each pass:
+ *   k_radix_hist    per-tile digit histogram  -> hist[digit * tiles + tile]
+ *   k_radix_scan    exclusive scan of that digit-major matrix (single block)
+ *   k_radix_scatter stable in-tile ranking (warp match-any multisplit) + scatter
+ * Stability gives ties in ascending original index, i.e. exactly the permutation of the reference's stable merge sort.
+ * Keys are non-negative ints (valid cells), so unsigned order == signed order. */
+constexpr int kRadixBits = 8;
+constexpr int kRadixSize = 1 << kRadixBits;
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+
+template <int ITEMS>
+__global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint32_t *__restrict__ keys, int n, int shift,
+		int tiles, uint32_t *__restrict__ hist, const m3dreg_grid_params *__restrict__ gp)
+{
+	__shared__ uint32_t sh[kRadixSize];
+	if (gp && gp->number_of_buckets <= 0) return;
+	sh[threadIdx.x] = 0;
+	__syncthreads();
+	int base = blockIdx.x * (kSortThreads * ITEMS);
+#pragma unroll
+	for (int j = 0; j < ITEMS; j++) {
+		int i = base + j * kSortThreads + threadIdx.x;
+		if (i < n) atomicAdd(&sh[(__ldg(keys + i) >> shift) & (kRadixSize - 1)], 1u);
+	}
+	__syncthreads();
+	hist[threadIdx.x * tiles + blockIdx.x] = sh[threadIdx.x];
+}
+
+/* single-block exclusive scan over `count` uint32 (count = 256 * tiles) */
+__global__ void __launch_bounds__(1024) k_radix_scan(uint32_t *__restrict__ hist, int count, const m3dreg_grid_params *__restrict__ gp)
+{
+	__shared__ uint32_t warp_tot[32];
+	if (gp && gp->number_of_buckets <= 0) return;
+	int per = (count + 1023) / 1024;
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	int beg = threadIdx.x * per, end = min(beg + per, count);
+	uint32_t sum = 0;
+	for (int i = beg; i < end; i++) sum += hist[i];
+	uint32_t incl = sum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += t;
+	}
+	if (lane == 31) warp_tot[w] = incl;
+	__syncthreads();
+	if (w == 0) {
+		uint32_t v = warp_tot[lane], iv = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			uint32_t t = __shfl_up_sync(0xffffffffu, iv, o);
+			if (lane >= o) iv += t;
+		}
+		warp_tot[lane] = iv - v;
+	}
+	__syncthreads();
+	uint32_t run = warp_tot[w] + incl - sum;
+	for (int i = beg; i < end; i++) {
+		uint32_t v = hist[i];
+		hist[i] = run;
+		run += v;
+	}
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+		uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int n, int shift, int tiles,
+		const uint32_t *__restrict__ hist, const m3dreg_grid_params *__restrict__ gp)
+{
+	__shared__ uint32_t wcnt[kSortWarps][kRadixSize];   /* per-warp digit counts, then per-warp exclusive offsets */
+	__shared__ uint32_t gbase[kRadixSize];
+	if (gp && gp->number_of_buckets <= 0) return;
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+	for (int k = 0; k < kSortWarps; k++) wcnt[k][threadIdx.x] = 0;
+	gbase[threadIdx.x] = hist[threadIdx.x * tiles + blockIdx.x];
+	__syncthreads();
+
+	int wbase = blockIdx.x * (kSortThreads * ITEMS) + w * (32 * ITEMS);
+	uint32_t key[ITEMS], val[ITEMS], rank[ITEMS];
+	const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+	for (int j = 0; j < ITEMS; j++) {
+		int i = wbase + j * 32 + lane;
+		bool valid = i < n;
+		key[j] = valid ? __ldg(keys_in + i) : 0xFFFFFFFFu;
+		val[j] = valid ? __ldg(vals_in + i) : 0u;
+		uint32_t d = (key[j] >> shift) & (kRadixSize - 1);
+		/* invalid lanes must not disturb the counts of digit 0xFF: give them their own match group */
+		uint32_t mk = valid ? d : (0x100u + lane);
+		uint32_t peers = __match_any_sync(0xffffffffu, mk);
+		int leader = __ffs(peers) - 1;
+		uint32_t old = 0;
+		if (lane == leader && valid) {
+			old = wcnt[w][d];
+			wcnt[w][d] = old + __popc(peers);
+		}
+		old = __shfl_sync(0xffffffffu, old, leader);
+		rank[j] = old + __popc(peers & lt);
+		__syncwarp();
+	}
+	__syncthreads();
+	{   /* exclusive scan over warps for digit = threadIdx.x */
+		uint32_t run = 0;
+#pragma unroll
+		for (int k = 0; k < kSortWarps; k++) {
+			uint32_t c = wcnt[k][threadIdx.x];
+			wcnt[k][threadIdx.x] = run;
+			run += c;
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (int j = 0; j < ITEMS; j++) {
+		int i = wbase + j * 32 + lane;
+		if (i < n) {
+			uint32_t d = (key[j] >> shift) & (kRadixSize - 1);
+			uint32_t pos = gbase[d] + wcnt[w][d] + rank[j];
+			keys_out[pos] = key[j];
+			vals_out[pos] = val[j];
+		}
+	}
+}
+
+/* ---- dense bucket table (kernel_initializeBuckets / updateBuckets / countNumberOfPointsForBuckets,
+ *      lesson_16.cu:131-189) + gather of the first cloud into sorted order ---------------------------------- */
+__global__ void k_init_buckets(m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp, long long nb_host)
+{
+	long long nb = gp ? gp->number_of_buckets : nb_host;
+	/* 12-byte records written as a flat int stream: -1,-1,0,-1,-1,0,... */
+	long long total = nb * 3;
+	int *flat = reinterpret_cast<int *>(buckets);
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+		flat[i] = (i % 3 == 2) ? 0 : -1;
+}
+
+__device__ __forceinline__ int lower_bound_u32(const uint32_t *__restrict__ a, int n, uint32_t key)
+{
+	int lo = 0, hi = n;
+	while (lo < hi) {
+		int mid = (lo + hi) >> 1;
+		if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+	}
+	return lo;
+}
+
+/* One thread per sorted position p.  The thread at the END of a run writes the whole 12-byte record
+ * {begin, end, n} (begin by binary search), so no separate count pass is needed.  Reference quirk reproduced
+ * (lesson_16.cu:148-158): when element 0 is alone in its bucket, the run that starts at position 1 never gets
+ * index_begin (it receives index_end=1 instead), so that bucket reads {-1, end, 0}.  Its index_end is a write
+ * race upstream (1 vs run end); we store the run end.
+ * Also gathers the transformed first cloud into sorted order and (optionally) materialises the reference's
+ * hashElement table. */
+__global__ void k_finalize_grid(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int n,
+		const m3dreg_grid_params *__restrict__ gp, m3dreg_bucket *__restrict__ buckets,
+		const float4 *__restrict__ g_xyzl, const float4 *__restrict__ g_nrm,
+		float4 *__restrict__ s_xyzl, float4 *__restrict__ s_nrm, m3dreg_hash_element *__restrict__ table_out)
+{
+	if (gp && gp->number_of_buckets <= 0) return;
+	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+		uint32_t k = __ldg(keys + p);
+		uint32_t v = __ldg(vals + p);
+		if (s_xyzl) {
+			s_xyzl[p] = __ldg(g_xyzl + v);
+			s_nrm[p] = __ldg(g_nrm + v);
+		}
+		if (table_out) {
+			m3dreg_hash_element h;
+			h.index_of_point = (int)v;
+			h.index_of_bucket = (int)k;
+			table_out[p] = h;
+		}
+		bool run_end = (p == n - 1) || (__ldg(keys + p + 1) != k);
+		if (run_end) {
+			int begin = lower_bound_u32(keys, p + 1, k);
+			m3dreg_bucket b;
+			if (begin == 1 && n > 1) {           /* element 0 alone in its bucket -> quirk for this (second) run */
+				b.index_begin = -1; b.index_end = p + 1; b.number_of_points = 0;
+			} else {
+				b.index_begin = begin; b.index_end = p + 1; b.number_of_points = p + 1 - begin;
+			}
+			buckets[k] = b;
+		}
+	}
+}
+
+/* gather by an externally supplied reference-layout table (stage-level m3dreg_nn_search) */
+__global__ void k_gather_by_table(const m3dreg_hash_element *__restrict__ table, int n,
+		const float4 *__restrict__ g_xyzl, const float4 *__restrict__ g_nrm,
+		float4 *__restrict__ s_xyzl, float4 *__restrict__ s_nrm, uint32_t *__restrict__ vals)
+{
+	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+		int v = table[p].index_of_point;
+		vals[p] = (uint32_t)v;
+		s_xyzl[p] = __ldg(g_xyzl + v);
+		s_nrm[p] = __ldg(g_nrm + v);
+	}
+}
+
+/* ---- semantic nearest neighbour (kernel_semanticNearestNeighborSearch, lesson_16.cu:531-703) ------------- */
+
+/* The reference's angle gate, written exactly as upstream (lesson_16.cu:666-671) so nvcc inlines the same
+ * acosf code: acos -> *180.0f (f32) -> /M_PI (f64) -> f32 -> abs -> < 90.0f.  Evaluated only for candidates that
+ * already passed the label, radius and improvement tests (all gates are a pure conjunction, so order is free). */
+__device__ __forceinline__ bool angle_gate(float dot)
+{
+	float angle = acosf(dot);
+	float angled = angle * 180.0f / M_PI;
+	if (angled < 0) angled = -angled;
+	return angled < 90.0f;
+}
+
+struct NNQuery {
+	float x, y, z, nx, ny, nz, r2;
+	int label;
+	float best;
+	int best_l;
+};
+
+/* Scan one bucket's (sub-sampled) candidates.  Visit order in the reference is ascending sorted position l
+ * (cells are visited in ascending linear index and the table is sorted by it), and the update is a strict `<`,
+ * so the reference result is the lexicographic minimum of (dist, l) over admissible candidates.  Keeping that
+ * pair lets cells be visited in any order and skipped when provably useless. */
+__device__ __forceinline__ void nn_visit_bucket(NNQuery &q, const m3dreg_bucket *__restrict__ buckets, int cell, int cap, int n_first,
+		const float4 *__restrict__ s_xyzl, const float4 *__restrict__ s_nrm)
+{
+	const int *bp = reinterpret_cast<const int *>(buckets + cell);
+	int npts = __ldg(bp + 2);
+	if (npts <= 0 || cap <= 0) return;
+	int iter = 1;
+	if (cap < npts) { iter = npts / cap; if (iter <= 0) iter = 1; }
+	int lb = __ldg(bp), le = __ldg(bp + 1);
+	for (int l = lb; l < le; l += iter) {
+		if (l < 0 || l >= n_first) continue;
+		float4 c = __ldg(s_xyzl + l);
+		float dx = __fsub_rn(q.x, c.x), dy = __fsub_rn(q.y, c.y), dz = __fsub_rn(q.z, c.z);
+		float dist = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+		if (__float_as_int(c.w) == q.label && dist <= q.r2 && (dist < q.best || (dist == q.best && l < q.best_l))) {
+			float4 cn = __ldg(s_nrm + l);
+			float dot = __fmaf_rn(q.nz, cn.z, __fmaf_rn(q.nx, cn.x, __fmul_rn(q.ny, cn.y)));
+			if (angle_gate(dot)) { q.best = dist; q.best_l = l; }
+		}
+	}
+}
+
+/* Conservative per-axis gap between the query and the slab of cells at offset -1 / +1 (rounded DOWN to float).
+ * A point stored in cell c satisfies trunc(fl(fl(v-min)/res)) == c; with two roundings of relative error 2^-24,
+ * (v-min) < ix*res*(1+2^-21) for cells <= ix-1 and (v-min) >= (ix+1)*res*(1-2^-21) for cells >= ix+1.
+ * A factor 2^-20 is used.  fl(q - v) is the correctly rounded true difference, rounding is monotone and the gap
+ * is a float, so |fl(q-v)| >= gap, hence fma(gz,gz,fma(gx,gx,gy*gy)) <= the reference's dist for every
+ * candidate of that cell: skipping a cell whose bound exceeds the current best (or r^2) cannot change the result. */
+__device__ __forceinline__ void axis_gaps(float q, float mn, float res, int ic, float &g_lo, float &g_hi)
+{
+	const double eps = 9.5367431640625e-07; /* 2^-20 */
+	double dq = (double)q - (double)mn;
+	double up = (double)ic * (double)res * (1.0 + eps);          /* exclusive upper bound of cells <= ic-1 */
+	double lo = (double)(ic + 1) * (double)res * (1.0 - eps);    /* inclusive lower bound of cells >= ic+1 */
+	double a = dq - up, b = lo - dq;
+	g_lo = a > 0.0 ? __double2float_rd(a) : 0.0f;
+	g_hi = b > 0.0 ? __double2float_rd(b) : 0.0f;
+}
+
+/* v1: one thread per query, candidates read from the sorted SoA copy of the first cloud (contiguous per bucket). */
+__global__ void __launch_bounds__(256) k_nn_search(const float4 *__restrict__ q_xyzl, const float4 *__restrict__ q_nrm, int n_second,
+		const float4 *__restrict__ s_xyzl, const float4 *__restrict__ s_nrm, const uint32_t *__restrict__ s_vals, int n_first,
+		const m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp,
+		float search_radius, int max_inner, int max_outer, int prune,
+		int *__restrict__ nn, unsigned long long *__restrict__ label_counts)
+{
+	__shared__ unsigned int s_cnt[4];
+	if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+	__syncthreads();
+	int qi = blockIdx.x * blockDim.x + threadIdx.x;
+	int result = -1;
+	int qlabel = -1;
+	long long nb = gp->number_of_buckets;
+	if (qi < n_second && nb > 0) {
+		float4 p = __ldg(q_xyzl + qi), pn = __ldg(q_nrm + qi);
+		qlabel = __float_as_int(p.w);
+		float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
+		bool inside = !(p.x < mnx || p.x > gp->bounding_box_max_X) && !(p.y < mny || p.y > gp->bounding_box_max_Y) &&
+				!(p.z < mnz || p.z > gp->bounding_box_max_Z);
+		if (inside) {
+			float rx = gp->resolution_X, ry = gp->resolution_Y, rz = gp->resolution_Z;
+			int nbx = gp->number_of_buckets_X, nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
+			int ix = cell_of(p.x, mnx, rx), iy = cell_of(p.y, mny, ry), iz = cell_of(p.z, mnz, rz);
+			int home = ix * nby * nbz + iy * nbz + iz;
+			if (home >= 0 && (long long)home < nb) {
+				NNQuery q;
+				q.x = p.x; q.y = p.y; q.z = p.z; q.nx = pn.x; q.ny = pn.y; q.nz = pn.z;
+				q.r2 = __fmul_rn(search_radius, search_radius);
+				q.label = qlabel;
+				q.best = 100000000.0f;
+				q.best_l = 0x7fffffff;
+				int sx = ix == 0 ? 0 : -1, sy = iy == 0 ? 0 : -1, sz = iz == 0 ? 0 : -1;
+				int stx = ix == nbx - 1 ? 1 : 2, sty = iy == nby - 1 ? 1 : 2, stz = iz == nbz - 1 ? 1 : 2;
+				float gx[3], gy[3], gz[3];
+				gx[1] = gy[1] = gz[1] = 0.0f;
+				if (prune) {
+					axis_gaps(p.x, mnx, rx, ix, gx[0], gx[2]);
+					axis_gaps(p.y, mny, ry, iy, gy[0], gy[2]);
+					axis_gaps(p.z, mnz, rz, iz, gz[0], gz[2]);
+					nn_visit_bucket(q, buckets, home, max_inner, n_first, s_xyzl, s_nrm);
+				} else {
+					gx[0] = gx[2] = gy[0] = gy[2] = gz[0] = gz[2] = 0.0f;
+				}
+				for (int i = sx; i < stx; i++)
+				for (int j = sy; j < sty; j++)
+				for (int k = sz; k < stz; k++) {
+					int cell = home + i * nby * nbz + j * nbz + k;
+					if (cell < 0 || (long long)cell >= nb) continue;
+					if (prune) {
+						if (cell == home) continue;
+						float lbd = __fmaf_rn(gz[k + 1], gz[k + 1], __fmaf_rn(gx[i + 1], gx[i + 1], __fmul_rn(gy[j + 1], gy[j + 1])));
+						if (lbd > q.best || lbd > q.r2) continue;
+					}
+					nn_visit_bucket(q, buckets, cell, cell == home ? max_inner : max_outer, n_first, s_xyzl, s_nrm);
+				}
+				if (q.best_l != 0x7fffffff) result = (int)__ldg(s_vals + q.best_l);
+			}
+		}
+	}
+	if (qi < n_second) nn[qi] = result;
+	if (label_counts) {
+		if (result >= 0 && qlabel >= 0 && qlabel < 4) atomicAdd(&s_cnt[qlabel], 1u);
+		__syncthreads();
+		if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(&label_counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+	}
+}
+
+/* ---- normal equations: fused fp64 reduction, never materialising A / P / AtP ------------------------------
+ * (replaces kernel_fill_A_l_cuda, kernel_cudaCompute_AtP and both DGEMMs; lesson_16.cu:245-439, AXB:407-428)
+ *
+ * With A_k = -[I | J_k] and J_k linear in the local point p0, all of AtPA / AtPl follow from
+ * pose-independent weighted raw moments:
+ *   S = sum w,  M1 = sum w p0,  M2 = sum w p0 p0^T (6),  L1 = sum w l,  L2 = sum w p0 l^T (9)   -> 22 sums.
+ * Every thread accumulates them in registers over a grid-stride loop, warps reduce with shuffles, the block
+ * writes one partial row, and the LAST block to finish (atomic ticket) adds the rows in fixed order, forms the
+ * 6x6 system for the current Euler angles, applies the observation gate, runs the Cholesky solve and updates the
+ * pose — so the iteration never returns to the host. */
+
+struct Moments {
+	double v[kMomentCount];
+	__device__ __forceinline__ void clear()
+	{
+#pragma unroll
+		for (int i = 0; i < kMomentCount; i++) v[i] = 0.0;
+	}
+	__device__ __forceinline__ void add(double w, double x, double y, double z, double lx, double ly, double lz)
+	{
+		double wx = w * x, wy = w * y, wz = w * z;
+		v[0] += w;
+		v[1] += wx; v[2] += wy; v[3] += wz;
+		v[4] = fma(wx, x, v[4]); v[5] = fma(wx, y, v[5]); v[6] = fma(wx, z, v[6]);
+		v[7] = fma(wy, y, v[7]); v[8] = fma(wy, z, v[8]); v[9] = fma(wz, z, v[9]);
+		v[10] = fma(w, lx, v[10]); v[11] = fma(w, ly, v[11]); v[12] = fma(w, lz, v[12]);
+		v[13] = fma(wx, lx, v[13]); v[14] = fma(wx, ly, v[14]); v[15] = fma(wx, lz, v[15]);
+		v[16] = fma(wy, lx, v[16]); v[17] = fma(wy, ly, v[17]); v[18] = fma(wy, lz, v[18]);
+		v[19] = fma(wz, lx, v[19]); v[20] = fma(wz, ly, v[20]); v[21] = fma(wz, lz, v[21]);
+		v[22] += 1.0;
+	}
+};
+
+/* 6x6 system (28-double packing) from moments and Euler angles.  R = Rx(om) Ry(fi) Rz(ka) (lesson_16.cu:278-293);
+ * C[r][c] is the coefficient 3-vector of J[r][c] = dR p0 / d(om,fi,ka) (lesson_16.cu:310-353). */
+__device__ __host__ inline void moments_to_neq(const double *mo, double om, double fi, double ka, double *neq)
+{
+	double so = sin(om), co = cos(om), sf = sin(fi), cf = cos(fi), sk = sin(ka), ck = cos(ka);
+	double R11 = cf * ck, R12 = -cf * sk;
+	double R21 = co * sk + so * sf * ck, R22 = co * ck - so * sf * sk, R23 = -so * cf;
+	double R31 = so * sk - co * sf * ck, R32 = so * ck + co * sf * sk, R33 = co * cf;
+	double C[3][3][3] = {
+		{{0, 0, 0}, {-sf * ck, sf * sk, cf}, {R12, -R11, 0}},
+		{{-R31, -R32, -R33}, {so * cf * ck, -so * cf * sk, so * sf}, {R22, -R21, 0}},
+		{{R21, R22, R23}, {-co * cf * ck, co * cf * sk, -co * sf}, {R32, -R31, 0}}};
+	double S = mo[0];
+	const double *M1 = mo + 1;
+	double M2[3][3] = {{mo[4], mo[5], mo[6]}, {mo[5], mo[7], mo[8]}, {mo[6], mo[8], mo[9]}};
+	const double *L1 = mo + 10;
+	const double *L2 = mo + 13;   /* L2[i*3+r] = sum w p0_i l_r */
+	double N[6][6], b[6];
+	for (int i = 0; i < 6; i++) { b[i] = 0; for (int j = 0; j < 6; j++) N[i][j] = 0; }
+	for (int r = 0; r < 3; r++) {
+		N[r][r] = S;
+		b[r] = -L1[r];
+		for (int c = 0; c < 3; c++) {
+			double s = 0;
+			for (int i = 0; i < 3; i++) s += C[r][c][i] * M1[i];
+			N[r][3 + c] = s;
+		}
+	}
+	for (int c = 0; c < 3; c++) {
+		for (int c2 = c; c2 < 3; c2++) {
+			double s = 0;
+			for (int r = 0; r < 3; r++)
+				for (int i = 0; i < 3; i++) {
+					double t = 0;
+					for (int j = 0; j < 3; j++) t += M2[i][j] * C[r][c2][j];
+					s += C[r][c][i] * t;
+				}
+			N[3 + c][3 + c2] = s;
+		}
+		double s = 0;
+		for (int r = 0; r < 3; r++)
+			for (int i = 0; i < 3; i++) s += C[r][c][i] * L2[i * 3 + r];
+		b[3 + c] = -s;
+	}
+	int k = 0;
+	for (int i = 0; i < 6; i++)
+		for (int j = i; j < 6; j++) neq[k++] = N[i][j];
+	for (int i = 0; i < 6; i++) neq[k++] = b[i];
+	neq[k] = mo[22];
+}
+
+/* Lower Cholesky + two triangular solves (linearSolverCHOL, AXB:484-539) of the dof-subsystem of a packed system.
+ * dof 6: all unknowns; dof 4: {tx,ty,tz,ka} (fill_A_l_4DOFcuda keeps columns 0,1,2,5, lesson_16.cu:493-495).
+ * Returns 0 or M3DREG_E_NOT_SPD. */
+__device__ __host__ inline int solve_packed(const double *neq, int dof, double *x)
+{
+	const int sel6[6] = {0, 1, 2, 3, 4, 5}, sel4[4] = {0, 1, 2, 5};
+	const int *sel = dof == 6 ? sel6 : sel4;
+	double full[6][6];
+	int k = 0;
+	for (int i = 0; i < 6; i++)
+		for (int j = i; j < 6; j++) { full[i][j] = neq[k]; full[j][i] = neq[k]; k++; }
+	double A[6][6], b[6], L[6][6], y[6];
+	for (int i = 0; i < dof; i++) {
+		b[i] = neq[21 + sel[i]];
+		for (int j = 0; j < dof; j++) { A[i][j] = full[sel[i]][sel[j]]; L[i][j] = 0; }
+	}
+	for (int j = 0; j < dof; j++) {
+		double d = A[j][j];
+		for (int c = 0; c < j; c++) d -= L[j][c] * L[j][c];
+		if (!(d > 0.0)) return M3DREG_E_NOT_SPD;
+		d = sqrt(d);
+		L[j][j] = d;
+		for (int i = j + 1; i < dof; i++) {
+			double s = A[i][j];
+			for (int c = 0; c < j; c++) s -= L[i][c] * L[j][c];
+			L[i][j] = s / d;
+		}
+	}
+	for (int i = 0; i < dof; i++) {
+		double s = b[i];
+		for (int c = 0; c < i; c++) s -= L[i][c] * y[c];
+		y[i] = s / L[i][i];
+	}
+	for (int i = dof - 1; i >= 0; i--) {
+		double s = y[i];
+		for (int c = i + 1; c < dof; c++) s -= L[c][i] * x[c];
+		x[i] = s / L[i][i];
+	}
+	return 0;
+}
+
+/* Matrix4ToEuler / EulerToMatrix (cudaWrapper.cpp:470-514), row-major 4x4.  Double transcendental functions
+ * rounded to float, identical text in oracle/m3d_oracle.c so both sides round the same way; upstream's Eigen float
+ * quaternion path cannot be reproduced to the last ulp (Eigen absent) — tolerance parity, see DESIGN.md. */
+__device__ __host__ inline void matrix4_to_euler(const float *m, float *omfika, float *xyz)
+{
+	const double kPi = 3.14159265358979323846;
+	double trX, trY;
+	if (m[0] > 0.0) omfika[1] = (float)asin((double)m[2]);
+	else omfika[1] = (float)(kPi - asin((double)m[2]));
+	double C = cos((double)omfika[1]);
+	if (fabs(C) > 0.005) {
+		trX = m[10] / C; trY = -m[6] / C;
+		omfika[0] = (float)atan2(trY, trX);
+		trX = m[0] / C; trY = -m[1] / C;
+		omfika[2] = (float)atan2(trY, trX);
+	} else {
+		omfika[0] = 0.0f;
+		trX = m[5]; trY = m[4];
+		omfika[2] = (float)atan2(trY, trX);
+	}
+	xyz[0] = m[3]; xyz[1] = m[7]; xyz[2] = m[11];
+}
+
+__device__ __host__ inline void euler_to_matrix(const float *omfika, const float *xyz, float *m)
+{
+	float hx = 0.5f * omfika[0], hy = 0.5f * omfika[1], hz = 0.5f * omfika[2];
+	float ax = (float)sin((double)hx), aw = (float)cos((double)hx);
+	float by = (float)sin((double)hy), bw = (float)cos((double)hy);
+	float cz = (float)sin((double)hz), cw = (float)cos((double)hz);
+#ifdef __CUDA_ARCH__
+#define M3D_MUL(a, b) __fmul_rn(a, b)
+#define M3D_ADD(a, b) __fadd_rn(a, b)
+#define M3D_SUB(a, b) __fsub_rn(a, b)
+#else
+#define M3D_MUL(a, b) ((a) * (b))
+#define M3D_ADD(a, b) ((a) + (b))
+#define M3D_SUB(a, b) ((a) - (b))
+#endif
+	float w1 = M3D_MUL(aw, bw), x1 = M3D_MUL(ax, bw), y1 = M3D_MUL(aw, by), z1 = M3D_MUL(ax, by);
+	float w = M3D_SUB(M3D_MUL(w1, cw), M3D_MUL(z1, cz));
+	float x = M3D_ADD(M3D_MUL(x1, cw), M3D_MUL(y1, cz));
+	float y = M3D_SUB(M3D_MUL(y1, cw), M3D_MUL(x1, cz));
+	float z = M3D_ADD(M3D_MUL(w1, cz), M3D_MUL(z1, cw));
+	float tx = M3D_MUL(2.0f, x), ty = M3D_MUL(2.0f, y), tz = M3D_MUL(2.0f, z);
+	float twx = M3D_MUL(tx, w), twy = M3D_MUL(ty, w), twz = M3D_MUL(tz, w);
+	float txx = M3D_MUL(tx, x), txy = M3D_MUL(ty, x), txz = M3D_MUL(tz, x);
+	float tyy = M3D_MUL(ty, y), tyz = M3D_MUL(tz, y), tzz = M3D_MUL(tz, z);
+	m[0] = M3D_SUB(1.0f, M3D_ADD(tyy, tzz)); m[1] = M3D_SUB(txy, twz); m[2] = M3D_ADD(txz, twy); m[3] = xyz[0];
+	m[4] = M3D_ADD(txy, twz); m[5] = M3D_SUB(1.0f, M3D_ADD(txx, tzz)); m[6] = M3D_SUB(tyz, twx); m[7] = xyz[1];
+	m[8] = M3D_SUB(txz, twy); m[9] = M3D_ADD(tyz, twx); m[10] = M3D_SUB(1.0f, M3D_ADD(txx, tyy)); m[11] = xyz[2];
+	m[12] = 0.0f; m[13] = 0.0f; m[14] = 0.0f; m[15] = 1.0f;
+#undef M3D_MUL
+#undef M3D_ADD
+#undef M3D_SUB
+}
+
+/* Start of an iteration of registerLastArrivedScan (gpu6DSLAM.cpp:276-291): Euler round trip of the stored pose. */
+__device__ inline void pose_prepare(PoseState *ps)
+{
+	float of[3], t[3];
+	matrix4_to_euler(ps->m, of, t);
+	euler_to_matrix(of, t, ps->pose1);
+	ps->pose6[0] = t[0]; ps->pose6[1] = t[1]; ps->pose6[2] = t[2];
+	ps->pose6[3] = of[0]; ps->pose6[4] = of[1]; ps->pose6[5] = of[2];
+}
+
+__global__ void k_pose_prepare(PoseState *ps)
+{
+	if (threadIdx.x == 0 && blockIdx.x == 0) pose_prepare(ps);
+}
+
+/* Per-observation sources for the moment reduction. */
+struct ObsFromNN {   /* fused path: nn[] + clouds (gpu6DSLAM.cpp:323-398 done on the device) */
+	const int *nn;
+	const float4 *q_xyzl;       /* queries (second cloud, global)           */
+	const float4 *g_xyzl;       /* first cloud, global, original order      */
+	const float4 *l_xyzl;       /* first cloud, local, original order       */
+	const unsigned long long *label_counts;
+	float weight[4];
+	__device__ __forceinline__ bool get(int i, const float *wl, double &w, double &x, double &y, double &z, double &lx, double &ly, double &lz) const
+	{
+		int j = __ldg(nn + i);
+		if (j < 0) return false;
+		float4 p2 = __ldg(q_xyzl + i), p1 = __ldg(g_xyzl + j), p0 = __ldg(l_xyzl + j);
+		int label = __float_as_int(p2.w);
+		w = (label >= 0 && label < 4) ? (double)wl[label] : 0.0;
+		x = p0.x; y = p0.y; z = p0.z;
+		lx = (double)__fsub_rn(p1.x, p2.x); ly = (double)__fsub_rn(p1.y, p2.y); lz = (double)__fsub_rn(p1.z, p2.z);
+		return true;
+	}
+};
+
+struct ObsFromList { /* stage-level path: the reference's obs_nn_t array */
+	const m3dreg_obs_nn *obs;
+	__device__ __forceinline__ bool get(int i, const float *, double &w, double &x, double &y, double &z, double &lx, double &ly, double &lz) const
+	{
+		const float *o = reinterpret_cast<const float *>(obs + i);
+		lx = __ldg(o); ly = __ldg(o + 1); lz = __ldg(o + 2);
+		x = __ldg(o + 3); y = __ldg(o + 4); z = __ldg(o + 5);
+		w = __ldg(o + 6);
+		return true;
+	}
+};
+
+/* What the last block does once all partial rows are in. */
+struct FinalizeArgs {
+	PoseState *ps;            /* pose state to read Euler angles from / update (may be 0: only write neq_out)      */
+	double *neq_out;          /* 28 doubles, overwritten (mode 0) or accumulated into (mode 1)                      */
+	int accumulate;           /* 1: neq_out += (sweep)                                                               */
+	int solve;                /* 1: gate + Cholesky + pose update + next-iteration pose_prepare                      */
+	int dof;
+	int obs_threshold;
+	const double *pose6_in;   /* Euler angles when ps == 0                                                           */
+	uint32_t *bounds_reset;   /* reset for the next iteration (may be 0)                                             */
+	unsigned long long *label_counts_reset;
+};
+
+constexpr int kNeqThreads = 256;
+
+template <class Src>
+__global__ void __launch_bounds__(kNeqThreads) k_normal_equations(Src src, int n, double *__restrict__ partials,
+		unsigned int *__restrict__ ticket, FinalizeArgs fin)
+{
+	__shared__ double sm[kNeqThreads / 32][kMomentCount];
+	__shared__ float wl[4];
+	__shared__ bool is_last;
+	if (threadIdx.x < 4) {
+		float w = 0.0f;
+		if constexpr (std::is_same<Src, ObsFromNN>::value) {
+			unsigned long long c = src.label_counts[threadIdx.x];
+			/* P = weight / count, float / int -> float (gpu6DSLAM.cpp:377-393) */
+			w = c ? __fdiv_rn(src.weight[threadIdx.x], (float)(int)c) : 0.0f;
+		}
+		wl[threadIdx.x] = w;
+	}
+	__syncthreads();
+	Moments mo;
+	mo.clear();
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		double w, x, y, z, lx, ly, lz;
+		if (src.get(i, wl, w, x, y, z, lx, ly, lz)) mo.add(w, x, y, z, lx, ly, lz);
+	}
+	int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+	for (int k = 0; k < kMomentCount; k++) {
+		double s = warp_sum(mo.v[k]);
+		if (lane == 0) sm[wid][k] = s;
+	}
+	__syncthreads();
+	if (threadIdx.x < kMomentCount) {
+		double s = 0;
+#pragma unroll
+		for (int k = 0; k < kNeqThreads / 32; k++) s += sm[k][threadIdx.x];
+		partials[(size_t)blockIdx.x * kMomentCount + threadIdx.x] = s;
+	}
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned int t = atomicAdd(ticket, 1u);
+		is_last = (t == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (!is_last) return;
+	__threadfence();
+	/* deterministic final reduction: fixed row order */
+	__shared__ double tot[kMomentCount];
+	if (threadIdx.x < kMomentCount) {
+		double s = 0;
+		for (unsigned int b = 0; b < gridDim.x; b++) s += __ldcg(partials + (size_t)b * kMomentCount + threadIdx.x);
+		tot[threadIdx.x] = s;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		*ticket = 0;
+		double neq[kNeqCount];
+		const double *p6 = fin.ps ? fin.ps->pose6 : fin.pose6_in;
+		moments_to_neq(tot, p6[3], p6[4], p6[5], neq);
+		if (fin.neq_out) {
+			for (int k = 0; k < kNeqCount; k++) fin.neq_out[k] = fin.accumulate ? fin.neq_out[k] + neq[k] : neq[k];
+		}
+		if (fin.solve && fin.ps) {
+			PoseState *ps = fin.ps;
+			for (int k = 0; k < kNeqCount; k++) ps->neq[k] = neq[k];
+			long long n_obs = (long long)(tot[22] + 0.5);
+			ps->n_obs = n_obs;
+			int status = M3DREG_E_TOO_FEW_OBS;
+			double x[6] = {0, 0, 0, 0, 0, 0};
+			if (n_obs > (long long)fin.obs_threshold) {                       /* gpu6DSLAM.cpp:402 */
+				status = solve_packed(neq, fin.dof, x);
+				if (status == 0) {
+					/* registerLS tail (cudaWrapper.cpp:574-579 / 641-646) + EulerToMatrix (gpu6DSLAM.cpp:408-413) */
+					ps->pose6[0] += x[0]; ps->pose6[1] += x[1]; ps->pose6[2] += x[2];
+					if (fin.dof == 6) { ps->pose6[3] += x[3]; ps->pose6[4] += x[4]; ps->pose6[5] += x[5]; }
+					else ps->pose6[5] += x[3];
+					float of[3] = {(float)ps->pose6[3], (float)ps->pose6[4], (float)ps->pose6[5]};
+					float t[3] = {(float)ps->pose6[0], (float)ps->pose6[1], (float)ps->pose6[2]};
+					euler_to_matrix(of, t, ps->m);
+				}
+			}
+			for (int k = 0; k < 6; k++) ps->x[k] = x[k];
+			ps->status = status;
+			ps->iterations += 1;
+			pose_prepare(ps);   /* next iteration's Euler round trip */
+		}
+		if (fin.bounds_reset) {
+			fin.bounds_reset[0] = fin.bounds_reset[1] = fin.bounds_reset[2] = 0xFFFFFFFFu;
+			fin.bounds_reset[3] = fin.bounds_reset[4] = fin.bounds_reset[5] = 0u;
+		}
+		if (fin.label_counts_reset) {
+			fin.label_counts_reset[0] = fin.label_counts_reset[1] = fin.label_counts_reset[2] = fin.label_counts_reset[3] = 0ull;
+		}
+	}
+}
+
+/* Standalone device Cholesky (m3dreg_solve_chol): column-major dof x dof in, x out. */
+__global__ void k_solve_dense(const double *A, const double *b, int dof, double *x, int *status)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	double neq[kNeqCount];
+	const int sel6[6] = {0, 1, 2, 3, 4, 5}, sel4[4] = {0, 1, 2, 5};
+	const int *sel = dof == 6 ? sel6 : sel4;
+	for (int k = 0; k < kNeqCount; k++) neq[k] = 0;
+	/* embed into the 6-DOF packing; unused rows get identity so the packed solver's selection is well defined */
+	double full[6][6];
+	for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) full[i][j] = (i == j) ? 1.0 : 0.0;
+	for (int i = 0; i < dof; i++) for (int j = 0; j < dof; j++) full[sel[i]][sel[j]] = A[i + j * dof];
+	int k = 0;
+	for (int i = 0; i < 6; i++) for (int j = i; j < 6; j++) neq[k++] = full[i][j];
+	for (int i = 0; i < dof; i++) neq[21 + sel[i]] = b[i];
+	double xs[6] = {0, 0, 0, 0, 0, 0};
+	*status = solve_packed(neq, dof, xs);
+	for (int i = 0; i < dof; i++) x[i] = xs[i];
+}
+
+/* Sweep solve (registerAll tail, gpu6DSLAM.cpp:572-593) for scans [begin,end): one thread per scan. */
+__global__ void k_sweep_solve(const double *__restrict__ neq, int begin, int end, float *__restrict__ poses,
+		int dof, int obs_threshold, int *__restrict__ status_out)
+{
+	int s = begin + blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= end) return;
+	float *m = poses + 16 * (size_t)s;
+	float of[3], t[3];
+	matrix4_to_euler(m, of, t);
+	double p6[6] = {t[0], t[1], t[2], of[0], of[1], of[2]};
+	const double *q = neq + (size_t)s * kNeqCount;
+	long long n_obs = (long long)(q[27] + 0.5);
+	int status = M3DREG_E_TOO_FEW_OBS;
+	if (n_obs > (long long)obs_threshold) {
+		double x[6] = {0, 0, 0, 0, 0, 0};
+		double loc[kNeqCount];
+		for (int k = 0; k < kNeqCount; k++) loc[k] = q[k];
+		status = solve_packed(loc, dof, x);
+		if (status == 0) {
+			p6[0] += x[0]; p6[1] += x[1]; p6[2] += x[2];
+			if (dof == 6) { p6[3] += x[3]; p6[4] += x[4]; p6[5] += x[5]; }
+			else p6[5] += x[3];
+		}
+	}
+	float of2[3] = {(float)p6[3], (float)p6[4], (float)p6[5]};
+	float t2[3] = {(float)p6[0], (float)p6[1], (float)p6[2]};
+	euler_to_matrix(of2, t2, m);     /* replaced by its round trip even when the gate fails (gpu6DSLAM.cpp:586-593) */
+	if (status_out) status_out[s] = status;
+}
+
+__global__ void k_zero_f64(double *p, int n)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0.0;
+}
+
+} /* namespace m3d */

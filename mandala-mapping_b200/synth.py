@@ -319,6 +319,17 @@ def slam_scans(n_scans: int, kind: str = "hdl32", seed: int = 42, spacing: float
     return scans, truth.astype(np.float32), init
 
 
+def concat_points(scans) -> np.ndarray:
+    """Concatenate point arrays keeping the 40-byte layout (np.concatenate re-packs padded dtypes to 38 B)."""
+    out = np.zeros(sum(len(s) for s in scans), dtype=POINT_DTYPE)
+    o = 0
+    for s in scans:
+        assert s.dtype.itemsize == 40
+        out[o:o + len(s)] = s
+        o += len(s)
+    return out
+
+
 def random_cloud(n: int, seed: int = 0, extent=(10.0, 8.0, 3.0), n_labels: int = 4, unit_normals: bool = True) -> np.ndarray:
     """Unstructured random cloud for edge-case parity tests (uniform points, random normals/labels)."""
     rng = np.random.Generator(np.random.PCG64(seed))

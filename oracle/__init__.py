@@ -84,6 +84,8 @@ def ref() -> C.CDLL:
 
 def _ptr(a: np.ndarray):
     assert a.flags["C_CONTIGUOUS"]
+    if a.dtype.names and "normal_x" in a.dtype.names:
+        assert a.dtype.itemsize == 40, "point array lost its 40-byte layout (np.concatenate re-packs it)"
     return a.ctypes.data_as(_P)
 
 
@@ -212,7 +214,7 @@ def icp_iteration(first_local, second_global, pose, params: RegParams, want_nn=F
 def register_all_sweep(scans, poses, params: RegParams, pair_thr=10.0):
     off = np.zeros(len(scans) + 1, dtype=np.int64)
     off[1:] = np.cumsum([len(s) for s in scans])
-    allp = np.concatenate(scans)
+    allp = _synth.concat_points(scans)
     poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(len(scans), 16).copy()
     neq = np.zeros((len(scans), 28))
     status = np.zeros(len(scans), dtype=np.int32)

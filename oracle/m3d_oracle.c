@@ -486,9 +486,11 @@ void orc_matrix4_to_euler(const float *m, float *omfika, float *xyz)
 void orc_euler_to_matrix(const float *omfika, const float *xyz, float *m)
 {
 	float hx = 0.5f * omfika[0], hy = 0.5f * omfika[1], hz = 0.5f * omfika[2];
-	float ax = sinf(hx), aw = cosf(hx);        /* qx = (aw; ax,0,0) */
-	float by = sinf(hy), bw = cosf(hy);        /* qy = (bw; 0,by,0) */
-	float cz = sinf(hz), cw = cosf(hz);        /* qz = (cw; 0,0,cz) */
+	/* half-angle sin/cos evaluated in double and rounded to float (Eigen uses sinf/cosf; libm and CUDA
+	 * float versions differ in the last ulp, the double ones rounded to float practically never do) */
+	float ax = (float)sin((double)hx), aw = (float)cos((double)hx);        /* qx = (aw; ax,0,0) */
+	float by = (float)sin((double)hy), bw = (float)cos((double)hy);        /* qy = (bw; 0,by,0) */
+	float cz = (float)sin((double)hz), cw = (float)cos((double)hz);        /* qz = (cw; 0,0,cz) */
 	/* q1 = qx*qy */
 	float w1 = aw * bw, x1 = ax * bw, y1 = aw * by, z1 = ax * by;
 	/* q = q1*qz */

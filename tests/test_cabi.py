@@ -1,0 +1,83 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/m3dreg.h
+declares; without a GPU the product refuses to run (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "m3dreg.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(m3dreg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(pkg):
+    pkg.build()
+    names = _declared()
+    assert len(names) >= 30
+    assert sorted(pkg.EXPORTS) == names
+    out = subprocess.check_output(["nm", "-D", "--defined-only", pkg.LIB_PATH]).decode()
+    exported = set(re.findall(r" T (m3dreg_[a-z0-9_]+)", out))
+    assert set(names) <= exported
+    L = pkg.lib()
+    assert L.m3dreg_version() == 100
+    assert L.m3dreg_status_string(-3).decode().startswith("normal equations")
+
+
+def test_struct_layouts_match_header(pkg):
+    assert C.sizeof(pkg.RegParams) == 48
+    assert pkg.POINT_DTYPE.itemsize == 40 and pkg.GRID_PARAMS_DTYPE.itemsize == 64
+    # compile a tiny C program against the header to pin sizeof/offsetof
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "m3dreg.h"
+int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(m3dreg_point), sizeof(m3dreg_hash_element), sizeof(m3dreg_bucket),
+ sizeof(m3dreg_grid_params), offsetof(m3dreg_grid_params, number_of_buckets), sizeof(m3dreg_obs_nn), sizeof(m3dreg_reg_params),
+ offsetof(m3dreg_point, normal_x), offsetof(m3dreg_point, label)); return 0; }
+'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
+        vals = [int(v) for v in subprocess.check_output([os.path.join(d, "t")]).split()]
+    assert vals == [40, 8, 12, 64, 40, 28, 48, 20, 32]
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    st = pkg.lib().m3dreg_create(C.byref(h), 0)
+    assert st == pkg.E_NO_DEVICE and not h.value
+    with pytest.raises(pkg.M3dRegError):
+        pkg.Context(0)
+
+
+def test_host_euler_helpers_match_oracle(pkg, oracle):
+    rng = np.random.default_rng(3)
+    for _ in range(100):
+        o = rng.uniform(-1.3, 1.3, 3).astype(np.float32)
+        t = rng.uniform(-20, 20, 3).astype(np.float32)
+        m = pkg.euler_to_matrix(o, t)
+        assert np.array_equal(m, oracle.euler_to_matrix(o, t))
+        o2, t2 = pkg.matrix4_to_euler(m)
+        o3, t3 = oracle.matrix4_to_euler(m)
+        assert np.array_equal(o2, o3) and np.array_equal(t2, t3)
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through the oracle."""
+    pdir = os.path.join(ROOT, "mandala-mapping_b200")
+    for dp, _, files in os.walk(pdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "libm3d_oracle" not in txt and "libm3dref" not in txt, f
