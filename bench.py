@@ -243,7 +243,9 @@ def main():
     prm = pkg.default_params(res, dof=args.dof, mode=pkg.MODE_NDT if args.mode == "ndt" else pkg.MODE_ICP)
 
     ctx = pkg.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    # everything (kernels, NCCL, timing events) runs on ONE explicit non-default stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.scan_upload(0, first)
     ctx.scan_upload(1, second)
