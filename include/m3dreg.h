@@ -141,6 +141,15 @@ int  m3dreg_synchronize(m3dreg_ctx *ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches claim). */
 int64_t m3dreg_launch_count(const m3dreg_ctx *ctx);
 
+/* Diagnostic: switch the NN search's exact bucket pruning off (every query then walks all <= 27 buckets like the
+ * reference kernel does).  Results are identical either way (tests/test_gpu_stages.py::test_pruning_is_exact);
+ * only m3dreg_nn_search / m3dreg_semantic_nn_host honour it.  Default: on. */
+int m3dreg_set_pruning(m3dreg_ctx *ctx, int enabled);
+
+/* Diagnostic counter: number of candidate records the NN search staged (summed over warps; every staged candidate
+ * is tested by the 32 queries of the warp) since the last reset.  Reported by bench.py as evaluations per query. */
+int m3dreg_get_nn_evaluations(m3dreg_ctx *ctx, uint64_t *count_out, int reset);
+
 /* ---- stage-level entry points on DEVICE pointers (parity surface = reference L0) ---------- */
 
 /* ref: cudaCalculateGridParams (include/lesson_16.h:61-62, src/lesson_16.cu:23-106).

@@ -27,10 +27,22 @@ using namespace m3d;
 namespace {
 
 struct Scan {
-	float4 *xyzl = nullptr;
+	float4 *xyzl = nullptr;     /* original order: the order the grid's tie-break (ascending index) refers to   */
 	float4 *nrm = nullptr;
+	float4 *sx = nullptr;       /* cell-sorted copy, used when the scan plays the QUERY role (warp coherence)     */
+	float4 *sn = nullptr;
+	uint32_t *perm = nullptr;   /* perm[sorted position] = original index                                         */
 	int n = 0;
 	size_t cap = 0;
+	void release()
+	{
+		if (xyzl) cudaFree(xyzl);
+		if (nrm) cudaFree(nrm);
+		if (sx) cudaFree(sx);
+		if (sn) cudaFree(sn);
+		if (perm) cudaFree(perm);
+		xyzl = nrm = sx = sn = nullptr; perm = nullptr; n = 0; cap = 0;
+	}
 };
 
 template <class T>
@@ -70,14 +82,15 @@ struct m3dreg_ctx {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	int64_t launches = 0;
+	int prune = 1;               /* exact bucket pruning in the NN search (0 only for the equivalence test) */
 
 	std::vector<Scan> scans;
 
 	/* arena */
-	DevBuf<float4> g_xyzl, g_nrm, s_xyzl, s_nrm, q_xyzl, q_nrm, l_xyzl, l_nrm;
-	DevBuf<uint32_t> keys[2], vals[2], hist;
+	DevBuf<float4> g_xyzl, g_nrm, ci_xyzl, ci_nrm, co_xyzl, co_nrm, q_xyzl, q_nrm, l_xyzl, l_nrm;
+	DevBuf<uint32_t> keys[2], vals[2], hist, digit_tot;
 	DevBuf<m3dreg_bucket> buckets;
-	DevBuf<int> nn;
+	DevBuf<int> nn, nn_seq;
 	DevBuf<m3dreg_point> aos_a, aos_b;
 	DevBuf<m3dreg_obs_nn> obs;
 	DevBuf<double> partials;
@@ -92,6 +105,7 @@ struct m3dreg_ctx {
 	int *flags = nullptr;
 	unsigned long long *label_counts = nullptr;
 	unsigned int *ticket = nullptr;
+	unsigned long long *eval_counter = nullptr;   /* candidates staged by the NN search (warp-level), diagnostic */
 	double *scratch = nullptr;   /* 64 doubles */
 	float *mats = nullptr;       /* 32 floats  */
 	HostSmall *h = nullptr;      /* pinned */
@@ -99,6 +113,7 @@ struct m3dreg_ctx {
 	/* active fused loop (icp_begin .. icp_end) */
 	bool active = false;
 	const float4 *act_lx = nullptr, *act_ln = nullptr;
+	const uint32_t *act_perm = nullptr;
 	int act_n1 = 0, act_n2 = 0, act_sort_bits = 0;
 	m3dreg_reg_params act_prm;
 
@@ -173,8 +188,9 @@ int ensure_first(m3dreg_ctx *c, size_t n)
 	int e;
 	if ((e = c->g_xyzl.ensure(n))) return e;
 	if ((e = c->g_nrm.ensure(n))) return e;
-	if ((e = c->s_xyzl.ensure(n))) return e;
-	if ((e = c->s_nrm.ensure(n))) return e;
+	if ((e = c->ci_xyzl.ensure(n))) return e;
+	if ((e = c->ci_nrm.ensure(n))) return e;
+	if ((e = c->digit_tot.ensure(kRadixSize))) return e;
 	for (int k = 0; k < 2; k++) {
 		if ((e = c->keys[k].ensure(n))) return e;
 		if ((e = c->vals[k].ensure(n))) return e;
@@ -190,6 +206,7 @@ int ensure_second(m3dreg_ctx *c, size_t n)
 	if ((e = c->q_xyzl.ensure(n))) return e;
 	if ((e = c->q_nrm.ensure(n))) return e;
 	if ((e = c->nn.ensure(n))) return e;
+	if ((e = c->nn_seq.ensure(n))) return e;
 	return 0;
 }
 
@@ -212,9 +229,9 @@ int sort_by_bucket(m3dreg_ctx *c, int n, int bits, const m3dreg_grid_params *gp)
 		int shift = p * kRadixBits;
 		if (big) LAUNCH(c, k_radix_hist<16>, tiles, kSortThreads, c->keys[cur].p, n, shift, tiles, c->hist.p, gp);
 		else LAUNCH(c, k_radix_hist<4>, tiles, kSortThreads, c->keys[cur].p, n, shift, tiles, c->hist.p, gp);
-		LAUNCH(c, k_radix_scan, 1, 1024, c->hist.p, tiles * kRadixSize, gp);
-		if (big) LAUNCH(c, k_radix_scatter<16>, tiles, kSortThreads, c->keys[cur].p, c->vals[cur].p, c->keys[cur ^ 1].p, c->vals[cur ^ 1].p, n, shift, tiles, c->hist.p, gp);
-		else LAUNCH(c, k_radix_scatter<4>, tiles, kSortThreads, c->keys[cur].p, c->vals[cur].p, c->keys[cur ^ 1].p, c->vals[cur ^ 1].p, n, shift, tiles, c->hist.p, gp);
+		LAUNCH(c, k_radix_scan, kRadixSize, 256, c->hist.p, tiles, c->digit_tot.p, gp);
+		if (big) LAUNCH(c, k_radix_scatter<16>, tiles, kSortThreads, c->keys[cur].p, c->vals[cur].p, c->keys[cur ^ 1].p, c->vals[cur ^ 1].p, n, shift, tiles, c->hist.p, c->digit_tot.p, gp);
+		else LAUNCH(c, k_radix_scatter<4>, tiles, kSortThreads, c->keys[cur].p, c->vals[cur].p, c->keys[cur ^ 1].p, c->vals[cur ^ 1].p, n, shift, tiles, c->hist.p, c->digit_tot.p, gp);
 		cur ^= 1;
 	}
 	return cur;
@@ -231,6 +248,36 @@ void host_roundtrip_pose(const float *m, float *pose1, double *pose6)
 	}
 }
 
+/* Compact candidate arrays: the OUTER set aliases the INNER one when both caps are equal. */
+int ensure_candidates(m3dreg_ctx *c, size_t n1, int max_inner, int max_outer)
+{
+	int e;
+	if ((e = c->ci_xyzl.ensure(n1))) return e;
+	if ((e = c->ci_nrm.ensure(n1))) return e;
+	if (max_inner != max_outer) {
+		if ((e = c->co_xyzl.ensure(n1))) return e;
+		if ((e = c->co_nrm.ensure(n1))) return e;
+	}
+	return 0;
+}
+
+void compact_candidates(m3dreg_ctx *c, const uint32_t *keys, const uint32_t *vals, int n1, const m3dreg_bucket *buckets,
+		int max_inner, int max_outer)
+{
+	bool same = max_inner == max_outer;
+	LAUNCH(c, k_compact_candidates, grid_for(c, n1, 256), 256, keys, vals, n1, c->gp, buckets, c->g_xyzl.p, c->g_nrm.p,
+			max_inner, max_outer, c->ci_xyzl.p, c->ci_nrm.p, same ? c->ci_xyzl.p : c->co_xyzl.p, same ? c->ci_nrm.p : c->co_nrm.p);
+}
+
+void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *vals, int n1, const m3dreg_bucket *buckets,
+		float radius, int max_inner, int max_outer, int prune, int *nn_out, int *nn_seq, unsigned long long *label_counts)
+{
+	bool same = max_inner == max_outer;
+	LAUNCH(c, k_nn_search, (n2 + 255) / 256, 256, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
+			c->ci_xyzl.p, c->ci_nrm.p, same ? c->ci_xyzl.p : c->co_xyzl.p, same ? c->ci_nrm.p : c->co_nrm.p,
+			vals, n1, buckets, c->gp, radius, max_inner, max_outer, prune, nn_out, nn_seq, label_counts, c->eval_counter);
+}
+
 /* Grid of the (already transformed) first cloud in g_*: params (device) from bounds, keys, sort, dense table,
  * sorted SoA copy.  bounds must already hold the reduced box. */
 void build_grid_fused(m3dreg_ctx *c, int n1, const m3dreg_reg_params *prm, int sort_bits)
@@ -241,7 +288,8 @@ void build_grid_fused(m3dreg_ctx *c, int n1, const m3dreg_reg_params *prm, int s
 	int cur = sort_by_bucket(c, n1, sort_bits, c->gp);
 	LAUNCH(c, k_init_buckets, grid_for(c, (long long)c->buckets.cap * 3, 256), 256, c->buckets.p, c->gp, 0LL);
 	LAUNCH(c, k_finalize_grid, grid_for(c, n1, 256), 256, c->keys[cur].p, c->vals[cur].p, n1, c->gp, c->buckets.p,
-			c->g_xyzl.p, c->g_nrm.p, c->s_xyzl.p, c->s_nrm.p, (m3dreg_hash_element *)nullptr);
+			(m3dreg_hash_element *)nullptr);
+	compact_candidates(c, c->keys[cur].p, c->vals[cur].p, n1, c->buckets.p, prm->max_inner, prm->max_outer);
 	c->last_sorted = cur;
 }
 
@@ -295,11 +343,10 @@ void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int
 	if (prof) cudaEventRecord(c->pev[1], c->stream);
 	build_grid_fused(c, n1, prm, sort_bits);
 	if (prof) cudaEventRecord(c->pev[2], c->stream);
-	LAUNCH(c, k_nn_search, (n2 + 255) / 256, 256, c->q_xyzl.p, c->q_nrm.p, n2, c->s_xyzl.p, c->s_nrm.p,
-			c->vals[c->last_sorted].p, n1, c->buckets.p, c->gp, prm->search_radius, prm->max_inner, prm->max_outer, 1,
-			c->nn.p, c->label_counts);
+	launch_nn(c, c->act_perm, n2, c->vals[c->last_sorted].p, n1, c->buckets.p, prm->search_radius, prm->max_inner, prm->max_outer, 1,
+			c->nn.p, c->nn_seq.p, c->label_counts);
 	ObsFromNN src;
-	src.nn = c->nn.p; src.q_xyzl = c->q_xyzl.p; src.g_xyzl = c->g_xyzl.p; src.l_xyzl = lx; src.label_counts = c->label_counts;
+	src.nn = c->nn_seq.p; src.q_xyzl = c->q_xyzl.p; src.g_xyzl = c->g_xyzl.p; src.l_xyzl = lx; src.label_counts = c->label_counts;
 	for (int k = 0; k < 4; k++) src.weight[k] = prm->weight[k];
 	FinalizeArgs fin;
 	fin.ps = c->ps; fin.neq_out = nullptr; fin.accumulate = 0; fin.solve = 1; fin.dof = prm->dof;
@@ -376,7 +423,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	cudaEventCreate(&c->ev0);
 	cudaEventCreate(&c->ev1);
 	size_t small = sizeof(PoseState) + 8 * sizeof(uint32_t) + sizeof(m3dreg_grid_params) + FLAG_COUNT * sizeof(int) +
-			4 * sizeof(unsigned long long) + 16 + 64 * sizeof(double) + 32 * sizeof(float) + 256;
+			4 * sizeof(unsigned long long) + 32 + 64 * sizeof(double) + 32 * sizeof(float) + 256;
 	char *blk = nullptr;
 	e = cudaMalloc((void **)&blk, small);
 	if (e != cudaSuccess) { m3dreg_destroy(c); return (int)e; }
@@ -390,6 +437,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	c->bounds = (uint32_t *)take(8 * sizeof(uint32_t));
 	c->flags = (int *)take(FLAG_COUNT * sizeof(int));
 	c->ticket = (unsigned int *)take(16);
+	c->eval_counter = (unsigned long long *)take(16);
 	c->mats = (float *)take(32 * sizeof(float));
 	e = cudaMallocHost((void **)&c->h, sizeof(HostSmall));
 	if (e != cudaSuccess) { m3dreg_destroy(c); return (int)e; }
@@ -405,11 +453,11 @@ void m3dreg_destroy(m3dreg_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->dev);
 	if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-	for (auto &s : c->scans) { if (s.xyzl) cudaFree(s.xyzl); if (s.nrm) cudaFree(s.nrm); }
-	c->g_xyzl.release(); c->g_nrm.release(); c->s_xyzl.release(); c->s_nrm.release();
+	for (auto &s : c->scans) s.release();
+	c->g_xyzl.release(); c->g_nrm.release(); c->ci_xyzl.release(); c->ci_nrm.release(); c->co_xyzl.release(); c->co_nrm.release(); c->digit_tot.release();
 	c->q_xyzl.release(); c->q_nrm.release(); c->l_xyzl.release(); c->l_nrm.release();
 	for (int k = 0; k < 2; k++) { c->keys[k].release(); c->vals[k].release(); }
-	c->hist.release(); c->buckets.release(); c->nn.release(); c->aos_a.release(); c->aos_b.release();
+	c->hist.release(); c->buckets.release(); c->nn.release(); c->nn_seq.release(); c->aos_a.release(); c->aos_b.release();
 	c->obs.release(); c->partials.release(); c->table.release(); c->d_poses1.release(); c->d_pose6.release();
 	if (c->ps) cudaFree(c->ps);   /* base of the small block */
 	if (c->h) cudaFreeHost(c->h);
@@ -448,6 +496,24 @@ int m3dreg_synchronize(m3dreg_ctx *c)
 
 int64_t m3dreg_launch_count(const m3dreg_ctx *c) { return c ? c->launches : 0; }
 
+int m3dreg_get_nn_evaluations(m3dreg_ctx *c, uint64_t *count_out, int reset)
+{
+	if (!c || !count_out) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	CK(cudaMemcpyAsync(c->h->label_counts, c->eval_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+	if (reset) CK(cudaMemsetAsync(c->eval_counter, 0, sizeof(unsigned long long), c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	*count_out = (uint64_t)c->h->label_counts[0];
+	return 0;
+}
+
+int m3dreg_set_pruning(m3dreg_ctx *c, int enabled)
+{
+	if (!c) return M3DREG_E_INVALID_ARG;
+	c->prune = enabled ? 1 : 0;
+	return 0;
+}
+
 /* ---- stage-level entry points ------------------------------------------------------------------------ */
 
 int m3dreg_calculate_grid_params(m3dreg_ctx *c, const m3dreg_point *d_cloud, int n, float rx, float ry, float rz, float ext,
@@ -478,8 +544,7 @@ int m3dreg_calculate_grid(m3dreg_ctx *c, const m3dreg_point *d_cloud, int n, con
 	int cur = sort_by_bucket(c, n, bits_for(params->number_of_buckets), nullptr);
 	LAUNCH(c, k_init_buckets, grid_for(c, params->number_of_buckets * 3, 256), 256, d_buckets, (const m3dreg_grid_params *)nullptr,
 			(long long)params->number_of_buckets);
-	LAUNCH(c, k_finalize_grid, grid_for(c, n, 256), 256, c->keys[cur].p, c->vals[cur].p, n, (const m3dreg_grid_params *)nullptr, d_buckets,
-			(const float4 *)nullptr, (const float4 *)nullptr, (float4 *)nullptr, (float4 *)nullptr, d_table);
+	LAUNCH(c, k_finalize_grid, grid_for(c, n, 256), 256, c->keys[cur].p, c->vals[cur].p, n, (const m3dreg_grid_params *)nullptr, d_buckets, d_table);
 	c->last_valid = false;
 	CK(cudaStreamSynchronize(c->stream));   /* c->h->gp is reused by the next call */
 	return (int)cudaGetLastError();
@@ -498,9 +563,10 @@ int m3dreg_nn_search(m3dreg_ctx *c, const m3dreg_point *d_first, int n1, const m
 	CK(cudaMemcpyAsync(c->gp, &c->h->gp, sizeof(m3dreg_grid_params), cudaMemcpyHostToDevice, c->stream));
 	LAUNCH(c, k_unpack_points, (n1 + 255) / 256, 256, d_first, n1, c->g_xyzl.p, c->g_nrm.p);
 	LAUNCH(c, k_unpack_points, (n2 + 255) / 256, 256, d_second, n2, c->q_xyzl.p, c->q_nrm.p);
-	LAUNCH(c, k_gather_by_table, grid_for(c, n1, 256), 256, d_table, n1, c->g_xyzl.p, c->g_nrm.p, c->s_xyzl.p, c->s_nrm.p, c->vals[0].p);
-	LAUNCH(c, k_nn_search, (n2 + 255) / 256, 256, c->q_xyzl.p, c->q_nrm.p, n2, c->s_xyzl.p, c->s_nrm.p, c->vals[0].p, n1,
-			d_buckets, c->gp, search_radius, max_inner, max_outer, 1, d_nn, (unsigned long long *)nullptr);
+	if ((e = ensure_candidates(c, (size_t)n1, max_inner, max_outer))) return e;
+	LAUNCH(c, k_split_table, grid_for(c, n1, 256), 256, d_table, n1, c->keys[0].p, c->vals[0].p);
+	compact_candidates(c, c->keys[0].p, c->vals[0].p, n1, d_buckets, max_inner, max_outer);
+	launch_nn(c, nullptr, n2, c->vals[0].p, n1, d_buckets, search_radius, max_inner, max_outer, c->prune, d_nn, nullptr, nullptr);
 	c->last_valid = false;
 	CK(cudaStreamSynchronize(c->stream));
 	return (int)cudaGetLastError();
@@ -600,12 +666,13 @@ int m3dreg_semantic_nn_host(m3dreg_ctx *c, const m3dreg_point *first, int n1, co
 	m3dreg_reg_params prm;
 	memset(&prm, 0, sizeof(prm));
 	prm.bucket_size = bucket_size; prm.bbox_extension = ext; prm.search_radius = search_radius;
+	prm.max_inner = max_inner; prm.max_outer = max_outer;
+	if ((e = ensure_candidates(c, (size_t)n1, max_inner, max_outer))) return e;
 	int sort_bits = 0;
 	if ((e = plan_buckets(c, &prm, &sort_bits))) return e;
 	build_grid_fused(c, n1, &prm, sort_bits);
-	LAUNCH(c, k_nn_search, (n2 + 255) / 256, 256, c->q_xyzl.p, c->q_nrm.p, n2, c->s_xyzl.p, c->s_nrm.p,
-			c->vals[c->last_sorted].p, n1, c->buckets.p, c->gp, search_radius, max_inner, max_outer, 1,
-			c->nn.p, (unsigned long long *)nullptr);
+	launch_nn(c, nullptr, n2, c->vals[c->last_sorted].p, n1, c->buckets.p, search_radius, max_inner, max_outer, c->prune,
+			c->nn.p, nullptr, nullptr);
 	CK(cudaMemcpyAsync(nn_out, c->nn.p, (size_t)n2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 	c->last_n_first = n1; c->last_n_second = n2; c->last_valid = true;
 	int f = check_flags(c);
@@ -636,6 +703,37 @@ void m3dreg_euler_to_matrix(const float *omfika, const float *xyz, float *m) { e
 
 /* ---- scan store ------------------------------------------------------------------------------------------ */
 
+/* Cell-sorted copy of a scan for its QUERY role: stable radix sort by the key of a fine local grid (0.25 m cells,
+ * coarsened until the cell count fits 2^22).  Any spatially coherent order works — the NN result does not depend on
+ * query order — this one reuses the grid machinery. */
+static int presort_scan(m3dreg_ctx *c, Scan &s, const m3dreg_point *d_aos)
+{
+	int n = s.n, e;
+	if ((e = ensure_first(c, (size_t)n))) return e;
+	LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
+	LAUNCH(c, k_bounds_aos, grid_for(c, n, 256), 256, d_aos, n, c->bounds);
+	CK(cudaMemcpyAsync(c->h->bounds, c->bounds, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	float mn[3], mx[3];
+	for (int k = 0; k < 3; k++) { mn[k] = o2f_host(c->h->bounds[k]); mx[k] = o2f_host(c->h->bounds[3 + k]); }
+	float res = 0.25f;
+	m3dreg_grid_params gp;
+	for (;;) {
+		int st = grid_params_from_bounds(mn, mx, res, res, res, 0.0f, &gp);
+		if (st == 0 && gp.number_of_buckets <= (1 << 22)) break;
+		res *= 2.0f;
+		if (res > 1.0e6f) return M3DREG_E_TOO_MANY_BUCKETS;
+	}
+	c->h->gp = gp;
+	CK(cudaMemcpyAsync(c->gp, &c->h->gp, sizeof(m3dreg_grid_params), cudaMemcpyHostToDevice, c->stream));
+	LAUNCH(c, k_keys_aos, grid_for(c, n, 256), 256, d_aos, n, c->gp, c->keys[0].p, c->vals[0].p);
+	int cur = sort_by_bucket(c, n, bits_for(gp.number_of_buckets), nullptr);
+	CK(cudaMemcpyAsync(s.perm, c->vals[cur].p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+	LAUNCH(c, k_gather_perm, grid_for(c, n, 256), 256, s.perm, n, s.xyzl, s.nrm, s.sx, s.sn);
+	CK(cudaStreamSynchronize(c->stream));
+	return (int)cudaGetLastError();
+}
+
 int m3dreg_scan_upload(m3dreg_ctx *c, int slot, const m3dreg_point *src, int n, int src_on_device)
 {
 	if (!c || slot < 0 || !src || n <= 0) return M3DREG_E_INVALID_ARG;
@@ -643,11 +741,12 @@ int m3dreg_scan_upload(m3dreg_ctx *c, int slot, const m3dreg_point *src, int n, 
 	if ((size_t)slot >= c->scans.size()) c->scans.resize((size_t)slot + 1);
 	Scan &s = c->scans[(size_t)slot];
 	if ((size_t)n > s.cap) {
-		if (s.xyzl) cudaFree(s.xyzl);
-		if (s.nrm) cudaFree(s.nrm);
-		s.xyzl = s.nrm = nullptr; s.cap = 0; s.n = 0;
+		s.release();
 		CK(cudaMalloc((void **)&s.xyzl, (size_t)n * sizeof(float4)));
 		CK(cudaMalloc((void **)&s.nrm, (size_t)n * sizeof(float4)));
+		CK(cudaMalloc((void **)&s.sx, (size_t)n * sizeof(float4)));
+		CK(cudaMalloc((void **)&s.sn, (size_t)n * sizeof(float4)));
+		CK(cudaMalloc((void **)&s.perm, (size_t)n * sizeof(uint32_t)));
 		s.cap = (size_t)n;
 	}
 	const m3dreg_point *d_src = src;
@@ -659,8 +758,9 @@ int m3dreg_scan_upload(m3dreg_ctx *c, int slot, const m3dreg_point *src, int n, 
 	}
 	LAUNCH(c, k_unpack_points, (n + 255) / 256, 256, d_src, n, s.xyzl, s.nrm);
 	s.n = n;
-	CK(cudaStreamSynchronize(c->stream));
-	return (int)cudaGetLastError();
+	c->active = false;
+	c->last_valid = false;
+	return presort_scan(c, s, d_src);
 }
 
 int m3dreg_scan_size(const m3dreg_ctx *c, int slot)
@@ -674,7 +774,7 @@ int m3dreg_scan_clear(m3dreg_ctx *c)
 	if (!c) return M3DREG_E_INVALID_ARG;
 	CK(cudaSetDevice(c->dev));
 	CK(cudaStreamSynchronize(c->stream));
-	for (auto &s : c->scans) { if (s.xyzl) cudaFree(s.xyzl); if (s.nrm) cudaFree(s.nrm); }
+	for (auto &s : c->scans) s.release();
 	c->scans.clear();
 	return 0;
 }
@@ -685,6 +785,7 @@ static int icp_begin_internal(m3dreg_ctx *c, const float4 *lx, const float4 *ln,
 		const m3dreg_reg_params *prm)
 {
 	int e;
+	if ((e = ensure_candidates(c, (size_t)n1, prm->max_inner, prm->max_outer))) return e;
 	memset(&c->h->ps, 0, sizeof(PoseState));
 	memcpy(c->h->ps.m, pose_first, 16 * sizeof(float));
 	CK(cudaMemcpyAsync(c->ps, &c->h->ps, sizeof(PoseState), cudaMemcpyHostToDevice, c->stream));
@@ -734,7 +835,8 @@ static int stage_queries(m3dreg_ctx *c, int second_slot, const float *pose_secon
 	/* queries: second scan transformed once by the Euler round trip of its pose (gpu6DSLAM.cpp:295-307) */
 	host_roundtrip_pose(pose_second, c->h->mats, nullptr);
 	CK(cudaMemcpyAsync(c->mats, c->h->mats, 16 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-	LAUNCH(c, k_transform_soa<false>, grid_for(c, B.n, 256), 256, B.xyzl, B.nrm, B.n, c->mats, c->q_xyzl.p, c->q_nrm.p, (uint32_t *)nullptr);
+	LAUNCH(c, k_transform_soa<false>, grid_for(c, B.n, 256), 256, B.sx, B.sn, B.n, c->mats, c->q_xyzl.p, c->q_nrm.p, (uint32_t *)nullptr);
+	c->act_perm = B.perm;
 	return 0;
 }
 
@@ -836,6 +938,7 @@ int m3dreg_icp_iteration_host(m3dreg_ctx *c, const m3dreg_point *first_local, in
 	CK(cudaMemcpyAsync(c->aos_b.p, second_global, (size_t)n2 * sizeof(m3dreg_point), cudaMemcpyHostToDevice, c->stream));
 	LAUNCH(c, k_unpack_points, (n1 + 255) / 256, 256, c->aos_a.p, n1, c->l_xyzl.p, c->l_nrm.p);
 	LAUNCH(c, k_unpack_points, (n2 + 255) / 256, 256, c->aos_b.p, n2, c->q_xyzl.p, c->q_nrm.p);
+	c->act_perm = nullptr;
 	e = icp_loop(c, c->l_xyzl.p, c->l_nrm.p, n1, n2, pose_first, prm, 1, stats);
 	c->active = false;
 	if (e) return e;
@@ -930,6 +1033,7 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 		const Scan &A = c->scans[(size_t)i], &B = c->scans[(size_t)j];
 		if (i != cur_i) {
 			if ((e = ensure_first(c, (size_t)A.n))) return e;
+			if ((e = ensure_candidates(c, (size_t)A.n, prm->max_inner, prm->max_outer))) return e;
 			LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
 			LAUNCH(c, k_transform_soa<true>, grid_for(c, A.n, 256), 256, A.xyzl, A.nrm, A.n, c->d_poses1.p + 16 * (size_t)i,
 					c->g_xyzl.p, c->g_nrm.p, c->bounds);
@@ -938,13 +1042,12 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 			cur_i = i;
 		}
 		if ((e = ensure_second(c, (size_t)B.n))) return e;
-		LAUNCH(c, k_transform_soa<false>, grid_for(c, B.n, 256), 256, B.xyzl, B.nrm, B.n, c->d_poses1.p + 16 * (size_t)j,
+		LAUNCH(c, k_transform_soa<false>, grid_for(c, B.n, 256), 256, B.sx, B.sn, B.n, c->d_poses1.p + 16 * (size_t)j,
 				c->q_xyzl.p, c->q_nrm.p, (uint32_t *)nullptr);
-		LAUNCH(c, k_nn_search, (B.n + 255) / 256, 256, c->q_xyzl.p, c->q_nrm.p, B.n, c->s_xyzl.p, c->s_nrm.p,
-				c->vals[c->last_sorted].p, A.n, c->buckets.p, c->gp, prm->search_radius, prm->max_inner, prm->max_outer, 1,
-				c->nn.p, c->label_counts);
+		launch_nn(c, B.perm, B.n, c->vals[c->last_sorted].p, A.n, c->buckets.p, prm->search_radius, prm->max_inner, prm->max_outer, 1,
+				c->nn.p, c->nn_seq.p, c->label_counts);
 		ObsFromNN src;
-		src.nn = c->nn.p; src.q_xyzl = c->q_xyzl.p; src.g_xyzl = c->g_xyzl.p; src.l_xyzl = A.xyzl; src.label_counts = c->label_counts;
+		src.nn = c->nn_seq.p; src.q_xyzl = c->q_xyzl.p; src.g_xyzl = c->g_xyzl.p; src.l_xyzl = A.xyzl; src.label_counts = c->label_counts;
 		for (int k = 0; k < 4; k++) src.weight[k] = prm->weight[k];
 		FinalizeArgs fin;
 		fin.ps = nullptr; fin.neq_out = d_neq + (size_t)i * kNeqCount; fin.accumulate = 1; fin.solve = 0; fin.dof = prm->dof;

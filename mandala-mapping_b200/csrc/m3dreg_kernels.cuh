@@ -260,63 +260,76 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint32_t *__r
 	sh[threadIdx.x] = 0;
 	__syncthreads();
 	int base = blockIdx.x * (kSortThreads * ITEMS);
+	int lane = threadIdx.x & 31;
 #pragma unroll
 	for (int j = 0; j < ITEMS; j++) {
 		int i = base + j * kSortThreads + threadIdx.x;
-		if (i < n) atomicAdd(&sh[(__ldg(keys + i) >> shift) & (kRadixSize - 1)], 1u);
+		bool valid = i < n;
+		uint32_t d = valid ? ((__ldg(keys + i) >> shift) & (kRadixSize - 1)) : (0x100u + lane);
+		/* bucket keys are heavily skewed (dense cells): aggregate equal digits inside the warp first */
+		uint32_t peers = __match_any_sync(0xffffffffu, d);
+		if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[d], (uint32_t)__popc(peers));
 	}
 	__syncthreads();
 	hist[threadIdx.x * tiles + blockIdx.x] = sh[threadIdx.x];
 }
 
-/* single-block exclusive scan over `count` uint32 (count = 256 * tiles) */
-__global__ void __launch_bounds__(1024) k_radix_scan(uint32_t *__restrict__ hist, int count, const m3dreg_grid_params *__restrict__ gp)
+/* One block per digit: exclusive scan of that digit's row of per-tile counts (in place) and the row total. */
+__global__ void __launch_bounds__(256) k_radix_scan(uint32_t *__restrict__ hist, int tiles, uint32_t *__restrict__ digit_tot,
+		const m3dreg_grid_params *__restrict__ gp)
 {
-	__shared__ uint32_t warp_tot[32];
+	__shared__ uint32_t warp_tot[8];
+	__shared__ uint32_t carry;
 	if (gp && gp->number_of_buckets <= 0) return;
-	int per = (count + 1023) / 1024;
+	uint32_t *row = hist + (size_t)blockIdx.x * tiles;
 	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	int beg = threadIdx.x * per, end = min(beg + per, count);
-	uint32_t sum = 0;
-	for (int i = beg; i < end; i++) sum += hist[i];
-	uint32_t incl = sum;
-#pragma unroll
-	for (int o = 1; o < 32; o <<= 1) {
-		uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-		if (lane >= o) incl += t;
-	}
-	if (lane == 31) warp_tot[w] = incl;
+	if (threadIdx.x == 0) carry = 0;
 	__syncthreads();
-	if (w == 0) {
-		uint32_t v = warp_tot[lane], iv = v;
+	for (int base = 0; base < tiles; base += 256) {
+		int i = base + threadIdx.x;
+		uint32_t v = i < tiles ? row[i] : 0u, incl = v;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
-			uint32_t t = __shfl_up_sync(0xffffffffu, iv, o);
-			if (lane >= o) iv += t;
+			uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
 		}
-		warp_tot[lane] = iv - v;
+		if (lane == 31) warp_tot[w] = incl;
+		__syncthreads();
+		uint32_t off = carry;
+		for (int k = 0; k < w; k++) off += warp_tot[k];
+		if (i < tiles) row[i] = off + incl - v;
+		__syncthreads();
+		if (threadIdx.x == 255) carry = off + incl;
+		__syncthreads();
 	}
-	__syncthreads();
-	uint32_t run = warp_tot[w] + incl - sum;
-	for (int i = beg; i < end; i++) {
-		uint32_t v = hist[i];
-		hist[i] = run;
-		run += v;
-	}
+	if (threadIdx.x == 0) digit_tot[blockIdx.x] = carry;
 }
 
 template <int ITEMS>
 __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
 		uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int n, int shift, int tiles,
-		const uint32_t *__restrict__ hist, const m3dreg_grid_params *__restrict__ gp)
+		const uint32_t *__restrict__ hist, const uint32_t *__restrict__ digit_tot, const m3dreg_grid_params *__restrict__ gp)
 {
 	__shared__ uint32_t wcnt[kSortWarps][kRadixSize];   /* per-warp digit counts, then per-warp exclusive offsets */
 	__shared__ uint32_t gbase[kRadixSize];
+	__shared__ uint32_t wtot[kSortWarps];
 	if (gp && gp->number_of_buckets <= 0) return;
 	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
 	for (int k = 0; k < kSortWarps; k++) wcnt[k][threadIdx.x] = 0;
-	gbase[threadIdx.x] = hist[threadIdx.x * tiles + blockIdx.x];
+	{   /* exclusive scan of the 256 digit totals (thread = digit) + this tile's prefix inside the digit */
+		uint32_t v = __ldg(digit_tot + threadIdx.x), incl = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		if (lane == 31) wtot[w] = incl;
+		__syncthreads();
+		uint32_t off = 0;
+		for (int k = 0; k < w; k++) off += wtot[k];
+		gbase[threadIdx.x] = off + incl - v + __ldg(hist + (size_t)threadIdx.x * tiles + blockIdx.x);
+	}
 	__syncthreads();
 
 	int wbase = blockIdx.x * (kSortThreads * ITEMS) + w * (32 * ITEMS);
@@ -391,25 +404,16 @@ __device__ __forceinline__ int lower_bound_u32(const uint32_t *__restrict__ a, i
  * {begin, end, n} (begin by binary search), so no separate count pass is needed.  Reference quirk reproduced
  * (lesson_16.cu:148-158): when element 0 is alone in its bucket, the run that starts at position 1 never gets
  * index_begin (it receives index_end=1 instead), so that bucket reads {-1, end, 0}.  Its index_end is a write
- * race upstream (1 vs run end); we store the run end.
- * Also gathers the transformed first cloud into sorted order and (optionally) materialises the reference's
- * hashElement table. */
+ * race upstream (1 vs run end); we store the run end.  Optionally materialises the reference's hashElement table. */
 __global__ void k_finalize_grid(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int n,
-		const m3dreg_grid_params *__restrict__ gp, m3dreg_bucket *__restrict__ buckets,
-		const float4 *__restrict__ g_xyzl, const float4 *__restrict__ g_nrm,
-		float4 *__restrict__ s_xyzl, float4 *__restrict__ s_nrm, m3dreg_hash_element *__restrict__ table_out)
+		const m3dreg_grid_params *__restrict__ gp, m3dreg_bucket *__restrict__ buckets, m3dreg_hash_element *__restrict__ table_out)
 {
 	if (gp && gp->number_of_buckets <= 0) return;
 	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
 		uint32_t k = __ldg(keys + p);
-		uint32_t v = __ldg(vals + p);
-		if (s_xyzl) {
-			s_xyzl[p] = __ldg(g_xyzl + v);
-			s_nrm[p] = __ldg(g_nrm + v);
-		}
 		if (table_out) {
 			m3dreg_hash_element h;
-			h.index_of_point = (int)v;
+			h.index_of_point = (int)__ldg(vals + p);
 			h.index_of_bucket = (int)k;
 			table_out[p] = h;
 		}
@@ -427,30 +431,66 @@ __global__ void k_finalize_grid(const uint32_t *__restrict__ keys, const uint32_
 	}
 }
 
-/* gather by an externally supplied reference-layout table (stage-level m3dreg_nn_search) */
-__global__ void k_gather_by_table(const m3dreg_hash_element *__restrict__ table, int n,
-		const float4 *__restrict__ g_xyzl, const float4 *__restrict__ g_nrm,
-		float4 *__restrict__ s_xyzl, float4 *__restrict__ s_nrm, uint32_t *__restrict__ vals)
+/* The reference never looks at every point of a bucket: it walks positions begin, begin+s, begin+2s, ... with
+ * s = n / cap (lesson_16.cu:628-640), i.e. at most 2*cap-1 CANDIDATES per bucket.  Only those are ever read by the
+ * NN search, so only those are gathered — densely, candidate k of a bucket at slot begin+k of the compact arrays
+ * (a bucket's candidates always fit inside its own [begin,end) range, so no prefix sum is needed).  Contiguous
+ * candidates are what lets a warp fetch 32 of them with one coalesced load and stage them in shared memory.
+ * Two compact sets exist when the INNER and OUTER caps differ (different strides). */
+__device__ __forceinline__ int candidate_stride(int npts, int cap)
+{
+	int iter = 1;
+	if (cap < npts) { iter = npts / cap; if (iter <= 0) iter = 1; }
+	return iter;
+}
+
+__global__ void k_compact_candidates(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int n,
+		const m3dreg_grid_params *__restrict__ gp, const m3dreg_bucket *__restrict__ buckets,
+		const float4 *__restrict__ g_xyzl, const float4 *__restrict__ g_nrm, int max_inner, int max_outer,
+		float4 *__restrict__ ci_xyzl, float4 *__restrict__ ci_nrm, float4 *__restrict__ co_xyzl, float4 *__restrict__ co_nrm)
+{
+	if (gp->number_of_buckets <= 0) return;
+	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+		uint32_t k = __ldg(keys + p);
+		const int *bp = reinterpret_cast<const int *>(buckets + k);
+		int npts = __ldg(bp + 2);
+		if (npts <= 0) continue;                          /* quirk bucket: invisible to the search */
+		int rank = p - __ldg(bp);
+		bool in_i = false, in_o = false;
+		int slot_i = 0, slot_o = 0;
+		if (max_inner > 0) { int it = candidate_stride(npts, max_inner); in_i = (rank % it) == 0; slot_i = p - rank + rank / it; }
+		if (co_xyzl != ci_xyzl && max_outer > 0) { int it = candidate_stride(npts, max_outer); in_o = (rank % it) == 0; slot_o = p - rank + rank / it; }
+		if (in_i || in_o) {
+			uint32_t v = __ldg(vals + p);
+			float4 a = __ldg(g_xyzl + v), b = __ldg(g_nrm + v);
+			if (in_i) { ci_xyzl[slot_i] = a; ci_nrm[slot_i] = b; }
+			if (in_o) { co_xyzl[slot_o] = a; co_nrm[slot_o] = b; }
+		}
+	}
+}
+
+/* split an externally supplied reference-layout table into key / value streams (stage-level m3dreg_nn_search) */
+__global__ void k_split_table(const m3dreg_hash_element *__restrict__ table, int n, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
 	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-		int v = table[p].index_of_point;
-		vals[p] = (uint32_t)v;
-		s_xyzl[p] = __ldg(g_xyzl + v);
-		s_nrm[p] = __ldg(g_nrm + v);
+		m3dreg_hash_element h = table[p];
+		keys[p] = (uint32_t)h.index_of_bucket;
+		vals[p] = (uint32_t)h.index_of_point;
 	}
 }
 
 /* ---- semantic nearest neighbour (kernel_semanticNearestNeighborSearch, lesson_16.cu:531-703) ------------- */
 
-/* The reference's angle gate, written exactly as upstream (lesson_16.cu:666-671) so nvcc inlines the same
- * acosf code: acos -> *180.0f (f32) -> /M_PI (f64) -> f32 -> abs -> < 90.0f.  Evaluated only for candidates that
- * already passed the label, radius and improvement tests (all gates are a pure conjunction, so order is free). */
+/* The reference's angle gate (lesson_16.cu:666-676): acos(dot)*180.0f/M_PI, |.| < 90.0f, with acos the CUDA
+ * float acosf.  As a function of the f32 dot product its accepted set is exactly the interval
+ *      0x328885AC (1.589327e-08) <= dot <= 1.0f
+ * (NaN, |dot| > 1, zero and negative dots are rejected; tiny positive dots still round to >= 90.0f degrees).
+ * tests/test_gpu_gate.py proves this equal to the upstream expression for ALL 2^32 float bit patterns on the
+ * device, so the two compares below are bit-exact and ~60 instructions (acosf + an f64 divide) cheaper. */
+constexpr uint32_t kAngleGateMinBits = 0x328885ACu;
 __device__ __forceinline__ bool angle_gate(float dot)
 {
-	float angle = acosf(dot);
-	float angled = angle * 180.0f / M_PI;
-	if (angled < 0) angled = -angled;
-	return angled < 90.0f;
+	return dot >= __uint_as_float(kAngleGateMinBits) && dot <= 1.0f;
 }
 
 struct NNQuery {
@@ -460,28 +500,49 @@ struct NNQuery {
 	int best_l;
 };
 
-/* Scan one bucket's (sub-sampled) candidates.  Visit order in the reference is ascending sorted position l
- * (cells are visited in ascending linear index and the table is sorted by it), and the update is a strict `<`,
- * so the reference result is the lexicographic minimum of (dist, l) over admissible candidates.  Keeping that
- * pair lets cells be visited in any order and skipped when provably useless. */
-__device__ __forceinline__ void nn_visit_bucket(NNQuery &q, const m3dreg_bucket *__restrict__ buckets, int cell, int cap, int n_first,
-		const float4 *__restrict__ s_xyzl, const float4 *__restrict__ s_nrm)
+/* Visit order in the reference is ascending sorted position l (cells are visited in ascending linear index and
+ * the table is sorted by it) and its update is a strict `<`, so the reference result is the lexicographic minimum
+ * of (dist, l) over the admissible candidates.  Keeping that pair lets cells be visited in ANY order, lets cells be
+ * skipped when provably useless, and makes evaluating extra candidates harmless — which is what allows a whole
+ * warp to walk one candidate list together.
+ *
+ * Warp-cooperative bucket scan: every lane holds one query.  The warp fetches 32 compact candidates with one
+ * coalesced LDG.128 per lane, stages them in its 512-byte slice of shared memory, then all lanes test the same
+ * candidate (broadcast LDS.128) against their own query.  Hot loop: LDS + 3 FSUB + FMUL + 2 FFMA + one compare
+ * against thr = min(best, r^2) + a warp vote; label, tie-break, normal load and angle gate run only when some lane
+ * passes (rare).  `active` masks lanes for which this cell is irrelevant; they run in lock step (no divergence). */
+__device__ __forceinline__ void nn_visit_bucket_warp(NNQuery &q, bool active, const m3dreg_bucket *__restrict__ buckets, int cell, int cap,
+		const float4 *__restrict__ c_xyzl, const float4 *__restrict__ c_nrm, float4 *stage, int lane, unsigned int &evals)
 {
 	const int *bp = reinterpret_cast<const int *>(buckets + cell);
 	int npts = __ldg(bp + 2);
 	if (npts <= 0 || cap <= 0) return;
-	int iter = 1;
-	if (cap < npts) { iter = npts / cap; if (iter <= 0) iter = 1; }
+	int iter = candidate_stride(npts, cap);
 	int lb = __ldg(bp), le = __ldg(bp + 1);
-	for (int l = lb; l < le; l += iter) {
-		if (l < 0 || l >= n_first) continue;
-		float4 c = __ldg(s_xyzl + l);
-		float dx = __fsub_rn(q.x, c.x), dy = __fsub_rn(q.y, c.y), dz = __fsub_rn(q.z, c.z);
-		float dist = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-		if (__float_as_int(c.w) == q.label && dist <= q.r2 && (dist < q.best || (dist == q.best && l < q.best_l))) {
-			float4 cn = __ldg(s_nrm + l);
-			float dot = __fmaf_rn(q.nz, cn.z, __fmaf_rn(q.nx, cn.x, __fmul_rn(q.ny, cn.y)));
-			if (angle_gate(dot)) { q.best = dist; q.best_l = l; }
+	int ncand = (le - lb + iter - 1) / iter;
+	float thr = fminf(q.best, q.r2);
+	for (int k0 = 0; k0 < ncand; k0 += 32) {
+		int cnt = min(32, ncand - k0);
+		__syncwarp();
+		if (lane < cnt) stage[lane] = __ldg(c_xyzl + lb + k0 + lane);
+		__syncwarp();
+		evals += (unsigned int)cnt;
+#pragma unroll 4
+		for (int kk = 0; kk < cnt; kk++) {
+			float4 c = stage[kk];
+			float dx = __fsub_rn(q.x, c.x), dy = __fsub_rn(q.y, c.y), dz = __fsub_rn(q.z, c.z);
+			float dist = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+			bool pre = active && dist <= thr;
+			if (__any_sync(0xffffffffu, pre)) {
+				if (pre && __float_as_int(c.w) == q.label) {
+					int l = lb + (k0 + kk) * iter;
+					if (dist < q.best || (dist == q.best && l < q.best_l)) {
+						float4 cn = __ldg(c_nrm + lb + k0 + kk);
+						float dot = __fmaf_rn(q.nz, cn.z, __fmaf_rn(q.nx, cn.x, __fmul_rn(q.ny, cn.y)));
+						if (angle_gate(dot)) { q.best = dist; q.best_l = l; thr = fminf(dist, q.r2); }
+					}
+				}
+			}
 		}
 	}
 }
@@ -503,71 +564,107 @@ __device__ __forceinline__ void axis_gaps(float q, float mn, float res, int ic, 
 	g_hi = b > 0.0 ? __double2float_rd(b) : 0.0f;
 }
 
-/* v1: one thread per query, candidates read from the sorted SoA copy of the first cloud (contiguous per bucket). */
-__global__ void __launch_bounds__(256) k_nn_search(const float4 *__restrict__ q_xyzl, const float4 *__restrict__ q_nrm, int n_second,
-		const float4 *__restrict__ s_xyzl, const float4 *__restrict__ s_nrm, const uint32_t *__restrict__ s_vals, int n_first,
+/* Semantic NN, one query per lane, one candidate list per warp.
+ * Queries are expected in a spatially coherent order (the scan store keeps a cell-sorted copy of every scan, and a
+ * rigid transform preserves coherence), so the 32 queries of a warp usually share their home bucket.  Lanes are
+ * grouped by home bucket with ballots; each group walks its <= 27 buckets once, home bucket first; a neighbour
+ * bucket is walked only if some lane of the group cannot exclude it by the lower bound above.
+ * q_perm (may be null = identity) maps the query's position to its index in the caller's order: nn_out is written
+ * in the caller's order (the reference's layout), nn_seq (may be null) in query-array order for the next stage. */
+__global__ void __launch_bounds__(256) k_nn_search(const float4 *__restrict__ q_xyzl, const float4 *__restrict__ q_nrm,
+		const uint32_t *__restrict__ q_perm, int n_second,
+		const float4 *__restrict__ ci_xyzl, const float4 *__restrict__ ci_nrm, const float4 *__restrict__ co_xyzl, const float4 *__restrict__ co_nrm,
+		const uint32_t *__restrict__ s_vals, int n_first,
 		const m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp,
 		float search_radius, int max_inner, int max_outer, int prune,
-		int *__restrict__ nn, unsigned long long *__restrict__ label_counts)
+		int *__restrict__ nn_out, int *__restrict__ nn_seq, unsigned long long *__restrict__ label_counts,
+		unsigned long long *__restrict__ eval_counter)
 {
 	__shared__ unsigned int s_cnt[4];
+	__shared__ float4 s_stage[8][32];
 	if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
 	__syncthreads();
+	const unsigned full = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	float4 *stage = s_stage[threadIdx.x >> 5];
+	unsigned int evals = 0;
 	int qi = blockIdx.x * blockDim.x + threadIdx.x;
-	int result = -1;
-	int qlabel = -1;
 	long long nb = gp->number_of_buckets;
+	int nbx = gp->number_of_buckets_X, nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
+	float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
+	float rx = gp->resolution_X, ry = gp->resolution_Y, rz = gp->resolution_Z;
+	NNQuery q;
+	q.x = q.y = q.z = q.nx = q.ny = q.nz = 0.0f;
+	q.r2 = __fmul_rn(search_radius, search_radius);
+	q.label = -1;
+	q.best = 100000000.0f;
+	q.best_l = 0x7fffffff;
+	int home = -1, ix = 0, iy = 0, iz = 0;
 	if (qi < n_second && nb > 0) {
 		float4 p = __ldg(q_xyzl + qi), pn = __ldg(q_nrm + qi);
-		qlabel = __float_as_int(p.w);
-		float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
+		q.x = p.x; q.y = p.y; q.z = p.z; q.nx = pn.x; q.ny = pn.y; q.nz = pn.z;
+		q.label = __float_as_int(p.w);
 		bool inside = !(p.x < mnx || p.x > gp->bounding_box_max_X) && !(p.y < mny || p.y > gp->bounding_box_max_Y) &&
 				!(p.z < mnz || p.z > gp->bounding_box_max_Z);
 		if (inside) {
-			float rx = gp->resolution_X, ry = gp->resolution_Y, rz = gp->resolution_Z;
-			int nbx = gp->number_of_buckets_X, nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
-			int ix = cell_of(p.x, mnx, rx), iy = cell_of(p.y, mny, ry), iz = cell_of(p.z, mnz, rz);
-			int home = ix * nby * nbz + iy * nbz + iz;
-			if (home >= 0 && (long long)home < nb) {
-				NNQuery q;
-				q.x = p.x; q.y = p.y; q.z = p.z; q.nx = pn.x; q.ny = pn.y; q.nz = pn.z;
-				q.r2 = __fmul_rn(search_radius, search_radius);
-				q.label = qlabel;
-				q.best = 100000000.0f;
-				q.best_l = 0x7fffffff;
-				int sx = ix == 0 ? 0 : -1, sy = iy == 0 ? 0 : -1, sz = iz == 0 ? 0 : -1;
-				int stx = ix == nbx - 1 ? 1 : 2, sty = iy == nby - 1 ? 1 : 2, stz = iz == nbz - 1 ? 1 : 2;
-				float gx[3], gy[3], gz[3];
-				gx[1] = gy[1] = gz[1] = 0.0f;
-				if (prune) {
-					axis_gaps(p.x, mnx, rx, ix, gx[0], gx[2]);
-					axis_gaps(p.y, mny, ry, iy, gy[0], gy[2]);
-					axis_gaps(p.z, mnz, rz, iz, gz[0], gz[2]);
-					nn_visit_bucket(q, buckets, home, max_inner, n_first, s_xyzl, s_nrm);
-				} else {
-					gx[0] = gx[2] = gy[0] = gy[2] = gz[0] = gz[2] = 0.0f;
-				}
-				for (int i = sx; i < stx; i++)
-				for (int j = sy; j < sty; j++)
-				for (int k = sz; k < stz; k++) {
-					int cell = home + i * nby * nbz + j * nbz + k;
-					if (cell < 0 || (long long)cell >= nb) continue;
-					if (prune) {
-						if (cell == home) continue;
-						float lbd = __fmaf_rn(gz[k + 1], gz[k + 1], __fmaf_rn(gx[i + 1], gx[i + 1], __fmul_rn(gy[j + 1], gy[j + 1])));
-						if (lbd > q.best || lbd > q.r2) continue;
-					}
-					nn_visit_bucket(q, buckets, cell, cell == home ? max_inner : max_outer, n_first, s_xyzl, s_nrm);
-				}
-				if (q.best_l != 0x7fffffff) result = (int)__ldg(s_vals + q.best_l);
-			}
+			ix = cell_of(p.x, mnx, rx); iy = cell_of(p.y, mny, ry); iz = cell_of(p.z, mnz, rz);
+			int h = ix * nby * nbz + iy * nbz + iz;
+			if (h >= 0 && (long long)h < nb) home = h;
 		}
 	}
-	if (qi < n_second) nn[qi] = result;
+	float gx[3], gy[3], gz[3];
+	gx[0] = gx[1] = gx[2] = gy[0] = gy[1] = gy[2] = gz[0] = gz[1] = gz[2] = 0.0f;
+	if (prune && home >= 0) {
+		axis_gaps(q.x, mnx, rx, ix, gx[0], gx[2]);
+		axis_gaps(q.y, mny, ry, iy, gy[0], gy[2]);
+		axis_gaps(q.z, mnz, rz, iz, gz[0], gz[2]);
+	}
+	unsigned remaining = __ballot_sync(full, home >= 0);
+	while (remaining) {
+		int leader = __ffs(remaining) - 1;
+		int h = __shfl_sync(full, home, leader);
+		int hx = __shfl_sync(full, ix, leader), hy = __shfl_sync(full, iy, leader), hz = __shfl_sync(full, iz, leader);
+		bool mine = (home == h);
+		remaining &= ~__ballot_sync(full, mine);
+		nn_visit_bucket_warp(q, mine, buckets, h, max_inner, ci_xyzl, ci_nrm, stage, lane, evals);
+		int sx = hx == 0 ? 0 : -1, sy = hy == 0 ? 0 : -1, sz = hz == 0 ? 0 : -1;
+		int stx = hx == nbx - 1 ? 1 : 2, sty = hy == nby - 1 ? 1 : 2, stz = hz == nbz - 1 ? 1 : 2;
+		for (int i = sx; i < stx; i++)
+		for (int j = sy; j < sty; j++)
+		for (int k = sz; k < stz; k++) {
+			int cell = h + i * nby * nbz + j * nbz + k;
+			if (cell == h || cell < 0 || (long long)cell >= nb) continue;
+			bool need = mine;
+			if (prune) {
+				float lbd = __fmaf_rn(gz[k + 1], gz[k + 1], __fmaf_rn(gx[i + 1], gx[i + 1], __fmul_rn(gy[j + 1], gy[j + 1])));
+				need = mine && !(lbd > q.best || lbd > q.r2);
+			}
+			if (!__any_sync(full, need)) continue;
+			nn_visit_bucket_warp(q, need, buckets, cell, max_outer, co_xyzl, co_nrm, stage, lane, evals);
+		}
+	}
+	if (eval_counter && lane == 0 && evals) atomicAdd(eval_counter, (unsigned long long)evals);
+	int result = -1;
+	if (q.best_l != 0x7fffffff && q.best_l < n_first) result = (int)__ldg(s_vals + q.best_l);
+	if (qi < n_second) {
+		if (nn_seq) nn_seq[qi] = result;
+		nn_out[q_perm ? __ldg(q_perm + qi) : (uint32_t)qi] = result;
+	}
 	if (label_counts) {
-		if (result >= 0 && qlabel >= 0 && qlabel < 4) atomicAdd(&s_cnt[qlabel], 1u);
+		if (qi < n_second && result >= 0 && q.label >= 0 && q.label < 4) atomicAdd(&s_cnt[q.label], 1u);
 		__syncthreads();
 		if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(&label_counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+	}
+}
+
+/* gather a stored scan into query order: out[i] = in[perm[i]] */
+__global__ void k_gather_perm(const uint32_t *__restrict__ perm, int n, const float4 *__restrict__ in_xyzl, const float4 *__restrict__ in_nrm,
+		float4 *__restrict__ out_xyzl, float4 *__restrict__ out_nrm)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		uint32_t v = __ldg(perm + i);
+		out_xyzl[i] = __ldg(in_xyzl + v);
+		out_nrm[i] = __ldg(in_nrm + v);
 	}
 }
 
@@ -862,10 +959,11 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(Src src, int n
 	__threadfence();
 	/* deterministic final reduction: fixed row order */
 	__shared__ double tot[kMomentCount];
-	if (threadIdx.x < kMomentCount) {
+	for (int col = wid; col < kMomentCount; col += kNeqThreads / 32) {     /* warp per column, lanes stride the rows */
 		double s = 0;
-		for (unsigned int b = 0; b < gridDim.x; b++) s += __ldcg(partials + (size_t)b * kMomentCount + threadIdx.x);
-		tot[threadIdx.x] = s;
+		for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * kMomentCount + col);
+		s = warp_sum(s);
+		if (lane == 0) tot[col] = s;
 	}
 	__syncthreads();
 	if (threadIdx.x == 0) {

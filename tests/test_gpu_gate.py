@@ -17,7 +17,7 @@ def test_gate_exhaustive_on_device():
     mm_product, mm_restated, accepted, lo, hi, first_bad = list(out)
     assert mm_product == 0 and mm_restated == 0, (mm_product, mm_restated, hex(first_bad - 1) if first_bad else None)
     # accepted set is one contiguous interval of positive floats [T, 1.0]
-    assert hi == 0x3F800000
+    assert hi == 0x3F800000 and lo == 0x328885AC
     assert accepted == hi - lo + 1
     t = np.array([lo], dtype=np.uint32).view(np.float32)[0]
     assert 0 < t < 1e-6

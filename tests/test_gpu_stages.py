@@ -102,6 +102,21 @@ def test_c1_full_size_vs_reference(pkg, synth, oracle, ctx, ref, hdl_pair):
     assert np.array_equal(nn_o, nn_r)
 
 
+def test_pruning_is_exact(pkg, synth, oracle, ctx):
+    """The lower-bound bucket pruning never changes a result: pruned == unpruned == oracle, incl. queries in random order."""
+    first = synth.hdl32_scan(seed=51, n_azimuth=512)
+    second = synth.hdl32_scan(seed=52, n_azimuth=512)
+    rng = np.random.default_rng(0)
+    second = second[rng.permutation(len(second))].copy()         # incoherent query order: every warp holds many home buckets
+    for radius, bucket in ((0.5, 0.5), (2.5, 2.5), (0.3, 1.0), (1.0, 0.4)):
+        nn_o, *_ = oracle.semantic_nn(first, second, radius, bucket)
+        ctx.set_pruning(False)
+        nn_a = ctx.semantic_nn_host(first, second, radius, bucket)
+        ctx.set_pruning(True)
+        nn_b = ctx.semantic_nn_host(first, second, radius, bucket)
+        assert np.array_equal(nn_a, nn_o) and np.array_equal(nn_b, nn_o), (radius, bucket)
+
+
 def test_transform_bit_exact(pkg, synth, oracle, ctx):
     import torch
     c = synth.random_cloud(10007, seed=31)
