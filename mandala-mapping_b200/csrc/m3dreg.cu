@@ -273,7 +273,7 @@ void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *va
 		float radius, int max_inner, int max_outer, int prune, int *nn_out, int *nn_seq, unsigned long long *label_counts)
 {
 	bool same = max_inner == max_outer;
-	LAUNCH(c, k_nn_search, (n2 + 255) / 256, 256, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
+	LAUNCH(c, k_nn_search, (n2 + kNNThreads - 1) / kNNThreads, kNNThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
 			c->ci_xyzl.p, c->ci_nrm.p, same ? c->ci_xyzl.p : c->co_xyzl.p, same ? c->ci_nrm.p : c->co_nrm.p,
 			vals, n1, buckets, c->gp, radius, max_inner, max_outer, prune, nn_out, nn_seq, label_counts, c->eval_counter);
 }

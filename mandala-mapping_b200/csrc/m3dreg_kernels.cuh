@@ -506,11 +506,35 @@ struct NNQuery {
  * skipped when provably useless, and makes evaluating extra candidates harmless — which is what allows a whole
  * warp to walk one candidate list together.
  *
- * Warp-cooperative bucket scan: every lane holds one query.  The warp fetches 32 compact candidates with one
- * coalesced LDG.128 per lane, stages them in its 512-byte slice of shared memory, then all lanes test the same
- * candidate (broadcast LDS.128) against their own query.  Hot loop: LDS + 3 FSUB + FMUL + 2 FFMA + one compare
- * against thr = min(best, r^2) + a warp vote; label, tie-break, normal load and angle gate run only when some lane
- * passes (rare).  `active` masks lanes for which this cell is irrelevant; they run in lock step (no divergence). */
+ * Warp-cooperative bucket scan: every lane holds one query.  The warp fetches up to 32 compact candidates with one
+ * coalesced LDG.128 per lane and stages them in its 512-byte slice of shared memory (slots beyond the candidate
+ * count get a +inf sentinel).
+ *   HOT  loop (straight-line, unrolled 8/16/32): broadcast LDS.128 + 3 FADD + FMUL + 2 FFMA, then a branch-free
+ *        running minimum over the candidates whose label matches (strict <, ascending position: the earliest of
+ *        equal distances is kept, as in the reference).  No votes, no branches.
+ *   COLD step (once per block of candidates): if the block minimum can beat min(best, r^2), load that candidate's
+ *        normal, apply the angle gate and the exact (dist, l) comparison.  Should the gate reject the block minimum
+ *        (rare: opposite faces of thin structures) the lane re-scans the block sequentially with the full predicate.
+ * `active` masks lanes for which this cell is irrelevant. */
+__device__ __forceinline__ float nn_dist(float qx, float qy, float qz, const float4 &c)
+{
+	float dx = __fsub_rn(qx, c.x), dy = __fsub_rn(qy, c.y), dz = __fsub_rn(qz, c.z);
+	return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+template <int W>
+__device__ __forceinline__ void nn_block_min(const NNQuery &q, const float4 *stage, float &bmin, int &bidx)
+{
+#pragma unroll
+	for (int kk = 0; kk < W; kk++) {
+		float4 c = stage[kk];
+		float d = nn_dist(q.x, q.y, q.z, c);
+		bool better = (__float_as_int(c.w) == q.label) && (d < bmin);
+		bmin = better ? d : bmin;
+		bidx = better ? kk : bidx;
+	}
+}
+
 __device__ __forceinline__ void nn_visit_bucket_warp(NNQuery &q, bool active, const m3dreg_bucket *__restrict__ buckets, int cell, int cap,
 		const float4 *__restrict__ c_xyzl, const float4 *__restrict__ c_nrm, float4 *stage, int lane, unsigned int &evals)
 {
@@ -520,26 +544,36 @@ __device__ __forceinline__ void nn_visit_bucket_warp(NNQuery &q, bool active, co
 	int iter = candidate_stride(npts, cap);
 	int lb = __ldg(bp), le = __ldg(bp + 1);
 	int ncand = (le - lb + iter - 1) / iter;
-	float thr = fminf(q.best, q.r2);
 	for (int k0 = 0; k0 < ncand; k0 += 32) {
 		int cnt = min(32, ncand - k0);
 		__syncwarp();
-		if (lane < cnt) stage[lane] = __ldg(c_xyzl + lb + k0 + lane);
+		stage[lane] = lane < cnt ? __ldg(c_xyzl + lb + k0 + lane) : make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(0x7fffffff));
 		__syncwarp();
 		evals += (unsigned int)cnt;
-#pragma unroll 4
-		for (int kk = 0; kk < cnt; kk++) {
-			float4 c = stage[kk];
-			float dx = __fsub_rn(q.x, c.x), dy = __fsub_rn(q.y, c.y), dz = __fsub_rn(q.z, c.z);
-			float dist = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-			bool pre = active && dist <= thr;
-			if (__any_sync(0xffffffffu, pre)) {
-				if (pre && __float_as_int(c.w) == q.label) {
-					int l = lb + (k0 + kk) * iter;
-					if (dist < q.best || (dist == q.best && l < q.best_l)) {
-						float4 cn = __ldg(c_nrm + lb + k0 + kk);
-						float dot = __fmaf_rn(q.nz, cn.z, __fmaf_rn(q.nx, cn.x, __fmul_rn(q.ny, cn.y)));
-						if (angle_gate(dot)) { q.best = dist; q.best_l = l; thr = fminf(dist, q.r2); }
+		float bmin = INFINITY;
+		int bidx = -1;
+		if (cnt <= 8) nn_block_min<8>(q, stage, bmin, bidx);
+		else if (cnt <= 16) nn_block_min<16>(q, stage, bmin, bidx);
+		else nn_block_min<32>(q, stage, bmin, bidx);
+		/* cold step */
+		if (active && bidx >= 0 && bmin <= fminf(q.best, q.r2)) {
+			int l = lb + (k0 + bidx) * iter;
+			if (bmin < q.best || (bmin == q.best && l < q.best_l)) {
+				float4 cn = __ldg(c_nrm + lb + k0 + bidx);
+				float dot = __fmaf_rn(q.nz, cn.z, __fmaf_rn(q.nx, cn.x, __fmul_rn(q.ny, cn.y)));
+				if (angle_gate(dot)) {
+					q.best = bmin; q.best_l = l;
+				} else {
+					/* the block minimum is inadmissible: sequential re-scan of this block with the full predicate */
+					for (int kk = 0; kk < cnt; kk++) {
+						float4 c = stage[kk];
+						float d = nn_dist(q.x, q.y, q.z, c);
+						int l2 = lb + (k0 + kk) * iter;
+						if (__float_as_int(c.w) == q.label && d <= q.r2 && (d < q.best || (d == q.best && l2 < q.best_l))) {
+							float4 cn2 = __ldg(c_nrm + lb + k0 + kk);
+							float dot2 = __fmaf_rn(q.nz, cn2.z, __fmaf_rn(q.nx, cn2.x, __fmul_rn(q.ny, cn2.y)));
+							if (angle_gate(dot2)) { q.best = d; q.best_l = l2; }
+						}
 					}
 				}
 			}
@@ -571,7 +605,9 @@ __device__ __forceinline__ void axis_gaps(float q, float mn, float res, int ic, 
  * bucket is walked only if some lane of the group cannot exclude it by the lower bound above.
  * q_perm (may be null = identity) maps the query's position to its index in the caller's order: nn_out is written
  * in the caller's order (the reference's layout), nn_seq (may be null) in query-array order for the next stage. */
-__global__ void __launch_bounds__(256) k_nn_search(const float4 *__restrict__ q_xyzl, const float4 *__restrict__ q_nrm,
+constexpr int kNNThreads = 128;
+
+__global__ void __launch_bounds__(kNNThreads, 8) k_nn_search(const float4 *__restrict__ q_xyzl, const float4 *__restrict__ q_nrm,
 		const uint32_t *__restrict__ q_perm, int n_second,
 		const float4 *__restrict__ ci_xyzl, const float4 *__restrict__ ci_nrm, const float4 *__restrict__ co_xyzl, const float4 *__restrict__ co_nrm,
 		const uint32_t *__restrict__ s_vals, int n_first,
@@ -580,10 +616,7 @@ __global__ void __launch_bounds__(256) k_nn_search(const float4 *__restrict__ q_
 		int *__restrict__ nn_out, int *__restrict__ nn_seq, unsigned long long *__restrict__ label_counts,
 		unsigned long long *__restrict__ eval_counter)
 {
-	__shared__ unsigned int s_cnt[4];
-	__shared__ float4 s_stage[8][32];
-	if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
-	__syncthreads();
+	__shared__ float4 s_stage[kNNThreads / 32][32];
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	float4 *stage = s_stage[threadIdx.x >> 5];
@@ -612,12 +645,12 @@ __global__ void __launch_bounds__(256) k_nn_search(const float4 *__restrict__ q_
 			if (h >= 0 && (long long)h < nb) home = h;
 		}
 	}
-	float gx[3], gy[3], gz[3];
-	gx[0] = gx[1] = gx[2] = gy[0] = gy[1] = gy[2] = gz[0] = gz[1] = gz[2] = 0.0f;
+	/* per-axis gaps to the slabs at offset -1 / +1 (0 for the own slab) */
+	float gxl = 0.0f, gxh = 0.0f, gyl = 0.0f, gyh = 0.0f, gzl = 0.0f, gzh = 0.0f;
 	if (prune && home >= 0) {
-		axis_gaps(q.x, mnx, rx, ix, gx[0], gx[2]);
-		axis_gaps(q.y, mny, ry, iy, gy[0], gy[2]);
-		axis_gaps(q.z, mnz, rz, iz, gz[0], gz[2]);
+		axis_gaps(q.x, mnx, rx, ix, gxl, gxh);
+		axis_gaps(q.y, mny, ry, iy, gyl, gyh);
+		axis_gaps(q.z, mnz, rz, iz, gzl, gzh);
 	}
 	unsigned remaining = __ballot_sync(full, home >= 0);
 	while (remaining) {
@@ -626,21 +659,44 @@ __global__ void __launch_bounds__(256) k_nn_search(const float4 *__restrict__ q_
 		int hx = __shfl_sync(full, ix, leader), hy = __shfl_sync(full, iy, leader), hz = __shfl_sync(full, iz, leader);
 		bool mine = (home == h);
 		remaining &= ~__ballot_sync(full, mine);
-		nn_visit_bucket_warp(q, mine, buckets, h, max_inner, ci_xyzl, ci_nrm, stage, lane, evals);
-		int sx = hx == 0 ? 0 : -1, sy = hy == 0 ? 0 : -1, sz = hz == 0 ? 0 : -1;
-		int stx = hx == nbx - 1 ? 1 : 2, sty = hy == nby - 1 ? 1 : 2, stz = hz == nbz - 1 ? 1 : 2;
-		for (int i = sx; i < stx; i++)
-		for (int j = sy; j < sty; j++)
-		for (int k = sz; k < stz; k++) {
-			int cell = h + i * nby * nbz + j * nbz + k;
-			if (cell == h || cell < 0 || (long long)cell >= nb) continue;
-			bool need = mine;
-			if (prune) {
-				float lbd = __fmaf_rn(gz[k + 1], gz[k + 1], __fmaf_rn(gx[i + 1], gx[i + 1], __fmul_rn(gy[j + 1], gy[j + 1])));
-				need = mine && !(lbd > q.best || lbd > q.r2);
+		/* phase 0: the home bucket (offset 13); phase 1: whichever of the other 26 buckets can still matter.
+		 * One visit call site keeps the kernel small enough for the instruction cache. */
+#pragma unroll 1
+		for (int phase = 0; phase < 2; phase++) {
+			unsigned need_mask = 0;    /* bit o = (i+1)*9 + (j+1)*3 + (k+1) */
+			if (phase == 0) {
+				need_mask = mine ? (1u << 13) : 0u;
+			} else if (mine) {
+				float lim = fminf(q.best, q.r2);
+#pragma unroll
+				for (int o = 0; o < 27; o++) {
+					if (o == 13) continue;
+					const int i = o / 9 - 1, j = (o / 3) % 3 - 1, k = o % 3 - 1;
+					float gx = i < 0 ? gxl : (i > 0 ? gxh : 0.0f), gy = j < 0 ? gyl : (j > 0 ? gyh : 0.0f), gz = k < 0 ? gzl : (k > 0 ? gzh : 0.0f);
+					float lbd = __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
+					bool ok = !prune || !(lbd > lim);
+					ok = ok && (unsigned)(hx + i) < (unsigned)nbx && (unsigned)(hy + j) < (unsigned)nby && (unsigned)(hz + k) < (unsigned)nbz;
+					need_mask |= ok ? (1u << o) : 0u;
+				}
 			}
-			if (!__any_sync(full, need)) continue;
-			nn_visit_bucket_warp(q, need, buckets, cell, max_outer, co_xyzl, co_nrm, stage, lane, evals);
+			unsigned warp_mask = __reduce_or_sync(full, need_mask);
+			while (warp_mask) {
+				int o = __ffs(warp_mask) - 1;
+				warp_mask &= warp_mask - 1;
+				int i = o / 9 - 1, j = (o / 3) % 3 - 1, k = o % 3 - 1;
+				int cell = h + i * nby * nbz + j * nbz + k;
+				if (cell < 0 || (long long)cell >= nb) continue;
+				bool need = (need_mask >> o) & 1u;
+				if (prune && need && o != 13) {   /* re-check with the live best */
+					float gx = i < 0 ? gxl : (i > 0 ? gxh : 0.0f), gy = j < 0 ? gyl : (j > 0 ? gyh : 0.0f), gz = k < 0 ? gzl : (k > 0 ? gzh : 0.0f);
+					float lbd = __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
+					need = !(lbd > q.best || lbd > q.r2);
+				}
+				if (!__any_sync(full, need)) continue;
+				bool inner = (o == 13);
+				nn_visit_bucket_warp(q, need, buckets, cell, inner ? max_inner : max_outer, inner ? ci_xyzl : co_xyzl,
+						inner ? ci_nrm : co_nrm, stage, lane, evals);
+			}
 		}
 	}
 	if (eval_counter && lane == 0 && evals) atomicAdd(eval_counter, (unsigned long long)evals);
@@ -650,10 +706,13 @@ __global__ void __launch_bounds__(256) k_nn_search(const float4 *__restrict__ q_
 		if (nn_seq) nn_seq[qi] = result;
 		nn_out[q_perm ? __ldg(q_perm + qi) : (uint32_t)qi] = result;
 	}
-	if (label_counts) {
-		if (qi < n_second && result >= 0 && q.label >= 0 && q.label < 4) atomicAdd(&s_cnt[q.label], 1u);
-		__syncthreads();
-		if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(&label_counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+	if (label_counts) {   /* per-label match counts (gpu6DSLAM.cpp:323-357): warp ballots, one atomic per label per warp */
+		bool hit = qi < n_second && result >= 0;
+#pragma unroll
+		for (int L = 0; L < 4; L++) {
+			unsigned m = __ballot_sync(full, hit && q.label == L);
+			if (m && lane == L) atomicAdd(&label_counts[L], (unsigned long long)__popc(m));
+		}
 	}
 }
 
