@@ -93,7 +93,7 @@ struct m3dreg_ctx {
 	DevBuf<int> nn, nn_seq;
 	DevBuf<m3dreg_point> aos_a, aos_b;
 	DevBuf<m3dreg_obs_nn> obs;
-	DevBuf<double> partials;
+	DevBuf<double> partials, ndt_acc, ndt_qacc;
 	DevBuf<m3dreg_hash_element> table;
 	DevBuf<float> d_poses1;      /* sweep: round-tripped poses, 16 floats per scan */
 	DevBuf<double> d_pose6;      /* sweep: tx,ty,tz,om,fi,ka per scan             */
@@ -125,7 +125,7 @@ struct m3dreg_ctx {
 
 	/* what the last fused iteration left behind (export hooks) */
 	int last_n_first = 0, last_n_second = 0, last_sorted = 0;
-	bool last_valid = false;
+	bool last_valid = false, last_nn_valid = true;
 };
 
 namespace {
@@ -212,7 +212,7 @@ int ensure_second(m3dreg_ctx *c, size_t n)
 
 int ensure_partials(m3dreg_ctx *c)
 {
-	return c->partials.ensure((size_t)c->sm_count * 8 * kMomentCount);
+	return c->partials.ensure((size_t)c->sm_count * 8 * kPartialCols);
 }
 
 /* stable LSD radix sort of (keys[0], vals[0]) by the low `bits` bits; returns the index (0/1) of the buffers
@@ -289,7 +289,8 @@ void build_grid_fused(m3dreg_ctx *c, int n1, const m3dreg_reg_params *prm, int s
 	LAUNCH(c, k_init_buckets, grid_for(c, (long long)c->buckets.cap * 3, 256), 256, c->buckets.p, c->gp, 0LL);
 	LAUNCH(c, k_finalize_grid, grid_for(c, n1, 256), 256, c->keys[cur].p, c->vals[cur].p, n1, c->gp, c->buckets.p,
 			(m3dreg_hash_element *)nullptr);
-	compact_candidates(c, c->keys[cur].p, c->vals[cur].p, n1, c->buckets.p, prm->max_inner, prm->max_outer);
+	if (prm->mode != M3DREG_MODE_NDT)
+		compact_candidates(c, c->keys[cur].p, c->vals[cur].p, n1, c->buckets.p, prm->max_inner, prm->max_outer);
 	c->last_sorted = cur;
 }
 
@@ -309,6 +310,10 @@ int plan_buckets(m3dreg_ctx *c, const m3dreg_reg_params *prm, int *sort_bits)
 	if (gp.number_of_buckets > cap) return M3DREG_E_TOO_MANY_BUCKETS;
 	int e = c->buckets.ensure((size_t)cap);
 	if (e) return e;
+	if (prm->mode == M3DREG_MODE_NDT) {
+		if ((e = c->ndt_acc.ensure(c->buckets.cap * 12))) return e;
+		if ((e = c->ndt_qacc.ensure(c->buckets.cap * 4))) return e;
+	}
 	*sort_bits = bits_for((long long)c->buckets.cap);
 	return 0;
 }
@@ -333,6 +338,23 @@ bool valid_params(const m3dreg_reg_params *p)
 	return true;
 }
 
+/* NDT: per-bucket statistics of the gridded cloud (once per grid) and the query pass + bucket reduction (per pair). */
+void ndt_bucket_stats(m3dreg_ctx *c, const float4 *lx, int n1)
+{
+	int cur = c->last_sorted;
+	LAUNCH(c, k_ndt_zero, grid_for(c, (long long)c->buckets.cap * 16, 256), 256, c->ndt_acc.p, c->ndt_qacc.p, c->gp, 1);
+	LAUNCH(c, k_ndt_accumulate_points, grid_for(c, n1, 256), 256, c->keys[cur].p, c->vals[cur].p, n1, c->g_xyzl.p, lx, c->gp, c->ndt_acc.p);
+	LAUNCH(c, k_ndt_finalize_buckets, grid_for(c, (long long)c->buckets.cap, 256), 256, c->buckets.p, c->gp, c->ndt_acc.p);
+}
+
+void ndt_queries_and_reduce(m3dreg_ctx *c, int n2, const FinalizeArgs &fin, bool zero_qacc)
+{
+	if (zero_qacc) LAUNCH(c, k_ndt_zero, grid_for(c, (long long)c->buckets.cap * 4, 256), 256, c->ndt_acc.p, c->ndt_qacc.p, c->gp, 0);
+	LAUNCH(c, k_ndt_accumulate_queries, grid_for(c, n2, 256), 256, c->q_xyzl.p, n2, c->gp, c->ndt_acc.p, c->ndt_qacc.p);
+	LAUNCH(c, k_ndt_normal_equations, grid_for(c, (long long)c->buckets.cap, kNeqThreads, 2), kNeqThreads, c->ndt_acc.p, c->ndt_qacc.p, c->gp,
+			c->partials.p, c->ticket, fin);
+}
+
 /* One registerLastArrivedScan iteration, fully on the device.  first local cloud = (lx, ln), queries already in q_*. */
 void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, int n2,
 		const m3dreg_reg_params *prm, int sort_bits)
@@ -342,6 +364,27 @@ void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int
 	LAUNCH(c, k_transform_soa<true>, grid_for(c, n1, 256), 256, lx, ln, n1, c->ps->pose1, c->g_xyzl.p, c->g_nrm.p, c->bounds);
 	if (prof) cudaEventRecord(c->pev[1], c->stream);
 	build_grid_fused(c, n1, prm, sort_bits);
+	if (prm->mode == M3DREG_MODE_NDT) {
+		ndt_bucket_stats(c, lx, n1);
+		if (prof) { cudaEventRecord(c->pev[2], c->stream); cudaEventRecord(c->pev[3], c->stream); }
+		FinalizeArgs fin;
+		fin.ps = c->ps; fin.neq_out = nullptr; fin.accumulate = 0; fin.solve = 1; fin.dof = prm->dof;
+		fin.obs_threshold = prm->obs_threshold; fin.pose6_in = nullptr; fin.bounds_reset = c->bounds;
+		fin.label_counts_reset = nullptr;
+		ndt_queries_and_reduce(c, n2, fin, false);
+		if (prof) {
+			cudaEventRecord(c->pev[4], c->stream);
+			cudaEventSynchronize(c->pev[4]);
+			for (int k = 0; k < M3DREG_STAGE_COUNT; k++) {
+				float ms = 0.0f;
+				cudaEventElapsedTime(&ms, c->pev[k], c->pev[k + 1]);
+				c->stage_ms[k] += ms;
+			}
+			c->stage_iters++;
+		}
+		c->last_n_first = n1; c->last_n_second = n2; c->last_valid = true; c->last_nn_valid = false;
+		return;
+	}
 	if (prof) cudaEventRecord(c->pev[2], c->stream);
 	launch_nn(c, c->act_perm, n2, c->vals[c->last_sorted].p, n1, c->buckets.p, prm->search_radius, prm->max_inner, prm->max_outer, 1,
 			c->nn.p, c->nn_seq.p, c->label_counts);
@@ -354,6 +397,7 @@ void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int
 	fin.label_counts_reset = c->label_counts;
 	if (prof) cudaEventRecord(c->pev[3], c->stream);
 	LAUNCH(c, k_normal_equations<ObsFromNN>, grid_for(c, n2, kNeqThreads, 4), kNeqThreads, src, n2, c->partials.p, c->ticket, fin);
+	c->last_nn_valid = true;
 	if (prof) {
 		cudaEventRecord(c->pev[4], c->stream);
 		cudaEventSynchronize(c->pev[4]);
@@ -458,7 +502,7 @@ void m3dreg_destroy(m3dreg_ctx *c)
 	c->q_xyzl.release(); c->q_nrm.release(); c->l_xyzl.release(); c->l_nrm.release();
 	for (int k = 0; k < 2; k++) { c->keys[k].release(); c->vals[k].release(); }
 	c->hist.release(); c->buckets.release(); c->nn.release(); c->nn_seq.release(); c->aos_a.release(); c->aos_b.release();
-	c->obs.release(); c->partials.release(); c->table.release(); c->d_poses1.release(); c->d_pose6.release();
+	c->obs.release(); c->partials.release(); c->ndt_acc.release(); c->ndt_qacc.release(); c->table.release(); c->d_poses1.release(); c->d_pose6.release();
 	if (c->ps) cudaFree(c->ps);   /* base of the small block */
 	if (c->h) cudaFreeHost(c->h);
 	for (int k = 0; k <= M3DREG_STAGE_COUNT; k++) if (c->pev[k]) cudaEventDestroy(c->pev[k]);
@@ -943,6 +987,7 @@ int m3dreg_icp_iteration_host(m3dreg_ctx *c, const m3dreg_point *first_local, in
 	c->active = false;
 	if (e) return e;
 	if (nn_out) {
+		if (prm->mode == M3DREG_MODE_NDT) CK(cudaMemsetAsync(c->nn.p, 0xFF, (size_t)n2 * sizeof(int), c->stream));
 		CK(cudaMemcpyAsync(nn_out, c->nn.p, (size_t)n2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
 	}
@@ -978,7 +1023,7 @@ int m3dreg_export_last_grid(m3dreg_ctx *c, m3dreg_grid_params *params_out, m3dre
 int m3dreg_export_last_nn(m3dreg_ctx *c, int *nn_out, int nn_cap)
 {
 	if (!c || !nn_out) return M3DREG_E_INVALID_ARG;
-	if (!c->last_valid) return M3DREG_E_BAD_SLOT;
+	if (!c->last_valid || !c->last_nn_valid) return M3DREG_E_BAD_SLOT;   /* NDT has no correspondences */
 	if (nn_cap < c->last_n_second) return M3DREG_E_SIZE_MISMATCH;
 	CK(cudaSetDevice(c->dev));
 	CK(cudaMemcpyAsync(nn_out, c->nn.p, (size_t)c->last_n_second * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1039,11 +1084,21 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 					c->g_xyzl.p, c->g_nrm.p, c->bounds);
 			if ((e = plan_buckets(c, prm, &sort_bits))) return e;
 			build_grid_fused(c, A.n, prm, sort_bits);
+			if (prm->mode == M3DREG_MODE_NDT) ndt_bucket_stats(c, A.xyzl, A.n);
 			cur_i = i;
 		}
 		if ((e = ensure_second(c, (size_t)B.n))) return e;
 		LAUNCH(c, k_transform_soa<false>, grid_for(c, B.n, 256), 256, B.sx, B.sn, B.n, c->d_poses1.p + 16 * (size_t)j,
 				c->q_xyzl.p, c->q_nrm.p, (uint32_t *)nullptr);
+		if (prm->mode == M3DREG_MODE_NDT) {
+			FinalizeArgs fin;
+			fin.ps = nullptr; fin.neq_out = d_neq + (size_t)i * kNeqCount; fin.accumulate = 1; fin.solve = 0; fin.dof = prm->dof;
+			fin.obs_threshold = prm->obs_threshold; fin.pose6_in = c->d_pose6.p + 6 * (size_t)i; fin.bounds_reset = nullptr;
+			fin.label_counts_reset = nullptr;
+			ndt_queries_and_reduce(c, B.n, fin, true);
+			c->last_n_first = A.n; c->last_n_second = B.n; c->last_valid = true; c->last_nn_valid = false;
+			continue;
+		}
 		launch_nn(c, B.perm, B.n, c->vals[c->last_sorted].p, A.n, c->buckets.p, prm->search_radius, prm->max_inner, prm->max_outer, 1,
 				c->nn.p, c->nn_seq.p, c->label_counts);
 		ObsFromNN src;

@@ -25,6 +25,7 @@
 namespace m3d {
 
 constexpr int kMomentCount = 24;   /* S, M1[3], M2[6], L1[3], L2[9], n_obs, (pad) */
+constexpr int kPartialCols = 28;   /* row width of the per-block partial sums (ICP uses 24 of them, NDT all 28) */
 constexpr int kNeqCount = 28;      /* 21 upper-tri AtPA + 6 AtPl + count */
 
 /* flags[] slots */
@@ -969,6 +970,46 @@ struct FinalizeArgs {
 	unsigned long long *label_counts_reset;
 };
 
+/* What ONE thread of the last block does with the finished 28-double system: publish / accumulate it, and (fused
+ * loop) gate on the observation count, Cholesky, pose update, Euler round trip for the next iteration, resets. */
+__device__ inline void neq_tail(const double *neq, const FinalizeArgs &fin)
+{
+	if (fin.neq_out) {
+		for (int k = 0; k < kNeqCount; k++) fin.neq_out[k] = fin.accumulate ? fin.neq_out[k] + neq[k] : neq[k];
+	}
+	if (fin.solve && fin.ps) {
+		PoseState *ps = fin.ps;
+		for (int k = 0; k < kNeqCount; k++) ps->neq[k] = neq[k];
+		long long n_obs = (long long)(neq[27] + 0.5);
+		ps->n_obs = n_obs;
+		int status = M3DREG_E_TOO_FEW_OBS;
+		double x[6] = {0, 0, 0, 0, 0, 0};
+		if (n_obs > (long long)fin.obs_threshold) {                       /* gpu6DSLAM.cpp:402 */
+			status = solve_packed(neq, fin.dof, x);
+			if (status == 0) {
+				/* registerLS tail (cudaWrapper.cpp:574-579 / 641-646) + EulerToMatrix (gpu6DSLAM.cpp:408-413) */
+				ps->pose6[0] += x[0]; ps->pose6[1] += x[1]; ps->pose6[2] += x[2];
+				if (fin.dof == 6) { ps->pose6[3] += x[3]; ps->pose6[4] += x[4]; ps->pose6[5] += x[5]; }
+				else ps->pose6[5] += x[3];
+				float of[3] = {(float)ps->pose6[3], (float)ps->pose6[4], (float)ps->pose6[5]};
+				float t[3] = {(float)ps->pose6[0], (float)ps->pose6[1], (float)ps->pose6[2]};
+				euler_to_matrix(of, t, ps->m);
+			}
+		}
+		for (int k = 0; k < 6; k++) ps->x[k] = x[k];
+		ps->status = status;
+		ps->iterations += 1;
+		pose_prepare(ps);   /* next iteration's Euler round trip */
+	}
+	if (fin.bounds_reset) {
+		fin.bounds_reset[0] = fin.bounds_reset[1] = fin.bounds_reset[2] = 0xFFFFFFFFu;
+		fin.bounds_reset[3] = fin.bounds_reset[4] = fin.bounds_reset[5] = 0u;
+	}
+	if (fin.label_counts_reset) {
+		fin.label_counts_reset[0] = fin.label_counts_reset[1] = fin.label_counts_reset[2] = fin.label_counts_reset[3] = 0ull;
+	}
+}
+
 constexpr int kNeqThreads = 256;
 
 template <class Src>
@@ -1005,7 +1046,7 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(Src src, int n
 		double s = 0;
 #pragma unroll
 		for (int k = 0; k < kNeqThreads / 32; k++) s += sm[k][threadIdx.x];
-		partials[(size_t)blockIdx.x * kMomentCount + threadIdx.x] = s;
+		partials[(size_t)blockIdx.x * kPartialCols + threadIdx.x] = s;
 	}
 	__threadfence();
 	__syncthreads();
@@ -1020,7 +1061,7 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(Src src, int n
 	__shared__ double tot[kMomentCount];
 	for (int col = wid; col < kMomentCount; col += kNeqThreads / 32) {     /* warp per column, lanes stride the rows */
 		double s = 0;
-		for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * kMomentCount + col);
+		for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * kPartialCols + col);
 		s = warp_sum(s);
 		if (lane == 0) tot[col] = s;
 	}
@@ -1030,40 +1071,7 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(Src src, int n
 		double neq[kNeqCount];
 		const double *p6 = fin.ps ? fin.ps->pose6 : fin.pose6_in;
 		moments_to_neq(tot, p6[3], p6[4], p6[5], neq);
-		if (fin.neq_out) {
-			for (int k = 0; k < kNeqCount; k++) fin.neq_out[k] = fin.accumulate ? fin.neq_out[k] + neq[k] : neq[k];
-		}
-		if (fin.solve && fin.ps) {
-			PoseState *ps = fin.ps;
-			for (int k = 0; k < kNeqCount; k++) ps->neq[k] = neq[k];
-			long long n_obs = (long long)(tot[22] + 0.5);
-			ps->n_obs = n_obs;
-			int status = M3DREG_E_TOO_FEW_OBS;
-			double x[6] = {0, 0, 0, 0, 0, 0};
-			if (n_obs > (long long)fin.obs_threshold) {                       /* gpu6DSLAM.cpp:402 */
-				status = solve_packed(neq, fin.dof, x);
-				if (status == 0) {
-					/* registerLS tail (cudaWrapper.cpp:574-579 / 641-646) + EulerToMatrix (gpu6DSLAM.cpp:408-413) */
-					ps->pose6[0] += x[0]; ps->pose6[1] += x[1]; ps->pose6[2] += x[2];
-					if (fin.dof == 6) { ps->pose6[3] += x[3]; ps->pose6[4] += x[4]; ps->pose6[5] += x[5]; }
-					else ps->pose6[5] += x[3];
-					float of[3] = {(float)ps->pose6[3], (float)ps->pose6[4], (float)ps->pose6[5]};
-					float t[3] = {(float)ps->pose6[0], (float)ps->pose6[1], (float)ps->pose6[2]};
-					euler_to_matrix(of, t, ps->m);
-				}
-			}
-			for (int k = 0; k < 6; k++) ps->x[k] = x[k];
-			ps->status = status;
-			ps->iterations += 1;
-			pose_prepare(ps);   /* next iteration's Euler round trip */
-		}
-		if (fin.bounds_reset) {
-			fin.bounds_reset[0] = fin.bounds_reset[1] = fin.bounds_reset[2] = 0xFFFFFFFFu;
-			fin.bounds_reset[3] = fin.bounds_reset[4] = fin.bounds_reset[5] = 0u;
-		}
-		if (fin.label_counts_reset) {
-			fin.label_counts_reset[0] = fin.label_counts_reset[1] = fin.label_counts_reset[2] = fin.label_counts_reset[3] = 0ull;
-		}
+		neq_tail(neq, fin);
 	}
 }
 
@@ -1120,6 +1128,246 @@ __global__ void k_sweep_solve(const double *__restrict__ neq, int begin, int end
 __global__ void k_zero_f64(double *p, int n)
 {
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0.0;
+}
+
+/* ================================ NDT (point-to-distribution) ====================================================
+ * Not in the reference; definition of record: oracle/m3d_oracle.c orc_ndt_normal_equations.
+ * Per bucket of the gridded (moving) cloud: mean / covariance of its points' GLOBAL coordinates, accumulated
+ * relative to the cell centre in fp64, and the mean of their LOCAL coordinates; W = (Sigma + eps I)^-1.
+ * All queries that fall into a bucket share its (mu, W, Jacobian), so the query pass only needs a COUNT and a
+ * coordinate SUM per bucket; the normal equations are then a reduction over buckets:
+ *     N += cnt * A^T W A,   rhs += A^T W (cnt*mu_g - sum q),   A = -[I | J(mu_l)].
+ * Layout: acc[b*12 ..] = {sum p'(3), sum p'p'^T(6), sum p_local(3)} -> finalised in place to
+ *         {mu_g(3), mu_l(3), W(6: xx,xy,xz,yy,yz,zz)}; W.xx == 0 marks an unusable bucket.  qacc[b*4..] = {cnt, sum q(3)}. */
+constexpr int kNdtMinPoints = 5;
+constexpr double kNdtRegRel = 0.05;
+
+__global__ void k_ndt_zero(double *__restrict__ acc, double *__restrict__ qacc, const m3dreg_grid_params *__restrict__ gp, int zero_acc)
+{
+	long long nb = gp->number_of_buckets;
+	long long total = nb * (zero_acc ? 16 : 4);
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+		if (i < nb * 4) qacc[i] = 0.0;
+		else acc[i - nb * 4] = 0.0;
+	}
+}
+
+__device__ __forceinline__ void cell_centre(uint32_t key, const m3dreg_grid_params *gp, double &cx, double &cy, double &cz)
+{
+	int nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
+	int ix = (int)(key / (uint32_t)(nby * nbz)), iy = (int)((key / (uint32_t)nbz) % (uint32_t)nby), iz = (int)(key % (uint32_t)nbz);
+	cx = (double)gp->bounding_box_min_X + ((double)ix + 0.5) * (double)gp->resolution_X;
+	cy = (double)gp->bounding_box_min_Y + ((double)iy + 0.5) * (double)gp->resolution_Y;
+	cz = (double)gp->bounding_box_min_Z + ((double)iz + 0.5) * (double)gp->resolution_Z;
+}
+
+/* Segmented warp reduction over runs of equal keys (lanes with key 0xFFFFFFFF are idle): after the call the FIRST
+ * lane of every run holds the run total. */
+template <int NV>
+__device__ __forceinline__ void warp_segmented_sum(uint32_t key, double (&v)[NV], bool &is_head)
+{
+	const unsigned full = 0xffffffffu;
+	int lane = threadIdx.x & 31;
+	uint32_t prev = __shfl_up_sync(full, key, 1);
+	is_head = (lane == 0) || (prev != key);
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		uint32_t k2 = __shfl_down_sync(full, key, o);
+		bool take = (lane + o < 32) && (k2 == key);
+#pragma unroll
+		for (int i = 0; i < NV; i++) {
+			double t = __shfl_down_sync(full, v[i], o);
+			if (take) v[i] += t;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) k_ndt_accumulate_points(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int n,
+		const float4 *__restrict__ g_xyzl, const float4 *__restrict__ l_xyzl, const m3dreg_grid_params *__restrict__ gp,
+		double *__restrict__ acc)
+{
+	if (gp->number_of_buckets <= 0) return;
+	int nround = (n + 31) & ~31;
+	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
+		uint32_t key = 0xFFFFFFFFu;
+		double v[12];
+#pragma unroll
+		for (int i = 0; i < 12; i++) v[i] = 0.0;
+		if (p < n) {
+			key = __ldg(keys + p);
+			uint32_t idx = __ldg(vals + p);
+			float4 g = __ldg(g_xyzl + idx), l = __ldg(l_xyzl + idx);
+			double cx, cy, cz;
+			cell_centre(key, gp, cx, cy, cz);
+			double x = (double)g.x - cx, y = (double)g.y - cy, z = (double)g.z - cz;
+			v[0] = x; v[1] = y; v[2] = z;
+			v[3] = x * x; v[4] = x * y; v[5] = x * z; v[6] = y * y; v[7] = y * z; v[8] = z * z;
+			v[9] = l.x; v[10] = l.y; v[11] = l.z;
+		}
+		bool head;
+		warp_segmented_sum<12>(key, v, head);
+		if (head && key != 0xFFFFFFFFu) {
+			double *a = acc + (size_t)key * 12;
+#pragma unroll
+			for (int i = 0; i < 12; i++) atomicAdd(a + i, v[i]);
+		}
+	}
+}
+
+__device__ __host__ inline bool sym3_inverse(const double *S, double *W)
+{
+	double a = S[0], b = S[1], c = S[2], d = S[3], e = S[4], f = S[5];
+	double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+	double det = a * c00 + b * c01 + c * c02;
+	if (!(det > 0.0)) return false;
+	double id = 1.0 / det;
+	W[0] = c00 * id; W[1] = c01 * id; W[2] = c02 * id;
+	W[3] = (a * f - c * c) * id; W[4] = (b * c - a * e) * id; W[5] = (a * d - b * b) * id;
+	return true;
+}
+
+__global__ void k_ndt_finalize_buckets(const m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp,
+		double *__restrict__ acc)
+{
+	long long nb = gp->number_of_buckets;
+	double res = (double)gp->resolution_X;
+	double eps = (kNdtRegRel * res) * (kNdtRegRel * res);
+	for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (long long)gridDim.x * blockDim.x) {
+		int n = buckets[b].number_of_points;
+		double *a = acc + (size_t)b * 12;
+		if (n < kNdtMinPoints) { a[6] = 0.0; continue; }
+		double s[3] = {a[0], a[1], a[2]}, ss[6] = {a[3], a[4], a[5], a[6], a[7], a[8]}, sl[3] = {a[9], a[10], a[11]};
+		double inv = 1.0 / n, d = 1.0 / (n - 1);
+		double m[3] = {s[0] * inv, s[1] * inv, s[2] * inv};
+		double S[6], W[6];
+		S[0] = (ss[0] - n * m[0] * m[0]) * d + eps; S[1] = (ss[1] - n * m[0] * m[1]) * d; S[2] = (ss[2] - n * m[0] * m[2]) * d;
+		S[3] = (ss[3] - n * m[1] * m[1]) * d + eps; S[4] = (ss[4] - n * m[1] * m[2]) * d; S[5] = (ss[5] - n * m[2] * m[2]) * d + eps;
+		if (!sym3_inverse(S, W)) { a[6] = 0.0; continue; }
+		double cx, cy, cz;
+		cell_centre((uint32_t)b, gp, cx, cy, cz);
+		a[0] = m[0] + cx; a[1] = m[1] + cy; a[2] = m[2] + cz;
+		a[3] = sl[0] * inv; a[4] = sl[1] * inv; a[5] = sl[2] * inv;
+#pragma unroll
+		for (int i = 0; i < 6; i++) a[6 + i] = W[i];
+	}
+}
+
+__global__ void __launch_bounds__(256) k_ndt_accumulate_queries(const float4 *__restrict__ q_xyzl, int n2,
+		const m3dreg_grid_params *__restrict__ gp, const double *__restrict__ acc, double *__restrict__ qacc)
+{
+	long long nb = gp->number_of_buckets;
+	if (nb <= 0) return;
+	float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
+	float rx = gp->resolution_X, ry = gp->resolution_Y, rz = gp->resolution_Z;
+	int nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
+	int nround = (n2 + 31) & ~31;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+		uint32_t key = 0xFFFFFFFFu;
+		double v[4] = {0.0, 0.0, 0.0, 0.0};
+		if (i < n2) {
+			float4 p = __ldg(q_xyzl + i);
+			bool inside = !(p.x < mnx || p.x > gp->bounding_box_max_X) && !(p.y < mny || p.y > gp->bounding_box_max_Y) &&
+					!(p.z < mnz || p.z > gp->bounding_box_max_Z);
+			if (inside) {
+				int h = cell_of(p.x, mnx, rx) * nby * nbz + cell_of(p.y, mny, ry) * nbz + cell_of(p.z, mnz, rz);
+				if (h >= 0 && (long long)h < nb && __ldg(acc + (size_t)h * 12 + 6) > 0.0) {
+					key = (uint32_t)h;
+					v[0] = 1.0; v[1] = p.x; v[2] = p.y; v[3] = p.z;
+				}
+			}
+		}
+		bool head;
+		warp_segmented_sum<4>(key, v, head);
+		if (head && key != 0xFFFFFFFFu) {
+			double *a = qacc + (size_t)key * 4;
+#pragma unroll
+			for (int k = 0; k < 4; k++) atomicAdd(a + k, v[k]);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(kNeqThreads) k_ndt_normal_equations(const double *__restrict__ acc, const double *__restrict__ qacc,
+		const m3dreg_grid_params *__restrict__ gp, double *__restrict__ partials, unsigned int *__restrict__ ticket, FinalizeArgs fin)
+{
+	__shared__ double sm[kNeqThreads / 32][kPartialCols];
+	__shared__ bool is_last;
+	long long nb = gp->number_of_buckets;
+	const double *p6 = fin.ps ? fin.ps->pose6 : fin.pose6_in;
+	double om = p6[3], fi = p6[4], ka = p6[5];
+	double so = sin(om), co = cos(om), sf = sin(fi), cf = cos(fi), sk = sin(ka), ck = cos(ka);
+	double R11 = cf * ck, R12 = -cf * sk;
+	double R21 = co * sk + so * sf * ck, R22 = co * ck - so * sf * sk, R23 = -so * cf;
+	double R31 = so * sk - co * sf * ck, R32 = so * ck + co * sf * sk, R33 = co * cf;
+	const double C[3][3][3] = {
+		{{0, 0, 0}, {-sf * ck, sf * sk, cf}, {R12, -R11, 0}},
+		{{-R31, -R32, -R33}, {so * cf * ck, -so * cf * sk, so * sf}, {R22, -R21, 0}},
+		{{R21, R22, R23}, {-co * cf * ck, co * cf * sk, -co * sf}, {R32, -R31, 0}}};
+	double sum[kPartialCols];
+#pragma unroll
+	for (int k = 0; k < kPartialCols; k++) sum[k] = 0.0;
+	for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (long long)gridDim.x * blockDim.x) {
+		const double *a = acc + (size_t)b * 12;
+		const double *qa = qacc + (size_t)b * 4;
+		double cnt = qa[0];
+		if (!(a[6] > 0.0) || !(cnt > 0.0)) continue;
+		double A[3][6];
+#pragma unroll
+		for (int r = 0; r < 3; r++)
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				A[r][c] = (r == c) ? -1.0 : 0.0;
+				A[r][3 + c] = -(C[r][c][0] * a[3] + C[r][c][1] * a[4] + C[r][c][2] * a[5]);
+			}
+		double W[3][3] = {{a[6], a[7], a[8]}, {a[7], a[9], a[10]}, {a[8], a[10], a[11]}};
+		double sl[3] = {cnt * a[0] - qa[1], cnt * a[1] - qa[2], cnt * a[2] - qa[3]};
+		int k = 0;
+#pragma unroll
+		for (int i = 0; i < 6; i++) {
+			double wa[3];
+#pragma unroll
+			for (int r = 0; r < 3; r++) wa[r] = A[0][i] * W[0][r] + A[1][i] * W[1][r] + A[2][i] * W[2][r];
+#pragma unroll
+			for (int j = i; j < 6; j++) sum[k++] += cnt * (wa[0] * A[0][j] + wa[1] * A[1][j] + wa[2] * A[2][j]);
+			sum[21 + i] += wa[0] * sl[0] + wa[1] * sl[1] + wa[2] * sl[2];
+		}
+		sum[27] += cnt;
+	}
+	int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+	for (int k = 0; k < kPartialCols; k++) {
+		double s = warp_sum(sum[k]);
+		if (lane == 0) sm[wid][k] = s;
+	}
+	__syncthreads();
+	if (threadIdx.x < kPartialCols) {
+		double s = 0;
+#pragma unroll
+		for (int k = 0; k < kNeqThreads / 32; k++) s += sm[k][threadIdx.x];
+		partials[(size_t)blockIdx.x * kPartialCols + threadIdx.x] = s;
+	}
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned int t = atomicAdd(ticket, 1u);
+		is_last = (t == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (!is_last) return;
+	__threadfence();
+	__shared__ double tot[kPartialCols];
+	for (int col = wid; col < kPartialCols; col += kNeqThreads / 32) {
+		double s = 0;
+		for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * kPartialCols + col);
+		s = warp_sum(s);
+		if (lane == 0) tot[col] = s;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		*ticket = 0;
+		double neq[kNeqCount];
+		for (int k = 0; k < kNeqCount; k++) neq[k] = tot[k];
+		neq_tail(neq, fin);
+	}
 }
 
 } /* namespace m3d */

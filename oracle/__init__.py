@@ -199,6 +199,22 @@ def transform_cloud(cloud, m):
     return out
 
 
+def ndt_normal_equations(first_global, first_local, second_global, table, buckets, gp, pose6):
+    neq = np.zeros(28)
+    p = np.asarray(pose6, dtype=np.float64).copy()
+    lib().orc_ndt_normal_equations.restype = C.c_int64
+    n = lib().orc_ndt_normal_equations(_ptr(first_global), _ptr(first_local), C.c_int(len(first_global)), _ptr(second_global),
+                                       C.c_int(len(second_global)), _ptr(table), _ptr(buckets), _ptr(gp), _ptr(p), _ptr(neq))
+    return int(n), neq
+
+
+def solve_packed(neq, dof=6):
+    x = np.zeros(6)
+    q = np.ascontiguousarray(neq, dtype=np.float64)
+    st = lib().orc_solve_packed(_ptr(q), C.c_int(dof), _ptr(x))
+    return st, x[:dof]
+
+
 def icp_iteration(first_local, second_global, pose, params: RegParams, want_nn=False):
     pose = np.ascontiguousarray(pose, dtype=np.float32).reshape(16).copy()
     scratch = np.zeros_like(first_local)

@@ -531,6 +531,139 @@ void orc_transform_cloud(const orc_point *in, orc_point *out, int n, const float
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * NDT, point-to-distribution.  The reference has no NDT (only an unused #include, include/gpu6DSLAM.h:17), so this
+ * is the DEFINITION the CUDA path is checked against (tolerance; parity unpinned), built from the reference's own
+ * pieces: the same grid (L16:23-243), the same pose parametrisation and Jacobian (L16:278-353), the same solve.
+ *   bucket b with n_b >= 5 points of the (transformed) first cloud:
+ *        mu_g, Sigma_g  mean / sample covariance of the GLOBAL coordinates (accumulated relative to the cell centre)
+ *        mu_l           mean of the same points' LOCAL coordinates
+ *        W_b = (Sigma_g + eps I)^-1,  eps = (0.05 * resolution)^2
+ *   query q (second cloud, global) inside the box whose home bucket is such a b:
+ *        l = mu_g - q,  A = -[ I | J(mu_l) ]   (3x6, J = dR/d(om,fi,ka) mu_l),  weight matrix W_b
+ *   N = sum A^T W A,  rhs = sum A^T W l,  n_obs = number of such queries.
+ * --------------------------------------------------------------------------------------------- */
+#define ORC_NDT_MIN_POINTS 5
+#define ORC_NDT_REG_REL 0.05
+
+static void ndt_jacobian_coeffs(double om, double fi, double ka, double C[3][3][3])
+{
+	double so = sin(om), co = cos(om), sf = sin(fi), cf = cos(fi), sk = sin(ka), ck = cos(ka);
+	double R11 = cf * ck, R12 = -cf * sk;
+	double R21 = co * sk + so * sf * ck, R22 = co * ck - so * sf * sk, R23 = -so * cf;
+	double R31 = so * sk - co * sf * ck, R32 = so * ck + co * sf * sk, R33 = co * cf;
+	double T[3][3][3] = {
+		{{0, 0, 0}, {-sf * ck, sf * sk, cf}, {R12, -R11, 0}},
+		{{-R31, -R32, -R33}, {so * cf * ck, -so * cf * sk, so * sf}, {R22, -R21, 0}},
+		{{R21, R22, R23}, {-co * cf * ck, co * cf * sk, -co * sf}, {R32, -R31, 0}}};
+	memcpy(C, T, sizeof(T));
+}
+
+static int sym3_inverse(const double *S, double *W)   /* S, W = {xx,xy,xz,yy,yz,zz} */
+{
+	double a = S[0], b = S[1], c = S[2], d = S[3], e = S[4], f = S[5];
+	double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+	double det = a * c00 + b * c01 + c * c02;
+	if (!(det > 0.0)) return 0;
+	double id = 1.0 / det;
+	W[0] = c00 * id; W[1] = c01 * id; W[2] = c02 * id;
+	W[3] = (a * f - c * c) * id; W[4] = (b * c - a * e) * id; W[5] = (a * d - b * b) * id;
+	return 1;
+}
+
+int64_t orc_ndt_normal_equations(const orc_point *fg, const orc_point *fl, int n_first,
+		const orc_point *second, int n_second, const orc_hash_element *table, const orc_bucket *buckets,
+		const orc_grid_params *p, const double *pose6, double *neq28)
+{
+	(void)n_first;
+	int64_t nb = p->number_of_buckets;
+	int nbY = p->number_of_buckets_Y, nbZ = p->number_of_buckets_Z;
+	double res = p->resolution_X;
+	double eps = (ORC_NDT_REG_REL * res) * (ORC_NDT_REG_REL * res);
+	double *st = (double *)calloc((size_t)nb * 12, sizeof(double));   /* mu_g[3], mu_l[3], W[6] */
+	unsigned char *valid = (unsigned char *)calloc((size_t)nb, 1);
+#pragma omp parallel for schedule(dynamic, 64)
+	for (int64_t b = 0; b < nb; b++) {
+		int n = buckets[b].number_of_points;
+		if (n < ORC_NDT_MIN_POINTS) continue;
+		int ix = (int)(b / ((int64_t)nbY * nbZ)), iy = (int)((b / nbZ) % nbY), iz = (int)(b % nbZ);
+		double cx = (double)p->bounding_box_min_X + ((double)ix + 0.5) * (double)p->resolution_X;
+		double cy = (double)p->bounding_box_min_Y + ((double)iy + 0.5) * (double)p->resolution_Y;
+		double cz = (double)p->bounding_box_min_Z + ((double)iz + 0.5) * (double)p->resolution_Z;
+		double s[3] = {0, 0, 0}, ss[6] = {0, 0, 0, 0, 0, 0}, sl[3] = {0, 0, 0};
+		for (int l = buckets[b].index_begin; l < buckets[b].index_end; l++) {
+			int i = table[l].index_of_point;
+			double x = (double)fg[i].x - cx, y = (double)fg[i].y - cy, z = (double)fg[i].z - cz;
+			s[0] += x; s[1] += y; s[2] += z;
+			ss[0] += x * x; ss[1] += x * y; ss[2] += x * z; ss[3] += y * y; ss[4] += y * z; ss[5] += z * z;
+			sl[0] += fl[i].x; sl[1] += fl[i].y; sl[2] += fl[i].z;
+		}
+		double inv = 1.0 / n, m[3] = {s[0] * inv, s[1] * inv, s[2] * inv};
+		double S[6];
+		double d = 1.0 / (n - 1);
+		S[0] = (ss[0] - n * m[0] * m[0]) * d + eps; S[1] = (ss[1] - n * m[0] * m[1]) * d; S[2] = (ss[2] - n * m[0] * m[2]) * d;
+		S[3] = (ss[3] - n * m[1] * m[1]) * d + eps; S[4] = (ss[4] - n * m[1] * m[2]) * d; S[5] = (ss[5] - n * m[2] * m[2]) * d + eps;
+		double *o = st + 12 * b;
+		if (!sym3_inverse(S, o + 6)) continue;
+		o[0] = m[0] + cx; o[1] = m[1] + cy; o[2] = m[2] + cz;
+		o[3] = sl[0] * inv; o[4] = sl[1] * inv; o[5] = sl[2] * inv;
+		valid[b] = 1;
+	}
+	double C[3][3][3];
+	ndt_jacobian_coeffs(pose6[3], pose6[4], pose6[5], C);
+	long double N[6][6], rhs[6];
+	for (int i = 0; i < 6; i++) { rhs[i] = 0; for (int j = 0; j < 6; j++) N[i][j] = 0; }
+	int64_t n_obs = 0;
+	for (int qi = 0; qi < n_second; qi++) {
+		const orc_point *q = &second[qi];
+		if (q->x < p->bounding_box_min_X || q->x > p->bounding_box_max_X) continue;
+		if (q->y < p->bounding_box_min_Y || q->y > p->bounding_box_max_Y) continue;
+		if (q->z < p->bounding_box_min_Z || q->z > p->bounding_box_max_Z) continue;
+		int32_t b = bucket_key(q->x, q->y, q->z, p, 0, 0, 0);
+		if (!(b >= 0 && (int64_t)b < nb) || !valid[b]) continue;
+		const double *o = st + 12 * (int64_t)b;
+		double l[3] = {o[0] - (double)q->x, o[1] - (double)q->y, o[2] - (double)q->z};
+		double W[3][3] = {{o[6], o[7], o[8]}, {o[7], o[9], o[10]}, {o[8], o[10], o[11]}};
+		double A[3][6];
+		for (int r = 0; r < 3; r++) {
+			for (int c = 0; c < 3; c++) {
+				A[r][c] = (r == c) ? -1.0 : 0.0;
+				A[r][3 + c] = -(C[r][c][0] * o[3] + C[r][c][1] * o[4] + C[r][c][2] * o[5]);
+			}
+		}
+		for (int i = 0; i < 6; i++) {
+			double wa[3];   /* (A^T W) row i */
+			for (int r = 0; r < 3; r++) wa[r] = A[0][i] * W[0][r] + A[1][i] * W[1][r] + A[2][i] * W[2][r];
+			rhs[i] += (long double)(wa[0] * l[0] + wa[1] * l[1] + wa[2] * l[2]);
+			for (int j = 0; j < 6; j++) N[i][j] += (long double)(wa[0] * A[0][j] + wa[1] * A[1][j] + wa[2] * A[2][j]);
+		}
+		n_obs++;
+	}
+	int k = 0;
+	for (int i = 0; i < 6; i++)
+		for (int j = i; j < 6; j++) neq28[k++] = (double)N[i][j];
+	for (int i = 0; i < 6; i++) neq28[k++] = (double)rhs[i];
+	neq28[k] = (double)n_obs;
+	free(st); free(valid);
+	return n_obs;
+}
+
+/* dof-subsystem of a packed 28-double system solved by Cholesky (dof 4 keeps tx,ty,tz,ka). 0 ok, -3 not SPD. */
+int orc_solve_packed(const double *neq, int dof, double *x)
+{
+	const int sel6[6] = {0, 1, 2, 3, 4, 5}, sel4[4] = {0, 1, 2, 5};
+	const int *sel = dof == 6 ? sel6 : sel4;
+	double full[6][6], A[36], b[6];
+	int k = 0;
+	for (int i = 0; i < 6; i++)
+		for (int j = i; j < 6; j++) { full[i][j] = neq[k]; full[j][i] = neq[k]; k++; }
+	for (int i = 0; i < dof; i++) {
+		b[i] = neq[21 + sel[i]];
+		for (int j = 0; j < dof; j++) A[i + j * dof] = full[sel[i]][sel[j]];
+	}
+	return orc_chol_solve(A, b, dof, x) == 0 ? 0 : -3;
+}
+
+/* ---------------------------------------------------------------------------------------------
  * One iteration of registerLastArrivedScan on pair (i=first, j=second) — SL:264-422.
  *   SL:276-277  Euler round trip of the stored float pose, SL:279-280 transform of cloud i,
  *   SL:313      semantic NN (grid on cloud i, queries = cloud j), SL:323-398 observations,
@@ -552,11 +685,33 @@ int orc_icp_iteration(const orc_point *first_local, int n_first, const orc_point
 	int32_t *nn = nn_out ? nn_out : (int32_t *)malloc((size_t)n_second * sizeof(int32_t));
 	orc_obs_nn *obs = (orc_obs_nn *)malloc((size_t)(n_second > 0 ? n_second : 1) * sizeof(*obs));
 	orc_build_grid(scratch_first, n_first, &gp, buckets, table);
+	int status = -4;
+	if (prm->mode == 1) {   /* NDT */
+		double pose6[6] = {xyz[0], xyz[1], xyz[2], omfika[0], omfika[1], omfika[2]};
+		double neq[28], x[6] = {0, 0, 0, 0, 0, 0};
+		int64_t n_ndt = orc_ndt_normal_equations(scratch_first, first_local, n_first, second_global, n_second, table, buckets, &gp, pose6, neq);
+		if (n_obs_out) *n_obs_out = n_ndt;
+		if (nn_out) for (int i = 0; i < n_second; i++) nn_out[i] = -1;
+		if (n_ndt > prm->obs_threshold) {
+			status = orc_solve_packed(neq, prm->dof, x);
+			if (status == 0) {
+				pose6[0] += x[0]; pose6[1] += x[1]; pose6[2] += x[2];
+				if (prm->dof == 6) { pose6[3] += x[3]; pose6[4] += x[4]; pose6[5] += x[5]; }
+				else pose6[5] += x[3];
+				if (x_out) memcpy(x_out, x, sizeof(double) * (size_t)prm->dof);
+				float of[3] = {(float)pose6[3], (float)pose6[4], (float)pose6[5]};
+				float tf[3] = {(float)pose6[0], (float)pose6[1], (float)pose6[2]};
+				orc_euler_to_matrix(of, tf, pose);
+			}
+		}
+		free(table); free(buckets); free(obs);
+		if (!nn_out) free(nn);
+		return status;
+	}
 	orc_nn_search(scratch_first, n_first, second_global, n_second, table, buckets, &gp,
 			prm->search_radius, prm->max_inner, prm->max_outer, nn);
 	int n_obs = orc_build_observations(scratch_first, first_local, second_global, n_second, nn, prm->weight, obs);
 	if (n_obs_out) *n_obs_out = n_obs;
-	int status = -4;
 	if (n_obs > prm->obs_threshold) {
 		double pose6[6] = {xyz[0], xyz[1], xyz[2], omfika[0], omfika[1], omfika[2]};
 		status = orc_register_ls(obs, n_obs, pose6, prm->dof, x_out);
@@ -607,8 +762,10 @@ int orc_register_all_sweep(const orc_point *scans, const int64_t *off, int n_sca
 		orc_hash_element *table = (orc_hash_element *)malloc((size_t)n1 * sizeof(*table));
 		orc_bucket *buckets = (orc_bucket *)malloc((size_t)gp.number_of_buckets * sizeof(*buckets));
 		orc_build_grid(pc1, n1, &gp, buckets, table);   /* upstream rebuilds this per j (SL:478); same result */
-		size_t obs_cap = 1024, n_obs = 0;
-		orc_obs_nn *obs = (orc_obs_nn *)malloc(obs_cap * sizeof(*obs));
+		double pose6[6] = {t1[0], t1[1], t1[2], of1[0], of1[1], of1[2]};
+		double acc[28];
+		for (int k = 0; k < 28; k++) acc[k] = 0.0;
+		orc_obs_nn *obs = (orc_obs_nn *)malloc((size_t)(maxn > 0 ? maxn : 1) * sizeof(*obs));
 		for (int j = 0; j < n_scans; j++) {
 			if (j == i) continue;
 			int n2 = (int)(off[j + 1] - off[j]);
@@ -618,21 +775,29 @@ int orc_register_all_sweep(const orc_point *scans, const int64_t *off, int n_sca
 			float dist = sqrtf((t1[0] - t2[0]) * (t1[0] - t2[0]) + (t1[1] - t2[1]) * (t1[1] - t2[1]) + (t1[2] - t2[2]) * (t1[2] - t2[2]));
 			if (!(dist < pair_thr)) continue;                                     /* SL:469 */
 			orc_transform_cloud(scans + off[j], pc2, n2, pose2);
-			orc_nn_search(pc1, n1, pc2, n2, table, buckets, &gp, prm->search_radius, prm->max_inner, prm->max_outer, nn);
-			if (n_obs + (size_t)n2 > obs_cap) {
-				while (n_obs + (size_t)n2 > obs_cap) obs_cap *= 2;
-				obs = (orc_obs_nn *)realloc(obs, obs_cap * sizeof(*obs));
+			double pair[28];
+			if (prm->mode == 1) {
+				orc_ndt_normal_equations(pc1, scans + off[i], n1, pc2, n2, table, buckets, &gp, pose6, pair);
+			} else {
+				orc_nn_search(pc1, n1, pc2, n2, table, buckets, &gp, prm->search_radius, prm->max_inner, prm->max_outer, nn);
+				int n_pair = orc_build_observations(pc1, scans + off[i], pc2, n2, nn, prm->weight, obs);   /* per-pair label counts, SL:490-562 */
+				double N6[36], b6[6];
+				orc_normal_equations(obs, n_pair, pose6, 6, N6, b6);
+				pack_neq(N6, b6, (double)n_pair, pair);
 			}
-			n_obs += (size_t)orc_build_observations(pc1, scans + off[i], pc2, n2, nn, prm->weight, obs + n_obs);
+			for (int k = 0; k < 28; k++) acc[k] += pair[k];
 		}
-		double pose6[6] = {t1[0], t1[1], t1[2], of1[0], of1[1], of1[2]};
-		if (neq_out) {
-			double N6[36], b6[6];
-			orc_normal_equations(obs, (int)n_obs, pose6, 6, N6, b6);
-			pack_neq(N6, b6, (double)n_obs, neq_out + 28 * (size_t)i);
-		}
+		if (neq_out) memcpy(neq_out + 28 * (size_t)i, acc, sizeof(acc));
 		int status = -4;
-		if ((int64_t)n_obs > prm->obs_threshold) status = orc_register_ls(obs, (int)n_obs, pose6, prm->dof, 0);
+		if ((int64_t)(acc[27] + 0.5) > prm->obs_threshold) {                      /* SL:572 */
+			double x[6] = {0, 0, 0, 0, 0, 0};
+			status = orc_solve_packed(acc, prm->dof, x);
+			if (status == 0) {
+				pose6[0] += x[0]; pose6[1] += x[1]; pose6[2] += x[2];
+				if (prm->dof == 6) { pose6[3] += x[3]; pose6[4] += x[4]; pose6[5] += x[5]; }
+				else pose6[5] += x[3];
+			}
+		}
 		if (status_out) status_out[i] = status;
 		float of[3] = {(float)pose6[3], (float)pose6[4], (float)pose6[5]};
 		float tf[3] = {(float)pose6[0], (float)pose6[1], (float)pose6[2]};

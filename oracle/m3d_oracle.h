@@ -86,6 +86,13 @@ void orc_matrix4_to_euler(const float *m4x4, float *omfika, float *xyz);
 void orc_euler_to_matrix(const float *omfika, const float *xyz, float *m4x4);
 void orc_transform_cloud(const orc_point *in, orc_point *out, int n, const float *m4x4);
 
+/* NDT (point-to-distribution) — NOT IN THE REFERENCE: definition of record for this repository,
+ * "parity unpinned".  neq28 = 21 upper-triangular AtPA + 6 AtPl + observation count.  Returns n_obs. */
+int64_t orc_ndt_normal_equations(const orc_point *first_global, const orc_point *first_local, int n_first,
+		const orc_point *second_global, int n_second, const orc_hash_element *table, const orc_bucket *buckets,
+		const orc_grid_params *p, const double *pose6, double *neq28);
+int  orc_solve_packed(const double *neq28, int dof, double *x_out);
+
 /* loops ------------------------------------------------------------------------------------------- */
 /* one registerLastArrivedScan iteration body on an (i=first, j=second) pair; second_global is
  * already transformed.  scratch_first (n_first points) receives the transformed first cloud.

@@ -1,0 +1,73 @@
+"""NDT (point-to-distribution) on the device vs the repository's own CPU definition (oracle: orc_ndt_*).
+The reference has no NDT, so parity here is 'unpinned': tolerance against the oracle + convergence to the known
+perturbation + agreement with the ICP result."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _second_global(oracle, second, pose2):
+    return oracle.transform_cloud(second, oracle.euler_to_matrix(*oracle.matrix4_to_euler(pose2)))
+
+
+@pytest.mark.parametrize("kind,kw,res", [("hdl32", {"n_azimuth": 512}, 1.0), ("sick", {"n_beams": 256, "n_profiles": 256}, 1.0),
+                                         ("hdl32", {"n_azimuth": 512}, 0.5)])
+def test_ndt_iterations_track_oracle(pkg, oracle, ctx, synth, kind, kw, res):
+    first, second, pose_init, pose2, pose_true = synth.scan_pair(kind, seed=61, **kw)
+    ctx.scan_clear()
+    ctx.scan_upload(0, first)
+    ctx.scan_upload(1, second)
+    prm = pkg.default_params(res, mode=pkg.MODE_NDT)
+    oprm = oracle.default_params(res, mode=1)
+    sg = _second_global(oracle, second, pose2)
+    pose_d, pose_o = pose_init.copy(), pose_init.copy()
+    for it in range(8):
+        pose_d, st = ctx.icp_pair(0, 1, pose_d, pose2, prm, 1)
+        status, pose_o, n_obs, x_o, _ = oracle.icp_iteration(first, sg, pose_o, oprm)
+        assert st.last_status == 0 and status == 0
+        assert st.n_obs_last == n_obs
+        assert np.allclose(np.array(st.x_last), x_o, rtol=1e-6, atol=1e-9), it
+    o_d, t_d = pkg.matrix4_to_euler(pose_d)
+    o_o, t_o = oracle.matrix4_to_euler(pose_o)
+    assert np.abs(t_d - t_o).max() < 1e-5 and np.abs(o_d - o_o).max() < 1e-6
+    # converges to the known perturbation-free pose
+    assert np.abs(pose_d[:3, 3] - pose_true[:3, 3]).max() < 5e-3
+    assert np.abs(o_d).max() < 2e-3
+
+
+def test_ndt_multi_iteration_and_icp_agreement(pkg, ctx, synth):
+    first, second, pose_init, pose2, pose_true = synth.scan_pair("sick", seed=62, n_beams=256, n_profiles=256)
+    ctx.scan_clear()
+    ctx.scan_upload(0, first)
+    ctx.scan_upload(1, second)
+    pose_ndt, st = ctx.icp_pair(0, 1, pose_init, pose2, pkg.default_params(1.0, mode=pkg.MODE_NDT), 10)
+    assert st.iterations_run == 10 and st.last_status == 0
+    pose_icp, st2 = ctx.icp_pair(0, 1, pose_init, pose2, pkg.default_params(1.0), 30)
+    assert st2.last_status == 0
+    assert np.abs(pose_ndt[:3, 3] - pose_icp[:3, 3]).max() < 0.02
+    assert np.abs(pose_ndt[:3, :3] - pose_icp[:3, :3]).max() < 5e-3
+    with pytest.raises(pkg.M3dRegError):
+        ctx.icp_pair(0, 1, pose_init, pose2, pkg.default_params(1.0, mode=pkg.MODE_NDT), 1)
+        ctx.export_last_nn(len(second))       # NDT has no correspondences to export
+
+
+def test_ndt_sweep_matches_oracle(pkg, oracle, ctx, synth):
+    import torch
+    scans, truth, init = synth.slam_scans(4, kind="hdl32", seed=19, spacing=1.0, n_azimuth=256)
+    ctx.scan_clear()
+    for k, s in enumerate(scans):
+        ctx.scan_upload(k, s)
+    prm = pkg.default_params(1.0, dof=6, mode=pkg.MODE_NDT)
+    poses_o, neq_o, status_o = oracle.register_all_sweep(scans, init, oracle.default_params(1.0, dof=6, mode=1), pair_thr=10.0)
+    pairs = [(i, j) for i in range(4) for j in range(4) if i != j]
+    d_neq = torch.zeros(4 * 28, dtype=torch.float64, device="cuda")
+    ctx.sweep_zero(d_neq, 4)
+    ctx.sweep_accumulate([p[0] for p in pairs], [p[1] for p in pairs], init, prm, d_neq)
+    poses_d, status_d = ctx.sweep_solve(d_neq, init, prm)
+    neq_d = d_neq.cpu().numpy().reshape(4, 28)
+    assert np.array_equal(neq_d[:, 27], neq_o[:, 27])
+    scale = np.abs(neq_o[:, :27]).max(axis=1, keepdims=True)
+    assert (np.abs(neq_d[:, :27] - neq_o[:, :27]) <= 1e-9 * scale).all()
+    assert np.array_equal(status_d, status_o)
+    assert np.abs(poses_d - poses_o).max() < 1e-6

@@ -267,3 +267,62 @@ def test_golden_vectors(oracle, path):
             assert np.allclose(b, g[f"AtPl{dof}"], rtol=1e-10, atol=1e-9)
             st, p_new, x = oracle.register_ls(obs, g["pose6"], dof)
             assert st == 0 and np.allclose(x, g[f"x{dof}"], rtol=1e-7, atol=1e-10)
+
+
+def test_ndt_definition_against_numpy(oracle, synth):
+    """orc_ndt_normal_equations against a direct numpy evaluation of its definition."""
+    first = synth.hdl32_scan(seed=71, n_azimuth=128)
+    second = synth.hdl32_scan(seed=72, n_azimuth=128)
+    pose = synth.pose_matrix(0.05, -0.02, 2.0, 0.004, -0.003, 0.01).astype(np.float32)
+    fg = oracle.transform_cloud(first, pose)
+    gp = oracle.grid_params(fg, 1.0)
+    buckets, table = oracle.build_grid(fg, gp)
+    pose6 = [0.05, -0.02, 2.0, 0.004, -0.003, 0.01]
+    n_obs, neq = oracle.ndt_normal_equations(fg, first, second, table, buckets, gp, pose6)
+    keys = oracle.bucket_keys(second, gp)
+    mn = np.array([gp["min_X"][0], gp["min_Y"][0], gp["min_Z"][0]], dtype=np.float64)
+    nbY, nbZ = int(gp["nb_Y"][0]), int(gp["nb_Z"][0])
+    eps = 1e-6
+    def Rm(a, b, c):
+        return synth.pose_matrix(0, 0, 0, a, b, c)[:3, :3]
+    om, fi, ka = pose6[3:]
+    dR = [(Rm(om + eps, fi, ka) - Rm(om - eps, fi, ka)) / (2 * eps), (Rm(om, fi + eps, ka) - Rm(om, fi - eps, ka)) / (2 * eps),
+          (Rm(om, fi, ka + eps) - Rm(om, fi, ka - eps)) / (2 * eps)]
+    N = np.zeros((6, 6)); rhs = np.zeros(6); cnt = 0
+    inside = ((second["x"] >= gp["min_X"][0]) & (second["x"] <= gp["max_X"][0]) & (second["y"] >= gp["min_Y"][0]) &
+              (second["y"] <= gp["max_Y"][0]) & (second["z"] >= gp["min_Z"][0]) & (second["z"] <= gp["max_Z"][0]))
+    cache = {}
+    for qi in np.nonzero(inside)[0]:
+        b = int(keys[qi])
+        if buckets["number_of_points"][b] < 5:
+            continue
+        if b not in cache:
+            idx = table["index_of_point"][buckets["index_begin"][b]:buckets["index_end"][b]]
+            pg = np.stack([fg["x"][idx], fg["y"][idx], fg["z"][idx]], 1).astype(np.float64)
+            pl = np.stack([first["x"][idx], first["y"][idx], first["z"][idx]], 1).astype(np.float64)
+            S = np.cov(pg.T) + (0.05 * 1.0) ** 2 * np.eye(3)
+            cache[b] = (pg.mean(0), pl.mean(0), np.linalg.inv(S))
+        mu_g, mu_l, W = cache[b]
+        q = np.array([second["x"][qi], second["y"][qi], second["z"][qi]], dtype=np.float64)
+        A = -np.hstack([np.eye(3), np.stack([d @ mu_l for d in dR], 1)])
+        N += A.T @ W @ A
+        rhs += A.T @ W @ (mu_g - q)
+        cnt += 1
+    assert cnt == n_obs and neq[27] == cnt
+    assert np.allclose(neq[:21], N[np.triu_indices(6)], rtol=1e-6, atol=1e-6 * np.abs(N).max())
+    assert np.allclose(neq[21:27], rhs, rtol=1e-6, atol=1e-6 * np.abs(rhs).max())
+    st, x = oracle.solve_packed(neq, 6)
+    assert st == 0 and np.allclose(x, np.linalg.solve(N, rhs), rtol=1e-4, atol=1e-8)
+
+
+def test_ndt_converges(oracle, synth):
+    f, s, p_init, p2, p_true = synth.scan_pair("hdl32", seed=11, n_azimuth=512)
+    prm = oracle.default_params(1.0, mode=1)
+    sg = oracle.transform_cloud(s, oracle.euler_to_matrix(*oracle.matrix4_to_euler(p2)))
+    pose = p_init.copy()
+    for _ in range(8):
+        st, pose, n_obs, _, _ = oracle.icp_iteration(f, sg, pose, prm)
+        assert st == 0 and n_obs > 1000
+    assert np.abs(pose[:3, 3] - p_true[:3, 3]).max() < 5e-3
+    o, _ = oracle.matrix4_to_euler(pose)
+    assert np.abs(o).max() < 2e-3
