@@ -1170,10 +1170,14 @@ __device__ __forceinline__ void warp_segmented_sum(uint32_t key, double (&v)[NV]
 	int lane = threadIdx.x & 31;
 	uint32_t prev = __shfl_up_sync(full, key, 1);
 	is_head = (lane == 0) || (prev != key);
+	/* a run is identified by the lane of its head, not by its key: the same key may re-occur later in the warp
+	 * (unsorted queries), and comparing keys would then add a later run into an earlier one */
+	unsigned heads = __ballot_sync(full, is_head);
+	int seg = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1) {
-		uint32_t k2 = __shfl_down_sync(full, key, o);
-		bool take = (lane + o < 32) && (k2 == key);
+		int s2 = __shfl_down_sync(full, seg, o);
+		bool take = (lane + o < 32) && (s2 == seg);
 #pragma unroll
 		for (int i = 0; i < NV; i++) {
 			double t = __shfl_down_sync(full, v[i], o);
