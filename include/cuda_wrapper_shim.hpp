@@ -1,0 +1,212 @@
+/* cuda_wrapper_shim.hpp — header-only C++ mirror of the reference's L1 call surface, `class CCudaWrapper`
+ * (ref: gpu_6dslam/gpu_6dslam/include/cudaWrapper.h:26-105, src/cudaWrapper.cpp), forwarding to the C ABI of
+ * include/m3dreg.h.  Same method names, argument order/meaning and error behaviour as the reference, so
+ * gpu6DSLAM.cpp's call sites (src/gpu6DSLAM.cpp:12-13, 313, 405-406, 478, 574-575) compile against it unchanged.
+ *
+ * The reference's signatures use pcl::PointCloud<lidar_pointcloud::PointXYZIRNLRGB> and Eigen::Affine3f.  Neither
+ * PCL nor Eigen is needed here: the methods are templates over
+ *     Cloud  — anything with `.points` (contiguous container of 40-byte points with `.data()` / `.size()`) and `.size()`
+ *              (pcl::PointCloud<PointXYZIRNLRGB> qualifies: custom_point_types.h:8-20 is byte-identical to m3dreg_point);
+ *     Affine — anything with `float operator()(int row, int col)` (read) and `float &operator()(int,int)` (write)
+ *              (Eigen::Affine3f qualifies); Vec3 — anything with x() y() z() accessors (Eigen::Vector3f qualifies).
+ * m3dreg::Affine3f / Vector3f below are minimal stand-ins used by this repository's own tests.
+ *
+ * Beyond the reference surface the shim exposes the device-resident fused loop (registerPair / scan store), which is
+ * what a patched gpu6DSLAM::registerLastArrivedScan calls instead of one NN + one registerLS call per iteration.
+ */
+#ifndef M3DREG_CUDA_WRAPPER_SHIM_HPP_
+#define M3DREG_CUDA_WRAPPER_SHIM_HPP_
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "m3dreg.h"
+
+namespace m3dreg {
+
+/* stand-ins for Eigen types (tests / ROS-free harnesses) */
+struct Vector3f {
+	float v[3] = {0, 0, 0};
+	Vector3f() {}
+	Vector3f(float a, float b, float c) { v[0] = a; v[1] = b; v[2] = c; }
+	float &x() { return v[0]; } float &y() { return v[1]; } float &z() { return v[2]; }
+	float x() const { return v[0]; } float y() const { return v[1]; } float z() const { return v[2]; }
+};
+struct Affine3f {
+	float m[16];   /* row-major 4x4 */
+	Affine3f() { setIdentity(); }
+	void setIdentity() { for (int i = 0; i < 16; i++) m[i] = (i % 5 == 0) ? 1.0f : 0.0f; }
+	float &operator()(int r, int c) { return m[r * 4 + c]; }
+	float operator()(int r, int c) const { return m[r * 4 + c]; }
+};
+
+/* Stands in for thrust::system_error thrown by throw_on_cuda_error (ref: src/cudaWrapper.cpp:650-660): carries the
+ * status (a cudaError_t value when > 0, an M3DREG_E_* code when < 0) and "file(line)". */
+class system_error : public std::runtime_error {
+public:
+	system_error(int code, const std::string &where)
+		: std::runtime_error(where + ": " + m3dreg_status_string(code)), code_(code) {}
+	int code() const { return code_; }
+private:
+	int code_;
+};
+
+} /* namespace m3dreg */
+
+/* ref: include/cudaWrapper.h:14-24 */
+template <class Affine = m3dreg::Affine3f>
+struct observations_tmpl {
+	std::vector<m3dreg_obs_nn> vobs_nn;
+	Affine m_pose;
+	double om = 0, fi = 0, ka = 0, tx = 0, ty = 0, tz = 0;
+};
+typedef observations_tmpl<> observations_t;
+
+class CCudaWrapper {
+public:
+	/* ref: src/cudaWrapper.cpp:4-18 — the context is created lazily by warmUpGPU, like the reference picks its device there */
+	CCudaWrapper() : threads(0), threadsNV(0), cuda_device(0), ctx_(nullptr) {}
+	~CCudaWrapper() { if (ctx_) m3dreg_destroy(ctx_); }
+	CCudaWrapper(const CCudaWrapper &) = delete;
+	CCudaWrapper &operator=(const CCudaWrapper &) = delete;
+
+	/* ref: src/cudaWrapper.cpp:36-44 */
+	void warmUpGPU(int cudaDevice)
+	{
+		if (!ctx_ || cuda_device != cudaDevice) {
+			if (ctx_) { m3dreg_destroy(ctx_); ctx_ = nullptr; }
+			throw_on_cuda_error(m3dreg_create(&ctx_, cudaDevice), __FILE__, __LINE__);
+			cuda_device = cudaDevice;
+		}
+		throw_on_cuda_error(m3dreg_warm_up(ctx_), __FILE__, __LINE__);
+		getNumberOfAvailableThreads(cudaDevice, threads, threadsNV);
+	}
+
+	/* ref: src/cudaWrapper.cpp:46-91 — kept for source compatibility; launch shapes are internal to the kernels now */
+	int getNumberOfAvailableThreads(int) { return 1024; }
+	bool getNumberOfAvailableThreads(int, int &t, int &tNV) { t = 1024; tNV = 256; return true; }
+	void coutMemoryStatus() {}
+
+	/* ref: src/cudaWrapper.cpp:344-424 */
+	template <class Cloud>
+	void semanticNearestNeighbourhoodSearch(Cloud &first_point_cloud, Cloud &second_point_cloud, float search_radius,
+			float bucket_size, float bounding_box_extension, int max_number_considered_in_INNER_bucket,
+			int max_number_considered_in_OUTER_bucket, std::vector<int> &nearest_neighbour_indexes)
+	{
+		static_assert(sizeof(first_point_cloud.points[0]) == sizeof(m3dreg_point), "point type must be the 40-byte PointXYZIRNLRGB");
+		if (nearest_neighbour_indexes.size() != second_point_cloud.size()) return;     /* ref: cudaWrapper.cpp:354 */
+		int st = m3dreg_semantic_nn_host(context(),
+				reinterpret_cast<const m3dreg_point *>(first_point_cloud.points.data()), (int)first_point_cloud.points.size(),
+				reinterpret_cast<const m3dreg_point *>(second_point_cloud.points.data()), (int)second_point_cloud.points.size(),
+				search_radius, bucket_size, bounding_box_extension, max_number_considered_in_INNER_bucket,
+				max_number_considered_in_OUTER_bucket, nearest_neighbour_indexes.data());
+		throw_on_cuda_error(st, __FILE__, __LINE__);
+	}
+
+	/* ref: src/cudaWrapper.cpp:427-468 (double[16] column-major variant) */
+	static void Matrix4ToEuler(const double *alignxf, double *rPosTheta, double *rPos)
+	{
+		float m[16], of[3], t[3];
+		for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) m[r * 4 + c] = (float)alignxf[c * 4 + r];
+		m3dreg_matrix4_to_euler(m, of, t);
+		for (int k = 0; k < 3; k++) { rPosTheta[k] = of[k]; if (rPos) rPos[k] = alignxf[12 + k]; }
+	}
+	/* ref: src/cudaWrapper.cpp:470-504 */
+	template <class Affine, class Vec3>
+	static void Matrix4ToEuler(const Affine &m, Vec3 &omfika, Vec3 &xyz)
+	{
+		float a[16], of[3], t[3];
+		for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) a[r * 4 + c] = (r < 3) ? m(r, c) : (c == 3 ? 1.0f : 0.0f);
+		m3dreg_matrix4_to_euler(a, of, t);
+		omfika.x() = of[0]; omfika.y() = of[1]; omfika.z() = of[2];
+		xyz.x() = t[0]; xyz.y() = t[1]; xyz.z() = t[2];
+	}
+	/* ref: src/cudaWrapper.cpp:506-514 */
+	template <class Affine, class Vec3>
+	static void EulerToMatrix(const Vec3 &omfika, const Vec3 &xyz, Affine &m)
+	{
+		float of[3] = {omfika.x(), omfika.y(), omfika.z()}, t[3] = {xyz.x(), xyz.y(), xyz.z()}, a[16];
+		m3dreg_euler_to_matrix(of, t, a);
+		for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) m(r, c) = a[r * 4 + c];
+	}
+
+	/* ref: src/cudaWrapper.cpp:516-581 (6-DOF) and 583-648 (4-DOF: x, y, z, yaw).  Returns false when the system
+	 * cannot be solved (the reference prints and carries on, CCUDAAXBSolverWrapper.cpp:520-522); obs is then unchanged. */
+	template <class Obs>
+	bool registerLS(Obs &obs) { return register_ls(obs, 6); }
+	template <class Obs>
+	bool registerLS_4DOF(Obs &obs) { return register_ls(obs, 4); }
+
+	/* ref: src/cudaWrapper.cpp:650-660 */
+	void throw_on_cuda_error(int code, const char *file, int line)
+	{
+		if (code != 0) {
+			std::stringstream ss;
+			ss << file << "(" << line << ")";
+			throw m3dreg::system_error(code, ss.str());
+		}
+	}
+
+	/* ---- beyond the reference surface: device-resident scans + fused loop --------------------------------------
+	 * uploadScan keeps scan `slot` in HBM; registerPair runs `iterations` complete iterations of
+	 * gpu6DSLAM::registerLastArrivedScan (src/gpu6DSLAM.cpp:264-422) on the device and updates pose_first. */
+	template <class Cloud>
+	void uploadScan(int slot, const Cloud &cloud)
+	{
+		throw_on_cuda_error(m3dreg_scan_upload(context(), slot, reinterpret_cast<const m3dreg_point *>(cloud.points.data()),
+				(int)cloud.points.size(), 0), __FILE__, __LINE__);
+	}
+	template <class Affine>
+	bool registerPair(int first_slot, int second_slot, Affine &pose_first, const Affine &pose_second,
+			const m3dreg_reg_params &params, int iterations, m3dreg_icp_stats *stats = nullptr)
+	{
+		float a[16], b[16];
+		for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) {
+			a[r * 4 + c] = (r < 3) ? pose_first(r, c) : (c == 3 ? 1.0f : 0.0f);
+			b[r * 4 + c] = (r < 3) ? pose_second(r, c) : (c == 3 ? 1.0f : 0.0f);
+		}
+		m3dreg_icp_stats local;
+		int st = m3dreg_icp_pair(context(), first_slot, second_slot, a, b, &params, iterations, stats ? stats : &local);
+		throw_on_cuda_error(st, __FILE__, __LINE__);
+		for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) pose_first(r, c) = a[r * 4 + c];
+		return (stats ? stats : &local)->last_status == 0;
+	}
+
+	m3dreg_ctx *context()
+	{
+		if (!ctx_) warmUpGPU(cuda_device);
+		return ctx_;
+	}
+
+	int threads;
+	int threadsNV;
+	int cuda_device;
+
+private:
+	template <class Obs>
+	bool register_ls(Obs &obs, int dof)
+	{
+		if (obs.vobs_nn.empty()) return false;
+		static_assert(sizeof(obs.vobs_nn[0]) == sizeof(m3dreg_obs_nn), "obs_nn_t must be the 28-byte reference layout");
+		double pose6[6] = {obs.tx, obs.ty, obs.tz, obs.om, obs.fi, obs.ka};
+		int st = m3dreg_register_ls_host(context(), reinterpret_cast<const m3dreg_obs_nn *>(obs.vobs_nn.data()),
+				(int)obs.vobs_nn.size(), pose6, dof, nullptr);
+		if (st == M3DREG_E_NOT_SPD) {
+			std::fprintf(stderr, "problem with solving Ax=B\n");
+			return false;
+		}
+		throw_on_cuda_error(st, __FILE__, __LINE__);
+		obs.tx = pose6[0]; obs.ty = pose6[1]; obs.tz = pose6[2];
+		obs.om = pose6[3]; obs.fi = pose6[4]; obs.ka = pose6[5];
+		return true;
+	}
+
+	m3dreg_ctx *ctx_;
+};
+
+#endif /* M3DREG_CUDA_WRAPPER_SHIM_HPP_ */

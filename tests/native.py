@@ -23,3 +23,20 @@ def build(force: bool = False) -> str:
 
 def lib() -> C.CDLL:
     return C.CDLL(SO)
+
+SHIM_EXE = os.path.join(_HERE, "_build", "shim_host")
+SHIM_SRC = os.path.join(_HERE, "csrc", "shim_host.cpp")
+
+
+def build_shim_host(force: bool = False) -> str:
+    """C++ host program over include/cuda_wrapper_shim.hpp, linked against the product library (plain g++, no CUDA headers)."""
+    root = os.path.dirname(_HERE)
+    inc = os.path.join(root, "include")
+    libdir = os.path.join(root, "mandala-mapping_b200")
+    deps = [SHIM_SRC, os.path.join(inc, "cuda_wrapper_shim.hpp"), os.path.join(inc, "m3dreg.h"), os.path.join(libdir, "libm3dreg.so")]
+    stale = (not os.path.exists(SHIM_EXE)) or any(os.path.getmtime(f) > os.path.getmtime(SHIM_EXE) for f in deps)
+    if force or stale:
+        os.makedirs(os.path.dirname(SHIM_EXE), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-ffp-contract=off", "-I", inc, "-o", SHIM_EXE, SHIM_SRC,
+                               "-L", libdir, "-lm3dreg", "-Wl,-rpath," + libdir])
+    return SHIM_EXE

@@ -81,3 +81,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "libm3d_oracle" not in txt and "libm3dref" not in txt, f
+
+
+def test_cpp_shim_compiles_and_links(pkg):
+    """include/cuda_wrapper_shim.hpp (the CCudaWrapper mirror) builds with plain g++ against the product library."""
+    from tests import native
+    pkg.build()
+    exe = native.build_shim_host(force=True)
+    assert os.path.exists(exe)
+    # without a GPU the host program must fail loudly through the shim's exception path, not fall back to anything
+    import subprocess
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "/dev/null", "/dev/null", "/dev/null", "0.5", "1", "6", "/dev/null"], capture_output=True, text=True)
+        assert r.returncode != 0
