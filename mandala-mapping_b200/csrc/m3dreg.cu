@@ -88,6 +88,7 @@ struct m3dreg_ctx {
 
 	/* arena */
 	DevBuf<float4> g_xyzl, g_nrm, ci_xyzl, ci_nrm, co_xyzl, co_nrm, q_xyzl, q_nrm, l_xyzl, l_nrm;
+	DevBuf<float4> ci_mlo, ci_mhi, co_mlo, co_mhi;   /* candidate block boxes + label masks */
 	DevBuf<uint32_t> keys[2], vals[2], hist, digit_tot;
 	DevBuf<m3dreg_bucket> buckets;
 	DevBuf<int> nn, nn_seq;
@@ -105,6 +106,7 @@ struct m3dreg_ctx {
 	int *flags = nullptr;
 	unsigned long long *label_counts = nullptr;
 	unsigned int *ticket = nullptr;
+	unsigned int *cell_count = nullptr;           /* number of searchable buckets in the compact list */
 	unsigned long long *eval_counter = nullptr;   /* candidates staged by the NN search (warp-level), diagnostic */
 	double *scratch = nullptr;   /* 64 doubles */
 	float *mats = nullptr;       /* 32 floats  */
@@ -188,8 +190,6 @@ int ensure_first(m3dreg_ctx *c, size_t n)
 	int e;
 	if ((e = c->g_xyzl.ensure(n))) return e;
 	if ((e = c->g_nrm.ensure(n))) return e;
-	if ((e = c->ci_xyzl.ensure(n))) return e;
-	if ((e = c->ci_nrm.ensure(n))) return e;
 	if ((e = c->digit_tot.ensure(kRadixSize))) return e;
 	for (int k = 0; k < 2; k++) {
 		if ((e = c->keys[k].ensure(n))) return e;
@@ -248,34 +248,48 @@ void host_roundtrip_pose(const float *m, float *pose1, double *pose6)
 	}
 }
 
-/* Compact candidate arrays: the OUTER set aliases the INNER one when both caps are equal. */
+/* Candidate sets: the OUTER set is only materialised when the caps differ. */
 int ensure_candidates(m3dreg_ctx *c, size_t n1, int max_inner, int max_outer)
 {
 	int e;
 	if ((e = c->ci_xyzl.ensure(n1))) return e;
 	if ((e = c->ci_nrm.ensure(n1))) return e;
+	if ((e = c->ci_mlo.ensure(n1))) return e;
+	if ((e = c->ci_mhi.ensure(n1))) return e;
 	if (max_inner != max_outer) {
 		if ((e = c->co_xyzl.ensure(n1))) return e;
 		if ((e = c->co_nrm.ensure(n1))) return e;
+		if ((e = c->co_mlo.ensure(n1))) return e;
+		if ((e = c->co_mhi.ensure(n1))) return e;
 	}
 	return 0;
 }
 
-void compact_candidates(m3dreg_ctx *c, const uint32_t *keys, const uint32_t *vals, int n1, const m3dreg_bucket *buckets,
-		int max_inner, int max_outer)
+CandSet cand_set(m3dreg_ctx *c, bool outer)
 {
-	bool same = max_inner == max_outer;
-	LAUNCH(c, k_compact_candidates, grid_for(c, n1, 256), 256, keys, vals, n1, c->gp, buckets, c->g_xyzl.p, c->g_nrm.p,
-			max_inner, max_outer, c->ci_xyzl.p, c->ci_nrm.p, same ? c->ci_xyzl.p : c->co_xyzl.p, same ? c->ci_nrm.p : c->co_nrm.p);
+	CandSet s;
+	if (outer) { s.xyzl = c->co_xyzl.p; s.nrm = c->co_nrm.p; s.mlo = c->co_mlo.p; s.mhi = c->co_mhi.p; }
+	else { s.xyzl = c->ci_xyzl.p; s.nrm = c->ci_nrm.p; s.mlo = c->ci_mlo.p; s.mhi = c->ci_mhi.p; }
+	return s;
+}
+
+/* gp must already be on the device (c->gp); src = the gridded cloud in original order; cell_list / c->cell_count
+ * hold the searchable buckets. */
+void build_candidates(m3dreg_ctx *c, const uint32_t *vals, const m3dreg_bucket *buckets, const uint32_t *cell_list,
+		const float4 *src_xyzl, const float4 *src_nrm, int max_inner, int max_outer)
+{
+	bool two = max_inner != max_outer;
+	LAUNCH(c, k_build_candidates, c->sm_count * 4, kBuildWarps * 32, vals, c->gp, buckets, cell_list, c->cell_count, src_xyzl, src_nrm,
+			max_inner, max_outer, cand_set(c, false), cand_set(c, two), two ? 1 : 0);
 }
 
 void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *vals, int n1, const m3dreg_bucket *buckets,
 		float radius, int max_inner, int max_outer, int prune, int *nn_out, int *nn_seq, unsigned long long *label_counts)
 {
-	bool same = max_inner == max_outer;
+	bool two = max_inner != max_outer;
 	LAUNCH(c, k_nn_search, (n2 + kNNThreads - 1) / kNNThreads, kNNThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
-			c->ci_xyzl.p, c->ci_nrm.p, same ? c->ci_xyzl.p : c->co_xyzl.p, same ? c->ci_nrm.p : c->co_nrm.p,
-			vals, n1, buckets, c->gp, radius, max_inner, max_outer, prune, nn_out, nn_seq, label_counts, c->eval_counter);
+			cand_set(c, false), cand_set(c, two), vals, n1, buckets, c->gp, radius, max_inner, max_outer, prune, nn_out, nn_seq,
+			label_counts, c->eval_counter);
 }
 
 /* Grid of the (already transformed) first cloud in g_*: params (device) from bounds, keys, sort, dense table,
@@ -283,14 +297,15 @@ void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *va
 void build_grid_fused(m3dreg_ctx *c, int n1, const m3dreg_reg_params *prm, int sort_bits)
 {
 	LAUNCH(c, k_grid_params, 1, 32, c->bounds, prm->bucket_size, prm->bucket_size, prm->bucket_size, prm->bbox_extension,
-			(long long)c->buckets.cap, c->gp, c->flags);
+			(long long)c->buckets.cap, c->gp, c->flags, c->cell_count);
 	LAUNCH(c, k_keys_soa, grid_for(c, n1, 256), 256, c->g_xyzl.p, n1, c->gp, c->keys[0].p, c->vals[0].p);
 	int cur = sort_by_bucket(c, n1, sort_bits, c->gp);
 	LAUNCH(c, k_init_buckets, grid_for(c, (long long)c->buckets.cap * 3, 256), 256, c->buckets.p, c->gp, 0LL);
+	/* the spare ping-pong key buffer holds the compact list of searchable buckets */
 	LAUNCH(c, k_finalize_grid, grid_for(c, n1, 256), 256, c->keys[cur].p, c->vals[cur].p, n1, c->gp, c->buckets.p,
-			(m3dreg_hash_element *)nullptr);
+			(m3dreg_hash_element *)nullptr, c->keys[cur ^ 1].p, c->cell_count);
 	if (prm->mode != M3DREG_MODE_NDT)
-		compact_candidates(c, c->keys[cur].p, c->vals[cur].p, n1, c->buckets.p, prm->max_inner, prm->max_outer);
+		build_candidates(c, c->vals[cur].p, c->buckets.p, c->keys[cur ^ 1].p, c->g_xyzl.p, c->g_nrm.p, prm->max_inner, prm->max_outer);
 	c->last_sorted = cur;
 }
 
@@ -467,7 +482,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	cudaEventCreate(&c->ev0);
 	cudaEventCreate(&c->ev1);
 	size_t small = sizeof(PoseState) + 8 * sizeof(uint32_t) + sizeof(m3dreg_grid_params) + FLAG_COUNT * sizeof(int) +
-			4 * sizeof(unsigned long long) + 32 + 64 * sizeof(double) + 32 * sizeof(float) + 256;
+			4 * sizeof(unsigned long long) + 64 + 64 * sizeof(double) + 32 * sizeof(float) + 256;
 	char *blk = nullptr;
 	e = cudaMalloc((void **)&blk, small);
 	if (e != cudaSuccess) { m3dreg_destroy(c); return (int)e; }
@@ -481,6 +496,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	c->bounds = (uint32_t *)take(8 * sizeof(uint32_t));
 	c->flags = (int *)take(FLAG_COUNT * sizeof(int));
 	c->ticket = (unsigned int *)take(16);
+	c->cell_count = (unsigned int *)take(16);
 	c->eval_counter = (unsigned long long *)take(16);
 	c->mats = (float *)take(32 * sizeof(float));
 	e = cudaMallocHost((void **)&c->h, sizeof(HostSmall));
@@ -499,6 +515,7 @@ void m3dreg_destroy(m3dreg_ctx *c)
 	if (c->own_stream) cudaStreamSynchronize(c->own_stream);
 	for (auto &s : c->scans) s.release();
 	c->g_xyzl.release(); c->g_nrm.release(); c->ci_xyzl.release(); c->ci_nrm.release(); c->co_xyzl.release(); c->co_nrm.release(); c->digit_tot.release();
+	c->ci_mlo.release(); c->ci_mhi.release(); c->co_mlo.release(); c->co_mhi.release();
 	c->q_xyzl.release(); c->q_nrm.release(); c->l_xyzl.release(); c->l_nrm.release();
 	for (int k = 0; k < 2; k++) { c->keys[k].release(); c->vals[k].release(); }
 	c->hist.release(); c->buckets.release(); c->nn.release(); c->nn_seq.release(); c->aos_a.release(); c->aos_b.release();
@@ -588,7 +605,8 @@ int m3dreg_calculate_grid(m3dreg_ctx *c, const m3dreg_point *d_cloud, int n, con
 	int cur = sort_by_bucket(c, n, bits_for(params->number_of_buckets), nullptr);
 	LAUNCH(c, k_init_buckets, grid_for(c, params->number_of_buckets * 3, 256), 256, d_buckets, (const m3dreg_grid_params *)nullptr,
 			(long long)params->number_of_buckets);
-	LAUNCH(c, k_finalize_grid, grid_for(c, n, 256), 256, c->keys[cur].p, c->vals[cur].p, n, (const m3dreg_grid_params *)nullptr, d_buckets, d_table);
+	LAUNCH(c, k_finalize_grid, grid_for(c, n, 256), 256, c->keys[cur].p, c->vals[cur].p, n, (const m3dreg_grid_params *)nullptr, d_buckets, d_table,
+			(uint32_t *)nullptr, (unsigned int *)nullptr);
 	c->last_valid = false;
 	CK(cudaStreamSynchronize(c->stream));   /* c->h->gp is reused by the next call */
 	return (int)cudaGetLastError();
@@ -609,7 +627,9 @@ int m3dreg_nn_search(m3dreg_ctx *c, const m3dreg_point *d_first, int n1, const m
 	LAUNCH(c, k_unpack_points, (n2 + 255) / 256, 256, d_second, n2, c->q_xyzl.p, c->q_nrm.p);
 	if ((e = ensure_candidates(c, (size_t)n1, max_inner, max_outer))) return e;
 	LAUNCH(c, k_split_table, grid_for(c, n1, 256), 256, d_table, n1, c->keys[0].p, c->vals[0].p);
-	compact_candidates(c, c->keys[0].p, c->vals[0].p, n1, d_buckets, max_inner, max_outer);
+	CK(cudaMemsetAsync(c->cell_count, 0, sizeof(unsigned int), c->stream));
+	LAUNCH(c, k_list_cells, grid_for(c, n1, 256), 256, c->keys[0].p, n1, d_buckets, c->keys[1].p, c->cell_count);
+	build_candidates(c, c->vals[0].p, d_buckets, c->keys[1].p, c->g_xyzl.p, c->g_nrm.p, max_inner, max_outer);
 	launch_nn(c, nullptr, n2, c->vals[0].p, n1, d_buckets, search_radius, max_inner, max_outer, c->prune, d_nn, nullptr, nullptr);
 	c->last_valid = false;
 	CK(cudaStreamSynchronize(c->stream));
@@ -747,9 +767,9 @@ void m3dreg_euler_to_matrix(const float *omfika, const float *xyz, float *m) { e
 
 /* ---- scan store ------------------------------------------------------------------------------------------ */
 
-/* Cell-sorted copy of a scan for its QUERY role: stable radix sort by the key of a fine local grid (0.25 m cells,
- * coarsened until the cell count fits 2^22).  Any spatially coherent order works — the NN result does not depend on
- * query order — this one reuses the grid machinery. */
+/* (label, Morton)-sorted copy of a scan for its QUERY role: stable radix sort by label | Morton code of a fine local
+ * grid (cell = extent/512, at least 6.25 cm).  Any order is correct — the NN result does not depend on query order —
+ * this one makes the 32 queries of a warp one small patch of one semantic surface. */
 static int presort_scan(m3dreg_ctx *c, Scan &s, const m3dreg_point *d_aos)
 {
 	int n = s.n, e;
@@ -758,20 +778,15 @@ static int presort_scan(m3dreg_ctx *c, Scan &s, const m3dreg_point *d_aos)
 	LAUNCH(c, k_bounds_aos, grid_for(c, n, 256), 256, d_aos, n, c->bounds);
 	CK(cudaMemcpyAsync(c->h->bounds, c->bounds, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
-	float mn[3], mx[3];
-	for (int k = 0; k < 3; k++) { mn[k] = o2f_host(c->h->bounds[k]); mx[k] = o2f_host(c->h->bounds[3 + k]); }
-	float res = 0.25f;
-	m3dreg_grid_params gp;
-	for (;;) {
-		int st = grid_params_from_bounds(mn, mx, res, res, res, 0.0f, &gp);
-		if (st == 0 && gp.number_of_buckets <= (1 << 22)) break;
-		res *= 2.0f;
-		if (res > 1.0e6f) return M3DREG_E_TOO_MANY_BUCKETS;
+	float mn[3], mx[3], ext = 0.0f;
+	for (int k = 0; k < 3; k++) {
+		mn[k] = o2f_host(c->h->bounds[k]); mx[k] = o2f_host(c->h->bounds[3 + k]);
+		if (mx[k] - mn[k] > ext) ext = mx[k] - mn[k];
 	}
-	c->h->gp = gp;
-	CK(cudaMemcpyAsync(c->gp, &c->h->gp, sizeof(m3dreg_grid_params), cudaMemcpyHostToDevice, c->stream));
-	LAUNCH(c, k_keys_aos, grid_for(c, n, 256), 256, d_aos, n, c->gp, c->keys[0].p, c->vals[0].p);
-	int cur = sort_by_bucket(c, n, bits_for(gp.number_of_buckets), nullptr);
+	float res = ext / 511.0f;
+	if (!(res > 0.0625f)) res = 0.0625f;
+	LAUNCH(c, k_keys_presort, grid_for(c, n, 256), 256, d_aos, n, mn[0], mn[1], mn[2], 1.0f / res, c->keys[0].p, c->vals[0].p);
+	int cur = sort_by_bucket(c, n, 29, nullptr);
 	CK(cudaMemcpyAsync(s.perm, c->vals[cur].p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
 	LAUNCH(c, k_gather_perm, grid_for(c, n, 256), 256, s.perm, n, s.xyzl, s.nrm, s.sx, s.sn);
 	CK(cudaStreamSynchronize(c->stream));

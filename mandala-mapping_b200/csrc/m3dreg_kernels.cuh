@@ -178,9 +178,10 @@ __global__ void k_transform_soa(const float4 *__restrict__ in_xyzl, const float4
  * Sets flags[FLAG_ERROR] when B overflows int32 or the planned capacity; B is then forced to 0 so that every
  * later kernel of the iteration is a no-op. */
 __global__ void k_grid_params(const uint32_t *__restrict__ bounds, float rx, float ry, float rz, float ext,
-		long long bucket_cap, m3dreg_grid_params *gp, int *flags)
+		long long bucket_cap, m3dreg_grid_params *gp, int *flags, unsigned int *cell_count)
 {
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	*cell_count = 0u;
 	float mnx = o2f(bounds[0]), mny = o2f(bounds[1]), mnz = o2f(bounds[2]);
 	float mxx = o2f(bounds[3]), mxy = o2f(bounds[4]), mxz = o2f(bounds[5]);
 	mxx = __fadd_rn(mxx, ext); mnx = __fsub_rn(mnx, ext);
@@ -236,6 +237,33 @@ __global__ void k_keys_aos(const m3dreg_point *__restrict__ in, int n, const m3d
 		uint2 a = __ldg(p), b = __ldg(p + 1);
 		int ix = cell_of(__uint_as_float(a.x), mnx, rx), iy = cell_of(__uint_as_float(a.y), mny, ry), iz = cell_of(__uint_as_float(b.x), mnz, rz);
 		keys[i] = (uint32_t)(ix * nby * nbz + iy * nbz + iz);
+		vals[i] = (uint32_t)i;
+	}
+}
+
+/* Query-role ordering of a stored scan: key = label (2 bits) | 27-bit Morton code of a fine local grid, so that 32
+ * consecutive queries are one small patch of one semantic surface.  Any order is correct (the NN result does not
+ * depend on query order); this one makes the warp-cooperative search cheap. */
+__device__ __forceinline__ uint32_t spread3(uint32_t v)   /* 9 bits -> every third bit */
+{
+	v &= 0x1FFu;
+	v = (v | (v << 16)) & 0x030000FFu;
+	v = (v | (v << 8)) & 0x0300F00Fu;
+	v = (v | (v << 4)) & 0x030C30C3u;
+	v = (v | (v << 2)) & 0x09249249u;
+	return v;
+}
+
+__global__ void k_keys_presort(const m3dreg_point *__restrict__ in, int n, float mnx, float mny, float mnz, float inv_res,
+		uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint2 *p = reinterpret_cast<const uint2 *>(in + i);
+		uint2 a = __ldg(p), b = __ldg(p + 1), e = __ldg(p + 4);
+		int ix = min(511, max(0, (int)((__uint_as_float(a.x) - mnx) * inv_res)));
+		int iy = min(511, max(0, (int)((__uint_as_float(a.y) - mny) * inv_res)));
+		int iz = min(511, max(0, (int)((__uint_as_float(b.x) - mnz) * inv_res)));
+		keys[i] = ((e.x & 3u) << 27) | spread3((uint32_t)ix) | (spread3((uint32_t)iy) << 1) | (spread3((uint32_t)iz) << 2);
 		vals[i] = (uint32_t)i;
 	}
 }
@@ -407,37 +435,97 @@ __device__ __forceinline__ int lower_bound_u32(const uint32_t *__restrict__ a, i
  * index_begin (it receives index_end=1 instead), so that bucket reads {-1, end, 0}.  Its index_end is a write
  * race upstream (1 vs run end); we store the run end.  Optionally materialises the reference's hashElement table. */
 __global__ void k_finalize_grid(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int n,
-		const m3dreg_grid_params *__restrict__ gp, m3dreg_bucket *__restrict__ buckets, m3dreg_hash_element *__restrict__ table_out)
+		const m3dreg_grid_params *__restrict__ gp, m3dreg_bucket *__restrict__ buckets, m3dreg_hash_element *__restrict__ table_out,
+		uint32_t *__restrict__ cell_list, unsigned int *__restrict__ cell_count)
 {
 	if (gp && gp->number_of_buckets <= 0) return;
-	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-		uint32_t k = __ldg(keys + p);
-		if (table_out) {
-			m3dreg_hash_element h;
-			h.index_of_point = (int)__ldg(vals + p);
-			h.index_of_bucket = (int)k;
-			table_out[p] = h;
-		}
-		bool run_end = (p == n - 1) || (__ldg(keys + p + 1) != k);
-		if (run_end) {
-			int begin = lower_bound_u32(keys, p + 1, k);
-			m3dreg_bucket b;
-			if (begin == 1 && n > 1) {           /* element 0 alone in its bucket -> quirk for this (second) run */
-				b.index_begin = -1; b.index_end = p + 1; b.number_of_points = 0;
-			} else {
-				b.index_begin = begin; b.index_end = p + 1; b.number_of_points = p + 1 - begin;
+	const unsigned full = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const int nround = (n + 31) & ~31;      /* whole warps stay together for the ballot below */
+	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
+		bool listed = false;
+		uint32_t k = 0;
+		if (p < n) {
+			k = __ldg(keys + p);
+			if (table_out) {
+				m3dreg_hash_element h;
+				h.index_of_point = (int)__ldg(vals + p);
+				h.index_of_bucket = (int)k;
+				table_out[p] = h;
 			}
-			buckets[k] = b;
+			bool run_end = (p == n - 1) || (__ldg(keys + p + 1) != k);
+			if (run_end) {
+				int begin = lower_bound_u32(keys, p + 1, k);
+				m3dreg_bucket b;
+				if (begin == 1 && n > 1) {           /* element 0 alone in its bucket -> quirk for this (second) run */
+					b.index_begin = -1; b.index_end = p + 1; b.number_of_points = 0;
+				} else {
+					b.index_begin = begin; b.index_end = p + 1; b.number_of_points = p + 1 - begin;
+					listed = true;
+				}
+				buckets[k] = b;
+			}
+		}
+		if (cell_list) {   /* compact list of the searchable buckets (order irrelevant): one atomic per warp */
+			unsigned m = __ballot_sync(full, listed);
+			if (m) {
+				unsigned int base = 0;
+				if (lane == 0) base = atomicAdd(cell_count, (unsigned int)__popc(m));
+				base = __shfl_sync(full, base, 0);
+				if (listed) cell_list[base + __popc(m & ((1u << lane) - 1u))] = k;
+			}
 		}
 	}
 }
 
-/* The reference never looks at every point of a bucket: it walks positions begin, begin+s, begin+2s, ... with
- * s = n / cap (lesson_16.cu:628-640), i.e. at most 2*cap-1 CANDIDATES per bucket.  Only those are ever read by the
- * NN search, so only those are gathered — densely, candidate k of a bucket at slot begin+k of the compact arrays
- * (a bucket's candidates always fit inside its own [begin,end) range, so no prefix sum is needed).  Contiguous
- * candidates are what lets a warp fetch 32 of them with one coalesced load and stage them in shared memory.
- * Two compact sets exist when the INNER and OUTER caps differ (different strides). */
+/* Same list from an externally supplied bucket table (stage-level m3dreg_nn_search). */
+__global__ void k_list_cells(const uint32_t *__restrict__ keys, int n, const m3dreg_bucket *__restrict__ buckets,
+		uint32_t *__restrict__ cell_list, unsigned int *__restrict__ cell_count)
+{
+	const unsigned full = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const int nround = (n + 31) & ~31;
+	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
+		bool listed = false;
+		uint32_t k = 0;
+		if (p < n) {
+			k = __ldg(keys + p);
+			bool run_end = (p == n - 1) || (__ldg(keys + p + 1) != k);
+			listed = run_end && __ldg(reinterpret_cast<const int *>(buckets + k) + 2) > 0;
+		}
+		unsigned m = __ballot_sync(full, listed);
+		if (m) {
+			unsigned int base = 0;
+			if (lane == 0) base = atomicAdd(cell_count, (unsigned int)__popc(m));
+			base = __shfl_sync(full, base, 0);
+			if (listed) cell_list[base + __popc(m & ((1u << lane) - 1u))] = k;
+		}
+	}
+}
+
+/* ---- candidate sets -------------------------------------------------------------------------------------------
+ * The reference never looks at every point of a bucket: it walks sorted positions begin, begin+s, begin+2s, ... with
+ * s = n / cap (lesson_16.cu:628-640), i.e. at most 2*cap-1 CANDIDATES per bucket, and only those can ever be a
+ * result.  k_build_candidates gathers exactly those, per bucket, into the bucket's own [begin, begin+ncand) range of
+ * the compact arrays (a bucket's candidates always fit inside its own range, so no prefix sum is needed) and —
+ * because the search result is the lexicographic minimum of (dist, sorted position), which is independent of the
+ * order in which candidates are looked at — stores them in a SPATIAL order: counting sort by
+ * (label & 3, Morton code of the 4x4x4 sub-cell inside the bucket).  Every 8 consecutive candidates form a block
+ * with an axis-aligned bounding box and a label mask; the search only touches blocks whose box can contain
+ * something closer than the current best.  Each record keeps its sorted position l for the tie-break and result.
+ * Two sets exist when the INNER and OUTER caps differ (different strides). */
+struct CandSet {
+	float4 *xyzl;     /* {x, y, z, label bits}                               */
+	float4 *nrm;      /* {nx, ny, nz, bits of l = position in the sorted table (hashElement index)} */
+	float4 *mlo;      /* per block: {min x, min y, min z, label mask bits}   */
+	float4 *mhi;      /* per block: {max x, max y, max z, 0}                 */
+};
+
+constexpr int kCandBlock = 8;
+constexpr int kBuildWarps = 4;
+constexpr int kBuildBins = 256;
+constexpr int kBuildPerLane = 4;   /* candidates per lane in flight (loads issued together) */
+
 __device__ __forceinline__ int candidate_stride(int npts, int cap)
 {
 	int iter = 1;
@@ -445,28 +533,146 @@ __device__ __forceinline__ int candidate_stride(int npts, int cap)
 	return iter;
 }
 
-__global__ void k_compact_candidates(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int n,
-		const m3dreg_grid_params *__restrict__ gp, const m3dreg_bucket *__restrict__ buckets,
-		const float4 *__restrict__ g_xyzl, const float4 *__restrict__ g_nrm, int max_inner, int max_outer,
-		float4 *__restrict__ ci_xyzl, float4 *__restrict__ ci_nrm, float4 *__restrict__ co_xyzl, float4 *__restrict__ co_nrm)
+__device__ __forceinline__ uint32_t label_bit(int label) { return 1u << (label & 31); }
+
+struct CellFrame { float ox, oy, oz, sx, sy, sz; };   /* bucket origin and 4/resolution (layout only, not parity relevant) */
+
+__device__ __forceinline__ uint32_t cand_bin(const float4 &p, const CellFrame &f)
 {
-	if (gp->number_of_buckets <= 0) return;
-	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-		uint32_t k = __ldg(keys + p);
-		const int *bp = reinterpret_cast<const int *>(buckets + k);
-		int npts = __ldg(bp + 2);
-		if (npts <= 0) continue;                          /* quirk bucket: invisible to the search */
-		int rank = p - __ldg(bp);
-		bool in_i = false, in_o = false;
-		int slot_i = 0, slot_o = 0;
-		if (max_inner > 0) { int it = candidate_stride(npts, max_inner); in_i = (rank % it) == 0; slot_i = p - rank + rank / it; }
-		if (co_xyzl != ci_xyzl && max_outer > 0) { int it = candidate_stride(npts, max_outer); in_o = (rank % it) == 0; slot_o = p - rank + rank / it; }
-		if (in_i || in_o) {
-			uint32_t v = __ldg(vals + p);
-			float4 a = __ldg(g_xyzl + v), b = __ldg(g_nrm + v);
-			if (in_i) { ci_xyzl[slot_i] = a; ci_nrm[slot_i] = b; }
-			if (in_o) { co_xyzl[slot_o] = a; co_nrm[slot_o] = b; }
+	int ux = min(3, max(0, (int)((p.x - f.ox) * f.sx)));
+	int uy = min(3, max(0, (int)((p.y - f.oy) * f.sy)));
+	int uz = min(3, max(0, (int)((p.z - f.oz) * f.sz)));
+	uint32_t mx = (ux & 1) | ((ux & 2) << 2), my = (uy & 1) | ((uy & 2) << 2), mz = (uz & 1) | ((uz & 2) << 2);
+	return ((uint32_t)(__float_as_int(p.w) & 3) << 6) | mx | (my << 1) | (mz << 2);
+}
+
+__device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict__ vals, const float4 *__restrict__ src_xyzl,
+		const float4 *__restrict__ src_nrm, int begin, int npts, int cap, const CellFrame &f, const CandSet &set,
+		uint32_t *hist, int lane)
+{
+	const unsigned full = 0xffffffffu;
+	if (cap <= 0 || npts <= 0) return;
+	const int iter = candidate_stride(npts, cap);
+	const int ncand = (npts + iter - 1) / iter;
+	const uint32_t lt = (1u << lane) - 1u;
+	/* pass 1: bin histogram */
+#pragma unroll
+	for (int k = 0; k < kBuildBins / 32; k++) hist[lane + 32 * k] = 0;
+	__syncwarp();
+	for (int c0 = 0; c0 < ncand; c0 += 32 * kBuildPerLane) {
+		float4 p[kBuildPerLane];
+#pragma unroll
+		for (int k = 0; k < kBuildPerLane; k++) {
+			int cc = c0 + k * 32 + lane;
+			if (cc < ncand) p[k] = __ldg(src_xyzl + __ldg(vals + begin + cc * iter));
 		}
+#pragma unroll
+		for (int k = 0; k < kBuildPerLane; k++) {
+			int cc = c0 + k * 32 + lane;
+			if (c0 + k * 32 >= ncand) break;
+			bool valid = cc < ncand;
+			uint32_t bin = valid ? cand_bin(p[k], f) : (0x100u + lane);
+			uint32_t peers = __match_any_sync(full, bin);
+			if (valid && lane == __ffs(peers) - 1) hist[bin] += __popc(peers);
+			__syncwarp();
+		}
+	}
+	/* exclusive scan of the 256 bins: 8 consecutive bins per lane */
+	{
+		uint32_t v[8], sum = 0;
+#pragma unroll
+		for (int k = 0; k < 8; k++) { v[k] = hist[lane * 8 + k]; sum += v[k]; }
+		uint32_t incl = sum;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			uint32_t t = __shfl_up_sync(full, incl, o);
+			if (lane >= o) incl += t;
+		}
+		uint32_t run = incl - sum;
+		__syncwarp();
+#pragma unroll
+		for (int k = 0; k < 8; k++) { hist[lane * 8 + k] = run; run += v[k]; }
+		__syncwarp();
+	}
+	/* pass 2: stable placement (ascending sorted position inside a bin) */
+	for (int c0 = 0; c0 < ncand; c0 += 32 * kBuildPerLane) {
+		float4 p[kBuildPerLane], nr[kBuildPerLane];
+		int ls[kBuildPerLane];
+#pragma unroll
+		for (int k = 0; k < kBuildPerLane; k++) {
+			int cc = c0 + k * 32 + lane;
+			if (cc < ncand) {
+				ls[k] = begin + cc * iter;
+				uint32_t v = __ldg(vals + ls[k]);
+				p[k] = __ldg(src_xyzl + v);
+				nr[k] = __ldg(src_nrm + v);
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < kBuildPerLane; k++) {
+			int cc = c0 + k * 32 + lane;
+			if (c0 + k * 32 >= ncand) break;
+			bool valid = cc < ncand;
+			uint32_t bin = valid ? cand_bin(p[k], f) : (0x100u + lane);
+			uint32_t peers = __match_any_sync(full, bin);
+			int leader = __ffs(peers) - 1;
+			uint32_t old = 0;
+			if (valid && lane == leader) { old = hist[bin]; hist[bin] = old + __popc(peers); }
+			old = __shfl_sync(full, old, leader);
+			if (valid) {
+				int pos = begin + (int)(old + __popc(peers & lt));
+				set.xyzl[pos] = p[k];
+				set.nrm[pos] = make_float4(nr[k].x, nr[k].y, nr[k].z, __int_as_float(ls[k]));
+			}
+			__syncwarp();
+		}
+	}
+	__syncwarp();
+	/* block boxes + label masks (re-read through L2: the records were written by other lanes of this warp) */
+	const int nblocks = (ncand + kCandBlock - 1) / kCandBlock;
+	for (int j = lane; j < nblocks; j += 32) {
+		float lox = INFINITY, loy = INFINITY, loz = INFINITY, hix = -INFINITY, hiy = -INFINITY, hiz = -INFINITY;
+		uint32_t mask = 0;
+#pragma unroll
+		for (int k = 0; k < kCandBlock; k++) {
+			int idx = j * kCandBlock + k;
+			if (idx < ncand) {
+				float4 c = __ldcg(set.xyzl + begin + idx);
+				lox = fminf(lox, c.x); loy = fminf(loy, c.y); loz = fminf(loz, c.z);
+				hix = fmaxf(hix, c.x); hiy = fmaxf(hiy, c.y); hiz = fmaxf(hiz, c.z);
+				mask |= label_bit(__float_as_int(c.w));
+			}
+		}
+		set.mlo[begin + j] = make_float4(lox, loy, loz, __uint_as_float(mask));
+		set.mhi[begin + j] = make_float4(hix, hiy, hiz, 0.0f);
+	}
+}
+
+/* One warp per searchable bucket of the compact list k_finalize_grid / k_list_cells left behind. */
+__global__ void __launch_bounds__(kBuildWarps * 32, 4) k_build_candidates(const uint32_t *__restrict__ vals,
+		const m3dreg_grid_params *__restrict__ gp, const m3dreg_bucket *__restrict__ buckets,
+		const uint32_t *__restrict__ cell_list, const unsigned int *__restrict__ cell_count,
+		const float4 *__restrict__ src_xyzl, const float4 *__restrict__ src_nrm, int max_inner, int max_outer,
+		CandSet ci, CandSet co, int two_sets)
+{
+	__shared__ uint32_t s_hist[kBuildWarps][kBuildBins];
+	if (gp->number_of_buckets <= 0) return;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
+	const float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
+	const float rx = gp->resolution_X, ry = gp->resolution_Y, rz = gp->resolution_Z;
+	const unsigned int ncells = *cell_count;
+	const unsigned int nwarps = gridDim.x * kBuildWarps;
+	for (unsigned int t = blockIdx.x * kBuildWarps + w; t < ncells; t += nwarps) {
+		int c = (int)__ldg(cell_list + t);
+		const int *bp = reinterpret_cast<const int *>(buckets + c);
+		int c_begin = __ldg(bp), c_n = __ldg(bp + 2);
+		int ix = c / (nby * nbz), iy = (c / nbz) % nby, iz = c % nbz;
+		CellFrame f;
+		f.ox = mnx + (float)ix * rx; f.oy = mny + (float)iy * ry; f.oz = mnz + (float)iz * rz;
+		f.sx = 4.0f / rx; f.sy = 4.0f / ry; f.sz = 4.0f / rz;
+		build_cell_candidates(vals, src_xyzl, src_nrm, c_begin, c_n, max_inner, f, ci, s_hist[w], lane);
+		if (two_sets) build_cell_candidates(vals, src_xyzl, src_nrm, c_begin, c_n, max_outer, f, co, s_hist[w], lane);
 	}
 }
 
@@ -503,81 +709,156 @@ struct NNQuery {
 
 /* Visit order in the reference is ascending sorted position l (cells are visited in ascending linear index and
  * the table is sorted by it) and its update is a strict `<`, so the reference result is the lexicographic minimum
- * of (dist, l) over the admissible candidates.  Keeping that pair lets cells be visited in ANY order, lets cells be
- * skipped when provably useless, and makes evaluating extra candidates harmless — which is what allows a whole
- * warp to walk one candidate list together.
+ * of (dist, l) over the admissible candidates.  Keeping that pair lets candidates be looked at in ANY order, lets
+ * whole groups be skipped when provably useless, and makes evaluating extra candidates harmless — which is what
+ * allows a whole warp to walk one candidate list together.
  *
- * Warp-cooperative bucket scan: every lane holds one query.  The warp fetches up to 32 compact candidates with one
- * coalesced LDG.128 per lane and stages them in its 512-byte slice of shared memory (slots beyond the candidate
- * count get a +inf sentinel).
- *   HOT  loop (straight-line, unrolled 8/16/32): broadcast LDS.128 + 3 FADD + FMUL + 2 FFMA, then a branch-free
- *        running minimum over the candidates whose label matches (strict <, ascending position: the earliest of
- *        equal distances is kept, as in the reference).  No votes, no branches.
- *   COLD step (once per block of candidates): if the block minimum can beat min(best, r^2), load that candidate's
- *        normal, apply the angle gate and the exact (dist, l) comparison.  Should the gate reject the block minimum
- *        (rare: opposite faces of thin structures) the lane re-scans the block sequentially with the full predicate.
- * `active` masks lanes for which this cell is irrelevant. */
+ * Warp-cooperative search: every lane holds one query; the warp stages up to 4 candidate blocks (32 records) in its
+ * 512-byte slice of shared memory with one coalesced LDG.128 per lane.
+ *   HOT  loop (straight-line): broadcast LDS.128 + 3 FADD + FMUL + 2 FFMA, then a branch-free running minimum over
+ *        the candidates whose label matches, plus a flag that records an exact tie at the minimum.
+ *   COLD step (once per staged group): if the group minimum can beat min(best, r^2), fetch that candidate's sorted
+ *        position and normal, apply the angle gate and the exact (dist, l) comparison.  Should the gate reject it, or
+ *        a tie have been seen (staging order is spatial, not ascending l), the lane re-scans the group sequentially
+ *        with the full predicate. */
 __device__ __forceinline__ float nn_dist(float qx, float qy, float qz, const float4 &c)
 {
 	float dx = __fsub_rn(qx, c.x), dy = __fsub_rn(qy, c.y), dz = __fsub_rn(qz, c.z);
 	return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
-template <int W>
-__device__ __forceinline__ void nn_block_min(const NNQuery &q, const float4 *stage, float &bmin, int &bidx)
+__device__ __forceinline__ void nn_group_min(const NNQuery &q, const float4 *stage, int base, float &bmin, int &bidx, bool &tie)
 {
 #pragma unroll
-	for (int kk = 0; kk < W; kk++) {
-		float4 c = stage[kk];
+	for (int kk = 0; kk < kCandBlock; kk++) {
+		float4 c = stage[base + kk];
 		float d = nn_dist(q.x, q.y, q.z, c);
-		bool better = (__float_as_int(c.w) == q.label) && (d < bmin);
+		bool ok = __float_as_int(c.w) == q.label;
+		bool better = ok && (d < bmin);
+		bool eq = ok && (d == bmin);
+		tie = better ? false : (tie || eq);
 		bmin = better ? d : bmin;
-		bidx = better ? kk : bidx;
+		bidx = better ? base + kk : bidx;
 	}
 }
 
-__device__ __forceinline__ void nn_visit_bucket_warp(NNQuery &q, bool active, const m3dreg_bucket *__restrict__ buckets, int cell, int cap,
-		const float4 *__restrict__ c_xyzl, const float4 *__restrict__ c_nrm, float4 *stage, int lane, unsigned int &evals)
+/* Stage the blocks b[0..nsel) (block indices inside the bucket) and evaluate them for every lane. */
+__device__ __forceinline__ void nn_eval_blocks(NNQuery &q, bool need, const CandSet &set, int begin, int ncand,
+		int b0, int b1, int b2, int b3, int nsel, float4 *stage, int lane, unsigned int &evals)
 {
-	const int *bp = reinterpret_cast<const int *>(buckets + cell);
-	int npts = __ldg(bp + 2);
-	if (npts <= 0 || cap <= 0) return;
-	int iter = candidate_stride(npts, cap);
-	int lb = __ldg(bp), le = __ldg(bp + 1);
-	int ncand = (le - lb + iter - 1) / iter;
-	for (int k0 = 0; k0 < ncand; k0 += 32) {
-		int cnt = min(32, ncand - k0);
-		__syncwarp();
-		stage[lane] = lane < cnt ? __ldg(c_xyzl + lb + k0 + lane) : make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(0x7fffffff));
-		__syncwarp();
-		evals += (unsigned int)cnt;
-		float bmin = INFINITY;
-		int bidx = -1;
-		if (cnt <= 8) nn_block_min<8>(q, stage, bmin, bidx);
-		else if (cnt <= 16) nn_block_min<16>(q, stage, bmin, bidx);
-		else nn_block_min<32>(q, stage, bmin, bidx);
-		/* cold step */
-		if (active && bidx >= 0 && bmin <= fminf(q.best, q.r2)) {
-			int l = lb + (k0 + bidx) * iter;
+	const int g = lane >> 3;
+	const int blk = g == 0 ? b0 : (g == 1 ? b1 : (g == 2 ? b2 : b3));
+	const int idx = blk * kCandBlock + (lane & 7);
+	const bool valid = g < nsel && idx < ncand;
+	__syncwarp();
+	stage[lane] = valid ? __ldg(set.xyzl + begin + idx) : make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(0x7fffffff));
+	__syncwarp();
+	evals += (unsigned int)(nsel * kCandBlock);
+	float bmin = INFINITY;
+	int bidx = -1;
+	bool tie = false;
+#pragma unroll 1
+	for (int g8 = 0; g8 < nsel; g8++) nn_group_min(q, stage, g8 * kCandBlock, bmin, bidx, tie);
+	/* cold step */
+	if (need && bidx >= 0 && bmin <= fminf(q.best, q.r2)) {
+		bool rescan = tie;
+		if (!rescan) {
+			int gg = bidx >> 3;
+			int cand = begin + (gg == 0 ? b0 : (gg == 1 ? b1 : (gg == 2 ? b2 : b3))) * kCandBlock + (bidx & 7);
+			float4 cn = __ldg(set.nrm + cand);
+			int l = __float_as_int(cn.w);
 			if (bmin < q.best || (bmin == q.best && l < q.best_l)) {
-				float4 cn = __ldg(c_nrm + lb + k0 + bidx);
 				float dot = __fmaf_rn(q.nz, cn.z, __fmaf_rn(q.nx, cn.x, __fmul_rn(q.ny, cn.y)));
-				if (angle_gate(dot)) {
-					q.best = bmin; q.best_l = l;
-				} else {
-					/* the block minimum is inadmissible: sequential re-scan of this block with the full predicate */
-					for (int kk = 0; kk < cnt; kk++) {
-						float4 c = stage[kk];
-						float d = nn_dist(q.x, q.y, q.z, c);
-						int l2 = lb + (k0 + kk) * iter;
-						if (__float_as_int(c.w) == q.label && d <= q.r2 && (d < q.best || (d == q.best && l2 < q.best_l))) {
-							float4 cn2 = __ldg(c_nrm + lb + k0 + kk);
-							float dot2 = __fmaf_rn(q.nz, cn2.z, __fmaf_rn(q.nx, cn2.x, __fmul_rn(q.ny, cn2.y)));
-							if (angle_gate(dot2)) { q.best = d; q.best_l = l2; }
-						}
+				if (angle_gate(dot)) { q.best = bmin; q.best_l = l; }
+				else rescan = true;     /* group minimum inadmissible (rare: opposite faces of thin structures) */
+			}
+		}
+		if (rescan) {
+			for (int kk = 0; kk < nsel * kCandBlock; kk++) {
+				float4 c = stage[kk];
+				float d = nn_dist(q.x, q.y, q.z, c);
+				if (__float_as_int(c.w) == q.label && d <= q.r2 && d <= q.best) {
+					int gg = kk >> 3;
+					int cand = begin + (gg == 0 ? b0 : (gg == 1 ? b1 : (gg == 2 ? b2 : b3))) * kCandBlock + (kk & 7);
+					float4 cn2 = __ldg(set.nrm + cand);
+					int l2 = __float_as_int(cn2.w);
+					if (d < q.best || l2 < q.best_l) {
+						float dot2 = __fmaf_rn(q.nz, cn2.z, __fmaf_rn(q.nx, cn2.x, __fmul_rn(q.ny, cn2.y)));
+						if (angle_gate(dot2)) { q.best = d; q.best_l = l2; }
 					}
 				}
 			}
+		}
+	}
+}
+
+/* Search one bucket's candidate set for the lanes flagged `need`.
+ * Buckets with <= 4 blocks are staged whole.  Larger ones are searched in rounds of growing radius rho: the warp
+ * forms the bounding box of the queries that are still UNSETTLED (min(best, r^2) > rho^2 of the previous round),
+ * inflates it by rho, and lane j tests block j's box (and label mask) against it; blocks that pass and were not yet
+ * staged are evaluated by all lanes.  Exactness: a candidate c with dist(q, c) <= lim_q has |q.x - c.x| <= sqrt(lim_q)
+ * up to two float roundings (dist >= fl(dx*dx) by monotonicity of fma/mul), so with R = sqrt_ru(rho^2) * (1 + 2^-20),
+ * box bounds rounded outwards and lim_q <= rho^2, c lies inside the inflated box and its block's box overlaps it.
+ * A lane whose limit does not exceed rho^2 therefore has nothing left to find in this bucket; the others go on to
+ * the next round (rho doubles) until rho^2 covers every remaining limit. */
+__device__ __forceinline__ void nn_visit_set(NNQuery &q, bool need, int begin, int npts, int cap, const CandSet &set,
+		float trial_unit2, int prune, float4 *stage, int lane, unsigned int &evals)
+{
+	const unsigned full = 0xffffffffu;
+	if (npts <= 0 || cap <= 0) return;
+	if (!__any_sync(full, need)) return;
+	const int iter = candidate_stride(npts, cap);
+	const int ncand = (npts + iter - 1) / iter;
+	const int nblocks = (ncand + kCandBlock - 1) / kCandBlock;
+	const bool flat = nblocks <= 4 || !prune;
+	const float trial2 = trial_unit2 / (float)ncand;
+	const uint32_t ox = f2o(q.x), oy = f2o(q.y), oz = f2o(q.z);
+	const uint32_t lbit = label_bit(q.label);
+#pragma unroll 1
+	for (int cb = 0; cb < nblocks; cb += 32) {
+		const int nblk = min(32, nblocks - cb);
+		float4 mlo = make_float4(0, 0, 0, 0), mhi = make_float4(0, 0, 0, 0);
+		if (!flat && lane < nblk) { mlo = __ldg(set.mlo + begin + cb + lane); mhi = __ldg(set.mhi + begin + cb + lane); }
+		unsigned staged = 0;
+		bool U = need;
+		float rho2 = -1.0f;
+#pragma unroll 1
+		for (;;) {
+			unsigned m;
+			float maxlim = 0.0f;
+			if (flat) {
+				m = nblk == 32 ? 0xffffffffu : ((1u << nblk) - 1u);
+			} else {
+				/* non-negative floats order like their bit patterns */
+				unsigned lv = U ? __float_as_uint(fminf(q.best, q.r2)) + 1u : 0u;
+				unsigned mv = __reduce_max_sync(full, lv);
+				if (mv == 0u) break;
+				maxlim = __uint_as_float(mv - 1u);
+				rho2 = rho2 < 0.0f ? fminf(maxlim, trial2) : fminf(maxlim, rho2 * 4.0f);
+				float R = __fmul_ru(__fsqrt_ru(rho2), 1.00000095367431640625f);
+				float bxl = __fsub_rd(o2f(__reduce_min_sync(full, U ? ox : 0xFFFFFFFFu)), R);
+				float byl = __fsub_rd(o2f(__reduce_min_sync(full, U ? oy : 0xFFFFFFFFu)), R);
+				float bzl = __fsub_rd(o2f(__reduce_min_sync(full, U ? oz : 0xFFFFFFFFu)), R);
+				float bxh = __fadd_ru(o2f(__reduce_max_sync(full, U ? ox : 0u)), R);
+				float byh = __fadd_ru(o2f(__reduce_max_sync(full, U ? oy : 0u)), R);
+				float bzh = __fadd_ru(o2f(__reduce_max_sync(full, U ? oz : 0u)), R);
+				unsigned labels = __reduce_or_sync(full, U ? lbit : 0u);
+				bool hit = lane < nblk && (__float_as_uint(mlo.w) & labels) &&
+						!(mlo.x > bxh || mhi.x < bxl || mlo.y > byh || mhi.y < byl || mlo.z > bzh || mhi.z < bzl);
+				m = __ballot_sync(full, hit) & ~staged;
+				staged |= m;
+			}
+#pragma unroll 1
+			while (m) {
+				int b0 = __ffs(m) - 1; m &= m - 1;
+				int nsel = 1, b1 = 0, b2 = 0, b3 = 0;
+				if (m) { b1 = __ffs(m) - 1; m &= m - 1; nsel = 2; }
+				if (m) { b2 = __ffs(m) - 1; m &= m - 1; nsel = 3; }
+				if (m) { b3 = __ffs(m) - 1; m &= m - 1; nsel = 4; }
+				nn_eval_blocks(q, need, set, begin, ncand, cb + b0, cb + b1, cb + b2, cb + b3, nsel, stage, lane, evals);
+			}
+			if (flat || rho2 >= maxlim) break;
+			U = U && (fminf(q.best, q.r2) > rho2);
 		}
 	}
 }
@@ -599,18 +880,61 @@ __device__ __forceinline__ void axis_gaps(float q, float mn, float res, int ic, 
 	g_hi = b > 0.0 ? __double2float_rd(b) : 0.0f;
 }
 
-/* Semantic NN, one query per lane, one candidate list per warp.
- * Queries are expected in a spatially coherent order (the scan store keeps a cell-sorted copy of every scan, and a
- * rigid transform preserves coherence), so the 32 queries of a warp usually share their home bucket.  Lanes are
- * grouped by home bucket with ballots; each group walks its <= 27 buckets once, home bucket first; a neighbour
- * bucket is walked only if some lane of the group cannot exclude it by the lower bound above.
+struct NNLane {          /* per-lane search state besides the query itself */
+	int home, ix, iy, iz;
+	float gxl, gxh, gyl, gyh, gzl, gzh;
+	unsigned done;       /* bit o = (dx+1)*9 + (dy+1)*3 + (dz+1): neighbour bucket already handled (or pruned) */
+};
+
+struct NNGrid {
+	long long nb;
+	int nbx, nby, nbz;
+	const m3dreg_bucket *buckets;
+	CandSet ci, co;
+	int max_inner, max_outer, two_sets, prune;
+	float trial_unit2;
+};
+
+/* Bucket (cx,cy,cz) for EVERY lane that has it in its 27-neighbourhood and has not handled it yet — whatever the
+ * lane's home bucket is, so a bucket is staged once per warp, not once per group of equal homes. */
+__device__ __forceinline__ void nn_visit_cell(NNQuery &q, NNLane &s, const NNGrid &G, int cx, int cy, int cz,
+		float4 *stage, int lane, unsigned int &evals)
+{
+	int dx = cx - s.ix, dy = cy - s.iy, dz = cz - s.iz;
+	bool in27 = s.home >= 0 && (unsigned)(dx + 1) <= 2u && (unsigned)(dy + 1) <= 2u && (unsigned)(dz + 1) <= 2u;
+	int o = (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1);
+	bool part = in27 && !((s.done >> (o & 31)) & 1u);
+	if (part) s.done |= 1u << o;
+	float gx = dx < 0 ? s.gxl : (dx > 0 ? s.gxh : 0.0f), gy = dy < 0 ? s.gyl : (dy > 0 ? s.gyh : 0.0f), gz = dz < 0 ? s.gzl : (dz > 0 ? s.gzh : 0.0f);
+	float lbd = __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
+	bool need = part && (!G.prune || !(lbd > q.best || lbd > q.r2));
+	if (!__any_sync(0xffffffffu, need)) return;
+	int cell = (cx * G.nby + cy) * G.nbz + cz;
+	const int *bp = reinterpret_cast<const int *>(G.buckets + cell);
+	int npts = __ldg(bp + 2);
+	if (npts <= 0) return;
+	int begin = __ldg(bp);
+	const bool inner = (o == 13);
+#pragma unroll 1
+	for (int pass = 0; pass < (G.two_sets ? 2 : 1); pass++) {
+		/* equal caps: one shared set for every role; different caps: INNER set for the home role, OUTER for the rest */
+		bool mine = G.two_sets ? (need && (pass == 0 ? inner : !inner)) : need;
+		nn_visit_set(q, mine, begin, npts, pass == 0 ? G.max_inner : G.max_outer, pass == 0 ? G.ci : G.co, G.trial_unit2, G.prune,
+				stage, lane, evals);
+	}
+}
+
+/* Semantic NN, one query per lane, candidate groups shared by the warp.
+ * Queries are expected in a spatially coherent order (the scan store keeps a (label, Morton)-sorted copy of every
+ * scan, and a rigid transform preserves coherence), so the 32 queries of a warp cover a small patch of one surface.
+ * Phase A visits every distinct home bucket of the warp; phase B the neighbour buckets some lane cannot exclude by
+ * the lower bound above with its best-so-far.
  * q_perm (may be null = identity) maps the query's position to its index in the caller's order: nn_out is written
  * in the caller's order (the reference's layout), nn_seq (may be null) in query-array order for the next stage. */
 constexpr int kNNThreads = 128;
 
-__global__ void __launch_bounds__(kNNThreads, 8) k_nn_search(const float4 *__restrict__ q_xyzl, const float4 *__restrict__ q_nrm,
-		const uint32_t *__restrict__ q_perm, int n_second,
-		const float4 *__restrict__ ci_xyzl, const float4 *__restrict__ ci_nrm, const float4 *__restrict__ co_xyzl, const float4 *__restrict__ co_nrm,
+__global__ void __launch_bounds__(kNNThreads, 6) k_nn_search(const float4 *__restrict__ q_xyzl, const float4 *__restrict__ q_nrm,
+		const uint32_t *__restrict__ q_perm, int n_second, CandSet ci, CandSet co,
 		const uint32_t *__restrict__ s_vals, int n_first,
 		const m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp,
 		float search_radius, int max_inner, int max_outer, int prune,
@@ -623,82 +947,84 @@ __global__ void __launch_bounds__(kNNThreads, 8) k_nn_search(const float4 *__res
 	float4 *stage = s_stage[threadIdx.x >> 5];
 	unsigned int evals = 0;
 	int qi = blockIdx.x * blockDim.x + threadIdx.x;
-	long long nb = gp->number_of_buckets;
-	int nbx = gp->number_of_buckets_X, nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
+	NNGrid G;
+	G.nb = gp->number_of_buckets;
+	G.nbx = gp->number_of_buckets_X; G.nby = gp->number_of_buckets_Y; G.nbz = gp->number_of_buckets_Z;
+	G.buckets = buckets; G.ci = ci; G.co = co;
+	G.max_inner = max_inner; G.max_outer = max_outer; G.two_sets = (max_inner != max_outer); G.prune = prune;
 	float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
 	float rx = gp->resolution_X, ry = gp->resolution_Y, rz = gp->resolution_Z;
+	G.trial_unit2 = 2.0f * fmaxf(rx, fmaxf(ry, rz)) * fmaxf(rx, fmaxf(ry, rz));
 	NNQuery q;
 	q.x = q.y = q.z = q.nx = q.ny = q.nz = 0.0f;
 	q.r2 = __fmul_rn(search_radius, search_radius);
 	q.label = -1;
 	q.best = 100000000.0f;
 	q.best_l = 0x7fffffff;
-	int home = -1, ix = 0, iy = 0, iz = 0;
-	if (qi < n_second && nb > 0) {
+	NNLane s;
+	s.home = -1; s.ix = s.iy = s.iz = 0; s.done = 0;
+	s.gxl = s.gxh = s.gyl = s.gyh = s.gzl = s.gzh = 0.0f;
+	if (qi < n_second && G.nb > 0) {
 		float4 p = __ldg(q_xyzl + qi), pn = __ldg(q_nrm + qi);
 		q.x = p.x; q.y = p.y; q.z = p.z; q.nx = pn.x; q.ny = pn.y; q.nz = pn.z;
 		q.label = __float_as_int(p.w);
 		bool inside = !(p.x < mnx || p.x > gp->bounding_box_max_X) && !(p.y < mny || p.y > gp->bounding_box_max_Y) &&
 				!(p.z < mnz || p.z > gp->bounding_box_max_Z);
 		if (inside) {
-			ix = cell_of(p.x, mnx, rx); iy = cell_of(p.y, mny, ry); iz = cell_of(p.z, mnz, rz);
-			int h = ix * nby * nbz + iy * nbz + iz;
-			if (h >= 0 && (long long)h < nb) home = h;
+			s.ix = cell_of(p.x, mnx, rx); s.iy = cell_of(p.y, mny, ry); s.iz = cell_of(p.z, mnz, rz);
+			int h = s.ix * G.nby * G.nbz + s.iy * G.nbz + s.iz;
+			if (h >= 0 && (long long)h < G.nb) s.home = h;
 		}
 	}
 	/* per-axis gaps to the slabs at offset -1 / +1 (0 for the own slab) */
-	float gxl = 0.0f, gxh = 0.0f, gyl = 0.0f, gyh = 0.0f, gzl = 0.0f, gzh = 0.0f;
-	if (prune && home >= 0) {
-		axis_gaps(q.x, mnx, rx, ix, gxl, gxh);
-		axis_gaps(q.y, mny, ry, iy, gyl, gyh);
-		axis_gaps(q.z, mnz, rz, iz, gzl, gzh);
+	if (prune && s.home >= 0) {
+		axis_gaps(q.x, mnx, rx, s.ix, s.gxl, s.gxh);
+		axis_gaps(q.y, mny, ry, s.iy, s.gyl, s.gyh);
+		axis_gaps(q.z, mnz, rz, s.iz, s.gzl, s.gzh);
 	}
-	unsigned remaining = __ballot_sync(full, home >= 0);
-	while (remaining) {
-		int leader = __ffs(remaining) - 1;
-		int h = __shfl_sync(full, home, leader);
-		int hx = __shfl_sync(full, ix, leader), hy = __shfl_sync(full, iy, leader), hz = __shfl_sync(full, iz, leader);
-		bool mine = (home == h);
-		remaining &= ~__ballot_sync(full, mine);
-		/* phase 0: the home bucket (offset 13); phase 1: whichever of the other 26 buckets can still matter.
-		 * One visit call site keeps the kernel small enough for the instruction cache. */
+	/* phase A: every distinct home bucket of the warp; phase B: the neighbour buckets that can still matter with the
+	 * limits phase A left behind.  One visit call site keeps the kernel small enough for the instruction cache. */
+	unsigned remaining = __ballot_sync(full, s.home >= 0);
+	unsigned todo = 0;
+	bool phase_b = false;
 #pragma unroll 1
-		for (int phase = 0; phase < 2; phase++) {
-			unsigned need_mask = 0;    /* bit o = (i+1)*9 + (j+1)*3 + (k+1) */
-			if (phase == 0) {
-				need_mask = mine ? (1u << 13) : 0u;
-			} else if (mine) {
+	for (;;) {
+		int cx, cy, cz;
+		if (remaining) {
+			int leader = __ffs(remaining) - 1;
+			int h = __shfl_sync(full, s.home, leader);
+			cx = __shfl_sync(full, s.ix, leader); cy = __shfl_sync(full, s.iy, leader); cz = __shfl_sync(full, s.iz, leader);
+			remaining &= ~__ballot_sync(full, s.home == h);
+		} else {
+			if (!phase_b) {
+				phase_b = true;
+				/* a neighbour can only matter if one of the six face gaps is within the limit: usually none is */
 				float lim = fminf(q.best, q.r2);
+				float gmin = fminf(fminf(fminf(s.gxl, s.gxh), fminf(s.gyl, s.gyh)), fminf(s.gzl, s.gzh));
+				bool near_face = s.home >= 0 && (!prune || !(__fmul_rn(gmin, gmin) > lim));
+				if (!__any_sync(full, near_face)) break;
+				if (near_face) {
 #pragma unroll
-				for (int o = 0; o < 27; o++) {
-					if (o == 13) continue;
-					const int i = o / 9 - 1, j = (o / 3) % 3 - 1, k = o % 3 - 1;
-					float gx = i < 0 ? gxl : (i > 0 ? gxh : 0.0f), gy = j < 0 ? gyl : (j > 0 ? gyh : 0.0f), gz = k < 0 ? gzl : (k > 0 ? gzh : 0.0f);
-					float lbd = __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
-					bool ok = !prune || !(lbd > lim);
-					ok = ok && (unsigned)(hx + i) < (unsigned)nbx && (unsigned)(hy + j) < (unsigned)nby && (unsigned)(hz + k) < (unsigned)nbz;
-					need_mask |= ok ? (1u << o) : 0u;
+					for (int o = 0; o < 27; o++) {
+						const int i = o / 9 - 1, j = (o / 3) % 3 - 1, k = o % 3 - 1;
+						float gx = i < 0 ? s.gxl : (i > 0 ? s.gxh : 0.0f), gy = j < 0 ? s.gyl : (j > 0 ? s.gyh : 0.0f), gz = k < 0 ? s.gzl : (k > 0 ? s.gzh : 0.0f);
+						float lbd = __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
+						bool ok = !prune || !(lbd > lim);
+						ok = ok && (unsigned)(s.ix + i) < (unsigned)G.nbx && (unsigned)(s.iy + j) < (unsigned)G.nby && (unsigned)(s.iz + k) < (unsigned)G.nbz;
+						todo |= ok ? (1u << o) : 0u;
+					}
+					todo &= ~s.done;
 				}
 			}
-			unsigned warp_mask = __reduce_or_sync(full, need_mask);
-			while (warp_mask) {
-				int o = __ffs(warp_mask) - 1;
-				warp_mask &= warp_mask - 1;
-				int i = o / 9 - 1, j = (o / 3) % 3 - 1, k = o % 3 - 1;
-				int cell = h + i * nby * nbz + j * nbz + k;
-				if (cell < 0 || (long long)cell >= nb) continue;
-				bool need = (need_mask >> o) & 1u;
-				if (prune && need && o != 13) {   /* re-check with the live best */
-					float gx = i < 0 ? gxl : (i > 0 ? gxh : 0.0f), gy = j < 0 ? gyl : (j > 0 ? gyh : 0.0f), gz = k < 0 ? gzl : (k > 0 ? gzh : 0.0f);
-					float lbd = __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
-					need = !(lbd > q.best || lbd > q.r2);
-				}
-				if (!__any_sync(full, need)) continue;
-				bool inner = (o == 13);
-				nn_visit_bucket_warp(q, need, buckets, cell, inner ? max_inner : max_outer, inner ? ci_xyzl : co_xyzl,
-						inner ? ci_nrm : co_nrm, stage, lane, evals);
-			}
+			unsigned pending = __ballot_sync(full, todo != 0u);
+			if (!pending) break;
+			int leader = __ffs(pending) - 1;
+			int o = __ffs(__shfl_sync(full, todo, leader)) - 1;
+			cx = __shfl_sync(full, s.ix, leader) + (o / 9 - 1); cy = __shfl_sync(full, s.iy, leader) + ((o / 3) % 3 - 1);
+			cz = __shfl_sync(full, s.iz, leader) + (o % 3 - 1);
 		}
+		nn_visit_cell(q, s, G, cx, cy, cz, stage, lane, evals);
+		todo &= ~s.done;
 	}
 	if (eval_counter && lane == 0 && evals) atomicAdd(eval_counter, (unsigned long long)evals);
 	int result = -1;

@@ -21,6 +21,30 @@ def _cases(synth):
     z = synth.random_cloud(4000, seed=13, extent=(2, 2, 1), unit_normals=False)
     z["normal_x"][::3] = 0; z["normal_y"][::3] = 0; z["normal_z"][::3] = 0      # zero normals: never match
     yield "zero_normals", z, synth.random_cloud(2000, seed=14, extent=(2, 2, 1)), 0.5, 1.0, 100, 100
+    # exact distance ties: gridded points on a lattice (shuffled storage order), queries at lattice cell centres, so every
+    # query has up to 8 equidistant same-label candidates and the smallest sorted position must win
+    rng = np.random.default_rng(15)
+    g = np.stack(np.meshgrid(np.arange(24), np.arange(20), np.arange(6), indexing="ij"), -1).reshape(-1, 3).astype(np.float32) * 0.25
+    lat = synth.random_cloud(len(g), seed=16, n_labels=2)
+    g = g[rng.permutation(len(g))]
+    lat["x"], lat["y"], lat["z"] = g[:, 0], g[:, 1], g[:, 2]
+    lat["normal_x"], lat["normal_y"], lat["normal_z"] = 0.0, 0.0, 1.0
+    qs = synth.random_cloud(6000, seed=17, n_labels=2)
+    c = (rng.integers(0, [23, 19, 5], size=(len(qs), 3)).astype(np.float32) + 0.5) * 0.25
+    qs["x"], qs["y"], qs["z"] = c[:, 0], c[:, 1], c[:, 2]
+    qs["normal_x"], qs["normal_y"], qs["normal_z"] = 0.0, 0.0, 1.0
+    yield "lattice_ties", lat, qs, 1.0, 1.0, 100, 100
+    yield "lattice_ties_stride", lat, qs, 2.0, 0.5, 5, 9
+    # many candidate blocks per bucket, more than 256 candidates per bucket (several 32-block chunks), mixed labels
+    yield "dense_blocks", synth.random_cloud(200000, seed=18, extent=(3, 3, 2)), synth.random_cloud(30000, seed=19, extent=(3.2, 3.2, 2.2)), 0.7, 1.0, 100, 100
+    yield "huge_caps", synth.random_cloud(150000, seed=20, extent=(3, 2, 2)), synth.random_cloud(20000, seed=23, extent=(3, 2, 2)), 0.5, 1.0, 1000, 400
+    # a planar scene (points on few surfaces, like a scan) with sparse labels: rounds have to grow to find the rare label
+    pl = synth.random_cloud(120000, seed=24, extent=(6, 6, 0.02), n_labels=1)
+    pl["label"][::997] = 1
+    pq = synth.random_cloud(20000, seed=25, extent=(6, 6, 0.02), n_labels=2)
+    pl["normal_x"], pl["normal_y"], pl["normal_z"] = 0.0, 0.0, 1.0
+    pq["normal_x"], pq["normal_y"], pq["normal_z"] = 0.0, 0.0, 1.0
+    yield "planar_rare_label", pl, pq, 1.0, 1.0, 100, 100
 
 
 def _same_points(a, b):
