@@ -196,7 +196,7 @@ int ensure_first(m3dreg_ctx *c, size_t n)
 		if ((e = c->vals[k].ensure(n))) return e;
 	}
 	size_t tiles = (n + 1023) / 1024 + 1;
-	if ((e = c->hist.ensure(tiles * kRadixSize))) return e;
+	if ((e = c->hist.ensure(4 * tiles * kRadixSize))) return e;      /* one digit-by-tile matrix per radix pass */
 	return 0;
 }
 
@@ -215,23 +215,41 @@ int ensure_partials(m3dreg_ctx *c)
 	return c->partials.ensure((size_t)c->sm_count * 8 * kPartialCols);
 }
 
-/* stable LSD radix sort of (keys[0], vals[0]) by the low `bits` bits; returns the index (0/1) of the buffers
- * holding the result.  gp (device, may be null) lets every pass no-op when the grid was rejected on the device. */
-int sort_by_bucket(m3dreg_ctx *c, int n, int bits, const m3dreg_grid_params *gp)
+struct SortPlan { int items, tiles, passes; };
+
+SortPlan plan_sort(int n, int bits)
 {
-	int passes = (bits + kRadixBits - 1) / kRadixBits;
-	if (passes < 1) passes = 1;
+	SortPlan sp;
+	sp.passes = (bits + kRadixBits - 1) / kRadixBits;
+	if (sp.passes < 1) sp.passes = 1;
+	sp.items = n >= (1 << 19) ? 16 : 4;
+	sp.tiles = (n + kSortThreads * sp.items - 1) / (kSortThreads * sp.items);
+	return sp;
+}
+
+/* stable LSD radix sort of keys[0] (+ vals[0], or the implicit indices 0..n-1 when vals_implicit) by the low `bits`
+ * bits; returns the index (0/1) of the buffers holding the result.  gp (device, may be null) lets every pass no-op
+ * when the grid was rejected on the device.  hist0_ready: the first pass's histogram matrix was already produced
+ * (and the later ones zeroed) by k_grid_head.  Pass p+1's histogram is accumulated by pass p's scatter. */
+int sort_by_bucket(m3dreg_ctx *c, int n, int bits, const m3dreg_grid_params *gp, bool hist0_ready = false, bool vals_implicit = false)
+{
+	SortPlan sp = plan_sort(n, bits);
+	const size_t mat = (size_t)kRadixSize * sp.tiles;
+	const bool big = sp.items == 16;
 	int cur = 0;
-	bool big = n >= (1 << 19);
-	int items = big ? 16 : 4;
-	int tiles = (n + kSortThreads * items - 1) / (kSortThreads * items);
-	for (int p = 0; p < passes; p++) {
+	if (!hist0_ready) {
+		if (sp.passes > 1) cudaMemsetAsync(c->hist.p + mat, 0, (size_t)(sp.passes - 1) * mat * sizeof(uint32_t), c->stream);
+		if (big) LAUNCH(c, k_radix_hist<16>, sp.tiles, kSortThreads, c->keys[0].p, n, 0, sp.tiles, c->hist.p, gp);
+		else LAUNCH(c, k_radix_hist<4>, sp.tiles, kSortThreads, c->keys[0].p, n, 0, sp.tiles, c->hist.p, gp);
+	}
+	for (int p = 0; p < sp.passes; p++) {
 		int shift = p * kRadixBits;
-		if (big) LAUNCH(c, k_radix_hist<16>, tiles, kSortThreads, c->keys[cur].p, n, shift, tiles, c->hist.p, gp);
-		else LAUNCH(c, k_radix_hist<4>, tiles, kSortThreads, c->keys[cur].p, n, shift, tiles, c->hist.p, gp);
-		LAUNCH(c, k_radix_scan, kRadixSize, 256, c->hist.p, tiles, c->digit_tot.p, gp);
-		if (big) LAUNCH(c, k_radix_scatter<16>, tiles, kSortThreads, c->keys[cur].p, c->vals[cur].p, c->keys[cur ^ 1].p, c->vals[cur ^ 1].p, n, shift, tiles, c->hist.p, c->digit_tot.p, gp);
-		else LAUNCH(c, k_radix_scatter<4>, tiles, kSortThreads, c->keys[cur].p, c->vals[cur].p, c->keys[cur ^ 1].p, c->vals[cur ^ 1].p, n, shift, tiles, c->hist.p, c->digit_tot.p, gp);
+		uint32_t *h = c->hist.p + (size_t)p * mat;
+		uint32_t *hn = p + 1 < sp.passes ? h + mat : nullptr;
+		const uint32_t *vin = (p == 0 && vals_implicit) ? nullptr : c->vals[cur].p;
+		LAUNCH(c, k_radix_scan, kRadixSize, 256, h, sp.tiles, c->digit_tot.p, gp);
+		if (big) LAUNCH(c, k_radix_scatter<16>, sp.tiles, kSortThreads, c->keys[cur].p, vin, c->keys[cur ^ 1].p, c->vals[cur ^ 1].p, n, shift, sp.tiles, h, c->digit_tot.p, gp, hn);
+		else LAUNCH(c, k_radix_scatter<4>, sp.tiles, kSortThreads, c->keys[cur].p, vin, c->keys[cur ^ 1].p, c->vals[cur ^ 1].p, n, shift, sp.tiles, h, c->digit_tot.p, gp, hn);
 		cur ^= 1;
 	}
 	return cur;
@@ -296,11 +314,14 @@ void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *va
  * sorted SoA copy.  bounds must already hold the reduced box. */
 void build_grid_fused(m3dreg_ctx *c, int n1, const m3dreg_reg_params *prm, int sort_bits)
 {
-	LAUNCH(c, k_grid_params, 1, 32, c->bounds, prm->bucket_size, prm->bucket_size, prm->bucket_size, prm->bbox_extension,
-			(long long)c->buckets.cap, c->gp, c->flags, c->cell_count);
-	LAUNCH(c, k_keys_soa, grid_for(c, n1, 256), 256, c->g_xyzl.p, n1, c->gp, c->keys[0].p, c->vals[0].p);
-	int cur = sort_by_bucket(c, n1, sort_bits, c->gp);
-	LAUNCH(c, k_init_buckets, grid_for(c, (long long)c->buckets.cap * 3, 256), 256, c->buckets.p, c->gp, 0LL);
+	SortPlan sp = plan_sort(n1, sort_bits);
+	if (sp.items == 16)
+		LAUNCH(c, k_grid_head<16>, sp.tiles, kSortThreads, c->g_xyzl.p, n1, c->bounds, prm->bucket_size, prm->bucket_size, prm->bucket_size,
+				prm->bbox_extension, (long long)c->buckets.cap, c->gp, c->flags, c->cell_count, c->buckets.p, c->keys[0].p, sp.tiles, sp.passes, c->hist.p);
+	else
+		LAUNCH(c, k_grid_head<4>, sp.tiles, kSortThreads, c->g_xyzl.p, n1, c->bounds, prm->bucket_size, prm->bucket_size, prm->bucket_size,
+				prm->bbox_extension, (long long)c->buckets.cap, c->gp, c->flags, c->cell_count, c->buckets.p, c->keys[0].p, sp.tiles, sp.passes, c->hist.p);
+	int cur = sort_by_bucket(c, n1, sort_bits, c->gp, true, true);
 	/* the spare ping-pong key buffer holds the compact list of searchable buckets */
 	LAUNCH(c, k_finalize_grid, grid_for(c, n1, 256), 256, c->keys[cur].p, c->vals[cur].p, n1, c->gp, c->buckets.p,
 			(m3dreg_hash_element *)nullptr, c->keys[cur ^ 1].p, c->cell_count);
@@ -411,7 +432,7 @@ void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int
 	fin.obs_threshold = prm->obs_threshold; fin.pose6_in = nullptr; fin.bounds_reset = c->bounds;
 	fin.label_counts_reset = c->label_counts;
 	if (prof) cudaEventRecord(c->pev[3], c->stream);
-	LAUNCH(c, k_normal_equations<ObsFromNN>, grid_for(c, n2, kNeqThreads, 4), kNeqThreads, src, n2, c->partials.p, c->ticket, fin);
+	LAUNCH(c, k_normal_equations<ObsFromNN>, grid_for(c, n2, kNeqThreads, 2), kNeqThreads, src, n2, c->partials.p, c->ticket, fin);
 	c->last_nn_valid = true;
 	if (prof) {
 		cudaEventRecord(c->pev[4], c->stream);
@@ -1123,7 +1144,7 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 		fin.ps = nullptr; fin.neq_out = d_neq + (size_t)i * kNeqCount; fin.accumulate = 1; fin.solve = 0; fin.dof = prm->dof;
 		fin.obs_threshold = prm->obs_threshold; fin.pose6_in = c->d_pose6.p + 6 * (size_t)i; fin.bounds_reset = nullptr;
 		fin.label_counts_reset = c->label_counts;
-		LAUNCH(c, k_normal_equations<ObsFromNN>, grid_for(c, B.n, kNeqThreads, 4), kNeqThreads, src, B.n, c->partials.p, c->ticket, fin);
+		LAUNCH(c, k_normal_equations<ObsFromNN>, grid_for(c, B.n, kNeqThreads, 2), kNeqThreads, src, B.n, c->partials.p, c->ticket, fin);
 		c->last_n_first = A.n; c->last_n_second = B.n; c->last_valid = true;
 	}
 	int f = check_flags(c);

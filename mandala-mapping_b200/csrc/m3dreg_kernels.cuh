@@ -174,14 +174,11 @@ __global__ void k_transform_soa(const float4 *__restrict__ in_xyzl, const float4
 }
 
 /* Grid parameters from the reduced bounds, on the device (host part of cudaCalculateGridParams, lesson_16.cu:64-91):
- * max += ext; min -= ext; nb = int((max-min)/res + 1); B = nbX*nbY*nbZ.  One thread.
- * Sets flags[FLAG_ERROR] when B overflows int32 or the planned capacity; B is then forced to 0 so that every
- * later kernel of the iteration is a no-op. */
-__global__ void k_grid_params(const uint32_t *__restrict__ bounds, float rx, float ry, float rz, float ext,
-		long long bucket_cap, m3dreg_grid_params *gp, int *flags, unsigned int *cell_count)
+ * max += ext; min -= ext; nb = int((max-min)/res + 1); B = nbX*nbY*nbZ.
+ * Returns false (and number_of_buckets = 0) when B overflows int32 or the planned capacity. */
+__device__ __forceinline__ bool grid_params_from_bounds_dev(const uint32_t *__restrict__ bounds, float rx, float ry, float rz, float ext,
+		long long bucket_cap, m3dreg_grid_params &g)
 {
-	if (threadIdx.x != 0 || blockIdx.x != 0) return;
-	*cell_count = 0u;
 	float mnx = o2f(bounds[0]), mny = o2f(bounds[1]), mnz = o2f(bounds[2]);
 	float mxx = o2f(bounds[3]), mxy = o2f(bounds[4]), mxz = o2f(bounds[5]);
 	mxx = __fadd_rn(mxx, ext); mnx = __fsub_rn(mnx, ext);
@@ -191,17 +188,14 @@ __global__ void k_grid_params(const uint32_t *__restrict__ bounds, float rx, flo
 	int nby = (int)__fadd_rn(__fdiv_rn(__fsub_rn(mxy, mny), ry), 1.0f);
 	int nbz = (int)__fadd_rn(__fdiv_rn(__fsub_rn(mxz, mnz), rz), 1.0f);
 	long long nb = (long long)nbx * (long long)nby * (long long)nbz;
-	gp->bounding_box_min_X = mnx; gp->bounding_box_min_Y = mny; gp->bounding_box_min_Z = mnz;
-	gp->bounding_box_max_X = mxx; gp->bounding_box_max_Y = mxy; gp->bounding_box_max_Z = mxz;
-	gp->number_of_buckets_X = nbx; gp->number_of_buckets_Y = nby; gp->number_of_buckets_Z = nbz;
-	gp->resolution_X = rx; gp->resolution_Y = ry; gp->resolution_Z = rz;
-	gp->_pad0 = 0; gp->_pad1 = 0;
-	if (nbx <= 0 || nby <= 0 || nbz <= 0 || nb > 2147483647LL || nb > bucket_cap) {
-		gp->number_of_buckets = 0;
-		atomicExch(&flags[FLAG_ERROR], M3DREG_E_TOO_MANY_BUCKETS);
-	} else {
-		gp->number_of_buckets = nb;
-	}
+	g.bounding_box_min_X = mnx; g.bounding_box_min_Y = mny; g.bounding_box_min_Z = mnz;
+	g.bounding_box_max_X = mxx; g.bounding_box_max_Y = mxy; g.bounding_box_max_Z = mxz;
+	g.number_of_buckets_X = nbx; g.number_of_buckets_Y = nby; g.number_of_buckets_Z = nbz;
+	g.resolution_X = rx; g.resolution_Y = ry; g.resolution_Z = rz;
+	g._pad0 = 0; g._pad1 = 0;
+	bool ok = !(nbx <= 0 || nby <= 0 || nbz <= 0 || nb > 2147483647LL || nb > bucket_cap);
+	g.number_of_buckets = ok ? nb : 0;
+	return ok;
 }
 
 __device__ __forceinline__ int cell_of(float v, float mn, float res)
@@ -209,21 +203,79 @@ __device__ __forceinline__ int cell_of(float v, float mn, float res)
 	return (int)__fdiv_rn(__fsub_rn(v, mn), res);     /* sub.f32, div.rn.f32, cvt.rzi.s32.f32 */
 }
 
-/* Bucket key of every point (kernel_initializeIndByKey + kernel_getIndexOfBucketForPoints, lesson_16.cu:109-129),
- * values are the implicit original indices. */
-__global__ void k_keys_soa(const float4 *__restrict__ xyzl, int n, const m3dreg_grid_params *__restrict__ gp,
-		uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+/* Warp-level histogram update for one item per lane: lanes holding the same bin as their left neighbour form a run,
+ * and only the first lane of a run touches shared memory (bucket keys of a scan are strongly coherent, so a warp
+ * usually holds one or two runs).  bin < 0 marks an idle lane. */
+__device__ __forceinline__ void warp_run_hist(int bin, uint32_t *sh, int lane)
 {
-	if (gp->number_of_buckets <= 0) return;
-	float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
-	float rx = gp->resolution_X, ry = gp->resolution_Y, rz = gp->resolution_Z;
-	int nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		float4 p = __ldg(xyzl + i);
-		int ix = cell_of(p.x, mnx, rx), iy = cell_of(p.y, mny, ry), iz = cell_of(p.z, mnz, rz);
-		keys[i] = (uint32_t)(ix * nby * nbz + iy * nbz + iz);
-		vals[i] = (uint32_t)i;
+	const unsigned full = 0xffffffffu;
+	int prev = __shfl_up_sync(full, bin, 1);
+	bool head = (lane == 0) || (prev != bin);
+	unsigned heads = __ballot_sync(full, head);
+	if (head && bin >= 0) {
+		unsigned later = heads & ~((2u << lane) - 1u);      /* heads strictly above this lane */
+		int len = (later ? __ffs(later) - 1 : 32) - lane;
+		atomicAdd(&sh[bin], (uint32_t)len);
 	}
+}
+
+constexpr int kRadixBits = 8;
+constexpr int kRadixSize = 1 << kRadixBits;
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+
+/* Head of the grid build of the fused loop, one block per sort tile:
+ *   - grid parameters from the reduced bounds (every block recomputes them; block 0 publishes them, raises the error
+ *     flag and resets the occupied-bucket counter),
+ *   - dense bucket table reset to {-1,-1,0} (kernel_initializeBuckets, lesson_16.cu:131-140),
+ *   - bucket key of every point (kernel_initializeIndByKey + kernel_getIndexOfBucketForPoints, lesson_16.cu:109-129;
+ *     values are the implicit original indices and are not stored),
+ *   - the first radix pass's per-tile digit histogram, and zeroing of the later passes' histograms. */
+template <int ITEMS>
+__global__ void __launch_bounds__(kSortThreads) k_grid_head(const float4 *__restrict__ xyzl, int n, const uint32_t *__restrict__ bounds,
+		float rx, float ry, float rz, float ext, long long bucket_cap, m3dreg_grid_params *__restrict__ gp_out, int *__restrict__ flags,
+		unsigned int *__restrict__ cell_count, m3dreg_bucket *__restrict__ buckets, uint32_t *__restrict__ keys,
+		int tiles, int passes, uint32_t *__restrict__ hist)
+{
+	__shared__ uint32_t sh[kRadixSize];
+	m3dreg_grid_params g;
+	bool ok = grid_params_from_bounds_dev(bounds, rx, ry, rz, ext, bucket_cap, g);
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		*gp_out = g;
+		*cell_count = 0u;
+		if (!ok) atomicExch(&flags[FLAG_ERROR], M3DREG_E_TOO_MANY_BUCKETS);
+	}
+	if (!ok) return;
+	sh[threadIdx.x] = 0;
+	{   /* bucket table reset, 12-byte records written as a flat int stream: -1,-1,0,-1,-1,0,... */
+		long long total = g.number_of_buckets * 3;
+		int *flat = reinterpret_cast<int *>(buckets);
+		for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+			flat[i] = (i % 3 == 2) ? 0 : -1;
+		/* histograms of passes 1.. are accumulated by the scatter kernels */
+		long long hz = (long long)(passes - 1) * kRadixSize * tiles;
+		for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hz; i += (long long)gridDim.x * blockDim.x)
+			hist[(size_t)kRadixSize * tiles + i] = 0u;
+	}
+	__syncthreads();
+	const int nby = g.number_of_buckets_Y, nbz = g.number_of_buckets_Z;
+	const int lane = threadIdx.x & 31;
+	const int base = blockIdx.x * (kSortThreads * ITEMS);
+#pragma unroll
+	for (int j = 0; j < ITEMS; j++) {
+		int i = base + j * kSortThreads + threadIdx.x;
+		int bin = -1;
+		if (i < n) {
+			float4 p = __ldg(xyzl + i);
+			int ix = cell_of(p.x, g.bounding_box_min_X, rx), iy = cell_of(p.y, g.bounding_box_min_Y, ry), iz = cell_of(p.z, g.bounding_box_min_Z, rz);
+			uint32_t k = (uint32_t)(ix * nby * nbz + iy * nbz + iz);
+			keys[i] = k;
+			bin = (int)(k & (kRadixSize - 1));
+		}
+		warp_run_hist(bin, sh, lane);
+	}
+	__syncthreads();
+	hist[(size_t)threadIdx.x * tiles + blockIdx.x] = sh[threadIdx.x];
 }
 
 __global__ void k_keys_aos(const m3dreg_point *__restrict__ in, int n, const m3dreg_grid_params *__restrict__ gp,
@@ -275,11 +327,6 @@ __global__ void k_keys_presort(const m3dreg_point *__restrict__ in, int n, float
  *   k_radix_scatter stable in-tile ranking (warp match-any multisplit) + scatter
  * Stability gives ties in ascending original index, i.e. exactly the permutation of the reference's stable merge sort.
  * Keys are non-negative ints (valid cells), so unsigned order == signed order. */
-constexpr int kRadixBits = 8;
-constexpr int kRadixSize = 1 << kRadixBits;
-constexpr int kSortThreads = 256;
-constexpr int kSortWarps = kSortThreads / 32;
-
 template <int ITEMS>
 __global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint32_t *__restrict__ keys, int n, int shift,
 		int tiles, uint32_t *__restrict__ hist, const m3dreg_grid_params *__restrict__ gp)
@@ -293,14 +340,11 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint32_t *__r
 #pragma unroll
 	for (int j = 0; j < ITEMS; j++) {
 		int i = base + j * kSortThreads + threadIdx.x;
-		bool valid = i < n;
-		uint32_t d = valid ? ((__ldg(keys + i) >> shift) & (kRadixSize - 1)) : (0x100u + lane);
-		/* bucket keys are heavily skewed (dense cells): aggregate equal digits inside the warp first */
-		uint32_t peers = __match_any_sync(0xffffffffu, d);
-		if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[d], (uint32_t)__popc(peers));
+		int bin = i < n ? (int)((__ldg(keys + i) >> shift) & (kRadixSize - 1)) : -1;
+		warp_run_hist(bin, sh, lane);
 	}
 	__syncthreads();
-	hist[threadIdx.x * tiles + blockIdx.x] = sh[threadIdx.x];
+	hist[(size_t)threadIdx.x * tiles + blockIdx.x] = sh[threadIdx.x];
 }
 
 /* One block per digit: exclusive scan of that digit's row of per-tile counts (in place) and the row total. */
@@ -337,7 +381,8 @@ __global__ void __launch_bounds__(256) k_radix_scan(uint32_t *__restrict__ hist,
 template <int ITEMS>
 __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
 		uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int n, int shift, int tiles,
-		const uint32_t *__restrict__ hist, const uint32_t *__restrict__ digit_tot, const m3dreg_grid_params *__restrict__ gp)
+		const uint32_t *__restrict__ hist, const uint32_t *__restrict__ digit_tot, const m3dreg_grid_params *__restrict__ gp,
+		uint32_t *__restrict__ next_hist)
 {
 	__shared__ uint32_t wcnt[kSortWarps][kRadixSize];   /* per-warp digit counts, then per-warp exclusive offsets */
 	__shared__ uint32_t gbase[kRadixSize];
@@ -369,7 +414,7 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *
 		int i = wbase + j * 32 + lane;
 		bool valid = i < n;
 		key[j] = valid ? __ldg(keys_in + i) : 0xFFFFFFFFu;
-		val[j] = valid ? __ldg(vals_in + i) : 0u;
+		val[j] = valid ? (vals_in ? __ldg(vals_in + i) : (uint32_t)i) : 0u;      /* vals_in == 0: implicit original indices */
 		uint32_t d = (key[j] >> shift) & (kRadixSize - 1);
 		/* invalid lanes must not disturb the counts of digit 0xFF: give them their own match group */
 		uint32_t mk = valid ? d : (0x100u + lane);
@@ -403,6 +448,20 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *
 			uint32_t pos = gbase[d] + wcnt[w][d] + rank[j];
 			keys_out[pos] = key[j];
 			vals_out[pos] = val[j];
+			rank[j] = pos;
+		}
+	}
+	if (next_hist) {
+		/* the next pass's per-tile digit histogram, accumulated where the items land: one atomic per group of equal
+		 * (next digit, destination tile) inside the warp */
+#pragma unroll
+		for (int j = 0; j < ITEMS; j++) {
+			int i = wbase + j * 32 + lane;
+			bool valid = i < n;
+			uint32_t slot = valid ? ((key[j] >> (shift + kRadixBits)) & (kRadixSize - 1)) * (uint32_t)tiles + rank[j] / (uint32_t)(kSortThreads * ITEMS)
+					: (0xFFFFFF00u + lane);
+			uint32_t peers = __match_any_sync(0xffffffffu, slot);
+			if (valid && lane == __ffs(peers) - 1) atomicAdd(next_hist + slot, (uint32_t)__popc(peers));
 		}
 	}
 }
@@ -429,11 +488,13 @@ __device__ __forceinline__ int lower_bound_u32(const uint32_t *__restrict__ a, i
 	return lo;
 }
 
-/* One thread per sorted position p.  The thread at the END of a run writes the whole 12-byte record
- * {begin, end, n} (begin by binary search), so no separate count pass is needed.  Reference quirk reproduced
- * (lesson_16.cu:148-158): when element 0 is alone in its bucket, the run that starts at position 1 never gets
- * index_begin (it receives index_end=1 instead), so that bucket reads {-1, end, 0}.  Its index_end is a write
- * race upstream (1 vs run end); we store the run end.  Optionally materialises the reference's hashElement table. */
+/* One thread per sorted position p (kernel_updateBuckets + kernel_countNumberOfPointsForBuckets, lesson_16.cu:142-189).
+ * The thread at the START of a run writes index_begin, the one at its END index_end, and every warp adds the length of
+ * its piece of the run to number_of_points (integer atomics: deterministic) — no search, every step is one memory
+ * latency.  Reference quirk reproduced (lesson_16.cu:148-158): when element 0 is alone in its bucket, the run that
+ * starts at position 1 never gets index_begin (it receives index_end = 1 instead), so that bucket reads {-1, end, 0}.
+ * Its index_end is a write race upstream (1 vs run end); we store the run end.  The table must have been reset to
+ * {-1,-1,0}.  Optionally materialises the reference's hashElement table and the compact list of searchable buckets. */
 __global__ void k_finalize_grid(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int n,
 		const m3dreg_grid_params *__restrict__ gp, m3dreg_bucket *__restrict__ buckets, m3dreg_hash_element *__restrict__ table_out,
 		uint32_t *__restrict__ cell_list, unsigned int *__restrict__ cell_count)
@@ -441,11 +502,14 @@ __global__ void k_finalize_grid(const uint32_t *__restrict__ keys, const uint32_
 	if (gp && gp->number_of_buckets <= 0) return;
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
-	const int nround = (n + 31) & ~31;      /* whole warps stay together for the ballot below */
+	const int nround = (n + 31) & ~31;      /* whole warps stay together for the ballots below */
+	const uint32_t k0 = __ldg(keys), k1 = n > 1 ? __ldg(keys + 1) : k0;
+	const bool has_quirk = n > 1 && k0 != k1;
 	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
-		bool listed = false;
-		uint32_t k = 0;
-		if (p < n) {
+		bool listed = false, valid = p < n;
+		uint32_t k = 0xFFFFFFFFu;
+		bool quirk = false;
+		if (valid) {
 			k = __ldg(keys + p);
 			if (table_out) {
 				m3dreg_hash_element h;
@@ -453,17 +517,22 @@ __global__ void k_finalize_grid(const uint32_t *__restrict__ keys, const uint32_
 				h.index_of_bucket = (int)k;
 				table_out[p] = h;
 			}
+			quirk = has_quirk && k == k1;
+			bool run_start = (p == 0) || (__ldg(keys + p - 1) != k);
 			bool run_end = (p == n - 1) || (__ldg(keys + p + 1) != k);
-			if (run_end) {
-				int begin = lower_bound_u32(keys, p + 1, k);
-				m3dreg_bucket b;
-				if (begin == 1 && n > 1) {           /* element 0 alone in its bucket -> quirk for this (second) run */
-					b.index_begin = -1; b.index_end = p + 1; b.number_of_points = 0;
-				} else {
-					b.index_begin = begin; b.index_end = p + 1; b.number_of_points = p + 1 - begin;
-					listed = true;
-				}
-				buckets[k] = b;
+			int *bp = reinterpret_cast<int *>(buckets + k);
+			if (run_start && !quirk) bp[0] = p;
+			if (run_end) { bp[1] = p + 1; listed = !quirk; }
+		}
+		{   /* number_of_points: one atomic per piece of a run inside this warp */
+			uint32_t prev = __shfl_up_sync(full, k, 1);
+			bool head = (lane == 0) || (prev != k);
+			unsigned heads = __ballot_sync(full, head);
+			if (head && valid && !quirk) {
+				unsigned later = heads & ~((2u << lane) - 1u);
+				int len = (later ? __ffs(later) - 1 : 32) - lane;
+				if (p + len > n) len = n - p;
+				atomicAdd(reinterpret_cast<int *>(buckets + k) + 2, len);
 			}
 		}
 		if (cell_list) {   /* compact list of the searchable buckets (order irrelevant): one atomic per warp */
@@ -1140,43 +1209,56 @@ __device__ __host__ inline void moments_to_neq(const double *mo, double om, doub
 
 /* Lower Cholesky + two triangular solves (linearSolverCHOL, AXB:484-539) of the dof-subsystem of a packed system.
  * dof 6: all unknowns; dof 4: {tx,ty,tz,ka} (fill_A_l_4DOFcuda keeps columns 0,1,2,5, lesson_16.cu:493-495).
+ * Fully unrolled so the whole factorisation lives in registers; one sqrt and one reciprocal per column.
  * Returns 0 or M3DREG_E_NOT_SPD. */
-__device__ __host__ inline int solve_packed(const double *neq, int dof, double *x)
+template <int DOF>
+__device__ __forceinline__ int solve_packed_n(const double *neq, double *x)
 {
-	const int sel6[6] = {0, 1, 2, 3, 4, 5}, sel4[4] = {0, 1, 2, 5};
-	const int *sel = dof == 6 ? sel6 : sel4;
-	double full[6][6];
-	int k = 0;
-	for (int i = 0; i < 6; i++)
-		for (int j = i; j < 6; j++) { full[i][j] = neq[k]; full[j][i] = neq[k]; k++; }
-	double A[6][6], b[6], L[6][6], y[6];
-	for (int i = 0; i < dof; i++) {
-		b[i] = neq[21 + sel[i]];
-		for (int j = 0; j < dof; j++) { A[i][j] = full[sel[i]][sel[j]]; L[i][j] = 0; }
-	}
-	for (int j = 0; j < dof; j++) {
-		double d = A[j][j];
+	/* packed index of (i, j), i <= j, in the 6x6 upper triangle */
+	auto pk = [](int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); };
+	auto sel = [](int i) { return DOF == 6 ? i : (i < 3 ? i : 5); };
+	double L[DOF][DOF], inv[DOF], y[DOF];
+#pragma unroll
+	for (int j = 0; j < DOF; j++) {
+		double d = neq[pk(sel(j), sel(j))];
+#pragma unroll
 		for (int c = 0; c < j; c++) d -= L[j][c] * L[j][c];
 		if (!(d > 0.0)) return M3DREG_E_NOT_SPD;
 		d = sqrt(d);
 		L[j][j] = d;
-		for (int i = j + 1; i < dof; i++) {
-			double s = A[i][j];
+		inv[j] = 1.0 / d;
+#pragma unroll
+		for (int i = j + 1; i < DOF; i++) {
+			double s = neq[pk(sel(j), sel(i))];
+#pragma unroll
 			for (int c = 0; c < j; c++) s -= L[i][c] * L[j][c];
-			L[i][j] = s / d;
+			L[i][j] = s * inv[j];
 		}
 	}
-	for (int i = 0; i < dof; i++) {
-		double s = b[i];
+#pragma unroll
+	for (int i = 0; i < DOF; i++) {
+		double s = neq[21 + sel(i)];
+#pragma unroll
 		for (int c = 0; c < i; c++) s -= L[i][c] * y[c];
-		y[i] = s / L[i][i];
+		y[i] = s * inv[i];
 	}
-	for (int i = dof - 1; i >= 0; i--) {
+#pragma unroll
+	for (int i = DOF - 1; i >= 0; i--) {
 		double s = y[i];
-		for (int c = i + 1; c < dof; c++) s -= L[c][i] * x[c];
-		x[i] = s / L[i][i];
+#pragma unroll
+		for (int c = i + 1; c < DOF; c++) s -= L[c][i] * x[c];
+		x[i] = s * inv[i];
 	}
 	return 0;
+}
+
+__device__ inline int solve_packed(const double *neq, int dof, double *x)
+{
+	if (dof == 6) return solve_packed_n<6>(neq, x);
+	double x4[4] = {0, 0, 0, 0};
+	int st = solve_packed_n<4>(neq, x4);
+	x[0] = x4[0]; x[1] = x4[1]; x[2] = x4[2]; x[3] = x4[3];
+	return st;
 }
 
 /* Matrix4ToEuler / EulerToMatrix (cudaWrapper.cpp:470-514), row-major 4x4.  Double transcendental functions
@@ -1235,6 +1317,8 @@ __device__ __host__ inline void euler_to_matrix(const float *omfika, const float
 #undef M3D_SUB
 }
 
+__device__ inline void pose_prepare_warp(PoseState *ps, int lane);
+
 /* Start of an iteration of registerLastArrivedScan (gpu6DSLAM.cpp:276-291): Euler round trip of the stored pose. */
 __device__ inline void pose_prepare(PoseState *ps)
 {
@@ -1247,10 +1331,138 @@ __device__ inline void pose_prepare(PoseState *ps)
 
 __global__ void k_pose_prepare(PoseState *ps)
 {
-	if (threadIdx.x == 0 && blockIdx.x == 0) pose_prepare(ps);
+	if (blockIdx.x == 0 && threadIdx.x < 32) pose_prepare_warp(ps, threadIdx.x);
 }
 
-/* Per-observation sources for the moment reduction. */
+/* ---- warp-cooperative versions of the serial tail ------------------------------------------------------------
+ * The last block's tail (6x6 system, Cholesky, pose update, two Euler conversions) is a chain of ~20 double
+ * precision transcendental calls when one thread runs it; here the calls that do not depend on each other are
+ * spread over lanes executing the SAME code (no divergence), which cuts the chain to 6 call latencies.  Results are
+ * bit-identical to the serial helpers above (same operations on the same operands). */
+__device__ __forceinline__ double shfl_f64(double v, int src)
+{
+	return __shfl_sync(0xffffffffu, v, src);
+}
+
+__device__ inline void euler_to_matrix_warp(const float *omfika, const float *xyz, float *m, int lane)
+{
+	/* lanes 0..2: sin/cos of the three half angles */
+	float h = 0.5f * omfika[lane < 3 ? lane : 0];
+	float sn = (float)sin((double)h), cs = (float)cos((double)h);
+	float ax = __shfl_sync(0xffffffffu, sn, 0), aw = __shfl_sync(0xffffffffu, cs, 0);
+	float by = __shfl_sync(0xffffffffu, sn, 1), bw = __shfl_sync(0xffffffffu, cs, 1);
+	float cz = __shfl_sync(0xffffffffu, sn, 2), cw = __shfl_sync(0xffffffffu, cs, 2);
+	float w1 = __fmul_rn(aw, bw), x1 = __fmul_rn(ax, bw), y1 = __fmul_rn(aw, by), z1 = __fmul_rn(ax, by);
+	float w = __fsub_rn(__fmul_rn(w1, cw), __fmul_rn(z1, cz));
+	float x = __fadd_rn(__fmul_rn(x1, cw), __fmul_rn(y1, cz));
+	float y = __fsub_rn(__fmul_rn(y1, cw), __fmul_rn(x1, cz));
+	float z = __fadd_rn(__fmul_rn(w1, cz), __fmul_rn(z1, cw));
+	float tx = __fmul_rn(2.0f, x), ty = __fmul_rn(2.0f, y), tz = __fmul_rn(2.0f, z);
+	float twx = __fmul_rn(tx, w), twy = __fmul_rn(ty, w), twz = __fmul_rn(tz, w);
+	float txx = __fmul_rn(tx, x), txy = __fmul_rn(ty, x), txz = __fmul_rn(tz, x);
+	float tyy = __fmul_rn(ty, y), tyz = __fmul_rn(tz, y), tzz = __fmul_rn(tz, z);
+	if (lane == 0) {
+		m[0] = __fsub_rn(1.0f, __fadd_rn(tyy, tzz)); m[1] = __fsub_rn(txy, twz); m[2] = __fadd_rn(txz, twy); m[3] = xyz[0];
+		m[4] = __fadd_rn(txy, twz); m[5] = __fsub_rn(1.0f, __fadd_rn(txx, tzz)); m[6] = __fsub_rn(tyz, twx); m[7] = xyz[1];
+		m[8] = __fsub_rn(txz, twy); m[9] = __fadd_rn(tyz, twx); m[10] = __fsub_rn(1.0f, __fadd_rn(txx, tyy)); m[11] = xyz[2];
+		m[12] = 0.0f; m[13] = 0.0f; m[14] = 0.0f; m[15] = 1.0f;
+	}
+	__syncwarp();
+}
+
+/* m: 16 floats readable by every lane (shared or global, already visible); results returned in every lane. */
+__device__ inline void matrix4_to_euler_warp(const float *m, float *omfika, float *xyz, int lane)
+{
+	const double kPi = 3.14159265358979323846;
+	float fi;
+	if (m[0] > 0.0) fi = (float)asin((double)m[2]);
+	else fi = (float)(kPi - asin((double)m[2]));
+	double C = cos((double)fi);
+	float om, ka;
+	if (fabs(C) > 0.005) {
+		/* lane 0: om = atan2(-m6/C, m10/C); lane 1: ka = atan2(-m1/C, m0/C) */
+		double trX = (lane == 0 ? m[10] : m[0]) / C, trY = -(lane == 0 ? m[6] : m[1]) / C;
+		float a = (float)atan2(trY, trX);
+		om = __shfl_sync(0xffffffffu, a, 0);
+		ka = __shfl_sync(0xffffffffu, a, 1);
+	} else {
+		om = 0.0f;
+		ka = (float)atan2((double)m[4], (double)m[5]);
+	}
+	omfika[0] = om; omfika[1] = fi; omfika[2] = ka;
+	xyz[0] = m[3]; xyz[1] = m[7]; xyz[2] = m[11];
+}
+
+/* Start of an iteration (gpu6DSLAM.cpp:276-291) by one warp: Euler round trip of ps->m into pose1 / pose6. */
+__device__ inline void pose_prepare_warp(PoseState *ps, int lane)
+{
+	float of[3], t[3];
+	matrix4_to_euler_warp(ps->m, of, t, lane);
+	euler_to_matrix_warp(of, t, ps->pose1, lane);
+	if (lane == 0) {
+		ps->pose6[0] = t[0]; ps->pose6[1] = t[1]; ps->pose6[2] = t[2];
+		ps->pose6[3] = of[0]; ps->pose6[4] = of[1]; ps->pose6[5] = of[2];
+	}
+	__syncwarp();
+}
+
+/* 6x6 system from the 24 moments, one output per lane (27 outputs), same formula for every lane:
+ * with A = -[I | J], J[r][c] = C[r][c] . p0, every column a of A is, in row r, -(E[r][a] . (1, p0)) for a 4-vector
+ * E[r][a] ( (delta_ra,0,0,0) for a < 3, (0, C[r][a-3]) otherwise ), hence
+ *     N[a][b] = sum_r E[r][a]^T Mext E[r][b],   rhs[a] = - sum_r E[r][a]^T Lext[:, r],
+ * Mext = [[S, M1^T], [M1, M2]] (4x4), Lext = [[L1^T], [L2]] (4x3). */
+__device__ inline void moments_to_neq_warp(const double *mo, double om, double fi, double ka, double *neq, int lane)
+{
+	/* lanes 0..2: sincos of om, fi, ka */
+	double ang = lane == 0 ? om : (lane == 1 ? fi : ka), sn, cs;
+	sincos(ang, &sn, &cs);
+	double so = shfl_f64(sn, 0), co = shfl_f64(cs, 0), sf = shfl_f64(sn, 1), cf = shfl_f64(cs, 1), sk = shfl_f64(sn, 2), ck = shfl_f64(cs, 2);
+	double R11 = cf * ck, R12 = -cf * sk;
+	double R21 = co * sk + so * sf * ck, R22 = co * ck - so * sf * sk, R23 = -so * cf;
+	double R31 = so * sk - co * sf * ck, R32 = so * ck + co * sf * sk, R33 = co * cf;
+	const double C[3][3][3] = {
+		{{0, 0, 0}, {-sf * ck, sf * sk, cf}, {R12, -R11, 0}},
+		{{-R31, -R32, -R33}, {so * cf * ck, -so * cf * sk, so * sf}, {R22, -R21, 0}},
+		{{R21, R22, R23}, {-co * cf * ck, co * cf * sk, -co * sf}, {R32, -R31, 0}}};
+	/* output index -> (a, b): k < 21 walks the upper triangle row by row, 21..26 are the right-hand side */
+	int a = 0, b = 0;
+	bool rhs = lane >= 21;
+	if (!rhs) { int k = lane, row = 0; while (k >= 6 - row) { k -= 6 - row; row++; } a = row; b = row + k; }
+	else a = lane - 21;
+	const double Mext[4][4] = {{mo[0], mo[1], mo[2], mo[3]}, {mo[1], mo[4], mo[5], mo[6]}, {mo[2], mo[5], mo[7], mo[8]}, {mo[3], mo[6], mo[8], mo[9]}};
+	double acc = 0.0;
+#pragma unroll
+	for (int r = 0; r < 3; r++) {
+		double ea[4], eb[4];
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			double ca = 0.0, cb = 0.0;
+#pragma unroll
+			for (int c = 0; c < 3; c++) {   /* select C[r][a-3][i-1] / C[r][b-3][i-1] without dynamic indexing */
+				if (i > 0 && a == 3 + c) ca = C[r][c][i - 1];
+				if (i > 0 && b == 3 + c) cb = C[r][c][i - 1];
+			}
+			ea[i] = (a < 3) ? ((i == 0 && a == r) ? 1.0 : 0.0) : ca;
+			eb[i] = (b < 3) ? ((i == 0 && b == r) ? 1.0 : 0.0) : cb;
+		}
+		if (!rhs) {
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				double t = Mext[i][0] * eb[0] + Mext[i][1] * eb[1] + Mext[i][2] * eb[2] + Mext[i][3] * eb[3];
+				acc += ea[i] * t;
+			}
+		} else {
+			/* Lext[:, r] = (L1[r], L2[0*3+r], L2[1*3+r], L2[2*3+r]) */
+			acc -= ea[0] * mo[10 + r] + ea[1] * mo[13 + r] + ea[2] * mo[16 + r] + ea[3] * mo[19 + r];
+		}
+	}
+	if (lane < 27) neq[lane] = acc;
+	if (lane == 27) neq[27] = mo[22];
+	__syncwarp();
+}
+
+/* Per-observation sources for the moment reduction.  Three steps so that a thread can keep several observations in
+ * flight: token(i) (first load), fetch(i, token, raw) (dependent gathers), finish(raw, ...) (arithmetic). */
 struct ObsFromNN {   /* fused path: nn[] + clouds (gpu6DSLAM.cpp:323-398 done on the device) */
 	const int *nn;
 	const float4 *q_xyzl;       /* queries (second cloud, global)           */
@@ -1258,28 +1470,36 @@ struct ObsFromNN {   /* fused path: nn[] + clouds (gpu6DSLAM.cpp:323-398 done on
 	const float4 *l_xyzl;       /* first cloud, local, original order       */
 	const unsigned long long *label_counts;
 	float weight[4];
-	__device__ __forceinline__ bool get(int i, const float *wl, double &w, double &x, double &y, double &z, double &lx, double &ly, double &lz) const
+	struct Raw { float4 p2, p1, p0; };
+	__device__ __forceinline__ int token(int i) const { return __ldg(nn + i); }
+	__device__ __forceinline__ void fetch(int i, int j, Raw &r) const
 	{
-		int j = __ldg(nn + i);
-		if (j < 0) return false;
-		float4 p2 = __ldg(q_xyzl + i), p1 = __ldg(g_xyzl + j), p0 = __ldg(l_xyzl + j);
-		int label = __float_as_int(p2.w);
+		r.p2 = __ldg(q_xyzl + i); r.p1 = __ldg(g_xyzl + j); r.p0 = __ldg(l_xyzl + j);
+	}
+	__device__ __forceinline__ void finish(const Raw &r, const float *wl, double &w, double &x, double &y, double &z,
+			double &lx, double &ly, double &lz) const
+	{
+		int label = __float_as_int(r.p2.w);
 		w = (label >= 0 && label < 4) ? (double)wl[label] : 0.0;
-		x = p0.x; y = p0.y; z = p0.z;
-		lx = (double)__fsub_rn(p1.x, p2.x); ly = (double)__fsub_rn(p1.y, p2.y); lz = (double)__fsub_rn(p1.z, p2.z);
-		return true;
+		x = r.p0.x; y = r.p0.y; z = r.p0.z;
+		lx = (double)__fsub_rn(r.p1.x, r.p2.x); ly = (double)__fsub_rn(r.p1.y, r.p2.y); lz = (double)__fsub_rn(r.p1.z, r.p2.z);
 	}
 };
 
 struct ObsFromList { /* stage-level path: the reference's obs_nn_t array */
 	const m3dreg_obs_nn *obs;
-	__device__ __forceinline__ bool get(int i, const float *, double &w, double &x, double &y, double &z, double &lx, double &ly, double &lz) const
+	struct Raw { float v[7]; };
+	__device__ __forceinline__ int token(int) const { return 0; }
+	__device__ __forceinline__ void fetch(int i, int, Raw &r) const
 	{
 		const float *o = reinterpret_cast<const float *>(obs + i);
-		lx = __ldg(o); ly = __ldg(o + 1); lz = __ldg(o + 2);
-		x = __ldg(o + 3); y = __ldg(o + 4); z = __ldg(o + 5);
-		w = __ldg(o + 6);
-		return true;
+#pragma unroll
+		for (int k = 0; k < 7; k++) r.v[k] = __ldg(o + k);
+	}
+	__device__ __forceinline__ void finish(const Raw &r, const float *, double &w, double &x, double &y, double &z,
+			double &lx, double &ly, double &lz) const
+	{
+		lx = r.v[0]; ly = r.v[1]; lz = r.v[2]; x = r.v[3]; y = r.v[4]; z = r.v[5]; w = r.v[6];
 	}
 };
 
@@ -1296,47 +1516,54 @@ struct FinalizeArgs {
 	unsigned long long *label_counts_reset;
 };
 
-/* What ONE thread of the last block does with the finished 28-double system: publish / accumulate it, and (fused
- * loop) gate on the observation count, Cholesky, pose update, Euler round trip for the next iteration, resets. */
-__device__ inline void neq_tail(const double *neq, const FinalizeArgs &fin)
+/* What warp 0 of the last block does with the finished 28-double system `neq` (shared memory): publish / accumulate
+ * it, and (fused loop) gate on the observation count, Cholesky, pose update, Euler round trip for the next iteration,
+ * resets. */
+__device__ inline void neq_tail_warp(const double *neq, const FinalizeArgs &fin, int lane)
 {
-	if (fin.neq_out) {
-		for (int k = 0; k < kNeqCount; k++) fin.neq_out[k] = fin.accumulate ? fin.neq_out[k] + neq[k] : neq[k];
-	}
+	if (fin.neq_out && lane < kNeqCount) fin.neq_out[lane] = fin.accumulate ? fin.neq_out[lane] + neq[lane] : neq[lane];
 	if (fin.solve && fin.ps) {
 		PoseState *ps = fin.ps;
-		for (int k = 0; k < kNeqCount; k++) ps->neq[k] = neq[k];
+		if (lane < kNeqCount) ps->neq[lane] = neq[lane];
 		long long n_obs = (long long)(neq[27] + 0.5);
-		ps->n_obs = n_obs;
 		int status = M3DREG_E_TOO_FEW_OBS;
 		double x[6] = {0, 0, 0, 0, 0, 0};
-		if (n_obs > (long long)fin.obs_threshold) {                       /* gpu6DSLAM.cpp:402 */
-			status = solve_packed(neq, fin.dof, x);
-			if (status == 0) {
-				/* registerLS tail (cudaWrapper.cpp:574-579 / 641-646) + EulerToMatrix (gpu6DSLAM.cpp:408-413) */
-				ps->pose6[0] += x[0]; ps->pose6[1] += x[1]; ps->pose6[2] += x[2];
-				if (fin.dof == 6) { ps->pose6[3] += x[3]; ps->pose6[4] += x[4]; ps->pose6[5] += x[5]; }
-				else ps->pose6[5] += x[3];
-				float of[3] = {(float)ps->pose6[3], (float)ps->pose6[4], (float)ps->pose6[5]};
-				float t[3] = {(float)ps->pose6[0], (float)ps->pose6[1], (float)ps->pose6[2]};
-				euler_to_matrix(of, t, ps->m);
-			}
+		if (n_obs > (long long)fin.obs_threshold) status = solve_packed(neq, fin.dof, x);     /* gpu6DSLAM.cpp:402; uniform over lanes */
+		double p6[6];
+#pragma unroll
+		for (int k = 0; k < 6; k++) p6[k] = ps->pose6[k];
+		__syncwarp();
+		if (status == 0) {
+			/* registerLS tail (cudaWrapper.cpp:574-579 / 641-646) + EulerToMatrix (gpu6DSLAM.cpp:408-413) */
+			p6[0] += x[0]; p6[1] += x[1]; p6[2] += x[2];
+			if (fin.dof == 6) { p6[3] += x[3]; p6[4] += x[4]; p6[5] += x[5]; }
+			else p6[5] += x[3];
+			float of[3] = {(float)p6[3], (float)p6[4], (float)p6[5]};
+			float t[3] = {(float)p6[0], (float)p6[1], (float)p6[2]};
+			euler_to_matrix_warp(of, t, ps->m, lane);
 		}
-		for (int k = 0; k < 6; k++) ps->x[k] = x[k];
-		ps->status = status;
-		ps->iterations += 1;
-		pose_prepare(ps);   /* next iteration's Euler round trip */
+		if (lane == 0) {
+			for (int k = 0; k < 6; k++) ps->x[k] = x[k];
+			ps->n_obs = n_obs;
+			ps->status = status;
+			ps->iterations += 1;
+		}
+		__syncwarp();
+		pose_prepare_warp(ps, lane);   /* next iteration's Euler round trip */
 	}
-	if (fin.bounds_reset) {
-		fin.bounds_reset[0] = fin.bounds_reset[1] = fin.bounds_reset[2] = 0xFFFFFFFFu;
-		fin.bounds_reset[3] = fin.bounds_reset[4] = fin.bounds_reset[5] = 0u;
-	}
-	if (fin.label_counts_reset) {
-		fin.label_counts_reset[0] = fin.label_counts_reset[1] = fin.label_counts_reset[2] = fin.label_counts_reset[3] = 0ull;
+	if (lane == 0) {
+		if (fin.bounds_reset) {
+			fin.bounds_reset[0] = fin.bounds_reset[1] = fin.bounds_reset[2] = 0xFFFFFFFFu;
+			fin.bounds_reset[3] = fin.bounds_reset[4] = fin.bounds_reset[5] = 0u;
+		}
+		if (fin.label_counts_reset) {
+			fin.label_counts_reset[0] = fin.label_counts_reset[1] = fin.label_counts_reset[2] = fin.label_counts_reset[3] = 0ull;
+		}
 	}
 }
 
 constexpr int kNeqThreads = 256;
+constexpr int kNeqInFlight = 4;
 
 template <class Src>
 __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(Src src, int n, double *__restrict__ partials,
@@ -1357,9 +1584,25 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(Src src, int n
 	__syncthreads();
 	Moments mo;
 	mo.clear();
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		double w, x, y, z, lx, ly, lz;
-		if (src.get(i, wl, w, x, y, z, lx, ly, lz)) mo.add(w, x, y, z, lx, ly, lz);
+	{
+		/* kNeqInFlight observations per thread in flight: index loads, then the dependent gathers, then the arithmetic */
+		const int stride = gridDim.x * blockDim.x;
+		for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += kNeqInFlight * stride) {
+			int tok[kNeqInFlight];
+			typename Src::Raw raw[kNeqInFlight];
+#pragma unroll
+			for (int k = 0; k < kNeqInFlight; k++) { int i = i0 + k * stride; tok[k] = i < n ? src.token(i) : -1; }
+#pragma unroll
+			for (int k = 0; k < kNeqInFlight; k++) { int i = i0 + k * stride; if (tok[k] >= 0) src.fetch(i, tok[k], raw[k]); }
+#pragma unroll
+			for (int k = 0; k < kNeqInFlight; k++) {
+				if (tok[k] >= 0) {
+					double w, x, y, z, lx, ly, lz;
+					src.finish(raw[k], wl, w, x, y, z, lx, ly, lz);
+					mo.add(w, x, y, z, lx, ly, lz);
+				}
+			}
+		}
 	}
 	int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -1392,12 +1635,12 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(Src src, int n
 		if (lane == 0) tot[col] = s;
 	}
 	__syncthreads();
-	if (threadIdx.x == 0) {
-		*ticket = 0;
-		double neq[kNeqCount];
+	if (wid == 0) {
+		__shared__ double neq[kNeqCount];
+		if (lane == 0) *ticket = 0;
 		const double *p6 = fin.ps ? fin.ps->pose6 : fin.pose6_in;
-		moments_to_neq(tot, p6[3], p6[4], p6[5], neq);
-		neq_tail(neq, fin);
+		moments_to_neq_warp(tot, p6[3], p6[4], p6[5], neq, lane);
+		neq_tail_warp(neq, fin, lane);
 	}
 }
 
@@ -1692,11 +1935,9 @@ __global__ void __launch_bounds__(kNeqThreads) k_ndt_normal_equations(const doub
 		if (lane == 0) tot[col] = s;
 	}
 	__syncthreads();
-	if (threadIdx.x == 0) {
-		*ticket = 0;
-		double neq[kNeqCount];
-		for (int k = 0; k < kNeqCount; k++) neq[k] = tot[k];
-		neq_tail(neq, fin);
+	if (wid == 0) {
+		if (lane == 0) *ticket = 0;
+		neq_tail_warp(tot, fin, lane);
 	}
 }
 

@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """SASS-level execution profile of a kernel from an .ncu-rep: consecutive instructions with the same execution
-count are folded into basic-block-like runs.  usage: python tools/ncu_sass.py rep [min_pct=1.0] [kernel-index=0]"""
+count are folded into basic-block-like runs.  usage: python tools/ncu_sass.py rep [min_pct=1.0] [kernel-regex]"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]
 min_pct = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+sel = ["-k", "regex:" + sys.argv[3], "-c", "1"] if len(sys.argv) > 3 else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr, data = None, []
 for r in rows:
