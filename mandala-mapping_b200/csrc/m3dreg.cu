@@ -215,6 +215,11 @@ int ensure_partials(m3dreg_ctx *c)
 	return c->partials.ensure((size_t)c->sm_count * 8 * kPartialCols);
 }
 
+#ifndef M3D_SORT_ITEMS
+#define M3D_SORT_ITEMS 8
+#endif
+constexpr int kSortItemsBig = M3D_SORT_ITEMS;   /* keys per thread of a sort tile for large inputs */
+
 struct SortPlan { int items, tiles, passes; };
 
 SortPlan plan_sort(int n, int bits)
@@ -222,7 +227,7 @@ SortPlan plan_sort(int n, int bits)
 	SortPlan sp;
 	sp.passes = (bits + kRadixBits - 1) / kRadixBits;
 	if (sp.passes < 1) sp.passes = 1;
-	sp.items = n >= (1 << 19) ? 16 : 4;
+	sp.items = n >= (1 << 19) ? kSortItemsBig : 4;
 	sp.tiles = (n + kSortThreads * sp.items - 1) / (kSortThreads * sp.items);
 	return sp;
 }
@@ -235,11 +240,11 @@ int sort_by_bucket(m3dreg_ctx *c, int n, int bits, const m3dreg_grid_params *gp,
 {
 	SortPlan sp = plan_sort(n, bits);
 	const size_t mat = (size_t)kRadixSize * sp.tiles;
-	const bool big = sp.items == 16;
+	const bool big = sp.items == kSortItemsBig;
 	int cur = 0;
 	if (!hist0_ready) {
 		if (sp.passes > 1) cudaMemsetAsync(c->hist.p + mat, 0, (size_t)(sp.passes - 1) * mat * sizeof(uint32_t), c->stream);
-		if (big) LAUNCH(c, k_radix_hist<16>, sp.tiles, kSortThreads, c->keys[0].p, n, 0, sp.tiles, c->hist.p, gp);
+		if (big) LAUNCH(c, k_radix_hist<kSortItemsBig>, sp.tiles, kSortThreads, c->keys[0].p, n, 0, sp.tiles, c->hist.p, gp);
 		else LAUNCH(c, k_radix_hist<4>, sp.tiles, kSortThreads, c->keys[0].p, n, 0, sp.tiles, c->hist.p, gp);
 	}
 	for (int p = 0; p < sp.passes; p++) {
@@ -248,7 +253,7 @@ int sort_by_bucket(m3dreg_ctx *c, int n, int bits, const m3dreg_grid_params *gp,
 		uint32_t *hn = p + 1 < sp.passes ? h + mat : nullptr;
 		const uint32_t *vin = (p == 0 && vals_implicit) ? nullptr : c->vals[cur].p;
 		LAUNCH(c, k_radix_scan, kRadixSize, 256, h, sp.tiles, c->digit_tot.p, gp);
-		if (big) LAUNCH(c, k_radix_scatter<16>, sp.tiles, kSortThreads, c->keys[cur].p, vin, c->keys[cur ^ 1].p, c->vals[cur ^ 1].p, n, shift, sp.tiles, h, c->digit_tot.p, gp, hn);
+		if (big) LAUNCH(c, k_radix_scatter<kSortItemsBig>, sp.tiles, kSortThreads, c->keys[cur].p, vin, c->keys[cur ^ 1].p, c->vals[cur ^ 1].p, n, shift, sp.tiles, h, c->digit_tot.p, gp, hn);
 		else LAUNCH(c, k_radix_scatter<4>, sp.tiles, kSortThreads, c->keys[cur].p, vin, c->keys[cur ^ 1].p, c->vals[cur ^ 1].p, n, shift, sp.tiles, h, c->digit_tot.p, gp, hn);
 		cur ^= 1;
 	}
@@ -294,10 +299,10 @@ CandSet cand_set(m3dreg_ctx *c, bool outer)
 /* gp must already be on the device (c->gp); src = the gridded cloud in original order; cell_list / c->cell_count
  * hold the searchable buckets. */
 void build_candidates(m3dreg_ctx *c, const uint32_t *vals, const m3dreg_bucket *buckets, const uint32_t *cell_list,
-		const float4 *src_xyzl, const float4 *src_nrm, int max_inner, int max_outer)
+		const float4 *src_xyzl, const float4 *src_nrm, const float *nrm_m, int max_inner, int max_outer)
 {
 	bool two = max_inner != max_outer;
-	LAUNCH(c, k_build_candidates, c->sm_count * 4, kBuildWarps * 32, vals, c->gp, buckets, cell_list, c->cell_count, src_xyzl, src_nrm,
+	LAUNCH(c, k_build_candidates, c->sm_count * 4, kBuildWarps * 32, vals, c->gp, buckets, cell_list, c->cell_count, src_xyzl, src_nrm, nrm_m,
 			max_inner, max_outer, cand_set(c, false), cand_set(c, two), two ? 1 : 0);
 }
 
@@ -312,11 +317,11 @@ void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *va
 
 /* Grid of the (already transformed) first cloud in g_*: params (device) from bounds, keys, sort, dense table,
  * sorted SoA copy.  bounds must already hold the reduced box. */
-void build_grid_fused(m3dreg_ctx *c, int n1, const m3dreg_reg_params *prm, int sort_bits)
+void build_grid_fused(m3dreg_ctx *c, int n1, const m3dreg_reg_params *prm, int sort_bits, const float4 *src_nrm, const float *nrm_m)
 {
 	SortPlan sp = plan_sort(n1, sort_bits);
-	if (sp.items == 16)
-		LAUNCH(c, k_grid_head<16>, sp.tiles, kSortThreads, c->g_xyzl.p, n1, c->bounds, prm->bucket_size, prm->bucket_size, prm->bucket_size,
+	if (sp.items == kSortItemsBig)
+		LAUNCH(c, k_grid_head<kSortItemsBig>, sp.tiles, kSortThreads, c->g_xyzl.p, n1, c->bounds, prm->bucket_size, prm->bucket_size, prm->bucket_size,
 				prm->bbox_extension, (long long)c->buckets.cap, c->gp, c->flags, c->cell_count, c->buckets.p, c->keys[0].p, sp.tiles, sp.passes, c->hist.p);
 	else
 		LAUNCH(c, k_grid_head<4>, sp.tiles, kSortThreads, c->g_xyzl.p, n1, c->bounds, prm->bucket_size, prm->bucket_size, prm->bucket_size,
@@ -326,7 +331,7 @@ void build_grid_fused(m3dreg_ctx *c, int n1, const m3dreg_reg_params *prm, int s
 	LAUNCH(c, k_finalize_grid, grid_for(c, n1, 256), 256, c->keys[cur].p, c->vals[cur].p, n1, c->gp, c->buckets.p,
 			(m3dreg_hash_element *)nullptr, c->keys[cur ^ 1].p, c->cell_count);
 	if (prm->mode != M3DREG_MODE_NDT)
-		build_candidates(c, c->vals[cur].p, c->buckets.p, c->keys[cur ^ 1].p, c->g_xyzl.p, c->g_nrm.p, prm->max_inner, prm->max_outer);
+		build_candidates(c, c->vals[cur].p, c->buckets.p, c->keys[cur ^ 1].p, c->g_xyzl.p, src_nrm, nrm_m, prm->max_inner, prm->max_outer);
 	c->last_sorted = cur;
 }
 
@@ -397,9 +402,9 @@ void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int
 {
 	const bool prof = c->profiling;
 	if (prof) cudaEventRecord(c->pev[0], c->stream);
-	LAUNCH(c, k_transform_soa<true>, grid_for(c, n1, 256), 256, lx, ln, n1, c->ps->pose1, c->g_xyzl.p, c->g_nrm.p, c->bounds);
+	LAUNCH(c, k_transform_soa<true>, grid_for(c, n1, 256), 256, lx, ln, n1, c->ps->pose1, c->g_xyzl.p, (float4 *)nullptr, c->bounds);
 	if (prof) cudaEventRecord(c->pev[1], c->stream);
-	build_grid_fused(c, n1, prm, sort_bits);
+	build_grid_fused(c, n1, prm, sort_bits, ln, c->ps->pose1);
 	if (prm->mode == M3DREG_MODE_NDT) {
 		ndt_bucket_stats(c, lx, n1);
 		if (prof) { cudaEventRecord(c->pev[2], c->stream); cudaEventRecord(c->pev[3], c->stream); }
@@ -650,7 +655,7 @@ int m3dreg_nn_search(m3dreg_ctx *c, const m3dreg_point *d_first, int n1, const m
 	LAUNCH(c, k_split_table, grid_for(c, n1, 256), 256, d_table, n1, c->keys[0].p, c->vals[0].p);
 	CK(cudaMemsetAsync(c->cell_count, 0, sizeof(unsigned int), c->stream));
 	LAUNCH(c, k_list_cells, grid_for(c, n1, 256), 256, c->keys[0].p, n1, d_buckets, c->keys[1].p, c->cell_count);
-	build_candidates(c, c->vals[0].p, d_buckets, c->keys[1].p, c->g_xyzl.p, c->g_nrm.p, max_inner, max_outer);
+	build_candidates(c, c->vals[0].p, d_buckets, c->keys[1].p, c->g_xyzl.p, c->g_nrm.p, (const float *)nullptr, max_inner, max_outer);
 	launch_nn(c, nullptr, n2, c->vals[0].p, n1, d_buckets, search_radius, max_inner, max_outer, c->prune, d_nn, nullptr, nullptr);
 	c->last_valid = false;
 	CK(cudaStreamSynchronize(c->stream));
@@ -755,7 +760,7 @@ int m3dreg_semantic_nn_host(m3dreg_ctx *c, const m3dreg_point *first, int n1, co
 	if ((e = ensure_candidates(c, (size_t)n1, max_inner, max_outer))) return e;
 	int sort_bits = 0;
 	if ((e = plan_buckets(c, &prm, &sort_bits))) return e;
-	build_grid_fused(c, n1, &prm, sort_bits);
+	build_grid_fused(c, n1, &prm, sort_bits, c->g_nrm.p, (const float *)nullptr);
 	launch_nn(c, nullptr, n2, c->vals[c->last_sorted].p, n1, c->buckets.p, search_radius, max_inner, max_outer, c->prune,
 			c->nn.p, nullptr, nullptr);
 	CK(cudaMemcpyAsync(nn_out, c->nn.p, (size_t)n2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -875,7 +880,7 @@ static int icp_begin_internal(m3dreg_ctx *c, const float4 *lx, const float4 *ln,
 	LAUNCH(c, k_pose_prepare, 1, 32, c->ps);
 	/* size the dense bucket table from the initial box (one sync, outside the iteration loop) */
 	LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
-	LAUNCH(c, k_transform_soa<true>, grid_for(c, n1, 256), 256, lx, ln, n1, c->ps->pose1, c->g_xyzl.p, c->g_nrm.p, c->bounds);
+	LAUNCH(c, k_transform_soa<true>, grid_for(c, n1, 256), 256, lx, ln, n1, c->ps->pose1, c->g_xyzl.p, (float4 *)nullptr, c->bounds);
 	int sort_bits = 0;
 	if ((e = plan_buckets(c, prm, &sort_bits))) return e;
 	LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
@@ -1117,9 +1122,9 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 			if ((e = ensure_candidates(c, (size_t)A.n, prm->max_inner, prm->max_outer))) return e;
 			LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
 			LAUNCH(c, k_transform_soa<true>, grid_for(c, A.n, 256), 256, A.xyzl, A.nrm, A.n, c->d_poses1.p + 16 * (size_t)i,
-					c->g_xyzl.p, c->g_nrm.p, c->bounds);
+					c->g_xyzl.p, (float4 *)nullptr, c->bounds);
 			if ((e = plan_buckets(c, prm, &sort_bits))) return e;
-			build_grid_fused(c, A.n, prm, sort_bits);
+			build_grid_fused(c, A.n, prm, sort_bits, A.nrm, c->d_poses1.p + 16 * (size_t)i);
 			if (prm->mode == M3DREG_MODE_NDT) ndt_bucket_stats(c, A.xyzl, A.n);
 			cur_i = i;
 		}

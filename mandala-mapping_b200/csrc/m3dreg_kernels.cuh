@@ -156,15 +156,18 @@ __global__ void k_transform_soa(const float4 *__restrict__ in_xyzl, const float4
 	float r20 = __ldg(m + 8), r21 = __ldg(m + 9), r22 = __ldg(m + 10), t2 = __ldg(m + 11);
 	float mnx = INFINITY, mny = INFINITY, mnz = INFINITY, mxx = -INFINITY, mxy = -INFINITY, mxz = -INFINITY;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		float4 p = __ldg(in_xyzl + i), q = __ldg(in_nrm + i);
+		float4 p = __ldg(in_xyzl + i);
 		float x = __fadd_rn(t0, __fmaf_rn(r02, p.z, __fmaf_rn(r00, p.x, __fmul_rn(r01, p.y))));
 		float y = __fadd_rn(t1, __fmaf_rn(r12, p.z, __fmaf_rn(r10, p.x, __fmul_rn(r11, p.y))));
 		float z = __fadd_rn(t2, __fmaf_rn(r22, p.z, __fmaf_rn(r20, p.x, __fmul_rn(r21, p.y))));
-		float nx = __fmaf_rn(r02, q.z, __fmaf_rn(r00, q.x, __fmul_rn(r01, q.y)));
-		float ny = __fmaf_rn(r12, q.z, __fmaf_rn(r10, q.x, __fmul_rn(r11, q.y)));
-		float nz = __fmaf_rn(r22, q.z, __fmaf_rn(r20, q.x, __fmul_rn(r21, q.y)));
 		out_xyzl[i] = make_float4(x, y, z, p.w);
-		out_nrm[i] = make_float4(nx, ny, nz, 0.0f);
+		if (out_nrm) {      /* the fused loop rotates only the candidates' normals (k_build_candidates), not all of them */
+			float4 q = __ldg(in_nrm + i);
+			float nx = __fmaf_rn(r02, q.z, __fmaf_rn(r00, q.x, __fmul_rn(r01, q.y)));
+			float ny = __fmaf_rn(r12, q.z, __fmaf_rn(r10, q.x, __fmul_rn(r11, q.y)));
+			float nz = __fmaf_rn(r22, q.z, __fmaf_rn(r20, q.x, __fmul_rn(r21, q.y)));
+			out_nrm[i] = make_float4(nx, ny, nz, 0.0f);
+		}
 		if (WITH_BOUNDS) {
 			mnx = fminf(mnx, x); mny = fminf(mny, y); mnz = fminf(mnz, z);
 			mxx = fmaxf(mxx, x); mxy = fmaxf(mxy, y); mxz = fmaxf(mxz, z);
@@ -615,12 +618,18 @@ __device__ __forceinline__ uint32_t cand_bin(const float4 &p, const CellFrame &f
 	return ((uint32_t)(__float_as_int(p.w) & 3) << 6) | mx | (my << 1) | (mz << 2);
 }
 
+struct NormalRotation { float r[9]; int on; };   /* rotation applied to the candidates' normals (same rounding as the transform kernels) */
+
 __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict__ vals, const float4 *__restrict__ src_xyzl,
-		const float4 *__restrict__ src_nrm, int begin, int npts, int cap, const CellFrame &f, const CandSet &set,
+		const float4 *__restrict__ src_nrm, const NormalRotation &rot, int begin, int npts, int cap, const CellFrame &f, const CandSet &set,
 		uint32_t *hist, int lane)
 {
 	const unsigned full = 0xffffffffu;
-	if (cap <= 0 || npts <= 0) return;
+	if (npts <= 0) return;
+	if (cap <= 0) {    /* nothing of this bucket may be looked at in this role */
+		if (lane == 0) set.mhi[begin] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
+		return;
+	}
 	const int iter = candidate_stride(npts, cap);
 	const int ncand = (npts + iter - 1) / iter;
 	const uint32_t lt = (1u << lane) - 1u;
@@ -691,7 +700,13 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 			if (valid) {
 				int pos = begin + (int)(old + __popc(peers & lt));
 				set.xyzl[pos] = p[k];
-				set.nrm[pos] = make_float4(nr[k].x, nr[k].y, nr[k].z, __int_as_float(ls[k]));
+				float4 nn = nr[k];
+				if (rot.on) {
+					nn.x = __fmaf_rn(rot.r[2], nr[k].z, __fmaf_rn(rot.r[0], nr[k].x, __fmul_rn(rot.r[1], nr[k].y)));
+					nn.y = __fmaf_rn(rot.r[5], nr[k].z, __fmaf_rn(rot.r[3], nr[k].x, __fmul_rn(rot.r[4], nr[k].y)));
+					nn.z = __fmaf_rn(rot.r[8], nr[k].z, __fmaf_rn(rot.r[6], nr[k].x, __fmul_rn(rot.r[7], nr[k].y)));
+				}
+				set.nrm[pos] = make_float4(nn.x, nn.y, nn.z, __int_as_float(ls[k]));
 			}
 			__syncwarp();
 		}
@@ -713,7 +728,7 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 			}
 		}
 		set.mlo[begin + j] = make_float4(lox, loy, loz, __uint_as_float(mask));
-		set.mhi[begin + j] = make_float4(hix, hiy, hiz, 0.0f);
+		set.mhi[begin + j] = make_float4(hix, hiy, hiz, __int_as_float(j == 0 ? ncand : 0));   /* the first header carries the candidate count */
 	}
 }
 
@@ -721,10 +736,14 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 __global__ void __launch_bounds__(kBuildWarps * 32, 4) k_build_candidates(const uint32_t *__restrict__ vals,
 		const m3dreg_grid_params *__restrict__ gp, const m3dreg_bucket *__restrict__ buckets,
 		const uint32_t *__restrict__ cell_list, const unsigned int *__restrict__ cell_count,
-		const float4 *__restrict__ src_xyzl, const float4 *__restrict__ src_nrm, int max_inner, int max_outer,
+		const float4 *__restrict__ src_xyzl, const float4 *__restrict__ src_nrm, const float *__restrict__ nrm_m, int max_inner, int max_outer,
 		CandSet ci, CandSet co, int two_sets)
 {
 	__shared__ uint32_t s_hist[kBuildWarps][kBuildBins];
+	NormalRotation rot;
+	rot.on = nrm_m != nullptr;
+#pragma unroll
+	for (int k = 0; k < 9; k++) rot.r[k] = rot.on ? __ldg(nrm_m + (k / 3) * 4 + (k % 3)) : 0.0f;    /* row-major 4x4 */
 	if (gp->number_of_buckets <= 0) return;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
@@ -740,8 +759,8 @@ __global__ void __launch_bounds__(kBuildWarps * 32, 4) k_build_candidates(const 
 		CellFrame f;
 		f.ox = mnx + (float)ix * rx; f.oy = mny + (float)iy * ry; f.oz = mnz + (float)iz * rz;
 		f.sx = 4.0f / rx; f.sy = 4.0f / ry; f.sz = 4.0f / rz;
-		build_cell_candidates(vals, src_xyzl, src_nrm, c_begin, c_n, max_inner, f, ci, s_hist[w], lane);
-		if (two_sets) build_cell_candidates(vals, src_xyzl, src_nrm, c_begin, c_n, max_outer, f, co, s_hist[w], lane);
+		build_cell_candidates(vals, src_xyzl, src_nrm, rot, c_begin, c_n, max_inner, f, ci, s_hist[w], lane);
+		if (two_sets) build_cell_candidates(vals, src_xyzl, src_nrm, rot, c_begin, c_n, max_outer, f, co, s_hist[w], lane);
 	}
 }
 
@@ -870,14 +889,16 @@ __device__ __forceinline__ void nn_eval_blocks(NNQuery &q, bool need, const Cand
  * box bounds rounded outwards and lim_q <= rho^2, c lies inside the inflated box and its block's box overlaps it.
  * A lane whose limit does not exceed rho^2 therefore has nothing left to find in this bucket; the others go on to
  * the next round (rho doubles) until rho^2 covers every remaining limit. */
-__device__ __forceinline__ void nn_visit_set(NNQuery &q, bool need, int begin, int npts, int cap, const CandSet &set,
+__device__ __forceinline__ void nn_visit_set(NNQuery &q, bool need, int begin, const CandSet &set,
 		float trial_unit2, int prune, float4 *stage, int lane, unsigned int &evals)
 {
 	const unsigned full = 0xffffffffu;
-	if (npts <= 0 || cap <= 0) return;
 	if (!__any_sync(full, need)) return;
-	const int iter = candidate_stride(npts, cap);
-	const int ncand = (npts + iter - 1) / iter;
+	/* block headers of the first 32 blocks (lanes beyond the bucket's block count read slack that is never used);
+	 * the candidate count rides in the first header */
+	float4 mlo = __ldg(set.mlo + begin + lane), mhi = __ldg(set.mhi + begin + lane);
+	const int ncand = __float_as_int(__shfl_sync(full, mhi.w, 0));
+	if (ncand <= 0) return;
 	const int nblocks = (ncand + kCandBlock - 1) / kCandBlock;
 	const bool flat = nblocks <= 4 || !prune;
 	const float trial2 = trial_unit2 / (float)ncand;
@@ -886,8 +907,7 @@ __device__ __forceinline__ void nn_visit_set(NNQuery &q, bool need, int begin, i
 #pragma unroll 1
 	for (int cb = 0; cb < nblocks; cb += 32) {
 		const int nblk = min(32, nblocks - cb);
-		float4 mlo = make_float4(0, 0, 0, 0), mhi = make_float4(0, 0, 0, 0);
-		if (!flat && lane < nblk) { mlo = __ldg(set.mlo + begin + cb + lane); mhi = __ldg(set.mhi + begin + cb + lane); }
+		if (cb > 0 && !flat && lane < nblk) { mlo = __ldg(set.mlo + begin + cb + lane); mhi = __ldg(set.mhi + begin + cb + lane); }
 		unsigned staged = 0;
 		bool U = need;
 		float rho2 = -1.0f;
@@ -940,13 +960,11 @@ __device__ __forceinline__ void nn_visit_set(NNQuery &q, bool need, int begin, i
  * candidate of that cell: skipping a cell whose bound exceeds the current best (or r^2) cannot change the result. */
 __device__ __forceinline__ void axis_gaps(float q, float mn, float res, int ic, float &g_lo, float &g_hi)
 {
-	const double eps = 9.5367431640625e-07; /* 2^-20 */
-	double dq = (double)q - (double)mn;
-	double up = (double)ic * (double)res * (1.0 + eps);          /* exclusive upper bound of cells <= ic-1 */
-	double lo = (double)(ic + 1) * (double)res * (1.0 - eps);    /* inclusive lower bound of cells >= ic+1 */
-	double a = dq - up, b = lo - dq;
-	g_lo = a > 0.0 ? __double2float_rd(a) : 0.0f;
-	g_hi = b > 0.0 ? __double2float_rd(b) : 0.0f;
+	const float up_f = 1.00000095367431640625f, dn_f = 0.99999904632568359375f;     /* 1 +- 2^-20 */
+	float up = __fmul_ru(__fmul_ru((float)ic, res), up_f);            /* exclusive upper bound of cells <= ic-1, rounded up   */
+	float lo = __fmul_rd(__fmul_rd((float)(ic + 1), res), dn_f);      /* inclusive lower bound of cells >= ic+1, rounded down */
+	g_lo = fmaxf(0.0f, __fsub_rd(__fsub_rd(q, mn), up));
+	g_hi = fmaxf(0.0f, __fsub_rd(lo, __fsub_ru(q, mn)));
 }
 
 struct NNLane {          /* per-lane search state besides the query itself */
@@ -979,17 +997,14 @@ __device__ __forceinline__ void nn_visit_cell(NNQuery &q, NNLane &s, const NNGri
 	bool need = part && (!G.prune || !(lbd > q.best || lbd > q.r2));
 	if (!__any_sync(0xffffffffu, need)) return;
 	int cell = (cx * G.nby + cy) * G.nbz + cz;
-	const int *bp = reinterpret_cast<const int *>(G.buckets + cell);
-	int npts = __ldg(bp + 2);
-	if (npts <= 0) return;
-	int begin = __ldg(bp);
+	int begin = __ldg(reinterpret_cast<const int *>(G.buckets + cell));
+	if (begin < 0) return;       /* empty bucket, or the quirk bucket the reference cannot see (number_of_points == 0) */
 	const bool inner = (o == 13);
 #pragma unroll 1
 	for (int pass = 0; pass < (G.two_sets ? 2 : 1); pass++) {
 		/* equal caps: one shared set for every role; different caps: INNER set for the home role, OUTER for the rest */
 		bool mine = G.two_sets ? (need && (pass == 0 ? inner : !inner)) : need;
-		nn_visit_set(q, mine, begin, npts, pass == 0 ? G.max_inner : G.max_outer, pass == 0 ? G.ci : G.co, G.trial_unit2, G.prune,
-				stage, lane, evals);
+		nn_visit_set(q, mine, begin, pass == 0 ? G.ci : G.co, G.trial_unit2, G.prune, stage, lane, evals);
 	}
 }
 
@@ -1023,7 +1038,7 @@ __global__ void __launch_bounds__(kNNThreads, 6) k_nn_search(const float4 *__res
 	G.max_inner = max_inner; G.max_outer = max_outer; G.two_sets = (max_inner != max_outer); G.prune = prune;
 	float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
 	float rx = gp->resolution_X, ry = gp->resolution_Y, rz = gp->resolution_Z;
-	G.trial_unit2 = 2.0f * fmaxf(rx, fmaxf(ry, rz)) * fmaxf(rx, fmaxf(ry, rz));
+	G.trial_unit2 = 1.0f * fmaxf(rx, fmaxf(ry, rz)) * fmaxf(rx, fmaxf(ry, rz));   /* first-round radius^2 = res^2 / candidates: about one candidate spacing */
 	NNQuery q;
 	q.x = q.y = q.z = q.nx = q.ny = q.nz = 0.0f;
 	q.r2 = __fmul_rn(search_radius, search_radius);
@@ -1073,15 +1088,25 @@ __global__ void __launch_bounds__(kNNThreads, 6) k_nn_search(const float4 *__res
 				bool near_face = s.home >= 0 && (!prune || !(__fmul_rn(gmin, gmin) > lim));
 				if (!__any_sync(full, near_face)) break;
 				if (near_face) {
+					/* superset of the buckets worth a visit (sum of squared gaps with a reassociation margin; the exact
+					 * bound is re-checked when the bucket is visited); out-of-grid neighbours get an infinite gap */
+					const float limm = prune ? __fmul_ru(lim, 1.00000095367431640625f) : 3.0e38f;     /* finite: out-of-grid stays excluded */
+					float sx[3], sy[3], sz[3];
+					sx[0] = s.ix > 0 ? __fmul_rd(s.gxl, s.gxl) : INFINITY; sx[1] = 0.0f; sx[2] = s.ix + 1 < G.nbx ? __fmul_rd(s.gxh, s.gxh) : INFINITY;
+					sy[0] = s.iy > 0 ? __fmul_rd(s.gyl, s.gyl) : INFINITY; sy[1] = 0.0f; sy[2] = s.iy + 1 < G.nby ? __fmul_rd(s.gyh, s.gyh) : INFINITY;
+					sz[0] = s.iz > 0 ? __fmul_rd(s.gzl, s.gzl) : INFINITY; sz[1] = 0.0f; sz[2] = s.iz + 1 < G.nbz ? __fmul_rd(s.gzh, s.gzh) : INFINITY;
+					if (!prune) {
 #pragma unroll
-					for (int o = 0; o < 27; o++) {
-						const int i = o / 9 - 1, j = (o / 3) % 3 - 1, k = o % 3 - 1;
-						float gx = i < 0 ? s.gxl : (i > 0 ? s.gxh : 0.0f), gy = j < 0 ? s.gyl : (j > 0 ? s.gyh : 0.0f), gz = k < 0 ? s.gzl : (k > 0 ? s.gzh : 0.0f);
-						float lbd = __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
-						bool ok = !prune || !(lbd > lim);
-						ok = ok && (unsigned)(s.ix + i) < (unsigned)G.nbx && (unsigned)(s.iy + j) < (unsigned)G.nby && (unsigned)(s.iz + k) < (unsigned)G.nbz;
-						todo |= ok ? (1u << o) : 0u;
+						for (int a = 0; a < 3; a += 2) { if (sx[a] != INFINITY) sx[a] = 0.0f; if (sy[a] != INFINITY) sy[a] = 0.0f; if (sz[a] != INFINITY) sz[a] = 0.0f; }
 					}
+#pragma unroll
+					for (int i = 0; i < 3; i++)
+#pragma unroll
+						for (int j = 0; j < 3; j++) {
+							float sxy = __fadd_rd(sx[i], sy[j]);
+#pragma unroll
+							for (int k = 0; k < 3; k++) todo |= (__fadd_rd(sxy, sz[k]) <= limm) ? (1u << (i * 9 + j * 3 + k)) : 0u;
+						}
 					todo &= ~s.done;
 				}
 			}
