@@ -98,6 +98,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(kernel, workload):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/roofline_traffic.json), else None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        e = json.load(open(p))[kernel]
+        return int(e["dram_bytes_per_launch"]) if e.get("workload") == workload else None
+    except Exception:
+        return None
+
+
 def alg_bytes(n1, n2, nb, nc):
     """Algorithmic bytes per ICP iteration: B_alg = 104*N1 + 36*N2 + 24*B + 40*Nc."""
     return 104 * n1 + 36 * n2 + 24 * nb + 40 * nc
@@ -235,6 +245,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     peak_gbs, peak_src = load_peaks()
@@ -361,7 +373,7 @@ def main():
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "kernel": "k_nn_search", "achieved": nn_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": nn_gbs / peak_gbs,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": nn_bytes, "launch_ms": nn_ms,
+                "traffic": ncu_traffic("k_nn_search", args.workload) if args.mode == "icp" else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": nn_bytes, "launch_ms": nn_ms,
                 "dominant_stage": stage_names[dom],
                 "nn_candidate_evaluations_per_query": evals_per_query,
                 "stage_ms": {stage_names[k]: float(stage_ms[k]) for k in range(4)},

@@ -105,5 +105,7 @@ class SweepDriver:
             import torch.distributed as dist
             dist.all_reduce(neq, group=self.group)
         self.last_pairs = len(pi)
+        self.last_my_pairs = len(mine)
         self.last_points = int((self.sizes[pi] + self.sizes[pj]).sum())
+        self.last_neq = neq          # all-reduced per-scan normal equations (n_scans x 28), kept for checks
         return self.backend.solve(neq, poses)
