@@ -88,7 +88,7 @@ struct m3dreg_ctx {
 
 	/* arena */
 	DevBuf<float4> g_xyzl, g_nrm, ci_xyzl, ci_nrm, co_xyzl, co_nrm, q_xyzl, q_nrm, l_xyzl, l_nrm;
-	DevBuf<float4> ci_mlo, ci_mhi, co_mlo, co_mhi;   /* candidate block boxes + label masks */
+	DevBuf<unsigned short> ci_tab, co_tab;           /* per-bucket bin offset tables of the candidate sets (nn_core.cuh) */
 	DevBuf<uint32_t> keys[2], vals[2], hist, digit_tot;
 	DevBuf<m3dreg_bucket> buckets;
 	DevBuf<int> nn, nn_seq;
@@ -277,13 +277,11 @@ int ensure_candidates(m3dreg_ctx *c, size_t n1, int max_inner, int max_outer)
 	int e;
 	if ((e = c->ci_xyzl.ensure(n1))) return e;
 	if ((e = c->ci_nrm.ensure(n1))) return e;
-	if ((e = c->ci_mlo.ensure(n1))) return e;
-	if ((e = c->ci_mhi.ensure(n1))) return e;
+	if ((e = c->ci_tab.ensure(2 * n1 + 8))) return e;
 	if (max_inner != max_outer) {
 		if ((e = c->co_xyzl.ensure(n1))) return e;
 		if ((e = c->co_nrm.ensure(n1))) return e;
-		if ((e = c->co_mlo.ensure(n1))) return e;
-		if ((e = c->co_mhi.ensure(n1))) return e;
+		if ((e = c->co_tab.ensure(2 * n1 + 8))) return e;
 	}
 	return 0;
 }
@@ -291,8 +289,8 @@ int ensure_candidates(m3dreg_ctx *c, size_t n1, int max_inner, int max_outer)
 CandSet cand_set(m3dreg_ctx *c, bool outer)
 {
 	CandSet s;
-	if (outer) { s.xyzl = c->co_xyzl.p; s.nrm = c->co_nrm.p; s.mlo = c->co_mlo.p; s.mhi = c->co_mhi.p; }
-	else { s.xyzl = c->ci_xyzl.p; s.nrm = c->ci_nrm.p; s.mlo = c->ci_mlo.p; s.mhi = c->ci_mhi.p; }
+	if (outer) { s.xyzl = c->co_xyzl.p; s.nrm = c->co_nrm.p; s.tab = c->co_tab.p; }
+	else { s.xyzl = c->ci_xyzl.p; s.nrm = c->ci_nrm.p; s.tab = c->ci_tab.p; }
 	return s;
 }
 
@@ -302,7 +300,7 @@ void build_candidates(m3dreg_ctx *c, const uint32_t *vals, const m3dreg_bucket *
 		const float4 *src_xyzl, const float4 *src_nrm, const float *nrm_m, int max_inner, int max_outer)
 {
 	bool two = max_inner != max_outer;
-	LAUNCH(c, k_build_candidates, c->sm_count * 4, kBuildWarps * 32, vals, c->gp, buckets, cell_list, c->cell_count, src_xyzl, src_nrm, nrm_m,
+	LAUNCH(c, k_build_candidates, c->sm_count * 8, kBuildWarps * 32, vals, c->gp, buckets, cell_list, c->cell_count, src_xyzl, src_nrm, nrm_m,
 			max_inner, max_outer, cand_set(c, false), cand_set(c, two), two ? 1 : 0);
 }
 
@@ -430,7 +428,7 @@ void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int
 	launch_nn(c, c->act_perm, n2, c->vals[c->last_sorted].p, n1, c->buckets.p, prm->search_radius, prm->max_inner, prm->max_outer, 1,
 			c->nn.p, c->nn_seq.p, c->label_counts);
 	ObsFromNN src;
-	src.nn = c->nn_seq.p; src.q_xyzl = c->q_xyzl.p; src.g_xyzl = c->g_xyzl.p; src.l_xyzl = lx; src.label_counts = c->label_counts;
+	src.nn = c->nn_seq.p; src.q_xyzl = c->q_xyzl.p; src.l_xyzl = lx; src.m = c->ps->pose1; src.label_counts = c->label_counts;
 	for (int k = 0; k < 4; k++) src.weight[k] = prm->weight[k];
 	FinalizeArgs fin;
 	fin.ps = c->ps; fin.neq_out = nullptr; fin.accumulate = 0; fin.solve = 1; fin.dof = prm->dof;
@@ -541,7 +539,7 @@ void m3dreg_destroy(m3dreg_ctx *c)
 	if (c->own_stream) cudaStreamSynchronize(c->own_stream);
 	for (auto &s : c->scans) s.release();
 	c->g_xyzl.release(); c->g_nrm.release(); c->ci_xyzl.release(); c->ci_nrm.release(); c->co_xyzl.release(); c->co_nrm.release(); c->digit_tot.release();
-	c->ci_mlo.release(); c->ci_mhi.release(); c->co_mlo.release(); c->co_mhi.release();
+	c->ci_tab.release(); c->co_tab.release();
 	c->q_xyzl.release(); c->q_nrm.release(); c->l_xyzl.release(); c->l_nrm.release();
 	for (int k = 0; k < 2; k++) { c->keys[k].release(); c->vals[k].release(); }
 	c->hist.release(); c->buckets.release(); c->nn.release(); c->nn_seq.release(); c->aos_a.release(); c->aos_b.release();
@@ -1143,7 +1141,7 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 		launch_nn(c, B.perm, B.n, c->vals[c->last_sorted].p, A.n, c->buckets.p, prm->search_radius, prm->max_inner, prm->max_outer, 1,
 				c->nn.p, c->nn_seq.p, c->label_counts);
 		ObsFromNN src;
-		src.nn = c->nn_seq.p; src.q_xyzl = c->q_xyzl.p; src.g_xyzl = c->g_xyzl.p; src.l_xyzl = A.xyzl; src.label_counts = c->label_counts;
+		src.nn = c->nn_seq.p; src.q_xyzl = c->q_xyzl.p; src.l_xyzl = A.xyzl; src.m = c->d_poses1.p + 16 * (size_t)i; src.label_counts = c->label_counts;
 		for (int k = 0; k < 4; k++) src.weight[k] = prm->weight[k];
 		FinalizeArgs fin;
 		fin.ps = nullptr; fin.neq_out = d_neq + (size_t)i * kNeqCount; fin.accumulate = 1; fin.solve = 0; fin.dof = prm->dof;

@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <math.h>
 #include "../../include/m3dreg.h"
+#include "nn_core.cuh"
 
 namespace m3d {
 
@@ -199,11 +200,6 @@ __device__ __forceinline__ bool grid_params_from_bounds_dev(const uint32_t *__re
 	bool ok = !(nbx <= 0 || nby <= 0 || nbz <= 0 || nb > 2147483647LL || nb > bucket_cap);
 	g.number_of_buckets = ok ? nb : 0;
 	return ok;
-}
-
-__device__ __forceinline__ int cell_of(float v, float mn, float res)
-{
-	return (int)__fdiv_rn(__fsub_rn(v, mn), res);     /* sub.f32, div.rn.f32, cvt.rzi.s32.f32 */
 }
 
 /* Warp-level histogram update for one item per lane: lanes holding the same bin as their left neighbour form a run,
@@ -579,87 +575,95 @@ __global__ void k_list_cells(const uint32_t *__restrict__ keys, int n, const m3d
  * The reference never looks at every point of a bucket: it walks sorted positions begin, begin+s, begin+2s, ... with
  * s = n / cap (lesson_16.cu:628-640), i.e. at most 2*cap-1 CANDIDATES per bucket, and only those can ever be a
  * result.  k_build_candidates gathers exactly those, per bucket, into the bucket's own [begin, begin+ncand) range of
- * the compact arrays (a bucket's candidates always fit inside its own range, so no prefix sum is needed) and —
- * because the search result is the lexicographic minimum of (dist, sorted position), which is independent of the
- * order in which candidates are looked at — stores them in a SPATIAL order: counting sort by
- * (label & 3, Morton code of the 4x4x4 sub-cell inside the bucket).  Every 8 consecutive candidates form a block
- * with an axis-aligned bounding box and a label mask; the search only touches blocks whose box can contain
- * something closer than the current best.  Each record keeps its sorted position l for the tie-break and result.
- * Two sets exist when the INNER and OUTER caps differ (different strides). */
-struct CandSet {
-	float4 *xyzl;     /* {x, y, z, label bits}                               */
-	float4 *nrm;      /* {nx, ny, nz, bits of l = position in the sorted table (hashElement index)} */
-	float4 *mlo;      /* per block: {min x, min y, min z, label mask bits}   */
-	float4 *mhi;      /* per block: {max x, max y, max z, 0}                 */
-};
-
-constexpr int kCandBlock = 8;
+ * the compact arrays (a bucket's candidates always fit inside its own range, so no prefix sum is needed), grouped by
+ * (label & 3, sub-cell) bin with a u16 table of bin offsets — layout and exactness argument in nn_core.cuh.  Inside a
+ * bin candidates keep ascending sorted position (stable counting sort).  Each record carries its sorted position l
+ * for the tie-break and the result.  Two sets exist when the INNER and OUTER caps differ (different strides). */
 constexpr int kBuildWarps = 4;
-constexpr int kBuildBins = 256;
-constexpr int kBuildPerLane = 4;   /* candidates per lane in flight (loads issued together) */
-
-__device__ __forceinline__ int candidate_stride(int npts, int cap)
-{
-	int iter = 1;
-	if (cap < npts) { iter = npts / cap; if (iter <= 0) iter = 1; }
-	return iter;
-}
-
-__device__ __forceinline__ uint32_t label_bit(int label) { return 1u << (label & 31); }
-
-struct CellFrame { float ox, oy, oz, sx, sy, sz; };   /* bucket origin and 4/resolution (layout only, not parity relevant) */
-
-__device__ __forceinline__ uint32_t cand_bin(const float4 &p, const CellFrame &f)
-{
-	int ux = min(3, max(0, (int)((p.x - f.ox) * f.sx)));
-	int uy = min(3, max(0, (int)((p.y - f.oy) * f.sy)));
-	int uz = min(3, max(0, (int)((p.z - f.oz) * f.sz)));
-	uint32_t mx = (ux & 1) | ((ux & 2) << 2), my = (uy & 1) | ((uy & 2) << 2), mz = (uz & 1) | ((uz & 2) << 2);
-	return ((uint32_t)(__float_as_int(p.w) & 3) << 6) | mx | (my << 1) | (mz << 2);
-}
+constexpr int kBuildPerLane = 8;          /* candidates per lane held in registers (256 per warp pass) */
+constexpr int kBuildTabMax = 4 * 64 + 1;   /* bins + 1 at the finest level */
 
 struct NormalRotation { float r[9]; int on; };   /* rotation applied to the candidates' normals (same rounding as the transform kernels) */
 
+struct CellGeom { float mnx, mny, mnz, rx, ry, rz; int cx, cy, cz; };
+
 __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict__ vals, const float4 *__restrict__ src_xyzl,
-		const float4 *__restrict__ src_nrm, const NormalRotation &rot, int begin, int npts, int cap, const CellFrame &f, const CandSet &set,
-		uint32_t *hist, int lane)
+		const float4 *__restrict__ src_nrm, const NormalRotation &rot, int begin, int npts, int cap, int tables, const CellGeom &g,
+		const CandSet &set, uint32_t *hist, int lane)
 {
 	const unsigned full = 0xffffffffu;
-	if (npts <= 0) return;
-	if (cap <= 0) {    /* nothing of this bucket may be looked at in this role */
-		if (lane == 0) set.mhi[begin] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
-		return;
-	}
+	if (npts <= 0 || cap <= 0 || begin < 0) return;
 	const int iter = candidate_stride(npts, cap);
 	const int ncand = (npts + iter - 1) / iter;
+	const int level = tables ? nn_level(npts) : -1;
 	const uint32_t lt = (1u << lane) - 1u;
-	/* pass 1: bin histogram */
+	const int nbins = level >= 0 ? (4 << (3 * level)) : 0;
+	const float wx = nn_subcell_width(g.rx, level < 0 ? 0 : level), wy = nn_subcell_width(g.ry, level < 0 ? 0 : level),
+			wz = nn_subcell_width(g.rz, level < 0 ? 0 : level);
+	if (level >= 0) {
+		for (int k = lane; k <= nbins; k += 32) hist[k] = 0;
+		__syncwarp();
+	}
+	const bool single = ncand <= 32 * kBuildPerLane;
+	float4 p[kBuildPerLane], nr[kBuildPerLane];
+	auto load = [&](int c0) {
+		uint32_t v[kBuildPerLane];
 #pragma unroll
-	for (int k = 0; k < kBuildBins / 32; k++) hist[lane + 32 * k] = 0;
-	__syncwarp();
-	for (int c0 = 0; c0 < ncand; c0 += 32 * kBuildPerLane) {
-		float4 p[kBuildPerLane];
-#pragma unroll
-		for (int k = 0; k < kBuildPerLane; k++) {
-			int cc = c0 + k * 32 + lane;
-			if (cc < ncand) p[k] = __ldg(src_xyzl + __ldg(vals + begin + cc * iter));
+		for (int j = 0; j < kBuildPerLane; j++) {
+			int k = c0 + j * 32 + lane;
+			v[j] = k < ncand ? __ldg(vals + begin + k * iter) : 0u;
 		}
 #pragma unroll
-		for (int k = 0; k < kBuildPerLane; k++) {
-			int cc = c0 + k * 32 + lane;
-			if (c0 + k * 32 >= ncand) break;
-			bool valid = cc < ncand;
-			uint32_t bin = valid ? cand_bin(p[k], f) : (0x100u + lane);
+		for (int j = 0; j < kBuildPerLane; j++) {
+			int k = c0 + j * 32 + lane;
+			if (k < ncand) { p[j] = __ldg(src_xyzl + v[j]); nr[j] = __ldg(src_nrm + v[j]); }
+		}
+	};
+	auto bin_of = [&](const float4 &c) {
+		int ux = nn_col(c.x, g.mnx, wx, g.cx, level), uy = nn_col(c.y, g.mny, wy, g.cy, level), uz = nn_col(c.z, g.mnz, wz, g.cz, level);
+		return (uint32_t)nn_bin(__float_as_int(c.w), ux, uy, uz, level);
+	};
+	auto store = [&](int pos, int k, const float4 &c, const float4 &n) {
+		float4 nn = n;
+		if (rot.on) {
+			nn.x = __fmaf_rn(rot.r[2], n.z, __fmaf_rn(rot.r[0], n.x, __fmul_rn(rot.r[1], n.y)));
+			nn.y = __fmaf_rn(rot.r[5], n.z, __fmaf_rn(rot.r[3], n.x, __fmul_rn(rot.r[4], n.y)));
+			nn.z = __fmaf_rn(rot.r[8], n.z, __fmaf_rn(rot.r[6], n.x, __fmul_rn(rot.r[7], n.y)));
+		}
+		set.xyzl[pos] = make_float4(c.x, c.y, c.z, __int_as_float(begin + k * iter));
+		set.nrm[pos] = make_float4(nn.x, nn.y, nn.z, c.w);
+	};
+	if (single) load(0);
+	if (level < 0) {     /* no table: candidates in walk order */
+		for (int c0 = 0; c0 < ncand; c0 += 32 * kBuildPerLane) {
+			if (!single) load(c0);
+#pragma unroll
+			for (int j = 0; j < kBuildPerLane; j++) {
+				int k = c0 + j * 32 + lane;
+				if (k < ncand) store(begin + k, k, p[j], nr[j]);
+			}
+		}
+		return;
+	}
+	/* pass 1: bin histogram */
+	for (int c0 = 0; c0 < ncand; c0 += 32 * kBuildPerLane) {
+		if (!single) load(c0);
+#pragma unroll
+		for (int j = 0; j < kBuildPerLane; j++) {
+			if (c0 + j * 32 >= ncand) break;
+			int k = c0 + j * 32 + lane;
+			bool valid = k < ncand;
+			uint32_t bin = valid ? bin_of(p[j]) : (0x1000u + lane);
 			uint32_t peers = __match_any_sync(full, bin);
 			if (valid && lane == __ffs(peers) - 1) hist[bin] += __popc(peers);
 			__syncwarp();
 		}
 	}
-	/* exclusive scan of the 256 bins: 8 consecutive bins per lane */
+	/* exclusive scan of the nbins + 1 table entries (9 consecutive entries per lane cover 288 >= 257), table out */
 	{
-		uint32_t v[8], sum = 0;
+		uint32_t v[9], sum = 0;
 #pragma unroll
-		for (int k = 0; k < 8; k++) { v[k] = hist[lane * 8 + k]; sum += v[k]; }
+		for (int k = 0; k < 9; k++) { int e = lane * 9 + k; v[k] = e < nbins ? hist[e] : 0u; sum += v[k]; }
 		uint32_t incl = sum;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
@@ -668,78 +672,44 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 		}
 		uint32_t run = incl - sum;
 		__syncwarp();
+		unsigned short *tab = set.tab + 2 * (size_t)begin;
 #pragma unroll
-		for (int k = 0; k < 8; k++) { hist[lane * 8 + k] = run; run += v[k]; }
+		for (int k = 0; k < 9; k++) {
+			int e = lane * 9 + k;
+			if (e <= nbins) { hist[e] = run; tab[e] = (unsigned short)run; }
+			run += v[k];
+		}
 		__syncwarp();
 	}
 	/* pass 2: stable placement (ascending sorted position inside a bin) */
 	for (int c0 = 0; c0 < ncand; c0 += 32 * kBuildPerLane) {
-		float4 p[kBuildPerLane], nr[kBuildPerLane];
-		int ls[kBuildPerLane];
+		if (!single) load(c0);
 #pragma unroll
-		for (int k = 0; k < kBuildPerLane; k++) {
-			int cc = c0 + k * 32 + lane;
-			if (cc < ncand) {
-				ls[k] = begin + cc * iter;
-				uint32_t v = __ldg(vals + ls[k]);
-				p[k] = __ldg(src_xyzl + v);
-				nr[k] = __ldg(src_nrm + v);
-			}
-		}
-#pragma unroll
-		for (int k = 0; k < kBuildPerLane; k++) {
-			int cc = c0 + k * 32 + lane;
-			if (c0 + k * 32 >= ncand) break;
-			bool valid = cc < ncand;
-			uint32_t bin = valid ? cand_bin(p[k], f) : (0x100u + lane);
+		for (int j = 0; j < kBuildPerLane; j++) {
+			if (c0 + j * 32 >= ncand) break;
+			int k = c0 + j * 32 + lane;
+			bool valid = k < ncand;
+			uint32_t bin = valid ? bin_of(p[j]) : (0x1000u + lane);
 			uint32_t peers = __match_any_sync(full, bin);
 			int leader = __ffs(peers) - 1;
 			uint32_t old = 0;
 			if (valid && lane == leader) { old = hist[bin]; hist[bin] = old + __popc(peers); }
 			old = __shfl_sync(full, old, leader);
-			if (valid) {
-				int pos = begin + (int)(old + __popc(peers & lt));
-				set.xyzl[pos] = p[k];
-				float4 nn = nr[k];
-				if (rot.on) {
-					nn.x = __fmaf_rn(rot.r[2], nr[k].z, __fmaf_rn(rot.r[0], nr[k].x, __fmul_rn(rot.r[1], nr[k].y)));
-					nn.y = __fmaf_rn(rot.r[5], nr[k].z, __fmaf_rn(rot.r[3], nr[k].x, __fmul_rn(rot.r[4], nr[k].y)));
-					nn.z = __fmaf_rn(rot.r[8], nr[k].z, __fmaf_rn(rot.r[6], nr[k].x, __fmul_rn(rot.r[7], nr[k].y)));
-				}
-				set.nrm[pos] = make_float4(nn.x, nn.y, nn.z, __int_as_float(ls[k]));
-			}
+			if (valid) store(begin + (int)(old + __popc(peers & lt)), k, p[j], nr[j]);
 			__syncwarp();
 		}
 	}
 	__syncwarp();
-	/* block boxes + label masks (re-read through L2: the records were written by other lanes of this warp) */
-	const int nblocks = (ncand + kCandBlock - 1) / kCandBlock;
-	for (int j = lane; j < nblocks; j += 32) {
-		float lox = INFINITY, loy = INFINITY, loz = INFINITY, hix = -INFINITY, hiy = -INFINITY, hiz = -INFINITY;
-		uint32_t mask = 0;
-#pragma unroll
-		for (int k = 0; k < kCandBlock; k++) {
-			int idx = j * kCandBlock + k;
-			if (idx < ncand) {
-				float4 c = __ldcg(set.xyzl + begin + idx);
-				lox = fminf(lox, c.x); loy = fminf(loy, c.y); loz = fminf(loz, c.z);
-				hix = fmaxf(hix, c.x); hiy = fmaxf(hiy, c.y); hiz = fmaxf(hiz, c.z);
-				mask |= label_bit(__float_as_int(c.w));
-			}
-		}
-		set.mlo[begin + j] = make_float4(lox, loy, loz, __uint_as_float(mask));
-		set.mhi[begin + j] = make_float4(hix, hiy, hiz, __int_as_float(j == 0 ? ncand : 0));   /* the first header carries the candidate count */
-	}
 }
 
 /* One warp per searchable bucket of the compact list k_finalize_grid / k_list_cells left behind. */
-__global__ void __launch_bounds__(kBuildWarps * 32, 4) k_build_candidates(const uint32_t *__restrict__ vals,
+__global__ void __launch_bounds__(kBuildWarps * 32) k_build_candidates(const uint32_t *__restrict__ vals,
 		const m3dreg_grid_params *__restrict__ gp, const m3dreg_bucket *__restrict__ buckets,
 		const uint32_t *__restrict__ cell_list, const unsigned int *__restrict__ cell_count,
 		const float4 *__restrict__ src_xyzl, const float4 *__restrict__ src_nrm, const float *__restrict__ nrm_m, int max_inner, int max_outer,
 		CandSet ci, CandSet co, int two_sets)
 {
-	__shared__ uint32_t s_hist[kBuildWarps][kBuildBins];
+	__shared__ uint32_t s_hist[kBuildWarps][kBuildTabMax + 7];
 	NormalRotation rot;
 	rot.on = nrm_m != nullptr;
 #pragma unroll
@@ -747,20 +717,19 @@ __global__ void __launch_bounds__(kBuildWarps * 32, 4) k_build_candidates(const 
 	if (gp->number_of_buckets <= 0) return;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
-	const float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
-	const float rx = gp->resolution_X, ry = gp->resolution_Y, rz = gp->resolution_Z;
+	CellGeom g;
+	g.mnx = gp->bounding_box_min_X; g.mny = gp->bounding_box_min_Y; g.mnz = gp->bounding_box_min_Z;
+	g.rx = gp->resolution_X; g.ry = gp->resolution_Y; g.rz = gp->resolution_Z;
+	const int tables = nn_tables_usable(max_inner, max_outer) ? 1 : 0;
 	const unsigned int ncells = *cell_count;
 	const unsigned int nwarps = gridDim.x * kBuildWarps;
 	for (unsigned int t = blockIdx.x * kBuildWarps + w; t < ncells; t += nwarps) {
 		int c = (int)__ldg(cell_list + t);
 		const int *bp = reinterpret_cast<const int *>(buckets + c);
 		int c_begin = __ldg(bp), c_n = __ldg(bp + 2);
-		int ix = c / (nby * nbz), iy = (c / nbz) % nby, iz = c % nbz;
-		CellFrame f;
-		f.ox = mnx + (float)ix * rx; f.oy = mny + (float)iy * ry; f.oz = mnz + (float)iz * rz;
-		f.sx = 4.0f / rx; f.sy = 4.0f / ry; f.sz = 4.0f / rz;
-		build_cell_candidates(vals, src_xyzl, src_nrm, rot, c_begin, c_n, max_inner, f, ci, s_hist[w], lane);
-		if (two_sets) build_cell_candidates(vals, src_xyzl, src_nrm, rot, c_begin, c_n, max_outer, f, co, s_hist[w], lane);
+		g.cx = c / (nby * nbz); g.cy = (c / nbz) % nby; g.cz = c % nbz;
+		build_cell_candidates(vals, src_xyzl, src_nrm, rot, c_begin, c_n, max_inner, tables, g, ci, s_hist[w], lane);
+		if (two_sets) build_cell_candidates(vals, src_xyzl, src_nrm, rot, c_begin, c_n, max_outer, tables, g, co, s_hist[w], lane);
 	}
 }
 
@@ -774,250 +743,15 @@ __global__ void k_split_table(const m3dreg_hash_element *__restrict__ table, int
 	}
 }
 
-/* ---- semantic nearest neighbour (kernel_semanticNearestNeighborSearch, lesson_16.cu:531-703) ------------- */
-
-/* The reference's angle gate (lesson_16.cu:666-676): acos(dot)*180.0f/M_PI, |.| < 90.0f, with acos the CUDA
- * float acosf.  As a function of the f32 dot product its accepted set is exactly the interval
- *      0x328885AC (1.589327e-08) <= dot <= 1.0f
- * (NaN, |dot| > 1, zero and negative dots are rejected; tiny positive dots still round to >= 90.0f degrees).
- * tests/test_gpu_gate.py proves this equal to the upstream expression for ALL 2^32 float bit patterns on the
- * device, so the two compares below are bit-exact and ~60 instructions (acosf + an f64 divide) cheaper. */
-constexpr uint32_t kAngleGateMinBits = 0x328885ACu;
-__device__ __forceinline__ bool angle_gate(float dot)
-{
-	return dot >= __uint_as_float(kAngleGateMinBits) && dot <= 1.0f;
-}
-
-struct NNQuery {
-	float x, y, z, nx, ny, nz, r2;
-	int label;
-	float best;
-	int best_l;
-};
-
-/* Visit order in the reference is ascending sorted position l (cells are visited in ascending linear index and
- * the table is sorted by it) and its update is a strict `<`, so the reference result is the lexicographic minimum
- * of (dist, l) over the admissible candidates.  Keeping that pair lets candidates be looked at in ANY order, lets
- * whole groups be skipped when provably useless, and makes evaluating extra candidates harmless — which is what
- * allows a whole warp to walk one candidate list together.
- *
- * Warp-cooperative search: every lane holds one query; the warp stages up to 4 candidate blocks (32 records) in its
- * 512-byte slice of shared memory with one coalesced LDG.128 per lane.
- *   HOT  loop (straight-line): broadcast LDS.128 + 3 FADD + FMUL + 2 FFMA, then a branch-free running minimum over
- *        the candidates whose label matches, plus a flag that records an exact tie at the minimum.
- *   COLD step (once per staged group): if the group minimum can beat min(best, r^2), fetch that candidate's sorted
- *        position and normal, apply the angle gate and the exact (dist, l) comparison.  Should the gate reject it, or
- *        a tie have been seen (staging order is spatial, not ascending l), the lane re-scans the group sequentially
- *        with the full predicate. */
-__device__ __forceinline__ float nn_dist(float qx, float qy, float qz, const float4 &c)
-{
-	float dx = __fsub_rn(qx, c.x), dy = __fsub_rn(qy, c.y), dz = __fsub_rn(qz, c.z);
-	return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-}
-
-__device__ __forceinline__ void nn_group_min(const NNQuery &q, const float4 *stage, int base, float &bmin, int &bidx, bool &tie)
-{
-#pragma unroll
-	for (int kk = 0; kk < kCandBlock; kk++) {
-		float4 c = stage[base + kk];
-		float d = nn_dist(q.x, q.y, q.z, c);
-		bool ok = __float_as_int(c.w) == q.label;
-		bool better = ok && (d < bmin);
-		bool eq = ok && (d == bmin);
-		tie = better ? false : (tie || eq);
-		bmin = better ? d : bmin;
-		bidx = better ? base + kk : bidx;
-	}
-}
-
-/* Stage the blocks b[0..nsel) (block indices inside the bucket) and evaluate them for every lane. */
-__device__ __forceinline__ void nn_eval_blocks(NNQuery &q, bool need, const CandSet &set, int begin, int ncand,
-		int b0, int b1, int b2, int b3, int nsel, float4 *stage, int lane, unsigned int &evals)
-{
-	const int g = lane >> 3;
-	const int blk = g == 0 ? b0 : (g == 1 ? b1 : (g == 2 ? b2 : b3));
-	const int idx = blk * kCandBlock + (lane & 7);
-	const bool valid = g < nsel && idx < ncand;
-	__syncwarp();
-	stage[lane] = valid ? __ldg(set.xyzl + begin + idx) : make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(0x7fffffff));
-	__syncwarp();
-	evals += (unsigned int)(nsel * kCandBlock);
-	float bmin = INFINITY;
-	int bidx = -1;
-	bool tie = false;
-#pragma unroll 1
-	for (int g8 = 0; g8 < nsel; g8++) nn_group_min(q, stage, g8 * kCandBlock, bmin, bidx, tie);
-	/* cold step */
-	if (need && bidx >= 0 && bmin <= fminf(q.best, q.r2)) {
-		bool rescan = tie;
-		if (!rescan) {
-			int gg = bidx >> 3;
-			int cand = begin + (gg == 0 ? b0 : (gg == 1 ? b1 : (gg == 2 ? b2 : b3))) * kCandBlock + (bidx & 7);
-			float4 cn = __ldg(set.nrm + cand);
-			int l = __float_as_int(cn.w);
-			if (bmin < q.best || (bmin == q.best && l < q.best_l)) {
-				float dot = __fmaf_rn(q.nz, cn.z, __fmaf_rn(q.nx, cn.x, __fmul_rn(q.ny, cn.y)));
-				if (angle_gate(dot)) { q.best = bmin; q.best_l = l; }
-				else rescan = true;     /* group minimum inadmissible (rare: opposite faces of thin structures) */
-			}
-		}
-		if (rescan) {
-			for (int kk = 0; kk < nsel * kCandBlock; kk++) {
-				float4 c = stage[kk];
-				float d = nn_dist(q.x, q.y, q.z, c);
-				if (__float_as_int(c.w) == q.label && d <= q.r2 && d <= q.best) {
-					int gg = kk >> 3;
-					int cand = begin + (gg == 0 ? b0 : (gg == 1 ? b1 : (gg == 2 ? b2 : b3))) * kCandBlock + (kk & 7);
-					float4 cn2 = __ldg(set.nrm + cand);
-					int l2 = __float_as_int(cn2.w);
-					if (d < q.best || l2 < q.best_l) {
-						float dot2 = __fmaf_rn(q.nz, cn2.z, __fmaf_rn(q.nx, cn2.x, __fmul_rn(q.ny, cn2.y)));
-						if (angle_gate(dot2)) { q.best = d; q.best_l = l2; }
-					}
-				}
-			}
-		}
-	}
-}
-
-/* Search one bucket's candidate set for the lanes flagged `need`.
- * Buckets with <= 4 blocks are staged whole.  Larger ones are searched in rounds of growing radius rho: the warp
- * forms the bounding box of the queries that are still UNSETTLED (min(best, r^2) > rho^2 of the previous round),
- * inflates it by rho, and lane j tests block j's box (and label mask) against it; blocks that pass and were not yet
- * staged are evaluated by all lanes.  Exactness: a candidate c with dist(q, c) <= lim_q has |q.x - c.x| <= sqrt(lim_q)
- * up to two float roundings (dist >= fl(dx*dx) by monotonicity of fma/mul), so with R = sqrt_ru(rho^2) * (1 + 2^-20),
- * box bounds rounded outwards and lim_q <= rho^2, c lies inside the inflated box and its block's box overlaps it.
- * A lane whose limit does not exceed rho^2 therefore has nothing left to find in this bucket; the others go on to
- * the next round (rho doubles) until rho^2 covers every remaining limit. */
-__device__ __forceinline__ void nn_visit_set(NNQuery &q, bool need, int begin, const CandSet &set,
-		float trial_unit2, int prune, float4 *stage, int lane, unsigned int &evals)
-{
-	const unsigned full = 0xffffffffu;
-	if (!__any_sync(full, need)) return;
-	/* block headers of the first 32 blocks (lanes beyond the bucket's block count read slack that is never used);
-	 * the candidate count rides in the first header */
-	float4 mlo = __ldg(set.mlo + begin + lane), mhi = __ldg(set.mhi + begin + lane);
-	const int ncand = __float_as_int(__shfl_sync(full, mhi.w, 0));
-	if (ncand <= 0) return;
-	const int nblocks = (ncand + kCandBlock - 1) / kCandBlock;
-	const bool flat = nblocks <= 4 || !prune;
-	const float trial2 = trial_unit2 / (float)ncand;
-	const uint32_t ox = f2o(q.x), oy = f2o(q.y), oz = f2o(q.z);
-	const uint32_t lbit = label_bit(q.label);
-#pragma unroll 1
-	for (int cb = 0; cb < nblocks; cb += 32) {
-		const int nblk = min(32, nblocks - cb);
-		if (cb > 0 && !flat && lane < nblk) { mlo = __ldg(set.mlo + begin + cb + lane); mhi = __ldg(set.mhi + begin + cb + lane); }
-		unsigned staged = 0;
-		bool U = need;
-		float rho2 = -1.0f;
-#pragma unroll 1
-		for (;;) {
-			unsigned m;
-			float maxlim = 0.0f;
-			if (flat) {
-				m = nblk == 32 ? 0xffffffffu : ((1u << nblk) - 1u);
-			} else {
-				/* non-negative floats order like their bit patterns */
-				unsigned lv = U ? __float_as_uint(fminf(q.best, q.r2)) + 1u : 0u;
-				unsigned mv = __reduce_max_sync(full, lv);
-				if (mv == 0u) break;
-				maxlim = __uint_as_float(mv - 1u);
-				rho2 = rho2 < 0.0f ? fminf(maxlim, trial2) : fminf(maxlim, rho2 * 4.0f);
-				float R = __fmul_ru(__fsqrt_ru(rho2), 1.00000095367431640625f);
-				float bxl = __fsub_rd(o2f(__reduce_min_sync(full, U ? ox : 0xFFFFFFFFu)), R);
-				float byl = __fsub_rd(o2f(__reduce_min_sync(full, U ? oy : 0xFFFFFFFFu)), R);
-				float bzl = __fsub_rd(o2f(__reduce_min_sync(full, U ? oz : 0xFFFFFFFFu)), R);
-				float bxh = __fadd_ru(o2f(__reduce_max_sync(full, U ? ox : 0u)), R);
-				float byh = __fadd_ru(o2f(__reduce_max_sync(full, U ? oy : 0u)), R);
-				float bzh = __fadd_ru(o2f(__reduce_max_sync(full, U ? oz : 0u)), R);
-				unsigned labels = __reduce_or_sync(full, U ? lbit : 0u);
-				bool hit = lane < nblk && (__float_as_uint(mlo.w) & labels) &&
-						!(mlo.x > bxh || mhi.x < bxl || mlo.y > byh || mhi.y < byl || mlo.z > bzh || mhi.z < bzl);
-				m = __ballot_sync(full, hit) & ~staged;
-				staged |= m;
-			}
-#pragma unroll 1
-			while (m) {
-				int b0 = __ffs(m) - 1; m &= m - 1;
-				int nsel = 1, b1 = 0, b2 = 0, b3 = 0;
-				if (m) { b1 = __ffs(m) - 1; m &= m - 1; nsel = 2; }
-				if (m) { b2 = __ffs(m) - 1; m &= m - 1; nsel = 3; }
-				if (m) { b3 = __ffs(m) - 1; m &= m - 1; nsel = 4; }
-				nn_eval_blocks(q, need, set, begin, ncand, cb + b0, cb + b1, cb + b2, cb + b3, nsel, stage, lane, evals);
-			}
-			if (flat || rho2 >= maxlim) break;
-			U = U && (fminf(q.best, q.r2) > rho2);
-		}
-	}
-}
-
-/* Conservative per-axis gap between the query and the slab of cells at offset -1 / +1 (rounded DOWN to float).
- * A point stored in cell c satisfies trunc(fl(fl(v-min)/res)) == c; with two roundings of relative error 2^-24,
- * (v-min) < ix*res*(1+2^-21) for cells <= ix-1 and (v-min) >= (ix+1)*res*(1-2^-21) for cells >= ix+1.
- * A factor 2^-20 is used.  fl(q - v) is the correctly rounded true difference, rounding is monotone and the gap
- * is a float, so |fl(q-v)| >= gap, hence fma(gz,gz,fma(gx,gx,gy*gy)) <= the reference's dist for every
- * candidate of that cell: skipping a cell whose bound exceeds the current best (or r^2) cannot change the result. */
-__device__ __forceinline__ void axis_gaps(float q, float mn, float res, int ic, float &g_lo, float &g_hi)
-{
-	const float up_f = 1.00000095367431640625f, dn_f = 0.99999904632568359375f;     /* 1 +- 2^-20 */
-	float up = __fmul_ru(__fmul_ru((float)ic, res), up_f);            /* exclusive upper bound of cells <= ic-1, rounded up   */
-	float lo = __fmul_rd(__fmul_rd((float)(ic + 1), res), dn_f);      /* inclusive lower bound of cells >= ic+1, rounded down */
-	g_lo = fmaxf(0.0f, __fsub_rd(__fsub_rd(q, mn), up));
-	g_hi = fmaxf(0.0f, __fsub_rd(lo, __fsub_ru(q, mn)));
-}
-
-struct NNLane {          /* per-lane search state besides the query itself */
-	int home, ix, iy, iz;
-	float gxl, gxh, gyl, gyh, gzl, gzh;
-	unsigned done;       /* bit o = (dx+1)*9 + (dy+1)*3 + (dz+1): neighbour bucket already handled (or pruned) */
-};
-
-struct NNGrid {
-	long long nb;
-	int nbx, nby, nbz;
-	const m3dreg_bucket *buckets;
-	CandSet ci, co;
-	int max_inner, max_outer, two_sets, prune;
-	float trial_unit2;
-};
-
-/* Bucket (cx,cy,cz) for EVERY lane that has it in its 27-neighbourhood and has not handled it yet — whatever the
- * lane's home bucket is, so a bucket is staged once per warp, not once per group of equal homes. */
-__device__ __forceinline__ void nn_visit_cell(NNQuery &q, NNLane &s, const NNGrid &G, int cx, int cy, int cz,
-		float4 *stage, int lane, unsigned int &evals)
-{
-	int dx = cx - s.ix, dy = cy - s.iy, dz = cz - s.iz;
-	bool in27 = s.home >= 0 && (unsigned)(dx + 1) <= 2u && (unsigned)(dy + 1) <= 2u && (unsigned)(dz + 1) <= 2u;
-	int o = (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1);
-	bool part = in27 && !((s.done >> (o & 31)) & 1u);
-	if (part) s.done |= 1u << o;
-	float gx = dx < 0 ? s.gxl : (dx > 0 ? s.gxh : 0.0f), gy = dy < 0 ? s.gyl : (dy > 0 ? s.gyh : 0.0f), gz = dz < 0 ? s.gzl : (dz > 0 ? s.gzh : 0.0f);
-	float lbd = __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
-	bool need = part && (!G.prune || !(lbd > q.best || lbd > q.r2));
-	if (!__any_sync(0xffffffffu, need)) return;
-	int cell = (cx * G.nby + cy) * G.nbz + cz;
-	int begin = __ldg(reinterpret_cast<const int *>(G.buckets + cell));
-	if (begin < 0) return;       /* empty bucket, or the quirk bucket the reference cannot see (number_of_points == 0) */
-	const bool inner = (o == 13);
-#pragma unroll 1
-	for (int pass = 0; pass < (G.two_sets ? 2 : 1); pass++) {
-		/* equal caps: one shared set for every role; different caps: INNER set for the home role, OUTER for the rest */
-		bool mine = G.two_sets ? (need && (pass == 0 ? inner : !inner)) : need;
-		nn_visit_set(q, mine, begin, pass == 0 ? G.ci : G.co, G.trial_unit2, G.prune, stage, lane, evals);
-	}
-}
-
-/* Semantic NN, one query per lane, candidate groups shared by the warp.
- * Queries are expected in a spatially coherent order (the scan store keeps a (label, Morton)-sorted copy of every
- * scan, and a rigid transform preserves coherence), so the 32 queries of a warp cover a small patch of one surface.
- * Phase A visits every distinct home bucket of the warp; phase B the neighbour buckets some lane cannot exclude by
- * the lower bound above with its best-so-far.
+/* ---- semantic nearest neighbour (kernel_semanticNearestNeighborSearch, lesson_16.cu:531-703) -------------
+ * One query per thread; the search itself is nn_query() in nn_core.cuh.  Queries are expected in a spatially coherent
+ * order (the scan store keeps a (label, Morton)-sorted copy of every scan, and a rigid transform preserves coherence),
+ * so the 32 queries of a warp read the same few bins and their loads coalesce in L1.
  * q_perm (may be null = identity) maps the query's position to its index in the caller's order: nn_out is written
  * in the caller's order (the reference's layout), nn_seq (may be null) in query-array order for the next stage. */
 constexpr int kNNThreads = 128;
 
-__global__ void __launch_bounds__(kNNThreads, 6) k_nn_search(const float4 *__restrict__ q_xyzl, const float4 *__restrict__ q_nrm,
+__global__ void __launch_bounds__(kNNThreads) k_nn_search(const float4 *__restrict__ q_xyzl, const float4 *__restrict__ q_nrm,
 		const uint32_t *__restrict__ q_perm, int n_second, CandSet ci, CandSet co,
 		const uint32_t *__restrict__ s_vals, int n_first,
 		const m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp,
@@ -1025,113 +759,46 @@ __global__ void __launch_bounds__(kNNThreads, 6) k_nn_search(const float4 *__res
 		int *__restrict__ nn_out, int *__restrict__ nn_seq, unsigned long long *__restrict__ label_counts,
 		unsigned long long *__restrict__ eval_counter)
 {
-	__shared__ float4 s_stage[kNNThreads / 32][32];
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
-	float4 *stage = s_stage[threadIdx.x >> 5];
+	const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+	NNParams P;
+	P.mnx = gp->bounding_box_min_X; P.mny = gp->bounding_box_min_Y; P.mnz = gp->bounding_box_min_Z;
+	P.mxx = gp->bounding_box_max_X; P.mxy = gp->bounding_box_max_Y; P.mxz = gp->bounding_box_max_Z;
+	P.rx = gp->resolution_X; P.ry = gp->resolution_Y; P.rz = gp->resolution_Z;
+	P.nbx = gp->number_of_buckets_X; P.nby = gp->number_of_buckets_Y; P.nbz = gp->number_of_buckets_Z;
+	P.nb = gp->number_of_buckets;
+	P.buckets = buckets; P.ci = ci; P.co = co;
+	P.cap_in = max_inner; P.cap_out = max_outer;
+	P.tables = nn_tables_usable(max_inner, max_outer) ? 1 : 0;
+	P.prune = prune;
+	P.r2 = __fmul_rn(search_radius, search_radius);
+	{
+		float rmin = fminf(P.rx, fminf(P.ry, P.rz)) * 0.125f;
+		P.rho2_first = fmaxf(rmin * rmin, 1.0e-30f);
+	}
 	unsigned int evals = 0;
-	int qi = blockIdx.x * blockDim.x + threadIdx.x;
-	NNGrid G;
-	G.nb = gp->number_of_buckets;
-	G.nbx = gp->number_of_buckets_X; G.nby = gp->number_of_buckets_Y; G.nbz = gp->number_of_buckets_Z;
-	G.buckets = buckets; G.ci = ci; G.co = co;
-	G.max_inner = max_inner; G.max_outer = max_outer; G.two_sets = (max_inner != max_outer); G.prune = prune;
-	float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
-	float rx = gp->resolution_X, ry = gp->resolution_Y, rz = gp->resolution_Z;
-	G.trial_unit2 = 1.0f * fmaxf(rx, fmaxf(ry, rz)) * fmaxf(rx, fmaxf(ry, rz));   /* first-round radius^2 = res^2 / candidates: about one candidate spacing */
-	NNQuery q;
-	q.x = q.y = q.z = q.nx = q.ny = q.nz = 0.0f;
-	q.r2 = __fmul_rn(search_radius, search_radius);
-	q.label = -1;
-	q.best = 100000000.0f;
-	q.best_l = 0x7fffffff;
-	NNLane s;
-	s.home = -1; s.ix = s.iy = s.iz = 0; s.done = 0;
-	s.gxl = s.gxh = s.gyl = s.gyh = s.gzl = s.gzh = 0.0f;
-	if (qi < n_second && G.nb > 0) {
+	int best_l = kNNNone, label = -1;
+	if (qi < n_second && P.nb > 0) {
 		float4 p = __ldg(q_xyzl + qi), pn = __ldg(q_nrm + qi);
-		q.x = p.x; q.y = p.y; q.z = p.z; q.nx = pn.x; q.ny = pn.y; q.nz = pn.z;
-		q.label = __float_as_int(p.w);
-		bool inside = !(p.x < mnx || p.x > gp->bounding_box_max_X) && !(p.y < mny || p.y > gp->bounding_box_max_Y) &&
-				!(p.z < mnz || p.z > gp->bounding_box_max_Z);
-		if (inside) {
-			s.ix = cell_of(p.x, mnx, rx); s.iy = cell_of(p.y, mny, ry); s.iz = cell_of(p.z, mnz, rz);
-			int h = s.ix * G.nby * G.nbz + s.iy * G.nbz + s.iz;
-			if (h >= 0 && (long long)h < G.nb) s.home = h;
-		}
+		label = __float_as_int(p.w);
+		best_l = nn_query(P, p, pn, evals);
 	}
-	/* per-axis gaps to the slabs at offset -1 / +1 (0 for the own slab) */
-	if (prune && s.home >= 0) {
-		axis_gaps(q.x, mnx, rx, s.ix, s.gxl, s.gxh);
-		axis_gaps(q.y, mny, ry, s.iy, s.gyl, s.gyh);
-		axis_gaps(q.z, mnz, rz, s.iz, s.gzl, s.gzh);
-	}
-	/* phase A: every distinct home bucket of the warp; phase B: the neighbour buckets that can still matter with the
-	 * limits phase A left behind.  One visit call site keeps the kernel small enough for the instruction cache. */
-	unsigned remaining = __ballot_sync(full, s.home >= 0);
-	unsigned todo = 0;
-	bool phase_b = false;
-#pragma unroll 1
-	for (;;) {
-		int cx, cy, cz;
-		if (remaining) {
-			int leader = __ffs(remaining) - 1;
-			int h = __shfl_sync(full, s.home, leader);
-			cx = __shfl_sync(full, s.ix, leader); cy = __shfl_sync(full, s.iy, leader); cz = __shfl_sync(full, s.iz, leader);
-			remaining &= ~__ballot_sync(full, s.home == h);
-		} else {
-			if (!phase_b) {
-				phase_b = true;
-				/* a neighbour can only matter if one of the six face gaps is within the limit: usually none is */
-				float lim = fminf(q.best, q.r2);
-				float gmin = fminf(fminf(fminf(s.gxl, s.gxh), fminf(s.gyl, s.gyh)), fminf(s.gzl, s.gzh));
-				bool near_face = s.home >= 0 && (!prune || !(__fmul_rn(gmin, gmin) > lim));
-				if (!__any_sync(full, near_face)) break;
-				if (near_face) {
-					/* superset of the buckets worth a visit (sum of squared gaps with a reassociation margin; the exact
-					 * bound is re-checked when the bucket is visited); out-of-grid neighbours get an infinite gap */
-					const float limm = prune ? __fmul_ru(lim, 1.00000095367431640625f) : 3.0e38f;     /* finite: out-of-grid stays excluded */
-					float sx[3], sy[3], sz[3];
-					sx[0] = s.ix > 0 ? __fmul_rd(s.gxl, s.gxl) : INFINITY; sx[1] = 0.0f; sx[2] = s.ix + 1 < G.nbx ? __fmul_rd(s.gxh, s.gxh) : INFINITY;
-					sy[0] = s.iy > 0 ? __fmul_rd(s.gyl, s.gyl) : INFINITY; sy[1] = 0.0f; sy[2] = s.iy + 1 < G.nby ? __fmul_rd(s.gyh, s.gyh) : INFINITY;
-					sz[0] = s.iz > 0 ? __fmul_rd(s.gzl, s.gzl) : INFINITY; sz[1] = 0.0f; sz[2] = s.iz + 1 < G.nbz ? __fmul_rd(s.gzh, s.gzh) : INFINITY;
-					if (!prune) {
-#pragma unroll
-						for (int a = 0; a < 3; a += 2) { if (sx[a] != INFINITY) sx[a] = 0.0f; if (sy[a] != INFINITY) sy[a] = 0.0f; if (sz[a] != INFINITY) sz[a] = 0.0f; }
-					}
-#pragma unroll
-					for (int i = 0; i < 3; i++)
-#pragma unroll
-						for (int j = 0; j < 3; j++) {
-							float sxy = __fadd_rd(sx[i], sy[j]);
-#pragma unroll
-							for (int k = 0; k < 3; k++) todo |= (__fadd_rd(sxy, sz[k]) <= limm) ? (1u << (i * 9 + j * 3 + k)) : 0u;
-						}
-					todo &= ~s.done;
-				}
-			}
-			unsigned pending = __ballot_sync(full, todo != 0u);
-			if (!pending) break;
-			int leader = __ffs(pending) - 1;
-			int o = __ffs(__shfl_sync(full, todo, leader)) - 1;
-			cx = __shfl_sync(full, s.ix, leader) + (o / 9 - 1); cy = __shfl_sync(full, s.iy, leader) + ((o / 3) % 3 - 1);
-			cz = __shfl_sync(full, s.iz, leader) + (o % 3 - 1);
-		}
-		nn_visit_cell(q, s, G, cx, cy, cz, stage, lane, evals);
-		todo &= ~s.done;
-	}
-	if (eval_counter && lane == 0 && evals) atomicAdd(eval_counter, (unsigned long long)evals);
 	int result = -1;
-	if (q.best_l != 0x7fffffff && q.best_l < n_first) result = (int)__ldg(s_vals + q.best_l);
+	if (best_l != kNNNone && best_l >= 0 && best_l < n_first) result = (int)__ldg(s_vals + best_l);
 	if (qi < n_second) {
 		if (nn_seq) nn_seq[qi] = result;
 		nn_out[q_perm ? __ldg(q_perm + qi) : (uint32_t)qi] = result;
+	}
+	if (eval_counter) {
+		unsigned int tot = __reduce_add_sync(full, evals);
+		if (lane == 0 && tot) atomicAdd(eval_counter, (unsigned long long)tot);
 	}
 	if (label_counts) {   /* per-label match counts (gpu6DSLAM.cpp:323-357): warp ballots, one atomic per label per warp */
 		bool hit = qi < n_second && result >= 0;
 #pragma unroll
 		for (int L = 0; L < 4; L++) {
-			unsigned m = __ballot_sync(full, hit && q.label == L);
+			unsigned m = __ballot_sync(full, hit && label == L);
 			if (m && lane == L) atomicAdd(&label_counts[L], (unsigned long long)__popc(m));
 		}
 	}
@@ -1491,29 +1158,41 @@ __device__ inline void moments_to_neq_warp(const double *mo, double om, double f
 struct ObsFromNN {   /* fused path: nn[] + clouds (gpu6DSLAM.cpp:323-398 done on the device) */
 	const int *nn;
 	const float4 *q_xyzl;       /* queries (second cloud, global)           */
-	const float4 *g_xyzl;       /* first cloud, global, original order      */
 	const float4 *l_xyzl;       /* first cloud, local, original order       */
+	const float *m;             /* pose the first cloud was transformed with this iteration (device, row-major 4x4) */
 	const unsigned long long *label_counts;
 	float weight[4];
-	struct Raw { float4 p2, p1, p0; };
-	__device__ __forceinline__ int token(int i) const { return __ldg(nn + i); }
-	__device__ __forceinline__ void fetch(int i, int j, Raw &r) const
+	float r[12];                /* m's 3x4 part, loaded once per thread by prepare() */
+	struct Raw { float4 p2, p0; };
+	__device__ __forceinline__ void prepare()
 	{
-		r.p2 = __ldg(q_xyzl + i); r.p1 = __ldg(g_xyzl + j); r.p0 = __ldg(l_xyzl + j);
+#pragma unroll
+		for (int k = 0; k < 12; k++) r[k] = __ldg(m + k);
 	}
-	__device__ __forceinline__ void finish(const Raw &r, const float *wl, double &w, double &x, double &y, double &z,
+	__device__ __forceinline__ int token(int i) const { return __ldg(nn + i); }
+	__device__ __forceinline__ void fetch(int i, int j, Raw &raw) const
+	{
+		raw.p2 = __ldg(q_xyzl + i); raw.p0 = __ldg(l_xyzl + j);
+	}
+	__device__ __forceinline__ void finish(const Raw &raw, const float *wl, double &w, double &x, double &y, double &z,
 			double &lx, double &ly, double &lz) const
 	{
-		int label = __float_as_int(r.p2.w);
+		int label = __float_as_int(raw.p2.w);
 		w = (label >= 0 && label < 4) ? (double)wl[label] : 0.0;
-		x = r.p0.x; y = r.p0.y; z = r.p0.z;
-		lx = (double)__fsub_rn(r.p1.x, r.p2.x); ly = (double)__fsub_rn(r.p1.y, r.p2.y); lz = (double)__fsub_rn(r.p1.z, r.p2.z);
+		x = raw.p0.x; y = raw.p0.y; z = raw.p0.z;
+		/* the matched point in the global frame, recomputed with k_transform_soa's exact operation sequence (same bits as
+		 * the transformed cloud the search ran on) instead of a second random gather */
+		float p1x = __fadd_rn(r[3], __fmaf_rn(r[2], raw.p0.z, __fmaf_rn(r[0], raw.p0.x, __fmul_rn(r[1], raw.p0.y))));
+		float p1y = __fadd_rn(r[7], __fmaf_rn(r[6], raw.p0.z, __fmaf_rn(r[4], raw.p0.x, __fmul_rn(r[5], raw.p0.y))));
+		float p1z = __fadd_rn(r[11], __fmaf_rn(r[10], raw.p0.z, __fmaf_rn(r[8], raw.p0.x, __fmul_rn(r[9], raw.p0.y))));
+		lx = (double)__fsub_rn(p1x, raw.p2.x); ly = (double)__fsub_rn(p1y, raw.p2.y); lz = (double)__fsub_rn(p1z, raw.p2.z);
 	}
 };
 
 struct ObsFromList { /* stage-level path: the reference's obs_nn_t array */
 	const m3dreg_obs_nn *obs;
 	struct Raw { float v[7]; };
+	__device__ __forceinline__ void prepare() {}
 	__device__ __forceinline__ int token(int) const { return 0; }
 	__device__ __forceinline__ void fetch(int i, int, Raw &r) const
 	{
@@ -1591,9 +1270,11 @@ constexpr int kNeqThreads = 256;
 constexpr int kNeqInFlight = 4;
 
 template <class Src>
-__global__ void __launch_bounds__(kNeqThreads) k_normal_equations(Src src, int n, double *__restrict__ partials,
+__global__ void __launch_bounds__(kNeqThreads) k_normal_equations(const Src src_in, int n, double *__restrict__ partials,
 		unsigned int *__restrict__ ticket, FinalizeArgs fin)
 {
+	Src src = src_in;
+	src.prepare();
 	__shared__ double sm[kNeqThreads / 32][kMomentCount];
 	__shared__ float wl[4];
 	__shared__ bool is_last;

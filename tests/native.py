@@ -40,3 +40,35 @@ def build_shim_host(force: bool = False) -> str:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-ffp-contract=off", "-I", inc, "-o", SHIM_EXE, SHIM_SRC,
                                "-L", libdir, "-lm3dreg", "-Wl,-rpath," + libdir])
     return SHIM_EXE
+
+
+EMUL_SO = os.path.join(_HERE, "_build", "libnn_emul.so")
+EMUL_SRC = os.path.join(_HERE, "csrc", "nn_emul.cpp")
+
+
+def build_nn_emul(force: bool = False) -> str:
+    """Host instantiation of the device NN search logic (nn_core.cuh) for CPU-side checks against the oracle."""
+    root = os.path.dirname(_HERE)
+    core = os.path.join(root, "mandala-mapping_b200", "csrc", "nn_core.cuh")
+    deps = [EMUL_SRC, core, os.path.join(root, "include", "m3dreg.h")]
+    stale = (not os.path.exists(EMUL_SO)) or any(os.path.getmtime(f) > os.path.getmtime(EMUL_SO) for f in deps)
+    if force or stale:
+        os.makedirs(os.path.dirname(EMUL_SO), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared",
+                               "-x", "c++", "-I", "/usr/local/cuda/include", "-o", EMUL_SO, EMUL_SRC])
+    return EMUL_SO
+
+
+def nn_emul_search(first, second, table, buckets, gp, radius, max_inner=100, max_outer=100, prune=True):
+    """Run the emulated search; returns (nn, candidate evaluations)."""
+    import numpy as np
+    lib = C.CDLL(build_nn_emul())
+    first = np.ascontiguousarray(first); second = np.ascontiguousarray(second)
+    table = np.ascontiguousarray(table); buckets = np.ascontiguousarray(buckets); gp = np.ascontiguousarray(gp)
+    nn = np.full(len(second), -7, dtype=np.int32)
+    ev = C.c_longlong(0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.emul_nn_search(vp(first), C.c_int(len(first)), vp(second), C.c_int(len(second)), vp(table), vp(buckets), vp(gp),
+                            C.c_float(radius), C.c_int(max_inner), C.c_int(max_outer), C.c_int(1 if prune else 0), vp(nn), C.byref(ev))
+    assert rc == 0
+    return nn, int(ev.value)
