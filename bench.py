@@ -311,7 +311,7 @@ def main():
     ctx.nn_evaluations(reset=True)
     ctx.icp_step(min(args.steps, 10))
     stage_ms, stage_iters = ctx.get_stage_ms()
-    evals_per_query = ctx.nn_evaluations(reset=True) / max(stage_iters, 1) / (n2 / 32.0)
+    evals_per_query = ctx.nn_evaluations(reset=True) / max(stage_iters, 1) / float(n2)
     ctx.set_profiling(False)
     ctx.icp_end()
     stage_ms = stage_ms / max(stage_iters, 1)

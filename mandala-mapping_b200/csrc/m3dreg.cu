@@ -173,7 +173,7 @@ int grid_params_from_bounds(const float mn[3], const float mx[3], float rx, floa
 	out->resolution_X = rx; out->resolution_Y = ry; out->resolution_Z = rz;
 	long long nb = (long long)nbx * nby * nbz;
 	out->number_of_buckets = nb;
-	if (nbx <= 0 || nby <= 0 || nbz <= 0 || nb > 2147483647LL) return M3DREG_E_TOO_MANY_BUCKETS;
+	if (nbx <= 0 || nby <= 0 || nbz <= 0 || nb > 2147483647LL || !nn_columns_usable(nbx, nby, nbz)) return M3DREG_E_TOO_MANY_BUCKETS;
 	return 0;
 }
 
@@ -641,6 +641,7 @@ int m3dreg_nn_search(m3dreg_ctx *c, const m3dreg_point *d_first, int n1, const m
 		float search_radius, int max_inner, int max_outer, int *d_nn)
 {
 	if (!c || !d_first || !d_second || n1 <= 0 || n2 <= 0 || !d_table || !d_buckets || !params || !d_nn) return M3DREG_E_INVALID_ARG;
+	if (!nn_columns_usable(params->number_of_buckets_X, params->number_of_buckets_Y, params->number_of_buckets_Z)) return M3DREG_E_TOO_MANY_BUCKETS;
 	CK(cudaSetDevice(c->dev));
 	int e = ensure_first(c, (size_t)n1);
 	if (e) return e;

@@ -197,7 +197,7 @@ __device__ __forceinline__ bool grid_params_from_bounds_dev(const uint32_t *__re
 	g.number_of_buckets_X = nbx; g.number_of_buckets_Y = nby; g.number_of_buckets_Z = nbz;
 	g.resolution_X = rx; g.resolution_Y = ry; g.resolution_Z = rz;
 	g._pad0 = 0; g._pad1 = 0;
-	bool ok = !(nbx <= 0 || nby <= 0 || nbz <= 0 || nb > 2147483647LL || nb > bucket_cap);
+	bool ok = !(nbx <= 0 || nby <= 0 || nbz <= 0 || nb > 2147483647LL || nb > bucket_cap) && nn_columns_usable(nbx, nby, nbz);
 	g.number_of_buckets = ok ? nb : 0;
 	return ok;
 }
@@ -770,13 +770,7 @@ __global__ void __launch_bounds__(kNNThreads) k_nn_search(const float4 *__restri
 	P.nb = gp->number_of_buckets;
 	P.buckets = buckets; P.ci = ci; P.co = co;
 	P.cap_in = max_inner; P.cap_out = max_outer;
-	P.tables = nn_tables_usable(max_inner, max_outer) ? 1 : 0;
-	P.prune = prune;
-	P.r2 = __fmul_rn(search_radius, search_radius);
-	{
-		float rmin = fminf(P.rx, fminf(P.ry, P.rz)) * 0.125f;
-		P.rho2_first = fmaxf(rmin * rmin, 1.0e-30f);
-	}
+	nn_params_finish(P, search_radius, prune);
 	unsigned int evals = 0;
 	int best_l = kNNNone, label = -1;
 	if (qi < n_second && P.nb > 0) {

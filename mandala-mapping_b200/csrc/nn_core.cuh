@@ -107,20 +107,6 @@ M3D_HD float nn_dist(float qx, float qy, float qz, const float4 &c)
 	return f_fma(dz, dz, f_fma(dx, dx, f_mul(dy, dy)));
 }
 
-/* Conservative per-axis gap between the query and the slab of cells at offset -1 / +1 (rounded DOWN to float).
- * A point stored in cell c satisfies trunc(fl(fl(v-min)/res)) == c; with two roundings of relative error 2^-24,
- * (v-min) < ix*res*(1+2^-21) for cells <= ix-1 and (v-min) >= (ix+1)*res*(1-2^-21) for cells >= ix+1.
- * A factor 2^-20 is used.  fl(q - v) is the correctly rounded true difference, rounding is monotone and the gap
- * is a float, so |fl(q-v)| >= gap for every point of those cells. */
-M3D_HD void axis_gaps(float q, float mn, float res, int ic, float &g_lo, float &g_hi)
-{
-	const float up_f = 1.00000095367431640625f, dn_f = 0.99999904632568359375f;     /* 1 +- 2^-20 */
-	float up = f_mul_up(f_mul_up((float)ic, res), up_f);            /* exclusive upper bound of cells <= ic-1, rounded up   */
-	float lo = f_mul_dn(f_mul_dn((float)(ic + 1), res), dn_f);      /* inclusive lower bound of cells >= ic+1, rounded down */
-	g_lo = fmaxf(0.0f, f_sub_dn(f_sub_dn(q, mn), up));
-	g_hi = fmaxf(0.0f, f_sub_dn(lo, f_sub_up(q, mn)));
-}
-
 /* ---- candidate layout ------------------------------------------------------------------------------------------ */
 struct CandSet {
 	float4 *xyzl;            /* {x, y, z, bits of l = position in the sorted table (hashElement index)} */
@@ -140,6 +126,12 @@ M3D_HD bool nn_tables_usable(int cap_inner, int cap_outer)
 {
 	int c = cap_inner > cap_outer ? cap_inner : cap_outer;
 	return c <= 32768;
+}
+
+/* the search addresses fine columns (4 per bucket and axis) with ints */
+M3D_HD bool nn_columns_usable(int nbx, int nby, int nbz)
+{
+	return nbx <= (1 << 27) && nby <= (1 << 27) && nbz <= (1 << 27);
 }
 
 M3D_HD float nn_subcell_width(float res, int level)
@@ -165,12 +157,13 @@ M3D_HD int nn_bin(int label, int ux, int uy, int uz, int level)
 /* ---- one query --------------------------------------------------------------------------------------------------- */
 struct NNParams {
 	float mnx, mny, mnz, mxx, mxy, mxz, rx, ry, rz;
+	float iwx, iwy, iwz;       /* 4 / res: fine (level-2) columns per metre, only used for conservative column boxes */
 	int nbx, nby, nbz;
 	long long nb;
 	const m3dreg_bucket *buckets;
 	CandSet ci, co;            /* INNER (home bucket) and OUTER (neighbours) sets; the same set when the caps are equal */
 	int cap_in, cap_out;
-	int tables;                /* nn_tables_usable(cap_in, cap_out) */
+	int tables;                /* nn_tables_usable(cap_in, cap_out, nbx, nby, nbz) */
 	int prune;                 /* 0: one round over the whole neighbourhood (equivalence test only) */
 	float r2;                  /* fl(radius * radius) */
 	float rho2_first;          /* squared radius of the first non-trivial round */
@@ -178,11 +171,35 @@ struct NNParams {
 
 constexpr int kNNNone = 0x7fffffff;
 
-struct NNBest {
-	float best_d;
-	int best_l;
-	float lim;                 /* a candidate can only matter if dist <= lim */
-};
+/* derived fields of NNParams from the grid fields, the caps and the search radius (same code on device and host) */
+M3D_HD void nn_params_finish(NNParams &P, float search_radius, int prune)
+{
+	P.tables = (nn_tables_usable(P.cap_in, P.cap_out) && nn_columns_usable(P.nbx, P.nby, P.nbz)) ? 1 : 0;
+	P.prune = prune;
+	P.r2 = f_mul(search_radius, search_radius);                         /* lesson_16.cu:553 */
+	P.iwx = f_div(4.0f, P.rx); P.iwy = f_div(4.0f, P.ry); P.iwz = f_div(4.0f, P.rz);
+	const float rmin = f_mul(fminf(P.rx, fminf(P.ry, P.rz)), 0.0625f);
+	P.rho2_first = fmaxf(f_mul(rmin, rmin), 1.0e-30f);
+}
+
+/* Conservative fine-column bounds of a coordinate interval.  The fine column of a stored candidate with coordinate v is
+ * U(v) = 4 * cell_of(v) + (thresholds reached inside the cell); its cell boundary and thresholds lie within a few ulps
+ * (relative 2^-22 of the magnitudes involved) of the ideal lattice mn + U * res/4.  t = fl(fl(v - mn) * iw) carries a
+ * comparable error, so with the margin m = |t| * 2^-18 + mg, mg = (|q| + |mn|) * iw * 2^-18 + 2^-10 (32x the worst
+ * case), every candidate with v >= lo has U(v) >= col_floor(lo) and every candidate with v <= hi has
+ * U(v) <= col_ceil(hi).  Only a SUPERSET of the bins is needed for exactness, never the exact set. */
+M3D_HD int col_floor(float lo, float mn, float iw, float mg)
+{
+	float t = f_mul(f_sub(lo, mn), iw);
+	t = t - (fabsf(t) * 3.814697265625e-06f + mg);
+	return (int)fminf(fmaxf(t, -1.0f), 1.0e9f);        /* negative values truncate towards 0 / clamp to -1: callers clamp to >= 0 */
+}
+M3D_HD int col_ceil(float hi, float mn, float iw, float mg)
+{
+	float t = f_mul(f_sub(hi, mn), iw);
+	t = t + (fabsf(t) * 3.814697265625e-06f + mg);
+	return (int)fminf(fmaxf(t, -1.0f), 1.0e9f);
+}
 
 /* Returns the sorted position l of the reference's answer, or kNNNone.  p = {x,y,z,label bits}, pn = normal. */
 M3D_HD int nn_query(const NNParams &P, const float4 &p, const float4 &pn, unsigned int &evals)
@@ -195,74 +212,73 @@ M3D_HD int nn_query(const NNParams &P, const float4 &p, const float4 &pn, unsign
 	const int home = ix * P.nby * P.nbz + iy * P.nbz + iz;
 	if (!(home >= 0 && (long long)home < P.nb)) return kNNNone;         /* lesson_16.cu:583 */
 
-	NNBest b;
-	b.best_d = 100000000.0f;                                            /* lesson_16.cu:597 */
-	b.best_l = kNNNone;
-	b.lim = fminf(P.r2, 99999992.0f);                                   /* dist <= r2 && dist < 1e8 */
-	if (!(b.lim >= 0.0f)) return kNNNone;
+	float best_d = 100000000.0f;                                        /* lesson_16.cu:597 */
+	int best_l = kNNNone;
+	float lim = fminf(P.r2, 99999992.0f);                               /* a candidate can only matter if dist <= lim (<= r2, < 1e8) */
+	if (!(lim >= 0.0f)) return kNNNone;
 
-	float gxl, gxh, gyl, gyh, gzl, gzh;
-	axis_gaps(qx, P.mnx, P.rx, ix, gxl, gxh);
-	axis_gaps(qy, P.mny, P.ry, iy, gyl, gyh);
-	axis_gaps(qz, P.mnz, P.rz, iz, gzl, gzh);
-	const bool has_xl = ix > 0, has_xh = ix != P.nbx - 1;               /* edge clamping, lesson_16.cu:588-595 */
-	const bool has_yl = iy > 0, has_yh = iy != P.nby - 1;
-	const bool has_zl = iz > 0, has_zh = iz != P.nbz - 1;
+	/* the 27-neighbourhood with edge clamping (lesson_16.cu:588-608), as a box of fine columns */
+	const int cx0 = (ix > 0 ? ix - 1 : ix) << 2, cx1 = ((ix != P.nbx - 1 ? ix + 1 : ix) << 2) + 3;
+	const int cy0 = (iy > 0 ? iy - 1 : iy) << 2, cy1 = ((iy != P.nby - 1 ? iy + 1 : iy) << 2) + 3;
+	const int cz0 = (iz > 0 ? iz - 1 : iz) << 2, cz1 = ((iz != P.nbz - 1 ? iz + 1 : iz) << 2) + 3;
+	const float mgx = f_fma(f_mul(fabsf(qx) + fabsf(P.mnx), P.iwx), 3.814697265625e-06f, 9.765625e-04f);
+	const float mgy = f_fma(f_mul(fabsf(qy) + fabsf(P.mny), P.iwy), 3.814697265625e-06f, 9.765625e-04f);
+	const float mgz = f_fma(f_mul(fabsf(qz) + fabsf(P.mnz), P.iwz), 3.814697265625e-06f, 9.765625e-04f);
 
-	float R_old = -1.0f;
-	float rho2 = 0.0f;
+	int oxl = 1, oxh = 0, oyl = 1, oyh = 0, ozl = 1, ozh = 0;          /* fine-column box of the previous round (empty) */
+	float rho2 = P.rho2_first;
 	for (int round = 0; round < 80; round++) {
 		/* every candidate with dist <= tau has |fl(q - c)| <= sqrt(tau) up to two roundings per axis (dist >= fl(d*d)),
 		 * hence lies in [q - R, q + R] with R rounded outwards and a 2^-20 margin */
-		const float tau = P.prune ? fminf(b.lim, rho2) : b.lim;
+		const float tau = P.prune ? fminf(lim, rho2) : lim;
 		const float R = P.prune ? f_add_up(f_mul_up(f_sqrt_up(tau), 1.00000095367431640625f), 1.0e-18f) : INFINITY;
-		const float lox = f_sub_dn(qx, R), hix = f_add_up(qx, R);
-		const float loy = f_sub_dn(qy, R), hiy = f_add_up(qy, R);
-		const float loz = f_sub_dn(qz, R), hiz = f_add_up(qz, R);
-		const bool have_old = R_old >= 0.0f;
-		const float olox = f_sub_dn(qx, R_old), ohix = f_add_up(qx, R_old);
-		const float oloy = f_sub_dn(qy, R_old), ohiy = f_add_up(qy, R_old);
-		const float oloz = f_sub_dn(qz, R_old), ohiz = f_add_up(qz, R_old);
-		const int dxlo = (has_xl && gxl <= R) ? -1 : 0, dxhi = (has_xh && gxh <= R) ? 1 : 0;
-		const int dylo = (has_yl && gyl <= R) ? -1 : 0, dyhi = (has_yh && gyh <= R) ? 1 : 0;
-		const int dzlo = (has_zl && gzl <= R) ? -1 : 0, dzhi = (has_zh && gzh <= R) ? 1 : 0;
-		const int odxlo = (has_xl && gxl <= R_old) ? -1 : 0, odxhi = (has_xh && gxh <= R_old) ? 1 : 0;
-		const int odylo = (has_yl && gyl <= R_old) ? -1 : 0, odyhi = (has_yh && gyh <= R_old) ? 1 : 0;
-		const int odzlo = (has_zl && gzl <= R_old) ? -1 : 0, odzhi = (has_zh && gzh <= R_old) ? 1 : 0;
+		int xl = col_floor(f_sub(qx, R), P.mnx, P.iwx, mgx), xh = col_ceil(f_add(qx, R), P.mnx, P.iwx, mgx);
+		int yl = col_floor(f_sub(qy, R), P.mny, P.iwy, mgy), yh = col_ceil(f_add(qy, R), P.mny, P.iwy, mgy);
+		int zl = col_floor(f_sub(qz, R), P.mnz, P.iwz, mgz), zh = col_ceil(f_add(qz, R), P.mnz, P.iwz, mgz);
+		xl = xl > cx0 ? xl : cx0; xh = xh < cx1 ? xh : cx1;
+		yl = yl > cy0 ? yl : cy0; yh = yh < cy1 ? yh : cy1;
+		zl = zl > cz0 ? zl : cz0; zh = zh < cz1 ? zh : cz1;
+		const bool have_old = oxl <= oxh;
 
-		for (int dx = dxlo; dx <= dxhi; dx++)
-		for (int dy = dylo; dy <= dyhi; dy++)
-		for (int dz = dzlo; dz <= dzhi; dz++) {
-			const bool inner = (dx | dy | dz) == 0;
+		for (int bx = xl >> 2; bx <= (xh >> 2); bx++)
+		for (int by = yl >> 2; by <= (yh >> 2); by++)
+		for (int bz = zl >> 2; bz <= (zh >> 2); bz++) {
+			const bool inner = bx == ix && by == iy && bz == iz;
 			const int cap = inner ? P.cap_in : P.cap_out;                /* lesson_16.cu:618-626 */
 			if (cap <= 0) continue;
-			const int cell = home + (dx * P.nby + dy) * P.nbz + dz;
+			const int cell = (bx * P.nby + by) * P.nbz + bz;
 			const int *rec = reinterpret_cast<const int *>(P.buckets + cell);
 			const int npts = M3D_LDG(rec + 2);
 			if (npts <= 0) continue;                                      /* lesson_16.cu:615-616 (also the quirk bucket) */
 			const int begin = M3D_LDG(rec);
 			if (begin < 0) continue;
-			const bool b_old = have_old && dx >= odxlo && dx <= odxhi && dy >= odylo && dy <= odyhi && dz >= odzlo && dz <= odzhi;
 			const float4 *cx = inner ? P.ci.xyzl : P.co.xyzl;
 			const float4 *cn = inner ? P.ci.nrm : P.co.nrm;
 			const int level = P.tables ? nn_level(npts) : -1;
+			const int fx = bx << 2, fy = by << 2, fz = bz << 2;         /* first fine column of this bucket */
+			/* this bucket's part of the previous round's box, in fine columns */
+			const int pxl = oxl > fx ? oxl : fx, pxh = oxh < fx + 3 ? oxh : fx + 3;
+			const int pyl = oyl > fy ? oyl : fy, pyh = oyh < fy + 3 ? oyh : fy + 3;
+			const int pzl = ozl > fz ? ozl : fz, pzh = ozh < fz + 3 ? ozh : fz + 3;
+			const bool b_old = have_old && pxl <= pxh && pyl <= pyh && pzl <= pzh;   /* visited before (in part) */
 			int xlo = 0, xhi = 0, ylo = 0, yhi = 0, zlo = 0, zhi = 0;
 			int oxlo = 0, oxhi = -1, oylo = 0, oyhi = -1, ozlo = 0, ozhi = -1;
 			int flat_n = 0, bin_l = 0;
 			const unsigned short *tab = nullptr;
 			if (level < 0) {
-				if (b_old) continue;
+				if (b_old) continue;                                      /* a bucket without a table is looked at as a whole */
 				const int iter = candidate_stride(npts, cap);
 				flat_n = (npts + iter - 1) / iter;
 			} else {
-				const float wx = nn_subcell_width(P.rx, level), wy = nn_subcell_width(P.ry, level), wz = nn_subcell_width(P.rz, level);
-				xlo = nn_col(lox, P.mnx, wx, ix + dx, level); xhi = nn_col(hix, P.mnx, wx, ix + dx, level);
-				ylo = nn_col(loy, P.mny, wy, iy + dy, level); yhi = nn_col(hiy, P.mny, wy, iy + dy, level);
-				zlo = nn_col(loz, P.mnz, wz, iz + dz, level); zhi = nn_col(hiz, P.mnz, wz, iz + dz, level);
-				if (b_old) {
-					oxlo = nn_col(olox, P.mnx, wx, ix + dx, level); oxhi = nn_col(ohix, P.mnx, wx, ix + dx, level);
-					oylo = nn_col(oloy, P.mny, wy, iy + dy, level); oyhi = nn_col(ohiy, P.mny, wy, iy + dy, level);
-					ozlo = nn_col(oloz, P.mnz, wz, iz + dz, level); ozhi = nn_col(ohiz, P.mnz, wz, iz + dz, level);
+				/* columns of this bucket at its own level: a level-L column is 2^(2-L) fine columns (identical thresholds) */
+				const int sh = 2 - level;
+				xlo = ((xl > fx ? xl : fx) - fx) >> sh; xhi = ((xh < fx + 3 ? xh : fx + 3) - fx) >> sh;
+				ylo = ((yl > fy ? yl : fy) - fy) >> sh; yhi = ((yh < fy + 3 ? yh : fy + 3) - fy) >> sh;
+				zlo = ((zl > fz ? zl : fz) - fz) >> sh; zhi = ((zh < fz + 3 ? zh : fz + 3) - fz) >> sh;
+				if (b_old) {     /* columns visited by the previous round (all their candidates were looked at) */
+					oxlo = (pxl - fx) >> sh; oxhi = (pxh - fx) >> sh;
+					oylo = (pyl - fy) >> sh; oyhi = (pyh - fy) >> sh;
+					ozlo = (pzl - fz) >> sh; ozhi = (pzh - fz) >> sh;
 				}
 				tab = (inner ? P.ci.tab : P.co.tab) + 2 * (size_t)begin;
 				bin_l = (label & 3) << (3 * level);
@@ -293,14 +309,14 @@ M3D_HD int nn_query(const NNParams &P, const float4 &p, const float4 &pn, unsign
 						const float d0 = nn_dist(qx, qy, qz, c0), d1 = nn_dist(qx, qy, qz, c1), d2 = nn_dist(qx, qy, qz, c2),
 								d3 = nn_dist(qx, qy, qz, c3);
 #define M3D_NN_CONSIDER(D, C, J)                                                                                       \
-						if ((D) <= b.lim) {                                                                                    \
+						if ((D) <= lim) {                                                                                      \
 							/* D <= lim <= best_d: a strictly smaller distance, or the same distance at a smaller position */   \
 							const int l_ = f_bits((C).w);                                                                       \
-							if ((D) < b.best_d || l_ < b.best_l) {                                                             \
+							if ((D) < best_d || l_ < best_l) {                                                                 \
 								const float4 n_ = M3D_LDG(cn + (J));                                                            \
 								if (f_bits(n_.w) == label) {                                                                    \
 									const float dot_ = f_fma(pn.z, n_.z, f_fma(pn.x, n_.x, f_mul(pn.y, n_.y)));                 \
-									if (angle_gate(dot_)) { b.best_d = (D); b.best_l = l_; b.lim = (D); }                      \
+									if (angle_gate(dot_)) { best_d = (D); best_l = l_; lim = (D); }                            \
 								}                                                                                               \
 							}                                                                                                   \
 						}
@@ -313,11 +329,11 @@ M3D_HD int nn_query(const NNParams &P, const float4 &p, const float4 &pn, unsign
 				}
 			}
 		}
-		if (!P.prune || b.lim <= rho2) break;      /* everything at or below the limit was inside this round's box */
-		R_old = R;
-		rho2 = rho2 > 0.0f ? f_mul(rho2, 4.0f) : P.rho2_first;
+		if (!P.prune || lim <= rho2) break;      /* everything at or below the limit was inside this round's box */
+		oxl = xl; oxh = xh; oyl = yl; oyh = yh; ozl = zl; ozh = zh;
+		rho2 = f_mul(rho2, 4.0f);
 	}
-	return b.best_l;
+	return best_l;
 }
 
 } /* namespace m3d */

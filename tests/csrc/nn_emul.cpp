@@ -89,11 +89,7 @@ extern "C" int emul_nn_search(const m3dreg_point *first, int n1, const m3dreg_po
 	P.ci = si.view();
 	P.co = two ? so.view() : si.view();
 	P.cap_in = max_inner; P.cap_out = max_outer;
-	P.tables = tables;
-	P.prune = prune;
-	P.r2 = f_mul(radius, radius);
-	float rmin = fminf(P.rx, fminf(P.ry, P.rz)) * 0.125f;
-	P.rho2_first = fmaxf(rmin * rmin, 1.0e-30f);
+	nn_params_finish(P, radius, prune);
 	long long total = 0;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+:total)
 	for (int q = 0; q < n2; q++) {
