@@ -108,6 +108,8 @@ struct m3dreg_ctx {
 	unsigned int *ticket = nullptr;
 	unsigned int *cell_count = nullptr;           /* number of searchable buckets in the compact list */
 	unsigned long long *eval_counter = nullptr;   /* candidates staged by the NN search (warp-level), diagnostic */
+	int nn_per_thread = 0;       /* test switch (env M3DREG_NN_PER_THREAD=1): k_nn_search instead of k_nn_search_grid */
+	int nn_rho_div = 0;          /* tuning (env M3DREG_NN_RHO_DIV): first-round radius = res / div */
 	double *scratch = nullptr;   /* 64 doubles */
 	float *mats = nullptr;       /* 32 floats  */
 	HostSmall *h = nullptr;      /* pinned */
@@ -308,6 +310,11 @@ void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *va
 		float radius, int max_inner, int max_outer, int prune, int *nn_out, int *nn_seq, unsigned long long *label_counts)
 {
 	bool two = max_inner != max_outer;
+	if (!two && !c->nn_per_thread) {     /* one candidate set (the reference's default caps): warp-shared lookup grid */
+		LAUNCH(c, k_nn_search_grid, (n2 + kNNThreads - 1) / kNNThreads, kNNThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
+				cand_set(c, false), vals, n1, buckets, c->gp, radius, max_outer, (prune && c->nn_rho_div > 1) ? c->nn_rho_div : prune, nn_out, nn_seq, label_counts, c->eval_counter);
+		return;
+	}
 	LAUNCH(c, k_nn_search, (n2 + kNNThreads - 1) / kNNThreads, kNNThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
 			cand_set(c, false), cand_set(c, two), vals, n1, buckets, c->gp, radius, max_inner, max_outer, prune, nn_out, nn_seq,
 			label_counts, c->eval_counter);
@@ -500,6 +507,8 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	if (!c) return (int)cudaErrorMemoryAllocation;
 	c->dev = cuda_device;
 	c->sm_count = prop.multiProcessorCount;
+	{ const char *e = getenv("M3DREG_NN_PER_THREAD"); c->nn_per_thread = (e && e[0] == '1') ? 1 : 0; }
+	{ const char *e = getenv("M3DREG_NN_RHO_DIV"); c->nn_rho_div = e ? atoi(e) : 0; }
 	cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
 	if (e != cudaSuccess) { delete c; return (int)e; }
 	c->stream = c->own_stream;

@@ -798,6 +798,351 @@ __global__ void __launch_bounds__(kNNThreads) k_nn_search(const float4 *__restri
 	}
 }
 
+/* ---- semantic NN, warp-shared search (k_nn_search_grid) ----------------------------------------------------------
+ * Same answer as k_nn_search / nn_query() (lexicographic minimum of (dist, l) over the admissible candidates, rounds of
+ * growing radius, conservative fine-column boxes — nn_core.cuh), organised so that the 32 queries of a warp (neighbours
+ * on one surface: the scan store keeps queries (label, Morton)-sorted) stay in lock step:
+ *   1. every unsettled lane computes its fine-column box for the round; the warp takes the HULL of the boxes (REDUX);
+ *   2. the lanes look up, side by side, the fine cells of the hull (bucket record + bin table, once per cell and warp)
+ *      and compact the non-empty bins of the warp's label into a segment list {first candidate, count, cell};
+ *   3. the segments' candidates are staged in shared memory with coalesced loads (groups of four, padded with +inf)
+ *      and ALL lanes evaluate ALL of them with broadcast LDS.128: a branch-free loop keeps, per lane, the minimum
+ *      distance and the group that produced it, plus a flag for an exact tie between groups;
+ *   4. one cold step per lane and batch applies the full predicate (label, angle gate, radius, (dist, l) order) to the
+ *      winning group; a tie or an inadmissible winner triggers a re-scan of the batch with the full predicate.
+ * Looking at more candidates than a lane's own box is harmless for a minimum as long as they belong to buckets of the
+ * lane's own 27-neighbourhood; when the hull leaves some lane's neighbourhood (search radius > bucket size) this is
+ * tested per group.  A bin of a coarser bucket (S = 2 or 1) covers several fine cells and is listed from one
+ * representative cell per axis (the hull's first cell or a cell aligned to the bin); cells inside the previous round's
+ * hull are skipped: a skipped representative means the bin touched that hull, where — by induction over the rounds —
+ * every touching bin was evaluated by all lanes.  A bin may be listed twice (harmless).  Hulls larger than the list
+ * are processed in chunks of whole (y,z) rows; warps whose queries are scattered (hull much larger than the lanes' own
+ * boxes) and grids beyond the column arithmetic fall back to nn_query().
+ * Requires one candidate set (INNER cap == OUTER cap, the reference's default). */
+constexpr int kNNCells = 128;       /* hull cells looked up per chunk (segment list capacity) */
+constexpr int kNNStage = 192;       /* candidates staged per batch (multiple of 4) */
+constexpr int kNNWarps = kNNThreads / 32;
+
+__device__ __noinline__ int nn_query_fallback(const m3dreg_grid_params *__restrict__ gp, const m3dreg_bucket *__restrict__ buckets,
+		const float4 *cxyzl, const float4 *cnrm, const unsigned short *ctab, float search_radius, int cap, int prune, float4 p, float4 pn,
+		unsigned int *evals)
+{
+	NNParams P;
+	P.mnx = gp->bounding_box_min_X; P.mny = gp->bounding_box_min_Y; P.mnz = gp->bounding_box_min_Z;
+	P.mxx = gp->bounding_box_max_X; P.mxy = gp->bounding_box_max_Y; P.mxz = gp->bounding_box_max_Z;
+	P.rx = gp->resolution_X; P.ry = gp->resolution_Y; P.rz = gp->resolution_Z;
+	P.nbx = gp->number_of_buckets_X; P.nby = gp->number_of_buckets_Y; P.nbz = gp->number_of_buckets_Z;
+	P.nb = gp->number_of_buckets;
+	P.buckets = buckets;
+	P.ci.xyzl = const_cast<float4 *>(cxyzl); P.ci.nrm = const_cast<float4 *>(cnrm); P.ci.tab = const_cast<unsigned short *>(ctab);
+	P.co = P.ci;
+	P.cap_in = cap; P.cap_out = cap;
+	nn_params_finish(P, search_radius, prune);
+	unsigned int ev = 0;
+	const int l = nn_query(P, p, pn, ev);
+	*evals += ev;
+	return l;
+}
+
+/* full predicate of the reference on one candidate (lesson_16.cu:658-686) with the (dist, l) order made explicit */
+#define M3D_NN_CONSIDER(D, C, J)                                                                                       \
+	if ((D) <= lim) {                                                                                                  \
+		const int l_ = __float_as_int((C).w);                                                                           \
+		if ((D) < best_d || l_ < best_l) {                                                                             \
+			const float4 n_ = __ldg(cn + (J));                                                                          \
+			if (__float_as_int(n_.w) == label) {                                                                        \
+				const float dot_ = f_fma(pn.z, n_.z, f_fma(pn.x, n_.x, f_mul(pn.y, n_.y)));                             \
+				if (angle_gate(dot_)) { best_d = (D); best_l = l_; lim = (D); }                                        \
+			}                                                                                                           \
+		}                                                                                                               \
+	}
+
+__global__ void __launch_bounds__(kNNThreads, 5) k_nn_search_grid(const float4 *__restrict__ q_xyzl, const float4 *__restrict__ q_nrm,
+		const uint32_t *__restrict__ q_perm, int n_second, CandSet cs,
+		const uint32_t *__restrict__ s_vals, int n_first,
+		const m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp,
+		float search_radius, int cap, int prune,
+		int *__restrict__ nn_out, int *__restrict__ nn_seq, unsigned long long *__restrict__ label_counts,
+		unsigned long long *__restrict__ eval_counter)
+{
+	__shared__ int4 s_segs[kNNWarps][kNNCells];                /* {first candidate, count, hull cell x | y << 16, hull cell z} */
+	__shared__ float4 s_cand[kNNWarps][kNNStage];              /* staged candidates {x, y, z, l bits}, groups of four */
+	__shared__ int4 s_grp[kNNWarps][kNNStage / 4];             /* per group: {index of its first candidate, -, hull cell x | y << 16, z} */
+	const unsigned full = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	int4 *segs = s_segs[threadIdx.x >> 5];
+	float4 *stage = s_cand[threadIdx.x >> 5];
+	int4 *grp = s_grp[threadIdx.x >> 5];
+	const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+	/* grid and search parameters (same expressions as nn_params_finish) */
+	const float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
+	const float res_x = gp->resolution_X, res_y = gp->resolution_Y, res_z = gp->resolution_Z;
+	const int nbx = gp->number_of_buckets_X, nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
+	const long long nb = gp->number_of_buckets;
+	const int tables = (nn_tables_usable(cap, cap) && nn_columns_usable(nbx, nby, nbz)) ? 1 : 0;
+	const float r2 = f_mul(search_radius, search_radius);                /* lesson_16.cu:553 */
+	const float iwx = f_div(4.0f, res_x), iwy = f_div(4.0f, res_y), iwz = f_div(4.0f, res_z);
+	float rho2_first;
+	{
+		const float rmin = prune > 1 ? f_div(fminf(res_x, fminf(res_y, res_z)), (float)prune)      /* tuning: min(res) / prune */
+				: f_mul(fminf(res_x, fminf(res_y, res_z)), 0.0625f);
+		rho2_first = fmaxf(f_mul(rmin, rmin), 1.0e-30f);
+	}
+	const float4 *__restrict__ cx = cs.xyzl;
+	const float4 *__restrict__ cn = cs.nrm;
+
+	unsigned int evals = 0;
+	int best_l = kNNNone, label = -1;
+	float best_d = 100000000.0f;                                        /* lesson_16.cu:597 */
+	float lim = fminf(r2, 99999992.0f);
+	float qx = 0.0f, qy = 0.0f, qz = 0.0f;
+	float4 pn = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	int ix = 0, iy = 0, iz = 0;
+	bool active = false;
+	if (qi < n_second && nb > 0 && cap > 0) {
+		const float4 p = __ldg(q_xyzl + qi);
+		pn = __ldg(q_nrm + qi);
+		qx = p.x; qy = p.y; qz = p.z;
+		label = __float_as_int(p.w);
+		/* lesson_16.cu:562-583 */
+		if (!(qx < mnx || qx > gp->bounding_box_max_X || qy < mny || qy > gp->bounding_box_max_Y || qz < mnz || qz > gp->bounding_box_max_Z)) {
+			ix = cell_of(qx, mnx, res_x); iy = cell_of(qy, mny, res_y); iz = cell_of(qz, mnz, res_z);
+			const int home = ix * nby * nbz + iy * nbz + iz;
+			active = home >= 0 && (long long)home < nb && lim >= 0.0f;
+		}
+	}
+	if (!nn_columns_usable(nbx, nby, nbz)) {                            /* warp-uniform */
+		if (active) best_l = nn_query_fallback(gp, buckets, cs.xyzl, cs.nrm, cs.tab, search_radius, cap, prune ? 1 : 0,
+				make_float4(qx, qy, qz, __int_as_float(label)), pn, &evals);
+		active = false;
+	}
+	/* the 27-neighbourhood with edge clamping (lesson_16.cu:588-608), as a box of fine columns */
+	const int cx0 = (ix > 0 ? ix - 1 : ix) << 2, cx1 = ((ix != nbx - 1 ? ix + 1 : ix) << 2) + 3;
+	const int cy0 = (iy > 0 ? iy - 1 : iy) << 2, cy1 = ((iy != nby - 1 ? iy + 1 : iy) << 2) + 3;
+	const int cz0 = (iz > 0 ? iz - 1 : iz) << 2, cz1 = ((iz != nbz - 1 ? iz + 1 : iz) << 2) + 3;
+	const float mgx = f_fma(f_mul(fabsf(qx) + fabsf(mnx), iwx), 3.814697265625e-06f, 9.765625e-04f);
+	const float mgy = f_fma(f_mul(fabsf(qy) + fabsf(mny), iwy), 3.814697265625e-06f, 9.765625e-04f);
+	const float mgz = f_fma(f_mul(fabsf(qz) + fabsf(mnz), iwz), 3.814697265625e-06f, 9.765625e-04f);
+
+	unsigned todo = __ballot_sync(full, active);
+	while (todo) {                                                      /* one pass per label present in the warp (almost always one) */
+		const int L = __shfl_sync(full, label, __ffs(todo) - 1);
+		const bool mine = active && label == L;
+		bool unsettled = mine;
+		todo &= ~__ballot_sync(full, mine);
+		int hxl = 1, hxh = 0, hyl = 1, hyh = 0, hzl = 1, hzh = 0;      /* previous round's hull (empty) */
+		float rho2 = rho2_first;
+		for (int round = 0; round < 80; round++) {
+			if (!__any_sync(full, unsettled)) break;
+			int xl = 0x7fffffff, xh = -0x7fffffff, yl = 0x7fffffff, yh = -0x7fffffff, zl = 0x7fffffff, zh = -0x7fffffff;
+			if (unsettled) {                                            /* exactly nn_query()'s box */
+				const float tau = prune ? fminf(lim, rho2) : lim;
+				const float R = prune ? f_add_up(f_mul_up(f_sqrt_up(tau), 1.00000095367431640625f), 1.0e-18f) : INFINITY;
+				xl = col_floor(f_sub(qx, R), mnx, iwx, mgx); xh = col_ceil(f_add(qx, R), mnx, iwx, mgx);
+				yl = col_floor(f_sub(qy, R), mny, iwy, mgy); yh = col_ceil(f_add(qy, R), mny, iwy, mgy);
+				zl = col_floor(f_sub(qz, R), mnz, iwz, mgz); zh = col_ceil(f_add(qz, R), mnz, iwz, mgz);
+				xl = xl > cx0 ? xl : cx0; xh = xh < cx1 ? xh : cx1;
+				yl = yl > cy0 ? yl : cy0; yh = yh < cy1 ? yh : cy1;
+				zl = zl > cz0 ? zl : cz0; zh = zh < cz1 ? zh : cz1;
+				if (xl > xh || yl > yh || zl > zh) { xl = yl = zl = 0x7fffffff; xh = yh = zh = -0x7fffffff; }
+			}
+			const int uxl = __reduce_min_sync(full, xl), uxh = __reduce_max_sync(full, xh);
+			const int uyl = __reduce_min_sync(full, yl), uyh = __reduce_max_sync(full, yh);
+			const int uzl = __reduce_min_sync(full, zl), uzh = __reduce_max_sync(full, zh);
+			if (uxl <= uxh) {
+				const int dx = uxh - uxl + 1, dy = uyh - uyl + 1, dz = uzh - uzl + 1;
+				const long long ncell = (long long)dx * dy * dz;
+				const int own = xl <= xh ? (xh - xl + 1) * (yh - yl + 1) * (zh - zl + 1) : 0;
+				const int own_max = __reduce_max_sync(full, own);
+				if (dx > kNNCells || dy > 32767 || dz > 32767 || (ncell > 512 && ncell > 4LL * own_max)) {   /* scattered warp: per-lane search from scratch */
+					if (unsettled) best_l = nn_query_fallback(gp, buckets, cs.xyzl, cs.nrm, cs.tab, search_radius, cap, prune ? 1 : 0,
+							make_float4(qx, qy, qz, __int_as_float(label)), pn, &evals);
+					unsettled = false;
+					break;
+				}
+				/* may every lane look at every bucket the hull touches? (always, unless the radius exceeds the bucket size) */
+				const bool nb_all = __all_sync(full, !mine || (uxl >= cx0 && uxh <= cx1 && uyl >= cy0 && uyh <= cy1 && uzl >= cz0 && uzh <= cz1));
+				const int nrows = dy * dz, rpc = __float2int_rz(__fdividef((float)kNNCells + 0.5f, (float)dx));   /* = kNNCells / dx for 1 <= dx <= kNNCells */
+				const float inv_dx = __frcp_rn((float)dx), inv_dy = __frcp_rn((float)dy);
+				for (int row0 = 0; row0 < nrows; row0 += rpc) {
+					const int nr = nrows - row0 < rpc ? nrows - row0 : rpc;
+					const int ncc = nr * dx;
+					/* 2. look up the hull cells of rows [row0, row0 + nr), row = (z - uzl) * dy + (y - uyl); list the non-empty bins */
+					int nseg = 0;
+					for (int c0 = 0; c0 < ncc; c0 += 32) {
+						const int c = c0 + lane;
+						int start = 0, cnt = 0, rel_xy = 0, rel_z = 0;
+						if (c < ncc) {
+							const int rr = __float2int_rz(((float)c + 0.5f) * inv_dx);
+							const int ax = c - rr * dx;
+							const int r = row0 + rr;
+							const int az = __float2int_rz(((float)r + 0.5f) * inv_dy);
+							const int ay = r - az * dy;
+							const int gx = uxl + ax, gy = uyl + ay, gz = uzl + az;
+							const bool in_old = gx >= hxl && gx <= hxh && gy >= hyl && gy <= hyh && gz >= hzl && gz <= hzh;
+							if (!in_old) {
+								const int cell = ((gx >> 2) * nby + (gy >> 2)) * nbz + (gz >> 2);
+								const int *rec = reinterpret_cast<const int *>(buckets + cell);
+								const int npts = __ldg(rec + 2), begin = __ldg(rec);
+								if (npts > 0 && begin >= 0) {           /* lesson_16.cu:615-616 (also the quirk bucket) */
+									const int level = tables ? nn_level(npts) : -1;
+									const int sh = level < 0 ? 2 : 2 - level;
+									const int am = (1 << sh) - 1;
+									const bool rep = (ax == 0 || !(gx & am)) && (ay == 0 || !(gy & am)) && (az == 0 || !(gz & am));
+									if (rep) {
+										if (level < 0) {                /* no table: the whole bucket, in walk order */
+											const int iter = candidate_stride(npts, cap);
+											start = begin; cnt = (npts + iter - 1) / iter;
+										} else {
+											const int bin = nn_bin(L, (gx & 3) >> sh, (gy & 3) >> sh, (gz & 3) >> sh, level);
+											const unsigned short *tab = cs.tab + 2 * (size_t)begin + bin;
+											const int s = __ldg(tab), e = __ldg(tab + 1);
+											start = begin + s; cnt = e - s;
+										}
+										rel_xy = ax | (ay << 16); rel_z = az;
+									}
+								}
+							}
+						}
+						const unsigned m = __ballot_sync(full, cnt > 0);
+						if (cnt > 0) segs[nseg + __popc(m & lt_mask)] = make_int4(start, cnt, rel_xy, rel_z);
+						nseg += __popc(m);
+					}
+					__syncwarp();
+					/* 3./4. batches of at most kNNStage staged candidates */
+					int k0 = 0;
+					while (k0 < nseg) {
+						/* lane k owns segment k0 + k: padded sizes, inclusive scan, how many segments fit */
+						int4 sg = make_int4(0, 0, 0, 0);
+						if (k0 + lane < nseg) sg = segs[k0 + lane];
+						const int padded = (sg.y + 3) & ~3;
+						int incl = padded;
+#pragma unroll
+						for (int o = 1; o < 32; o <<= 1) {
+							const int t = __shfl_up_sync(full, incl, o);
+							if (lane >= o) incl += t;
+						}
+						const unsigned fit = __ballot_sync(full, k0 + lane < nseg && incl <= kNNStage);
+						int ntake = __popc(fit);                        /* segments are taken in order: fit is a prefix mask */
+						int ncand;
+						if (ntake == 0) {                               /* the first segment alone exceeds a batch: take a part of it */
+							const int4 s0 = segs[k0];
+							__syncwarp();
+							if (lane == 0) segs[k0] = make_int4(s0.x + kNNStage, s0.y - kNNStage, s0.z, s0.w);
+							if (lane < kNNStage / 4) grp[lane] = make_int4(s0.x + 4 * lane, 4, s0.z, s0.w);
+							if (lane + 32 < kNNStage / 4) grp[lane + 32] = make_int4(s0.x + 4 * (lane + 32), 4, s0.z, s0.w);
+							ncand = kNNStage;
+						} else {
+							ncand = __shfl_sync(full, incl, ntake - 1);
+							if (lane < ntake) {                         /* group records of the lane's own segment */
+								const int g0 = (incl - padded) >> 2, ng = padded >> 2;
+								for (int g = 0; g < ng; g++) {
+									const int left = sg.y - 4 * g;
+									grp[g0 + g] = make_int4(sg.x + 4 * g, left < 4 ? left : 4, sg.z, sg.w);
+								}
+							}
+							k0 += ntake;
+						}
+						__syncwarp();
+						/* flat, coalesced copy: slot t belongs to group t / 4 (all loads independent, in flight together) */
+#pragma unroll 2
+						for (int t = lane; t < ncand; t += 32) {
+							const int4 gi = grp[t >> 2];
+							stage[t] = (t & 3) < gi.y ? __ldg(cx + gi.x + (t & 3)) : make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(kNNNone));
+						}
+						__syncwarp();
+						const int ngrp = ncand >> 2;
+						/* branch-free minimum over every staged candidate */
+						float rb = mine ? lim : -INFINITY;
+						int bg = -1;
+						bool flag = false;
+						if (nb_all) {
+							if (mine) evals += (unsigned int)ncand;
+#pragma unroll 2
+							for (int g = 0; g < ngrp; g++) {
+								const float4 c0 = stage[4 * g], c1 = stage[4 * g + 1], c2 = stage[4 * g + 2], c3 = stage[4 * g + 3];
+								const float d0 = nn_dist(qx, qy, qz, c0), d1 = nn_dist(qx, qy, qz, c1), d2 = nn_dist(qx, qy, qz, c2),
+										d3 = nn_dist(qx, qy, qz, c3);
+								const float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
+								const bool lt = m4 < rb;
+								flag = flag || (m4 == rb);
+								rb = lt ? m4 : rb; bg = lt ? g : bg;
+							}
+						} else {
+							for (int g = 0; g < ngrp; g++) {
+								const int4 gi = grp[g];
+								const int gx = uxl + (gi.z & 0xffff), gy = uyl + (gi.z >> 16), gz = uzl + gi.w;
+								const bool use = gx >= cx0 && gx <= cx1 && gy >= cy0 && gy <= cy1 && gz >= cz0 && gz <= cz1;
+								if (mine && use) evals += 4u;
+								const float4 c0 = stage[4 * g], c1 = stage[4 * g + 1], c2 = stage[4 * g + 2], c3 = stage[4 * g + 3];
+								const float d0 = nn_dist(qx, qy, qz, c0), d1 = nn_dist(qx, qy, qz, c1), d2 = nn_dist(qx, qy, qz, c2),
+										d3 = nn_dist(qx, qy, qz, c3);
+								float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
+								m4 = use ? m4 : INFINITY;
+								const bool lt = m4 < rb;
+								flag = flag || (m4 == rb);
+								rb = lt ? m4 : rb; bg = lt ? g : bg;
+							}
+						}
+						/* full predicate on the winning group; a tie between groups or an inadmissible winner needs the re-scan */
+						if (bg >= 0) {
+							const int j = grp[bg].x;
+							const float4 c0 = stage[4 * bg], c1 = stage[4 * bg + 1], c2 = stage[4 * bg + 2], c3 = stage[4 * bg + 3];
+							const float d0 = nn_dist(qx, qy, qz, c0), d1 = nn_dist(qx, qy, qz, c1), d2 = nn_dist(qx, qy, qz, c2),
+									d3 = nn_dist(qx, qy, qz, c3);
+							M3D_NN_CONSIDER(d0, c0, j)
+							M3D_NN_CONSIDER(d1, c1, j + 1)
+							M3D_NN_CONSIDER(d2, c2, j + 2)
+							M3D_NN_CONSIDER(d3, c3, j + 3)
+							if (best_d != rb) flag = true;
+						}
+						if (__any_sync(full, flag)) {
+							for (int g = 0; g < ngrp; g++) {
+								const int4 gi = grp[g];
+								const int gx = uxl + (gi.z & 0xffff), gy = uyl + (gi.z >> 16), gz = uzl + gi.w;
+								const bool use = flag && mine && gx >= cx0 && gx <= cx1 && gy >= cy0 && gy <= cy1 && gz >= cz0 && gz <= cz1;
+								if (use) {
+#pragma unroll
+									for (int t = 0; t < 4; t++) {
+										const float4 c0 = stage[4 * g + t];
+										const float d0 = nn_dist(qx, qy, qz, c0);
+										M3D_NN_CONSIDER(d0, c0, gi.x + t)
+									}
+								}
+							}
+						}
+						__syncwarp();
+					}
+				}
+				hxl = uxl; hxh = uxh; hyl = uyl; hyh = uyh; hzl = uzl; hzh = uzh;
+			}
+			if (unsettled && (!prune || lim <= rho2)) unsettled = false;   /* everything at or below the limit was inside this round's box */
+			rho2 = f_mul(rho2, 4.0f);
+		}
+	}
+#undef M3D_NN_CONSIDER
+
+	int result = -1;
+	if (best_l != kNNNone && best_l >= 0 && best_l < n_first) result = (int)__ldg(s_vals + best_l);
+	if (qi < n_second) {
+		if (nn_seq) nn_seq[qi] = result;
+		nn_out[q_perm ? __ldg(q_perm + qi) : (uint32_t)qi] = result;
+	}
+	if (eval_counter) {
+		unsigned int tot = __reduce_add_sync(full, evals);
+		if (lane == 0 && tot) atomicAdd(eval_counter, (unsigned long long)tot);
+	}
+	if (label_counts) {   /* per-label match counts (gpu6DSLAM.cpp:323-357): warp ballots, one atomic per label per warp */
+		bool hit = qi < n_second && result >= 0;
+#pragma unroll
+		for (int Lb = 0; Lb < 4; Lb++) {
+			unsigned m = __ballot_sync(full, hit && label == Lb);
+			if (m && lane == Lb) atomicAdd(&label_counts[Lb], (unsigned long long)__popc(m));
+		}
+	}
+}
+
 /* gather a stored scan into query order: out[i] = in[perm[i]] */
 __global__ void k_gather_perm(const uint32_t *__restrict__ perm, int n, const float4 *__restrict__ in_xyzl, const float4 *__restrict__ in_nrm,
 		float4 *__restrict__ out_xyzl, float4 *__restrict__ out_nrm)
