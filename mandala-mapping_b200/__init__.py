@@ -23,7 +23,7 @@ from .synth import BUCKET_DTYPE, GRID_PARAMS_DTYPE, HASH_DTYPE, OBS_DTYPE, POINT
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libm3dreg.so")
+LIB_PATH = os.environ.get("M3DREG_LIB_PATH") or os.path.join(_HERE, "libm3dreg.so")   # override: tuning builds only
 CSRC = os.path.join(_HERE, "csrc")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 

@@ -311,7 +311,7 @@ void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *va
 {
 	bool two = max_inner != max_outer;
 	if (!two && !c->nn_per_thread) {     /* one candidate set (the reference's default caps): warp-shared lookup grid */
-		LAUNCH(c, k_nn_search_grid, (n2 + kNNThreads - 1) / kNNThreads, kNNThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
+		LAUNCH(c, k_nn_search_grid, (n2 + kNNGThreads - 1) / kNNGThreads, kNNGThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
 				cand_set(c, false), vals, n1, buckets, c->gp, radius, max_outer, (prune && c->nn_rho_div > 1) ? c->nn_rho_div : prune, nn_out, nn_seq, label_counts, c->eval_counter);
 		return;
 	}

@@ -819,9 +819,42 @@ __global__ void __launch_bounds__(kNNThreads) k_nn_search(const float4 *__restri
  * are processed in chunks of whole (y,z) rows; warps whose queries are scattered (hull much larger than the lanes' own
  * boxes) and grids beyond the column arithmetic fall back to nn_query().
  * Requires one candidate set (INNER cap == OUTER cap, the reference's default). */
+#ifndef M3D_NNG_THREADS
+#define M3D_NNG_THREADS 64
+#endif
+#ifndef M3D_NNG_MINBLOCKS
+#define M3D_NNG_MINBLOCKS 12
+#endif
 constexpr int kNNCells = 128;       /* hull cells looked up per chunk (segment list capacity) */
 constexpr int kNNStage = 192;       /* candidates staged per batch (multiple of 4) */
-constexpr int kNNWarps = kNNThreads / 32;
+constexpr int kNNGThreads = M3D_NNG_THREADS;
+constexpr int kNNWarps = kNNGThreads / 32;
+
+/* Packed f32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2): two IEEE round-to-nearest operations per instruction, each
+ * component rounded exactly like the scalar sub.rn / mul.rn / fma.rn the reference's distance is made of. */
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b)
+{
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+	return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float &a, float &b)
+{
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+/* {dist(q, c_a), dist(q, c_b)} with dist = fma(dz,dz, fma(dx,dx, dy*dy)) (lesson_16.cu:658-660) */
+__device__ __forceinline__ unsigned long long nn_dist2(unsigned long long qx2, unsigned long long qy2, unsigned long long qz2,
+		unsigned long long x2, unsigned long long y2, unsigned long long z2)
+{
+	unsigned long long dx, dy, dz, t;
+	asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(qx2), "l"(x2));
+	asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(qy2), "l"(y2));
+	asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(qz2), "l"(z2));
+	asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(t) : "l"(dy));
+	asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dx), "l"(t));
+	asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dz), "l"(t));
+	return t;
+}
 
 __device__ __noinline__ int nn_query_fallback(const m3dreg_grid_params *__restrict__ gp, const m3dreg_bucket *__restrict__ buckets,
 		const float4 *cxyzl, const float4 *cnrm, const unsigned short *ctab, float search_radius, int cap, int prune, float4 p, float4 pn,
@@ -857,7 +890,7 @@ __device__ __noinline__ int nn_query_fallback(const m3dreg_grid_params *__restri
 		}                                                                                                               \
 	}
 
-__global__ void __launch_bounds__(kNNThreads, 5) k_nn_search_grid(const float4 *__restrict__ q_xyzl, const float4 *__restrict__ q_nrm,
+__global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_grid(const float4 *__restrict__ q_xyzl, const float4 *__restrict__ q_nrm,
 		const uint32_t *__restrict__ q_perm, int n_second, CandSet cs,
 		const uint32_t *__restrict__ s_vals, int n_first,
 		const m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp,
@@ -866,13 +899,14 @@ __global__ void __launch_bounds__(kNNThreads, 5) k_nn_search_grid(const float4 *
 		unsigned long long *__restrict__ eval_counter)
 {
 	__shared__ int4 s_segs[kNNWarps][kNNCells];                /* {first candidate, count, hull cell x | y << 16, hull cell z} */
-	__shared__ float4 s_cand[kNNWarps][kNNStage];              /* staged candidates {x, y, z, l bits}, groups of four */
+	__shared__ float4 s_cand[kNNWarps][kNNStage];              /* staged candidates, per group of four: {x0..x3}, {y0..y3}, {z0..z3}, {l0..l3} */
 	__shared__ int4 s_grp[kNNWarps][kNNStage / 4];             /* per group: {index of its first candidate, -, hull cell x | y << 16, z} */
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	const unsigned lt_mask = (1u << lane) - 1u;
 	int4 *segs = s_segs[threadIdx.x >> 5];
 	float4 *stage = s_cand[threadIdx.x >> 5];
+	float *stagef = reinterpret_cast<float *>(stage);
 	int4 *grp = s_grp[threadIdx.x >> 5];
 	const int qi = blockIdx.x * blockDim.x + threadIdx.x;
 	/* grid and search parameters (same expressions as nn_params_finish) */
@@ -925,6 +959,18 @@ __global__ void __launch_bounds__(kNNThreads, 5) k_nn_search_grid(const float4 *
 	const float mgy = f_fma(f_mul(fabsf(qy) + fabsf(mny), iwy), 3.814697265625e-06f, 9.765625e-04f);
 	const float mgz = f_fma(f_mul(fabsf(qz) + fabsf(mnz), iwz), 3.814697265625e-06f, 9.765625e-04f);
 
+	/* every candidate with dist <= tau lies in the box of fine columns this returns (nn_query()'s box: conservative
+	 * column bounds of [q - R, q + R], R >= sqrt(tau) rounded outwards, clamped to the lane's 27-neighbourhood) */
+	auto fine_box = [&](float tau, int &xl, int &xh, int &yl, int &yh, int &zl, int &zh) {
+		const float R = prune ? f_add_up(f_mul_up(f_sqrt_up(tau), 1.00000095367431640625f), 1.0e-18f) : INFINITY;
+		xl = col_floor(f_sub(qx, R), mnx, iwx, mgx); xh = col_ceil(f_add(qx, R), mnx, iwx, mgx);
+		yl = col_floor(f_sub(qy, R), mny, iwy, mgy); yh = col_ceil(f_add(qy, R), mny, iwy, mgy);
+		zl = col_floor(f_sub(qz, R), mnz, iwz, mgz); zh = col_ceil(f_add(qz, R), mnz, iwz, mgz);
+		xl = xl > cx0 ? xl : cx0; xh = xh < cx1 ? xh : cx1;
+		yl = yl > cy0 ? yl : cy0; yh = yh < cy1 ? yh : cy1;
+		zl = zl > cz0 ? zl : cz0; zh = zh < cz1 ? zh : cz1;
+	};
+
 	unsigned todo = __ballot_sync(full, active);
 	while (todo) {                                                      /* one pass per label present in the warp (almost always one) */
 		const int L = __shfl_sync(full, label, __ffs(todo) - 1);
@@ -936,15 +982,8 @@ __global__ void __launch_bounds__(kNNThreads, 5) k_nn_search_grid(const float4 *
 		for (int round = 0; round < 80; round++) {
 			if (!__any_sync(full, unsettled)) break;
 			int xl = 0x7fffffff, xh = -0x7fffffff, yl = 0x7fffffff, yh = -0x7fffffff, zl = 0x7fffffff, zh = -0x7fffffff;
-			if (unsettled) {                                            /* exactly nn_query()'s box */
-				const float tau = prune ? fminf(lim, rho2) : lim;
-				const float R = prune ? f_add_up(f_mul_up(f_sqrt_up(tau), 1.00000095367431640625f), 1.0e-18f) : INFINITY;
-				xl = col_floor(f_sub(qx, R), mnx, iwx, mgx); xh = col_ceil(f_add(qx, R), mnx, iwx, mgx);
-				yl = col_floor(f_sub(qy, R), mny, iwy, mgy); yh = col_ceil(f_add(qy, R), mny, iwy, mgy);
-				zl = col_floor(f_sub(qz, R), mnz, iwz, mgz); zh = col_ceil(f_add(qz, R), mnz, iwz, mgz);
-				xl = xl > cx0 ? xl : cx0; xh = xh < cx1 ? xh : cx1;
-				yl = yl > cy0 ? yl : cy0; yh = yh < cy1 ? yh : cy1;
-				zl = zl > cz0 ? zl : cz0; zh = zh < cz1 ? zh : cz1;
+			if (unsettled) {
+				fine_box(prune ? fminf(lim, rho2) : lim, xl, xh, yl, yh, zl, zh);
 				if (xl > xh || yl > yh || zl > zh) { xl = yl = zl = 0x7fffffff; xh = yh = zh = -0x7fffffff; }
 			}
 			const int uxl = __reduce_min_sync(full, xl), uxh = __reduce_max_sync(full, xh);
@@ -1045,11 +1084,14 @@ __global__ void __launch_bounds__(kNNThreads, 5) k_nn_search_grid(const float4 *
 							k0 += ntake;
 						}
 						__syncwarp();
-						/* flat, coalesced copy: slot t belongs to group t / 4 (all loads independent, in flight together) */
+						/* flat, coalesced copy: slot t belongs to group t / 4 (all loads independent, in flight together);
+						 * a group is stored transposed so that the hot loop reads coordinate pairs as 64-bit registers */
 #pragma unroll 2
 						for (int t = lane; t < ncand; t += 32) {
 							const int4 gi = grp[t >> 2];
-							stage[t] = (t & 3) < gi.y ? __ldg(cx + gi.x + (t & 3)) : make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(kNNNone));
+							const float4 cv = (t & 3) < gi.y ? __ldg(cx + gi.x + (t & 3)) : make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(kNNNone));
+							float *dst = stagef + ((t >> 2) << 4) + (t & 3);
+							dst[0] = cv.x; dst[4] = cv.y; dst[8] = cv.z; dst[12] = cv.w;
 						}
 						__syncwarp();
 						const int ngrp = ncand >> 2;
@@ -1057,13 +1099,15 @@ __global__ void __launch_bounds__(kNNThreads, 5) k_nn_search_grid(const float4 *
 						float rb = mine ? lim : -INFINITY;
 						int bg = -1;
 						bool flag = false;
+						const unsigned long long qx2 = f2_pack(qx, qx), qy2 = f2_pack(qy, qy), qz2 = f2_pack(qz, qz);
 						if (nb_all) {
 							if (mine) evals += (unsigned int)ncand;
 #pragma unroll 2
 							for (int g = 0; g < ngrp; g++) {
-								const float4 c0 = stage[4 * g], c1 = stage[4 * g + 1], c2 = stage[4 * g + 2], c3 = stage[4 * g + 3];
-								const float d0 = nn_dist(qx, qy, qz, c0), d1 = nn_dist(qx, qy, qz, c1), d2 = nn_dist(qx, qy, qz, c2),
-										d3 = nn_dist(qx, qy, qz, c3);
+								const float4 X = stage[4 * g], Y = stage[4 * g + 1], Z = stage[4 * g + 2];
+								float d0, d1, d2, d3;
+								f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.x, X.y), f2_pack(Y.x, Y.y), f2_pack(Z.x, Z.y)), d0, d1);
+								f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.z, X.w), f2_pack(Y.z, Y.w), f2_pack(Z.z, Z.w)), d2, d3);
 								const float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
 								const bool lt = m4 < rb;
 								flag = flag || (m4 == rb);
@@ -1075,9 +1119,10 @@ __global__ void __launch_bounds__(kNNThreads, 5) k_nn_search_grid(const float4 *
 								const int gx = uxl + (gi.z & 0xffff), gy = uyl + (gi.z >> 16), gz = uzl + gi.w;
 								const bool use = gx >= cx0 && gx <= cx1 && gy >= cy0 && gy <= cy1 && gz >= cz0 && gz <= cz1;
 								if (mine && use) evals += 4u;
-								const float4 c0 = stage[4 * g], c1 = stage[4 * g + 1], c2 = stage[4 * g + 2], c3 = stage[4 * g + 3];
-								const float d0 = nn_dist(qx, qy, qz, c0), d1 = nn_dist(qx, qy, qz, c1), d2 = nn_dist(qx, qy, qz, c2),
-										d3 = nn_dist(qx, qy, qz, c3);
+								const float4 X = stage[4 * g], Y = stage[4 * g + 1], Z = stage[4 * g + 2];
+								float d0, d1, d2, d3;
+								f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.x, X.y), f2_pack(Y.x, Y.y), f2_pack(Z.x, Z.y)), d0, d1);
+								f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.z, X.w), f2_pack(Y.z, Y.w), f2_pack(Z.z, Z.w)), d2, d3);
 								float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
 								m4 = use ? m4 : INFINITY;
 								const bool lt = m4 < rb;
@@ -1088,7 +1133,9 @@ __global__ void __launch_bounds__(kNNThreads, 5) k_nn_search_grid(const float4 *
 						/* full predicate on the winning group; a tie between groups or an inadmissible winner needs the re-scan */
 						if (bg >= 0) {
 							const int j = grp[bg].x;
-							const float4 c0 = stage[4 * bg], c1 = stage[4 * bg + 1], c2 = stage[4 * bg + 2], c3 = stage[4 * bg + 3];
+							const float4 X = stage[4 * bg], Y = stage[4 * bg + 1], Z = stage[4 * bg + 2], Lw = stage[4 * bg + 3];
+							const float4 c0 = make_float4(X.x, Y.x, Z.x, Lw.x), c1 = make_float4(X.y, Y.y, Z.y, Lw.y),
+									c2 = make_float4(X.z, Y.z, Z.z, Lw.z), c3 = make_float4(X.w, Y.w, Z.w, Lw.w);
 							const float d0 = nn_dist(qx, qy, qz, c0), d1 = nn_dist(qx, qy, qz, c1), d2 = nn_dist(qx, qy, qz, c2),
 									d3 = nn_dist(qx, qy, qz, c3);
 							M3D_NN_CONSIDER(d0, c0, j)
@@ -1105,7 +1152,8 @@ __global__ void __launch_bounds__(kNNThreads, 5) k_nn_search_grid(const float4 *
 								if (use) {
 #pragma unroll
 									for (int t = 0; t < 4; t++) {
-										const float4 c0 = stage[4 * g + t];
+										const float *src = stagef + (g << 4) + t;
+										const float4 c0 = make_float4(src[0], src[4], src[8], src[12]);
 										const float d0 = nn_dist(qx, qy, qz, c0);
 										M3D_NN_CONSIDER(d0, c0, gi.x + t)
 									}
@@ -1116,6 +1164,13 @@ __global__ void __launch_bounds__(kNNThreads, 5) k_nn_search_grid(const float4 *
 					}
 				}
 				hxl = uxl; hxh = uxh; hyl = uyl; hyh = uyh; hzl = uzl; hzh = uzh;
+				/* every cell of this hull has now been evaluated by all lanes (in this round or, for the cells skipped as
+				 * part of the previous hull, before): a lane whose box for its CURRENT limit lies inside the hull is done */
+				if (unsettled && prune && lim > rho2) {
+					int bxl, bxh, byl, byh, bzl, bzh;
+					fine_box(lim, bxl, bxh, byl, byh, bzl, bzh);
+					if (bxl >= uxl && bxh <= uxh && byl >= uyl && byh <= uyh && bzl >= uzl && bzh <= uzh) unsettled = false;
+				}
 			}
 			if (unsettled && (!prune || lim <= rho2)) unsettled = false;   /* everything at or below the limit was inside this round's box */
 			rho2 = f_mul(rho2, 4.0f);
