@@ -109,7 +109,7 @@ struct m3dreg_ctx {
 	unsigned int *cell_count = nullptr;           /* number of searchable buckets in the compact list */
 	unsigned long long *eval_counter = nullptr;   /* candidates staged by the NN search (warp-level), diagnostic */
 	int nn_per_thread = 0;       /* test switch (env M3DREG_NN_PER_THREAD=1): k_nn_search instead of k_nn_search_grid */
-	int nn_rho_div = 0;          /* tuning (env M3DREG_NN_RHO_DIV): first-round radius = res / div */
+	NNTuning nn_tune = {16, 128, 8};   /* heuristics of k_nn_search_grid (env M3DREG_NN_RHO_DIV / _HULL_MIN / _HULL_RATIO override) */
 	double *scratch = nullptr;   /* 64 doubles */
 	float *mats = nullptr;       /* 32 floats  */
 	HostSmall *h = nullptr;      /* pinned */
@@ -302,7 +302,7 @@ void build_candidates(m3dreg_ctx *c, const uint32_t *vals, const m3dreg_bucket *
 		const float4 *src_xyzl, const float4 *src_nrm, const float *nrm_m, int max_inner, int max_outer)
 {
 	bool two = max_inner != max_outer;
-	LAUNCH(c, k_build_candidates, c->sm_count * 8, kBuildWarps * 32, vals, c->gp, buckets, cell_list, c->cell_count, src_xyzl, src_nrm, nrm_m,
+	LAUNCH(c, k_build_candidates, c->sm_count * 7, kBuildWarps * 32, vals, c->gp, buckets, cell_list, c->cell_count, src_xyzl, src_nrm, nrm_m,
 			max_inner, max_outer, cand_set(c, false), cand_set(c, two), two ? 1 : 0);
 }
 
@@ -312,7 +312,7 @@ void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *va
 	bool two = max_inner != max_outer;
 	if (!two && !c->nn_per_thread) {     /* one candidate set (the reference's default caps): warp-shared lookup grid */
 		LAUNCH(c, k_nn_search_grid, (n2 + kNNGThreads - 1) / kNNGThreads, kNNGThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
-				cand_set(c, false), vals, n1, buckets, c->gp, radius, max_outer, (prune && c->nn_rho_div > 1) ? c->nn_rho_div : prune, nn_out, nn_seq, label_counts, c->eval_counter);
+				cand_set(c, false), vals, n1, buckets, c->gp, radius, max_outer, prune, c->nn_tune, nn_out, nn_seq, label_counts, c->eval_counter);
 		return;
 	}
 	LAUNCH(c, k_nn_search, (n2 + kNNThreads - 1) / kNNThreads, kNNThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
@@ -508,7 +508,9 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	c->dev = cuda_device;
 	c->sm_count = prop.multiProcessorCount;
 	{ const char *e = getenv("M3DREG_NN_PER_THREAD"); c->nn_per_thread = (e && e[0] == '1') ? 1 : 0; }
-	{ const char *e = getenv("M3DREG_NN_RHO_DIV"); c->nn_rho_div = e ? atoi(e) : 0; }
+	{ const char *e = getenv("M3DREG_NN_RHO_DIV"); if (e && atoi(e) > 0) c->nn_tune.rho_div = atoi(e); }
+	{ const char *e = getenv("M3DREG_NN_HULL_MIN"); if (e && atoi(e) > 0) c->nn_tune.hull_min = atoi(e); }
+	{ const char *e = getenv("M3DREG_NN_HULL_RATIO"); if (e && atoi(e) > 0) c->nn_tune.hull_ratio = atoi(e); }
 	cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
 	if (e != cudaSuccess) { delete c; return (int)e; }
 	c->stream = c->own_stream;

@@ -580,7 +580,7 @@ __global__ void k_list_cells(const uint32_t *__restrict__ keys, int n, const m3d
  * bin candidates keep ascending sorted position (stable counting sort).  Each record carries its sorted position l
  * for the tie-break and the result.  Two sets exist when the INNER and OUTER caps differ (different strides). */
 constexpr int kBuildWarps = 4;
-constexpr int kBuildPerLane = 8;          /* candidates per lane held in registers (256 per warp pass) */
+constexpr int kBuildPerLane = 7;          /* candidates per lane held in registers (224 per warp pass >= 2 * 100 - 1, the default caps) */
 constexpr int kBuildTabMax = 4 * 64 + 1;   /* bins + 1 at the finest level */
 
 struct NormalRotation { float r[9]; int on; };   /* rotation applied to the candidates' normals (same rounding as the transform kernels) */
@@ -605,25 +605,29 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 		__syncwarp();
 	}
 	const bool single = ncand <= 32 * kBuildPerLane;
-	float4 p[kBuildPerLane], nr[kBuildPerLane];
+	/* per candidate only its table value and its bin stay in registers (register pressure = resident warps, and this
+	 * kernel is a chain of dependent gathers); the point is re-read (L1/L2 hit) together with the normal when stored */
+	uint32_t v[kBuildPerLane], bin[kBuildPerLane];
 	auto load = [&](int c0) {
-		uint32_t v[kBuildPerLane];
 #pragma unroll
 		for (int j = 0; j < kBuildPerLane; j++) {
 			int k = c0 + j * 32 + lane;
 			v[j] = k < ncand ? __ldg(vals + begin + k * iter) : 0u;
 		}
+		float4 p[kBuildPerLane];
+#pragma unroll
+		for (int j = 0; j < kBuildPerLane; j++) p[j] = __ldg(src_xyzl + v[j]);      /* v = 0 past the end: a valid address */
 #pragma unroll
 		for (int j = 0; j < kBuildPerLane; j++) {
 			int k = c0 + j * 32 + lane;
-			if (k < ncand) { p[j] = __ldg(src_xyzl + v[j]); nr[j] = __ldg(src_nrm + v[j]); }
+			const int lv = level < 0 ? 0 : level;
+			int ux = nn_col(p[j].x, g.mnx, wx, g.cx, lv), uy = nn_col(p[j].y, g.mny, wy, g.cy, lv), uz = nn_col(p[j].z, g.mnz, wz, g.cz, lv);
+			bin[j] = k < ncand ? (uint32_t)nn_bin(__float_as_int(p[j].w), ux, uy, uz, lv) : 0x1000u + lane;
 		}
 	};
-	auto bin_of = [&](const float4 &c) {
-		int ux = nn_col(c.x, g.mnx, wx, g.cx, level), uy = nn_col(c.y, g.mny, wy, g.cy, level), uz = nn_col(c.z, g.mnz, wz, g.cz, level);
-		return (uint32_t)nn_bin(__float_as_int(c.w), ux, uy, uz, level);
-	};
-	auto store = [&](int pos, int k, const float4 &c, const float4 &n) {
+	auto store = [&](int pos, int k, uint32_t vi) {
+		const float4 c = __ldg(src_xyzl + vi);
+		const float4 n = __ldg(src_nrm + vi);
 		float4 nn = n;
 		if (rot.on) {
 			nn.x = __fmaf_rn(rot.r[2], n.z, __fmaf_rn(rot.r[0], n.x, __fmul_rn(rot.r[1], n.y)));
@@ -640,7 +644,7 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 #pragma unroll
 			for (int j = 0; j < kBuildPerLane; j++) {
 				int k = c0 + j * 32 + lane;
-				if (k < ncand) store(begin + k, k, p[j], nr[j]);
+				if (k < ncand) store(begin + k, k, v[j]);
 			}
 		}
 		return;
@@ -653,17 +657,16 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 			if (c0 + j * 32 >= ncand) break;
 			int k = c0 + j * 32 + lane;
 			bool valid = k < ncand;
-			uint32_t bin = valid ? bin_of(p[j]) : (0x1000u + lane);
-			uint32_t peers = __match_any_sync(full, bin);
-			if (valid && lane == __ffs(peers) - 1) hist[bin] += __popc(peers);
+			uint32_t peers = __match_any_sync(full, bin[j]);
+			if (valid && lane == __ffs(peers) - 1) hist[bin[j]] += __popc(peers);
 			__syncwarp();
 		}
 	}
 	/* exclusive scan of the nbins + 1 table entries (9 consecutive entries per lane cover 288 >= 257), table out */
 	{
-		uint32_t v[9], sum = 0;
+		uint32_t h[9], sum = 0;
 #pragma unroll
-		for (int k = 0; k < 9; k++) { int e = lane * 9 + k; v[k] = e < nbins ? hist[e] : 0u; sum += v[k]; }
+		for (int k = 0; k < 9; k++) { int e = lane * 9 + k; h[k] = e < nbins ? hist[e] : 0u; sum += h[k]; }
 		uint32_t incl = sum;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
@@ -677,7 +680,7 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 		for (int k = 0; k < 9; k++) {
 			int e = lane * 9 + k;
 			if (e <= nbins) { hist[e] = run; tab[e] = (unsigned short)run; }
-			run += v[k];
+			run += h[k];
 		}
 		__syncwarp();
 	}
@@ -689,13 +692,12 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 			if (c0 + j * 32 >= ncand) break;
 			int k = c0 + j * 32 + lane;
 			bool valid = k < ncand;
-			uint32_t bin = valid ? bin_of(p[j]) : (0x1000u + lane);
-			uint32_t peers = __match_any_sync(full, bin);
+			uint32_t peers = __match_any_sync(full, bin[j]);
 			int leader = __ffs(peers) - 1;
 			uint32_t old = 0;
-			if (valid && lane == leader) { old = hist[bin]; hist[bin] = old + __popc(peers); }
+			if (valid && lane == leader) { old = hist[bin[j]]; hist[bin[j]] = old + __popc(peers); }
 			old = __shfl_sync(full, old, leader);
-			if (valid) store(begin + (int)(old + __popc(peers & lt)), k, p[j], nr[j]);
+			if (valid) store(begin + (int)(old + __popc(peers & lt)), k, v[j]);
 			__syncwarp();
 		}
 	}
@@ -703,7 +705,7 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 }
 
 /* One warp per searchable bucket of the compact list k_finalize_grid / k_list_cells left behind. */
-__global__ void __launch_bounds__(kBuildWarps * 32) k_build_candidates(const uint32_t *__restrict__ vals,
+__global__ void __launch_bounds__(kBuildWarps * 32, 7) k_build_candidates(const uint32_t *__restrict__ vals,
 		const m3dreg_grid_params *__restrict__ gp, const m3dreg_bucket *__restrict__ buckets,
 		const uint32_t *__restrict__ cell_list, const unsigned int *__restrict__ cell_count,
 		const float4 *__restrict__ src_xyzl, const float4 *__restrict__ src_nrm, const float *__restrict__ nrm_m, int max_inner, int max_outer,
@@ -825,6 +827,9 @@ __global__ void __launch_bounds__(kNNThreads) k_nn_search(const float4 *__restri
 #ifndef M3D_NNG_MINBLOCKS
 #define M3D_NNG_MINBLOCKS 12
 #endif
+/* heuristics only (the answer is exact for any values): first-round radius = min(res) / rho_div; a warp whose hull has
+ * more than hull_min cells AND more than hull_ratio times its largest own box searches per lane instead */
+struct NNTuning { int rho_div, hull_min, hull_ratio; };
 constexpr int kNNCells = 128;       /* hull cells looked up per chunk (segment list capacity) */
 constexpr int kNNStage = 192;       /* candidates staged per batch (multiple of 4) */
 constexpr int kNNGThreads = M3D_NNG_THREADS;
@@ -894,7 +899,7 @@ __global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_gr
 		const uint32_t *__restrict__ q_perm, int n_second, CandSet cs,
 		const uint32_t *__restrict__ s_vals, int n_first,
 		const m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp,
-		float search_radius, int cap, int prune,
+		float search_radius, int cap, int prune, NNTuning tune,
 		int *__restrict__ nn_out, int *__restrict__ nn_seq, unsigned long long *__restrict__ label_counts,
 		unsigned long long *__restrict__ eval_counter)
 {
@@ -919,8 +924,7 @@ __global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_gr
 	const float iwx = f_div(4.0f, res_x), iwy = f_div(4.0f, res_y), iwz = f_div(4.0f, res_z);
 	float rho2_first;
 	{
-		const float rmin = prune > 1 ? f_div(fminf(res_x, fminf(res_y, res_z)), (float)prune)      /* tuning: min(res) / prune */
-				: f_mul(fminf(res_x, fminf(res_y, res_z)), 0.0625f);
+		const float rmin = f_div(fminf(res_x, fminf(res_y, res_z)), (float)(tune.rho_div > 0 ? tune.rho_div : 16));
 		rho2_first = fmaxf(f_mul(rmin, rmin), 1.0e-30f);
 	}
 	const float4 *__restrict__ cx = cs.xyzl;
@@ -994,7 +998,7 @@ __global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_gr
 				const long long ncell = (long long)dx * dy * dz;
 				const int own = xl <= xh ? (xh - xl + 1) * (yh - yl + 1) * (zh - zl + 1) : 0;
 				const int own_max = __reduce_max_sync(full, own);
-				if (dx > kNNCells || dy > 32767 || dz > 32767 || (ncell > 512 && ncell > 4LL * own_max)) {   /* scattered warp: per-lane search from scratch */
+				if (dx > kNNCells || dy > 32767 || dz > 32767 || (ncell > tune.hull_min && ncell > (long long)tune.hull_ratio * own_max)) {   /* scattered warp: per-lane search from scratch */
 					if (unsettled) best_l = nn_query_fallback(gp, buckets, cs.xyzl, cs.nrm, cs.tab, search_radius, cap, prune ? 1 : 0,
 							make_float4(qx, qy, qz, __int_as_float(label)), pn, &evals);
 					unsettled = false;
