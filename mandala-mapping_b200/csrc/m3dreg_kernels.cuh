@@ -1729,22 +1729,57 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(const Src src_
 	}
 	__syncthreads();
 	if (!is_last) return;
+#ifdef M3D_NEQ_TIMING
+	unsigned long long tq0, tq1, tq2, tq3;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq0));
+#endif
 	__threadfence();
 	/* deterministic final reduction: fixed row order */
 	__shared__ double tot[kMomentCount];
-	for (int col = wid; col < kMomentCount; col += kNeqThreads / 32) {     /* warp per column, lanes stride the rows */
-		double s = 0;
-		for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * kPartialCols + col);
-		s = warp_sum(s);
-		if (lane == 0) tot[col] = s;
+	{
+		/* thread (g, col), g = 0..kGroups-1: rows g, g + kGroups, ... — every load independent and in flight at once,
+		 * then the groups are added in fixed order */
+		constexpr int kGroups = kNeqThreads / kMomentCount;
+		__shared__ double part[kGroups][kMomentCount];
+		const int g = threadIdx.x / kMomentCount, col = threadIdx.x % kMomentCount;
+		if (g < kGroups) {
+			double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+			unsigned int b = g;
+			for (; b + 3 * kGroups < gridDim.x; b += 4 * kGroups) {
+				const double a0 = __ldcg(partials + (size_t)b * kPartialCols + col);
+				const double a1 = __ldcg(partials + (size_t)(b + kGroups) * kPartialCols + col);
+				const double a2 = __ldcg(partials + (size_t)(b + 2 * kGroups) * kPartialCols + col);
+				const double a3 = __ldcg(partials + (size_t)(b + 3 * kGroups) * kPartialCols + col);
+				s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+			}
+			for (; b < gridDim.x; b += kGroups) s0 += __ldcg(partials + (size_t)b * kPartialCols + col);
+			part[g][col] = (s0 + s1) + (s2 + s3);
+		}
+		__syncthreads();
+		if (threadIdx.x < kMomentCount) {
+			double s = 0;
+#pragma unroll
+			for (int k = 0; k < kGroups; k++) s += part[k][threadIdx.x];
+			tot[threadIdx.x] = s;
+		}
 	}
 	__syncthreads();
 	if (wid == 0) {
 		__shared__ double neq[kNeqCount];
 		if (lane == 0) *ticket = 0;
 		const double *p6 = fin.ps ? fin.ps->pose6 : fin.pose6_in;
+#ifdef M3D_NEQ_TIMING
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq1));
+#endif
 		moments_to_neq_warp(tot, p6[3], p6[4], p6[5], neq, lane);
+#ifdef M3D_NEQ_TIMING
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq2));
+#endif
 		neq_tail_warp(neq, fin, lane);
+#ifdef M3D_NEQ_TIMING
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq3));
+		if (lane == 0) printf("neq tail ns: reduce %llu moments_to_neq %llu tail %llu\n", tq1 - tq0, tq2 - tq1, tq3 - tq2);
+#endif
 	}
 }
 
