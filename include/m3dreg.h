@@ -146,8 +146,9 @@ int64_t m3dreg_launch_count(const m3dreg_ctx *ctx);
  * only m3dreg_nn_search / m3dreg_semantic_nn_host honour it.  Default: on. */
 int m3dreg_set_pruning(m3dreg_ctx *ctx, int enabled);
 
-/* Diagnostic counter: number of candidate records the NN search staged (summed over warps; every staged candidate
- * is tested by the 32 queries of the warp) since the last reset.  Reported by bench.py as evaluations per query. */
+/* Diagnostic counter: number of candidate distance evaluations the NN search made (summed over queries) since the
+ * last reset.  Only counted while m3dreg_set_profiling(ctx, 1) is in effect (the counter costs one atomic per warp).
+ * Reported by bench.py as evaluations per query. */
 int m3dreg_get_nn_evaluations(m3dreg_ctx *ctx, uint64_t *count_out, int reset);
 
 /* ---- stage-level entry points on DEVICE pointers (parity surface = reference L0) ---------- */

@@ -9,6 +9,7 @@
  */
 #include <type_traits>
 #include <vector>
+#include <utility>
 #include <new>
 #include <cstring>
 #include <cstdio>
@@ -108,6 +109,7 @@ struct m3dreg_ctx {
 	unsigned int *ticket = nullptr;
 	unsigned int *cell_count = nullptr;           /* number of searchable buckets in the compact list */
 	unsigned long long *eval_counter = nullptr;   /* candidates staged by the NN search (warp-level), diagnostic */
+	int use_pdl = 1;             /* programmatic dependent launch for every kernel (env M3DREG_NO_PDL=1 disables) */
 	int nn_per_thread = 0;       /* test switch (env M3DREG_NN_PER_THREAD=1): k_nn_search instead of k_nn_search_grid */
 	NNTuning nn_tune = {16, 128, 8};   /* heuristics of k_nn_search_grid (env M3DREG_NN_RHO_DIV / _HULL_MIN / _HULL_RATIO override) */
 	double *scratch = nullptr;   /* 64 doubles */
@@ -143,11 +145,26 @@ inline int grid_for(const m3dreg_ctx *c, long long n, int threads, int per_sm = 
 	return (int)b;
 }
 
-#define LAUNCH(ctx, kernel, grid, block, ...)                                  \
-	do {                                                                       \
-		kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);            \
-		(ctx)->launches++;                                                     \
-	} while (0)
+/* Every kernel goes out with programmatic stream serialisation (see pdl_enter() in m3dreg_kernels.cuh): its blocks
+ * are scheduled as the previous kernel's blocks exit and wait in griddepcontrol.wait for its completion.
+ * M3DREG_NO_PDL=1 in the environment falls back to plain stream order. */
+template <class... KArgs, class... Args>
+inline void launch_kernel(m3dreg_ctx *c, void (*kernel)(KArgs...), int grid, int block, Args &&... args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)grid, 1, 1);
+	cfg.blockDim = dim3((unsigned)block, 1, 1);
+	cfg.dynamicSmemBytes = 0;
+	cfg.stream = c->stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = c->use_pdl ? 1 : 0;
+	cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+	c->launches++;
+}
+#define LAUNCH(ctx, kernel, grid, block, ...) launch_kernel((ctx), kernel, (grid), (block), __VA_ARGS__)
 
 int bits_for(long long nb)
 {
@@ -312,7 +329,7 @@ void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *va
 	bool two = max_inner != max_outer;
 	if (!two && !c->nn_per_thread) {     /* one candidate set (the reference's default caps): warp-shared lookup grid */
 		LAUNCH(c, k_nn_search_grid, (n2 + kNNGThreads - 1) / kNNGThreads, kNNGThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
-				cand_set(c, false), vals, n1, buckets, c->gp, radius, max_outer, prune, c->nn_tune, nn_out, nn_seq, label_counts, c->eval_counter);
+				cand_set(c, false), vals, n1, buckets, c->gp, radius, max_outer, prune, c->nn_tune, nn_out, nn_seq, label_counts, c->profiling ? c->eval_counter : nullptr);
 		return;
 	}
 	LAUNCH(c, k_nn_search, (n2 + kNNThreads - 1) / kNNThreads, kNNThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
@@ -507,6 +524,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	if (!c) return (int)cudaErrorMemoryAllocation;
 	c->dev = cuda_device;
 	c->sm_count = prop.multiProcessorCount;
+	{ const char *e = getenv("M3DREG_NO_PDL"); c->use_pdl = (e && e[0] == '1') ? 0 : 1; }
 	{ const char *e = getenv("M3DREG_NN_PER_THREAD"); c->nn_per_thread = (e && e[0] == '1') ? 1 : 0; }
 	{ const char *e = getenv("M3DREG_NN_RHO_DIV"); if (e && atoi(e) > 0) c->nn_tune.rho_div = atoi(e); }
 	{ const char *e = getenv("M3DREG_NN_HULL_MIN"); if (e && atoi(e) > 0) c->nn_tune.hull_min = atoi(e); }

@@ -25,6 +25,19 @@
 
 namespace m3d {
 
+/* Programmatic dependent launch (sm_90+): the host launches every kernel with programmatic stream serialisation, so
+ * a kernel is set up and its blocks are scheduled as the blocks of the previous kernel of the stream exit, instead of
+ * after the whole grid has drained and a fresh launch has been processed.  Nothing the previous kernel wrote may be
+ * read, and nothing it reads may be overwritten, before griddepcontrol.wait returns — it is the FIRST statement of
+ * every kernel in this file.  No kernel calls griddepcontrol.launch_dependents: triggering early leaves the next grid's
+ * blocks resident and waiting, which measured SLOWER than plain stream order on small scans (C1: 134 vs 122 us per
+ * iteration), while the implicit trigger at block exit measured 98 us (C1) and 189 vs 211 us (C2).
+ * Without the launch attribute the instruction is a no-op. */
+__device__ __forceinline__ void pdl_enter()
+{
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 constexpr int kMomentCount = 24;   /* S, M1[3], M2[6], L1[3], L2[9], n_obs, (pad) */
 constexpr int kPartialCols = 28;   /* row width of the per-block partial sums (ICP uses 24 of them, NDT all 28) */
 constexpr int kNeqCount = 28;      /* 21 upper-tri AtPA + 6 AtPl + count */
@@ -99,6 +112,7 @@ __device__ __forceinline__ void block_bounds_commit(float mnx, float mny, float 
 /* ---- AoS (reference 40-byte point) <-> SoA ----------------------------------------------------------- */
 __global__ void k_unpack_points(const m3dreg_point *__restrict__ in, int n, float4 *__restrict__ xyzl, float4 *__restrict__ nrm)
 {
+	pdl_enter();
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const uint2 *p = reinterpret_cast<const uint2 *>(in + i);   /* 40-byte records are 8-byte aligned */
@@ -111,6 +125,7 @@ __global__ void k_unpack_points(const m3dreg_point *__restrict__ in, int n, floa
 /* min/max straight from an AoS cloud (stage-level m3dreg_grid_params). */
 __global__ void k_bounds_aos(const m3dreg_point *__restrict__ in, int n, uint32_t *bounds)
 {
+	pdl_enter();
 	float mnx = INFINITY, mny = INFINITY, mnz = INFINITY, mxx = -INFINITY, mxy = -INFINITY, mxz = -INFINITY;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const uint2 *p = reinterpret_cast<const uint2 *>(in + i);
@@ -124,6 +139,7 @@ __global__ void k_bounds_aos(const m3dreg_point *__restrict__ in, int n, uint32_
 
 __global__ void k_reset_bounds(uint32_t *bounds)
 {
+	pdl_enter();
 	if (threadIdx.x < 3) bounds[threadIdx.x] = 0xFFFFFFFFu;
 	else if (threadIdx.x < 6) bounds[threadIdx.x] = 0u;
 }
@@ -133,6 +149,7 @@ __global__ void k_transform_aos(const m3dreg_point *__restrict__ in, m3dreg_poin
 		float r00, float r01, float r02, float t0, float r10, float r11, float r12, float t1,
 		float r20, float r21, float r22, float t2)
 {
+	pdl_enter();
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	m3dreg_point p = in[i];
@@ -152,6 +169,7 @@ template <bool WITH_BOUNDS>
 __global__ void k_transform_soa(const float4 *__restrict__ in_xyzl, const float4 *__restrict__ in_nrm, int n,
 		const float *__restrict__ m, float4 *__restrict__ out_xyzl, float4 *__restrict__ out_nrm, uint32_t *bounds)
 {
+	pdl_enter();
 	float r00 = __ldg(m + 0), r01 = __ldg(m + 1), r02 = __ldg(m + 2), t0 = __ldg(m + 3);
 	float r10 = __ldg(m + 4), r11 = __ldg(m + 5), r12 = __ldg(m + 6), t1 = __ldg(m + 7);
 	float r20 = __ldg(m + 8), r21 = __ldg(m + 9), r22 = __ldg(m + 10), t2 = __ldg(m + 11);
@@ -236,6 +254,7 @@ __global__ void __launch_bounds__(kSortThreads) k_grid_head(const float4 *__rest
 		unsigned int *__restrict__ cell_count, m3dreg_bucket *__restrict__ buckets, uint32_t *__restrict__ keys,
 		int tiles, int passes, uint32_t *__restrict__ hist)
 {
+	pdl_enter();
 	__shared__ uint32_t sh[kRadixSize];
 	m3dreg_grid_params g;
 	bool ok = grid_params_from_bounds_dev(bounds, rx, ry, rz, ext, bucket_cap, g);
@@ -280,6 +299,7 @@ __global__ void __launch_bounds__(kSortThreads) k_grid_head(const float4 *__rest
 __global__ void k_keys_aos(const m3dreg_point *__restrict__ in, int n, const m3dreg_grid_params *__restrict__ gp,
 		uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
+	pdl_enter();
 	float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
 	float rx = gp->resolution_X, ry = gp->resolution_Y, rz = gp->resolution_Z;
 	int nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
@@ -308,6 +328,7 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v)   /* 9 bits -> every thi
 __global__ void k_keys_presort(const m3dreg_point *__restrict__ in, int n, float mnx, float mny, float mnz, float inv_res,
 		uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
+	pdl_enter();
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const uint2 *p = reinterpret_cast<const uint2 *>(in + i);
 		uint2 a = __ldg(p), b = __ldg(p + 1), e = __ldg(p + 4);
@@ -330,6 +351,7 @@ template <int ITEMS>
 __global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint32_t *__restrict__ keys, int n, int shift,
 		int tiles, uint32_t *__restrict__ hist, const m3dreg_grid_params *__restrict__ gp)
 {
+	pdl_enter();
 	__shared__ uint32_t sh[kRadixSize];
 	if (gp && gp->number_of_buckets <= 0) return;
 	sh[threadIdx.x] = 0;
@@ -350,6 +372,7 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint32_t *__r
 __global__ void __launch_bounds__(256) k_radix_scan(uint32_t *__restrict__ hist, int tiles, uint32_t *__restrict__ digit_tot,
 		const m3dreg_grid_params *__restrict__ gp)
 {
+	pdl_enter();
 	__shared__ uint32_t warp_tot[8];
 	__shared__ uint32_t carry;
 	if (gp && gp->number_of_buckets <= 0) return;
@@ -383,6 +406,7 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *
 		const uint32_t *__restrict__ hist, const uint32_t *__restrict__ digit_tot, const m3dreg_grid_params *__restrict__ gp,
 		uint32_t *__restrict__ next_hist)
 {
+	pdl_enter();
 	__shared__ uint32_t wcnt[kSortWarps][kRadixSize];   /* per-warp digit counts, then per-warp exclusive offsets */
 	__shared__ uint32_t gbase[kRadixSize];
 	__shared__ uint32_t wtot[kSortWarps];
@@ -469,6 +493,7 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *
  *      lesson_16.cu:131-189) + gather of the first cloud into sorted order ---------------------------------- */
 __global__ void k_init_buckets(m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp, long long nb_host)
 {
+	pdl_enter();
 	long long nb = gp ? gp->number_of_buckets : nb_host;
 	/* 12-byte records written as a flat int stream: -1,-1,0,-1,-1,0,... */
 	long long total = nb * 3;
@@ -498,6 +523,7 @@ __global__ void k_finalize_grid(const uint32_t *__restrict__ keys, const uint32_
 		const m3dreg_grid_params *__restrict__ gp, m3dreg_bucket *__restrict__ buckets, m3dreg_hash_element *__restrict__ table_out,
 		uint32_t *__restrict__ cell_list, unsigned int *__restrict__ cell_count)
 {
+	pdl_enter();
 	if (gp && gp->number_of_buckets <= 0) return;
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
@@ -550,6 +576,7 @@ __global__ void k_finalize_grid(const uint32_t *__restrict__ keys, const uint32_
 __global__ void k_list_cells(const uint32_t *__restrict__ keys, int n, const m3dreg_bucket *__restrict__ buckets,
 		uint32_t *__restrict__ cell_list, unsigned int *__restrict__ cell_count)
 {
+	pdl_enter();
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	const int nround = (n + 31) & ~31;
@@ -711,6 +738,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32, 7) k_build_candidates(const 
 		const float4 *__restrict__ src_xyzl, const float4 *__restrict__ src_nrm, const float *__restrict__ nrm_m, int max_inner, int max_outer,
 		CandSet ci, CandSet co, int two_sets)
 {
+	pdl_enter();
 	__shared__ uint32_t s_hist[kBuildWarps][kBuildTabMax + 7];
 	NormalRotation rot;
 	rot.on = nrm_m != nullptr;
@@ -738,6 +766,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32, 7) k_build_candidates(const 
 /* split an externally supplied reference-layout table into key / value streams (stage-level m3dreg_nn_search) */
 __global__ void k_split_table(const m3dreg_hash_element *__restrict__ table, int n, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
+	pdl_enter();
 	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
 		m3dreg_hash_element h = table[p];
 		keys[p] = (uint32_t)h.index_of_bucket;
@@ -761,6 +790,7 @@ __global__ void __launch_bounds__(kNNThreads) k_nn_search(const float4 *__restri
 		int *__restrict__ nn_out, int *__restrict__ nn_seq, unsigned long long *__restrict__ label_counts,
 		unsigned long long *__restrict__ eval_counter)
 {
+	pdl_enter();
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	const int qi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -903,6 +933,7 @@ __global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_gr
 		int *__restrict__ nn_out, int *__restrict__ nn_seq, unsigned long long *__restrict__ label_counts,
 		unsigned long long *__restrict__ eval_counter)
 {
+	pdl_enter();
 	__shared__ int4 s_segs[kNNWarps][kNNCells];                /* {first candidate, count, hull cell x | y << 16, hull cell z} */
 	__shared__ float4 s_cand[kNNWarps][kNNStage];              /* staged candidates, per group of four: {x0..x3}, {y0..y3}, {z0..z3}, {l0..l3} */
 	__shared__ int4 s_grp[kNNWarps][kNNStage / 4];             /* per group: {index of its first candidate, -, hull cell x | y << 16, z} */
@@ -966,7 +997,9 @@ __global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_gr
 	/* every candidate with dist <= tau lies in the box of fine columns this returns (nn_query()'s box: conservative
 	 * column bounds of [q - R, q + R], R >= sqrt(tau) rounded outwards, clamped to the lane's 27-neighbourhood) */
 	auto fine_box = [&](float tau, int &xl, int &xh, int &yl, int &yh, int &zl, int &zh) {
-		const float R = prune ? f_add_up(f_mul_up(f_sqrt_up(tau), 1.00000095367431640625f), 1.0e-18f) : INFINITY;
+		/* R >= sqrt(tau) * (1 + 2^-20) is all the proof needs: tau * rsqrt(tau) is within 2^-21 of sqrt(tau) (MUFU.RSQ: 2 ulp),
+		 * the factor 1 + 2^-13 covers that with three orders of magnitude to spare and costs a box 0.01 % wider */
+		const float R = !prune ? INFINITY : (tau > 1.0e-30f ? f_fma(f_mul(tau, rsqrtf(tau)), 1.0001220703125f, 1.0e-18f) : 1.1e-15f);
 		xl = col_floor(f_sub(qx, R), mnx, iwx, mgx); xh = col_ceil(f_add(qx, R), mnx, iwx, mgx);
 		yl = col_floor(f_sub(qy, R), mny, iwy, mgy); yh = col_ceil(f_add(qy, R), mny, iwy, mgy);
 		zl = col_floor(f_sub(qz, R), mnz, iwz, mgz); zh = col_ceil(f_add(qz, R), mnz, iwz, mgz);
@@ -1206,6 +1239,7 @@ __global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_gr
 __global__ void k_gather_perm(const uint32_t *__restrict__ perm, int n, const float4 *__restrict__ in_xyzl, const float4 *__restrict__ in_nrm,
 		float4 *__restrict__ out_xyzl, float4 *__restrict__ out_nrm)
 {
+	pdl_enter();
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		uint32_t v = __ldg(perm + i);
 		out_xyzl[i] = __ldg(in_xyzl + v);
@@ -1421,6 +1455,7 @@ __device__ inline void pose_prepare(PoseState *ps)
 
 __global__ void k_pose_prepare(PoseState *ps)
 {
+	pdl_enter();
 	if (blockIdx.x == 0 && threadIdx.x < 32) pose_prepare_warp(ps, threadIdx.x);
 }
 
@@ -1671,6 +1706,7 @@ template <class Src>
 __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(const Src src_in, int n, double *__restrict__ partials,
 		unsigned int *__restrict__ ticket, FinalizeArgs fin)
 {
+	pdl_enter();
 	Src src = src_in;
 	src.prepare();
 	__shared__ double sm[kNeqThreads / 32][kMomentCount];
@@ -1786,6 +1822,7 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(const Src src_
 /* Standalone device Cholesky (m3dreg_solve_chol): column-major dof x dof in, x out. */
 __global__ void k_solve_dense(const double *A, const double *b, int dof, double *x, int *status)
 {
+	pdl_enter();
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
 	double neq[kNeqCount];
 	const int sel6[6] = {0, 1, 2, 3, 4, 5}, sel4[4] = {0, 1, 2, 5};
@@ -1807,6 +1844,7 @@ __global__ void k_solve_dense(const double *A, const double *b, int dof, double 
 __global__ void k_sweep_solve(const double *__restrict__ neq, int begin, int end, float *__restrict__ poses,
 		int dof, int obs_threshold, int *__restrict__ status_out)
 {
+	pdl_enter();
 	int s = begin + blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= end) return;
 	float *m = poses + 16 * (size_t)s;
@@ -1835,6 +1873,7 @@ __global__ void k_sweep_solve(const double *__restrict__ neq, int begin, int end
 
 __global__ void k_zero_f64(double *p, int n)
 {
+	pdl_enter();
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0.0;
 }
 
@@ -1852,6 +1891,7 @@ constexpr double kNdtRegRel = 0.05;
 
 __global__ void k_ndt_zero(double *__restrict__ acc, double *__restrict__ qacc, const m3dreg_grid_params *__restrict__ gp, int zero_acc)
 {
+	pdl_enter();
 	long long nb = gp->number_of_buckets;
 	long long total = nb * (zero_acc ? 16 : 4);
 	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1898,6 +1938,7 @@ __global__ void __launch_bounds__(256) k_ndt_accumulate_points(const uint32_t *_
 		const float4 *__restrict__ g_xyzl, const float4 *__restrict__ l_xyzl, const m3dreg_grid_params *__restrict__ gp,
 		double *__restrict__ acc)
 {
+	pdl_enter();
 	if (gp->number_of_buckets <= 0) return;
 	int nround = (n + 31) & ~31;
 	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
@@ -1941,6 +1982,7 @@ __device__ __host__ inline bool sym3_inverse(const double *S, double *W)
 __global__ void k_ndt_finalize_buckets(const m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp,
 		double *__restrict__ acc)
 {
+	pdl_enter();
 	long long nb = gp->number_of_buckets;
 	double res = (double)gp->resolution_X;
 	double eps = (kNdtRegRel * res) * (kNdtRegRel * res);
@@ -1967,6 +2009,7 @@ __global__ void k_ndt_finalize_buckets(const m3dreg_bucket *__restrict__ buckets
 __global__ void __launch_bounds__(256) k_ndt_accumulate_queries(const float4 *__restrict__ q_xyzl, int n2,
 		const m3dreg_grid_params *__restrict__ gp, const double *__restrict__ acc, double *__restrict__ qacc)
 {
+	pdl_enter();
 	long long nb = gp->number_of_buckets;
 	if (nb <= 0) return;
 	float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
@@ -2001,6 +2044,7 @@ __global__ void __launch_bounds__(256) k_ndt_accumulate_queries(const float4 *__
 __global__ void __launch_bounds__(kNeqThreads) k_ndt_normal_equations(const double *__restrict__ acc, const double *__restrict__ qacc,
 		const m3dreg_grid_params *__restrict__ gp, double *__restrict__ partials, unsigned int *__restrict__ ticket, FinalizeArgs fin)
 {
+	pdl_enter();
 	__shared__ double sm[kNeqThreads / 32][kPartialCols];
 	__shared__ bool is_last;
 	long long nb = gp->number_of_buckets;
