@@ -315,7 +315,7 @@ def main():
     ctx.set_profiling(False)
     ctx.icp_end()
     stage_ms = stage_ms / max(stage_iters, 1)
-    stage_names = ["transform+bounds", "grid (keys, radix sort, bucket table, gather)", "semantic NN (k_nn_search)", "normal equations + solve"]
+    stage_names = ["transform+bounds", "grid (keys, radix sort, bucket table, gather)", "semantic NN (k_nn_search_grid)", "normal equations + solve"]
     dom = int(np.argmax(stage_ms))
     nn_ms = float(stage_ms[2])
     nn_bytes = nn_alg_bytes(n1, n2, nb)
@@ -372,8 +372,8 @@ def main():
             "launches_per_step": launches / args.steps,
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "k_nn_search", "achieved": nn_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": nn_gbs / peak_gbs,
-                "traffic": ncu_traffic("k_nn_search", args.workload) if args.mode == "icp" else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": nn_bytes, "launch_ms": nn_ms,
+                "bound": "hbm", "kernel": "k_nn_search_grid", "achieved": nn_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": nn_gbs / peak_gbs,
+                "traffic": ncu_traffic("k_nn_search_grid", args.workload) if args.mode == "icp" else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": nn_bytes, "launch_ms": nn_ms,
                 "dominant_stage": stage_names[dom],
                 "nn_candidate_evaluations_per_query": evals_per_query,
                 "stage_ms": {stage_names[k]: float(stage_ms[k]) for k in range(4)},
