@@ -309,9 +309,11 @@ def main():
     ctx.icp_begin(0, 1, pose_out, pose2, prm)
     ctx.set_profiling(True)
     ctx.nn_evaluations(reset=True)
+    ctx.nn_fallbacks(reset=True)
     ctx.icp_step(min(args.steps, 10))
     stage_ms, stage_iters = ctx.get_stage_ms()
     evals_per_query = ctx.nn_evaluations(reset=True) / max(stage_iters, 1) / float(n2)
+    fallback_share = ctx.nn_fallbacks(reset=True) / max(stage_iters, 1) / float(n2)
     ctx.set_profiling(False)
     ctx.icp_end()
     stage_ms = stage_ms / max(stage_iters, 1)
@@ -376,6 +378,7 @@ def main():
                 "traffic": ncu_traffic("k_nn_search_grid", args.workload) if args.mode == "icp" else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": nn_bytes, "launch_ms": nn_ms,
                 "dominant_stage": stage_names[dom],
                 "nn_candidate_evaluations_per_query": evals_per_query,
+                "nn_queries_on_per_thread_fallback": fallback_share,
                 "stage_ms": {stage_names[k]: float(stage_ms[k]) for k in range(4)},
                 "iteration": {"algorithmic_bytes": iter_bytes, "achieved": iter_gbs, "frac": iter_gbs / peak_gbs,
                               "note": "whole iteration (all kernels) vs the HBM roofline, B_alg = 104*N1 + 36*N2 + 24*B + 40*Nc"},

@@ -151,6 +151,11 @@ int m3dreg_set_pruning(m3dreg_ctx *ctx, int enabled);
  * Reported by bench.py as evaluations per query. */
 int m3dreg_get_nn_evaluations(m3dreg_ctx *ctx, uint64_t *count_out, int reset);
 
+/* Diagnostic counter (also only while profiling is on): number of queries the warp-shared search handed to the
+ * per-thread search because their warp's queries were scattered.  0 for spatially sorted queries (the scan store's
+ * order); tests use it to prove which code path produced a result. */
+int m3dreg_get_nn_fallbacks(m3dreg_ctx *ctx, uint64_t *count_out, int reset);
+
 /* ---- stage-level entry points on DEVICE pointers (parity surface = reference L0) ---------- */
 
 /* ref: cudaCalculateGridParams (include/lesson_16.h:61-62, src/lesson_16.cu:23-106).

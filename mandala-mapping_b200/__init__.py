@@ -44,7 +44,7 @@ EXPORTS = [
     "m3dreg_scan_upload", "m3dreg_scan_size", "m3dreg_scan_clear", "m3dreg_icp_pair", "m3dreg_icp_iteration_host",
     "m3dreg_export_last_grid", "m3dreg_export_last_nn", "m3dreg_sweep_zero", "m3dreg_sweep_accumulate",
     "m3dreg_sweep_solve", "m3dreg_icp_begin", "m3dreg_icp_step", "m3dreg_icp_end", "m3dreg_icp_copy_neq",
-    "m3dreg_set_profiling", "m3dreg_get_stage_ms", "m3dreg_set_pruning", "m3dreg_get_nn_evaluations",
+    "m3dreg_set_profiling", "m3dreg_get_stage_ms", "m3dreg_set_pruning", "m3dreg_get_nn_evaluations", "m3dreg_get_nn_fallbacks",
 ]
 
 
@@ -172,6 +172,12 @@ class Context:
     def nn_evaluations(self, reset: bool = True) -> int:
         v = C.c_uint64(0)
         _check(lib().m3dreg_get_nn_evaluations(self._h, C.byref(v), C.c_int(1 if reset else 0)), "m3dreg_get_nn_evaluations")
+        return int(v.value)
+
+    def nn_fallbacks(self, reset: bool = True) -> int:
+        """Queries handed to the per-thread search by the warp-shared NN kernel (counted while profiling is on)."""
+        v = C.c_uint64(0)
+        _check(lib().m3dreg_get_nn_fallbacks(self._h, C.byref(v), C.c_int(1 if reset else 0)), "m3dreg_get_nn_fallbacks")
         return int(v.value)
 
     def set_pruning(self, enabled: bool):

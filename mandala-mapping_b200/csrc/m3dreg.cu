@@ -621,6 +621,17 @@ int m3dreg_get_nn_evaluations(m3dreg_ctx *c, uint64_t *count_out, int reset)
 	return 0;
 }
 
+int m3dreg_get_nn_fallbacks(m3dreg_ctx *c, uint64_t *count_out, int reset)
+{
+	if (!c || !count_out) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	CK(cudaMemcpyAsync(c->h->label_counts, c->eval_counter + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+	if (reset) CK(cudaMemsetAsync(c->eval_counter + 1, 0, sizeof(unsigned long long), c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	*count_out = (uint64_t)c->h->label_counts[0];
+	return 0;
+}
+
 int m3dreg_set_pruning(m3dreg_ctx *c, int enabled)
 {
 	if (!c) return M3DREG_E_INVALID_ARG;

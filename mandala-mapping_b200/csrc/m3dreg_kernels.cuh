@@ -1032,6 +1032,10 @@ __global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_gr
 				const int own = xl <= xh ? (xh - xl + 1) * (yh - yl + 1) * (zh - zl + 1) : 0;
 				const int own_max = __reduce_max_sync(full, own);
 				if (dx > kNNCells || dy > 32767 || dz > 32767 || (ncell > tune.hull_min && ncell > (long long)tune.hull_ratio * own_max)) {   /* scattered warp: per-lane search from scratch */
+					if (eval_counter) {
+						const unsigned fb = __ballot_sync(full, unsettled);
+						if (lane == 0) atomicAdd(eval_counter + 1, (unsigned long long)__popc(fb));
+					}
 					if (unsettled) best_l = nn_query_fallback(gp, buckets, cs.xyzl, cs.nrm, cs.tab, search_radius, cap, prune ? 1 : 0,
 							make_float4(qx, qy, qz, __int_as_float(label)), pn, &evals);
 					unsettled = false;
