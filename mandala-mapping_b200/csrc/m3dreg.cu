@@ -100,6 +100,13 @@ struct m3dreg_ctx {
 	DevBuf<float> d_poses1;      /* sweep: round-tripped poses, 16 floats per scan */
 	DevBuf<double> d_pose6;      /* sweep: tx,ty,tz,om,fi,ka per scan             */
 
+	/* batched sweep step: segment table, chunk -> segment map, per-segment label counters, pinned staging */
+	DevBuf<SweepSeg> d_segs;
+	DevBuf<int> d_seg_of_chunk;
+	DevBuf<unsigned long long> d_seg_counts;
+	void *h_sweep = nullptr;     /* pinned: kMaxSegs SweepSeg + chunk map */
+	size_t h_sweep_bytes = 0;
+
 	/* small device block */
 	PoseState *ps = nullptr;
 	uint32_t *bounds = nullptr;
@@ -324,17 +331,18 @@ void build_candidates(m3dreg_ctx *c, const uint32_t *vals, const m3dreg_bucket *
 }
 
 void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *vals, int n1, const m3dreg_bucket *buckets,
-		float radius, int max_inner, int max_outer, int prune, int *nn_out, int *nn_seq, unsigned long long *label_counts)
+		float radius, int max_inner, int max_outer, int prune, int *nn_out, int *nn_seq, unsigned long long *label_counts,
+		const int *seg_of_chunk = nullptr)
 {
 	bool two = max_inner != max_outer;
 	if (!two && !c->nn_per_thread) {     /* one candidate set (the reference's default caps): warp-shared lookup grid */
 		LAUNCH(c, k_nn_search_grid, (n2 + kNNGThreads - 1) / kNNGThreads, kNNGThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
-				cand_set(c, false), vals, n1, buckets, c->gp, radius, max_outer, prune, c->nn_tune, nn_out, nn_seq, label_counts, c->profiling ? c->eval_counter : nullptr);
+				cand_set(c, false), vals, n1, buckets, c->gp, radius, max_outer, prune, c->nn_tune, nn_out, nn_seq, label_counts, c->profiling ? c->eval_counter : nullptr, seg_of_chunk);
 		return;
 	}
 	LAUNCH(c, k_nn_search, (n2 + kNNThreads - 1) / kNNThreads, kNNThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
 			cand_set(c, false), cand_set(c, two), vals, n1, buckets, c->gp, radius, max_inner, max_outer, prune, nn_out, nn_seq,
-			label_counts, c->eval_counter);
+			label_counts, c->profiling ? c->eval_counter : nullptr, seg_of_chunk);
 }
 
 /* Grid of the (already transformed) first cloud in g_*: params (device) from bounds, keys, sort, dense table,
@@ -430,7 +438,7 @@ void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int
 	if (prm->mode == M3DREG_MODE_NDT) {
 		ndt_bucket_stats(c, lx, n1);
 		if (prof) { cudaEventRecord(c->pev[2], c->stream); cudaEventRecord(c->pev[3], c->stream); }
-		FinalizeArgs fin;
+		FinalizeArgs fin = {};
 		fin.ps = c->ps; fin.neq_out = nullptr; fin.accumulate = 0; fin.solve = 1; fin.dof = prm->dof;
 		fin.obs_threshold = prm->obs_threshold; fin.pose6_in = nullptr; fin.bounds_reset = c->bounds;
 		fin.label_counts_reset = nullptr;
@@ -451,10 +459,11 @@ void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int
 	if (prof) cudaEventRecord(c->pev[2], c->stream);
 	launch_nn(c, c->act_perm, n2, c->vals[c->last_sorted].p, n1, c->buckets.p, prm->search_radius, prm->max_inner, prm->max_outer, 1,
 			c->nn.p, c->nn_seq.p, c->label_counts);
-	ObsFromNN src;
+	ObsFromNN src = {};
+	src.n_segs = 1;
 	src.nn = c->nn_seq.p; src.q_xyzl = c->q_xyzl.p; src.l_xyzl = lx; src.m = c->ps->pose1; src.label_counts = c->label_counts;
 	for (int k = 0; k < 4; k++) src.weight[k] = prm->weight[k];
-	FinalizeArgs fin;
+	FinalizeArgs fin = {};
 	fin.ps = c->ps; fin.neq_out = nullptr; fin.accumulate = 0; fin.solve = 1; fin.dof = prm->dof;
 	fin.obs_threshold = prm->obs_threshold; fin.pose6_in = nullptr; fin.bounds_reset = c->bounds;
 	fin.label_counts_reset = c->label_counts;
@@ -573,6 +582,8 @@ void m3dreg_destroy(m3dreg_ctx *c)
 	for (int k = 0; k < 2; k++) { c->keys[k].release(); c->vals[k].release(); }
 	c->hist.release(); c->buckets.release(); c->nn.release(); c->nn_seq.release(); c->aos_a.release(); c->aos_b.release();
 	c->obs.release(); c->partials.release(); c->ndt_acc.release(); c->ndt_qacc.release(); c->table.release(); c->d_poses1.release(); c->d_pose6.release();
+	c->d_segs.release(); c->d_seg_of_chunk.release(); c->d_seg_counts.release();
+	if (c->h_sweep) cudaFreeHost(c->h_sweep);
 	if (c->ps) cudaFree(c->ps);   /* base of the small block */
 	if (c->h) cudaFreeHost(c->h);
 	for (int k = 0; k <= M3DREG_STAGE_COUNT; k++) if (c->pev[k]) cudaEventDestroy(c->pev[k]);
@@ -716,7 +727,7 @@ static int normal_equations_device(m3dreg_ctx *c, const m3dreg_obs_nn *d_obs, in
 	CK(cudaMemcpyAsync(c->scratch, c->h->scratch, 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	ObsFromList src;
 	src.obs = d_obs;
-	FinalizeArgs fin;
+	FinalizeArgs fin = {};
 	fin.ps = nullptr; fin.neq_out = c->scratch + 8; fin.accumulate = 0; fin.solve = 0; fin.dof = 6; fin.obs_threshold = 0;
 	fin.pose6_in = c->scratch; fin.bounds_reset = nullptr; fin.label_counts_reset = nullptr;
 	LAUNCH(c, k_normal_equations<ObsFromList>, grid_for(c, n_obs, kNeqThreads, 4), kNeqThreads, src, n_obs, c->partials.p, c->ticket, fin);
@@ -1147,15 +1158,22 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 	CK(cudaMemsetAsync(c->flags, 0, FLAG_COUNT * sizeof(int), c->stream));
 	CK(cudaMemsetAsync(c->ticket, 0, sizeof(unsigned int), c->stream));
 
-	/* process pairs grouped by i so the grid of scan i is built once (the reference rebuilds it per j, gpu6DSLAM.cpp:478) */
+	/* process pairs grouped by i so the grid of scan i is built once (the reference rebuilds it per j, gpu6DSLAM.cpp:478);
+	 * ICP: the neighbours j of one i are searched in batches — one transform, ONE search and ONE moment reduction over the
+	 * concatenated queries of up to kMaxSegs neighbours (k_transform_segments) instead of three small launches per pair */
 	std::vector<int> order((size_t)n_pairs);
 	for (int p = 0; p < n_pairs; p++) order[(size_t)p] = p;
 	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pair_i[a] < pair_i[b]; });
+	const size_t kBatchQueries = (size_t)8 << 20;       /* queries per batch (incl. padding): 8 Mi x 36 B of query state */
+	if (prm->mode != M3DREG_MODE_NDT) {
+		if ((e = c->d_segs.ensure(kMaxSegs))) return e;
+		if ((e = c->d_seg_counts.ensure(4 * kMaxSegs))) return e;
+		CK(cudaMemsetAsync(c->d_seg_counts.p, 0, 4 * kMaxSegs * sizeof(unsigned long long), c->stream));
+	}
 	int cur_i = -1, sort_bits = 0;
-	for (int q = 0; q < n_pairs; q++) {
-		int p = order[(size_t)q];
-		int i = pair_i[p], j = pair_j[p];
-		const Scan &A = c->scans[(size_t)i], &B = c->scans[(size_t)j];
+	for (int q = 0; q < n_pairs;) {
+		const int i = pair_i[order[(size_t)q]];
+		const Scan &A = c->scans[(size_t)i];
 		if (i != cur_i) {
 			if ((e = ensure_first(c, (size_t)A.n))) return e;
 			if ((e = ensure_candidates(c, (size_t)A.n, prm->max_inner, prm->max_outer))) return e;
@@ -1167,29 +1185,69 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 			if (prm->mode == M3DREG_MODE_NDT) ndt_bucket_stats(c, A.xyzl, A.n);
 			cur_i = i;
 		}
-		if ((e = ensure_second(c, (size_t)B.n))) return e;
-		LAUNCH(c, k_transform_soa<false>, grid_for(c, B.n, 256), 256, B.sx, B.sn, B.n, c->d_poses1.p + 16 * (size_t)j,
-				c->q_xyzl.p, c->q_nrm.p, (uint32_t *)nullptr);
 		if (prm->mode == M3DREG_MODE_NDT) {
-			FinalizeArgs fin;
+			const Scan &B = c->scans[(size_t)pair_j[order[(size_t)q]]];
+			if ((e = ensure_second(c, (size_t)B.n))) return e;
+			LAUNCH(c, k_transform_soa<false>, grid_for(c, B.n, 256), 256, B.sx, B.sn, B.n, c->d_poses1.p + 16 * (size_t)pair_j[order[(size_t)q]],
+					c->q_xyzl.p, c->q_nrm.p, (uint32_t *)nullptr);
+			FinalizeArgs fin = {};
 			fin.ps = nullptr; fin.neq_out = d_neq + (size_t)i * kNeqCount; fin.accumulate = 1; fin.solve = 0; fin.dof = prm->dof;
 			fin.obs_threshold = prm->obs_threshold; fin.pose6_in = c->d_pose6.p + 6 * (size_t)i; fin.bounds_reset = nullptr;
 			fin.label_counts_reset = nullptr;
 			ndt_queries_and_reduce(c, B.n, fin, true);
 			c->last_n_first = A.n; c->last_n_second = B.n; c->last_valid = true; c->last_nn_valid = false;
+			q++;
 			continue;
 		}
-		launch_nn(c, B.perm, B.n, c->vals[c->last_sorted].p, A.n, c->buckets.p, prm->search_radius, prm->max_inner, prm->max_outer, 1,
-				c->nn.p, c->nn_seq.p, c->label_counts);
-		ObsFromNN src;
-		src.nn = c->nn_seq.p; src.q_xyzl = c->q_xyzl.p; src.l_xyzl = A.xyzl; src.m = c->d_poses1.p + 16 * (size_t)i; src.label_counts = c->label_counts;
+		/* one batch: consecutive pairs of this i while they fit */
+		SweepSeg segs[kMaxSegs];
+		int nseg = 0;
+		size_t total = 0;
+		while (q < n_pairs && pair_i[order[(size_t)q]] == i && nseg < kMaxSegs) {
+			const int j = pair_j[order[(size_t)q]];
+			const Scan &B = c->scans[(size_t)j];
+			const size_t padded = ((size_t)B.n + kSegChunk - 1) / kSegChunk * kSegChunk;
+			if (nseg > 0 && total + padded > kBatchQueries) break;
+			segs[nseg].sx = B.sx; segs[nseg].sn = B.sn; segs[nseg].n = B.n; segs[nseg].off = (int)total; segs[nseg].pose = j; segs[nseg].pad = 0;
+			total += padded;
+			nseg++;
+			q++;
+		}
+		if (total > 0x7fffffffu) return M3DREG_E_INVALID_ARG;
+		const int n_chunks = (int)(total / kSegChunk);
+		if ((e = ensure_second(c, total))) return e;
+		if ((e = c->d_seg_of_chunk.ensure((size_t)n_chunks))) return e;
+		const size_t need = sizeof(segs) + (size_t)n_chunks * sizeof(int);
+		if (c->h_sweep_bytes < need) {
+			CK(cudaStreamSynchronize(c->stream));
+			if (c->h_sweep) cudaFreeHost(c->h_sweep);
+			c->h_sweep = nullptr; c->h_sweep_bytes = 0;
+			CK(cudaMallocHost(&c->h_sweep, need * 2));
+			c->h_sweep_bytes = need * 2;
+		}
+		/* the previous batch's upload has completed: plan_buckets / the end of this loop body synchronise the stream */
+		memcpy(c->h_sweep, segs, sizeof(segs));
+		int *h_map = reinterpret_cast<int *>(static_cast<char *>(c->h_sweep) + sizeof(segs));
+		for (int sgi = 0; sgi < nseg; sgi++) {
+			const int c0 = segs[sgi].off / kSegChunk, c1 = sgi + 1 < nseg ? segs[sgi + 1].off / kSegChunk : n_chunks;
+			for (int k = c0; k < c1; k++) h_map[k] = sgi;
+		}
+		CK(cudaMemcpyAsync(c->d_segs.p, c->h_sweep, sizeof(segs), cudaMemcpyHostToDevice, c->stream));
+		CK(cudaMemcpyAsync(c->d_seg_of_chunk.p, h_map, (size_t)n_chunks * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+		LAUNCH(c, k_transform_segments, n_chunks, kSegChunk, c->d_segs.p, c->d_seg_of_chunk.p, c->d_poses1.p, c->q_xyzl.p, c->q_nrm.p);
+		launch_nn(c, nullptr, (int)total, c->vals[c->last_sorted].p, A.n, c->buckets.p, prm->search_radius, prm->max_inner, prm->max_outer, 1,
+				nullptr, c->nn_seq.p, c->d_seg_counts.p, c->d_seg_of_chunk.p);
+		ObsFromNN src = {};
+		src.nn = c->nn_seq.p; src.q_xyzl = c->q_xyzl.p; src.l_xyzl = A.xyzl; src.m = c->d_poses1.p + 16 * (size_t)i;
+		src.label_counts = c->d_seg_counts.p; src.seg_of_chunk = c->d_seg_of_chunk.p; src.n_segs = nseg;
 		for (int k = 0; k < 4; k++) src.weight[k] = prm->weight[k];
-		FinalizeArgs fin;
+		FinalizeArgs fin = {};
 		fin.ps = nullptr; fin.neq_out = d_neq + (size_t)i * kNeqCount; fin.accumulate = 1; fin.solve = 0; fin.dof = prm->dof;
 		fin.obs_threshold = prm->obs_threshold; fin.pose6_in = c->d_pose6.p + 6 * (size_t)i; fin.bounds_reset = nullptr;
-		fin.label_counts_reset = c->label_counts;
-		LAUNCH(c, k_normal_equations<ObsFromNN>, grid_for(c, B.n, kNeqThreads, 2), kNeqThreads, src, B.n, c->partials.p, c->ticket, fin);
-		c->last_n_first = A.n; c->last_n_second = B.n; c->last_valid = true;
+		fin.label_counts_reset = c->d_seg_counts.p; fin.label_count_sets = nseg;
+		LAUNCH(c, k_normal_equations<ObsFromNN>, grid_for(c, (long long)total, kNeqThreads, 2), kNeqThreads, src, (int)total, c->partials.p, c->ticket, fin);
+		CK(cudaStreamSynchronize(c->stream));      /* the pinned staging block is reused by the next batch */
+		c->last_n_first = A.n; c->last_n_second = segs[nseg - 1].n; c->last_valid = true; c->last_nn_valid = false;
 	}
 	int f = check_flags(c);
 	if (f) return f;

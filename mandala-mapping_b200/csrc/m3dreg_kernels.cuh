@@ -195,6 +195,47 @@ __global__ void k_transform_soa(const float4 *__restrict__ in_xyzl, const float4
 	if (WITH_BOUNDS) block_bounds_commit(mnx, mny, mnz, mxx, mxy, mxz, bounds);
 }
 
+/* ---- query segments of a batched sweep step ----------------------------------------------------------------------
+ * registerAll matches every neighbour j of a scan i against the SAME grid of i (gpu6DSLAM.cpp:469-565).  The sweep
+ * therefore concatenates the (transformed) clouds of several neighbours into one query array — segment s occupies
+ * [off_s, off_s + n_s), off_s a multiple of kSegChunk, padding queries sit at +inf (outside every box: no match) — and
+ * runs ONE search and ONE moment reduction over it.  seg_of_chunk[q / kSegChunk] names the segment of query q; the
+ * per-label match counts (the observation weights are weight_label / count_label PER PAIR, gpu6DSLAM.cpp:490-562)
+ * are kept per segment. */
+constexpr int kSegChunk = 256;
+constexpr int kMaxSegs = 64;
+struct SweepSeg {
+	const float4 *sx, *sn;      /* the neighbour's stored scan in query order (local frame) */
+	int n, off, pose, pad;      /* points, first query, index of its pose in the pose array */
+};
+
+__global__ void __launch_bounds__(kSegChunk) k_transform_segments(const SweepSeg *__restrict__ segs, const int *__restrict__ seg_of_chunk,
+		const float *__restrict__ poses, float4 *__restrict__ out_xyzl, float4 *__restrict__ out_nrm)
+{
+	pdl_enter();
+	const SweepSeg sg = segs[__ldg(seg_of_chunk + blockIdx.x)];
+	const float *m = poses + 16 * (size_t)sg.pose;
+	const int q = blockIdx.x * kSegChunk + threadIdx.x, i = q - sg.off;
+	if (i >= sg.n) {
+		out_xyzl[q] = make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(-1));
+		out_nrm[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		return;
+	}
+	/* same operation sequence as k_transform_soa */
+	const float r00 = __ldg(m + 0), r01 = __ldg(m + 1), r02 = __ldg(m + 2), t0 = __ldg(m + 3);
+	const float r10 = __ldg(m + 4), r11 = __ldg(m + 5), r12 = __ldg(m + 6), t1 = __ldg(m + 7);
+	const float r20 = __ldg(m + 8), r21 = __ldg(m + 9), r22 = __ldg(m + 10), t2 = __ldg(m + 11);
+	const float4 p = __ldg(sg.sx + i), nq = __ldg(sg.sn + i);
+	const float x = __fadd_rn(t0, __fmaf_rn(r02, p.z, __fmaf_rn(r00, p.x, __fmul_rn(r01, p.y))));
+	const float y = __fadd_rn(t1, __fmaf_rn(r12, p.z, __fmaf_rn(r10, p.x, __fmul_rn(r11, p.y))));
+	const float z = __fadd_rn(t2, __fmaf_rn(r22, p.z, __fmaf_rn(r20, p.x, __fmul_rn(r21, p.y))));
+	out_xyzl[q] = make_float4(x, y, z, p.w);
+	const float nx = __fmaf_rn(r02, nq.z, __fmaf_rn(r00, nq.x, __fmul_rn(r01, nq.y)));
+	const float ny = __fmaf_rn(r12, nq.z, __fmaf_rn(r10, nq.x, __fmul_rn(r11, nq.y)));
+	const float nz = __fmaf_rn(r22, nq.z, __fmaf_rn(r20, nq.x, __fmul_rn(r21, nq.y)));
+	out_nrm[q] = make_float4(nx, ny, nz, 0.0f);
+}
+
 /* Grid parameters from the reduced bounds, on the device (host part of cudaCalculateGridParams, lesson_16.cu:64-91):
  * max += ext; min -= ext; nb = int((max-min)/res + 1); B = nbX*nbY*nbZ.
  * Returns false (and number_of_buckets = 0) when B overflows int32 or the planned capacity. */
@@ -788,12 +829,13 @@ __global__ void __launch_bounds__(kNNThreads) k_nn_search(const float4 *__restri
 		const m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp,
 		float search_radius, int max_inner, int max_outer, int prune,
 		int *__restrict__ nn_out, int *__restrict__ nn_seq, unsigned long long *__restrict__ label_counts,
-		unsigned long long *__restrict__ eval_counter)
+		unsigned long long *__restrict__ eval_counter, const int *__restrict__ seg_of_chunk)
 {
 	pdl_enter();
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+	if (seg_of_chunk && label_counts) label_counts += 4 * __ldg(seg_of_chunk + (blockIdx.x * blockDim.x) / kSegChunk);   /* a block never straddles segments */
 	NNParams P;
 	P.mnx = gp->bounding_box_min_X; P.mny = gp->bounding_box_min_Y; P.mnz = gp->bounding_box_min_Z;
 	P.mxx = gp->bounding_box_max_X; P.mxy = gp->bounding_box_max_Y; P.mxz = gp->bounding_box_max_Z;
@@ -814,7 +856,7 @@ __global__ void __launch_bounds__(kNNThreads) k_nn_search(const float4 *__restri
 	if (best_l != kNNNone && best_l >= 0 && best_l < n_first) result = (int)__ldg(s_vals + best_l);
 	if (qi < n_second) {
 		if (nn_seq) nn_seq[qi] = result;
-		nn_out[q_perm ? __ldg(q_perm + qi) : (uint32_t)qi] = result;
+		if (nn_out) nn_out[q_perm ? __ldg(q_perm + qi) : (uint32_t)qi] = result;
 	}
 	if (eval_counter) {
 		unsigned int tot = __reduce_add_sync(full, evals);
@@ -931,9 +973,10 @@ __global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_gr
 		const m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp,
 		float search_radius, int cap, int prune, NNTuning tune,
 		int *__restrict__ nn_out, int *__restrict__ nn_seq, unsigned long long *__restrict__ label_counts,
-		unsigned long long *__restrict__ eval_counter)
+		unsigned long long *__restrict__ eval_counter, const int *__restrict__ seg_of_chunk)
 {
 	pdl_enter();
+	if (seg_of_chunk && label_counts) label_counts += 4 * __ldg(seg_of_chunk + (blockIdx.x * blockDim.x) / kSegChunk);   /* a block never straddles segments */
 	__shared__ int4 s_segs[kNNWarps][kNNCells];                /* {first candidate, count, hull cell x | y << 16, hull cell z} */
 	__shared__ float4 s_cand[kNNWarps][kNNStage];              /* staged candidates, per group of four: {x0..x3}, {y0..y3}, {z0..z3}, {l0..l3} */
 	__shared__ int4 s_grp[kNNWarps][kNNStage / 4];             /* per group: {index of its first candidate, -, hull cell x | y << 16, z} */
@@ -1223,7 +1266,7 @@ __global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_gr
 	if (best_l != kNNNone && best_l >= 0 && best_l < n_first) result = (int)__ldg(s_vals + best_l);
 	if (qi < n_second) {
 		if (nn_seq) nn_seq[qi] = result;
-		nn_out[q_perm ? __ldg(q_perm + qi) : (uint32_t)qi] = result;
+		if (nn_out) nn_out[q_perm ? __ldg(q_perm + qi) : (uint32_t)qi] = result;
 	}
 	if (eval_counter) {
 		unsigned int tot = __reduce_add_sync(full, evals);
@@ -1597,10 +1640,12 @@ struct ObsFromNN {   /* fused path: nn[] + clouds (gpu6DSLAM.cpp:323-398 done on
 	const float4 *q_xyzl;       /* queries (second cloud, global)           */
 	const float4 *l_xyzl;       /* first cloud, local, original order       */
 	const float *m;             /* pose the first cloud was transformed with this iteration (device, row-major 4x4) */
-	const unsigned long long *label_counts;
+	const unsigned long long *label_counts;   /* 4 counters per segment */
+	const int *seg_of_chunk;    /* batched sweep: segment of query i / kSegChunk (0: one segment) */
+	int n_segs;
 	float weight[4];
 	float r[12];                /* m's 3x4 part, loaded once per thread by prepare() */
-	struct Raw { float4 p2, p0; };
+	struct Raw { float4 p2, p0; int seg; };
 	__device__ __forceinline__ void prepare()
 	{
 #pragma unroll
@@ -1610,12 +1655,13 @@ struct ObsFromNN {   /* fused path: nn[] + clouds (gpu6DSLAM.cpp:323-398 done on
 	__device__ __forceinline__ void fetch(int i, int j, Raw &raw) const
 	{
 		raw.p2 = __ldg(q_xyzl + i); raw.p0 = __ldg(l_xyzl + j);
+		raw.seg = seg_of_chunk ? __ldg(seg_of_chunk + i / kSegChunk) : 0;
 	}
 	__device__ __forceinline__ void finish(const Raw &raw, const float *wl, double &w, double &x, double &y, double &z,
 			double &lx, double &ly, double &lz) const
 	{
 		int label = __float_as_int(raw.p2.w);
-		w = (label >= 0 && label < 4) ? (double)wl[label] : 0.0;
+		w = (label >= 0 && label < 4) ? (double)wl[4 * raw.seg + label] : 0.0;
 		x = raw.p0.x; y = raw.p0.y; z = raw.p0.z;
 		/* the matched point in the global frame, recomputed with k_transform_soa's exact operation sequence (same bits as
 		 * the transformed cloud the search ran on) instead of a second random gather */
@@ -1655,6 +1701,7 @@ struct FinalizeArgs {
 	const double *pose6_in;   /* Euler angles when ps == 0                                                           */
 	uint32_t *bounds_reset;   /* reset for the next iteration (may be 0)                                             */
 	unsigned long long *label_counts_reset;
+	int label_count_sets;     /* 4-counter sets to reset (0 counts as 1) */
 };
 
 /* What warp 0 of the last block does with the finished 28-double system `neq` (shared memory): publish / accumulate
@@ -1697,9 +1744,10 @@ __device__ inline void neq_tail_warp(const double *neq, const FinalizeArgs &fin,
 			fin.bounds_reset[0] = fin.bounds_reset[1] = fin.bounds_reset[2] = 0xFFFFFFFFu;
 			fin.bounds_reset[3] = fin.bounds_reset[4] = fin.bounds_reset[5] = 0u;
 		}
-		if (fin.label_counts_reset) {
-			fin.label_counts_reset[0] = fin.label_counts_reset[1] = fin.label_counts_reset[2] = fin.label_counts_reset[3] = 0ull;
-		}
+	}
+	if (fin.label_counts_reset) {
+		const int nc = 4 * (fin.label_count_sets > 0 ? fin.label_count_sets : 1);
+		for (int k = lane; k < nc; k += 32) fin.label_counts_reset[k] = 0ull;
 	}
 }
 
@@ -1714,16 +1762,17 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(const Src src_
 	Src src = src_in;
 	src.prepare();
 	__shared__ double sm[kNeqThreads / 32][kMomentCount];
-	__shared__ float wl[4];
+	__shared__ float wl[4 * kMaxSegs];
 	__shared__ bool is_last;
-	if (threadIdx.x < 4) {
-		float w = 0.0f;
-		if constexpr (std::is_same<Src, ObsFromNN>::value) {
+	if constexpr (std::is_same<Src, ObsFromNN>::value) {
+		static_assert(4 * kMaxSegs <= kNeqThreads, "one thread per (segment, label) weight");
+		if ((int)threadIdx.x < 4 * src.n_segs) {
 			unsigned long long c = src.label_counts[threadIdx.x];
 			/* P = weight / count, float / int -> float (gpu6DSLAM.cpp:377-393) */
-			w = c ? __fdiv_rn(src.weight[threadIdx.x], (float)(int)c) : 0.0f;
+			wl[threadIdx.x] = c ? __fdiv_rn(src.weight[threadIdx.x & 3], (float)(int)c) : 0.0f;
 		}
-		wl[threadIdx.x] = w;
+	} else {
+		if (threadIdx.x < 4) wl[threadIdx.x] = 0.0f;
 	}
 	__syncthreads();
 	Moments mo;
