@@ -141,7 +141,7 @@ def cpu_baseline(first, second, pose_init, pose2, res, dof, budget_s=20.0, max_i
             "sample": f"{iters} full ICP iterations of the same pair (transform+grid+NN+obs+solve), {dt:.1f} s wall"}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """Reference arm: the reference's own kernels driven the way cudaWrapper.cpp / gpu6DSLAM.cpp drive them."""
     if rank != 0:
         return
@@ -212,10 +212,20 @@ def run_reference(args, rank, world):
                          "sample": f"{steps} full iterations of the same pair, host glue on {cores} threads"},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
+
+
+def _claim_stdout():
+    """Rank 0 prints exactly ONE JSON line on stdout: keep a private handle on the real stdout and send everything any
+    library prints there (NCCL's version banner is a bare printf) to stderr."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -235,7 +245,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import torch
@@ -245,8 +255,6 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     peak_gbs, peak_src = load_peaks()
@@ -388,7 +396,7 @@ def main():
             "cpu_baseline": cpu,
             "result": {"status": int(st.last_status), "translation_error_m": float(np.abs(pose_out[:3, 3] - pose_true[:3, 3]).max())},
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

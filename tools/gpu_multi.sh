@@ -9,4 +9,4 @@ timeout 900 python tools/slam_bench.py --scans 100 --sweeps 3 --dof 6 > $out/${t
 timeout 900 $TR tools/slam_bench.py --scans 24 --kind sick --sweeps 2 --check --dof 6 > $out/${tag}_slam_sick_n$n.json 2> $out/${tag}_slam_sick_n$n.err
 timeout 900 python tools/slam_bench.py --scans 24 --kind sick --sweeps 2 --dof 6 > $out/${tag}_slam_sick_n1.json 2> $out/${tag}_slam_sick_n1.err
 for f in $out/${tag}_*.json; do echo "== $f"; cut -c1-900 $f; done
-tail -3 $out/${tag}_*.err
+tail -n 3 $out/${tag}_*.err

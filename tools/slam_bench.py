@@ -21,7 +21,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def _claim_stdout():
+    """Rank 0 prints exactly ONE JSON line on stdout: keep a private handle on the real stdout and send everything any
+    library prints there (NCCL's version banner is a bare printf) to stderr."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--scans", type=int, default=100)
     ap.add_argument("--kind", default="hdl32")
@@ -42,8 +52,6 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     kw = {}
@@ -110,7 +118,7 @@ def main():
                            "collective": f"one all_reduce of {args.scans}x28 float64 per sweep ({args.scans * 28 * 8} bytes)"},
                 "solved_scans": int((status == 0).sum()), "max_translation_error_m": {"initial": err0, "after": err1},
                 "check": check, "scan_generation_s": gen_s}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
