@@ -139,6 +139,8 @@ struct m3dreg_ctx {
 	/* what the last fused iteration left behind (export hooks) */
 	int last_n_first = 0, last_n_second = 0, last_sorted = 0;
 	bool last_valid = false, last_nn_valid = true;
+	bool nn_pending = false;                      /* nn_seq (query order) is newer than nn (caller order) */
+	const uint32_t *nn_pending_perm = nullptr;
 };
 
 namespace {
@@ -335,6 +337,7 @@ void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *va
 		const int *seg_of_chunk = nullptr)
 {
 	bool two = max_inner != max_outer;
+	if (nn_out == c->nn.p) c->nn_pending = false;      /* the caller-order buffer is being written directly */
 	if (!two && !c->nn_per_thread) {     /* one candidate set (the reference's default caps): warp-shared lookup grid */
 		LAUNCH(c, k_nn_search_grid, (n2 + kNNGThreads - 1) / kNNGThreads, kNNGThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
 				cand_set(c, false), vals, n1, buckets, c->gp, radius, max_outer, prune, c->nn_tune, nn_out, nn_seq, label_counts, c->profiling ? c->eval_counter : nullptr, seg_of_chunk);
@@ -426,6 +429,14 @@ void ndt_queries_and_reduce(m3dreg_ctx *c, int n2, const FinalizeArgs &fin, bool
 			c->partials.p, c->ticket, fin);
 }
 
+/* nn[] in the caller's order from the last fused iteration's query-order result */
+void materialize_nn(m3dreg_ctx *c)
+{
+	if (!c->nn_pending) return;
+	LAUNCH(c, k_scatter_nn, grid_for(c, c->last_n_second, 256), 256, c->nn_pending_perm, c->last_n_second, c->nn_seq.p, c->nn.p);
+	c->nn_pending = false;
+}
+
 /* One registerLastArrivedScan iteration, fully on the device.  first local cloud = (lx, ln), queries already in q_*. */
 void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, int n2,
 		const m3dreg_reg_params *prm, int sort_bits)
@@ -457,8 +468,10 @@ void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int
 		return;
 	}
 	if (prof) cudaEventRecord(c->pev[2], c->stream);
+	/* the caller-order copy of the correspondences is only materialised when somebody asks for it (materialize_nn) */
 	launch_nn(c, c->act_perm, n2, c->vals[c->last_sorted].p, n1, c->buckets.p, prm->search_radius, prm->max_inner, prm->max_outer, 1,
-			c->nn.p, c->nn_seq.p, c->label_counts);
+			nullptr, c->nn_seq.p, c->label_counts);
+	c->nn_pending = true; c->nn_pending_perm = c->act_perm;
 	ObsFromNN src = {};
 	src.n_segs = 1;
 	src.nn = c->nn_seq.p; src.q_xyzl = c->q_xyzl.p; src.l_xyzl = lx; src.m = c->ps->pose1; src.label_counts = c->label_counts;
@@ -1079,6 +1092,7 @@ int m3dreg_icp_iteration_host(m3dreg_ctx *c, const m3dreg_point *first_local, in
 	if (e) return e;
 	if (nn_out) {
 		if (prm->mode == M3DREG_MODE_NDT) CK(cudaMemsetAsync(c->nn.p, 0xFF, (size_t)n2 * sizeof(int), c->stream));
+		else materialize_nn(c);
 		CK(cudaMemcpyAsync(nn_out, c->nn.p, (size_t)n2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
 	}
@@ -1117,6 +1131,7 @@ int m3dreg_export_last_nn(m3dreg_ctx *c, int *nn_out, int nn_cap)
 	if (!c->last_valid || !c->last_nn_valid) return M3DREG_E_BAD_SLOT;   /* NDT has no correspondences */
 	if (nn_cap < c->last_n_second) return M3DREG_E_SIZE_MISMATCH;
 	CK(cudaSetDevice(c->dev));
+	materialize_nn(c);
 	CK(cudaMemcpyAsync(nn_out, c->nn.p, (size_t)c->last_n_second * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	return 0;
@@ -1247,7 +1262,7 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 		fin.label_counts_reset = c->d_seg_counts.p; fin.label_count_sets = nseg;
 		LAUNCH(c, k_normal_equations<ObsFromNN>, grid_for(c, (long long)total, kNeqThreads, 2), kNeqThreads, src, (int)total, c->partials.p, c->ticket, fin);
 		CK(cudaStreamSynchronize(c->stream));      /* the pinned staging block is reused by the next batch */
-		c->last_n_first = A.n; c->last_n_second = segs[nseg - 1].n; c->last_valid = true; c->last_nn_valid = false;
+		c->last_n_first = A.n; c->last_n_second = segs[nseg - 1].n; c->last_valid = true; c->last_nn_valid = false; c->nn_pending = false;
 	}
 	int f = check_flags(c);
 	if (f) return f;

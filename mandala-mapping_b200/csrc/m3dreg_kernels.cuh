@@ -1282,6 +1282,14 @@ __global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_gr
 	}
 }
 
+/* correspondences from query order into the caller's order: out[perm[i]] = in[i] (perm == 0: identity) */
+__global__ void k_scatter_nn(const uint32_t *__restrict__ perm, int n, const int *__restrict__ in, int *__restrict__ out)
+{
+	pdl_enter();
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+		out[perm ? __ldg(perm + i) : (uint32_t)i] = __ldg(in + i);
+}
+
 /* gather a stored scan into query order: out[i] = in[perm[i]] */
 __global__ void k_gather_perm(const uint32_t *__restrict__ perm, int n, const float4 *__restrict__ in_xyzl, const float4 *__restrict__ in_nrm,
 		float4 *__restrict__ out_xyzl, float4 *__restrict__ out_nrm)
