@@ -902,8 +902,14 @@ __global__ void __launch_bounds__(kNNThreads) k_nn_search(const float4 *__restri
 /* heuristics only (the answer is exact for any values): first-round radius = min(res) / rho_div; a warp whose hull has
  * more than hull_min cells AND more than hull_ratio times its largest own box searches per lane instead */
 struct NNTuning { int rho_div, hull_min, hull_ratio; };
-constexpr int kNNCells = 128;       /* hull cells looked up per chunk (segment list capacity) */
-constexpr int kNNStage = 192;       /* candidates staged per batch (multiple of 4) */
+#ifndef M3D_NNG_CELLS
+#define M3D_NNG_CELLS 128
+#endif
+#ifndef M3D_NNG_STAGE
+#define M3D_NNG_STAGE 192
+#endif
+constexpr int kNNCells = M3D_NNG_CELLS;       /* hull cells looked up per chunk (segment list capacity) */
+constexpr int kNNStage = M3D_NNG_STAGE;       /* candidates staged per batch (multiple of 4) */
 constexpr int kNNGThreads = M3D_NNG_THREADS;
 constexpr int kNNWarps = kNNGThreads / 32;
 
