@@ -276,12 +276,43 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1: the all-reduce of the normal-equation blocks runs on its own stream and overlaps the next iteration (nothing
+    # in the registration of a pair waits for it: in a sweep the reduced blocks are consumed once, by the final solve).
+    # Two buffers; the last block of the normal-equation kernel writes the rank's block straight into the buffer
+    # (m3dreg_icp_set_neq_out), and every all-reduce is complete before the closing event of the timed region (drain()).
+    comm = torch.cuda.Stream() if world > 1 else None
+    bufs = [torch.zeros(world * 28, dtype=torch.float64, device="cuda") for _ in range(2)] if world > 1 else []
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_zeroed = [torch.cuda.Event() for _ in range(2)]
+    ev_reduced = [torch.cuda.Event() for _ in range(2)]
+    step_no = [0]
+    if world > 1:
+        for k in range(2):
+            ev_zeroed[k].record(stream)
+            ev_reduced[k].record(stream)
+
     def one_step():
+        if world > 1:
+            k = step_no[0] % 2
+            step_no[0] += 1
+            stream.wait_event(ev_zeroed[k])                     # buffer k was reduced and cleared two steps ago
+            ctx.icp_set_neq_out(bufs[k][rank * 28:])            # the kernel that forms the block writes it there
         ctx.icp_step(1)
         if world > 1:
-            neq_all.zero_()
-            ctx.icp_copy_neq(neq_all[rank * 28:])
-            dist.all_reduce(neq_all)
+            ev_copied[k].record(stream)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev_copied[k])
+                dist.all_reduce(bufs[k])
+                ev_reduced[k].record(comm)
+                neq_all.copy_(bufs[k])                          # the latest reduced blocks, for whoever consumes them
+                bufs[k].zero_()
+                ev_zeroed[k].record(comm)
+
+    def drain():
+        if world > 1:
+            for k in range(2):
+                stream.wait_event(ev_zeroed[k])
+            ctx.icp_set_neq_out(None)
 
     # ---------------- device-resident timing: value ----------------
     ctx.icp_begin(0, 1, pose_init, pose2, prm)
@@ -298,9 +329,19 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         one_step()
+    drain()
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
+    allreduce_ok = None
+    if world > 1:     # the last reduced blocks must hold this rank's last block bit for bit, and every other rank's too
+        mine = torch.zeros(28, dtype=torch.float64, device="cuda")
+        ctx.icp_copy_neq(mine)
+        torch.cuda.synchronize()
+        ok = torch.equal(neq_all[rank * 28:(rank + 1) * 28], mine) and bool((neq_all.view(world, 28)[:, 27] > 0).all())
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        allreduce_ok = bool(flag.item())
     launches = ctx.launch_count - launches1
     clocks = sampler.stop() if rank == 0 else None
     pose_out, st = ctx.icp_end()
@@ -372,12 +413,13 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 geometry / f64 normal equations", "data": "synthetic",
             "config": {
-                "workload": WORKLOADS[args.workload][3] + (f"; one pair per rank x {world} ranks, NCCL all-reduce of the 28-double normal-equation blocks per step" if world > 1 else ""),
+                "workload": WORKLOADS[args.workload][3] + (f"; one pair per rank x {world} ranks, NCCL all-reduce of the 28-double normal-equation blocks per step on a second stream (overlaps the next step, drained inside the timed region)" if world > 1 else ""),
                 "mode": args.mode, "dof": args.dof, "n_first": n1, "n_second": n2, "buckets": nb, "correspondences": nc,
                 "search_radius_m": res, "bucket_m": res, "max_inner": 100, "max_outer": 100,
                 "l2_policy": f"no flush: per-iteration working set {working_set / 1e6:.0f} MB " + ("exceeds" if working_set > 126e6 else "is below") + " the 126 MB L2",
                 "parallelism": f"pairs{world}",
             },
+            "allreduce_check": allreduce_ok,
             "gpu_launches": int(launches),
             "launches_per_step": launches / args.steps,
             "clocks": clocks,

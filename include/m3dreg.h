@@ -249,6 +249,10 @@ int m3dreg_icp_begin(m3dreg_ctx *ctx, int first_slot, int second_slot, const flo
 int m3dreg_icp_step(m3dreg_ctx *ctx, int iterations);
 int m3dreg_icp_end(m3dreg_ctx *ctx, float *pose_first_out, m3dreg_icp_stats *stats);
 int m3dreg_icp_copy_neq(m3dreg_ctx *ctx, double *d_dst);
+/* Alternative without the copy: every following iteration of the fused loop also WRITES its 28-double block to d_dst
+ * (device memory, caller-owned; 0 switches it off) from the kernel that forms it — the buffer an NCCL all-reduce on a
+ * second stream picks up.  With several iterations per icp_step call the last one wins. */
+int m3dreg_icp_set_neq_out(m3dreg_ctx *ctx, double *d_dst);
 
 /* Per-stage CUDA-event timing of the fused iteration (off by default).  Stages: 0 transform+bounds,
  * 1 grid (params, keys, radix sort, bucket table, gather), 2 semantic NN, 3 normal equations + solve.

@@ -43,7 +43,7 @@ EXPORTS = [
     "m3dreg_semantic_nn_host", "m3dreg_register_ls_host", "m3dreg_matrix4_to_euler", "m3dreg_euler_to_matrix",
     "m3dreg_scan_upload", "m3dreg_scan_size", "m3dreg_scan_clear", "m3dreg_icp_pair", "m3dreg_icp_iteration_host",
     "m3dreg_export_last_grid", "m3dreg_export_last_nn", "m3dreg_sweep_zero", "m3dreg_sweep_accumulate",
-    "m3dreg_sweep_solve", "m3dreg_icp_begin", "m3dreg_icp_step", "m3dreg_icp_end", "m3dreg_icp_copy_neq",
+    "m3dreg_sweep_solve", "m3dreg_icp_begin", "m3dreg_icp_step", "m3dreg_icp_end", "m3dreg_icp_copy_neq", "m3dreg_icp_set_neq_out",
     "m3dreg_set_profiling", "m3dreg_get_stage_ms", "m3dreg_set_pruning", "m3dreg_get_nn_evaluations", "m3dreg_get_nn_fallbacks",
 ]
 
@@ -286,6 +286,11 @@ class Context:
 
     def icp_copy_neq(self, d_dst):
         _check(lib().m3dreg_icp_copy_neq(self._h, _p(d_dst)), "m3dreg_icp_copy_neq")
+
+    def icp_set_neq_out(self, d_dst):
+        """Following fused iterations also write their 28-double block to d_dst (device tensor / pointer; None: off)."""
+        ptr = C.c_void_p(0) if d_dst is None else _p(d_dst)
+        _check(lib().m3dreg_icp_set_neq_out(self._h, ptr), "m3dreg_icp_set_neq_out")
 
     def set_profiling(self, enabled: bool):
         _check(lib().m3dreg_set_profiling(self._h, C.c_int(1 if enabled else 0)), "m3dreg_set_profiling")

@@ -139,6 +139,7 @@ struct m3dreg_ctx {
 	/* what the last fused iteration left behind (export hooks) */
 	int last_n_first = 0, last_n_second = 0, last_sorted = 0;
 	bool last_valid = false, last_nn_valid = true;
+	double *neq_out_ext = nullptr;                /* m3dreg_icp_set_neq_out: extra destination of the fused loop's block */
 	bool nn_pending = false;                      /* nn_seq (query order) is newer than nn (caller order) */
 	const uint32_t *nn_pending_perm = nullptr;
 };
@@ -450,7 +451,7 @@ void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int
 		ndt_bucket_stats(c, lx, n1);
 		if (prof) { cudaEventRecord(c->pev[2], c->stream); cudaEventRecord(c->pev[3], c->stream); }
 		FinalizeArgs fin = {};
-		fin.ps = c->ps; fin.neq_out = nullptr; fin.accumulate = 0; fin.solve = 1; fin.dof = prm->dof;
+		fin.ps = c->ps; fin.neq_out = c->neq_out_ext; fin.accumulate = 0; fin.solve = 1; fin.dof = prm->dof;
 		fin.obs_threshold = prm->obs_threshold; fin.pose6_in = nullptr; fin.bounds_reset = c->bounds;
 		fin.label_counts_reset = nullptr;
 		ndt_queries_and_reduce(c, n2, fin, false);
@@ -477,7 +478,7 @@ void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int
 	src.nn = c->nn_seq.p; src.q_xyzl = c->q_xyzl.p; src.l_xyzl = lx; src.m = c->ps->pose1; src.label_counts = c->label_counts;
 	for (int k = 0; k < 4; k++) src.weight[k] = prm->weight[k];
 	FinalizeArgs fin = {};
-	fin.ps = c->ps; fin.neq_out = nullptr; fin.accumulate = 0; fin.solve = 1; fin.dof = prm->dof;
+	fin.ps = c->ps; fin.neq_out = c->neq_out_ext; fin.accumulate = 0; fin.solve = 1; fin.dof = prm->dof;
 	fin.obs_threshold = prm->obs_threshold; fin.pose6_in = nullptr; fin.bounds_reset = c->bounds;
 	fin.label_counts_reset = c->label_counts;
 	if (prof) cudaEventRecord(c->pev[3], c->stream);
@@ -1028,6 +1029,13 @@ int m3dreg_icp_copy_neq(m3dreg_ctx *c, double *d_dst)
 	if (!c || !d_dst) return M3DREG_E_INVALID_ARG;
 	CK(cudaSetDevice(c->dev));
 	CK(cudaMemcpyAsync(d_dst, c->ps->neq, kNeqCount * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+	return 0;
+}
+
+int m3dreg_icp_set_neq_out(m3dreg_ctx *c, double *d_dst)
+{
+	if (!c) return M3DREG_E_INVALID_ARG;
+	c->neq_out_ext = d_dst;
 	return 0;
 }
 
