@@ -51,6 +51,39 @@ def test_icp_pair_multi_iteration_equals_single_steps(pkg, ctx, hdl_pair_small):
     assert np.array_equal(pose_a, pose_b)
 
 
+def test_neq_out_equals_copy(pkg, ctx, hdl_pair_small):
+    """m3dreg_icp_set_neq_out: the block the normal-equation kernel writes into the caller's buffer (what the N > 1 bench
+    hands to NCCL) is the block icp_copy_neq returns, for every iteration; switching it off stops the writes."""
+    import torch
+    first, second, pose_init, pose2, _ = hdl_pair_small
+    ctx.scan_clear()
+    ctx.scan_upload(0, first)
+    ctx.scan_upload(1, second)
+    prm = pkg.default_params(0.5)
+    ctx.icp_begin(0, 1, pose_init, pose2, prm)
+    buf = torch.zeros(3 * 28, dtype=torch.float64, device="cuda")
+    ref = torch.zeros(28, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()          # the context runs on its own stream
+    try:
+        for it in range(3):
+            ctx.icp_set_neq_out(buf[28:])
+            ctx.icp_step(1)
+            ctx.icp_copy_neq(ref)
+            ctx.synchronize()
+            torch.cuda.synchronize()
+            assert torch.equal(buf[28:56], ref) and float(ref[27]) > 100
+            assert float(buf[:28].abs().sum()) == 0.0 and float(buf[56:].abs().sum()) == 0.0
+        ctx.icp_set_neq_out(None)
+        buf.zero_()
+        ctx.icp_step(1)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        assert float(buf.abs().sum()) == 0.0
+    finally:
+        ctx.icp_set_neq_out(None)
+        ctx.icp_end()
+
+
 def test_export_hooks_match_oracle(pkg, oracle, ctx, hdl_pair_small):
     first, second, pose_init, pose2, _ = hdl_pair_small
     ctx.scan_clear()
