@@ -1,6 +1,6 @@
 #!/bin/bash
 # Quick GPU pass: parity tests, bench, launch list and one full ncu capture of one kernel.  bash tools/gpu_quick.sh <tag> [kernel-regex] [skip]
-tag=${1:-q}; rx=${2:-k_nn_search}; skip=${3:-20}
+tag=${1:-q}; rx=${2:-k_nn_search_grid}; skip=${3:-20}
 out=gpurun_out; mkdir -p $out
 timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest_gpu.log
 timeout 600 python bench.py --steps 30 --warmup 5 > $out/${tag}_bench.json 2> $out/${tag}_bench.err
