@@ -644,9 +644,9 @@ __global__ void k_list_cells(const uint32_t *__restrict__ keys, int n, const m3d
  * s = n / cap (lesson_16.cu:628-640), i.e. at most 2*cap-1 CANDIDATES per bucket, and only those can ever be a
  * result.  k_build_candidates gathers exactly those, per bucket, into the bucket's own [begin, begin+ncand) range of
  * the compact arrays (a bucket's candidates always fit inside its own range, so no prefix sum is needed), grouped by
- * (label & 3, sub-cell) bin with a u16 table of bin offsets — layout and exactness argument in nn_core.cuh.  Inside a
- * bin candidates keep ascending sorted position (stable counting sort).  Each record carries its sorted position l
- * for the tie-break and the result.  Two sets exist when the INNER and OUTER caps differ (different strides). */
+ * (label & 3, sub-cell) bin with a u16 table of bin offsets — layout and exactness argument in nn_core.cuh.  The order
+ * inside a bin is arbitrary (counting sort with shared-memory atomics); each record carries its sorted position l for
+ * the tie-break and the result, which is all the search needs.  Two sets exist when the INNER and OUTER caps differ (different strides). */
 constexpr int kBuildWarps = 4;
 constexpr int kBuildPerLane = 7;          /* candidates per lane held in registers (224 per warp pass >= 2 * 100 - 1, the default caps) */
 constexpr int kBuildTabMax = 4 * 64 + 1;   /* bins + 1 at the finest level */
@@ -664,7 +664,6 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 	const int iter = candidate_stride(npts, cap);
 	const int ncand = (npts + iter - 1) / iter;
 	const int level = tables ? nn_level(npts) : -1;
-	const uint32_t lt = (1u << lane) - 1u;
 	const int nbins = level >= 0 ? (4 << (3 * level)) : 0;
 	const float wx = nn_subcell_width(g.rx, level < 0 ? 0 : level), wy = nn_subcell_width(g.ry, level < 0 ? 0 : level),
 			wz = nn_subcell_width(g.rz, level < 0 ? 0 : level);
@@ -717,19 +716,16 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 		}
 		return;
 	}
-	/* pass 1: bin histogram */
+	/* pass 1: bin histogram (shared-memory atomics: independent of each other, no warp-wide step per candidate) */
 	for (int c0 = 0; c0 < ncand; c0 += 32 * kBuildPerLane) {
 		if (!single) load(c0);
 #pragma unroll
 		for (int j = 0; j < kBuildPerLane; j++) {
-			if (c0 + j * 32 >= ncand) break;
 			int k = c0 + j * 32 + lane;
-			bool valid = k < ncand;
-			uint32_t peers = __match_any_sync(full, bin[j]);
-			if (valid && lane == __ffs(peers) - 1) hist[bin[j]] += __popc(peers);
-			__syncwarp();
+			if (k < ncand) atomicAdd(&hist[bin[j]], 1u);
 		}
 	}
+	__syncwarp();
 	/* exclusive scan of the nbins + 1 table entries (9 consecutive entries per lane cover 288 >= 257), table out */
 	{
 		uint32_t h[9], sum = 0;
@@ -752,21 +748,14 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 		}
 		__syncwarp();
 	}
-	/* pass 2: stable placement (ascending sorted position inside a bin) */
+	/* pass 2: placement.  The order of the candidates INSIDE a bin is whatever the atomics hand out: the search takes
+	 * the lexicographic minimum of (dist, l) with l carried in the record, so it does not depend on it */
 	for (int c0 = 0; c0 < ncand; c0 += 32 * kBuildPerLane) {
 		if (!single) load(c0);
 #pragma unroll
 		for (int j = 0; j < kBuildPerLane; j++) {
-			if (c0 + j * 32 >= ncand) break;
 			int k = c0 + j * 32 + lane;
-			bool valid = k < ncand;
-			uint32_t peers = __match_any_sync(full, bin[j]);
-			int leader = __ffs(peers) - 1;
-			uint32_t old = 0;
-			if (valid && lane == leader) { old = hist[bin[j]]; hist[bin[j]] = old + __popc(peers); }
-			old = __shfl_sync(full, old, leader);
-			if (valid) store(begin + (int)(old + __popc(peers & lt)), k, v[j]);
-			__syncwarp();
+			if (k < ncand) store(begin + (int)atomicAdd(&hist[bin[j]], 1u), k, v[j]);
 		}
 	}
 	__syncwarp();
