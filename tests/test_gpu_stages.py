@@ -203,6 +203,47 @@ def test_warp_shared_search_on_coherent_queries(pkg, synth, oracle, ctx):
         ctx.set_profiling(False)
 
 
+def test_c2_full_size_paths_agree(pkg, synth, oracle, ctx, ref):
+    """BASELINE config C2 at full size (1 048 576-point rotating-SICK pair, 1.0 m): three different code paths must give
+    the same 1 M correspondences — the warp-shared search on spatially sorted queries, the same kernel on randomly
+    permuted queries (scattered warps: per-thread fallback), and the per-thread kernel (M3DREG_NN_PER_THREAD=1) — and
+    they must equal the reference's own kernel run on the same box."""
+    import os
+    from tests import refwrap
+    first, second, pose_init, pose2, _ = synth.scan_pair("sick", seed=42)
+    fg = oracle.transform_cloud(first, pose_init)
+    sg = oracle.transform_cloud(second, pose2)
+    order = _spatial_order(sg, cell=0.02)
+    sq = sg[order].copy()
+    ctx.set_profiling(True)
+    try:
+        ctx.nn_fallbacks(reset=True)
+        nn_sorted = ctx.semantic_nn_host(fg, sq, 1.0, 1.0)
+        fb_sorted = ctx.nn_fallbacks(reset=True)
+        perm = np.random.default_rng(3).permutation(len(sg))
+        nn_perm = ctx.semantic_nn_host(fg, sg[perm].copy(), 1.0, 1.0)
+        fb_perm = ctx.nn_fallbacks(reset=True)
+    finally:
+        ctx.set_profiling(False)
+    assert fb_sorted < 0.05 * len(sg) and fb_perm > 0.9 * len(sg), (fb_sorted, fb_perm)    # really two different paths
+    nn_a = np.empty_like(nn_sorted); nn_a[order] = nn_sorted
+    nn_b = np.empty_like(nn_perm); nn_b[perm] = nn_perm
+    assert np.array_equal(nn_a, nn_b)
+    os.environ["M3DREG_NN_PER_THREAD"] = "1"
+    try:
+        c2 = pkg.Context(0)
+    finally:
+        del os.environ["M3DREG_NN_PER_THREAD"]
+    try:
+        nn_c = c2.semantic_nn_host(fg, sg, 1.0, 1.0)
+    finally:
+        c2.close()
+    assert np.array_equal(nn_a, nn_c)
+    assert (nn_a >= 0).mean() > 0.9
+    nn_r, *_ = refwrap.nn_search_host(fg, sg, 1.0, 1.0, 1.0, 100, 100)
+    assert np.array_equal(nn_a, nn_r)
+
+
 def test_transform_bit_exact(pkg, synth, oracle, ctx):
     import torch
     c = synth.random_cloud(10007, seed=31)
