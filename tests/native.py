@@ -72,3 +72,18 @@ def nn_emul_search(first, second, table, buckets, gp, radius, max_inner=100, max
                             C.c_float(radius), C.c_int(max_inner), C.c_int(max_outer), C.c_int(1 if prune else 0), vp(nn), C.byref(ev))
     assert rc == 0
     return nn, int(ev.value)
+
+
+def nn_emul_search_warp(first, second, table, buckets, gp, radius, cap=100, prune=True):
+    """Warp-level emulation of k_nn_search_grid (tests/csrc/nn_emul.cpp); returns (nn, fallback queries, re-scans)."""
+    import numpy as np
+    lib = C.CDLL(build_nn_emul())
+    first = np.ascontiguousarray(first); second = np.ascontiguousarray(second)
+    table = np.ascontiguousarray(table); buckets = np.ascontiguousarray(buckets); gp = np.ascontiguousarray(gp)
+    nn = np.full(len(second), -7, dtype=np.int32)
+    fb, rs = C.c_longlong(0), C.c_longlong(0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.emul_nn_search_warp(vp(first), C.c_int(len(first)), vp(second), C.c_int(len(second)), vp(table), vp(buckets), vp(gp),
+                                 C.c_float(radius), C.c_int(cap), C.c_int(1 if prune else 0), vp(nn), C.byref(fb), C.byref(rs))
+    assert rc == 0
+    return nn, int(fb.value), int(rs.value)
