@@ -137,8 +137,19 @@ def cpu_baseline(first, second, pose_init, pose2, res, dof, budget_s=20.0, max_i
         iters += 1
     dt = time.perf_counter() - t0
     pts = (len(first) + len(second)) * iters
-    return {"value": pts / dt, "unit": "points/s", "cores": oracle.lib().orc_num_threads(), "kind": "port",
-            "sample": f"{iters} full ICP iterations of the same pair (transform+grid+NN+obs+solve), {dt:.1f} s wall"}
+    cores = oracle.lib().orc_num_threads()
+    out = {"value": pts / dt, "unit": "points/s", "cores": cores, "kind": "port",
+           "sample": f"{iters} full ICP iterations of the same pair (transform+grid+NN+obs+solve), {dt:.1f} s wall"}
+    # also a single-thread figure (one iteration, bounded)
+    try:
+        oracle.lib().orc_set_num_threads(1)
+        t1 = time.perf_counter()
+        oracle.icp_iteration(first, sg, pose_init.copy(), prm)
+        out["single_thread"] = {"value": (len(first) + len(second)) / (time.perf_counter() - t1), "unit": "points/s", "cores": 1,
+                                "sample": "1 full ICP iteration of the same pair"}
+    finally:
+        oracle.lib().orc_set_num_threads(cores)
+    return out
 
 
 def run_reference(args, rank, world, out):
