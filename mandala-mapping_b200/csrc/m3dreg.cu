@@ -16,6 +16,7 @@
 #include <algorithm>
 
 #include "m3dreg_kernels.cuh"
+#include "grid_build.cuh"
 
 using namespace m3d;
 
@@ -35,6 +36,7 @@ struct Scan {
 	uint32_t *perm = nullptr;   /* perm[sorted position] = original index                                         */
 	int n = 0;
 	size_t cap = 0;
+	float diag = 0.0f;          /* diagonal of the local bounding box: bounds the extent of the scan under ANY rigid pose */
 	void release()
 	{
 		if (xyzl) cudaFree(xyzl);
@@ -90,21 +92,29 @@ struct m3dreg_ctx {
 	/* arena */
 	DevBuf<float4> g_xyzl, g_nrm, ci_xyzl, ci_nrm, co_xyzl, co_nrm, q_xyzl, q_nrm, l_xyzl, l_nrm;
 	DevBuf<unsigned short> ci_tab, co_tab;           /* per-bucket bin offset tables of the candidate sets (nn_core.cuh) */
-	DevBuf<uint32_t> keys[2], vals[2], hist, digit_tot;
+	DevBuf<float4> ci_loc, co_loc;                   /* candidates' local coordinates + original index (moment epilogue of the search) */
+	DevBuf<int> bcount, bbegin;                      /* grid megakernel: dense per-bucket counts (zero between launches), slice-relative begins */
+	DevBuf<GridBlockRec> brec;
+	int coop_pdl = -1;                               /* cooperative + programmatic launch accepted together? (-1: not tried yet) */
+	DevBuf<uint32_t> keys[2], vals[2], hist, digit_tot, cell_list;
 	DevBuf<m3dreg_bucket> buckets;
-	DevBuf<int> nn, nn_seq;
+	DevBuf<int> nn;
+	DevBuf<float4> obs_rec;                          /* per query, query order: matched point (local frame) + its index (k_nn_search*) */
+	int grid_legacy = 0;                             /* env M3DREG_GRID_LEGACY=1: the multi-kernel grid build of round 1 (A/B runs) */
+	cudaError_t launch_err = cudaSuccess;            /* first failed kernel launch since the last report */
 	DevBuf<m3dreg_point> aos_a, aos_b;
 	DevBuf<m3dreg_obs_nn> obs;
 	DevBuf<double> partials, ndt_acc, ndt_qacc;
 	DevBuf<m3dreg_hash_element> table;
 	DevBuf<float> d_poses1;      /* sweep: round-tripped poses, 16 floats per scan */
 	DevBuf<double> d_pose6;      /* sweep: tx,ty,tz,om,fi,ka per scan             */
+	DevBuf<int> d_sweep_status;  /* sweep: per-scan solve status                  */
 
 	/* batched sweep step: segment table, chunk -> segment map, per-segment label counters, pinned staging */
 	DevBuf<SweepSeg> d_segs;
 	DevBuf<int> d_seg_of_chunk;
 	DevBuf<unsigned long long> d_seg_counts;
-	void *h_sweep = nullptr;     /* pinned: kMaxSegs SweepSeg + chunk map */
+	void *h_sweep = nullptr;     /* pinned: a sweep's round-tripped poses + every batch's segment table */
 	size_t h_sweep_bytes = 0;
 
 	/* small device block */
@@ -115,6 +125,7 @@ struct m3dreg_ctx {
 	unsigned long long *label_counts = nullptr;
 	unsigned int *ticket = nullptr;
 	unsigned int *cell_count = nullptr;           /* number of searchable buckets in the compact list */
+	unsigned int *grid_bar = nullptr;             /* grid barrier of k_grid_build: arrival count, generation */
 	unsigned long long *eval_counter = nullptr;   /* candidates staged by the NN search (warp-level), diagnostic */
 	int use_pdl = 1;             /* programmatic dependent launch for every kernel (env M3DREG_NO_PDL=1 disables) */
 	int nn_per_thread = 0;       /* test switch (env M3DREG_NN_PER_THREAD=1): k_nn_search instead of k_nn_search_grid */
@@ -140,7 +151,7 @@ struct m3dreg_ctx {
 	int last_n_first = 0, last_n_second = 0, last_sorted = 0;
 	bool last_valid = false, last_nn_valid = true;
 	double *neq_out_ext = nullptr;                /* m3dreg_icp_set_neq_out: extra destination of the fused loop's block */
-	bool nn_pending = false;                      /* nn_seq (query order) is newer than nn (caller order) */
+	bool nn_pending = false;                      /* obs_rec (query order) is newer than nn (caller order) */
 	const uint32_t *nn_pending_perm = nullptr;
 };
 
@@ -171,10 +182,51 @@ inline void launch_kernel(m3dreg_ctx *c, void (*kernel)(KArgs...), int grid, int
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = c->use_pdl ? 1 : 0;
-	cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+	cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+	if (e != cudaSuccess && c->launch_err == cudaSuccess) c->launch_err = e;
 	c->launches++;
 }
 #define LAUNCH(ctx, kernel, grid, block, ...) launch_kernel((ctx), kernel, (grid), (block), __VA_ARGS__)
+
+/* status of the launches issued since the last call (launch errors are sticky in the context until reported) */
+inline int launch_status(m3dreg_ctx *c)
+{
+	cudaError_t e = c->launch_err;
+	c->launch_err = cudaSuccess;
+	if (e == cudaSuccess) e = cudaGetLastError();
+	return (int)e;
+}
+
+/* k_grid_build: one block per SM, all co-resident (cooperative launch: the kernel synchronises across the grid), chained
+ * to the previous kernel with programmatic stream serialisation like every other launch when the driver takes both
+ * attributes together (probed once per context). */
+inline void launch_grid_build(m3dreg_ctx *c, const GridBuildArgs &a)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)c->sm_count, 1, 1);
+	cfg.blockDim = dim3((unsigned)kGbThreads, 1, 1);
+	cfg.dynamicSmemBytes = 0;
+	cfg.stream = c->stream;
+	cudaLaunchAttribute attr[2];
+	attr[0].id = cudaLaunchAttributeCooperative;
+	attr[0].val.cooperative = 1;
+	attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[1].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cudaError_t e = cudaErrorUnknown;
+	if (c->use_pdl && c->coop_pdl != 0) {
+		cfg.numAttrs = 2;
+		e = cudaLaunchKernelEx(&cfg, k_grid_build, a);
+		if (c->coop_pdl < 0) c->coop_pdl = (e == cudaSuccess) ? 1 : 0;
+		if (e != cudaSuccess) cudaGetLastError();
+	}
+	if (e != cudaSuccess) {
+		cfg.numAttrs = 1;
+		e = cudaLaunchKernelEx(&cfg, k_grid_build, a);
+	}
+	if (e != cudaSuccess && c->launch_err == cudaSuccess) c->launch_err = e;
+	c->launches++;
+}
 
 int bits_for(long long nb)
 {
@@ -225,8 +277,44 @@ int ensure_first(m3dreg_ctx *c, size_t n)
 		if ((e = c->vals[k].ensure(n))) return e;
 	}
 	size_t tiles = (n + 1023) / 1024 + 1;
-	if ((e = c->hist.ensure(4 * tiles * kRadixSize))) return e;      /* one digit-by-tile matrix per radix pass */
+	size_t hist_need = 4 * tiles * kRadixSize;                       /* one digit-by-tile matrix per radix pass */
+	if (hist_need < (size_t)3 * c->sm_count * kGbRadix) hist_need = (size_t)3 * c->sm_count * kGbRadix;   /* k_grid_build: [block][digit] x 3 passes */
+	if ((e = c->hist.ensure(hist_need))) return e;
+	if ((e = c->brec.ensure((size_t)c->sm_count))) return e;
+	if ((e = c->cell_list.ensure(n))) return e;                      /* searchable buckets: at most one per point */
 	return 0;
+}
+
+/* Dense bucket table + the megakernel's count arrays for `cap` buckets.  bcount must be all zero between launches:
+ * a (re)allocation is cleared here, k_grid_build leaves it clean, rearm_grid() clears it after a rejected grid. */
+int ensure_buckets(m3dreg_ctx *c, size_t cap, bool ndt)
+{
+	int e;
+	if ((e = c->buckets.ensure(cap))) return e;
+	if (c->bcount.cap < c->buckets.cap) {
+		if ((e = c->bcount.ensure(c->buckets.cap))) return e;
+		cudaError_t ce = cudaMemsetAsync(c->bcount.p, 0, c->bcount.cap * sizeof(int), c->stream);
+		if (ce != cudaSuccess) return (int)ce;
+	}
+	if ((e = c->bbegin.ensure(c->buckets.cap))) return e;
+	if (ndt) {
+		if ((e = c->ndt_acc.ensure(c->buckets.cap * 12))) return e;
+		if ((e = c->ndt_qacc.ensure(c->buckets.cap * 4))) return e;
+	}
+	return 0;
+}
+
+/* Bucket capacity that holds the grid of a scan under ANY rigid pose: every axis extent of the transformed cloud is at
+ * most the diagonal of its local bounding box, so nb_axis <= (diag + 2 ext) / res + 1 (+2: float slack).  No read-back,
+ * no synchronisation (round 1 sized the table from the initial box: one D2H + sync per fused loop and per scan of a
+ * sweep, and a pose that drifted out of the margin aborted the loop). */
+long long bucket_capacity_for(float diag, const m3dreg_reg_params *prm)
+{
+	double per_axis = floor(((double)diag * 1.0001 + 2.0 * (double)prm->bbox_extension) / (double)prm->bucket_size) + 3.0;
+	if (!(per_axis >= 1.0)) per_axis = 1.0;
+	double cap = per_axis * per_axis * per_axis;
+	if (cap > 2147483647.0) cap = 2147483647.0;
+	return (long long)cap;
 }
 
 int ensure_second(m3dreg_ctx *c, size_t n)
@@ -235,7 +323,7 @@ int ensure_second(m3dreg_ctx *c, size_t n)
 	if ((e = c->q_xyzl.ensure(n))) return e;
 	if ((e = c->q_nrm.ensure(n))) return e;
 	if ((e = c->nn.ensure(n))) return e;
-	if ((e = c->nn_seq.ensure(n))) return e;
+	if ((e = c->obs_rec.ensure(n))) return e;
 	return 0;
 }
 
@@ -306,10 +394,12 @@ int ensure_candidates(m3dreg_ctx *c, size_t n1, int max_inner, int max_outer)
 	int e;
 	if ((e = c->ci_xyzl.ensure(n1))) return e;
 	if ((e = c->ci_nrm.ensure(n1))) return e;
+	if ((e = c->ci_loc.ensure(n1))) return e;
 	if ((e = c->ci_tab.ensure(2 * n1 + 8))) return e;
 	if (max_inner != max_outer) {
 		if ((e = c->co_xyzl.ensure(n1))) return e;
 		if ((e = c->co_nrm.ensure(n1))) return e;
+		if ((e = c->co_loc.ensure(n1))) return e;
 		if ((e = c->co_tab.ensure(2 * n1 + 8))) return e;
 	}
 	return 0;
@@ -318,40 +408,43 @@ int ensure_candidates(m3dreg_ctx *c, size_t n1, int max_inner, int max_outer)
 CandSet cand_set(m3dreg_ctx *c, bool outer)
 {
 	CandSet s;
-	if (outer) { s.xyzl = c->co_xyzl.p; s.nrm = c->co_nrm.p; s.tab = c->co_tab.p; }
-	else { s.xyzl = c->ci_xyzl.p; s.nrm = c->ci_nrm.p; s.tab = c->ci_tab.p; }
+	if (outer) { s.xyzl = c->co_xyzl.p; s.nrm = c->co_nrm.p; s.tab = c->co_tab.p; s.loc = c->co_loc.p; }
+	else { s.xyzl = c->ci_xyzl.p; s.nrm = c->ci_nrm.p; s.tab = c->ci_tab.p; s.loc = c->ci_loc.p; }
 	return s;
 }
 
-/* gp must already be on the device (c->gp); src = the gridded cloud in original order; cell_list / c->cell_count
- * hold the searchable buckets. */
+/* gp must already be on the device (c->gp); src = the gridded cloud in original order (global frame); loc_src = the same
+ * cloud in the frame the moment reduction wants (local; 0 = src); cell_list / c->cell_count hold the searchable buckets. */
 void build_candidates(m3dreg_ctx *c, const uint32_t *vals, const m3dreg_bucket *buckets, const uint32_t *cell_list,
-		const float4 *src_xyzl, const float4 *src_nrm, const float *nrm_m, int max_inner, int max_outer)
+		const float4 *src_xyzl, const float4 *src_nrm, const float4 *loc_src, const float *nrm_m, int max_inner, int max_outer)
 {
 	bool two = max_inner != max_outer;
-	LAUNCH(c, k_build_candidates, c->sm_count * 7, kBuildWarps * 32, vals, c->gp, buckets, cell_list, c->cell_count, src_xyzl, src_nrm, nrm_m,
+	LAUNCH(c, k_build_candidates, c->sm_count * 7, kBuildWarps * 32, vals, c->gp, buckets, cell_list, c->cell_count, src_xyzl, src_nrm, loc_src, nrm_m,
 			max_inner, max_outer, cand_set(c, false), cand_set(c, two), two ? 1 : 0);
 }
 
+/* src_xyzl: the first cloud as the moment reduction wants it (local frame in the fused loops), original order */
 void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *vals, int n1, const m3dreg_bucket *buckets,
-		float radius, int max_inner, int max_outer, int prune, int *nn_out, int *nn_seq, unsigned long long *label_counts,
-		const int *seg_of_chunk = nullptr)
+		float radius, int max_inner, int max_outer, int prune, int *nn_out, float4 *obs_rec, const float4 *src_xyzl,
+		unsigned long long *label_counts, const int *seg_of_chunk = nullptr)
 {
 	bool two = max_inner != max_outer;
 	if (nn_out == c->nn.p) c->nn_pending = false;      /* the caller-order buffer is being written directly */
 	if (!two && !c->nn_per_thread) {     /* one candidate set (the reference's default caps): warp-shared lookup grid */
 		LAUNCH(c, k_nn_search_grid, (n2 + kNNGThreads - 1) / kNNGThreads, kNNGThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
-				cand_set(c, false), vals, n1, buckets, c->gp, radius, max_outer, prune, c->nn_tune, nn_out, nn_seq, label_counts, c->profiling ? c->eval_counter : nullptr, seg_of_chunk);
+				cand_set(c, false), vals, n1, buckets, c->gp, radius, max_outer, prune, c->nn_tune, nn_out, obs_rec, src_xyzl, label_counts,
+				c->profiling ? c->eval_counter : nullptr, seg_of_chunk);
 		return;
 	}
 	LAUNCH(c, k_nn_search, (n2 + kNNThreads - 1) / kNNThreads, kNNThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
-			cand_set(c, false), cand_set(c, two), vals, n1, buckets, c->gp, radius, max_inner, max_outer, prune, nn_out, nn_seq,
+			cand_set(c, false), cand_set(c, two), vals, n1, buckets, c->gp, radius, max_inner, max_outer, prune, nn_out, obs_rec, src_xyzl,
 			label_counts, c->profiling ? c->eval_counter : nullptr, seg_of_chunk);
 }
 
-/* Grid of the (already transformed) first cloud in g_*: params (device) from bounds, keys, sort, dense table,
- * sorted SoA copy.  bounds must already hold the reduced box. */
-void build_grid_fused(m3dreg_ctx *c, int n1, const m3dreg_reg_params *prm, int sort_bits, const float4 *src_nrm, const float *nrm_m)
+/* Round-1 grid build (multi-kernel), kept for the stage-level entry points and A/B runs (M3DREG_GRID_LEGACY=1): grid of
+ * the (already transformed) first cloud in g_*: params (device) from bounds, keys, sort, dense table, candidate sets.
+ * bounds must already hold the reduced box. */
+void build_grid_legacy(m3dreg_ctx *c, int n1, const m3dreg_reg_params *prm, int sort_bits, const float4 *src_nrm, const float4 *loc_src, const float *nrm_m)
 {
 	SortPlan sp = plan_sort(n1, sort_bits);
 	if (sp.items == kSortItemsBig)
@@ -361,12 +454,32 @@ void build_grid_fused(m3dreg_ctx *c, int n1, const m3dreg_reg_params *prm, int s
 		LAUNCH(c, k_grid_head<4>, sp.tiles, kSortThreads, c->g_xyzl.p, n1, c->bounds, prm->bucket_size, prm->bucket_size, prm->bucket_size,
 				prm->bbox_extension, (long long)c->buckets.cap, c->gp, c->flags, c->cell_count, c->buckets.p, c->keys[0].p, sp.tiles, sp.passes, c->hist.p);
 	int cur = sort_by_bucket(c, n1, sort_bits, c->gp, true, true);
-	/* the spare ping-pong key buffer holds the compact list of searchable buckets */
 	LAUNCH(c, k_finalize_grid, grid_for(c, n1, 256), 256, c->keys[cur].p, c->vals[cur].p, n1, c->gp, c->buckets.p,
-			(m3dreg_hash_element *)nullptr, c->keys[cur ^ 1].p, c->cell_count);
+			(m3dreg_hash_element *)nullptr, c->cell_list.p, c->cell_count);
 	if (prm->mode != M3DREG_MODE_NDT)
-		build_candidates(c, c->vals[cur].p, c->buckets.p, c->keys[cur ^ 1].p, c->g_xyzl.p, src_nrm, nrm_m, prm->max_inner, prm->max_outer);
+		build_candidates(c, c->vals[cur].p, c->buckets.p, c->cell_list.p, c->g_xyzl.p, src_nrm, loc_src, nrm_m, prm->max_inner, prm->max_outer);
 	c->last_sorted = cur;
+}
+
+/* The grid of one iteration as ONE launch (grid_build.cuh): transform of (lx, ln) by the device pose + bounding box,
+ * grid parameters, keys, stable sort, dense bucket table, candidate sets.  pose == 0: the cloud is already global.
+ * The transformed cloud is only kept (g_xyzl) when keep_global is set (NDT statistics). */
+void build_grid_mega(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, const float *pose, const m3dreg_reg_params *prm, bool keep_global)
+{
+	GridBuildArgs a = {};
+	a.lx = lx; a.ln = ln; a.n = n1; a.pose = pose;
+	a.res = prm->bucket_size; a.ext = prm->bbox_extension;
+	a.bucket_cap = (long long)c->buckets.cap;
+	a.max_inner = prm->max_inner; a.max_outer = prm->max_outer;
+	a.build_cands = prm->mode != M3DREG_MODE_NDT ? 1 : 0;
+	a.g_xyzl = keep_global ? c->g_xyzl.p : nullptr;
+	a.keys[0] = c->keys[0].p; a.keys[1] = c->keys[1].p; a.vals[0] = c->vals[0].p; a.vals[1] = c->vals[1].p;
+	a.hist = c->hist.p; a.bcount = c->bcount.p; a.bbegin = c->bbegin.p; a.buckets = c->buckets.p;
+	a.cell_list = c->cell_list.p; a.cell_count = c->cell_count; a.brec = c->brec.p; a.gp = c->gp; a.flags = c->flags;
+	a.bounds = c->bounds; a.bar = c->grid_bar;
+	a.ci = cand_set(c, false); a.co = cand_set(c, prm->max_inner != prm->max_outer);
+	launch_grid_build(c, a);
+	c->last_sorted = 1;
 }
 
 /* Reads the reduced bounds back (one sync), sizes the dense bucket table with a margin so the box may drift
@@ -383,12 +496,8 @@ int plan_buckets(m3dreg_ctx *c, const m3dreg_reg_params *prm, int *sort_bits)
 	long long cap = (long long)(gp.number_of_buckets_X + 4) * (gp.number_of_buckets_Y + 4) * (gp.number_of_buckets_Z + 4);
 	if (cap > 2147483647LL) cap = 2147483647LL;
 	if (gp.number_of_buckets > cap) return M3DREG_E_TOO_MANY_BUCKETS;
-	int e = c->buckets.ensure((size_t)cap);
+	int e = ensure_buckets(c, (size_t)cap, prm->mode == M3DREG_MODE_NDT);
 	if (e) return e;
-	if (prm->mode == M3DREG_MODE_NDT) {
-		if ((e = c->ndt_acc.ensure(c->buckets.cap * 12))) return e;
-		if ((e = c->ndt_qacc.ensure(c->buckets.cap * 4))) return e;
-	}
 	*sort_bits = bits_for((long long)c->buckets.cap);
 	return 0;
 }
@@ -430,70 +539,68 @@ void ndt_queries_and_reduce(m3dreg_ctx *c, int n2, const FinalizeArgs &fin, bool
 			c->partials.p, c->ticket, fin);
 }
 
-/* nn[] in the caller's order from the last fused iteration's query-order result */
+/* nn[] in the caller's order from the last fused iteration's query-order records */
 void materialize_nn(m3dreg_ctx *c)
 {
 	if (!c->nn_pending) return;
-	LAUNCH(c, k_scatter_nn, grid_for(c, c->last_n_second, 256), 256, c->nn_pending_perm, c->last_n_second, c->nn_seq.p, c->nn.p);
+	LAUNCH(c, k_scatter_nn, grid_for(c, c->last_n_second, 256), 256, c->nn_pending_perm, c->last_n_second, c->obs_rec.p, c->nn.p);
 	c->nn_pending = false;
 }
 
-/* One registerLastArrivedScan iteration, fully on the device.  first local cloud = (lx, ln), queries already in q_*. */
+void stage_events_collect(m3dreg_ctx *c)
+{
+	cudaEventRecord(c->pev[4], c->stream);
+	cudaEventSynchronize(c->pev[4]);
+	for (int k = 0; k < M3DREG_STAGE_COUNT; k++) {
+		float ms = 0.0f;
+		cudaEventElapsedTime(&ms, c->pev[k], c->pev[k + 1]);
+		c->stage_ms[k] += ms;
+	}
+	c->stage_iters++;
+}
+
+/* One registerLastArrivedScan iteration, fully on the device: THREE launches (k_grid_build, k_nn_search_grid,
+ * k_normal_equations).  first local cloud = (lx, ln), queries already in q_*. */
 void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, int n2,
 		const m3dreg_reg_params *prm, int sort_bits)
 {
 	const bool prof = c->profiling;
+	const bool ndt = prm->mode == M3DREG_MODE_NDT;
 	if (prof) cudaEventRecord(c->pev[0], c->stream);
-	LAUNCH(c, k_transform_soa<true>, grid_for(c, n1, 256), 256, lx, ln, n1, c->ps->pose1, c->g_xyzl.p, (float4 *)nullptr, c->bounds);
-	if (prof) cudaEventRecord(c->pev[1], c->stream);
-	build_grid_fused(c, n1, prm, sort_bits, ln, c->ps->pose1);
-	if (prm->mode == M3DREG_MODE_NDT) {
+	if (c->grid_legacy) {
+		LAUNCH(c, k_transform_soa<true>, grid_for(c, n1, 256), 256, lx, ln, n1, c->ps->pose1, c->g_xyzl.p, (float4 *)nullptr, c->bounds);
+		if (prof) cudaEventRecord(c->pev[1], c->stream);
+		build_grid_legacy(c, n1, prm, sort_bits, ln, lx, c->ps->pose1);
+	} else {
+		if (prof) cudaEventRecord(c->pev[1], c->stream);      /* the transform is part of the grid launch */
+		build_grid_mega(c, lx, ln, n1, c->ps->pose1, prm, ndt);
+	}
+	FinalizeArgs fin = {};
+	fin.ps = c->ps; fin.neq_out = c->neq_out_ext; fin.accumulate = 0; fin.solve = 1; fin.dof = prm->dof;
+	fin.obs_threshold = prm->obs_threshold; fin.pose6_in = nullptr; fin.bounds_reset = c->bounds;
+	if (ndt) {
 		ndt_bucket_stats(c, lx, n1);
 		if (prof) { cudaEventRecord(c->pev[2], c->stream); cudaEventRecord(c->pev[3], c->stream); }
-		FinalizeArgs fin = {};
-		fin.ps = c->ps; fin.neq_out = c->neq_out_ext; fin.accumulate = 0; fin.solve = 1; fin.dof = prm->dof;
-		fin.obs_threshold = prm->obs_threshold; fin.pose6_in = nullptr; fin.bounds_reset = c->bounds;
 		fin.label_counts_reset = nullptr;
 		ndt_queries_and_reduce(c, n2, fin, false);
-		if (prof) {
-			cudaEventRecord(c->pev[4], c->stream);
-			cudaEventSynchronize(c->pev[4]);
-			for (int k = 0; k < M3DREG_STAGE_COUNT; k++) {
-				float ms = 0.0f;
-				cudaEventElapsedTime(&ms, c->pev[k], c->pev[k + 1]);
-				c->stage_ms[k] += ms;
-			}
-			c->stage_iters++;
-		}
+		if (prof) stage_events_collect(c);
 		c->last_n_first = n1; c->last_n_second = n2; c->last_valid = true; c->last_nn_valid = false;
 		return;
 	}
 	if (prof) cudaEventRecord(c->pev[2], c->stream);
 	/* the caller-order copy of the correspondences is only materialised when somebody asks for it (materialize_nn) */
 	launch_nn(c, c->act_perm, n2, c->vals[c->last_sorted].p, n1, c->buckets.p, prm->search_radius, prm->max_inner, prm->max_outer, 1,
-			nullptr, c->nn_seq.p, c->label_counts);
+			nullptr, c->obs_rec.p, lx, c->label_counts);
 	c->nn_pending = true; c->nn_pending_perm = c->act_perm;
-	ObsFromNN src = {};
+	ObsFromRec src = {};
 	src.n_segs = 1;
-	src.nn = c->nn_seq.p; src.q_xyzl = c->q_xyzl.p; src.l_xyzl = lx; src.m = c->ps->pose1; src.label_counts = c->label_counts;
+	src.rec = c->obs_rec.p; src.q_xyzl = c->q_xyzl.p; src.m = c->ps->pose1; src.label_counts = c->label_counts;
 	for (int k = 0; k < 4; k++) src.weight[k] = prm->weight[k];
-	FinalizeArgs fin = {};
-	fin.ps = c->ps; fin.neq_out = c->neq_out_ext; fin.accumulate = 0; fin.solve = 1; fin.dof = prm->dof;
-	fin.obs_threshold = prm->obs_threshold; fin.pose6_in = nullptr; fin.bounds_reset = c->bounds;
 	fin.label_counts_reset = c->label_counts;
 	if (prof) cudaEventRecord(c->pev[3], c->stream);
-	LAUNCH(c, k_normal_equations<ObsFromNN>, grid_for(c, n2, kNeqThreads, 2), kNeqThreads, src, n2, c->partials.p, c->ticket, fin);
+	LAUNCH(c, k_normal_equations<ObsFromRec>, grid_for(c, n2, kNeqThreads, 2), kNeqThreads, src, n2, c->partials.p, c->ticket, fin);
 	c->last_nn_valid = true;
-	if (prof) {
-		cudaEventRecord(c->pev[4], c->stream);
-		cudaEventSynchronize(c->pev[4]);
-		for (int k = 0; k < M3DREG_STAGE_COUNT; k++) {
-			float ms = 0.0f;
-			cudaEventElapsedTime(&ms, c->pev[k], c->pev[k + 1]);
-			c->stage_ms[k] += ms;
-		}
-		c->stage_iters++;
-	}
+	if (prof) stage_events_collect(c);
 	c->last_n_first = n1; c->last_n_second = n2; c->last_valid = true;
 }
 
@@ -549,6 +656,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	c->sm_count = prop.multiProcessorCount;
 	{ const char *e = getenv("M3DREG_NO_PDL"); c->use_pdl = (e && e[0] == '1') ? 0 : 1; }
 	{ const char *e = getenv("M3DREG_NN_PER_THREAD"); c->nn_per_thread = (e && e[0] == '1') ? 1 : 0; }
+	{ const char *e = getenv("M3DREG_GRID_LEGACY"); c->grid_legacy = (e && e[0] == '1') ? 1 : 0; }
 	{ const char *e = getenv("M3DREG_NN_RHO_DIV"); if (e && atoi(e) > 0) c->nn_tune.rho_div = atoi(e); }
 	{ const char *e = getenv("M3DREG_NN_HULL_MIN"); if (e && atoi(e) > 0) c->nn_tune.hull_min = atoi(e); }
 	{ const char *e = getenv("M3DREG_NN_HULL_RATIO"); if (e && atoi(e) > 0) c->nn_tune.hull_ratio = atoi(e); }
@@ -558,7 +666,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	cudaEventCreate(&c->ev0);
 	cudaEventCreate(&c->ev1);
 	size_t small = sizeof(PoseState) + 8 * sizeof(uint32_t) + sizeof(m3dreg_grid_params) + FLAG_COUNT * sizeof(int) +
-			4 * sizeof(unsigned long long) + 64 + 64 * sizeof(double) + 32 * sizeof(float) + 256;
+			4 * sizeof(unsigned long long) + 64 + 64 * sizeof(double) + 32 * sizeof(float) + 512;
 	char *blk = nullptr;
 	e = cudaMalloc((void **)&blk, small);
 	if (e != cudaSuccess) { m3dreg_destroy(c); return (int)e; }
@@ -573,6 +681,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	c->flags = (int *)take(FLAG_COUNT * sizeof(int));
 	c->ticket = (unsigned int *)take(16);
 	c->cell_count = (unsigned int *)take(16);
+	c->grid_bar = (unsigned int *)take(16);
 	c->eval_counter = (unsigned long long *)take(16);
 	c->mats = (float *)take(32 * sizeof(float));
 	e = cudaMallocHost((void **)&c->h, sizeof(HostSmall));
@@ -591,11 +700,12 @@ void m3dreg_destroy(m3dreg_ctx *c)
 	if (c->own_stream) cudaStreamSynchronize(c->own_stream);
 	for (auto &s : c->scans) s.release();
 	c->g_xyzl.release(); c->g_nrm.release(); c->ci_xyzl.release(); c->ci_nrm.release(); c->co_xyzl.release(); c->co_nrm.release(); c->digit_tot.release();
-	c->ci_tab.release(); c->co_tab.release();
+	c->ci_tab.release(); c->co_tab.release(); c->ci_loc.release(); c->co_loc.release();
+	c->bcount.release(); c->bbegin.release(); c->brec.release();
 	c->q_xyzl.release(); c->q_nrm.release(); c->l_xyzl.release(); c->l_nrm.release();
 	for (int k = 0; k < 2; k++) { c->keys[k].release(); c->vals[k].release(); }
-	c->hist.release(); c->buckets.release(); c->nn.release(); c->nn_seq.release(); c->aos_a.release(); c->aos_b.release();
-	c->obs.release(); c->partials.release(); c->ndt_acc.release(); c->ndt_qacc.release(); c->table.release(); c->d_poses1.release(); c->d_pose6.release();
+	c->hist.release(); c->buckets.release(); c->nn.release(); c->obs_rec.release(); c->cell_list.release(); c->aos_a.release(); c->aos_b.release();
+	c->obs.release(); c->partials.release(); c->ndt_acc.release(); c->ndt_qacc.release(); c->table.release(); c->d_poses1.release(); c->d_pose6.release(); c->d_sweep_status.release();
 	c->d_segs.release(); c->d_seg_of_chunk.release(); c->d_seg_counts.release();
 	if (c->h_sweep) cudaFreeHost(c->h_sweep);
 	if (c->ps) cudaFree(c->ps);   /* base of the small block */
@@ -718,9 +828,9 @@ int m3dreg_nn_search(m3dreg_ctx *c, const m3dreg_point *d_first, int n1, const m
 	if ((e = ensure_candidates(c, (size_t)n1, max_inner, max_outer))) return e;
 	LAUNCH(c, k_split_table, grid_for(c, n1, 256), 256, d_table, n1, c->keys[0].p, c->vals[0].p);
 	CK(cudaMemsetAsync(c->cell_count, 0, sizeof(unsigned int), c->stream));
-	LAUNCH(c, k_list_cells, grid_for(c, n1, 256), 256, c->keys[0].p, n1, d_buckets, c->keys[1].p, c->cell_count);
-	build_candidates(c, c->vals[0].p, d_buckets, c->keys[1].p, c->g_xyzl.p, c->g_nrm.p, (const float *)nullptr, max_inner, max_outer);
-	launch_nn(c, nullptr, n2, c->vals[0].p, n1, d_buckets, search_radius, max_inner, max_outer, c->prune, d_nn, nullptr, nullptr);
+	LAUNCH(c, k_list_cells, grid_for(c, n1, 256), 256, c->keys[0].p, n1, d_buckets, c->cell_list.p, c->cell_count);
+	build_candidates(c, c->vals[0].p, d_buckets, c->cell_list.p, c->g_xyzl.p, c->g_nrm.p, (const float4 *)nullptr, (const float *)nullptr, max_inner, max_outer);
+	launch_nn(c, nullptr, n2, c->vals[0].p, n1, d_buckets, search_radius, max_inner, max_outer, c->prune, d_nn, (float4 *)nullptr, c->g_xyzl.p, nullptr);
 	c->last_valid = false;
 	CK(cudaStreamSynchronize(c->stream));
 	return (int)cudaGetLastError();
@@ -823,10 +933,14 @@ int m3dreg_semantic_nn_host(m3dreg_ctx *c, const m3dreg_point *first, int n1, co
 	prm.max_inner = max_inner; prm.max_outer = max_outer;
 	if ((e = ensure_candidates(c, (size_t)n1, max_inner, max_outer))) return e;
 	int sort_bits = 0;
-	if ((e = plan_buckets(c, &prm, &sort_bits))) return e;
-	build_grid_fused(c, n1, &prm, sort_bits, c->g_nrm.p, (const float *)nullptr);
+	if ((e = plan_buckets(c, &prm, &sort_bits))) return e;      /* sizes the bucket table from the box (one read-back) */
+	if (c->grid_legacy) build_grid_legacy(c, n1, &prm, sort_bits, c->g_nrm.p, (const float4 *)nullptr, (const float *)nullptr);
+	else {
+		LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);              /* k_grid_build reduces the box itself */
+		build_grid_mega(c, c->g_xyzl.p, c->g_nrm.p, n1, (const float *)nullptr, &prm, false);
+	}
 	launch_nn(c, nullptr, n2, c->vals[c->last_sorted].p, n1, c->buckets.p, search_radius, max_inner, max_outer, c->prune,
-			c->nn.p, nullptr, nullptr);
+			c->nn.p, (float4 *)nullptr, c->g_xyzl.p, nullptr);
 	CK(cudaMemcpyAsync(nn_out, c->nn.p, (size_t)n2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 	c->last_n_first = n1; c->last_n_second = n2; c->last_valid = true;
 	int f = check_flags(c);
@@ -869,10 +983,13 @@ static int presort_scan(m3dreg_ctx *c, Scan &s, const m3dreg_point *d_aos)
 	CK(cudaMemcpyAsync(c->h->bounds, c->bounds, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	float mn[3], mx[3], ext = 0.0f;
+	double d2 = 0.0;
 	for (int k = 0; k < 3; k++) {
 		mn[k] = o2f_host(c->h->bounds[k]); mx[k] = o2f_host(c->h->bounds[3 + k]);
 		if (mx[k] - mn[k] > ext) ext = mx[k] - mn[k];
+		d2 += ((double)mx[k] - (double)mn[k]) * ((double)mx[k] - (double)mn[k]);
 	}
+	s.diag = (float)sqrt(d2);
 	float res = ext / 511.0f;
 	if (!(res > 0.0625f)) res = 0.0625f;
 	LAUNCH(c, k_keys_presort, grid_for(c, n, 256), 256, d_aos, n, mn[0], mn[1], mn[2], 1.0f / res, c->keys[0].p, c->vals[0].p);
@@ -930,8 +1047,25 @@ int m3dreg_scan_clear(m3dreg_ctx *c)
 
 /* ---- fused loops ------------------------------------------------------------------------------------------- */
 
+/* diagonal of the bounding box of an AoS cloud on the device (one read-back; host-buffer entry points only) */
+static int local_diag_aos(m3dreg_ctx *c, const m3dreg_point *d_aos, int n, float *diag)
+{
+	LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
+	LAUNCH(c, k_bounds_aos, grid_for(c, n, 256), 256, d_aos, n, c->bounds);
+	CK(cudaMemcpyAsync(c->h->bounds, c->bounds, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	double d2 = 0.0;
+	for (int k = 0; k < 3; k++) {
+		double d = (double)o2f_host(c->h->bounds[3 + k]) - (double)o2f_host(c->h->bounds[k]);
+		d2 += d * d;
+	}
+	*diag = (float)sqrt(d2);
+	return 0;
+}
+
+/* diag = diagonal of the first cloud's LOCAL bounding box (Scan::diag) */
 static int icp_begin_internal(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, int n2, const float *pose_first,
-		const m3dreg_reg_params *prm)
+		const m3dreg_reg_params *prm, float diag)
 {
 	int e;
 	if ((e = ensure_candidates(c, (size_t)n1, prm->max_inner, prm->max_outer))) return e;
@@ -942,11 +1076,17 @@ static int icp_begin_internal(m3dreg_ctx *c, const float4 *lx, const float4 *ln,
 	CK(cudaMemsetAsync(c->flags, 0, FLAG_COUNT * sizeof(int), c->stream));
 	CK(cudaMemsetAsync(c->ticket, 0, sizeof(unsigned int), c->stream));
 	LAUNCH(c, k_pose_prepare, 1, 32, c->ps);
-	/* size the dense bucket table from the initial box (one sync, outside the iteration loop) */
-	LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
-	LAUNCH(c, k_transform_soa<true>, grid_for(c, n1, 256), 256, lx, ln, n1, c->ps->pose1, c->g_xyzl.p, (float4 *)nullptr, c->bounds);
 	int sort_bits = 0;
-	if ((e = plan_buckets(c, prm, &sort_bits))) return e;
+	if (c->grid_legacy) {
+		/* round-1 path: size the dense bucket table from the initial box (one sync, outside the iteration loop) */
+		LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
+		LAUNCH(c, k_transform_soa<true>, grid_for(c, n1, 256), 256, lx, ln, n1, c->ps->pose1, c->g_xyzl.p, (float4 *)nullptr, c->bounds);
+		if ((e = plan_buckets(c, prm, &sort_bits))) return e;
+	} else {
+		/* a table that holds the grid of this scan under ANY pose: no read-back, no synchronisation, and a pose that
+		 * drifts cannot outgrow it */
+		if ((e = ensure_buckets(c, (size_t)bucket_capacity_for(diag, prm), prm->mode == M3DREG_MODE_NDT))) return e;
+	}
 	LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
 	c->act_lx = lx; c->act_ln = ln; c->act_n1 = n1; c->act_n2 = n2; c->act_sort_bits = sort_bits; c->act_prm = *prm;
 	c->active = true;
@@ -965,9 +1105,9 @@ static int icp_end_internal(m3dreg_ctx *c, float *pose_first_out, m3dreg_icp_sta
 }
 
 static int icp_loop(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, int n2, float *pose_first,
-		const m3dreg_reg_params *prm, int iterations, m3dreg_icp_stats *stats)
+		const m3dreg_reg_params *prm, int iterations, m3dreg_icp_stats *stats, float diag)
 {
-	int e = icp_begin_internal(c, lx, ln, n1, n2, pose_first, prm);
+	int e = icp_begin_internal(c, lx, ln, n1, n2, pose_first, prm, diag);
 	if (e) return e;
 	CK(cudaEventRecord(c->ev0, c->stream));
 	for (int it = 0; it < iterations; it++) icp_iteration_device(c, lx, ln, n1, n2, prm, c->act_sort_bits);
@@ -1002,7 +1142,7 @@ int m3dreg_icp_begin(m3dreg_ctx *c, int first_slot, int second_slot, const float
 	if ((e = ensure_first(c, (size_t)A.n))) return e;
 	if ((e = ensure_second(c, (size_t)B.n))) return e;
 	if ((e = stage_queries(c, second_slot, pose_second))) return e;
-	return icp_begin_internal(c, A.xyzl, A.nrm, A.n, B.n, pose_first, prm);
+	return icp_begin_internal(c, A.xyzl, A.nrm, A.n, B.n, pose_first, prm, A.diag);
 }
 
 int m3dreg_icp_step(m3dreg_ctx *c, int iterations)
@@ -1073,7 +1213,7 @@ int m3dreg_icp_pair(m3dreg_ctx *c, int first_slot, int second_slot, float *pose_
 	if ((e = ensure_first(c, (size_t)A.n))) return e;
 	if ((e = ensure_second(c, (size_t)B.n))) return e;
 	if ((e = stage_queries(c, second_slot, pose_second))) return e;
-	e = icp_loop(c, A.xyzl, A.nrm, A.n, B.n, pose_first, prm, iterations, stats);
+	e = icp_loop(c, A.xyzl, A.nrm, A.n, B.n, pose_first, prm, iterations, stats, A.diag);
 	c->active = false;
 	return e;
 }
@@ -1095,7 +1235,9 @@ int m3dreg_icp_iteration_host(m3dreg_ctx *c, const m3dreg_point *first_local, in
 	LAUNCH(c, k_unpack_points, (n1 + 255) / 256, 256, c->aos_a.p, n1, c->l_xyzl.p, c->l_nrm.p);
 	LAUNCH(c, k_unpack_points, (n2 + 255) / 256, 256, c->aos_b.p, n2, c->q_xyzl.p, c->q_nrm.p);
 	c->act_perm = nullptr;
-	e = icp_loop(c, c->l_xyzl.p, c->l_nrm.p, n1, n2, pose_first, prm, 1, stats);
+	float diag = 0.0f;
+	if (!c->grid_legacy && (e = local_diag_aos(c, c->aos_a.p, n1, &diag))) return e;
+	e = icp_loop(c, c->l_xyzl.p, c->l_nrm.p, n1, n2, pose_first, prm, 1, stats, diag);
 	c->active = false;
 	if (e) return e;
 	if (nn_out) {
@@ -1155,6 +1297,18 @@ int m3dreg_sweep_zero(m3dreg_ctx *c, double *d_neq, int n_scans)
 	return (int)cudaGetLastError();
 }
 
+/* pinned staging of a sweep: grows only (growth synchronises; steady-state sweeps never do) */
+static int ensure_sweep_staging(m3dreg_ctx *c, size_t bytes)
+{
+	if (c->h_sweep_bytes >= bytes) return 0;
+	CK(cudaStreamSynchronize(c->stream));
+	if (c->h_sweep) cudaFreeHost(c->h_sweep);
+	c->h_sweep = nullptr; c->h_sweep_bytes = 0;
+	CK(cudaMallocHost(&c->h_sweep, bytes + bytes / 2));
+	c->h_sweep_bytes = bytes + bytes / 2;
+	return 0;
+}
+
 int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const int *pair_j, const float *poses, int n_scans,
 		const m3dreg_reg_params *prm, double *d_neq)
 {
@@ -1168,113 +1322,128 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 				c->scans[(size_t)i].n <= 0 || c->scans[(size_t)j].n <= 0 || i == j)
 			return M3DREG_E_BAD_SLOT;
 	}
-	/* Euler round trip of every (old) pose: gpu6DSLAM.cpp:440-441, 461-462 */
-	std::vector<float> p1((size_t)n_scans * 16);
-	std::vector<double> p6((size_t)n_scans * 6);
-	for (int s = 0; s < n_scans; s++) host_roundtrip_pose(poses + 16 * (size_t)s, p1.data() + 16 * (size_t)s, p6.data() + 6 * (size_t)s);
-	if ((e = c->d_poses1.ensure(p1.size()))) return e;
-	if ((e = c->d_pose6.ensure(p6.size()))) return e;
-	CK(cudaMemcpyAsync(c->d_poses1.p, p1.data(), p1.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-	CK(cudaMemcpyAsync(c->d_pose6.p, p6.data(), p6.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-	CK(cudaStreamSynchronize(c->stream));   /* p1/p6 are pageable */
-	CK(cudaMemsetAsync(c->label_counts, 0, 4 * sizeof(unsigned long long), c->stream));
-	CK(cudaMemsetAsync(c->flags, 0, FLAG_COUNT * sizeof(int), c->stream));
-	CK(cudaMemsetAsync(c->ticket, 0, sizeof(unsigned int), c->stream));
-
-	/* process pairs grouped by i so the grid of scan i is built once (the reference rebuilds it per j, gpu6DSLAM.cpp:478);
-	 * ICP: the neighbours j of one i are searched in batches — one transform, ONE search and ONE moment reduction over the
-	 * concatenated queries of up to kMaxSegs neighbours (k_transform_segments) instead of three small launches per pair */
+	const bool ndt = prm->mode == M3DREG_MODE_NDT;
+	/* ---- plan (host only): pairs grouped by i so the grid of scan i is built once (the reference rebuilds it per j,
+	 * gpu6DSLAM.cpp:478); ICP: the neighbours j of one i are searched in batches — one transform, ONE search and ONE moment
+	 * reduction over the concatenated queries of up to kMaxSegs neighbours instead of three small launches per pair.
+	 * Everything the device needs (round-tripped poses, every batch's segment table) is staged in ONE pinned block and
+	 * uploaded up front, every buffer is sized up front: the loop below only launches kernels — no read-back, no
+	 * synchronisation, no allocation (round 1 synchronised per scan and per batch). */
 	std::vector<int> order((size_t)n_pairs);
 	for (int p = 0; p < n_pairs; p++) order[(size_t)p] = p;
 	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pair_i[a] < pair_i[b]; });
 	const size_t kBatchQueries = (size_t)8 << 20;       /* queries per batch (incl. padding): 8 Mi x 36 B of query state */
-	if (prm->mode != M3DREG_MODE_NDT) {
-		if ((e = c->d_segs.ensure(kMaxSegs))) return e;
-		if ((e = c->d_seg_counts.ensure(4 * kMaxSegs))) return e;
-		CK(cudaMemsetAsync(c->d_seg_counts.p, 0, 4 * kMaxSegs * sizeof(unsigned long long), c->stream));
-	}
-	int cur_i = -1, sort_bits = 0;
+	struct Batch { int i, seg0, nseg, j_single; size_t total; };
+	std::vector<Batch> batches;
+	std::vector<SweepSeg> all_segs;
+	size_t max_first = 0, max_second = 0;
+	long long max_cap = 1;
 	for (int q = 0; q < n_pairs;) {
 		const int i = pair_i[order[(size_t)q]];
 		const Scan &A = c->scans[(size_t)i];
+		if ((size_t)A.n > max_first) max_first = (size_t)A.n;
+		const long long cap = bucket_capacity_for(A.diag, prm);
+		if (cap > max_cap) max_cap = cap;
+		Batch bt;
+		bt.i = i; bt.seg0 = (int)all_segs.size(); bt.nseg = 0; bt.total = 0; bt.j_single = pair_j[order[(size_t)q]];
+		if (ndt) {      /* NDT: one pair per step (the per-bucket query sums are per pair) */
+			bt.total = (size_t)c->scans[(size_t)bt.j_single].n;
+			q++;
+		} else {
+			while (q < n_pairs && pair_i[order[(size_t)q]] == i && bt.nseg < kMaxSegs) {
+				const int j = pair_j[order[(size_t)q]];
+				const Scan &B = c->scans[(size_t)j];
+				const size_t padded = ((size_t)B.n + kSegChunk - 1) / kSegChunk * kSegChunk;
+				if (bt.nseg > 0 && bt.total + padded > kBatchQueries) break;
+				SweepSeg sg;
+				sg.sx = B.sx; sg.sn = B.sn; sg.n = B.n; sg.off = (int)bt.total; sg.pose = j; sg.pad = 0;
+				all_segs.push_back(sg);
+				bt.total += padded;
+				bt.nseg++;
+				q++;
+			}
+			if (bt.total > 0x7fffffffu) return M3DREG_E_INVALID_ARG;
+		}
+		if (bt.total > max_second) max_second = bt.total;
+		batches.push_back(bt);
+	}
+	if ((e = c->d_poses1.ensure((size_t)n_scans * 16))) return e;
+	if ((e = c->d_pose6.ensure((size_t)n_scans * 6))) return e;
+	if (max_first) {
+		if ((e = ensure_first(c, max_first))) return e;
+		if ((e = ensure_candidates(c, max_first, prm->max_inner, prm->max_outer))) return e;
+		if ((e = ensure_second(c, max_second))) return e;
+		if (c->grid_legacy) { if ((e = c->buckets.ensure((size_t)1))) return e; }
+		else if ((e = ensure_buckets(c, (size_t)max_cap, ndt))) return e;
+	}
+	if (!ndt) {
+		if ((e = c->d_segs.ensure(all_segs.size() + 1))) return e;
+		if ((e = c->d_seg_counts.ensure(4 * kMaxSegs))) return e;
+		if ((e = c->d_seg_of_chunk.ensure(max_second / kSegChunk + 1))) return e;
+	}
+	const size_t bytes_p1 = (size_t)n_scans * 16 * sizeof(float), bytes_p6 = (size_t)n_scans * 6 * sizeof(double),
+			bytes_segs = all_segs.size() * sizeof(SweepSeg);
+	if ((e = ensure_sweep_staging(c, bytes_p6 + bytes_p1 + bytes_segs + 64))) return e;
+	/* the previous sweep's uploads have completed: every sweep ends with check_flags (one synchronisation per sweep) */
+	double *h_p6 = static_cast<double *>(c->h_sweep);
+	float *h_p1 = reinterpret_cast<float *>(static_cast<char *>(c->h_sweep) + bytes_p6);
+	SweepSeg *h_segs = reinterpret_cast<SweepSeg *>(static_cast<char *>(c->h_sweep) + bytes_p6 + bytes_p1);
+	/* Euler round trip of every (old) pose: gpu6DSLAM.cpp:440-441, 461-462 */
+	for (int s = 0; s < n_scans; s++) host_roundtrip_pose(poses + 16 * (size_t)s, h_p1 + 16 * (size_t)s, h_p6 + 6 * (size_t)s);
+	if (bytes_segs) memcpy(h_segs, all_segs.data(), bytes_segs);
+	CK(cudaMemcpyAsync(c->d_poses1.p, h_p1, bytes_p1, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->d_pose6.p, h_p6, bytes_p6, cudaMemcpyHostToDevice, c->stream));
+	if (bytes_segs) CK(cudaMemcpyAsync(c->d_segs.p, h_segs, bytes_segs, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemsetAsync(c->label_counts, 0, 4 * sizeof(unsigned long long), c->stream));
+	CK(cudaMemsetAsync(c->flags, 0, FLAG_COUNT * sizeof(int), c->stream));
+	CK(cudaMemsetAsync(c->ticket, 0, sizeof(unsigned int), c->stream));
+	if (!ndt) CK(cudaMemsetAsync(c->d_seg_counts.p, 0, 4 * kMaxSegs * sizeof(unsigned long long), c->stream));
+
+	int cur_i = -1, sort_bits = 0;
+	for (const Batch &bt : batches) {
+		const int i = bt.i;
+		const Scan &A = c->scans[(size_t)i];
+		const float *pose_i = c->d_poses1.p + 16 * (size_t)i;
 		if (i != cur_i) {
-			if ((e = ensure_first(c, (size_t)A.n))) return e;
-			if ((e = ensure_candidates(c, (size_t)A.n, prm->max_inner, prm->max_outer))) return e;
 			LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
-			LAUNCH(c, k_transform_soa<true>, grid_for(c, A.n, 256), 256, A.xyzl, A.nrm, A.n, c->d_poses1.p + 16 * (size_t)i,
-					c->g_xyzl.p, (float4 *)nullptr, c->bounds);
-			if ((e = plan_buckets(c, prm, &sort_bits))) return e;
-			build_grid_fused(c, A.n, prm, sort_bits, A.nrm, c->d_poses1.p + 16 * (size_t)i);
-			if (prm->mode == M3DREG_MODE_NDT) ndt_bucket_stats(c, A.xyzl, A.n);
+			if (c->grid_legacy) {
+				LAUNCH(c, k_transform_soa<true>, grid_for(c, A.n, 256), 256, A.xyzl, A.nrm, A.n, pose_i, c->g_xyzl.p, (float4 *)nullptr, c->bounds);
+				if ((e = plan_buckets(c, prm, &sort_bits))) return e;
+				build_grid_legacy(c, A.n, prm, sort_bits, A.nrm, A.xyzl, pose_i);
+			} else {
+				build_grid_mega(c, A.xyzl, A.nrm, A.n, pose_i, prm, ndt);
+			}
+			if (ndt) ndt_bucket_stats(c, A.xyzl, A.n);
 			cur_i = i;
 		}
-		if (prm->mode == M3DREG_MODE_NDT) {
-			const Scan &B = c->scans[(size_t)pair_j[order[(size_t)q]]];
-			if ((e = ensure_second(c, (size_t)B.n))) return e;
-			LAUNCH(c, k_transform_soa<false>, grid_for(c, B.n, 256), 256, B.sx, B.sn, B.n, c->d_poses1.p + 16 * (size_t)pair_j[order[(size_t)q]],
-					c->q_xyzl.p, c->q_nrm.p, (uint32_t *)nullptr);
-			FinalizeArgs fin = {};
-			fin.ps = nullptr; fin.neq_out = d_neq + (size_t)i * kNeqCount; fin.accumulate = 1; fin.solve = 0; fin.dof = prm->dof;
-			fin.obs_threshold = prm->obs_threshold; fin.pose6_in = c->d_pose6.p + 6 * (size_t)i; fin.bounds_reset = nullptr;
-			fin.label_counts_reset = nullptr;
-			ndt_queries_and_reduce(c, B.n, fin, true);
-			c->last_n_first = A.n; c->last_n_second = B.n; c->last_valid = true; c->last_nn_valid = false;
-			q++;
-			continue;
-		}
-		/* one batch: consecutive pairs of this i while they fit */
-		SweepSeg segs[kMaxSegs];
-		int nseg = 0;
-		size_t total = 0;
-		while (q < n_pairs && pair_i[order[(size_t)q]] == i && nseg < kMaxSegs) {
-			const int j = pair_j[order[(size_t)q]];
-			const Scan &B = c->scans[(size_t)j];
-			const size_t padded = ((size_t)B.n + kSegChunk - 1) / kSegChunk * kSegChunk;
-			if (nseg > 0 && total + padded > kBatchQueries) break;
-			segs[nseg].sx = B.sx; segs[nseg].sn = B.sn; segs[nseg].n = B.n; segs[nseg].off = (int)total; segs[nseg].pose = j; segs[nseg].pad = 0;
-			total += padded;
-			nseg++;
-			q++;
-		}
-		if (total > 0x7fffffffu) return M3DREG_E_INVALID_ARG;
-		const int n_chunks = (int)(total / kSegChunk);
-		if ((e = ensure_second(c, total))) return e;
-		if ((e = c->d_seg_of_chunk.ensure((size_t)n_chunks))) return e;
-		const size_t need = sizeof(segs) + (size_t)n_chunks * sizeof(int);
-		if (c->h_sweep_bytes < need) {
-			CK(cudaStreamSynchronize(c->stream));
-			if (c->h_sweep) cudaFreeHost(c->h_sweep);
-			c->h_sweep = nullptr; c->h_sweep_bytes = 0;
-			CK(cudaMallocHost(&c->h_sweep, need * 2));
-			c->h_sweep_bytes = need * 2;
-		}
-		/* the previous batch's upload has completed: plan_buckets / the end of this loop body synchronise the stream */
-		memcpy(c->h_sweep, segs, sizeof(segs));
-		int *h_map = reinterpret_cast<int *>(static_cast<char *>(c->h_sweep) + sizeof(segs));
-		for (int sgi = 0; sgi < nseg; sgi++) {
-			const int c0 = segs[sgi].off / kSegChunk, c1 = sgi + 1 < nseg ? segs[sgi + 1].off / kSegChunk : n_chunks;
-			for (int k = c0; k < c1; k++) h_map[k] = sgi;
-		}
-		CK(cudaMemcpyAsync(c->d_segs.p, c->h_sweep, sizeof(segs), cudaMemcpyHostToDevice, c->stream));
-		CK(cudaMemcpyAsync(c->d_seg_of_chunk.p, h_map, (size_t)n_chunks * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-		LAUNCH(c, k_transform_segments, n_chunks, kSegChunk, c->d_segs.p, c->d_seg_of_chunk.p, c->d_poses1.p, c->q_xyzl.p, c->q_nrm.p);
-		launch_nn(c, nullptr, (int)total, c->vals[c->last_sorted].p, A.n, c->buckets.p, prm->search_radius, prm->max_inner, prm->max_outer, 1,
-				nullptr, c->nn_seq.p, c->d_seg_counts.p, c->d_seg_of_chunk.p);
-		ObsFromNN src = {};
-		src.nn = c->nn_seq.p; src.q_xyzl = c->q_xyzl.p; src.l_xyzl = A.xyzl; src.m = c->d_poses1.p + 16 * (size_t)i;
-		src.label_counts = c->d_seg_counts.p; src.seg_of_chunk = c->d_seg_of_chunk.p; src.n_segs = nseg;
-		for (int k = 0; k < 4; k++) src.weight[k] = prm->weight[k];
 		FinalizeArgs fin = {};
 		fin.ps = nullptr; fin.neq_out = d_neq + (size_t)i * kNeqCount; fin.accumulate = 1; fin.solve = 0; fin.dof = prm->dof;
 		fin.obs_threshold = prm->obs_threshold; fin.pose6_in = c->d_pose6.p + 6 * (size_t)i; fin.bounds_reset = nullptr;
-		fin.label_counts_reset = c->d_seg_counts.p; fin.label_count_sets = nseg;
-		LAUNCH(c, k_normal_equations<ObsFromNN>, grid_for(c, (long long)total, kNeqThreads, 2), kNeqThreads, src, (int)total, c->partials.p, c->ticket, fin);
-		CK(cudaStreamSynchronize(c->stream));      /* the pinned staging block is reused by the next batch */
-		c->last_n_first = A.n; c->last_n_second = segs[nseg - 1].n; c->last_valid = true; c->last_nn_valid = false; c->nn_pending = false;
+		if (ndt) {
+			const Scan &B = c->scans[(size_t)bt.j_single];
+			LAUNCH(c, k_transform_soa<false>, grid_for(c, B.n, 256), 256, B.sx, B.sn, B.n, c->d_poses1.p + 16 * (size_t)bt.j_single,
+					c->q_xyzl.p, c->q_nrm.p, (uint32_t *)nullptr);
+			fin.label_counts_reset = nullptr;
+			ndt_queries_and_reduce(c, B.n, fin, true);
+			c->last_n_first = A.n; c->last_n_second = B.n; c->last_valid = true; c->last_nn_valid = false;
+			continue;
+		}
+		const int n_chunks = (int)(bt.total / kSegChunk);
+		const SweepSeg *segs = c->d_segs.p + bt.seg0;
+		LAUNCH(c, k_transform_segments, n_chunks, kSegChunk, segs, bt.nseg, c->d_seg_of_chunk.p, c->d_poses1.p, c->q_xyzl.p, c->q_nrm.p);
+		launch_nn(c, nullptr, (int)bt.total, c->vals[c->last_sorted].p, A.n, c->buckets.p, prm->search_radius, prm->max_inner, prm->max_outer, 1,
+				nullptr, c->obs_rec.p, A.xyzl, c->d_seg_counts.p, c->d_seg_of_chunk.p);
+		ObsFromRec src = {};
+		src.rec = c->obs_rec.p; src.q_xyzl = c->q_xyzl.p; src.m = pose_i;
+		src.label_counts = c->d_seg_counts.p; src.seg_of_chunk = c->d_seg_of_chunk.p; src.n_segs = bt.nseg;
+		for (int k = 0; k < 4; k++) src.weight[k] = prm->weight[k];
+		fin.label_counts_reset = c->d_seg_counts.p; fin.label_count_sets = bt.nseg;
+		LAUNCH(c, k_normal_equations<ObsFromRec>, grid_for(c, (long long)bt.total, kNeqThreads, 2), kNeqThreads, src, (int)bt.total, c->partials.p, c->ticket, fin);
+		c->last_n_first = A.n; c->last_n_second = all_segs[(size_t)(bt.seg0 + bt.nseg - 1)].n; c->last_valid = true; c->last_nn_valid = false; c->nn_pending = false;
 	}
 	int f = check_flags(c);
 	if (f) return f;
-	return (int)cudaGetLastError();
+	return launch_status(c);
 }
 
 int m3dreg_sweep_solve(m3dreg_ctx *c, const double *d_neq, int n_scans, int scan_begin, int scan_end, float *poses,
@@ -1286,7 +1455,7 @@ int m3dreg_sweep_solve(m3dreg_ctx *c, const double *d_neq, int n_scans, int scan
 	CK(cudaSetDevice(c->dev));
 	int e;
 	if ((e = c->d_poses1.ensure((size_t)n_scans * 16))) return e;
-	DevBuf<int> st;
+	DevBuf<int> &st = c->d_sweep_status;      /* persistent arena member: nothing is allocated per sweep */
 	if ((e = st.ensure((size_t)n_scans))) return e;
 	CK(cudaMemcpyAsync(c->d_poses1.p, poses, (size_t)n_scans * 16 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
 	int cnt = scan_end - scan_begin;
@@ -1296,8 +1465,7 @@ int m3dreg_sweep_solve(m3dreg_ctx *c, const double *d_neq, int n_scans, int scan
 	if (status_out)
 		CK(cudaMemcpyAsync(status_out + scan_begin, st.p + scan_begin, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
-	st.release();
-	return (int)cudaGetLastError();
+	return launch_status(c);
 }
 
 } /* extern "C" */

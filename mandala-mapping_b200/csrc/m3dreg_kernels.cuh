@@ -209,13 +209,25 @@ struct SweepSeg {
 	int n, off, pose, pad;      /* points, first query, index of its pose in the pose array */
 };
 
-__global__ void __launch_bounds__(kSegChunk) k_transform_segments(const SweepSeg *__restrict__ segs, const int *__restrict__ seg_of_chunk,
+/* One block per chunk.  The chunk -> segment map the search and the moment reduction use afterwards is produced here
+ * (binary search over the segments' first queries) instead of on the host. */
+__global__ void __launch_bounds__(kSegChunk) k_transform_segments(const SweepSeg *__restrict__ segs, int n_segs, int *__restrict__ seg_of_chunk,
 		const float *__restrict__ poses, float4 *__restrict__ out_xyzl, float4 *__restrict__ out_nrm)
 {
 	pdl_enter();
-	const SweepSeg sg = segs[__ldg(seg_of_chunk + blockIdx.x)];
+	__shared__ int s_off[kMaxSegs];
+	if ((int)threadIdx.x < n_segs) s_off[threadIdx.x] = segs[threadIdx.x].off;
+	__syncthreads();
+	int lo = 0, hi = n_segs - 1;      /* last segment whose first query is <= this chunk's first query */
+	const int q0 = blockIdx.x * kSegChunk;
+	while (lo < hi) {
+		const int mid = (lo + hi + 1) >> 1;
+		if (s_off[mid] <= q0) lo = mid; else hi = mid - 1;
+	}
+	if (threadIdx.x == 0) seg_of_chunk[blockIdx.x] = lo;
+	const SweepSeg sg = segs[lo];
 	const float *m = poses + 16 * (size_t)sg.pose;
-	const int q = blockIdx.x * kSegChunk + threadIdx.x, i = q - sg.off;
+	const int q = q0 + threadIdx.x, i = q - sg.off;
 	if (i >= sg.n) {
 		out_xyzl[q] = make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(-1));
 		out_nrm[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -648,15 +660,40 @@ __global__ void k_list_cells(const uint32_t *__restrict__ keys, int n, const m3d
  * inside a bin is arbitrary (counting sort with shared-memory atomics); each record carries its sorted position l for
  * the tie-break and the result, which is all the search needs.  Two sets exist when the INNER and OUTER caps differ (different strides). */
 constexpr int kBuildWarps = 4;
-constexpr int kBuildPerLane = 7;          /* candidates per lane held in registers (224 per warp pass >= 2 * 100 - 1, the default caps) */
+constexpr int kBuildChunk = 4;            /* gathers per lane in flight while binning */
 constexpr int kBuildTabMax = 4 * 64 + 1;   /* bins + 1 at the finest level */
 
 struct NormalRotation { float r[9]; int on; };   /* rotation applied to the candidates' normals (same rounding as the transform kernels) */
 
 struct CellGeom { float mnx, mny, mnz, rx, ry, rz; int cx, cy, cz; };
 
-__device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict__ vals, const float4 *__restrict__ src_xyzl,
-		const float4 *__restrict__ src_nrm, const NormalRotation &rot, int begin, int npts, int cap, int tables, const CellGeom &g,
+/* rigid transform applied to the gridded cloud's points on the fly (the grid megakernel never materialises the
+ * transformed cloud): same operation sequence as k_transform_soa, so the bits equal the ones the keys were made from */
+struct PointXform { float r[12]; int on; };
+
+__device__ __forceinline__ float4 xform_point(const PointXform &x, const float4 &p)
+{
+	if (!x.on) return p;
+	return make_float4(__fadd_rn(x.r[3], __fmaf_rn(x.r[2], p.z, __fmaf_rn(x.r[0], p.x, __fmul_rn(x.r[1], p.y)))),
+			__fadd_rn(x.r[7], __fmaf_rn(x.r[6], p.z, __fmaf_rn(x.r[4], p.x, __fmul_rn(x.r[5], p.y)))),
+			__fadd_rn(x.r[11], __fmaf_rn(x.r[10], p.z, __fmaf_rn(x.r[8], p.x, __fmul_rn(x.r[9], p.y)))), p.w);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+	asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
+/* One warp builds one bucket's candidate set.  Two sweeps over the bucket's candidates (walk positions begin + k * iter):
+ * sweep 1 bins every candidate (histogram with shared-memory atomics; the normals the second sweep will want are
+ * prefetched into L2), the warp scans the bin counts into the bucket's offset table, sweep 2 bins them again (table value
+ * and point are L1/L2 hits by then) and places them.  Nothing per candidate is kept in registers between the sweeps:
+ * the kernel is a chain of dependent gathers, resident warps are what hides it, so registers matter more than the
+ * ~60 repeated instructions per candidate.
+ * VALS_CG: the sorted table was written earlier in the SAME launch by other blocks (grid megakernel): read it past L1. */
+template <bool VALS_CG = false>
+__device__ __forceinline__ void build_cell_candidates(const uint32_t *vals, const float4 *__restrict__ src_xyzl,
+		const float4 *__restrict__ src_nrm, const float4 *__restrict__ loc_src, const NormalRotation &rot, const PointXform &xf, int begin, int npts, int cap, int tables, const CellGeom &g,
 		const CandSet &set, uint32_t *hist, int lane)
 {
 	const unsigned full = 0xffffffffu;
@@ -665,36 +702,19 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 	const int ncand = (npts + iter - 1) / iter;
 	const int level = tables ? nn_level(npts) : -1;
 	const int nbins = level >= 0 ? (4 << (3 * level)) : 0;
-	const float wx = nn_subcell_width(g.rx, level < 0 ? 0 : level), wy = nn_subcell_width(g.ry, level < 0 ? 0 : level),
-			wz = nn_subcell_width(g.rz, level < 0 ? 0 : level);
-	if (level >= 0) {
-		for (int k = lane; k <= nbins; k += 32) hist[k] = 0;
-		__syncwarp();
-	}
-	const bool single = ncand <= 32 * kBuildPerLane;
-	/* per candidate only its table value and its bin stay in registers (register pressure = resident warps, and this
-	 * kernel is a chain of dependent gathers); the point is re-read (L1/L2 hit) together with the normal when stored */
-	uint32_t v[kBuildPerLane], bin[kBuildPerLane];
-	auto load = [&](int c0) {
-#pragma unroll
-		for (int j = 0; j < kBuildPerLane; j++) {
-			int k = c0 + j * 32 + lane;
-			v[j] = k < ncand ? __ldg(vals + begin + k * iter) : 0u;
-		}
-		float4 p[kBuildPerLane];
-#pragma unroll
-		for (int j = 0; j < kBuildPerLane; j++) p[j] = __ldg(src_xyzl + v[j]);      /* v = 0 past the end: a valid address */
-#pragma unroll
-		for (int j = 0; j < kBuildPerLane; j++) {
-			int k = c0 + j * 32 + lane;
-			const int lv = level < 0 ? 0 : level;
-			int ux = nn_col(p[j].x, g.mnx, wx, g.cx, lv), uy = nn_col(p[j].y, g.mny, wy, g.cy, lv), uz = nn_col(p[j].z, g.mnz, wz, g.cz, lv);
-			bin[j] = k < ncand ? (uint32_t)nn_bin(__float_as_int(p[j].w), ux, uy, uz, lv) : 0x1000u + lane;
-		}
+	const int lv = level < 0 ? 0 : level;
+	const float wx = nn_subcell_width(g.rx, lv), wy = nn_subcell_width(g.ry, lv), wz = nn_subcell_width(g.rz, lv);
+	auto table_value = [&](int k) { return VALS_CG ? __ldcg(vals + begin + k * iter) : __ldg(vals + begin + k * iter); };
+	auto bin_of = [&](const float4 &p) {
+		const int ux = nn_col(p.x, g.mnx, wx, g.cx, lv), uy = nn_col(p.y, g.mny, wy, g.cy, lv), uz = nn_col(p.z, g.mnz, wz, g.cz, lv);
+		return (uint32_t)nn_bin(__float_as_int(p.w), ux, uy, uz, lv);
 	};
-	auto store = [&](int pos, int k, uint32_t vi) {
-		const float4 c = __ldg(src_xyzl + vi);
+	auto store = [&](int pos, int k, uint32_t vi, const float4 &c0, const float4 &c) {
 		const float4 n = __ldg(src_nrm + vi);
+		{	/* the point in the frame the moment reduction wants (loc_src == 0: the source cloud itself) + its original index */
+			const float4 l0 = loc_src ? __ldg(loc_src + vi) : c0;
+			set.loc[pos] = make_float4(l0.x, l0.y, l0.z, __uint_as_float(vi));
+		}
 		float4 nn = n;
 		if (rot.on) {
 			nn.x = __fmaf_rn(rot.r[2], n.z, __fmaf_rn(rot.r[0], n.x, __fmul_rn(rot.r[1], n.y)));
@@ -704,25 +724,29 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 		set.xyzl[pos] = make_float4(c.x, c.y, c.z, __int_as_float(begin + k * iter));
 		set.nrm[pos] = make_float4(nn.x, nn.y, nn.z, c.w);
 	};
-	if (single) load(0);
 	if (level < 0) {     /* no table: candidates in walk order */
-		for (int c0 = 0; c0 < ncand; c0 += 32 * kBuildPerLane) {
-			if (!single) load(c0);
-#pragma unroll
-			for (int j = 0; j < kBuildPerLane; j++) {
-				int k = c0 + j * 32 + lane;
-				if (k < ncand) store(begin + k, k, v[j]);
-			}
+		for (int k = lane; k < ncand; k += 32) {
+			const uint32_t vi = table_value(k);
+			const float4 c0 = __ldg(src_xyzl + vi);
+			store(begin + k, k, vi, c0, xform_point(xf, c0));
 		}
 		return;
 	}
-	/* pass 1: bin histogram (shared-memory atomics: independent of each other, no warp-wide step per candidate) */
-	for (int c0 = 0; c0 < ncand; c0 += 32 * kBuildPerLane) {
-		if (!single) load(c0);
+	for (int k = lane; k <= nbins; k += 32) hist[k] = 0;
+	__syncwarp();
+	/* sweep 1: bin histogram (shared-memory atomics: independent of each other, no warp-wide step per candidate),
+	 * kBuildChunk gathers per lane in flight */
+	for (int k0 = 0; k0 < ncand; k0 += 32 * kBuildChunk) {
+		uint32_t v[kBuildChunk];
+		float4 p[kBuildChunk];
 #pragma unroll
-		for (int j = 0; j < kBuildPerLane; j++) {
-			int k = c0 + j * 32 + lane;
-			if (k < ncand) atomicAdd(&hist[bin[j]], 1u);
+		for (int j = 0; j < kBuildChunk; j++) { const int k = k0 + j * 32 + lane; v[j] = k < ncand ? table_value(k) : 0u; }      /* 0: a valid address */
+#pragma unroll
+		for (int j = 0; j < kBuildChunk; j++) { p[j] = __ldg(src_xyzl + v[j]); prefetch_l2(src_nrm + v[j]); }
+#pragma unroll
+		for (int j = 0; j < kBuildChunk; j++) {
+			const int k = k0 + j * 32 + lane;
+			if (k < ncand) atomicAdd(&hist[bin_of(xform_point(xf, p[j]))], 1u);
 		}
 	}
 	__syncwarp();
@@ -748,14 +772,22 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 		}
 		__syncwarp();
 	}
-	/* pass 2: placement.  The order of the candidates INSIDE a bin is whatever the atomics hand out: the search takes
+	/* sweep 2: placement.  The order of the candidates INSIDE a bin is whatever the atomics hand out: the search takes
 	 * the lexicographic minimum of (dist, l) with l carried in the record, so it does not depend on it */
-	for (int c0 = 0; c0 < ncand; c0 += 32 * kBuildPerLane) {
-		if (!single) load(c0);
+	for (int k0 = 0; k0 < ncand; k0 += 32 * kBuildChunk) {
+		uint32_t v[kBuildChunk];
+		float4 p[kBuildChunk];
 #pragma unroll
-		for (int j = 0; j < kBuildPerLane; j++) {
-			int k = c0 + j * 32 + lane;
-			if (k < ncand) store(begin + (int)atomicAdd(&hist[bin[j]], 1u), k, v[j]);
+		for (int j = 0; j < kBuildChunk; j++) { const int k = k0 + j * 32 + lane; v[j] = k < ncand ? table_value(k) : 0u; }
+#pragma unroll
+		for (int j = 0; j < kBuildChunk; j++) p[j] = __ldg(src_xyzl + v[j]);
+#pragma unroll
+		for (int j = 0; j < kBuildChunk; j++) {
+			const int k = k0 + j * 32 + lane;
+			if (k < ncand) {
+				const float4 c = xform_point(xf, p[j]);
+				store(begin + (int)atomicAdd(&hist[bin_of(c)], 1u), k, v[j], p[j], c);
+			}
 		}
 	}
 	__syncwarp();
@@ -765,8 +797,8 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *__restrict
 __global__ void __launch_bounds__(kBuildWarps * 32, 7) k_build_candidates(const uint32_t *__restrict__ vals,
 		const m3dreg_grid_params *__restrict__ gp, const m3dreg_bucket *__restrict__ buckets,
 		const uint32_t *__restrict__ cell_list, const unsigned int *__restrict__ cell_count,
-		const float4 *__restrict__ src_xyzl, const float4 *__restrict__ src_nrm, const float *__restrict__ nrm_m, int max_inner, int max_outer,
-		CandSet ci, CandSet co, int two_sets)
+		const float4 *__restrict__ src_xyzl, const float4 *__restrict__ src_nrm, const float4 *__restrict__ loc_src, const float *__restrict__ nrm_m,
+		int max_inner, int max_outer, CandSet ci, CandSet co, int two_sets)
 {
 	pdl_enter();
 	__shared__ uint32_t s_hist[kBuildWarps][kBuildTabMax + 7];
@@ -775,6 +807,8 @@ __global__ void __launch_bounds__(kBuildWarps * 32, 7) k_build_candidates(const 
 #pragma unroll
 	for (int k = 0; k < 9; k++) rot.r[k] = rot.on ? __ldg(nrm_m + (k / 3) * 4 + (k % 3)) : 0.0f;    /* row-major 4x4 */
 	if (gp->number_of_buckets <= 0) return;
+	PointXform xf;
+	xf.on = 0;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
 	CellGeom g;
@@ -788,8 +822,8 @@ __global__ void __launch_bounds__(kBuildWarps * 32, 7) k_build_candidates(const 
 		const int *bp = reinterpret_cast<const int *>(buckets + c);
 		int c_begin = __ldg(bp), c_n = __ldg(bp + 2);
 		g.cx = c / (nby * nbz); g.cy = (c / nbz) % nby; g.cz = c % nbz;
-		build_cell_candidates(vals, src_xyzl, src_nrm, rot, c_begin, c_n, max_inner, tables, g, ci, s_hist[w], lane);
-		if (two_sets) build_cell_candidates(vals, src_xyzl, src_nrm, rot, c_begin, c_n, max_outer, tables, g, co, s_hist[w], lane);
+		build_cell_candidates(vals, src_xyzl, src_nrm, loc_src, rot, xf, c_begin, c_n, max_inner, tables, g, ci, s_hist[w], lane);
+		if (two_sets) build_cell_candidates(vals, src_xyzl, src_nrm, loc_src, rot, xf, c_begin, c_n, max_outer, tables, g, co, s_hist[w], lane);
 	}
 }
 
@@ -809,7 +843,9 @@ __global__ void k_split_table(const m3dreg_hash_element *__restrict__ table, int
  * order (the scan store keeps a (label, Morton)-sorted copy of every scan, and a rigid transform preserves coherence),
  * so the 32 queries of a warp read the same few bins and their loads coalesce in L1.
  * q_perm (may be null = identity) maps the query's position to its index in the caller's order: nn_out is written
- * in the caller's order (the reference's layout), nn_seq (may be null) in query-array order for the next stage. */
+ * in the caller's order (the reference's layout); obs_rec (may be null), in query-array order, is what the moment
+ * reduction streams next: {matched point of the first cloud as stored in src_xyzl (its LOCAL frame in the fused loops:
+ * x0,y0,z0 of obs_nn_t, gpu6DSLAM.cpp:367-369), bits of its original index or -1}. */
 constexpr int kNNThreads = 128;
 
 __global__ void __launch_bounds__(kNNThreads) k_nn_search(const float4 *__restrict__ q_xyzl, const float4 *__restrict__ q_nrm,
@@ -817,7 +853,7 @@ __global__ void __launch_bounds__(kNNThreads) k_nn_search(const float4 *__restri
 		const uint32_t *__restrict__ s_vals, int n_first,
 		const m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp,
 		float search_radius, int max_inner, int max_outer, int prune,
-		int *__restrict__ nn_out, int *__restrict__ nn_seq, unsigned long long *__restrict__ label_counts,
+		int *__restrict__ nn_out, float4 *__restrict__ obs_rec, const float4 *__restrict__ src_xyzl, unsigned long long *__restrict__ label_counts,
 		unsigned long long *__restrict__ eval_counter, const int *__restrict__ seg_of_chunk)
 {
 	pdl_enter();
@@ -844,7 +880,11 @@ __global__ void __launch_bounds__(kNNThreads) k_nn_search(const float4 *__restri
 	int result = -1;
 	if (best_l != kNNNone && best_l >= 0 && best_l < n_first) result = (int)__ldg(s_vals + best_l);
 	if (qi < n_second) {
-		if (nn_seq) nn_seq[qi] = result;
+		if (obs_rec) {
+			float4 rec = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+			if (result >= 0) { rec = __ldg(src_xyzl + result); rec.w = __int_as_float(result); }
+			obs_rec[qi] = rec;
+		}
 		if (nn_out) nn_out[q_perm ? __ldg(q_perm + qi) : (uint32_t)qi] = result;
 	}
 	if (eval_counter) {
@@ -957,7 +997,7 @@ __device__ __noinline__ int nn_query_fallback(const m3dreg_grid_params *__restri
 			const float4 n_ = __ldg(cn + (J));                                                                          \
 			if (__float_as_int(n_.w) == label) {                                                                        \
 				const float dot_ = f_fma(pn.z, n_.z, f_fma(pn.x, n_.x, f_mul(pn.y, n_.y)));                             \
-				if (angle_gate(dot_)) { best_d = (D); best_l = l_; lim = (D); }                                        \
+				if (angle_gate(dot_)) { best_d = (D); best_l = l_; best_j = (J); lim = (D); }                          \
 			}                                                                                                           \
 		}                                                                                                               \
 	}
@@ -967,7 +1007,7 @@ __global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_gr
 		const uint32_t *__restrict__ s_vals, int n_first,
 		const m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp,
 		float search_radius, int cap, int prune, NNTuning tune,
-		int *__restrict__ nn_out, int *__restrict__ nn_seq, unsigned long long *__restrict__ label_counts,
+		int *__restrict__ nn_out, float4 *__restrict__ obs_rec, const float4 *__restrict__ src_xyzl, unsigned long long *__restrict__ label_counts,
 		unsigned long long *__restrict__ eval_counter, const int *__restrict__ seg_of_chunk)
 {
 	pdl_enter();
@@ -1000,7 +1040,7 @@ __global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_gr
 	const float4 *__restrict__ cn = cs.nrm;
 
 	unsigned int evals = 0;
-	int best_l = kNNNone, label = -1;
+	int best_l = kNNNone, best_j = -1, label = -1;                     /* best_j: the winner's slot in the candidate set (-1: found by nn_query()) */
 	float best_d = 100000000.0f;                                        /* lesson_16.cu:597 */
 	float lim = fminf(r2, 99999992.0f);
 	float qx = 0.0f, qy = 0.0f, qz = 0.0f;
@@ -1074,8 +1114,11 @@ __global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_gr
 						const unsigned fb = __ballot_sync(full, unsettled);
 						if (lane == 0) atomicAdd(eval_counter + 1, (unsigned long long)__popc(fb));
 					}
-					if (unsettled) best_l = nn_query_fallback(gp, buckets, cs.xyzl, cs.nrm, cs.tab, search_radius, cap, prune ? 1 : 0,
-							make_float4(qx, qy, qz, __int_as_float(label)), pn, &evals);
+					if (unsettled) {
+						best_l = nn_query_fallback(gp, buckets, cs.xyzl, cs.nrm, cs.tab, search_radius, cap, prune ? 1 : 0,
+								make_float4(qx, qy, qz, __int_as_float(label)), pn, &evals);
+						best_j = -1;
+					}
 					unsettled = false;
 					break;
 				}
@@ -1257,10 +1300,21 @@ __global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_gr
 	}
 #undef M3D_NN_CONSIDER
 
+	/* the winner: its record in the candidate set carries the point as stored in the scan (local frame) and its original
+	 * index — one gather instead of hash[l] -> cloud[index] (lesson_16.cu:640-647, gpu6DSLAM.cpp:367-369) */
 	int result = -1;
-	if (best_l != kNNNone && best_l >= 0 && best_l < n_first) result = (int)__ldg(s_vals + best_l);
+	float4 rec = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+	if (best_l != kNNNone && best_l >= 0 && best_l < n_first) {
+		if (best_j >= 0) {
+			rec = __ldg(cs.loc + best_j);
+			result = __float_as_int(rec.w);
+		} else {
+			result = (int)__ldg(s_vals + best_l);
+			if (obs_rec) { rec = __ldg(src_xyzl + result); rec.w = __int_as_float(result); }
+		}
+	}
 	if (qi < n_second) {
-		if (nn_seq) nn_seq[qi] = result;
+		if (obs_rec) obs_rec[qi] = rec;
 		if (nn_out) nn_out[q_perm ? __ldg(q_perm + qi) : (uint32_t)qi] = result;
 	}
 	if (eval_counter) {
@@ -1277,12 +1331,13 @@ __global__ void __launch_bounds__(kNNGThreads, M3D_NNG_MINBLOCKS) k_nn_search_gr
 	}
 }
 
-/* correspondences from query order into the caller's order: out[perm[i]] = in[i] (perm == 0: identity) */
-__global__ void k_scatter_nn(const uint32_t *__restrict__ perm, int n, const int *__restrict__ in, int *__restrict__ out)
+/* correspondences from the search's per-query records (query order) into the caller's order:
+ * out[perm[i]] = index carried by rec[i] (perm == 0: identity) */
+__global__ void k_scatter_nn(const uint32_t *__restrict__ perm, int n, const float4 *__restrict__ rec, int *__restrict__ out)
 {
 	pdl_enter();
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-		out[perm ? __ldg(perm + i) : (uint32_t)i] = __ldg(in + i);
+		out[perm ? __ldg(perm + i) : (uint32_t)i] = __float_as_int(__ldg(reinterpret_cast<const float *>(rec + i) + 3));
 }
 
 /* gather a stored scan into query order: out[i] = in[perm[i]] */
@@ -1636,12 +1691,11 @@ __device__ inline void moments_to_neq_warp(const double *mo, double om, double f
 	__syncwarp();
 }
 
-/* Per-observation sources for the moment reduction.  Three steps so that a thread can keep several observations in
- * flight: token(i) (first load), fetch(i, token, raw) (dependent gathers), finish(raw, ...) (arithmetic). */
-struct ObsFromNN {   /* fused path: nn[] + clouds (gpu6DSLAM.cpp:323-398 done on the device) */
-	const int *nn;
+/* Per-observation sources for the moment reduction: load(i, raw) issues the (independent, coalesced) loads of
+ * observation i and says whether there is one; finish(raw, ...) is the arithmetic.  A thread keeps several in flight. */
+struct ObsFromRec {  /* fused path: the search's per-query records + the queries (gpu6DSLAM.cpp:323-398 done on the device) */
+	const float4 *rec;          /* {x0, y0, z0 of the matched first-cloud point in ITS LOCAL frame, bits of its index or -1} */
 	const float4 *q_xyzl;       /* queries (second cloud, global)           */
-	const float4 *l_xyzl;       /* first cloud, local, original order       */
 	const float *m;             /* pose the first cloud was transformed with this iteration (device, row-major 4x4) */
 	const unsigned long long *label_counts;   /* 4 counters per segment */
 	const int *seg_of_chunk;    /* batched sweep: segment of query i / kSegChunk (0: one segment) */
@@ -1654,11 +1708,11 @@ struct ObsFromNN {   /* fused path: nn[] + clouds (gpu6DSLAM.cpp:323-398 done on
 #pragma unroll
 		for (int k = 0; k < 12; k++) r[k] = __ldg(m + k);
 	}
-	__device__ __forceinline__ int token(int i) const { return __ldg(nn + i); }
-	__device__ __forceinline__ void fetch(int i, int j, Raw &raw) const
+	__device__ __forceinline__ bool load(int i, Raw &raw) const
 	{
-		raw.p2 = __ldg(q_xyzl + i); raw.p0 = __ldg(l_xyzl + j);
+		raw.p0 = __ldg(rec + i); raw.p2 = __ldg(q_xyzl + i);
 		raw.seg = seg_of_chunk ? __ldg(seg_of_chunk + i / kSegChunk) : 0;
+		return __float_as_int(raw.p0.w) >= 0;
 	}
 	__device__ __forceinline__ void finish(const Raw &raw, const float *wl, double &w, double &x, double &y, double &z,
 			double &lx, double &ly, double &lz) const
@@ -1666,8 +1720,8 @@ struct ObsFromNN {   /* fused path: nn[] + clouds (gpu6DSLAM.cpp:323-398 done on
 		int label = __float_as_int(raw.p2.w);
 		w = (label >= 0 && label < 4) ? (double)wl[4 * raw.seg + label] : 0.0;
 		x = raw.p0.x; y = raw.p0.y; z = raw.p0.z;
-		/* the matched point in the global frame, recomputed with k_transform_soa's exact operation sequence (same bits as
-		 * the transformed cloud the search ran on) instead of a second random gather */
+		/* the matched point in the global frame, recomputed with the transform's exact operation sequence (same bits as
+		 * the transformed cloud the search ran on) instead of a second gather */
 		float p1x = __fadd_rn(r[3], __fmaf_rn(r[2], raw.p0.z, __fmaf_rn(r[0], raw.p0.x, __fmul_rn(r[1], raw.p0.y))));
 		float p1y = __fadd_rn(r[7], __fmaf_rn(r[6], raw.p0.z, __fmaf_rn(r[4], raw.p0.x, __fmul_rn(r[5], raw.p0.y))));
 		float p1z = __fadd_rn(r[11], __fmaf_rn(r[10], raw.p0.z, __fmaf_rn(r[8], raw.p0.x, __fmul_rn(r[9], raw.p0.y))));
@@ -1679,12 +1733,12 @@ struct ObsFromList { /* stage-level path: the reference's obs_nn_t array */
 	const m3dreg_obs_nn *obs;
 	struct Raw { float v[7]; };
 	__device__ __forceinline__ void prepare() {}
-	__device__ __forceinline__ int token(int) const { return 0; }
-	__device__ __forceinline__ void fetch(int i, int, Raw &r) const
+	__device__ __forceinline__ bool load(int i, Raw &r) const
 	{
 		const float *o = reinterpret_cast<const float *>(obs + i);
 #pragma unroll
 		for (int k = 0; k < 7; k++) r.v[k] = __ldg(o + k);
+		return true;
 	}
 	__device__ __forceinline__ void finish(const Raw &r, const float *, double &w, double &x, double &y, double &z,
 			double &lx, double &ly, double &lz) const
@@ -1767,7 +1821,7 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(const Src src_
 	__shared__ double sm[kNeqThreads / 32][kMomentCount];
 	__shared__ float wl[4 * kMaxSegs];
 	__shared__ bool is_last;
-	if constexpr (std::is_same<Src, ObsFromNN>::value) {
+	if constexpr (std::is_same<Src, ObsFromRec>::value) {
 		static_assert(4 * kMaxSegs <= kNeqThreads, "one thread per (segment, label) weight");
 		if ((int)threadIdx.x < 4 * src.n_segs) {
 			unsigned long long c = src.label_counts[threadIdx.x];
@@ -1781,18 +1835,16 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(const Src src_
 	Moments mo;
 	mo.clear();
 	{
-		/* kNeqInFlight observations per thread in flight: index loads, then the dependent gathers, then the arithmetic */
+		/* kNeqInFlight observations per thread in flight: all loads (coalesced streams), then the arithmetic */
 		const int stride = gridDim.x * blockDim.x;
 		for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += kNeqInFlight * stride) {
-			int tok[kNeqInFlight];
+			bool tok[kNeqInFlight];
 			typename Src::Raw raw[kNeqInFlight];
 #pragma unroll
-			for (int k = 0; k < kNeqInFlight; k++) { int i = i0 + k * stride; tok[k] = i < n ? src.token(i) : -1; }
-#pragma unroll
-			for (int k = 0; k < kNeqInFlight; k++) { int i = i0 + k * stride; if (tok[k] >= 0) src.fetch(i, tok[k], raw[k]); }
+			for (int k = 0; k < kNeqInFlight; k++) { int i = i0 + k * stride; tok[k] = i < n && src.load(i, raw[k]); }
 #pragma unroll
 			for (int k = 0; k < kNeqInFlight; k++) {
-				if (tok[k] >= 0) {
+				if (tok[k]) {
 					double w, x, y, z, lx, ly, lz;
 					src.finish(raw[k], wl, w, x, y, z, lx, ly, lz);
 					mo.add(w, x, y, z, lx, ly, lz);

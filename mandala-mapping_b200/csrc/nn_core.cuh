@@ -112,6 +112,8 @@ struct CandSet {
 	float4 *xyzl;            /* {x, y, z, bits of l = position in the sorted table (hashElement index)} */
 	float4 *nrm;             /* {nx, ny, nz, label bits}                                              */
 	unsigned short *tab;     /* bin offset tables: the bucket with index_begin b owns tab[2b, 2b + 2n) */
+	float4 *loc;             /* {x0, y0, z0 as stored in the scan (LOCAL frame in the fused loops), bits of the original index};
+	                          * only the device kernels touch it (nn_query() does not) */
 };
 
 /* log2 of the sub-cells per axis for a bucket with npts points, -1 = no table (candidates stored in walk order).
