@@ -372,12 +372,20 @@ def main():
     ctx.nn_fallbacks(reset=True)
     ctx.icp_step(min(args.steps, 10))
     stage_ms, stage_iters = ctx.get_stage_ms()
+    try:
+        gph = ctx.grid_phase_ns().astype(np.int64)
+        names = ["box", "barrier1", "keys+hist", "barrier2", "sort pass 1 + count scan", "barrier3", "bucket table + sort pass 2", "barrier4",
+                 "(sort pass 3)", "candidate sets"]
+        grid_phases_us = {names[k]: float(gph[k + 1] - gph[k]) / 1e3 for k in range(10)} if gph[10] > gph[0] > 0 else None
+    except Exception:
+        grid_phases_us = None
     evals_per_query = ctx.nn_evaluations(reset=True) / max(stage_iters, 1) / float(n2)
     fallback_share = ctx.nn_fallbacks(reset=True) / max(stage_iters, 1) / float(n2)
     ctx.set_profiling(False)
     ctx.icp_end()
     stage_ms = stage_ms / max(stage_iters, 1)
-    stage_names = ["transform+bounds", "grid (keys, radix sort, bucket table, gather)", "semantic NN (k_nn_search_grid)", "normal equations + solve"]
+    stage_names = ["transform+bounds (part of the grid launch unless M3DREG_GRID_LEGACY=1)", "grid (k_grid_build: transform, box, keys, sort, bucket table, candidate sets)",
+                   "semantic NN (k_nn_search_grid)", "normal equations + solve"]
     dom = int(np.argmax(stage_ms))
     nn_ms = float(stage_ms[2])
     nn_bytes = nn_alg_bytes(n1, n2, nb)
@@ -441,6 +449,7 @@ def main():
                 "nn_candidate_evaluations_per_query": evals_per_query,
                 "nn_queries_on_per_thread_fallback": fallback_share,
                 "stage_ms": {stage_names[k]: float(stage_ms[k]) for k in range(4)},
+                "grid_phases_us": grid_phases_us,
                 "iteration": {"algorithmic_bytes": iter_bytes, "achieved": iter_gbs, "frac": iter_gbs / peak_gbs,
                               "note": "whole iteration (all kernels) vs the HBM roofline, B_alg = 104*N1 + 36*N2 + 24*B + 40*Nc"},
             },

@@ -156,6 +156,11 @@ int m3dreg_get_nn_evaluations(m3dreg_ctx *ctx, uint64_t *count_out, int reset);
  * order); tests use it to prove which code path produced a result. */
 int m3dreg_get_nn_fallbacks(m3dreg_ctx *ctx, uint64_t *count_out, int reset);
 
+/* Diagnostic (only while profiling is on): %globaltimer stamps (ns) of block 0 at the phase boundaries of the last
+ * k_grid_build launch — 0 entry, 1 box done, 2 barrier, 3 keys done, 4 barrier, 5 first sort pass done, 6 barrier,
+ * 7 bucket table + second pass done, 8 barrier, 9 (third pass), 10 candidate sets done.  stamps_out: 16 entries. */
+int m3dreg_get_grid_phase_ns(m3dreg_ctx *ctx, uint64_t *stamps_out);
+
 /* ---- stage-level entry points on DEVICE pointers (parity surface = reference L0) ---------- */
 
 /* ref: cudaCalculateGridParams (include/lesson_16.h:61-62, src/lesson_16.cu:23-106).

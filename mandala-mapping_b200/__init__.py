@@ -45,6 +45,7 @@ EXPORTS = [
     "m3dreg_export_last_grid", "m3dreg_export_last_nn", "m3dreg_sweep_zero", "m3dreg_sweep_accumulate",
     "m3dreg_sweep_solve", "m3dreg_icp_begin", "m3dreg_icp_step", "m3dreg_icp_end", "m3dreg_icp_copy_neq", "m3dreg_icp_set_neq_out",
     "m3dreg_set_profiling", "m3dreg_get_stage_ms", "m3dreg_set_pruning", "m3dreg_get_nn_evaluations", "m3dreg_get_nn_fallbacks",
+    "m3dreg_get_grid_phase_ns",
 ]
 
 
@@ -179,6 +180,12 @@ class Context:
         v = C.c_uint64(0)
         _check(lib().m3dreg_get_nn_fallbacks(self._h, C.byref(v), C.c_int(1 if reset else 0)), "m3dreg_get_nn_fallbacks")
         return int(v.value)
+
+    def grid_phase_ns(self) -> np.ndarray:
+        """%globaltimer stamps of the last k_grid_build launch (profiling on): see m3dreg_get_grid_phase_ns."""
+        out = np.zeros(16, dtype=np.uint64)
+        _check(lib().m3dreg_get_grid_phase_ns(self._h, _p(out)), "m3dreg_get_grid_phase_ns")
+        return out
 
     def set_pruning(self, enabled: bool):
         _check(lib().m3dreg_set_pruning(self._h, C.c_int(1 if enabled else 0)), "m3dreg_set_pruning")

@@ -45,9 +45,13 @@ struct GridBlockRec {       /* level-1 result of the bucket-count scan for one b
 	int pad[3];
 };
 
+constexpr int kGbCacheMaxBytes = 160 * 1024;             /* dynamic shared memory for the block's transformed points */
+
 struct GridBuildArgs {
 	const float4 *lx, *ln;          /* the scan being gridded, original order (local frame unless pose == 0) */
 	int n;
+	int cache;                      /* the block's T transformed points fit in dynamic shared memory (3 float arrays of T) */
+	unsigned long long *dbg;        /* optional: globaltimer of block 0 at the phase boundaries (diagnostics), 0 = off */
 	const float *pose;              /* DEVICE row-major 4x4 applied to lx / ln; 0 = identity (cloud already global) */
 	float res, ext;
 	long long bucket_cap;           /* entries allocated for buckets / bcount */
@@ -55,7 +59,7 @@ struct GridBuildArgs {
 	int build_cands;                /* 0: grid only (NDT) */
 	float4 *g_xyzl;                 /* optional: the transformed cloud in original order (NDT, exports); 0 = not kept */
 	uint32_t *keys[2], *vals[2];
-	uint32_t *hist;                 /* 3 matrices [gridDim][256] */
+	uint32_t *hist;                 /* 3 matrices [256][Gp], Gp = gridDim rounded up to 4 (digit-major: a block reads rows with 128-bit loads) */
 	int *bcount;                    /* dense per-bucket counts: all zero on entry, all zero on exit */
 	int *bbegin;                    /* scratch, bucket_cap ints: slice-relative begin */
 	m3dreg_bucket *buckets;
@@ -135,35 +139,35 @@ __device__ __forceinline__ long long gb_block_excl_scan(long long v, long long *
 }
 
 /* One stable LSD pass over the block's range: keys_in/vals_in -> keys_out/vals_out by digit (key >> shift) & mask.
- * hist = this pass's [gridDim][256] matrix of per-block digit counts (complete); hist_next (0 for the last pass) gets
- * the next digit's counts per DESTINATION block.  vals_in == 0: implicit original indices. */
-__device__ __forceinline__ void gb_scatter_pass(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
+ * hist = this pass's [256][Gp] matrix of per-block digit counts (complete); hist_next (0 for the last pass) gets
+ * the next digit's counts per DESTINATION block.  vals_in == 0: implicit original indices.  keys_smem != 0: the block's
+ * keys are still in shared memory from the key phase (first pass: a block sorts the range it made the keys of). */
+__device__ __forceinline__ void gb_scatter_pass(const uint32_t *keys_in, const uint32_t *keys_smem, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
 		int n, int T, int shift, int dbits, const uint32_t *hist, uint32_t *hist_next, uint32_t (*s_w)[kGbRadix], uint32_t *s_gbase,
-		uint32_t (*s_part)[kGbRadix], long long *s_scan)
+		long long *s_scan)
 {
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const uint32_t mask = (1u << dbits) - 1u;
 	const int G = (int)gridDim.x, c = (int)blockIdx.x;
-	/* a) where this block's digits start: sum of the digit's counts in earlier blocks + all smaller digits everywhere */
+	/* a) where this block's digits start: sum of the digit's counts in earlier blocks + all smaller digits everywhere.
+	 * Thread (d, quarter) adds every fourth 128-bit piece of row d: ~10 independent loads in flight, one L2 latency */
 	{
-		const int d = threadIdx.x & 255, grp = threadIdx.x >> 8;          /* 4 groups of 256 threads split the rows */
+		const int d = threadIdx.x >> 2, qd = threadIdx.x & 3;
+		const int Gp = (G + 3) & ~3;
+		const uint4 *row = reinterpret_cast<const uint4 *>(hist + (size_t)d * Gp);
 		uint32_t pre = 0, tot = 0;
-		for (int r = grp; r < G; r += 4) {
-			const uint32_t v = __ldcg(hist + (size_t)r * kGbRadix + d);
-			tot += v;
-			pre += r < c ? v : 0u;
+#pragma unroll 5
+		for (int j = qd; j < (Gp >> 2); j += 4) {
+			const uint4 v = __ldcg(row + j);
+			const int r0 = j << 2;
+			tot += v.x + v.y + v.z + v.w;
+			pre += (r0 < c ? v.x : 0u) + (r0 + 1 < c ? v.y : 0u) + (r0 + 2 < c ? v.z : 0u) + (r0 + 3 < c ? v.w : 0u);
 		}
-		s_part[grp][d] = pre;
-		s_w[grp][d] = tot;
-		__syncthreads();
-		int tsum = 0, psum = 0;
-		if (threadIdx.x < 256) {
-			tsum = (int)(s_w[0][d] + s_w[1][d] + s_w[2][d] + s_w[3][d]);
-			psum = (int)(s_part[0][d] + s_part[1][d] + s_part[2][d] + s_part[3][d]);
-		}
+		tot += __shfl_xor_sync(0xffffffffu, tot, 1); tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+		pre += __shfl_xor_sync(0xffffffffu, pre, 1); pre += __shfl_xor_sync(0xffffffffu, pre, 2);
 		long long total;
-		const long long ex = gb_block_excl_scan(threadIdx.x < 256 ? (long long)tsum : 0LL, s_scan, &total);
-		if (threadIdx.x < 256) s_gbase[d] = (uint32_t)((int)ex + psum);
+		const long long ex = gb_block_excl_scan(qd == 0 ? (long long)tot : 0LL, s_scan, &total);      /* thread order = digit order */
+		if (qd == 0) s_gbase[d] = (uint32_t)((int)ex + (int)pre);
 		__syncthreads();
 	}
 	const int begin = c * T, end = min(n, begin + T);
@@ -178,7 +182,7 @@ __device__ __forceinline__ void gb_scatter_pass(const uint32_t *keys_in, const u
 		for (int j = 0; j < kGbItems; j++) {
 			const int i = wbase + j * 32 + lane;
 			const bool valid = i < end;
-			key[j] = valid ? __ldcg(keys_in + i) : 0xFFFFFFFFu;
+			key[j] = valid ? (keys_smem ? keys_smem[i - begin] : __ldcg(keys_in + i)) : 0xFFFFFFFFu;
 			val[j] = valid ? (vals_in ? __ldcg(vals_in + i) : (uint32_t)i) : 0u;
 		}
 #pragma unroll
@@ -228,7 +232,7 @@ __device__ __forceinline__ void gb_scatter_pass(const uint32_t *keys_in, const u
 			for (int j = 0; j < kGbItems; j++) {
 				const int i = wbase + j * 32 + lane;
 				const bool valid = i < end;
-				const uint32_t slot = valid ? (rank[j] / (uint32_t)T) * kGbRadix + ((key[j] >> (shift + dbits)) & mask) : (0xFFFFFF00u + lane);
+				const uint32_t slot = valid ? ((key[j] >> (shift + dbits)) & mask) * (uint32_t)((G + 3) & ~3) + rank[j] / (uint32_t)T : (0xFFFFFF00u + lane);
 				const uint32_t peers = __match_any_sync(0xffffffffu, slot);
 				if (valid && lane == __ffs(peers) - 1) atomicAdd(hist_next + slot, (uint32_t)__popc(peers));
 			}
@@ -239,40 +243,59 @@ __device__ __forceinline__ void gb_scatter_pass(const uint32_t *keys_in, const u
 	}
 }
 
+#define M3D_GB_STAMP(slot) do { if (a.dbg && c == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.dbg[slot] = t_; } } while (0)
+
 __global__ void __launch_bounds__(kGbThreads, 1) k_grid_build(const GridBuildArgs a)
 {
 	pdl_enter();
+	extern __shared__ float s_pts[];                               /* cache != 0: x[T], y[T], z[T] of the block's transformed points; x is later the keys */
 	__shared__ uint32_t s_raw[kGbWarps * (kBuildTabMax + 7)];      /* scatter: [32][256] warp digit counts; candidates: [32][264] bin tables */
 	__shared__ uint32_t s_gbase[kGbRadix];
-	__shared__ uint32_t s_part[4][kGbRadix];
 	__shared__ long long s_scan[kGbWarps + 1];
 	__shared__ int s_rec[8];
 	uint32_t (*s_w)[kGbRadix] = reinterpret_cast<uint32_t (*)[kGbRadix]>(s_raw);
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int G = (int)gridDim.x, c = (int)blockIdx.x;
+	const int Gp = (G + 3) & ~3;
 	const int n = a.n;
 	unsigned int gen = 0;
 	if (threadIdx.x == 0) gen = ld_acquire_u32(a.bar + 1);
+	M3D_GB_STAMP(0);
 	/* block ranges: T a multiple of 32 so that warps never straddle two blocks' ranges */
 	const int T = (((n + G - 1) / G) + 31) & ~31;
 	const int begin = min(n, c * T), end = min(n, begin + T);
+	float *s_x = s_pts, *s_y = s_pts + T, *s_z = s_pts + 2 * T;
+	uint32_t *s_keys = reinterpret_cast<uint32_t *>(s_pts);
 
 	PointXform xf;
 	xf.on = a.pose != nullptr;
 #pragma unroll
 	for (int k = 0; k < 12; k++) xf.r[k] = xf.on ? __ldg(a.pose + k) : 0.0f;
 
-	/* ---- P1: bounding box of the transformed cloud (replaces 3x thrust::minmax_element, lesson_16.cu:34-45) ---- */
+	/* ---- P1: bounding box of the transformed cloud (replaces 3x thrust::minmax_element, lesson_16.cu:34-45);
+	 *      four independent loads per thread in flight; the transformed points stay in shared memory for P2 ---- */
 	{
 		float mnx = INFINITY, mny = INFINITY, mnz = INFINITY, mxx = -INFINITY, mxy = -INFINITY, mxz = -INFINITY;
-		for (int i = begin + (int)threadIdx.x; i < end; i += kGbThreads) {
-			const float4 p = xform_point(xf, __ldg(a.lx + i));
-			mnx = fminf(mnx, p.x); mny = fminf(mny, p.y); mnz = fminf(mnz, p.z);
-			mxx = fmaxf(mxx, p.x); mxy = fmaxf(mxy, p.y); mxz = fmaxf(mxz, p.z);
+		for (int i0 = begin + (int)threadIdx.x; i0 < end; i0 += 4 * kGbThreads) {
+			float4 p[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++) { const int i = i0 + k * kGbThreads; p[k] = __ldg(a.lx + (i < end ? i : i0)); }
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const int i = i0 + k * kGbThreads;
+				if (i < end) {
+					const float4 q = xform_point(xf, p[k]);
+					mnx = fminf(mnx, q.x); mny = fminf(mny, q.y); mnz = fminf(mnz, q.z);
+					mxx = fmaxf(mxx, q.x); mxy = fmaxf(mxy, q.y); mxz = fmaxf(mxz, q.z);
+					if (a.cache) { s_x[i - begin] = q.x; s_y[i - begin] = q.y; s_z[i - begin] = q.z; }
+				}
+			}
 		}
 		block_bounds_commit(mnx, mny, mnz, mxx, mxy, mxz, a.bounds);
 	}
+	M3D_GB_STAMP(1);
 	grid_barrier(a.bar, gen);
+	M3D_GB_STAMP(2);
 
 	/* ---- P2: grid parameters, keys, first-digit histogram, dense bucket counts ---- */
 	m3dreg_grid_params g;
@@ -287,19 +310,23 @@ __global__ void __launch_bounds__(kGbThreads, 1) k_grid_build(const GridBuildArg
 		*a.gp = g;
 		if (!ok) atomicExch(&a.flags[FLAG_ERROR], M3DREG_E_TOO_MANY_BUCKETS);
 	}
-	if (!ok) return;      /* every block takes the same decision: nobody is left waiting (the host re-arms bounds / counts) */
+	if (!ok) return;      /* every block takes the same decision: nobody is left waiting (the host re-arms the bounds) */
 	const long long nb = g.number_of_buckets;
 	const int bits = gb_bits_for(nb);
 	const int passes = (bits + 7) / 8;
 	const int dbits = (bits + passes - 1) / passes;
 	const uint32_t dmask = (1u << dbits) - 1u;
 	const int start = (passes & 1) ? 0 : 1;      /* the sorted table always ends up in buffer 1 */
-	uint32_t *hist0 = a.hist, *hist1 = a.hist + (size_t)G * kGbRadix, *hist2 = a.hist + 2 * (size_t)G * kGbRadix;
+	uint32_t *hist0 = a.hist, *hist1 = a.hist + (size_t)Gp * kGbRadix, *hist2 = a.hist + 2 * (size_t)Gp * kGbRadix;
 	{
 		if (threadIdx.x < kGbRadix) {
 			s_gbase[threadIdx.x] = 0;      /* block digit histogram */
-			hist1[(size_t)c * kGbRadix + threadIdx.x] = 0;
-			hist2[(size_t)c * kGbRadix + threadIdx.x] = 0;
+			hist1[(size_t)threadIdx.x * Gp + c] = 0;
+			hist2[(size_t)threadIdx.x * Gp + c] = 0;
+		}
+		if (c == 0) {                     /* padding columns G..Gp-1 of the three matrices (the buffer is shared with other sorts) */
+			for (int t = (int)threadIdx.x; t < 3 * kGbRadix * (Gp - G); t += kGbThreads)
+				a.hist[(size_t)(t / (Gp - G)) * Gp + G + t % (Gp - G)] = 0;
 		}
 		__syncthreads();
 		const int nby = g.number_of_buckets_Y, nbz = g.number_of_buckets_Z;
@@ -308,12 +335,15 @@ __global__ void __launch_bounds__(kGbThreads, 1) k_grid_build(const GridBuildArg
 			const int i = begin + o;
 			int key = -1;
 			if (i < end) {
-				const float4 p = xform_point(xf, __ldg(a.lx + i));
+				float4 p;
+				if (a.cache) p = make_float4(s_x[o], s_y[o], s_z[o], 0.0f);
+				else p = xform_point(xf, __ldg(a.lx + i));
 				const int ix = cell_of(p.x, g.bounding_box_min_X, a.res), iy = cell_of(p.y, g.bounding_box_min_Y, a.res),
 						iz = cell_of(p.z, g.bounding_box_min_Z, a.res);
 				key = ix * nby * nbz + iy * nbz + iz;
-				a.keys[start][i] = (uint32_t)key;
-				if (a.g_xyzl) a.g_xyzl[i] = p;
+				if (a.cache) s_keys[o] = (uint32_t)key;      /* over x[o], which only this thread reads */
+				else a.keys[start][i] = (uint32_t)key;
+				if (a.g_xyzl) { p.w = a.cache ? __ldg(&a.lx[i].w) : p.w; a.g_xyzl[i] = p; }
 			}
 			/* runs of equal keys inside the warp: one shared-memory and one global atomic per run */
 			const int prev = __shfl_up_sync(0xffffffffu, key, 1);
@@ -327,9 +357,11 @@ __global__ void __launch_bounds__(kGbThreads, 1) k_grid_build(const GridBuildArg
 			}
 		}
 		__syncthreads();
-		if (threadIdx.x < kGbRadix) hist0[(size_t)c * kGbRadix + threadIdx.x] = s_gbase[threadIdx.x];
+		if (threadIdx.x < kGbRadix) hist0[(size_t)threadIdx.x * Gp + c] = s_gbase[threadIdx.x];
 	}
+	M3D_GB_STAMP(3);
 	grid_barrier(a.bar, gen);
+	M3D_GB_STAMP(4);
 
 	/* ---- P3: LSD pass 0 + bucket-count scan level 1 ---- */
 	const int S = (int)((nb + G - 1) / G);                       /* dense-table slice per block */
@@ -359,8 +391,10 @@ __global__ void __launch_bounds__(kGbThreads, 1) k_grid_build(const GridBuildArg
 			a.brec[c] = r;
 		}
 	}
-	gb_scatter_pass(a.keys[start], nullptr, a.keys[start ^ 1], a.vals[start ^ 1], n, T, 0, dbits, hist0, passes > 1 ? hist1 : nullptr, s_w, s_gbase, s_part, s_scan);
+	gb_scatter_pass(a.keys[start], a.cache ? s_keys : nullptr, nullptr, a.keys[start ^ 1], a.vals[start ^ 1], n, T, 0, dbits, hist0, passes > 1 ? hist1 : nullptr, s_w, s_gbase, s_scan);
+	M3D_GB_STAMP(5);
 	grid_barrier(a.bar, gen);
+	M3D_GB_STAMP(6);
 
 	/* ---- P4: bucket-count scan level 2 -> dense table + searchable-bucket list; LSD pass 1 ---- */
 	{
@@ -438,12 +472,15 @@ __global__ void __launch_bounds__(kGbThreads, 1) k_grid_build(const GridBuildArg
 		}
 	}
 	if (passes > 1)
-		gb_scatter_pass(a.keys[start ^ 1], a.vals[start ^ 1], a.keys[start], a.vals[start], n, T, dbits, dbits, hist1, passes > 2 ? hist2 : nullptr, s_w, s_gbase, s_part, s_scan);
+		gb_scatter_pass(a.keys[start ^ 1], nullptr, a.vals[start ^ 1], a.keys[start], a.vals[start], n, T, dbits, dbits, hist1, passes > 2 ? hist2 : nullptr, s_w, s_gbase, s_scan);
+	M3D_GB_STAMP(7);
 	grid_barrier(a.bar, gen);
+	M3D_GB_STAMP(8);
 	if (passes > 2) {
-		gb_scatter_pass(a.keys[start], a.vals[start], a.keys[start ^ 1], a.vals[start ^ 1], n, T, 2 * dbits, dbits, hist2, nullptr, s_w, s_gbase, s_part, s_scan);
+		gb_scatter_pass(a.keys[start], nullptr, a.vals[start], a.keys[start ^ 1], a.vals[start ^ 1], n, T, 2 * dbits, dbits, hist2, nullptr, s_w, s_gbase, s_scan);
 		grid_barrier(a.bar, gen);
 	}
+	M3D_GB_STAMP(9);
 	if (c == 0 && threadIdx.x == 0) {
 		a.bounds[0] = a.bounds[1] = a.bounds[2] = 0xFFFFFFFFu;      /* everybody read them before the second barrier */
 		a.bounds[3] = a.bounds[4] = a.bounds[5] = 0u;
@@ -476,6 +513,8 @@ __global__ void __launch_bounds__(kGbThreads, 1) k_grid_build(const GridBuildArg
 			if (two_sets) build_cell_candidates<true>(vals, a.lx, a.ln, nullptr, rot, xf, c_begin, c_n, a.max_outer, tables, cg, a.co, s_hist[w], lane);
 		}
 	}
+	__syncthreads();
+	M3D_GB_STAMP(10);
 }
 
 } /* namespace m3d */

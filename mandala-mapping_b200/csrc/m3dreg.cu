@@ -17,6 +17,7 @@
 
 #include "m3dreg_kernels.cuh"
 #include "grid_build.cuh"
+#include "nn_hull.cuh"
 
 using namespace m3d;
 
@@ -96,11 +97,14 @@ struct m3dreg_ctx {
 	DevBuf<int> bcount, bbegin;                      /* grid megakernel: dense per-bucket counts (zero between launches), slice-relative begins */
 	DevBuf<GridBlockRec> brec;
 	int coop_pdl = -1;                               /* cooperative + programmatic launch accepted together? (-1: not tried yet) */
+	bool gb_attr_set = false;                        /* k_grid_build's dynamic shared memory limit raised */
+	unsigned long long *gb_dbg = nullptr;            /* 16 phase time stamps of k_grid_build (only written while profiling) */
 	DevBuf<uint32_t> keys[2], vals[2], hist, digit_tot, cell_list;
 	DevBuf<m3dreg_bucket> buckets;
 	DevBuf<int> nn;
 	DevBuf<float4> obs_rec;                          /* per query, query order: matched point (local frame) + its index (k_nn_search*) */
 	int grid_legacy = 0;                             /* env M3DREG_GRID_LEGACY=1: the multi-kernel grid build of round 1 (A/B runs) */
+	int nn_v7 = 0;                                   /* env M3DREG_NN_V7=1: round 1's k_nn_search_grid instead of k_nn_search_hull (A/B runs) */
 	cudaError_t launch_err = cudaSuccess;            /* first failed kernel launch since the last report */
 	DevBuf<m3dreg_point> aos_a, aos_b;
 	DevBuf<m3dreg_obs_nn> obs;
@@ -202,10 +206,15 @@ inline int launch_status(m3dreg_ctx *c)
  * attributes together (probed once per context). */
 inline void launch_grid_build(m3dreg_ctx *c, const GridBuildArgs &a)
 {
+	if (!c->gb_attr_set) {
+		cudaFuncSetAttribute(k_grid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbCacheMaxBytes);
+		c->gb_attr_set = true;
+	}
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((unsigned)c->sm_count, 1, 1);
 	cfg.blockDim = dim3((unsigned)kGbThreads, 1, 1);
-	cfg.dynamicSmemBytes = 0;
+	const int T = (((a.n + c->sm_count - 1) / c->sm_count) + 31) & ~31;      /* same expression as the kernel's */
+	cfg.dynamicSmemBytes = a.cache ? (size_t)T * 12 : 0;
 	cfg.stream = c->stream;
 	cudaLaunchAttribute attr[2];
 	attr[0].id = cudaLaunchAttributeCooperative;
@@ -423,14 +432,35 @@ void build_candidates(m3dreg_ctx *c, const uint32_t *vals, const m3dreg_bucket *
 			max_inner, max_outer, cand_set(c, false), cand_set(c, two), two ? 1 : 0);
 }
 
-/* src_xyzl: the first cloud as the moment reduction wants it (local frame in the fused loops), original order */
-void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *vals, int n1, const m3dreg_bucket *buckets,
+/* src_xyzl: the first cloud as the moment reduction wants it (local frame in the fused loops), original order;
+ * res: the grid's resolution per axis (what c->gp holds on the device) */
+void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *vals, int n1, const m3dreg_bucket *buckets, const float res[3],
 		float radius, int max_inner, int max_outer, int prune, int *nn_out, float4 *obs_rec, const float4 *src_xyzl,
 		unsigned long long *label_counts, const int *seg_of_chunk = nullptr)
 {
 	bool two = max_inner != max_outer;
 	if (nn_out == c->nn.p) c->nn_pending = false;      /* the caller-order buffer is being written directly */
-	if (!two && !c->nn_per_thread) {     /* one candidate set (the reference's default caps): warp-shared lookup grid */
+	if (!two && !c->nn_per_thread && !c->nn_v7) {      /* one candidate set (the reference's default caps): warp-shared hull search */
+		NNHullArgs a = {};
+		a.q_xyzl = c->q_xyzl.p; a.q_nrm = c->q_nrm.p; a.q_perm = q_perm; a.n_second = n2;
+		a.cs = cand_set(c, false); a.s_vals = vals; a.n_first = n1; a.buckets = buckets; a.gp = c->gp;
+		a.search_radius = radius;
+		/* launch constants, same IEEE operations as nn_params_finish() / the round-1 kernel computed per thread */
+		{
+			volatile float r2 = radius * radius, iwx = 4.0f / res[0], iwy = 4.0f / res[1], iwz = 4.0f / res[2];
+			volatile float rmin = fminf(res[0], fminf(res[1], res[2])) / (float)(c->nn_tune.rho_div > 0 ? c->nn_tune.rho_div : 16);
+			volatile float rho2 = rmin * rmin;
+			a.r2 = r2; a.iwx = iwx; a.iwy = iwy; a.iwz = iwz; a.rho2_first = fmaxf(rho2, 1.0e-30f);
+		}
+		a.cap = max_outer; a.prune = prune; a.tune = c->nn_tune;
+		a.nn_out = nn_out; a.obs_rec = obs_rec; a.src_xyzl = src_xyzl; a.label_counts = label_counts;
+		a.eval_counter = c->profiling ? c->eval_counter : nullptr; a.seg_of_chunk = seg_of_chunk;
+		const int blocks = (n2 + kNNHThreads - 1) / kNNHThreads;
+		if (c->profiling) LAUNCH(c, k_nn_search_hull<true>, blocks, kNNHThreads, a);
+		else LAUNCH(c, k_nn_search_hull<false>, blocks, kNNHThreads, a);
+		return;
+	}
+	if (!two && !c->nn_per_thread) {
 		LAUNCH(c, k_nn_search_grid, (n2 + kNNGThreads - 1) / kNNGThreads, kNNGThreads, c->q_xyzl.p, c->q_nrm.p, q_perm, n2,
 				cand_set(c, false), vals, n1, buckets, c->gp, radius, max_outer, prune, c->nn_tune, nn_out, obs_rec, src_xyzl, label_counts,
 				c->profiling ? c->eval_counter : nullptr, seg_of_chunk);
@@ -468,6 +498,11 @@ void build_grid_mega(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, 
 {
 	GridBuildArgs a = {};
 	a.lx = lx; a.ln = ln; a.n = n1; a.pose = pose;
+	{
+		const int T = (((n1 + c->sm_count - 1) / c->sm_count) + 31) & ~31;
+		a.cache = ((size_t)T * 12 <= (size_t)kGbCacheMaxBytes) ? 1 : 0;
+	}
+	a.dbg = c->profiling ? c->gb_dbg : nullptr;
 	a.res = prm->bucket_size; a.ext = prm->bbox_extension;
 	a.bucket_cap = (long long)c->buckets.cap;
 	a.max_inner = prm->max_inner; a.max_outer = prm->max_outer;
@@ -589,7 +624,8 @@ void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int
 	}
 	if (prof) cudaEventRecord(c->pev[2], c->stream);
 	/* the caller-order copy of the correspondences is only materialised when somebody asks for it (materialize_nn) */
-	launch_nn(c, c->act_perm, n2, c->vals[c->last_sorted].p, n1, c->buckets.p, prm->search_radius, prm->max_inner, prm->max_outer, 1,
+	const float res3[3] = {prm->bucket_size, prm->bucket_size, prm->bucket_size};
+	launch_nn(c, c->act_perm, n2, c->vals[c->last_sorted].p, n1, c->buckets.p, res3, prm->search_radius, prm->max_inner, prm->max_outer, 1,
 			nullptr, c->obs_rec.p, lx, c->label_counts);
 	c->nn_pending = true; c->nn_pending_perm = c->act_perm;
 	ObsFromRec src = {};
@@ -657,6 +693,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	{ const char *e = getenv("M3DREG_NO_PDL"); c->use_pdl = (e && e[0] == '1') ? 0 : 1; }
 	{ const char *e = getenv("M3DREG_NN_PER_THREAD"); c->nn_per_thread = (e && e[0] == '1') ? 1 : 0; }
 	{ const char *e = getenv("M3DREG_GRID_LEGACY"); c->grid_legacy = (e && e[0] == '1') ? 1 : 0; }
+	{ const char *e = getenv("M3DREG_NN_V7"); c->nn_v7 = (e && e[0] == '1') ? 1 : 0; }
 	{ const char *e = getenv("M3DREG_NN_RHO_DIV"); if (e && atoi(e) > 0) c->nn_tune.rho_div = atoi(e); }
 	{ const char *e = getenv("M3DREG_NN_HULL_MIN"); if (e && atoi(e) > 0) c->nn_tune.hull_min = atoi(e); }
 	{ const char *e = getenv("M3DREG_NN_HULL_RATIO"); if (e && atoi(e) > 0) c->nn_tune.hull_ratio = atoi(e); }
@@ -666,7 +703,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	cudaEventCreate(&c->ev0);
 	cudaEventCreate(&c->ev1);
 	size_t small = sizeof(PoseState) + 8 * sizeof(uint32_t) + sizeof(m3dreg_grid_params) + FLAG_COUNT * sizeof(int) +
-			4 * sizeof(unsigned long long) + 64 + 64 * sizeof(double) + 32 * sizeof(float) + 512;
+			4 * sizeof(unsigned long long) + 64 + 64 * sizeof(double) + 32 * sizeof(float) + 1024;
 	char *blk = nullptr;
 	e = cudaMalloc((void **)&blk, small);
 	if (e != cudaSuccess) { m3dreg_destroy(c); return (int)e; }
@@ -682,6 +719,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	c->ticket = (unsigned int *)take(16);
 	c->cell_count = (unsigned int *)take(16);
 	c->grid_bar = (unsigned int *)take(16);
+	c->gb_dbg = (unsigned long long *)take(16 * sizeof(unsigned long long));
 	c->eval_counter = (unsigned long long *)take(16);
 	c->mats = (float *)take(32 * sizeof(float));
 	e = cudaMallocHost((void **)&c->h, sizeof(HostSmall));
@@ -767,6 +805,15 @@ int m3dreg_get_nn_fallbacks(m3dreg_ctx *c, uint64_t *count_out, int reset)
 	return 0;
 }
 
+int m3dreg_get_grid_phase_ns(m3dreg_ctx *c, uint64_t *stamps_out)
+{
+	if (!c || !stamps_out) return M3DREG_E_INVALID_ARG;
+	CK(cudaSetDevice(c->dev));
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaMemcpy(stamps_out, c->gb_dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	return 0;
+}
+
 int m3dreg_set_pruning(m3dreg_ctx *c, int enabled)
 {
 	if (!c) return M3DREG_E_INVALID_ARG;
@@ -830,7 +877,8 @@ int m3dreg_nn_search(m3dreg_ctx *c, const m3dreg_point *d_first, int n1, const m
 	CK(cudaMemsetAsync(c->cell_count, 0, sizeof(unsigned int), c->stream));
 	LAUNCH(c, k_list_cells, grid_for(c, n1, 256), 256, c->keys[0].p, n1, d_buckets, c->cell_list.p, c->cell_count);
 	build_candidates(c, c->vals[0].p, d_buckets, c->cell_list.p, c->g_xyzl.p, c->g_nrm.p, (const float4 *)nullptr, (const float *)nullptr, max_inner, max_outer);
-	launch_nn(c, nullptr, n2, c->vals[0].p, n1, d_buckets, search_radius, max_inner, max_outer, c->prune, d_nn, (float4 *)nullptr, c->g_xyzl.p, nullptr);
+	const float res3[3] = {params->resolution_X, params->resolution_Y, params->resolution_Z};
+	launch_nn(c, nullptr, n2, c->vals[0].p, n1, d_buckets, res3, search_radius, max_inner, max_outer, c->prune, d_nn, (float4 *)nullptr, c->g_xyzl.p, nullptr);
 	c->last_valid = false;
 	CK(cudaStreamSynchronize(c->stream));
 	return (int)cudaGetLastError();
@@ -939,7 +987,8 @@ int m3dreg_semantic_nn_host(m3dreg_ctx *c, const m3dreg_point *first, int n1, co
 		LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);              /* k_grid_build reduces the box itself */
 		build_grid_mega(c, c->g_xyzl.p, c->g_nrm.p, n1, (const float *)nullptr, &prm, false);
 	}
-	launch_nn(c, nullptr, n2, c->vals[c->last_sorted].p, n1, c->buckets.p, search_radius, max_inner, max_outer, c->prune,
+	const float res3[3] = {bucket_size, bucket_size, bucket_size};
+	launch_nn(c, nullptr, n2, c->vals[c->last_sorted].p, n1, c->buckets.p, res3, search_radius, max_inner, max_outer, c->prune,
 			c->nn.p, (float4 *)nullptr, c->g_xyzl.p, nullptr);
 	CK(cudaMemcpyAsync(nn_out, c->nn.p, (size_t)n2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 	c->last_n_first = n1; c->last_n_second = n2; c->last_valid = true;
@@ -1431,7 +1480,8 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 		const int n_chunks = (int)(bt.total / kSegChunk);
 		const SweepSeg *segs = c->d_segs.p + bt.seg0;
 		LAUNCH(c, k_transform_segments, n_chunks, kSegChunk, segs, bt.nseg, c->d_seg_of_chunk.p, c->d_poses1.p, c->q_xyzl.p, c->q_nrm.p);
-		launch_nn(c, nullptr, (int)bt.total, c->vals[c->last_sorted].p, A.n, c->buckets.p, prm->search_radius, prm->max_inner, prm->max_outer, 1,
+		const float res3[3] = {prm->bucket_size, prm->bucket_size, prm->bucket_size};
+		launch_nn(c, nullptr, (int)bt.total, c->vals[c->last_sorted].p, A.n, c->buckets.p, res3, prm->search_radius, prm->max_inner, prm->max_outer, 1,
 				nullptr, c->obs_rec.p, A.xyzl, c->d_seg_counts.p, c->d_seg_of_chunk.p);
 		ObsFromRec src = {};
 		src.rec = c->obs_rec.p; src.q_xyzl = c->q_xyzl.p; src.m = pose_i;

@@ -117,6 +117,9 @@ extern "C" int emul_nn_search(const m3dreg_point *first, int n1, const m3dreg_po
 namespace {
 
 constexpr int kWCells = 128, kWStage = 192, kHullMin = 128, kHullRatio = 8;
+/* 1: cells of the previous round's hull are skipped (k_nn_search_grid, round 1); 0: every round looks at its whole hull
+ * (k_nn_search_hull) */
+int g_skip_old_hull = 0;
 
 struct WLane {
 	float qx, qy, qz, pnx, pny, pnz, best_d, lim, mgx, mgy, mgz;
@@ -153,6 +156,8 @@ inline void w_consider(const CandSet &cs, WLane &q, float d, const float4 &c, in
 }
 
 } /* namespace */
+
+extern "C" void emul_set_skip_old_hull(int on) { g_skip_old_hull = on ? 1 : 0; }
 
 extern "C" int emul_nn_search_warp(const m3dreg_point *first, int n1, const m3dreg_point *second, int n2,
 		const m3dreg_hash_element *table, const m3dreg_bucket *buckets, const m3dreg_grid_params *gp,
@@ -248,7 +253,7 @@ extern "C" int emul_nn_search_warp(const m3dreg_point *first, int n1, const m3dr
 						for (int c = 0; c < nr * dx; c++) {
 							const int rr = c / dx, ax = c - rr * dx, r = row0 + rr, az = r / dy, ay = r - az * dy;
 							const int gx = uxl + ax, gy = uyl + ay, gz = uzl + az;
-							if (gx >= hxl && gx <= hxh && gy >= hyl && gy <= hyh && gz >= hzl && gz <= hzh) continue;
+							if (g_skip_old_hull && gx >= hxl && gx <= hxh && gy >= hyl && gy <= hyh && gz >= hzl && gz <= hzh) continue;
 							const int cell = ((gx >> 2) * P.nby + (gy >> 2)) * P.nbz + (gz >> 2);
 							const int npts = buckets[cell].number_of_points, begin = buckets[cell].index_begin;
 							if (!(npts > 0 && begin >= 0)) continue;

@@ -74,10 +74,12 @@ def nn_emul_search(first, second, table, buckets, gp, radius, max_inner=100, max
     return nn, int(ev.value)
 
 
-def nn_emul_search_warp(first, second, table, buckets, gp, radius, cap=100, prune=True):
-    """Warp-level emulation of k_nn_search_grid (tests/csrc/nn_emul.cpp); returns (nn, fallback queries, re-scans)."""
+def nn_emul_search_warp(first, second, table, buckets, gp, radius, cap=100, prune=True, skip_old_hull=False):
+    """Warp-level emulation of the warp-shared search (tests/csrc/nn_emul.cpp): k_nn_search_hull, or round 1's
+    k_nn_search_grid with skip_old_hull; returns (nn, fallback queries, re-scans)."""
     import numpy as np
     lib = C.CDLL(build_nn_emul())
+    lib.emul_set_skip_old_hull(C.c_int(1 if skip_old_hull else 0))
     first = np.ascontiguousarray(first); second = np.ascontiguousarray(second)
     table = np.ascontiguousarray(table); buckets = np.ascontiguousarray(buckets); gp = np.ascontiguousarray(gp)
     nn = np.full(len(second), -7, dtype=np.int32)

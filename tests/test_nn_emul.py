@@ -41,7 +41,7 @@ def test_emulated_search_scan_pairs(synth, oracle):
 
 
 def test_warp_shared_algorithm_matches_oracle(synth, oracle):
-    """The ALGORITHM of k_nn_search_grid (hull of the lanes' boxes, representative cells, previous-hull skipping, staged
+    """The ALGORITHM of k_nn_search_hull / k_nn_search_grid (hull of the lanes' boxes, representative cells, with and without previous-hull skipping, staged
     groups with group minimum / tie flag / cold step / re-scan, hull-based settle test, scattered-warp fallback), restated
     for the host in tests/csrc/nn_emul.cpp, against the oracle: sorted and unsorted queries, pruning on and off, radius
     above and below the bucket size, aliasing labels, bins larger than a staging batch, exact ties."""
@@ -67,10 +67,10 @@ def test_warp_shared_algorithm_matches_oracle(synth, oracle):
         for order in ("sorted", "mixed_labels", "as_is"):
             sq = second if order == "as_is" else second[_spatial_order(second, by_label=(order == "sorted"))].copy()
             nn_o, gp, table, buckets = oracle.semantic_nn(first, sq, radius, bucket, 1.0, cap, cap)
-            for prune in (True, False):
-                nn_w, fb, rs = native.nn_emul_search_warp(first, sq, table, buckets, gp, radius, cap, prune)
-                assert np.array_equal(nn_w, nn_o), (name, order, prune, int((nn_w != nn_o).sum()))
-                if prune:
+            for prune, skip_old in ((True, False), (False, False), (True, True)):      # k_nn_search_hull; round 1's hull skipping
+                nn_w, fb, rs = native.nn_emul_search_warp(first, sq, table, buckets, gp, radius, cap, prune, skip_old_hull=skip_old)
+                assert np.array_equal(nn_w, nn_o), (name, order, prune, skip_old, int((nn_w != nn_o).sum()))
+                if prune and not skip_old:
                     shared_total += len(sq) - fb
                     rescans_total += rs
     assert shared_total > 20000           # the warp-shared path (not the fallback) answered a good part of the queries
