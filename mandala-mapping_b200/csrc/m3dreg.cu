@@ -130,6 +130,8 @@ struct m3dreg_ctx {
 	unsigned int *ticket = nullptr;
 	unsigned int *cell_count = nullptr;           /* number of searchable buckets in the compact list */
 	unsigned int *grid_bar = nullptr;             /* grid barrier of k_grid_build: arrival count, generation */
+	unsigned int *nn_work = nullptr;              /* k_nn_search_hull's work counters (next chunk, idle warps): zero between launches */
+	int nn_blocks_per_sm[2] = {0, 0};             /* resident blocks per SM of k_nn_search_hull<false|true> (occupancy API, once) */
 	unsigned long long *eval_counter = nullptr;   /* candidates staged by the NN search (warp-level), diagnostic */
 	int use_pdl = 1;             /* programmatic dependent launch for every kernel (env M3DREG_NO_PDL=1 disables) */
 	int nn_per_thread = 0;       /* test switch (env M3DREG_NN_PER_THREAD=1): k_nn_search instead of k_nn_search_grid */
@@ -455,7 +457,19 @@ void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *va
 		a.cap = max_outer; a.prune = prune; a.tune = c->nn_tune;
 		a.nn_out = nn_out; a.obs_rec = obs_rec; a.src_xyzl = src_xyzl; a.label_counts = label_counts;
 		a.eval_counter = c->profiling ? c->eval_counter : nullptr; a.seg_of_chunk = seg_of_chunk;
-		const int blocks = (n2 + kNNHThreads - 1) / kNNHThreads;
+		a.work = c->nn_work;
+		/* persistent warps: one wave of resident blocks, chunks of 32 queries handed out by an atomic counter */
+		const int pi = c->profiling ? 1 : 0;
+		if (c->nn_blocks_per_sm[pi] <= 0) {
+			int nb = 0;
+			cudaError_t oe = pi ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_nn_search_hull<true>, kNNHThreads, 0)
+					: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_nn_search_hull<false>, kNNHThreads, 0);
+			c->nn_blocks_per_sm[pi] = (oe == cudaSuccess && nb > 0) ? nb : 8;
+		}
+		const int chunks = (n2 + 31) / 32;
+		int blocks = c->sm_count * c->nn_blocks_per_sm[pi];
+		if (blocks > (chunks + kNNHWarps - 1) / kNNHWarps) blocks = (chunks + kNNHWarps - 1) / kNNHWarps;
+		if (blocks < 1) blocks = 1;
 		if (c->profiling) LAUNCH(c, k_nn_search_hull<true>, blocks, kNNHThreads, a);
 		else LAUNCH(c, k_nn_search_hull<false>, blocks, kNNHThreads, a);
 		return;
@@ -720,6 +734,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	c->cell_count = (unsigned int *)take(16);
 	c->grid_bar = (unsigned int *)take(16);
 	c->gb_dbg = (unsigned long long *)take(16 * sizeof(unsigned long long));
+	c->nn_work = (unsigned int *)take(16);
 	c->eval_counter = (unsigned long long *)take(16);
 	c->mats = (float *)take(32 * sizeof(float));
 	e = cudaMallocHost((void **)&c->h, sizeof(HostSmall));

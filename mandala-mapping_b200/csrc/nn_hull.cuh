@@ -16,9 +16,11 @@
  *   - 64 registers instead of 80 -> 16 instead of 12 blocks per SM: the per-lane margins, neighbourhood clamps and the
  *     query normal are recomputed / re-read where they are used instead of living in registers; nothing spills;
  *   - everything that depends only on the launch (4 / res, r^2, first radius) comes in as kernel arguments;
- *   - cells of the previous round's hull are no longer skipped (1.1 rounds per warp: the bookkeeping cost more than the
- *     re-evaluation it saved, and the representative-cell rule becomes the obvious one: a coarser bin is listed from the
- *     first fine cell of the hull that it covers);
+ *   - PERSISTENT warps: the grid is one wave (blocks per SM x SM count), every warp fetches chunks of 32 queries from an
+ *     atomic counter until none is left.  16 384 two-warp blocks kept a third of the warp slots empty while the next
+ *     block was being launched; the launch-constant prologue now runs once per warp instead of once per 32 queries;
+ *   - the previous round's hull (whose cells are skipped, exactness argument in m3dreg_kernels.cuh) is kept packed in
+ *     four registers;
  *   - the cold step issues its (up to four) normal loads and the query normal together, one L2 latency instead of four
  *     dependent ones;
  *   - the winner's record comes from the candidate set's `loc` stream (point in the local frame + original index): one
@@ -61,6 +63,7 @@ struct NNHullArgs {
 	unsigned long long *label_counts;
 	unsigned long long *eval_counter;
 	const int *seg_of_chunk;
+	unsigned int *work;         /* [0] next chunk of 32 queries, [1] warps that ran out of work: both zero between launches */
 };
 
 /* the lane's conservative box of fine columns for dist <= tau (nn_query()'s box), clamped to its 27-neighbourhood */
@@ -94,7 +97,7 @@ __device__ __forceinline__ bool nnh_in_neighbourhood(int gx, int gy, int gz, int
 			gz >= ((iz > 0 ? iz - 1 : iz) << 2) && gz <= ((iz != nbz - 1 ? iz + 1 : iz) << 2) + 3;
 }
 
-__device__ __noinline__ int nnh_query_fallback(const NNHullArgs *a, float qx, float qy, float qz, int label, int qi)
+__device__ __noinline__ int2 nnh_query_fallback(const NNHullArgs *a, float qx, float qy, float qz, int label, int qi)
 {
 	const m3dreg_grid_params *gp = a->gp;
 	NNParams P;
@@ -110,8 +113,7 @@ __device__ __noinline__ int nnh_query_fallback(const NNHullArgs *a, float qx, fl
 	unsigned int ev = 0;
 	const float4 pn = __ldg(a->q_nrm + qi);
 	const int l = nn_query(P, make_float4(qx, qy, qz, __int_as_float(label)), pn, ev);
-	if (a->eval_counter && ev) atomicAdd(a->eval_counter, (unsigned long long)ev);
-	return l;
+	return make_int2(l, (int)ev);
 }
 
 /* full predicate of the reference on one candidate (lesson_16.cu:658-686) with the (dist, l) order made explicit;
@@ -139,7 +141,6 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 	float4 *stage = s_cand[threadIdx.x >> 5];
 	float *stagef = reinterpret_cast<float *>(stage);
 	int4 *grp = s_grp[threadIdx.x >> 5];
-	const int qi = blockIdx.x * kNNHThreads + threadIdx.x;
 	const m3dreg_grid_params *__restrict__ gp = a.gp;
 	const float mnx = gp->bounding_box_min_X, mny = gp->bounding_box_min_Y, mnz = gp->bounding_box_min_Z;
 	const int nbx = gp->number_of_buckets_X, nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
@@ -147,6 +148,14 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 	const int tables = (nn_tables_usable(a.cap, a.cap) && nn_columns_usable(nbx, nby, nbz)) ? 1 : 0;
 	const float4 *__restrict__ cx = a.cs.xyzl;
 	const float4 *__restrict__ cn = a.cs.nrm;
+	const int n_chunks = (a.n_second + 31) >> 5;
+
+	for (;;) {      /* persistent warp: one chunk of 32 queries per trip */
+	int chunk = 0;
+	if (lane == 0) chunk = (int)atomicAdd(a.work, 1u);
+	chunk = __shfl_sync(full, chunk, 0);
+	if (chunk >= n_chunks) break;
+	const int qi = (chunk << 5) + lane;
 
 	unsigned int evals = 0;
 	int best_l = kNNNone, best_j = -1, label = -1;                     /* best_j: the winner's slot in the candidate set (-1: found by nn_query()) */
@@ -167,7 +176,7 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 		}
 	}
 	if (!nn_columns_usable(nbx, nby, nbz)) {                            /* warp-uniform */
-		if (active) best_l = nnh_query_fallback(&a, qx, qy, qz, label, qi);
+		if (active) { const int2 fr = nnh_query_fallback(&a, qx, qy, qz, label, qi); best_l = fr.x; evals += (unsigned int)fr.y; }
 		active = false;
 	}
 
@@ -178,6 +187,10 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 		bool unsettled = mine;
 		todo &= ~__ballot_sync(full, mine);
 		float rho2 = a.rho2_first;
+		/* previous round's hull, packed: low corner + extents (x 8 bits, y and z 12 bits; a larger hull is simply not
+		 * remembered — skipping its cells is an optimisation, never needed for the answer) */
+		int hxl = 0, hyl = 0, hzl = 0;
+		unsigned hext = 0;                                              /* (dx) | (dy << 8) | (dz << 20), 0 = none */
 		for (int round = 0; round < 80; round++) {
 			if (!__any_sync(full, unsettled)) break;
 			NNBox b;
@@ -201,7 +214,7 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 							const unsigned fb = __ballot_sync(full, unsettled);
 							if (lane == 0) atomicAdd(a.eval_counter + 1, (unsigned long long)__popc(fb));
 						}
-						if (unsettled) { best_l = nnh_query_fallback(&a, qx, qy, qz, label, qi); best_j = -1; }
+						if (unsettled) { const int2 fr = nnh_query_fallback(&a, qx, qy, qz, label, qi); best_l = fr.x; best_j = -1; evals += (unsigned int)fr.y; }
 						unsettled = false;
 						break;
 					}
@@ -226,14 +239,20 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 							const int az = __float2int_rz(((float)r + 0.5f) * inv_dy);
 							const int ay = r - az * dy;
 							const int gx = uxl + ax, gy = uyl + ay, gz = uzl + az;
+							/* cells of the previous round's hull were evaluated by every lane then (unsigned compares: below the
+							 * low corner wraps to a huge value) */
+							const bool in_old = (unsigned)(gx - hxl) < (hext & 0xffu) && (unsigned)(gy - hyl) < ((hext >> 8) & 0xfffu) &&
+									(unsigned)(gz - hzl) < (hext >> 20);
 							const int cell = ((gx >> 2) * nby + (gy >> 2)) * nbz + (gz >> 2);
 							const int *rec = reinterpret_cast<const int *>(a.buckets + cell);
-							const int npts = __ldg(rec + 2), begin = __ldg(rec);
+							int npts = 0, begin = -1;
+							if (!in_old) { npts = __ldg(rec + 2); begin = __ldg(rec); }
 							if (npts > 0 && begin >= 0) {           /* lesson_16.cu:615-616 (also the quirk bucket) */
 								const int level = tables ? nn_level(npts) : -1;
 								const int sh = level < 0 ? 2 : 2 - level;
 								const int am = (1 << sh) - 1;
-								/* a bin of a coarser bucket covers 2^sh fine cells per axis: listed from the first one the hull holds */
+								/* a bin of a coarser bucket covers 2^sh fine cells per axis: listed from the first one the hull holds (a
+								 * skipped representative means the bin touched the previous hull, where it was listed whole) */
 								const bool rep = (ax == 0 || !(gx & am)) && (ay == 0 || !(gy & am)) && (az == 0 || !(gz & am));
 								if (rep) {
 									if (level < 0) {                /* no table: the whole bucket, in walk order */
@@ -339,8 +358,8 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 						/* full predicate on the winning group: its four {normal, label} records and the query's normal go out
 						 * together; a tie between groups or an inadmissible winner needs the re-scan */
 						float4 pn = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-						const bool any_cold = __any_sync(full, bg >= 0);
-						if (any_cold && mine) pn = __ldg(a.q_nrm + qi);
+						const bool need_pn = __any_sync(full, bg >= 0 || flag);      /* the re-scan below needs it too */
+						if (need_pn && mine) pn = __ldg(a.q_nrm + qi);
 						if (bg >= 0) {
 							const int4 gi = grp[bg];
 							const int j = gi.x;
@@ -376,8 +395,10 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 						__syncwarp();
 					}
 				}
-				/* every cell of this hull has now been evaluated by all lanes: a lane whose box for its CURRENT limit lies
-				 * inside the hull is done */
+				hxl = uxl; hyl = uyl; hzl = uzl;
+				hext = (dx <= 255 && dy <= 4095 && dz <= 4095) ? ((unsigned)dx | ((unsigned)dy << 8) | ((unsigned)dz << 20)) : 0u;
+				/* every cell of this hull has now been evaluated by all lanes (in this round or, for the cells skipped as part
+				 * of the previous hull, before): a lane whose box for its CURRENT limit lies inside the hull is done */
 				if (unsettled && a.prune && lim > rho2) {
 					const NNBox e = nnh_box(lim, a.prune, qx, qy, qz, mnx, mny, mnz, a.iwx, a.iwy, a.iwz, ix, iy, iz, nbx, nby, nbz);
 					if (e.xl >= uxl && e.xh <= uxh && e.yl >= uyl && e.yh <= uyh && e.zl >= uzl && e.zh <= uzh) unsettled = false;
@@ -411,13 +432,19 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 	}
 	if (a.label_counts) {   /* per-label match counts (gpu6DSLAM.cpp:323-357): warp ballots, one atomic per label per warp */
 		unsigned long long *lc = a.label_counts;
-		if (a.seg_of_chunk) lc += 4 * __ldg(a.seg_of_chunk + (blockIdx.x * kNNHThreads) / kSegChunk);      /* a block never straddles segments */
+		if (a.seg_of_chunk) lc += 4 * __ldg(a.seg_of_chunk + (chunk << 5) / kSegChunk);      /* 32 queries never straddle segments */
 		const bool hit = qi < a.n_second && result >= 0;
 #pragma unroll
 		for (int Lb = 0; Lb < 4; Lb++) {
 			const unsigned m = __ballot_sync(full, hit && label == Lb);
 			if (m && lane == Lb) atomicAdd(&lc[Lb], (unsigned long long)__popc(m));
 		}
+	}
+	}      /* persistent loop */
+	/* the last warp to run out of work re-arms the counters for the next launch */
+	if (lane == 0) {
+		const unsigned int total_warps = gridDim.x * kNNHWarps;
+		if (atomicAdd(a.work + 1, 1u) == total_warps - 1) { a.work[0] = 0u; a.work[1] = 0u; __threadfence(); }
 	}
 }
 #undef M3D_NNH_CONSIDER
