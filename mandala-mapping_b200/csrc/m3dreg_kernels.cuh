@@ -1546,7 +1546,7 @@ __device__ __host__ inline void euler_to_matrix(const float *omfika, const float
 #undef M3D_SUB
 }
 
-__device__ inline void pose_prepare_warp(PoseState *ps, int lane);
+__device__ __forceinline__ void pose_prepare_warp(PoseState *ps, int lane, const float *m_regs);
 
 /* Start of an iteration of registerLastArrivedScan (gpu6DSLAM.cpp:276-291): Euler round trip of the stored pose. */
 __device__ inline void pose_prepare(PoseState *ps)
@@ -1561,7 +1561,7 @@ __device__ inline void pose_prepare(PoseState *ps)
 __global__ void k_pose_prepare(PoseState *ps)
 {
 	pdl_enter();
-	if (blockIdx.x == 0 && threadIdx.x < 32) pose_prepare_warp(ps, threadIdx.x);
+	if (blockIdx.x == 0 && threadIdx.x < 32) pose_prepare_warp(ps, threadIdx.x, nullptr);
 }
 
 /* ---- warp-cooperative versions of the serial tail ------------------------------------------------------------
@@ -1574,7 +1574,8 @@ __device__ __forceinline__ double shfl_f64(double v, int src)
 	return __shfl_sync(0xffffffffu, v, src);
 }
 
-__device__ inline void euler_to_matrix_warp(const float *omfika, const float *xyz, float *m, int lane)
+/* every lane ends up with the 3x4 part of the matrix in r[12] (row-major [R|t]); lane 0 also stores the 4x4 to m (if any) */
+__device__ __forceinline__ void euler_to_matrix_warp(const float *omfika, const float *xyz, float *m, int lane, float *r = nullptr)
 {
 	/* lanes 0..2: sin/cos of the three half angles */
 	float h = 0.5f * omfika[lane < 3 ? lane : 0];
@@ -1591,17 +1592,24 @@ __device__ inline void euler_to_matrix_warp(const float *omfika, const float *xy
 	float twx = __fmul_rn(tx, w), twy = __fmul_rn(ty, w), twz = __fmul_rn(tz, w);
 	float txx = __fmul_rn(tx, x), txy = __fmul_rn(ty, x), txz = __fmul_rn(tz, x);
 	float tyy = __fmul_rn(ty, y), tyz = __fmul_rn(tz, y), tzz = __fmul_rn(tz, z);
-	if (lane == 0) {
-		m[0] = __fsub_rn(1.0f, __fadd_rn(tyy, tzz)); m[1] = __fsub_rn(txy, twz); m[2] = __fadd_rn(txz, twy); m[3] = xyz[0];
-		m[4] = __fadd_rn(txy, twz); m[5] = __fsub_rn(1.0f, __fadd_rn(txx, tzz)); m[6] = __fsub_rn(tyz, twx); m[7] = xyz[1];
-		m[8] = __fsub_rn(txz, twy); m[9] = __fadd_rn(tyz, twx); m[10] = __fsub_rn(1.0f, __fadd_rn(txx, tyy)); m[11] = xyz[2];
+	float q[12];
+	q[0] = __fsub_rn(1.0f, __fadd_rn(tyy, tzz)); q[1] = __fsub_rn(txy, twz); q[2] = __fadd_rn(txz, twy); q[3] = xyz[0];
+	q[4] = __fadd_rn(txy, twz); q[5] = __fsub_rn(1.0f, __fadd_rn(txx, tzz)); q[6] = __fsub_rn(tyz, twx); q[7] = xyz[1];
+	q[8] = __fsub_rn(txz, twy); q[9] = __fadd_rn(tyz, twx); q[10] = __fsub_rn(1.0f, __fadd_rn(txx, tyy)); q[11] = xyz[2];
+	if (r) {
+#pragma unroll
+		for (int k = 0; k < 12; k++) r[k] = q[k];
+	}
+	if (m && lane == 0) {
+#pragma unroll
+		for (int k = 0; k < 12; k++) m[k] = q[k];
 		m[12] = 0.0f; m[13] = 0.0f; m[14] = 0.0f; m[15] = 1.0f;
 	}
 	__syncwarp();
 }
 
 /* m: 16 floats readable by every lane (shared or global, already visible); results returned in every lane. */
-__device__ inline void matrix4_to_euler_warp(const float *m, float *omfika, float *xyz, int lane)
+__device__ __forceinline__ void matrix4_to_euler_warp(const float *m, float *omfika, float *xyz, int lane)
 {
 	const double kPi = 3.14159265358979323846;
 	float fi;
@@ -1623,11 +1631,13 @@ __device__ inline void matrix4_to_euler_warp(const float *m, float *omfika, floa
 	xyz[0] = m[3]; xyz[1] = m[7]; xyz[2] = m[11];
 }
 
-/* Start of an iteration (gpu6DSLAM.cpp:276-291) by one warp: Euler round trip of ps->m into pose1 / pose6. */
-__device__ inline void pose_prepare_warp(PoseState *ps, int lane)
+/* Start of an iteration (gpu6DSLAM.cpp:276-291) by one warp: Euler round trip of the stored pose into pose1 / pose6.
+ * m_regs (12 floats, every lane): the 3x4 part of ps->m when the caller still holds it in registers (0: read ps->m). */
+__device__ __forceinline__ void pose_prepare_warp(PoseState *ps, int lane, const float *m_regs = nullptr)
 {
 	float of[3], t[3];
-	matrix4_to_euler_warp(ps->m, of, t, lane);
+	if (m_regs) matrix4_to_euler_warp(m_regs, of, t, lane);      /* two inlined copies: a register array must not meet a pointer select */
+	else matrix4_to_euler_warp(ps->m, of, t, lane);
 	euler_to_matrix_warp(of, t, ps->pose1, lane);
 	if (lane == 0) {
 		ps->pose6[0] = t[0]; ps->pose6[1] = t[1]; ps->pose6[2] = t[2];
@@ -1764,7 +1774,7 @@ struct FinalizeArgs {
 /* What warp 0 of the last block does with the finished 28-double system `neq` (shared memory): publish / accumulate
  * it, and (fused loop) gate on the observation count, Cholesky, pose update, Euler round trip for the next iteration,
  * resets. */
-__device__ inline void neq_tail_warp(const double *neq, const FinalizeArgs &fin, int lane)
+__device__ inline void neq_tail_warp(const double *neq, const FinalizeArgs &fin, int lane, const double *p6_in = nullptr)
 {
 	if (fin.neq_out && lane < kNeqCount) fin.neq_out[lane] = fin.accumulate ? fin.neq_out[lane] + neq[lane] : neq[lane];
 	if (fin.solve && fin.ps) {
@@ -1776,8 +1786,10 @@ __device__ inline void neq_tail_warp(const double *neq, const FinalizeArgs &fin,
 		if (n_obs > (long long)fin.obs_threshold) status = solve_packed(neq, fin.dof, x);     /* gpu6DSLAM.cpp:402; uniform over lanes */
 		double p6[6];
 #pragma unroll
-		for (int k = 0; k < 6; k++) p6[k] = ps->pose6[k];
+		for (int k = 0; k < 6; k++) p6[k] = p6_in ? p6_in[k] : ps->pose6[k];
 		__syncwarp();
+		float mr[12];
+		bool have_m = false;
 		if (status == 0) {
 			/* registerLS tail (cudaWrapper.cpp:574-579 / 641-646) + EulerToMatrix (gpu6DSLAM.cpp:408-413) */
 			p6[0] += x[0]; p6[1] += x[1]; p6[2] += x[2];
@@ -1785,7 +1797,8 @@ __device__ inline void neq_tail_warp(const double *neq, const FinalizeArgs &fin,
 			else p6[5] += x[3];
 			float of[3] = {(float)p6[3], (float)p6[4], (float)p6[5]};
 			float t[3] = {(float)p6[0], (float)p6[1], (float)p6[2]};
-			euler_to_matrix_warp(of, t, ps->m, lane);
+			euler_to_matrix_warp(of, t, ps->m, lane, mr);
+			have_m = true;
 		}
 		if (lane == 0) {
 			for (int k = 0; k < 6; k++) ps->x[k] = x[k];
@@ -1794,7 +1807,7 @@ __device__ inline void neq_tail_warp(const double *neq, const FinalizeArgs &fin,
 			ps->iterations += 1;
 		}
 		__syncwarp();
-		pose_prepare_warp(ps, lane);   /* next iteration's Euler round trip */
+		pose_prepare_warp(ps, lane, have_m ? mr : nullptr);   /* next iteration's Euler round trip (the new pose is still in registers) */
 	}
 	if (lane == 0) {
 		if (fin.bounds_reset) {
@@ -1822,6 +1835,7 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(const Src src_
 	__shared__ float wl[4 * kMaxSegs];
 	__shared__ bool is_last;
 	if constexpr (std::is_same<Src, ObsFromRec>::value) {
+		static_assert(kNeqThreads / 32 * 3 == kMomentCount, "final reduction: three columns per warp");
 		static_assert(4 * kMaxSegs <= kNeqThreads, "one thread per (segment, label) weight");
 		if ((int)threadIdx.x < 4 * src.n_segs) {
 			unsigned long long c = src.label_counts[threadIdx.x];
@@ -1878,48 +1892,44 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(const Src src_
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq0));
 #endif
 	__threadfence();
-	/* deterministic final reduction: fixed row order */
+	/* the Euler angles the system is formed for: requested now, needed after the reduction */
+	const double *p6g = fin.ps ? fin.ps->pose6 : fin.pose6_in;
+	double p6r[6];
+#pragma unroll
+	for (int k = 0; k < 6; k++) p6r[k] = wid == 0 ? __ldcg(p6g + k) : 0.0;
+	/* deterministic final reduction, fixed order: warp w owns columns 3w .. 3w+2, lane l adds rows l, l + 32, ... (ten
+	 * rows x three columns of loads in flight per lane: one L2 latency per 320 rows), then a butterfly over the lanes */
 	__shared__ double tot[kMomentCount];
 	{
-		/* thread (g, col), g = 0..kGroups-1: rows g, g + kGroups, ... — every load independent and in flight at once,
-		 * then the groups are added in fixed order */
-		constexpr int kGroups = kNeqThreads / kMomentCount;
-		__shared__ double part[kGroups][kMomentCount];
-		const int g = threadIdx.x / kMomentCount, col = threadIdx.x % kMomentCount;
-		if (g < kGroups) {
-			double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-			unsigned int b = g;
-			for (; b + 3 * kGroups < gridDim.x; b += 4 * kGroups) {
-				const double a0 = __ldcg(partials + (size_t)b * kPartialCols + col);
-				const double a1 = __ldcg(partials + (size_t)(b + kGroups) * kPartialCols + col);
-				const double a2 = __ldcg(partials + (size_t)(b + 2 * kGroups) * kPartialCols + col);
-				const double a3 = __ldcg(partials + (size_t)(b + 3 * kGroups) * kPartialCols + col);
-				s0 += a0; s1 += a1; s2 += a2; s3 += a3;
-			}
-			for (; b < gridDim.x; b += kGroups) s0 += __ldcg(partials + (size_t)b * kPartialCols + col);
-			part[g][col] = (s0 + s1) + (s2 + s3);
-		}
-		__syncthreads();
-		if (threadIdx.x < kMomentCount) {
-			double s = 0;
+		double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+		const int c0 = 3 * wid;
+		for (unsigned int base = 0; base < gridDim.x; base += 320) {
+			double v[10][3];
 #pragma unroll
-			for (int k = 0; k < kGroups; k++) s += part[k][threadIdx.x];
-			tot[threadIdx.x] = s;
+			for (int k = 0; k < 10; k++) {
+				const unsigned int b = base + 32 * k + lane;
+				const bool in = b < gridDim.x;
+				const double *row = partials + (size_t)(in ? b : 0) * kPartialCols + c0;
+				v[k][0] = in ? __ldcg(row) : 0.0; v[k][1] = in ? __ldcg(row + 1) : 0.0; v[k][2] = in ? __ldcg(row + 2) : 0.0;
+			}
+#pragma unroll
+			for (int k = 0; k < 10; k++) { s0 += v[k][0]; s1 += v[k][1]; s2 += v[k][2]; }
 		}
+		s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+		if (lane == 0) { tot[c0] = s0; tot[c0 + 1] = s1; tot[c0 + 2] = s2; }
 	}
 	__syncthreads();
 	if (wid == 0) {
 		__shared__ double neq[kNeqCount];
 		if (lane == 0) *ticket = 0;
-		const double *p6 = fin.ps ? fin.ps->pose6 : fin.pose6_in;
 #ifdef M3D_NEQ_TIMING
 		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq1));
 #endif
-		moments_to_neq_warp(tot, p6[3], p6[4], p6[5], neq, lane);
+		moments_to_neq_warp(tot, p6r[3], p6r[4], p6r[5], neq, lane);
 #ifdef M3D_NEQ_TIMING
 		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq2));
 #endif
-		neq_tail_warp(neq, fin, lane);
+		neq_tail_warp(neq, fin, lane, p6r);
 #ifdef M3D_NEQ_TIMING
 		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq3));
 		if (lane == 0) printf("neq tail ns: reduce %llu moments_to_neq %llu tail %llu\n", tq1 - tq0, tq2 - tq1, tq3 - tq2);
