@@ -40,6 +40,8 @@ extern "C" {
 #define M3DREG_E_BAD_SLOT        (-5)   /* scan slot not uploaded / out of range                     */
 #define M3DREG_E_NO_DEVICE       (-6)   /* no CUDA device / wrong architecture (needs sm_100)        */
 #define M3DREG_E_SIZE_MISMATCH   (-7)   /* ref: cudaWrapper.cpp:354 silently returns; we report it    */
+#define M3DREG_E_NO_NCCL         (-8)   /* multi-GPU sweep without NCCL in the process / without a communicator */
+#define M3DREG_E_NCCL            (-9)   /* an NCCL call returned an error                            */
 
 /* ---- labels (ref: include/lesson_16.h:9-12) --------------------------------------------- */
 #define M3DREG_LABEL_PLANE   0
@@ -294,6 +296,50 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *ctx, int n_pairs, const int *pair_i, con
 		const float *poses, int n_scans, const m3dreg_reg_params *params, double *d_neq);
 int m3dreg_sweep_solve(m3dreg_ctx *ctx, const double *d_neq, int n_scans, int scan_begin, int scan_end,
 		float *poses, const m3dreg_reg_params *params, int *status_out);
+
+/* ---- the whole sweep as ONE call, sharded over the GPUs of a box ---------------------------------------------
+ * ref: gpu6DSLAM::registerAll(cudaWrapper, radius, bucket, number_of_last_EOZ) (src/gpu6DSLAM.cpp:424-597) and the
+ * service loop that calls it (src/main.cpp:36-60).  One context per GPU / per rank, every scan uploaded to every
+ * context (m3dreg_scan_upload, slots 0..n_scans-1).  Every rank calls m3dreg_slam_sweep with the SAME poses:
+ *   1. pair gate: (i, j), i in [first_optimised, n_scans), j != i, |t_i - t_j| < distance_threshold
+ *      (slam_registerAll_distance_threshold, include/gpu6DSLAM.h:180; src/gpu6DSLAM.cpp:464-469);
+ *   2. deterministic partition of the pairs over the ranks (whole groups of equal i, heavy groups split);
+ *   3. m3dreg_sweep_accumulate of the rank's pairs into n_scans x 28 doubles on the device;
+ *   4. ONE ncclAllReduce (sum, double) of that block over NVLink / NVSwitch, on the context's stream;
+ *   5. gate on obs_threshold, Cholesky, pose update, Euler round trip of scans [first_optimised, n_scans) on every rank
+ *      (src/gpu6DSLAM.cpp:572-593); poses (n_scans row-major 4x4 float, HOST) are updated in place, identically on
+ *      every rank; earlier scans keep their pose untouched (src/gpu6DSLAM.cpp:430).
+ * NCCL is looked up at run time (the process' own copy first, then libnccl.so.2): no link-time dependency. */
+typedef struct m3dreg_slam_params {
+	m3dreg_reg_params reg;          /* radius / bucket of this sweep, caps, weights, dof, mode (ICP or NDT)              */
+	float   distance_threshold;     /* slam_registerAll_distance_threshold (10 m)                                        */
+	int32_t first_optimised;        /* n_scans - number_of_last_EOZ: scans before it are only neighbours (0 = all)       */
+} m3dreg_slam_params;
+
+typedef struct m3dreg_sweep_stats {
+	int64_t n_pairs, n_pairs_mine;  /* gated pairs in the sweep / handled by this rank                                    */
+	int64_t points_all, points_mine;/* sum over those pairs of (points of i + points of j)                                */
+	float   accumulate_ms;          /* CUDA-event time of this rank's accumulation                                       */
+	float   allreduce_ms;           /* CUDA-event time from the end of the accumulation to the end of the all-reduce
+	                                   (includes waiting for the slowest rank)                                           */
+	int32_t rank, world;
+} m3dreg_sweep_stats;
+
+/* Communicator of this context's rank: either created here from a 128-byte ncclUniqueId that rank 0 obtained with
+ * m3dreg_nccl_get_unique_id and handed to the other ranks (any transport: MPI, a file, torch.distributed, ...), or an
+ * existing ncclComm_t of the host application (attach: not destroyed with the context).  world == 1 detaches. */
+int m3dreg_nccl_get_unique_id(void *id128);
+int m3dreg_nccl_init(m3dreg_ctx *ctx, const void *id128, int rank, int world);
+int m3dreg_nccl_attach(m3dreg_ctx *ctx, void *nccl_comm, int rank, int world);
+
+int m3dreg_slam_sweep(m3dreg_ctx *ctx, int n_scans, float *poses, const m3dreg_slam_params *params,
+		int *status_out /* n_scans, HOST, may be NULL */, m3dreg_sweep_stats *stats /* may be NULL */);
+/* The (all-reduced) normal-equation blocks of the last m3dreg_slam_sweep, n_scans x 28 doubles to HOST memory (checks). */
+int m3dreg_slam_copy_neq(m3dreg_ctx *ctx, double *neq_out, int n_scans);
+/* The plan alone, without a device (pure host function; the library loads without a GPU): pairs in sweep order and the
+ * rank that owns each.  Returns the number of pairs (or < 0); arrays may be NULL to only count.  sizes: points per scan. */
+int m3dreg_slam_plan(const float *poses, int n_scans, const int *sizes, float distance_threshold, int first_optimised,
+		int world, int *pair_i, int *pair_j, int *owner, int cap);
 
 #ifdef __cplusplus
 } /* extern "C" */

@@ -28,10 +28,11 @@ CSRC = os.path.join(_HERE, "csrc")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared"]
 
 # status codes (include/m3dreg.h)
 OK, E_INVALID_ARG, E_TOO_MANY_BUCKETS, E_NOT_SPD, E_TOO_FEW_OBS, E_BAD_SLOT, E_NO_DEVICE, E_SIZE_MISMATCH = 0, -1, -2, -3, -4, -5, -6, -7
+E_NO_NCCL, E_NCCL = -8, -9
 MODE_ICP, MODE_NDT = 0, 1
 
 #: every symbol include/m3dreg.h declares (checked by tests/test_cabi.py against the built library)
@@ -45,7 +46,8 @@ EXPORTS = [
     "m3dreg_export_last_grid", "m3dreg_export_last_nn", "m3dreg_sweep_zero", "m3dreg_sweep_accumulate",
     "m3dreg_sweep_solve", "m3dreg_icp_begin", "m3dreg_icp_step", "m3dreg_icp_end", "m3dreg_icp_copy_neq", "m3dreg_icp_set_neq_out",
     "m3dreg_set_profiling", "m3dreg_get_stage_ms", "m3dreg_set_pruning", "m3dreg_get_nn_evaluations", "m3dreg_get_nn_fallbacks",
-    "m3dreg_get_grid_phase_ns",
+    "m3dreg_get_grid_phase_ns", "m3dreg_slam_sweep", "m3dreg_slam_copy_neq", "m3dreg_slam_plan", "m3dreg_nccl_get_unique_id",
+    "m3dreg_nccl_init", "m3dreg_nccl_attach",
 ]
 
 
@@ -59,6 +61,40 @@ class RegParams(C.Structure):
 class IcpStats(C.Structure):
     _fields_ = [("iterations_run", C.c_int32), ("last_status", C.c_int32), ("n_obs_last", C.c_int64),
                 ("n_buckets_last", C.c_int64), ("x_last", C.c_double * 6), ("device_ms", C.c_float)]
+
+
+class SlamParams(C.Structure):
+    """m3dreg_slam_params (include/m3dreg.h)."""
+    _fields_ = [("reg", RegParams), ("distance_threshold", C.c_float), ("first_optimised", C.c_int32)]
+
+
+class SweepStats(C.Structure):
+    _fields_ = [("n_pairs", C.c_int64), ("n_pairs_mine", C.c_int64), ("points_all", C.c_int64), ("points_mine", C.c_int64),
+                ("accumulate_ms", C.c_float), ("allreduce_ms", C.c_float), ("rank", C.c_int32), ("world", C.c_int32)]
+
+
+def slam_plan(poses, sizes, distance_threshold: float = 10.0, first_optimised: int = 0, world: int = 1):
+    """Pairs of a sweep and the rank owning each (m3dreg_slam_plan: pure host code, no GPU needed)."""
+    poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, 16)
+    sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+    n = len(poses)
+    cnt = lib().m3dreg_slam_plan(_p(poses), C.c_int(n), _p(sizes), C.c_float(distance_threshold), C.c_int(first_optimised), C.c_int(world),
+                                 None, None, None, C.c_int(0))
+    if cnt < 0:
+        raise M3dRegError(cnt, "m3dreg_slam_plan")
+    pi, pj, ow = (np.zeros(max(cnt, 1), dtype=np.int32) for _ in range(3))
+    rc = lib().m3dreg_slam_plan(_p(poses), C.c_int(n), _p(sizes), C.c_float(distance_threshold), C.c_int(first_optimised), C.c_int(world),
+                                _p(pi), _p(pj), _p(ow), C.c_int(len(pi)))
+    if rc < 0:
+        raise M3dRegError(rc, "m3dreg_slam_plan")
+    return pi[:cnt], pj[:cnt], ow[:cnt]
+
+
+def nccl_unique_id() -> np.ndarray:
+    """128-byte ncclUniqueId (rank 0 creates it, every rank passes it to Context.nccl_init)."""
+    out = np.zeros(128, dtype=np.uint8)
+    _check(lib().m3dreg_nccl_get_unique_id(_p(out)), "m3dreg_nccl_get_unique_id")
+    return out
 
 
 def default_params(radius: float = 0.5, bucket: float | None = None, dof: int = 6, mode: int = MODE_ICP) -> RegParams:
@@ -342,6 +378,36 @@ class Context:
         ps = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, 16)
         _check(lib().m3dreg_sweep_accumulate(self._h, C.c_int(len(pi)), _p(pi), _p(pj), _p(ps), C.c_int(len(ps)),
                                              C.byref(params), _p(d_neq)), "m3dreg_sweep_accumulate")
+
+    def nccl_init(self, unique_id, rank: int, world: int):
+        """Create this rank's NCCL communicator from a 128-byte id (m3dreg_nccl_init)."""
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        assert uid.size == 128
+        _check(lib().m3dreg_nccl_init(self._h, _p(uid), C.c_int(rank), C.c_int(world)), "m3dreg_nccl_init")
+
+    def nccl_attach(self, comm, rank: int, world: int):
+        """Use an existing ncclComm_t (raw address) of the host application; world == 1 detaches."""
+        _check(lib().m3dreg_nccl_attach(self._h, C.c_void_p(int(comm)) if comm else None, C.c_int(rank), C.c_int(world)), "m3dreg_nccl_attach")
+
+    def slam_sweep(self, poses, params: RegParams, distance_threshold: float = 10.0, first_optimised: int = 0):
+        """One registerAll sweep over the uploaded scans 0..n-1 (m3dreg_slam_sweep): gate, partition, accumulate, NCCL
+        all-reduce of the normal-equation blocks, solve.  Returns (poses [n,4,4], status [n], SweepStats)."""
+        ps = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, 16).copy()
+        n = len(ps)
+        sp = SlamParams()
+        C.memmove(C.byref(sp.reg), C.byref(params), C.sizeof(RegParams))
+        sp.distance_threshold = distance_threshold
+        sp.first_optimised = first_optimised
+        status = np.zeros(n, dtype=np.int32)
+        st = SweepStats()
+        _check(lib().m3dreg_slam_sweep(self._h, C.c_int(n), _p(ps), C.byref(sp), _p(status), C.byref(st)), "m3dreg_slam_sweep")
+        return ps.reshape(-1, 4, 4), status, st
+
+    def slam_neq(self, n_scans: int) -> np.ndarray:
+        """The (all-reduced) normal-equation blocks of the last slam_sweep, [n_scans, 28] doubles."""
+        out = np.zeros((n_scans, 28), dtype=np.float64)
+        _check(lib().m3dreg_slam_copy_neq(self._h, _p(out), C.c_int(n_scans)), "m3dreg_slam_copy_neq")
+        return out
 
     def sweep_solve(self, d_neq, poses, params: RegParams, begin=0, end=None):
         ps = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, 16).copy()

@@ -113,6 +113,11 @@ struct m3dreg_ctx {
 	DevBuf<float> d_poses1;      /* sweep: round-tripped poses, 16 floats per scan */
 	DevBuf<double> d_pose6;      /* sweep: tx,ty,tz,om,fi,ka per scan             */
 	DevBuf<int> d_sweep_status;  /* sweep: per-scan solve status                  */
+	DevBuf<double> d_neq;        /* m3dreg_slam_sweep: n_scans x 28 normal-equation blocks (the all-reduce buffer) */
+	void *nccl_comm = nullptr;   /* ncclComm_t of this rank (m3dreg_nccl_init / m3dreg_nccl_attach), 0 = single GPU */
+	bool nccl_owned = false;
+	int nccl_rank = 0, nccl_world = 0;
+	cudaEvent_t ev2 = nullptr;
 
 	/* batched sweep step: segment table, chunk -> segment map, per-segment label counters, pinned staging */
 	DevBuf<SweepSeg> d_segs;
@@ -683,6 +688,8 @@ const char *m3dreg_status_string(int status)
 	case M3DREG_E_BAD_SLOT: return "bad scan slot";
 	case M3DREG_E_NO_DEVICE: return "no sm_100 CUDA device";
 	case M3DREG_E_SIZE_MISMATCH: return "size mismatch";
+	case M3DREG_E_NO_NCCL: return "NCCL not available (libnccl.so.2 not found) or no communicator attached";
+	case M3DREG_E_NCCL: return "NCCL call failed";
 	default: break;
 	}
 	if (status > 0) return cudaGetErrorString((cudaError_t)status);
@@ -751,6 +758,9 @@ void m3dreg_destroy(m3dreg_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->dev);
 	if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+	m3dreg_nccl_attach(c, nullptr, 0, 1);      /* destroys a communicator this context created */
+	c->d_neq.release();
+	if (c->ev2) cudaEventDestroy(c->ev2);
 	for (auto &s : c->scans) s.release();
 	c->g_xyzl.release(); c->g_nrm.release(); c->ci_xyzl.release(); c->ci_nrm.release(); c->co_xyzl.release(); c->co_nrm.release(); c->digit_tot.release();
 	c->ci_tab.release(); c->co_tab.release(); c->ci_loc.release(); c->co_loc.release();
@@ -904,7 +914,10 @@ int m3dreg_transform(m3dreg_ctx *c, const m3dreg_point *d_in, m3dreg_point *d_ou
 	if (!c || !d_in || !d_out || n <= 0 || !m) return M3DREG_E_INVALID_ARG;
 	CK(cudaSetDevice(c->dev));
 	LAUNCH(c, k_transform_aos, (n + 255) / 256, 256, d_in, d_out, n, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11]);
-	return (int)cudaGetLastError();
+	/* drop-in for cudaTransformPointCloud, which ends in cudaDeviceSynchronize (lesson_16.cu:1369-1384): the caller may
+	 * touch d_out from any stream when this returns */
+	CK(cudaStreamSynchronize(c->stream));
+	return launch_status(c);
 }
 
 static int normal_equations_device(m3dreg_ctx *c, const m3dreg_obs_nn *d_obs, int n_obs, const double *pose6)
@@ -1534,3 +1547,5 @@ int m3dreg_sweep_solve(m3dreg_ctx *c, const double *d_neq, int n_scans, int scan
 }
 
 } /* extern "C" */
+
+#include "slam_host.inl"

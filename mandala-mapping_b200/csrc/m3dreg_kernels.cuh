@@ -1878,12 +1878,13 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(const Src src_
 #pragma unroll
 		for (int k = 0; k < kNeqThreads / 32; k++) s += sm[k][threadIdx.x];
 		partials[(size_t)blockIdx.x * kPartialCols + threadIdx.x] = s;
+		__threadfence();      /* only the writers fence (release side of the ticket) */
 	}
-	__threadfence();
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		unsigned int t = atomicAdd(ticket, 1u);
 		is_last = (t == gridDim.x - 1);
+		__threadfence();      /* acquire side: one fence by the thread that took the ticket; the rows are read past L1 */
 	}
 	__syncthreads();
 	if (!is_last) return;
@@ -1891,7 +1892,6 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(const Src src_
 	unsigned long long tq0, tq1, tq2, tq3;
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq0));
 #endif
-	__threadfence();
 	/* the Euler angles the system is formed for: requested now, needed after the reduction */
 	const double *p6g = fin.ps ? fin.ps->pose6 : fin.pose6_in;
 	double p6r[6];

@@ -39,8 +39,15 @@ namespace m3d {
 #endif
 constexpr int kNNHThreads = 64;
 constexpr int kNNHWarps = kNNHThreads / 32;
-constexpr int kNNHCells = 128;            /* hull cells looked up per chunk (segment list capacity) */
-constexpr int kNNHStage = 192;            /* candidates staged per batch (multiple of 4) */
+#ifndef M3D_NNH_CELLS
+#define M3D_NNH_CELLS 128
+#endif
+#ifndef M3D_NNH_STAGE
+#define M3D_NNH_STAGE 192
+#endif
+constexpr int kNNHCells = M3D_NNH_CELLS;  /* hull cells looked up per chunk (segment list capacity) */
+constexpr int kNNHStage = M3D_NNH_STAGE;  /* candidates staged per batch (multiple of 4); shared memory per warp =
+                                           * 16 B x (cells + stage + stage / 4): what the blocks do not take stays L1 cache */
 
 struct NNHullArgs {
 	const float4 *q_xyzl, *q_nrm;
@@ -293,8 +300,8 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 							const int4 s0 = segs[k0];
 							__syncwarp();
 							if (lane == 0) segs[k0] = make_int4(s0.x + kNNHStage, s0.y - kNNHStage, s0.z, s0.w);
-							if (lane < kNNHStage / 4) grp[lane] = make_int4(s0.x + 4 * lane, 4, s0.z, s0.w);
-							if (lane + 32 < kNNHStage / 4) grp[lane + 32] = make_int4(s0.x + 4 * (lane + 32), 4, s0.z, s0.w);
+#pragma unroll
+							for (int g = lane; g < kNNHStage / 4; g += 32) grp[g] = make_int4(s0.x + 4 * g, 4, s0.z, s0.w);
 							ncand = kNNHStage;
 						} else {
 							ncand = __shfl_sync(full, incl, ntake - 1);

@@ -11,8 +11,12 @@ unit of work:
     dist.all_reduce(neq)                                   # NCCL over NVLink/NVSwitch: the ONLY exchange step
     poses  = ctx.sweep_solve(neq, poses, params)           # every rank solves all scans (6x6 Cholesky each): no gather
 
-The compute back-end is injected so the sharding / collective logic can be exercised on CPU (gloo) in the tests;
-the product back-end is :class:`DeviceBackend` (C ABI, no fallback).
+The PRODUCT path is :class:`DeviceSweep`: one call of the C entry point ``m3dreg_slam_sweep`` per sweep — gate,
+partition, accumulation, the NCCL all-reduce (NCCL resolved by the library itself, communicator created from an id that
+rank 0 broadcasts) and the solve all happen inside ``libm3dreg.so`` on the context's stream; Python only hands the
+128-byte id around.  :func:`gate_pairs` / :func:`partition_pairs` / :class:`SweepDriver` restate the same plan in
+Python with an injected back-end so the sharding logic can be exercised on CPU (gloo) in the tests, and the C++ plan
+(``m3dreg_slam_plan``) is checked against them.
 """
 from __future__ import annotations
 
@@ -58,26 +62,46 @@ def partition_pairs(pair_i, pair_j, sizes, world: int):
     return [np.sort(np.concatenate(o)) if o else np.zeros(0, dtype=np.int64) for o in out]
 
 
-class DeviceBackend:
-    """Product back-end: one m3dreg context per rank, scans resident in HBM."""
+class DeviceSweep:
+    """registerAll over the GPUs of one box through ``m3dreg_slam_sweep`` (one context per rank, scans uploaded to
+    slots 0..n-1 of every context).  With torch.distributed initialised (any backend) the NCCL communicator of the
+    library is created from an id broadcast from rank 0; without it the sweep runs on one GPU."""
 
-    def __init__(self, ctx, params):
-        import torch
-        self.ctx, self.params, self.torch = ctx, params, torch
+    def __init__(self, ctx, params, distance_threshold: float = 10.0, first_optimised: int = 0):
+        self.ctx, self.params = ctx, params
+        self.threshold, self.first_optimised = distance_threshold, first_optimised
+        self.rank, self.world = 0, 1
+        self.last_stats = None
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        except Exception:
+            pass
+        if self.world > 1:
+            import importlib
+            import torch
+            import torch.distributed as dist
+            pkg = importlib.import_module(__package__)
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if self.rank == 0:
+                uid = torch.from_numpy(pkg.nccl_unique_id().copy())
+            dev = torch.device("cuda", ctx.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+            uid = uid.to(dev)
+            dist.broadcast(uid, src=0)
+            ctx.nccl_init(uid.cpu().numpy(), self.rank, self.world)
 
-    def new_neq(self, n_scans):
-        return self.torch.zeros(n_scans * 28, dtype=self.torch.float64, device=f"cuda:{self.ctx.device}")
-
-    def accumulate(self, pair_i, pair_j, poses, neq):
-        self.ctx.sweep_zero(neq, len(poses))
-        if len(pair_i):
-            self.ctx.sweep_accumulate(pair_i, pair_j, poses, self.params, neq)
-
-    def solve(self, neq, poses):
-        return self.ctx.sweep_solve(neq, poses, self.params)
+    def sweep(self, poses: np.ndarray):
+        """One Jacobi sweep; returns (new_poses [n,4,4] float32, status [n] int32)."""
+        new_poses, status, st = self.ctx.slam_sweep(poses, self.params, self.threshold, self.first_optimised)
+        self.last_stats = st
+        return new_poses, status
 
 
 class SweepDriver:
+    """The same sweep with the compute back-end injected (tests: a CPU oracle back-end over gloo).  The back-end provides
+    new_neq(n), accumulate(pair_i, pair_j, poses, neq) and solve(neq, poses)."""
+
     def __init__(self, backend, sizes, distance_threshold: float = 10.0, process_group=None):
         self.backend = backend
         self.sizes = np.asarray(sizes)

@@ -114,3 +114,25 @@ def test_two_rank_sweep_equals_single_process(pkg, oracle):
     poses_o, neq_o, status_o = oracle.register_all_sweep(scans, init, prm, pair_thr=10.0)
     assert np.array_equal(status_o, status1)
     assert np.abs(poses_o - single).max() < 1e-6
+
+
+def test_cpp_plan_equals_python_plan(pkg):
+    """m3dreg_slam_plan (the C++ pair gate + partition m3dreg_slam_sweep runs; pure host code) == slam.gate_pairs /
+    slam.partition_pairs for several world sizes, scan sizes and gates; number_of_last_EOZ restricts i."""
+    slam = importlib.import_module("mandala-mapping_b200.slam")
+    rng = np.random.default_rng(3)
+    for n, spread, thr in ((40, 15.0, 10.0), (100, 30.0, 10.0), (12, 2.0, 10.0), (30, 50.0, 5.0)):
+        poses = np.tile(np.eye(4, dtype=np.float32), (n, 1, 1))
+        poses[:, :3, 3] = rng.uniform(-spread, spread, (n, 3)).astype(np.float32)
+        sizes = rng.integers(1000, 70000, n).astype(np.int32)
+        pi, pj = slam.gate_pairs(poses, thr)
+        for world in (1, 2, 3, 4, 8):
+            a, b, ow = pkg.slam_plan(poses, sizes, thr, 0, world)
+            assert np.array_equal(a, pi) and np.array_equal(b, pj)
+            ow_py = np.zeros(len(pi), dtype=np.int32)
+            for r, idx in enumerate(slam.partition_pairs(pi, pj, sizes, world)):
+                ow_py[idx] = r
+            assert np.array_equal(ow, ow_py), (n, world)
+        a, b, ow = pkg.slam_plan(poses, sizes, thr, n - 3, 2)
+        keep = pi >= n - 3
+        assert np.array_equal(a, pi[keep]) and np.array_equal(b, pj[keep])

@@ -159,3 +159,87 @@ def test_sweep_matches_oracle(pkg, oracle, ctx, synth):
         ctx.sweep_accumulate([p[0] for p in pairs[half:]], [p[1] for p in pairs[half:]], init, prm, d_b)
         s = (d_a + d_b).cpu().numpy().reshape(5, 28)
         assert (np.abs(s[:, :27] - neq_d[:, :27]) <= 1e-12 * scale).all() and np.array_equal(s[:, 27], neq_d[:, 27])
+
+
+def test_slam_sweep_entry_matches_oracle(pkg, oracle, ctx, synth):
+    """m3dreg_slam_sweep (gate + partition + accumulate + solve in ONE C call, registerAll of gpu6DSLAM.cpp:424-597) on one
+    rank vs the oracle's sweep: identical counts, normal equations to round-off, poses and statuses; then
+    number_of_last_EOZ semantics: only the last scans move, the others keep their pose bit for bit."""
+    scans, truth, init = synth.slam_scans(5, kind="hdl32", seed=9, spacing=1.0, n_azimuth=256)
+    ctx.scan_clear()
+    for k, s in enumerate(scans):
+        ctx.scan_upload(k, s)
+    for dof in (4, 6):
+        prm = pkg.default_params(1.0, dof=dof)
+        poses_o, neq_o, status_o = oracle.register_all_sweep(scans, init, oracle.default_params(1.0, dof=dof), pair_thr=10.0)
+        poses_d, status_d, st = ctx.slam_sweep(init, prm, 10.0, 0)
+        neq_d = ctx.slam_neq(5)
+        assert st.n_pairs == 20 and st.n_pairs_mine == 20 and st.world == 1
+        assert np.array_equal(neq_d[:, 27], neq_o[:, 27])
+        scale = np.abs(neq_o[:, :27]).max(axis=1, keepdims=True)
+        assert (np.abs(neq_d[:, :27] - neq_o[:, :27]) <= 1e-10 * scale).all()
+        assert np.array_equal(status_d, status_o)
+        assert np.abs(poses_d - poses_o).max() < 1e-6
+    # registerAll(..., number_of_last_EOZ = 2): scans 0..2 are neighbours only
+    prm = pkg.default_params(1.0, dof=4)
+    poses_l, status_l, st = ctx.slam_sweep(init, prm, 10.0, 3)
+    assert st.n_pairs == 8
+    assert np.array_equal(poses_l[:3], np.asarray(init, dtype=np.float32).reshape(-1, 4, 4)[:3])
+    poses_full, _, _ = ctx.slam_sweep(init, prm, 10.0, 0)
+    assert np.array_equal(poses_l[3:], poses_full[3:])       # Jacobi: a scan's update does not depend on who else is optimised
+    # a tight gate leaves scans without pairs: they are still replaced by their Euler round trip, status TOO_FEW_OBS
+    poses_t, status_t, st = ctx.slam_sweep(init, prm, 0.5, 0)
+    assert st.n_pairs == 0 and (status_t == pkg.E_TOO_FEW_OBS).all()
+
+
+def _nccl_rank(rank, world, port, q):
+    import importlib, os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("mandala-mapping_b200")
+    slam = importlib.import_module("mandala-mapping_b200.slam")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)      # only carries the 128-byte NCCL id; the all-reduce is the library's
+    scans, truth, init = pkg.synth.slam_scans(6, kind="hdl32", seed=9, spacing=1.0, n_azimuth=256)
+    ctx = pkg.Context(rank)
+    for k, s in enumerate(scans):
+        ctx.scan_upload(k, s)
+    prm = pkg.default_params(1.0, dof=4)
+    drv = slam.DeviceSweep(ctx, prm, 10.0)
+    poses, status = drv.sweep(init)
+    neq = ctx.slam_neq(6)
+    q.put((rank, poses, status, neq, int(drv.last_stats.n_pairs_mine)))
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_slam_sweep_two_ranks_nccl(pkg, ctx, synth):
+    """Two ranks, two GPUs, the library's own NCCL all-reduce: both ranks end with the single-rank result."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    scans, truth, init = synth.slam_scans(6, kind="hdl32", seed=9, spacing=1.0, n_azimuth=256)
+    ctx.scan_clear()
+    for k, s in enumerate(scans):
+        ctx.scan_upload(k, s)
+    prm = pkg.default_params(1.0, dof=4)
+    poses_1, status_1, _ = ctx.slam_sweep(init, prm, 10.0, 0)
+    neq_1 = ctx.slam_neq(6)
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_nccl_rank, args=(r, 2, 29591, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+    assert res[0][4] > 0 and res[1][4] > 0 and res[0][4] + res[1][4] == 30
+    for r in range(2):
+        assert np.array_equal(res[r][2], status_1)
+        assert np.array_equal(res[r][3][:, 27], neq_1[:, 27])
+        scale = np.abs(neq_1[:, :27]).max(axis=1, keepdims=True)
+        assert (np.abs(res[r][3][:, :27] - neq_1[:, :27]) <= 1e-12 * scale).all()
+        assert np.abs(res[r][1] - poses_1).max() < 1e-6
+    assert np.array_equal(res[0][1], res[1][1])          # both ranks hold the same poses bit for bit

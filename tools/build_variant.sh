@@ -3,5 +3,5 @@
 # -> build_variants/libm3dreg_<name>.so (use with M3DREG_LIB_PATH; never loaded by default).
 name=$1; shift
 mkdir -p build_variants
-/usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared "$@" \
+/usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -ffp-contract=off -shared "$@" \
     -o build_variants/libm3dreg_${name}.so mandala-mapping_b200/csrc/m3dreg.cu

@@ -69,7 +69,7 @@ def main():
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
     for k, s in enumerate(scans):            # scans are replicated: only the 28-double blocks ever cross NVLink
         ctx.scan_upload(k, s)
-    drv = slam.SweepDriver(slam.DeviceBackend(ctx, prm), sizes, 10.0)
+    drv = slam.DeviceSweep(ctx, prm, 10.0)
 
     def barrier():
         if world > 1:
@@ -96,13 +96,13 @@ def main():
     if args.check:
         # distributed normal equations of ONE sweep from the initial poses vs the same sweep computed by this rank alone
         drv.sweep(init)
-        neq_dist = drv.last_neq.clone()
+        a = ctx.slam_neq(len(init))
         pi, pj = slam.gate_pairs(init, 10.0)
-        solo = slam.DeviceBackend(ctx, prm)
-        neq_solo = solo.new_neq(len(init))
-        solo.accumulate(pi, pj, np.ascontiguousarray(init, dtype=np.float32).reshape(-1, 4, 4), neq_solo)
-        torch.cuda.synchronize()
-        a, b = neq_dist.cpu().numpy().reshape(-1, 28), neq_solo.cpu().numpy().reshape(-1, 28)
+        neq_solo = torch.zeros(len(init) * 28, dtype=torch.float64, device="cuda")
+        ctx.sweep_zero(neq_solo, len(init))
+        ctx.sweep_accumulate(pi, pj, np.ascontiguousarray(init, dtype=np.float32).reshape(-1, 4, 4), prm, neq_solo)
+        ctx.synchronize()
+        b = neq_solo.cpu().numpy().reshape(-1, 28)
         scale = np.abs(b[:, :27]).max(axis=1, keepdims=True) + 1e-300
         check = {"max_rel_dev_normal_equations": float((np.abs(a[:, :27] - b[:, :27]) / scale).max()),
                  "counts_identical": bool(np.array_equal(a[:, 27], b[:, 27]))}
@@ -112,9 +112,9 @@ def main():
         err1 = float(np.abs(poses[:, :3, 3] - truth[:, :3, 3]).max())
         line = {"metric": "6DSLAM scans/sec (one Jacobi registerAll sweep)", "value": args.scans / (ms_sweep * 1e-3), "unit": "scans/s",
                 "n_gpus": world, "sweeps": args.sweeps, "ms_per_sweep": ms_sweep, "scaling": "strong",
-                "points_per_s": drv.last_points / (ms_sweep * 1e-3),
+                "points_per_s": int(drv.last_stats.points_all) / (ms_sweep * 1e-3),
                 "config": {"workload": f"{args.scans} synthetic {args.kind} scans x {sizes[0]} points along a loop, {args.bucket} m buckets, 10 m pair gate",
-                           "pairs": drv.last_pairs, "pairs_rank0": drv.last_my_pairs, "mode": args.mode, "dof": args.dof,
+                           "pairs": int(drv.last_stats.n_pairs), "pairs_rank0": int(drv.last_stats.n_pairs_mine), "mode": args.mode, "dof": args.dof,
                            "collective": f"one all_reduce of {args.scans}x28 float64 per sweep ({args.scans * 28 * 8} bytes)"},
                 "solved_scans": int((status == 0).sum()), "max_translation_error_m": {"initial": err0, "after": err1},
                 "check": check, "scan_generation_s": gen_s}
