@@ -379,6 +379,14 @@ def main():
         names = ["box", "barrier1", "keys+hist", "barrier2", "sort pass 1 + count scan", "barrier3", "bucket table + sort pass 2", "barrier4",
                  "(sort pass 3)", "candidate sets"]
         grid_phases_us = {names[k]: float(gph[k + 1] - gph[k]) / 1e3 for k in range(10)} if gph[10] > gph[0] > 0 else None
+        if grid_phases_us and gph[21] > gph[15] > 0:
+            sub = ["count scan (before pass 1)", "digit bases", "ranks (match)", "warp scan", "scatter", "next histogram"]
+            grid_phases_us["sort pass 1 detail"] = dict(**{"count scan": float(gph[15] - gph[4]) / 1e3},
+                                                        **{sub[k]: float(gph[17 + k] - gph[16 + k]) / 1e3 for k in range(5)})
+        if grid_phases_us and gph[27] > gph[22] > 0:
+            subc = ["list + bucket record", "setup", "sweep 1 (bin)", "table scan", "sweep 2 (place)"]
+            grid_phases_us["one bucket detail"] = dict(**{subc[k]: float(gph[23 + k] - gph[22 + k]) / 1e3 for k in range(5)},
+                                                       **{"candidates": int(gph[29] & 0xffffffff), "points": int(gph[29] >> 32), "start after phase begin": float(gph[22] - gph[9]) / 1e3})
     except Exception:
         grid_phases_us = None
     evals_per_query = ctx.nn_evaluations(reset=True) / max(stage_iters, 1) / float(n2)

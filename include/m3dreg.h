@@ -160,7 +160,10 @@ int m3dreg_get_nn_fallbacks(m3dreg_ctx *ctx, uint64_t *count_out, int reset);
 
 /* Diagnostic (only while profiling is on): %globaltimer stamps (ns) of block 0 at the phase boundaries of the last
  * k_grid_build launch — 0 entry, 1 box done, 2 barrier, 3 keys done, 4 barrier, 5 first sort pass done, 6 barrier,
- * 7 bucket table + second pass done, 8 barrier, 9 (third pass), 10 candidate sets done.  stamps_out: 16 entries. */
+ * 7 bucket table + second pass done, 8 barrier, 9 (third pass), 10 candidate sets done; 15-21 inside the first sort pass
+ * (count scan done, entry, digit bases, ranks, warp scan, scatter, next histogram), 22-27 one bucket's candidate set
+ * (start, record read, binning start, binned, table written, placed), 29 its candidate / point counts.
+ * stamps_out: 32 entries. */
 int m3dreg_get_grid_phase_ns(m3dreg_ctx *ctx, uint64_t *stamps_out);
 
 /* ---- stage-level entry points on DEVICE pointers (parity surface = reference L0) ---------- */

@@ -219,7 +219,7 @@ class Context:
 
     def grid_phase_ns(self) -> np.ndarray:
         """%globaltimer stamps of the last k_grid_build launch (profiling on): see m3dreg_get_grid_phase_ns."""
-        out = np.zeros(16, dtype=np.uint64)
+        out = np.zeros(32, dtype=np.uint64)
         _check(lib().m3dreg_get_grid_phase_ns(self._h, _p(out)), "m3dreg_get_grid_phase_ns")
         return out
 

@@ -73,6 +73,16 @@ struct GridBuildArgs {
 	CandSet ci, co;
 };
 
+/* diagnostics: %globaltimer of one thread into dbg[slot] (dbg == 0: nothing) */
+__device__ __forceinline__ void gb_stamp(unsigned long long *dbg, int slot, bool who)
+{
+	if (dbg && who) {
+		unsigned long long t;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+		dbg[slot] = t;
+	}
+}
+
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
 {
 	unsigned int v;
@@ -144,8 +154,10 @@ __device__ __forceinline__ long long gb_block_excl_scan(long long v, long long *
  * keys are still in shared memory from the key phase (first pass: a block sorts the range it made the keys of). */
 __device__ __forceinline__ void gb_scatter_pass(const uint32_t *keys_in, const uint32_t *keys_smem, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
 		int n, int T, int shift, int dbits, const uint32_t *hist, uint32_t *hist_next, uint32_t (*s_w)[kGbRadix], uint32_t *s_gbase,
-		long long *s_scan)
+		long long *s_scan, unsigned long long *dbg = nullptr)
 {
+	const bool dbg_who = blockIdx.x == 0 && threadIdx.x == 0;
+	gb_stamp(dbg, 16, dbg_who);
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const uint32_t mask = (1u << dbits) - 1u;
 	const int G = (int)gridDim.x, c = (int)blockIdx.x;
@@ -170,6 +182,7 @@ __device__ __forceinline__ void gb_scatter_pass(const uint32_t *keys_in, const u
 		if (qd == 0) s_gbase[d] = (uint32_t)((int)ex + (int)pre);
 		__syncthreads();
 	}
+	gb_stamp(dbg, 17, dbg_who);
 	const int begin = c * T, end = min(n, begin + T);
 	const uint32_t lt = (1u << lane) - 1u;
 	for (int sub = begin; sub < end; sub += kGbSub) {
@@ -203,6 +216,7 @@ __device__ __forceinline__ void gb_scatter_pass(const uint32_t *keys_in, const u
 			__syncwarp();
 		}
 		__syncthreads();
+		gb_stamp(dbg, 18, dbg_who);
 		uint32_t sub_tot = 0;
 		if (threadIdx.x < 256) {     /* exclusive scan over the warps for digit = threadIdx.x */
 			uint32_t run = 0;
@@ -215,6 +229,7 @@ __device__ __forceinline__ void gb_scatter_pass(const uint32_t *keys_in, const u
 			sub_tot = run;
 		}
 		__syncthreads();
+		gb_stamp(dbg, 19, dbg_who);
 #pragma unroll
 		for (int j = 0; j < kGbItems; j++) {
 			const int i = wbase + j * 32 + lane;
@@ -226,6 +241,7 @@ __device__ __forceinline__ void gb_scatter_pass(const uint32_t *keys_in, const u
 				rank[j] = pos;
 			}
 		}
+		gb_stamp(dbg, 20, dbg_who);
 		if (hist_next) {
 			/* next pass: one atomic per group of equal (destination block, next digit) inside the warp */
 #pragma unroll
@@ -238,6 +254,7 @@ __device__ __forceinline__ void gb_scatter_pass(const uint32_t *keys_in, const u
 			}
 		}
 		__syncthreads();
+		gb_stamp(dbg, 21, dbg_who);
 		if (threadIdx.x < 256) s_gbase[threadIdx.x] += sub_tot;
 		__syncthreads();
 	}
@@ -391,7 +408,8 @@ __global__ void __launch_bounds__(kGbThreads, 1) k_grid_build(const GridBuildArg
 			a.brec[c] = r;
 		}
 	}
-	gb_scatter_pass(a.keys[start], a.cache ? s_keys : nullptr, nullptr, a.keys[start ^ 1], a.vals[start ^ 1], n, T, 0, dbits, hist0, passes > 1 ? hist1 : nullptr, s_w, s_gbase, s_scan);
+	M3D_GB_STAMP(15);
+	gb_scatter_pass(a.keys[start], a.cache ? s_keys : nullptr, nullptr, a.keys[start ^ 1], a.vals[start ^ 1], n, T, 0, dbits, hist0, passes > 1 ? hist1 : nullptr, s_w, s_gbase, s_scan, a.dbg);
 	M3D_GB_STAMP(5);
 	grid_barrier(a.bar, gen);
 	M3D_GB_STAMP(6);
@@ -505,11 +523,15 @@ __global__ void __launch_bounds__(kGbThreads, 1) k_grid_build(const GridBuildArg
 		const uint32_t *vals = a.vals[1];
 		/* warp-major over blocks: consecutive list entries go to different SMs */
 		for (unsigned int t = (unsigned int)w * G + c; t < ncells; t += nwarps) {
+			if (a.dbg && c == 0 && w == 12 && lane == 0 && t == (unsigned int)w * G + c) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.dbg[22] = t_; }
 			const int cell = (int)__ldcg(a.cell_list + t);
 			const int *bp = reinterpret_cast<const int *>(a.buckets + cell);
 			const int c_begin = __ldcg(bp), c_n = __ldcg(bp + 2);
 			cg.cx = cell / (nby * nbz); cg.cy = (cell / nbz) % nby; cg.cz = cell % nbz;
-			build_cell_candidates<true>(vals, a.lx, a.ln, nullptr, rot, xf, c_begin, c_n, a.max_inner, tables, cg, a.ci, s_hist[w], lane);
+			/* diagnostics: the phases of one mid-list bucket (block 0, warp 12) */
+			unsigned long long *bdbg = (a.dbg && c == 0 && w == 12 && t == (unsigned int)w * G + c) ? a.dbg : nullptr;
+			if (bdbg && lane == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); bdbg[23] = t_; }
+			build_cell_candidates<true>(vals, a.lx, a.ln, nullptr, rot, xf, c_begin, c_n, a.max_inner, tables, cg, a.ci, s_hist[w], lane, bdbg);
 			if (two_sets) build_cell_candidates<true>(vals, a.lx, a.ln, nullptr, rot, xf, c_begin, c_n, a.max_outer, tables, cg, a.co, s_hist[w], lane);
 		}
 	}

@@ -724,7 +724,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	cudaEventCreate(&c->ev0);
 	cudaEventCreate(&c->ev1);
 	size_t small = sizeof(PoseState) + 8 * sizeof(uint32_t) + sizeof(m3dreg_grid_params) + FLAG_COUNT * sizeof(int) +
-			4 * sizeof(unsigned long long) + 64 + 64 * sizeof(double) + 32 * sizeof(float) + 1024;
+			4 * sizeof(unsigned long long) + 64 + 64 * sizeof(double) + 32 * sizeof(float) + 1536;
 	char *blk = nullptr;
 	e = cudaMalloc((void **)&blk, small);
 	if (e != cudaSuccess) { m3dreg_destroy(c); return (int)e; }
@@ -740,7 +740,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	c->ticket = (unsigned int *)take(16);
 	c->cell_count = (unsigned int *)take(16);
 	c->grid_bar = (unsigned int *)take(16);
-	c->gb_dbg = (unsigned long long *)take(16 * sizeof(unsigned long long));
+	c->gb_dbg = (unsigned long long *)take(32 * sizeof(unsigned long long));
 	c->nn_work = (unsigned int *)take(16);
 	c->eval_counter = (unsigned long long *)take(16);
 	c->mats = (float *)take(32 * sizeof(float));
@@ -835,7 +835,7 @@ int m3dreg_get_grid_phase_ns(m3dreg_ctx *c, uint64_t *stamps_out)
 	if (!c || !stamps_out) return M3DREG_E_INVALID_ARG;
 	CK(cudaSetDevice(c->dev));
 	CK(cudaStreamSynchronize(c->stream));
-	CK(cudaMemcpy(stamps_out, c->gb_dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(stamps_out, c->gb_dbg, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
 	return 0;
 }
 

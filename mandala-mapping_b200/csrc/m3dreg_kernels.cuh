@@ -694,7 +694,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
 template <bool VALS_CG = false>
 __device__ __forceinline__ void build_cell_candidates(const uint32_t *vals, const float4 *__restrict__ src_xyzl,
 		const float4 *__restrict__ src_nrm, const float4 *__restrict__ loc_src, const NormalRotation &rot, const PointXform &xf, int begin, int npts, int cap, int tables, const CellGeom &g,
-		const CandSet &set, uint32_t *hist, int lane)
+		const CandSet &set, uint32_t *hist, int lane, unsigned long long *dbg = nullptr)
 {
 	const unsigned full = 0xffffffffu;
 	if (npts <= 0 || cap <= 0 || begin < 0) return;
@@ -703,6 +703,11 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *vals, cons
 	const int level = tables ? nn_level(npts) : -1;
 	const int nbins = level >= 0 ? (4 << (3 * level)) : 0;
 	const int lv = level < 0 ? 0 : level;
+	auto stamp = [&](int slot) {
+		if (dbg && lane == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[slot] = t_; }
+	};
+	stamp(24);
+	if (dbg && lane == 0) dbg[29] = (unsigned long long)ncand | ((unsigned long long)npts << 32);
 	const float wx = nn_subcell_width(g.rx, lv), wy = nn_subcell_width(g.ry, lv), wz = nn_subcell_width(g.rz, lv);
 	auto table_value = [&](int k) { return VALS_CG ? __ldcg(vals + begin + k * iter) : __ldg(vals + begin + k * iter); };
 	auto bin_of = [&](const float4 &p) {
@@ -750,6 +755,7 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *vals, cons
 		}
 	}
 	__syncwarp();
+	stamp(25);
 	/* exclusive scan of the nbins + 1 table entries (9 consecutive entries per lane cover 288 >= 257), table out */
 	{
 		uint32_t h[9], sum = 0;
@@ -772,6 +778,7 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *vals, cons
 		}
 		__syncwarp();
 	}
+	stamp(26);
 	/* sweep 2: placement.  The order of the candidates INSIDE a bin is whatever the atomics hand out: the search takes
 	 * the lexicographic minimum of (dist, l) with l carried in the record, so it does not depend on it */
 	for (int k0 = 0; k0 < ncand; k0 += 32 * kBuildChunk) {
@@ -791,6 +798,7 @@ __device__ __forceinline__ void build_cell_candidates(const uint32_t *vals, cons
 		}
 	}
 	__syncwarp();
+	stamp(27);
 }
 
 /* One warp per searchable bucket of the compact list k_finalize_grid / k_list_cells left behind. */

@@ -35,15 +35,15 @@
 namespace m3d {
 
 #ifndef M3D_NNH_MINBLOCKS
-#define M3D_NNH_MINBLOCKS 16
+#define M3D_NNH_MINBLOCKS 12
 #endif
 constexpr int kNNHThreads = 64;
 constexpr int kNNHWarps = kNNHThreads / 32;
 #ifndef M3D_NNH_CELLS
-#define M3D_NNH_CELLS 128
+#define M3D_NNH_CELLS 64
 #endif
 #ifndef M3D_NNH_STAGE
-#define M3D_NNH_STAGE 192
+#define M3D_NNH_STAGE 128
 #endif
 constexpr int kNNHCells = M3D_NNH_CELLS;  /* hull cells looked up per chunk (segment list capacity) */
 constexpr int kNNHStage = M3D_NNH_STAGE;  /* candidates staged per batch (multiple of 4); shared memory per warp =
@@ -76,7 +76,15 @@ struct NNHullArgs {
 /* the lane's conservative box of fine columns for dist <= tau (nn_query()'s box), clamped to its 27-neighbourhood */
 struct NNBox { int xl, xh, yl, yh, zl, zh; };
 
-__device__ __forceinline__ NNBox nnh_box(float tau, int prune, float qx, float qy, float qz, float mnx, float mny, float mnz,
+#ifndef M3D_NNH_BOX_INLINE
+#define M3D_NNH_BOX_INLINE 0
+#endif
+#if M3D_NNH_BOX_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+NNBox nnh_box(float tau, int prune, float qx, float qy, float qz, float mnx, float mny, float mnz,
 		float iwx, float iwy, float iwz, int ix, int iy, int iz, int nbx, int nby, int nbz)
 {
 	/* R >= sqrt(tau) * (1 + 2^-20) is all the proof needs: tau * rsqrt(tau) is within 2^-21 of sqrt(tau) (MUFU.RSQ: 2 ulp),
@@ -226,9 +234,19 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 						break;
 					}
 				}
-				/* may every lane look at every bucket the hull touches? (always, unless the radius exceeds the bucket size) */
-				const bool nb_all = __all_sync(full, !mine || (nnh_in_neighbourhood(uxl, uyl, uzl, ix, iy, iz, nbx, nby, nbz) &&
-						nnh_in_neighbourhood(uxh, uyh, uzh, ix, iy, iz, nbx, nby, nbz)));
+				/* may every lane look at every bucket the hull touches?  Always for coherent warps unless the radius exceeds
+				 * the bucket size; otherwise the lanes search on their own (the masked variant of the loops below would
+				 * double the code on the hot path for a case the reference's schedule never produces: radius == bucket) */
+				if (!__all_sync(full, !mine || (nnh_in_neighbourhood(uxl, uyl, uzl, ix, iy, iz, nbx, nby, nbz) &&
+						nnh_in_neighbourhood(uxh, uyh, uzh, ix, iy, iz, nbx, nby, nbz)))) {
+					if (COUNT) {
+						const unsigned fb = __ballot_sync(full, unsettled);
+						if (lane == 0) atomicAdd(a.eval_counter + 1, (unsigned long long)__popc(fb));
+					}
+					if (unsettled) { const int2 fr = nnh_query_fallback(&a, qx, qy, qz, label, qi); best_l = fr.x; best_j = -1; evals += (unsigned int)fr.y; }
+					unsettled = false;
+					break;
+				}
 				const int nrows = dy * dz, rpc = __float2int_rz(__fdividef((float)kNNHCells + 0.5f, (float)dx));   /* = kNNHCells / dx for 1 <= dx <= kNNHCells */
 				const float inv_dx = __frcp_rn((float)dx), inv_dy = __frcp_rn((float)dy);
 				for (int row0 = 0; row0 < nrows; row0 += rpc) {
@@ -332,34 +350,17 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 						bool flag = false;
 						{
 							const unsigned long long qx2 = f2_pack(qx, qx), qy2 = f2_pack(qy, qy), qz2 = f2_pack(qz, qz);
-							if (nb_all) {
-								if (COUNT && mine) evals += (unsigned int)ncand;
+							if (COUNT && mine) evals += (unsigned int)ncand;
 #pragma unroll 2
-								for (int g = 0; g < ngrp; g++) {
-									const float4 X = stage[4 * g], Y = stage[4 * g + 1], Z = stage[4 * g + 2];
-									float d0, d1, d2, d3;
-									f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.x, X.y), f2_pack(Y.x, Y.y), f2_pack(Z.x, Z.y)), d0, d1);
-									f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.z, X.w), f2_pack(Y.z, Y.w), f2_pack(Z.z, Z.w)), d2, d3);
-									const float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
-									const bool lt = m4 < rb;
-									flag = flag || (m4 == rb);
-									rb = lt ? m4 : rb; bg = lt ? g : bg;
-								}
-							} else {
-								for (int g = 0; g < ngrp; g++) {
-									const int4 gi = grp[g];
-									const bool use = nnh_in_neighbourhood(uxl + (gi.z & 0xffff), uyl + (gi.z >> 16), uzl + gi.w, ix, iy, iz, nbx, nby, nbz);
-									if (COUNT && mine && use) evals += 4u;
-									const float4 X = stage[4 * g], Y = stage[4 * g + 1], Z = stage[4 * g + 2];
-									float d0, d1, d2, d3;
-									f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.x, X.y), f2_pack(Y.x, Y.y), f2_pack(Z.x, Z.y)), d0, d1);
-									f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.z, X.w), f2_pack(Y.z, Y.w), f2_pack(Z.z, Z.w)), d2, d3);
-									float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
-									m4 = use ? m4 : INFINITY;
-									const bool lt = m4 < rb;
-									flag = flag || (m4 == rb);
-									rb = lt ? m4 : rb; bg = lt ? g : bg;
-								}
+							for (int g = 0; g < ngrp; g++) {
+								const float4 X = stage[4 * g], Y = stage[4 * g + 1], Z = stage[4 * g + 2];
+								float d0, d1, d2, d3;
+								f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.x, X.y), f2_pack(Y.x, Y.y), f2_pack(Z.x, Z.y)), d0, d1);
+								f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.z, X.w), f2_pack(Y.z, Y.w), f2_pack(Z.z, Z.w)), d2, d3);
+								const float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
+								const bool lt = m4 < rb;
+								flag = flag || (m4 == rb);
+								rb = lt ? m4 : rb; bg = lt ? g : bg;
 							}
 						}
 						/* full predicate on the winning group: its four {normal, label} records and the query's normal go out
@@ -385,8 +386,7 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 						if (__any_sync(full, flag)) {
 							for (int g = 0; g < ngrp; g++) {
 								const int4 gi = grp[g];
-								const bool use = flag && mine && (nb_all || nnh_in_neighbourhood(uxl + (gi.z & 0xffff), uyl + (gi.z >> 16), uzl + gi.w, ix, iy, iz, nbx, nby, nbz));
-								if (use) {
+								if (flag && mine) {
 #pragma unroll
 									for (int t = 0; t < 4; t++) {
 										const float *src = stagef + (g << 4) + t;
