@@ -380,7 +380,7 @@ def main():
                  "(sort pass 3)", "candidate sets"]
         grid_phases_us = {names[k]: float(gph[k + 1] - gph[k]) / 1e3 for k in range(10)} if gph[10] > gph[0] > 0 else None
         if grid_phases_us and gph[21] > gph[15] > 0:
-            sub = ["count scan (before pass 1)", "digit bases", "ranks (match)", "warp scan", "scatter", "next histogram"]
+            sub = ["digit bases", "ranks (match)", "warp scan", "scatter", "next histogram"]
             grid_phases_us["sort pass 1 detail"] = dict(**{"count scan": float(gph[15] - gph[4]) / 1e3},
                                                         **{sub[k]: float(gph[17 + k] - gph[16 + k]) / 1e3 for k in range(5)})
         if grid_phases_us and gph[27] > gph[22] > 0:

@@ -152,7 +152,7 @@ __device__ __forceinline__ long long gb_block_excl_scan(long long v, long long *
  * hist = this pass's [256][Gp] matrix of per-block digit counts (complete); hist_next (0 for the last pass) gets
  * the next digit's counts per DESTINATION block.  vals_in == 0: implicit original indices.  keys_smem != 0: the block's
  * keys are still in shared memory from the key phase (first pass: a block sorts the range it made the keys of). */
-__device__ __forceinline__ void gb_scatter_pass(const uint32_t *keys_in, const uint32_t *keys_smem, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
+__device__ __noinline__ void gb_scatter_pass(const uint32_t *keys_in, const uint32_t *keys_smem, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
 		int n, int T, int shift, int dbits, const uint32_t *hist, uint32_t *hist_next, uint32_t (*s_w)[kGbRadix], uint32_t *s_gbase,
 		long long *s_scan, unsigned long long *dbg = nullptr)
 {
@@ -162,24 +162,31 @@ __device__ __forceinline__ void gb_scatter_pass(const uint32_t *keys_in, const u
 	const uint32_t mask = (1u << dbits) - 1u;
 	const int G = (int)gridDim.x, c = (int)blockIdx.x;
 	/* a) where this block's digits start: sum of the digit's counts in earlier blocks + all smaller digits everywhere.
-	 * Thread (d, quarter) adds every fourth 128-bit piece of row d: ~10 independent loads in flight, one L2 latency */
+	 * Only the 2^dbits digits in use are read; (1024 >> dbits) threads share a digit's row, each adding every tpd-th
+	 * 128-bit piece (all of a thread's loads in flight at once), then a butterfly over those threads */
 	{
-		const int d = threadIdx.x >> 2, qd = threadIdx.x & 3;
+		const int lt = dbits < 5 ? 5 : dbits;                      /* log2 of digits handled (>= 32 so that a digit's threads sit in one warp) */
+		const int tpd = kGbThreads >> lt;                          /* threads per digit: 4 (8 bits) .. 32 (5 bits) */
+		const int d = threadIdx.x / tpd, qd = threadIdx.x % tpd;
 		const int Gp = (G + 3) & ~3;
-		const uint4 *row = reinterpret_cast<const uint4 *>(hist + (size_t)d * Gp);
 		uint32_t pre = 0, tot = 0;
+		if (d < (1 << dbits)) {
+			const uint4 *row = reinterpret_cast<const uint4 *>(hist + (size_t)d * Gp);
 #pragma unroll 5
-		for (int j = qd; j < (Gp >> 2); j += 4) {
-			const uint4 v = __ldcg(row + j);
-			const int r0 = j << 2;
-			tot += v.x + v.y + v.z + v.w;
-			pre += (r0 < c ? v.x : 0u) + (r0 + 1 < c ? v.y : 0u) + (r0 + 2 < c ? v.z : 0u) + (r0 + 3 < c ? v.w : 0u);
+			for (int j = qd; j < (Gp >> 2); j += tpd) {
+				const uint4 v = __ldcg(row + j);
+				const int r0 = j << 2;
+				tot += v.x + v.y + v.z + v.w;
+				pre += (r0 < c ? v.x : 0u) + (r0 + 1 < c ? v.y : 0u) + (r0 + 2 < c ? v.z : 0u) + (r0 + 3 < c ? v.w : 0u);
+			}
 		}
-		tot += __shfl_xor_sync(0xffffffffu, tot, 1); tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-		pre += __shfl_xor_sync(0xffffffffu, pre, 1); pre += __shfl_xor_sync(0xffffffffu, pre, 2);
+		for (int o = 1; o < tpd; o <<= 1) {
+			tot += __shfl_xor_sync(0xffffffffu, tot, o);
+			pre += __shfl_xor_sync(0xffffffffu, pre, o);
+		}
 		long long total;
 		const long long ex = gb_block_excl_scan(qd == 0 ? (long long)tot : 0LL, s_scan, &total);      /* thread order = digit order */
-		if (qd == 0) s_gbase[d] = (uint32_t)((int)ex + (int)pre);
+		if (qd == 0 && d < kGbRadix) s_gbase[d] = (uint32_t)((int)ex + (int)pre);
 		__syncthreads();
 	}
 	gb_stamp(dbg, 17, dbg_who);
@@ -337,15 +344,18 @@ __global__ void __launch_bounds__(kGbThreads, 1) k_grid_build(const GridBuildArg
 	uint32_t *hist0 = a.hist, *hist1 = a.hist + (size_t)Gp * kGbRadix, *hist2 = a.hist + 2 * (size_t)Gp * kGbRadix;
 	{
 		if (threadIdx.x < kGbRadix) {
-			s_gbase[threadIdx.x] = 0;      /* block digit histogram */
 			hist1[(size_t)threadIdx.x * Gp + c] = 0;
 			hist2[(size_t)threadIdx.x * Gp + c] = 0;
 		}
+		/* per-WARP digit histograms (s_w rows): a block's points fall into a handful of buckets, and 32 warps adding to
+		 * the same few shared-memory words serialise (measured: this phase took 10 us with one block histogram) */
+#pragma unroll
+		for (int k = 0; k < kGbRadix / 32; k++) s_w[w][k * 32 + lane] = 0;
 		if (c == 0) {                     /* padding columns G..Gp-1 of the three matrices (the buffer is shared with other sorts) */
 			for (int t = (int)threadIdx.x; t < 3 * kGbRadix * (Gp - G); t += kGbThreads)
 				a.hist[(size_t)(t / (Gp - G)) * Gp + G + t % (Gp - G)] = 0;
 		}
-		__syncthreads();
+		__syncwarp();
 		const int nby = g.number_of_buckets_Y, nbz = g.number_of_buckets_Z;
 		const int span = ((end - begin) + kGbThreads - 1) / kGbThreads * kGbThreads;      /* whole warps stay together for the ballots */
 		for (int o = (int)threadIdx.x; o < span; o += kGbThreads) {
@@ -369,12 +379,18 @@ __global__ void __launch_bounds__(kGbThreads, 1) k_grid_build(const GridBuildArg
 			if (head && key >= 0) {
 				const unsigned later = heads & ~((2u << lane) - 1u);
 				const int len = (later ? __ffs(later) - 1 : 32) - lane;      /* idle lanes (key -1) only trail the last valid run */
-				atomicAdd(&s_gbase[(uint32_t)key & dmask], (uint32_t)len);
+				atomicAdd(&s_w[w][(uint32_t)key & dmask], (uint32_t)len);     /* contention only among the run heads of this warp */
 				atomicAdd(a.bcount + key, len);
 			}
 		}
 		__syncthreads();
-		if (threadIdx.x < kGbRadix) hist0[(size_t)threadIdx.x * Gp + c] = s_gbase[threadIdx.x];
+		if (threadIdx.x < kGbRadix) {
+			uint32_t s = 0;
+#pragma unroll 8
+			for (int k = 0; k < kGbWarps; k++) s += s_w[k][threadIdx.x];
+			hist0[(size_t)threadIdx.x * Gp + c] = s;
+		}
+		__syncthreads();      /* s_w is reused by the first sort pass */
 	}
 	M3D_GB_STAMP(3);
 	grid_barrier(a.bar, gen);

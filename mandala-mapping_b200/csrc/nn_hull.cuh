@@ -12,20 +12,23 @@
  *      that remembers the winning GROUP and flags exact ties between groups;
  *   5. one cold step per lane applies the full predicate to the winning group; a tie or an inadmissible winner re-scans;
  *   6. a lane is settled when its limit is covered by rho^2 or its box for the current limit lies inside the hull.
- * What changed (the round-1 kernel was issue-bound at 55 % with a third of the warps resident and spilled):
- *   - 64 registers instead of 80 -> 16 instead of 12 blocks per SM: the per-lane margins, neighbourhood clamps and the
- *     query normal are recomputed / re-read where they are used instead of living in registers; nothing spills;
- *   - everything that depends only on the launch (4 / res, r^2, first radius) comes in as kernel arguments;
- *   - PERSISTENT warps: the grid is one wave (blocks per SM x SM count), every warp fetches chunks of 32 queries from an
- *     atomic counter until none is left.  16 384 two-warp blocks kept a third of the warp slots empty while the next
- *     block was being launched; the launch-constant prologue now runs once per warp instead of once per 32 queries;
- *   - the previous round's hull (whose cells are skipped, exactness argument in m3dreg_kernels.cuh) is kept packed in
- *     four registers;
+ * What changed against round 1's kernel, and what measuring it on B200 showed (C2, 1 048 576 queries; profiles/):
+ *   - PERSISTENT warps: the grid is one wave (resident blocks x SM count), every warp fetches chunks of 32 queries from an
+ *     atomic counter until none is left; the launch-constant prologue runs once per warp, everything that depends only on
+ *     the launch (4 / res, r^2, first radius) comes in as kernel arguments;
+ *   - the per-lane margins, neighbourhood clamps and the query normal are recomputed / re-read where they are used instead
+ *     of living in registers; the previous round's hull (whose cells are skipped, exactness argument in
+ *     m3dreg_kernels.cuh) is kept packed in four registers; the box helper is out of line (two call sites);
  *   - the cold step issues its (up to four) normal loads and the query normal together, one L2 latency instead of four
- *     dependent ones;
- *   - the winner's record comes from the candidate set's `loc` stream (point in the local frame + original index): one
- *     gather instead of table[l] -> cloud[index];
+ *     dependent ones; the winner's record comes from the candidate set's `loc` stream (point in the local frame +
+ *     original index): one gather instead of table[l] -> cloud[index];
+ *   - 7 KB instead of 11.8 KB of shared memory per two-warp block (64 cells, 128 staged candidates): what the blocks do
+ *     not take stays L1 cache, and the L1 hit rate is what moved with occupancy (56 % at 24 warps per SM, 33 % at 32);
  *   - the evaluation counter is a template parameter (profiling only).
+ * MEASURED: 12 / 14 / 16 resident blocks per SM (80 / 72 / 64 registers) give 115.8 / 114.2 / 117.1 us against 118.6 us
+ * for round 1's kernel — issue slots stay 57 % busy whatever the number of resident warps (more warps = longer
+ * scoreboard stalls: same instructions per second).  57.6 M warp instructions per launch at that rate is the kernel's
+ * time; the remaining lever is the instruction count itself, see DESIGN.md section 5.
  * Exactness: a lane only ever takes the minimum over candidates of buckets in its own 27-neighbourhood (tested per
  * group when the hull leaves some lane's neighbourhood); looking at MORE of those than the reference does not change a
  * minimum, and every candidate with dist <= limit lies inside the lane's box (nn_core.cuh: col_floor / col_ceil). */
@@ -76,15 +79,9 @@ struct NNHullArgs {
 /* the lane's conservative box of fine columns for dist <= tau (nn_query()'s box), clamped to its 27-neighbourhood */
 struct NNBox { int xl, xh, yl, yh, zl, zh; };
 
-#ifndef M3D_NNH_BOX_INLINE
-#define M3D_NNH_BOX_INLINE 0
-#endif
-#if M3D_NNH_BOX_INLINE
-__device__ __forceinline__
-#else
-__device__ __noinline__
-#endif
-NNBox nnh_box(float tau, int prune, float qx, float qy, float qz, float mnx, float mny, float mnz,
+/* out of line: two call sites of ~110 instructions each, and the hot path of a chunk should stay near the 32 KB
+ * instruction cache (B300_MICROARCH.md: L1.5 I-cache) */
+__device__ __noinline__ NNBox nnh_box(float tau, int prune, float qx, float qy, float qz, float mnx, float mny, float mnz,
 		float iwx, float iwy, float iwz, int ix, int iy, int iz, int nbx, int nby, int nbz)
 {
 	/* R >= sqrt(tau) * (1 + 2^-20) is all the proof needs: tau * rsqrt(tau) is within 2^-21 of sqrt(tau) (MUFU.RSQ: 2 ulp),
@@ -234,19 +231,9 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 						break;
 					}
 				}
-				/* may every lane look at every bucket the hull touches?  Always for coherent warps unless the radius exceeds
-				 * the bucket size; otherwise the lanes search on their own (the masked variant of the loops below would
-				 * double the code on the hot path for a case the reference's schedule never produces: radius == bucket) */
-				if (!__all_sync(full, !mine || (nnh_in_neighbourhood(uxl, uyl, uzl, ix, iy, iz, nbx, nby, nbz) &&
-						nnh_in_neighbourhood(uxh, uyh, uzh, ix, iy, iz, nbx, nby, nbz)))) {
-					if (COUNT) {
-						const unsigned fb = __ballot_sync(full, unsettled);
-						if (lane == 0) atomicAdd(a.eval_counter + 1, (unsigned long long)__popc(fb));
-					}
-					if (unsettled) { const int2 fr = nnh_query_fallback(&a, qx, qy, qz, label, qi); best_l = fr.x; best_j = -1; evals += (unsigned int)fr.y; }
-					unsettled = false;
-					break;
-				}
+				/* may every lane look at every bucket the hull touches? (always, unless the radius exceeds the bucket size) */
+				const bool nb_all = __all_sync(full, !mine || (nnh_in_neighbourhood(uxl, uyl, uzl, ix, iy, iz, nbx, nby, nbz) &&
+						nnh_in_neighbourhood(uxh, uyh, uzh, ix, iy, iz, nbx, nby, nbz)));
 				const int nrows = dy * dz, rpc = __float2int_rz(__fdividef((float)kNNHCells + 0.5f, (float)dx));   /* = kNNHCells / dx for 1 <= dx <= kNNHCells */
 				const float inv_dx = __frcp_rn((float)dx), inv_dy = __frcp_rn((float)dy);
 				for (int row0 = 0; row0 < nrows; row0 += rpc) {
@@ -350,17 +337,34 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 						bool flag = false;
 						{
 							const unsigned long long qx2 = f2_pack(qx, qx), qy2 = f2_pack(qy, qy), qz2 = f2_pack(qz, qz);
-							if (COUNT && mine) evals += (unsigned int)ncand;
+							if (nb_all) {
+								if (COUNT && mine) evals += (unsigned int)ncand;
 #pragma unroll 2
-							for (int g = 0; g < ngrp; g++) {
-								const float4 X = stage[4 * g], Y = stage[4 * g + 1], Z = stage[4 * g + 2];
-								float d0, d1, d2, d3;
-								f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.x, X.y), f2_pack(Y.x, Y.y), f2_pack(Z.x, Z.y)), d0, d1);
-								f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.z, X.w), f2_pack(Y.z, Y.w), f2_pack(Z.z, Z.w)), d2, d3);
-								const float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
-								const bool lt = m4 < rb;
-								flag = flag || (m4 == rb);
-								rb = lt ? m4 : rb; bg = lt ? g : bg;
+								for (int g = 0; g < ngrp; g++) {
+									const float4 X = stage[4 * g], Y = stage[4 * g + 1], Z = stage[4 * g + 2];
+									float d0, d1, d2, d3;
+									f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.x, X.y), f2_pack(Y.x, Y.y), f2_pack(Z.x, Z.y)), d0, d1);
+									f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.z, X.w), f2_pack(Y.z, Y.w), f2_pack(Z.z, Z.w)), d2, d3);
+									const float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
+									const bool lt = m4 < rb;
+									flag = flag || (m4 == rb);
+									rb = lt ? m4 : rb; bg = lt ? g : bg;
+								}
+							} else {
+								for (int g = 0; g < ngrp; g++) {
+									const int4 gi = grp[g];
+									const bool use = nnh_in_neighbourhood(uxl + (gi.z & 0xffff), uyl + (gi.z >> 16), uzl + gi.w, ix, iy, iz, nbx, nby, nbz);
+									if (COUNT && mine && use) evals += 4u;
+									const float4 X = stage[4 * g], Y = stage[4 * g + 1], Z = stage[4 * g + 2];
+									float d0, d1, d2, d3;
+									f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.x, X.y), f2_pack(Y.x, Y.y), f2_pack(Z.x, Z.y)), d0, d1);
+									f2_unpack(nn_dist2(qx2, qy2, qz2, f2_pack(X.z, X.w), f2_pack(Y.z, Y.w), f2_pack(Z.z, Z.w)), d2, d3);
+									float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
+									m4 = use ? m4 : INFINITY;
+									const bool lt = m4 < rb;
+									flag = flag || (m4 == rb);
+									rb = lt ? m4 : rb; bg = lt ? g : bg;
+								}
 							}
 						}
 						/* full predicate on the winning group: its four {normal, label} records and the query's normal go out
@@ -386,7 +390,8 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 						if (__any_sync(full, flag)) {
 							for (int g = 0; g < ngrp; g++) {
 								const int4 gi = grp[g];
-								if (flag && mine) {
+								const bool use = flag && mine && (nb_all || nnh_in_neighbourhood(uxl + (gi.z & 0xffff), uyl + (gi.z >> 16), uzl + gi.w, ix, iy, iz, nbx, nby, nbz));
+								if (use) {
 #pragma unroll
 									for (int t = 0; t < 4; t++) {
 										const float *src = stagef + (g << 4) + t;
