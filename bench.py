@@ -226,6 +226,107 @@ def run_reference(args, rank, world, out):
     print(json.dumps(line), file=out, flush=True)
 
 
+def slam_record(pkg, which, args, rank, world, local_rank):
+    """Multi-scan 6D SLAM record (BASELINE configs C4 / C5 shape): registerAll sweeps through the C entry point
+    m3dreg_slam_sweep — pairs gated at 10 m and sharded over the ranks, ONE NCCL all-reduce of the n_scans x 28
+    normal-equation blocks per sweep inside the library, redundant solve.  STRONG scaling: the scan set is fixed, the ranks
+    share its pairs.  Scan generation is spread over the ranks and exchanged (it is numpy ray casting, not the product)."""
+    import torch
+    import torch.distributed as dist
+    slam = importlib.import_module("mandala-mapping_b200.slam")
+    if which == "c4":
+        n_scans, kind, kw, res, modes, dof = args.slam_scans, "hdl32", {}, 1.0, ["icp"], 4
+        desc = f"C4: registerAll over {n_scans} synthetic HDL-32E scans x 65 536 points along a loop, 1.0 m buckets, 10 m pair gate, 4-DOF (the reference's live solver, gpu6DSLAM.cpp:575)"
+    else:
+        n_scans, kind, kw, res, modes, dof = args.slam_c5_scans, "sick", {}, 1.0, ["icp", "ndt"], 6
+        desc = (f"C5 shape: registerAll over {n_scans} synthetic rotating-SICK scans x 1 048 576 points, 1.0 m buckets, 10 m pair gate, "
+                "ICP and NDT sweeps alternating (BASELINE's 1000 scans do not fit a bench run: the scans are numpy ray casts, 2.4 s each)")
+    t0 = time.perf_counter()
+    mine = [k for k in range(n_scans) if k % world == rank]
+    scans, truth, init = pkg.synth.slam_scans(n_scans, kind=kind, seed=42, spacing=1.0, only=mine, **kw)
+    ctx = pkg.Context(local_rank)
+    npts = len(scans[mine[0]])
+    if world > 1:
+        per = (n_scans + world - 1) // world
+        loc = torch.zeros((per, npts * 40), dtype=torch.uint8, device="cuda")
+        for q, k in enumerate(mine):
+            assert len(scans[k]) == npts
+            loc[q] = torch.from_numpy(np.frombuffer(scans[k].tobytes(), dtype=np.uint8).copy()).cuda()
+        allb = [torch.empty_like(loc) for _ in range(world)]
+        dist.all_gather(allb, loc)
+        torch.cuda.synchronize()
+        for k in range(n_scans):
+            ctx.scan_upload(k, allb[k % world][k // world].data_ptr(), n=npts, on_device=True)
+        del allb, loc
+    else:
+        for k in range(n_scans):
+            ctx.scan_upload(k, scans[k])
+    gen_s = time.perf_counter() - t0
+    drivers = {m: slam.DeviceSweep(ctx, pkg.default_params(res, dof=dof, mode=pkg.MODE_NDT if m == "ndt" else pkg.MODE_ICP), 10.0) for m in modes[:1]}
+    for m in modes[1:]:      # the communicator lives in the context: later drivers reuse it
+        d = slam.DeviceSweep.__new__(slam.DeviceSweep)
+        d.ctx, d.params, d.threshold, d.first_optimised = ctx, pkg.default_params(res, dof=dof, mode=pkg.MODE_NDT if m == "ndt" else pkg.MODE_ICP), 10.0, 0
+        d.rank, d.world, d.last_stats = rank, world, None
+        drivers[m] = d
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    poses = init.copy()
+    for m in modes:                       # warm-up: one sweep per mode from the initial poses (result discarded)
+        drivers[m].sweep(init)
+    err = [pkg.synth.relative_pose_error(poses, truth)]
+    acc_ms, red_ms, wall = [], [], []
+    status = None
+    barrier()
+    for s in range(args.slam_sweeps):
+        m = modes[s % len(modes)]
+        barrier()
+        t1 = time.perf_counter()
+        poses, status = drivers[m].sweep(poses)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t1
+        st = drivers[m].last_stats
+        v = torch.tensor([dt * 1e3, st.accumulate_ms, st.allreduce_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        wall.append(float(v[0])); acc_ms.append(float(v[1])); red_ms.append(float(v[2]))
+        err.append(pkg.synth.relative_pose_error(poses, truth))
+    st = drivers[modes[0]].last_stats
+    ms_sweep = float(np.mean(wall))
+    # sharded == unsharded: the all-reduced blocks of a sweep from the initial poses vs the same rows accumulated by this rank alone
+    drivers[modes[0]].sweep(init)
+    neq = ctx.slam_neq(n_scans)
+    rows = sorted(set([0, n_scans // 3, n_scans - 1]))
+    pi, pj, _ = pkg.slam_plan(init, [npts] * n_scans, 10.0, 0, 1)
+    sel = np.isin(pi, rows)
+    solo = torch.zeros(n_scans * 28, dtype=torch.float64, device="cuda")
+    ctx.sweep_zero(solo, n_scans)
+    ctx.sweep_accumulate(pi[sel], pj[sel], init, drivers[modes[0]].params, solo)
+    ctx.synchronize()
+    b = solo.cpu().numpy().reshape(-1, 28)[rows]
+    a = neq[rows]
+    scale = np.abs(b[:, :27]).max(axis=1, keepdims=True) + 1e-300
+    dev = float((np.abs(a[:, :27] - b[:, :27]) / scale).max())
+    chk = torch.tensor([dev, 0.0 if np.array_equal(a[:, 27], b[:, 27]) else 1.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(chk, op=dist.ReduceOp.MAX)
+    ctx.close()
+    return {
+        "workload": desc, "scaling": "strong", "n_scans": n_scans, "points_per_scan": npts, "pairs": int(st.n_pairs), "pairs_rank0": int(st.n_pairs_mine),
+        "modes": modes, "dof": dof, "sweeps": args.slam_sweeps, "ms_per_sweep": ms_sweep, "scans_per_s": n_scans / (ms_sweep * 1e-3),
+        "points_per_s": int(st.points_all) / (ms_sweep * 1e-3),
+        "accumulate_ms_max_rank": float(np.mean(acc_ms)), "allreduce_wait_ms_max_rank": float(np.mean(red_ms)),
+        "timing": "host wall clock around m3dreg_slam_sweep (gate + partition + accumulate + NCCL all-reduce + solve + pose read-back), max over ranks, mean over sweeps",
+        "collective": f"one ncclAllReduce of {n_scans} x 28 float64 ({n_scans * 224} bytes) per sweep, issued by the library on its stream",
+        "sharded_vs_single_rank": {"rows": rows, "max_rel_dev_normal_equations": float(chk[0]), "counts_identical": bool(chk[1] == 0.0)},
+        "relative_pose_error_m": {"initial": err[0], "per_sweep": err[1:]},
+        "solved_scans": int((status == 0).sum()), "scan_generation_and_upload_s": gen_s,
+    }
+
+
 def _claim_stdout():
     """Rank 0 prints exactly ONE JSON line on stdout: keep a private handle on the real stdout and send everything any
     library prints there (NCCL's version banner is a bare printf) to stderr."""
@@ -248,6 +349,11 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--slam", default="c4", help="comma list of multi-scan records to add to the line: c4 (100 HDL-32E scans x 65 536, "
+                    "registerAll strong scaling), c5 (rotating-SICK scans x 1 048 576, ICP and NDT sweeps alternating), none")
+    ap.add_argument("--slam-scans", type=int, default=100)
+    ap.add_argument("--slam-c5-scans", type=int, default=16)
+    ap.add_argument("--slam-sweeps", type=int, default=6)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -394,8 +500,8 @@ def main():
     ctx.set_profiling(False)
     ctx.icp_end()
     stage_ms = stage_ms / max(stage_iters, 1)
-    stage_names = ["transform+bounds (part of the grid launch unless M3DREG_GRID_LEGACY=1)", "grid (k_grid_build: transform, box, keys, sort, bucket table, candidate sets)",
-                   "semantic NN (k_nn_search_grid)", "normal equations + solve"]
+    stage_names = ["box pass (transform in registers + bounding box)", "grid (keys, radix sort, bucket table, candidate sets)",
+                   "semantic NN (k_nn_search_hull)", "normal equations + solve"]
     dom = int(np.argmax(stage_ms))
     nn_ms = float(stage_ms[2])
     nn_bytes = nn_alg_bytes(n1, n2, nb)
@@ -429,6 +535,14 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * (n1 + n2) * e2e_steps / float(te.item())
 
+    ctx.close()
+    slam_out = {}
+    for which in [w for w in args.slam.split(",") if w in ("c4", "c5")]:
+        try:
+            slam_out[which] = slam_record(pkg, which, args, rank, world, local_rank)
+        except Exception as ex:  # pragma: no cover
+            slam_out[which] = {"failed": repr(ex)}
+
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -453,8 +567,8 @@ def main():
             "launches_per_step": launches / args.steps,
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "k_nn_search_grid", "achieved": nn_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": nn_gbs / peak_gbs,
-                "traffic": ncu_traffic("k_nn_search_grid", args.workload) if args.mode == "icp" else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": nn_bytes, "launch_ms": nn_ms,
+                "bound": "hbm", "kernel": "k_nn_search_hull", "achieved": nn_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": nn_gbs / peak_gbs,
+                "traffic": ncu_traffic("k_nn_search_hull", args.workload) if args.mode == "icp" else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": nn_bytes, "launch_ms": nn_ms,
                 "dominant_stage": stage_names[dom],
                 "nn_candidate_evaluations_per_query": evals_per_query,
                 "nn_queries_on_per_thread_fallback": fallback_share,
@@ -466,10 +580,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": 40 * (n1 + n2), "d2h_bytes_per_step": 4 * n2 + 64,
                     "steps": e2e_steps, "call": "m3dreg_icp_iteration_host (both 40-B clouds H2D from pinned memory, nn + pose D2H, every step)"},
             "cpu_baseline": cpu,
+            "slam": slam_out or None,
             "result": {"status": int(st.last_status), "translation_error_m": float(np.abs(pose_out[:3, 3] - pose_true[:3, 3]).max())},
         }
         print(json.dumps(line), file=out, flush=True)
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -29,6 +29,8 @@ using namespace m3d;
 
 namespace {
 
+struct LocalBox { float mn[3], mx[3], diag; };     /* a scan's bounding box in its local frame */
+
 struct Scan {
 	float4 *xyzl = nullptr;     /* original order: the order the grid's tie-break (ascending index) refers to   */
 	float4 *nrm = nullptr;
@@ -38,6 +40,14 @@ struct Scan {
 	int n = 0;
 	size_t cap = 0;
 	float diag = 0.0f;          /* diagonal of the local bounding box: bounds the extent of the scan under ANY rigid pose */
+	float bb_min[3] = {0, 0, 0}, bb_max[3] = {0, 0, 0};   /* local bounding box (host copy, read back once at upload) */
+	LocalBox box() const
+	{
+		LocalBox b;
+		for (int k = 0; k < 3; k++) { b.mn[k] = bb_min[k]; b.mx[k] = bb_max[k]; }
+		b.diag = diag;
+		return b;
+	}
 	void release()
 	{
 		if (xyzl) cudaFree(xyzl);
@@ -103,7 +113,8 @@ struct m3dreg_ctx {
 	DevBuf<m3dreg_bucket> buckets;
 	DevBuf<int> nn;
 	DevBuf<float4> obs_rec;                          /* per query, query order: matched point (local frame) + its index (k_nn_search*) */
-	int grid_legacy = 0;                             /* env M3DREG_GRID_LEGACY=1: the multi-kernel grid build of round 1 (A/B runs) */
+	int grid_mega = 0;                               /* env M3DREG_GRID_MEGA=1: the single-launch grid build (grid_build.cuh) instead of the
+	                                                  * PDL-chained kernels — measured slower on B200 at every size, kept for A/B runs */
 	int nn_v7 = 0;                                   /* env M3DREG_NN_V7=1: round 1's k_nn_search_grid instead of k_nn_search_hull (A/B runs) */
 	cudaError_t launch_err = cudaSuccess;            /* first failed kernel launch since the last report */
 	DevBuf<m3dreg_point> aos_a, aos_b;
@@ -244,6 +255,9 @@ inline void launch_grid_build(m3dreg_ctx *c, const GridBuildArgs &a)
 	c->launches++;
 }
 
+int bits_for(long long nb);
+long long sort_limit(const m3dreg_ctx *c, int bits);
+
 int bits_for(long long nb)
 {
 	int bits = 1;
@@ -331,6 +345,42 @@ long long bucket_capacity_for(float diag, const m3dreg_reg_params *prm)
 	double cap = per_axis * per_axis * per_axis;
 	if (cap > 2147483647.0) cap = 2147483647.0;
 	return (long long)cap;
+}
+
+/* Radix bits for the grid of a scan at (about) the given pose, WITHOUT looking at the device: the transformed cloud lies
+ * inside the transformed local bounding box, whose axis-aligned extent bounds every nb_axis; `margin` extra cells per
+ * axis absorb the pose changes of a registration loop.  The sort runs ceil(bits / 8) passes and therefore orders any
+ * grid of up to 2^(8 passes) buckets correctly — that (and the allocated table) is what the key kernel checks the actual
+ * bucket count against on the device (sort_limit()). */
+int planned_sort_bits(const float bb_min[3], const float bb_max[3], const float *pose16, const m3dreg_reg_params *prm, int margin)
+{
+	double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+	for (int k = 0; k < 8; k++) {
+		const double x = (k & 1) ? bb_max[0] : bb_min[0], y = (k & 2) ? bb_max[1] : bb_min[1], z = (k & 4) ? bb_max[2] : bb_min[2];
+		for (int r = 0; r < 3; r++) {
+			const double v = pose16 ? (double)pose16[4 * r] * x + (double)pose16[4 * r + 1] * y + (double)pose16[4 * r + 2] * z + (double)pose16[4 * r + 3]
+					: (r == 0 ? x : (r == 1 ? y : z));
+			if (v < lo[r]) lo[r] = v;
+			if (v > hi[r]) hi[r] = v;
+		}
+	}
+	double cap = 1.0;
+	for (int r = 0; r < 3; r++) {
+		double nb = floor(((hi[r] - lo[r]) * 1.0001 + 2.0 * (double)prm->bbox_extension) / (double)prm->bucket_size) + 2.0 + (double)margin;
+		if (!(nb >= 1.0)) nb = 1.0;
+		cap *= nb;
+	}
+	if (cap > 2147483647.0) cap = 2147483647.0;
+	return bits_for((long long)cap);
+}
+
+/* largest bucket count a sort planned for `bits` radix bits orders correctly, capped by the allocated table */
+long long sort_limit(const m3dreg_ctx *c, int bits)
+{
+	int passes = (bits + kRadixBits - 1) / kRadixBits;
+	if (passes < 1) passes = 1;
+	long long lim = passes * kRadixBits >= 31 ? 2147483647LL : (1LL << (passes * kRadixBits));
+	return lim < (long long)c->buckets.cap ? lim : (long long)c->buckets.cap;
 }
 
 int ensure_second(m3dreg_ctx *c, size_t n)
@@ -432,11 +482,11 @@ CandSet cand_set(m3dreg_ctx *c, bool outer)
 /* gp must already be on the device (c->gp); src = the gridded cloud in original order (global frame); loc_src = the same
  * cloud in the frame the moment reduction wants (local; 0 = src); cell_list / c->cell_count hold the searchable buckets. */
 void build_candidates(m3dreg_ctx *c, const uint32_t *vals, const m3dreg_bucket *buckets, const uint32_t *cell_list,
-		const float4 *src_xyzl, const float4 *src_nrm, const float4 *loc_src, const float *nrm_m, int max_inner, int max_outer)
+		const float4 *src_xyzl, const float4 *src_nrm, const float4 *loc_src, const float *nrm_m, bool xform_points, int max_inner, int max_outer)
 {
 	bool two = max_inner != max_outer;
 	LAUNCH(c, k_build_candidates, c->sm_count * 7, kBuildWarps * 32, vals, c->gp, buckets, cell_list, c->cell_count, src_xyzl, src_nrm, loc_src, nrm_m,
-			max_inner, max_outer, cand_set(c, false), cand_set(c, two), two ? 1 : 0);
+			xform_points ? 1 : 0, max_inner, max_outer, cand_set(c, false), cand_set(c, two), two ? 1 : 0);
 }
 
 /* src_xyzl: the first cloud as the moment reduction wants it (local frame in the fused loops), original order;
@@ -490,23 +540,26 @@ void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *va
 			label_counts, c->profiling ? c->eval_counter : nullptr, seg_of_chunk);
 }
 
-/* Round-1 grid build (multi-kernel), kept for the stage-level entry points and A/B runs (M3DREG_GRID_LEGACY=1): grid of
- * the (already transformed) first cloud in g_*: params (device) from bounds, keys, sort, dense table, candidate sets.
- * bounds must already hold the reduced box. */
-void build_grid_legacy(m3dreg_ctx *c, int n1, const m3dreg_reg_params *prm, int sort_bits, const float4 *src_nrm, const float4 *loc_src, const float *nrm_m)
+/* Multi-kernel grid build (PDL-chained launches): params (device) from the reduced box, keys, stable LSD sort, dense
+ * table, candidate sets.  (src_xyzl, src_nrm) = the cloud in original order: with pose != 0 the stored scan in its local
+ * frame, transformed on the fly by the key pass and the candidate gather exactly as the box pass did (the transformed
+ * cloud is never stored); with pose == 0 a cloud that is already global.  bounds must already hold the reduced box.
+ * Measured against the single-launch variant (build_grid_mega) on B200: 59 + 17 us vs 82 us on the 1 M-point pair,
+ * 49 + 8 vs 106 us on the 65 k-point pair — this is the default. */
+void build_grid_legacy(m3dreg_ctx *c, const float4 *src_xyzl, const float4 *src_nrm, int n1, const float *pose, const m3dreg_reg_params *prm, int sort_bits)
 {
 	SortPlan sp = plan_sort(n1, sort_bits);
 	if (sp.items == kSortItemsBig)
-		LAUNCH(c, k_grid_head<kSortItemsBig>, sp.tiles, kSortThreads, c->g_xyzl.p, n1, c->bounds, prm->bucket_size, prm->bucket_size, prm->bucket_size,
-				prm->bbox_extension, (long long)c->buckets.cap, c->gp, c->flags, c->cell_count, c->buckets.p, c->keys[0].p, sp.tiles, sp.passes, c->hist.p);
+		LAUNCH(c, k_grid_head<kSortItemsBig>, sp.tiles, kSortThreads, src_xyzl, pose, n1, c->bounds, prm->bucket_size, prm->bucket_size, prm->bucket_size,
+				prm->bbox_extension, sort_limit(c, sort_bits), c->gp, c->flags, c->cell_count, c->buckets.p, c->keys[0].p, sp.tiles, sp.passes, c->hist.p);
 	else
-		LAUNCH(c, k_grid_head<4>, sp.tiles, kSortThreads, c->g_xyzl.p, n1, c->bounds, prm->bucket_size, prm->bucket_size, prm->bucket_size,
-				prm->bbox_extension, (long long)c->buckets.cap, c->gp, c->flags, c->cell_count, c->buckets.p, c->keys[0].p, sp.tiles, sp.passes, c->hist.p);
+		LAUNCH(c, k_grid_head<4>, sp.tiles, kSortThreads, src_xyzl, pose, n1, c->bounds, prm->bucket_size, prm->bucket_size, prm->bucket_size,
+				prm->bbox_extension, sort_limit(c, sort_bits), c->gp, c->flags, c->cell_count, c->buckets.p, c->keys[0].p, sp.tiles, sp.passes, c->hist.p);
 	int cur = sort_by_bucket(c, n1, sort_bits, c->gp, true, true);
 	LAUNCH(c, k_finalize_grid, grid_for(c, n1, 256), 256, c->keys[cur].p, c->vals[cur].p, n1, c->gp, c->buckets.p,
 			(m3dreg_hash_element *)nullptr, c->cell_list.p, c->cell_count);
 	if (prm->mode != M3DREG_MODE_NDT)
-		build_candidates(c, c->vals[cur].p, c->buckets.p, c->cell_list.p, c->g_xyzl.p, src_nrm, loc_src, nrm_m, prm->max_inner, prm->max_outer);
+		build_candidates(c, c->vals[cur].p, c->buckets.p, c->cell_list.p, src_xyzl, src_nrm, (const float4 *)nullptr, pose, pose != nullptr, prm->max_inner, prm->max_outer);
 	c->last_sorted = cur;
 }
 
@@ -613,18 +666,20 @@ void stage_events_collect(m3dreg_ctx *c)
 	c->stage_iters++;
 }
 
-/* One registerLastArrivedScan iteration, fully on the device: THREE launches (k_grid_build, k_nn_search_grid,
- * k_normal_equations).  first local cloud = (lx, ln), queries already in q_*. */
+/* One registerLastArrivedScan iteration, fully on the device, nothing read back: box pass, key pass, sort passes, bucket
+ * table, candidate sets, search, moment reduction + solve (PDL-chained launches).  first local cloud = (lx, ln), queries
+ * already in q_*. */
 void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, int n2,
 		const m3dreg_reg_params *prm, int sort_bits)
 {
 	const bool prof = c->profiling;
 	const bool ndt = prm->mode == M3DREG_MODE_NDT;
 	if (prof) cudaEventRecord(c->pev[0], c->stream);
-	if (c->grid_legacy) {
-		LAUNCH(c, k_transform_soa<true>, grid_for(c, n1, 256), 256, lx, ln, n1, c->ps->pose1, c->g_xyzl.p, (float4 *)nullptr, c->bounds);
+	if (!c->grid_mega) {
+		/* box pass: transform in registers, nothing stored (NDT keeps the transformed cloud for its bucket statistics) */
+		LAUNCH(c, k_transform_soa<true>, grid_for(c, n1, 256), 256, lx, ln, n1, c->ps->pose1, ndt ? c->g_xyzl.p : (float4 *)nullptr, (float4 *)nullptr, c->bounds);
 		if (prof) cudaEventRecord(c->pev[1], c->stream);
-		build_grid_legacy(c, n1, prm, sort_bits, ln, lx, c->ps->pose1);
+		build_grid_legacy(c, lx, ln, n1, c->ps->pose1, prm, sort_bits);
 	} else {
 		if (prof) cudaEventRecord(c->pev[1], c->stream);      /* the transform is part of the grid launch */
 		build_grid_mega(c, lx, ln, n1, c->ps->pose1, prm, ndt);
@@ -713,7 +768,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	c->sm_count = prop.multiProcessorCount;
 	{ const char *e = getenv("M3DREG_NO_PDL"); c->use_pdl = (e && e[0] == '1') ? 0 : 1; }
 	{ const char *e = getenv("M3DREG_NN_PER_THREAD"); c->nn_per_thread = (e && e[0] == '1') ? 1 : 0; }
-	{ const char *e = getenv("M3DREG_GRID_LEGACY"); c->grid_legacy = (e && e[0] == '1') ? 1 : 0; }
+	{ const char *e = getenv("M3DREG_GRID_MEGA"); c->grid_mega = (e && e[0] == '1') ? 1 : 0; }
 	{ const char *e = getenv("M3DREG_NN_V7"); c->nn_v7 = (e && e[0] == '1') ? 1 : 0; }
 	{ const char *e = getenv("M3DREG_NN_RHO_DIV"); if (e && atoi(e) > 0) c->nn_tune.rho_div = atoi(e); }
 	{ const char *e = getenv("M3DREG_NN_HULL_MIN"); if (e && atoi(e) > 0) c->nn_tune.hull_min = atoi(e); }
@@ -901,7 +956,7 @@ int m3dreg_nn_search(m3dreg_ctx *c, const m3dreg_point *d_first, int n1, const m
 	LAUNCH(c, k_split_table, grid_for(c, n1, 256), 256, d_table, n1, c->keys[0].p, c->vals[0].p);
 	CK(cudaMemsetAsync(c->cell_count, 0, sizeof(unsigned int), c->stream));
 	LAUNCH(c, k_list_cells, grid_for(c, n1, 256), 256, c->keys[0].p, n1, d_buckets, c->cell_list.p, c->cell_count);
-	build_candidates(c, c->vals[0].p, d_buckets, c->cell_list.p, c->g_xyzl.p, c->g_nrm.p, (const float4 *)nullptr, (const float *)nullptr, max_inner, max_outer);
+	build_candidates(c, c->vals[0].p, d_buckets, c->cell_list.p, c->g_xyzl.p, c->g_nrm.p, (const float4 *)nullptr, (const float *)nullptr, false, max_inner, max_outer);
 	const float res3[3] = {params->resolution_X, params->resolution_Y, params->resolution_Z};
 	launch_nn(c, nullptr, n2, c->vals[0].p, n1, d_buckets, res3, search_radius, max_inner, max_outer, c->prune, d_nn, (float4 *)nullptr, c->g_xyzl.p, nullptr);
 	c->last_valid = false;
@@ -1010,7 +1065,7 @@ int m3dreg_semantic_nn_host(m3dreg_ctx *c, const m3dreg_point *first, int n1, co
 	if ((e = ensure_candidates(c, (size_t)n1, max_inner, max_outer))) return e;
 	int sort_bits = 0;
 	if ((e = plan_buckets(c, &prm, &sort_bits))) return e;      /* sizes the bucket table from the box (one read-back) */
-	if (c->grid_legacy) build_grid_legacy(c, n1, &prm, sort_bits, c->g_nrm.p, (const float4 *)nullptr, (const float *)nullptr);
+	if (!c->grid_mega) build_grid_legacy(c, c->g_xyzl.p, c->g_nrm.p, n1, (const float *)nullptr, &prm, sort_bits);
 	else {
 		LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);              /* k_grid_build reduces the box itself */
 		build_grid_mega(c, c->g_xyzl.p, c->g_nrm.p, n1, (const float *)nullptr, &prm, false);
@@ -1065,6 +1120,7 @@ static int presort_scan(m3dreg_ctx *c, Scan &s, const m3dreg_point *d_aos)
 		mn[k] = o2f_host(c->h->bounds[k]); mx[k] = o2f_host(c->h->bounds[3 + k]);
 		if (mx[k] - mn[k] > ext) ext = mx[k] - mn[k];
 		d2 += ((double)mx[k] - (double)mn[k]) * ((double)mx[k] - (double)mn[k]);
+		s.bb_min[k] = mn[k]; s.bb_max[k] = mx[k];
 	}
 	s.diag = (float)sqrt(d2);
 	float res = ext / 511.0f;
@@ -1124,8 +1180,8 @@ int m3dreg_scan_clear(m3dreg_ctx *c)
 
 /* ---- fused loops ------------------------------------------------------------------------------------------- */
 
-/* diagonal of the bounding box of an AoS cloud on the device (one read-back; host-buffer entry points only) */
-static int local_diag_aos(m3dreg_ctx *c, const m3dreg_point *d_aos, int n, float *diag)
+/* bounding box of an AoS cloud on the device (one read-back; host-buffer entry points only) */
+static int local_box_aos(m3dreg_ctx *c, const m3dreg_point *d_aos, int n, LocalBox *box)
 {
 	LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
 	LAUNCH(c, k_bounds_aos, grid_for(c, n, 256), 256, d_aos, n, c->bounds);
@@ -1133,16 +1189,17 @@ static int local_diag_aos(m3dreg_ctx *c, const m3dreg_point *d_aos, int n, float
 	CK(cudaStreamSynchronize(c->stream));
 	double d2 = 0.0;
 	for (int k = 0; k < 3; k++) {
-		double d = (double)o2f_host(c->h->bounds[3 + k]) - (double)o2f_host(c->h->bounds[k]);
+		box->mn[k] = o2f_host(c->h->bounds[k]); box->mx[k] = o2f_host(c->h->bounds[3 + k]);
+		const double d = (double)box->mx[k] - (double)box->mn[k];
 		d2 += d * d;
 	}
-	*diag = (float)sqrt(d2);
+	box->diag = (float)sqrt(d2);
 	return 0;
 }
 
-/* diag = diagonal of the first cloud's LOCAL bounding box (Scan::diag) */
+/* box = the first cloud's LOCAL bounding box (Scan::box()) */
 static int icp_begin_internal(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, int n2, const float *pose_first,
-		const m3dreg_reg_params *prm, float diag)
+		const m3dreg_reg_params *prm, const LocalBox &box)
 {
 	int e;
 	if ((e = ensure_candidates(c, (size_t)n1, prm->max_inner, prm->max_outer))) return e;
@@ -1153,17 +1210,12 @@ static int icp_begin_internal(m3dreg_ctx *c, const float4 *lx, const float4 *ln,
 	CK(cudaMemsetAsync(c->flags, 0, FLAG_COUNT * sizeof(int), c->stream));
 	CK(cudaMemsetAsync(c->ticket, 0, sizeof(unsigned int), c->stream));
 	LAUNCH(c, k_pose_prepare, 1, 32, c->ps);
-	int sort_bits = 0;
-	if (c->grid_legacy) {
-		/* round-1 path: size the dense bucket table from the initial box (one sync, outside the iteration loop) */
-		LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
-		LAUNCH(c, k_transform_soa<true>, grid_for(c, n1, 256), 256, lx, ln, n1, c->ps->pose1, c->g_xyzl.p, (float4 *)nullptr, c->bounds);
-		if ((e = plan_buckets(c, prm, &sort_bits))) return e;
-	} else {
-		/* a table that holds the grid of this scan under ANY pose: no read-back, no synchronisation, and a pose that
-		 * drifts cannot outgrow it */
-		if ((e = ensure_buckets(c, (size_t)bucket_capacity_for(diag, prm), prm->mode == M3DREG_MODE_NDT))) return e;
-	}
+	/* Nothing is read back to plan the loop (round 1 transformed the cloud once and synchronised to size the table):
+	 * the bucket table holds the grid of this scan under ANY pose (its extent never exceeds the local box's diagonal), and
+	 * the number of sort passes follows from the local box rotated by the initial pose plus a margin of four cells per
+	 * axis for the pose changes of the loop. */
+	if ((e = ensure_buckets(c, (size_t)bucket_capacity_for(box.diag, prm), prm->mode == M3DREG_MODE_NDT))) return e;
+	const int sort_bits = planned_sort_bits(box.mn, box.mx, pose_first, prm, 4);
 	LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
 	c->act_lx = lx; c->act_ln = ln; c->act_n1 = n1; c->act_n2 = n2; c->act_sort_bits = sort_bits; c->act_prm = *prm;
 	c->active = true;
@@ -1182,9 +1234,9 @@ static int icp_end_internal(m3dreg_ctx *c, float *pose_first_out, m3dreg_icp_sta
 }
 
 static int icp_loop(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, int n2, float *pose_first,
-		const m3dreg_reg_params *prm, int iterations, m3dreg_icp_stats *stats, float diag)
+		const m3dreg_reg_params *prm, int iterations, m3dreg_icp_stats *stats, const LocalBox &box)
 {
-	int e = icp_begin_internal(c, lx, ln, n1, n2, pose_first, prm, diag);
+	int e = icp_begin_internal(c, lx, ln, n1, n2, pose_first, prm, box);
 	if (e) return e;
 	CK(cudaEventRecord(c->ev0, c->stream));
 	for (int it = 0; it < iterations; it++) icp_iteration_device(c, lx, ln, n1, n2, prm, c->act_sort_bits);
@@ -1219,7 +1271,7 @@ int m3dreg_icp_begin(m3dreg_ctx *c, int first_slot, int second_slot, const float
 	if ((e = ensure_first(c, (size_t)A.n))) return e;
 	if ((e = ensure_second(c, (size_t)B.n))) return e;
 	if ((e = stage_queries(c, second_slot, pose_second))) return e;
-	return icp_begin_internal(c, A.xyzl, A.nrm, A.n, B.n, pose_first, prm, A.diag);
+	return icp_begin_internal(c, A.xyzl, A.nrm, A.n, B.n, pose_first, prm, A.box());
 }
 
 int m3dreg_icp_step(m3dreg_ctx *c, int iterations)
@@ -1290,7 +1342,7 @@ int m3dreg_icp_pair(m3dreg_ctx *c, int first_slot, int second_slot, float *pose_
 	if ((e = ensure_first(c, (size_t)A.n))) return e;
 	if ((e = ensure_second(c, (size_t)B.n))) return e;
 	if ((e = stage_queries(c, second_slot, pose_second))) return e;
-	e = icp_loop(c, A.xyzl, A.nrm, A.n, B.n, pose_first, prm, iterations, stats, A.diag);
+	e = icp_loop(c, A.xyzl, A.nrm, A.n, B.n, pose_first, prm, iterations, stats, A.box());
 	c->active = false;
 	return e;
 }
@@ -1312,9 +1364,9 @@ int m3dreg_icp_iteration_host(m3dreg_ctx *c, const m3dreg_point *first_local, in
 	LAUNCH(c, k_unpack_points, (n1 + 255) / 256, 256, c->aos_a.p, n1, c->l_xyzl.p, c->l_nrm.p);
 	LAUNCH(c, k_unpack_points, (n2 + 255) / 256, 256, c->aos_b.p, n2, c->q_xyzl.p, c->q_nrm.p);
 	c->act_perm = nullptr;
-	float diag = 0.0f;
-	if (!c->grid_legacy && (e = local_diag_aos(c, c->aos_a.p, n1, &diag))) return e;
-	e = icp_loop(c, c->l_xyzl.p, c->l_nrm.p, n1, n2, pose_first, prm, 1, stats, diag);
+	LocalBox box;
+	if ((e = local_box_aos(c, c->aos_a.p, n1, &box))) return e;
+	e = icp_loop(c, c->l_xyzl.p, c->l_nrm.p, n1, n2, pose_first, prm, 1, stats, box);
 	c->active = false;
 	if (e) return e;
 	if (nn_out) {
@@ -1450,8 +1502,7 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 		if ((e = ensure_first(c, max_first))) return e;
 		if ((e = ensure_candidates(c, max_first, prm->max_inner, prm->max_outer))) return e;
 		if ((e = ensure_second(c, max_second))) return e;
-		if (c->grid_legacy) { if ((e = c->buckets.ensure((size_t)1))) return e; }
-		else if ((e = ensure_buckets(c, (size_t)max_cap, ndt))) return e;
+		if ((e = ensure_buckets(c, (size_t)max_cap, ndt))) return e;
 	}
 	if (!ndt) {
 		if ((e = c->d_segs.ensure(all_segs.size() + 1))) return e;
@@ -1476,17 +1527,16 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 	CK(cudaMemsetAsync(c->ticket, 0, sizeof(unsigned int), c->stream));
 	if (!ndt) CK(cudaMemsetAsync(c->d_seg_counts.p, 0, 4 * kMaxSegs * sizeof(unsigned long long), c->stream));
 
-	int cur_i = -1, sort_bits = 0;
+	int cur_i = -1;
 	for (const Batch &bt : batches) {
 		const int i = bt.i;
 		const Scan &A = c->scans[(size_t)i];
 		const float *pose_i = c->d_poses1.p + 16 * (size_t)i;
 		if (i != cur_i) {
 			LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
-			if (c->grid_legacy) {
-				LAUNCH(c, k_transform_soa<true>, grid_for(c, A.n, 256), 256, A.xyzl, A.nrm, A.n, pose_i, c->g_xyzl.p, (float4 *)nullptr, c->bounds);
-				if ((e = plan_buckets(c, prm, &sort_bits))) return e;
-				build_grid_legacy(c, A.n, prm, sort_bits, A.nrm, A.xyzl, pose_i);
+			if (!c->grid_mega) {
+				LAUNCH(c, k_transform_soa<true>, grid_for(c, A.n, 256), 256, A.xyzl, A.nrm, A.n, pose_i, ndt ? c->g_xyzl.p : (float4 *)nullptr, (float4 *)nullptr, c->bounds);
+				build_grid_legacy(c, A.xyzl, A.nrm, A.n, pose_i, prm, planned_sort_bits(A.bb_min, A.bb_max, h_p1 + 16 * (size_t)i, prm, 1));
 			} else {
 				build_grid_mega(c, A.xyzl, A.nrm, A.n, pose_i, prm, ndt);
 			}

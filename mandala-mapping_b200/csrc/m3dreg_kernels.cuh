@@ -109,6 +109,18 @@ __device__ __forceinline__ void block_bounds_commit(float mnx, float mny, float 
 	}
 }
 
+/* rigid transform applied to a stored scan's points on the fly (the fused loop never materialises the transformed
+ * cloud): same operation sequence as k_transform_soa, so the bits equal the ones the bounding box was made from */
+struct PointXform { float r[12]; int on; };
+
+__device__ __forceinline__ float4 xform_point(const PointXform &x, const float4 &p)
+{
+	if (!x.on) return p;
+	return make_float4(__fadd_rn(x.r[3], __fmaf_rn(x.r[2], p.z, __fmaf_rn(x.r[0], p.x, __fmul_rn(x.r[1], p.y)))),
+			__fadd_rn(x.r[7], __fmaf_rn(x.r[6], p.z, __fmaf_rn(x.r[4], p.x, __fmul_rn(x.r[5], p.y)))),
+			__fadd_rn(x.r[11], __fmaf_rn(x.r[10], p.z, __fmaf_rn(x.r[8], p.x, __fmul_rn(x.r[9], p.y)))), p.w);
+}
+
 /* ---- AoS (reference 40-byte point) <-> SoA ----------------------------------------------------------- */
 __global__ void k_unpack_points(const m3dreg_point *__restrict__ in, int n, float4 *__restrict__ xyzl, float4 *__restrict__ nrm)
 {
@@ -179,7 +191,7 @@ __global__ void k_transform_soa(const float4 *__restrict__ in_xyzl, const float4
 		float x = __fadd_rn(t0, __fmaf_rn(r02, p.z, __fmaf_rn(r00, p.x, __fmul_rn(r01, p.y))));
 		float y = __fadd_rn(t1, __fmaf_rn(r12, p.z, __fmaf_rn(r10, p.x, __fmul_rn(r11, p.y))));
 		float z = __fadd_rn(t2, __fmaf_rn(r22, p.z, __fmaf_rn(r20, p.x, __fmul_rn(r21, p.y))));
-		out_xyzl[i] = make_float4(x, y, z, p.w);
+		if (out_xyzl) out_xyzl[i] = make_float4(x, y, z, p.w);      /* 0: bounding box only (the fused loop never stores the transformed cloud) */
 		if (out_nrm) {      /* the fused loop rotates only the candidates' normals (k_build_candidates), not all of them */
 			float4 q = __ldg(in_nrm + i);
 			float nx = __fmaf_rn(r02, q.z, __fmaf_rn(r00, q.x, __fmul_rn(r01, q.y)));
@@ -302,13 +314,17 @@ constexpr int kSortWarps = kSortThreads / 32;
  *     values are the implicit original indices and are not stored),
  *   - the first radix pass's per-tile digit histogram, and zeroing of the later passes' histograms. */
 template <int ITEMS>
-__global__ void __launch_bounds__(kSortThreads) k_grid_head(const float4 *__restrict__ xyzl, int n, const uint32_t *__restrict__ bounds,
+__global__ void __launch_bounds__(kSortThreads) k_grid_head(const float4 *__restrict__ xyzl, const float *__restrict__ pose, int n, const uint32_t *__restrict__ bounds,
 		float rx, float ry, float rz, float ext, long long bucket_cap, m3dreg_grid_params *__restrict__ gp_out, int *__restrict__ flags,
 		unsigned int *__restrict__ cell_count, m3dreg_bucket *__restrict__ buckets, uint32_t *__restrict__ keys,
 		int tiles, int passes, uint32_t *__restrict__ hist)
 {
 	pdl_enter();
 	__shared__ uint32_t sh[kRadixSize];
+	PointXform xf;      /* pose != 0: xyzl is the stored scan (local frame), transformed here exactly as the box pass did */
+	xf.on = pose != nullptr;
+#pragma unroll
+	for (int k = 0; k < 12; k++) xf.r[k] = xf.on ? __ldg(pose + k) : 0.0f;
 	m3dreg_grid_params g;
 	bool ok = grid_params_from_bounds_dev(bounds, rx, ry, rz, ext, bucket_cap, g);
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -337,7 +353,7 @@ __global__ void __launch_bounds__(kSortThreads) k_grid_head(const float4 *__rest
 		int i = base + j * kSortThreads + threadIdx.x;
 		int bin = -1;
 		if (i < n) {
-			float4 p = __ldg(xyzl + i);
+			float4 p = xform_point(xf, __ldg(xyzl + i));
 			int ix = cell_of(p.x, g.bounding_box_min_X, rx), iy = cell_of(p.y, g.bounding_box_min_Y, ry), iz = cell_of(p.z, g.bounding_box_min_Z, rz);
 			uint32_t k = (uint32_t)(ix * nby * nbz + iy * nbz + iz);
 			keys[i] = k;
@@ -667,18 +683,6 @@ struct NormalRotation { float r[9]; int on; };   /* rotation applied to the cand
 
 struct CellGeom { float mnx, mny, mnz, rx, ry, rz; int cx, cy, cz; };
 
-/* rigid transform applied to the gridded cloud's points on the fly (the grid megakernel never materialises the
- * transformed cloud): same operation sequence as k_transform_soa, so the bits equal the ones the keys were made from */
-struct PointXform { float r[12]; int on; };
-
-__device__ __forceinline__ float4 xform_point(const PointXform &x, const float4 &p)
-{
-	if (!x.on) return p;
-	return make_float4(__fadd_rn(x.r[3], __fmaf_rn(x.r[2], p.z, __fmaf_rn(x.r[0], p.x, __fmul_rn(x.r[1], p.y)))),
-			__fadd_rn(x.r[7], __fmaf_rn(x.r[6], p.z, __fmaf_rn(x.r[4], p.x, __fmul_rn(x.r[5], p.y)))),
-			__fadd_rn(x.r[11], __fmaf_rn(x.r[10], p.z, __fmaf_rn(x.r[8], p.x, __fmul_rn(x.r[9], p.y)))), p.w);
-}
-
 __device__ __forceinline__ void prefetch_l2(const void *p)
 {
 	asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
@@ -806,7 +810,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32, 7) k_build_candidates(const 
 		const m3dreg_grid_params *__restrict__ gp, const m3dreg_bucket *__restrict__ buckets,
 		const uint32_t *__restrict__ cell_list, const unsigned int *__restrict__ cell_count,
 		const float4 *__restrict__ src_xyzl, const float4 *__restrict__ src_nrm, const float4 *__restrict__ loc_src, const float *__restrict__ nrm_m,
-		int max_inner, int max_outer, CandSet ci, CandSet co, int two_sets)
+		int xform_points, int max_inner, int max_outer, CandSet ci, CandSet co, int two_sets)
 {
 	pdl_enter();
 	__shared__ uint32_t s_hist[kBuildWarps][kBuildTabMax + 7];
@@ -815,8 +819,10 @@ __global__ void __launch_bounds__(kBuildWarps * 32, 7) k_build_candidates(const 
 #pragma unroll
 	for (int k = 0; k < 9; k++) rot.r[k] = rot.on ? __ldg(nrm_m + (k / 3) * 4 + (k % 3)) : 0.0f;    /* row-major 4x4 */
 	if (gp->number_of_buckets <= 0) return;
-	PointXform xf;
-	xf.on = 0;
+	PointXform xf;      /* xform_points: src_xyzl is the stored scan (local frame) and nrm_m the pose: points are transformed on the fly */
+	xf.on = (xform_points && nrm_m) ? 1 : 0;
+#pragma unroll
+	for (int k = 0; k < 12; k++) xf.r[k] = xf.on ? __ldg(nrm_m + k) : 0.0f;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
 	CellGeom g;

@@ -303,20 +303,36 @@ def loop_trajectory(n_scans: int, spacing: float = 1.0, size=(25.0, 15.0), corne
 
 
 def slam_scans(n_scans: int, kind: str = "hdl32", seed: int = 42, spacing: float = 1.0,
-               drift_sigma_t: float = 0.05, drift_sigma_r: float = 0.01, **kw):
-    """Multi-scan data set (C4/C5): scans in their local frames, true poses, drifted initial poses."""
+               drift_sigma_t: float = 0.05, drift_sigma_r: float = 0.01, only=None, **kw):
+    """Multi-scan data set (C4/C5): scans in their local frames, true poses, drifted initial poses.
+    only: iterable of scan indices to generate (the others are None) — poses are always complete, so that the ranks of a
+    multi-GPU job can each generate a share of the scans and exchange them."""
     gen = {"hdl32": hdl32_scan, "sick": rotating_sick_scan}[kind]
     truth = loop_trajectory(n_scans, spacing)
     rng = np.random.Generator(np.random.PCG64(seed + 1000))
+    want = None if only is None else set(int(k) for k in only)
     scans, init = [], np.zeros((n_scans, 4, 4), dtype=np.float32)
     for k in range(n_scans):
-        scans.append(gen(truth[k], seed=seed + k, **kw))
+        scans.append(gen(truth[k], seed=seed + k, **kw) if (want is None or k in want) else None)
         dt = rng.normal(0, drift_sigma_t, 3)
         dr = rng.normal(0, drift_sigma_r, 3)
         yaw = math.atan2(truth[k][1, 0], truth[k][0, 0])
         init[k] = pose_matrix(truth[k][0, 3] + dt[0], truth[k][1, 3] + dt[1], truth[k][2, 3] + dt[2],
                               dr[0], dr[1], yaw + dr[2]).astype(np.float32)
     return scans, truth.astype(np.float32), init
+
+
+def relative_pose_error(poses, truth) -> float:
+    """Gauge-free trajectory error: mean translation error of the relative pose between consecutive scans (a sweep moves
+    every scan, so the absolute error against the truth also contains a rigid drift of the whole trajectory)."""
+    p = np.asarray(poses, dtype=np.float64).reshape(-1, 4, 4)
+    t = np.asarray(truth, dtype=np.float64).reshape(-1, 4, 4)
+    e = []
+    for k in range(len(p) - 1):
+        rel_e = np.linalg.inv(p[k]) @ p[k + 1]
+        rel_t = np.linalg.inv(t[k]) @ t[k + 1]
+        e.append(np.linalg.norm((np.linalg.inv(rel_t) @ rel_e)[:3, 3]))
+    return float(np.mean(e)) if e else 0.0
 
 
 def concat_points(scans) -> np.ndarray:
