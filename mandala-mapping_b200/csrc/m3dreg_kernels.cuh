@@ -186,22 +186,36 @@ __global__ void k_transform_soa(const float4 *__restrict__ in_xyzl, const float4
 	float r10 = __ldg(m + 4), r11 = __ldg(m + 5), r12 = __ldg(m + 6), t1 = __ldg(m + 7);
 	float r20 = __ldg(m + 8), r21 = __ldg(m + 9), r22 = __ldg(m + 10), t2 = __ldg(m + 11);
 	float mnx = INFINITY, mny = INFINITY, mnz = INFINITY, mxx = -INFINITY, mxy = -INFINITY, mxz = -INFINITY;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		float4 p = __ldg(in_xyzl + i);
-		float x = __fadd_rn(t0, __fmaf_rn(r02, p.z, __fmaf_rn(r00, p.x, __fmul_rn(r01, p.y))));
-		float y = __fadd_rn(t1, __fmaf_rn(r12, p.z, __fmaf_rn(r10, p.x, __fmul_rn(r11, p.y))));
-		float z = __fadd_rn(t2, __fmaf_rn(r22, p.z, __fmaf_rn(r20, p.x, __fmul_rn(r21, p.y))));
-		if (out_xyzl) out_xyzl[i] = make_float4(x, y, z, p.w);      /* 0: bounding box only (the fused loop never stores the transformed cloud) */
-		if (out_nrm) {      /* the fused loop rotates only the candidates' normals (k_build_candidates), not all of them */
-			float4 q = __ldg(in_nrm + i);
-			float nx = __fmaf_rn(r02, q.z, __fmaf_rn(r00, q.x, __fmul_rn(r01, q.y)));
-			float ny = __fmaf_rn(r12, q.z, __fmaf_rn(r10, q.x, __fmul_rn(r11, q.y)));
-			float nz = __fmaf_rn(r22, q.z, __fmaf_rn(r20, q.x, __fmul_rn(r21, q.y)));
-			out_nrm[i] = make_float4(nx, ny, nz, 0.0f);
+	/* four independent loads per thread in flight (one per trip measured 16 us for 16 MB: latency, not bandwidth) */
+	const int stride = gridDim.x * blockDim.x;
+	for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+		float4 pv[4], qv[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const int i = i0 + k * stride;
+			pv[k] = __ldg(in_xyzl + (i < n ? i : i0));
+			if (out_nrm) qv[k] = __ldg(in_nrm + (i < n ? i : i0));
 		}
-		if (WITH_BOUNDS) {
-			mnx = fminf(mnx, x); mny = fminf(mny, y); mnz = fminf(mnz, z);
-			mxx = fmaxf(mxx, x); mxy = fmaxf(mxy, y); mxz = fmaxf(mxz, z);
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const int i = i0 + k * stride;
+			if (i >= n) continue;
+			const float4 p = pv[k];
+			float x = __fadd_rn(t0, __fmaf_rn(r02, p.z, __fmaf_rn(r00, p.x, __fmul_rn(r01, p.y))));
+			float y = __fadd_rn(t1, __fmaf_rn(r12, p.z, __fmaf_rn(r10, p.x, __fmul_rn(r11, p.y))));
+			float z = __fadd_rn(t2, __fmaf_rn(r22, p.z, __fmaf_rn(r20, p.x, __fmul_rn(r21, p.y))));
+			if (out_xyzl) out_xyzl[i] = make_float4(x, y, z, p.w);      /* 0: bounding box only (the fused loop never stores the transformed cloud) */
+			if (out_nrm) {      /* the fused loop rotates only the candidates' normals (k_build_candidates), not all of them */
+				const float4 q = qv[k];
+				float nx = __fmaf_rn(r02, q.z, __fmaf_rn(r00, q.x, __fmul_rn(r01, q.y)));
+				float ny = __fmaf_rn(r12, q.z, __fmaf_rn(r10, q.x, __fmul_rn(r11, q.y)));
+				float nz = __fmaf_rn(r22, q.z, __fmaf_rn(r20, q.x, __fmul_rn(r21, q.y)));
+				out_nrm[i] = make_float4(nx, ny, nz, 0.0f);
+			}
+			if (WITH_BOUNDS) {
+				mnx = fminf(mnx, x); mny = fminf(mny, y); mnz = fminf(mnz, z);
+				mxx = fmaxf(mxx, x); mxy = fmaxf(mxy, y); mxz = fmaxf(mxz, z);
+			}
 		}
 	}
 	if (WITH_BOUNDS) block_bounds_commit(mnx, mny, mnz, mxx, mxy, mxz, bounds);
@@ -348,12 +362,19 @@ __global__ void __launch_bounds__(kSortThreads) k_grid_head(const float4 *__rest
 	const int nby = g.number_of_buckets_Y, nbz = g.number_of_buckets_Z;
 	const int lane = threadIdx.x & 31;
 	const int base = blockIdx.x * (kSortThreads * ITEMS);
+	/* all of the tile's loads first (ITEMS independent 16-byte loads per thread in flight), then the keys */
+	float4 pt[ITEMS];
+#pragma unroll
+	for (int j = 0; j < ITEMS; j++) {
+		const int i = base + j * kSortThreads + threadIdx.x;
+		pt[j] = __ldg(xyzl + (i < n ? i : 0));
+	}
 #pragma unroll
 	for (int j = 0; j < ITEMS; j++) {
 		int i = base + j * kSortThreads + threadIdx.x;
 		int bin = -1;
 		if (i < n) {
-			float4 p = xform_point(xf, __ldg(xyzl + i));
+			float4 p = xform_point(xf, pt[j]);
 			int ix = cell_of(p.x, g.bounding_box_min_X, rx), iy = cell_of(p.y, g.bounding_box_min_Y, ry), iz = cell_of(p.z, g.bounding_box_min_Z, rz);
 			uint32_t k = (uint32_t)(ix * nby * nbz + iy * nbz + iz);
 			keys[i] = k;
@@ -599,43 +620,59 @@ __global__ void k_finalize_grid(const uint32_t *__restrict__ keys, const uint32_
 	const int nround = (n + 31) & ~31;      /* whole warps stay together for the ballots below */
 	const uint32_t k0 = __ldg(keys), k1 = n > 1 ? __ldg(keys + 1) : k0;
 	const bool has_quirk = n > 1 && k0 != k1;
-	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
-		bool listed = false, valid = p < n;
-		uint32_t k = 0xFFFFFFFFu;
-		bool quirk = false;
-		if (valid) {
-			k = __ldg(keys + p);
-			if (table_out) {
-				m3dreg_hash_element h;
-				h.index_of_point = (int)__ldg(vals + p);
-				h.index_of_bucket = (int)k;
-				table_out[p] = h;
-			}
-			quirk = has_quirk && k == k1;
-			bool run_start = (p == 0) || (__ldg(keys + p - 1) != k);
-			bool run_end = (p == n - 1) || (__ldg(keys + p + 1) != k);
-			int *bp = reinterpret_cast<int *>(buckets + k);
-			if (run_start && !quirk) bp[0] = p;
-			if (run_end) { bp[1] = p + 1; listed = !quirk; }
+	const int stride = gridDim.x * blockDim.x;
+	for (int p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < nround; p0 += 4 * stride) {
+		/* four positions per trip: their key loads (and the neighbours') go out together */
+		uint32_t kc[4], kp[4], kn[4], vv[4];
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			const int p = p0 + u * stride;
+			const bool valid = p < n;
+			kc[u] = valid ? __ldg(keys + p) : 0xFFFFFFFFu;
+			kp[u] = (valid && p > 0) ? __ldg(keys + p - 1) : 0xFFFFFFFFu;
+			kn[u] = (valid && p < n - 1) ? __ldg(keys + p + 1) : 0xFFFFFFFFu;
+			vv[u] = (valid && table_out) ? __ldg(vals + p) : 0u;
 		}
-		{   /* number_of_points: one atomic per piece of a run inside this warp */
-			uint32_t prev = __shfl_up_sync(full, k, 1);
-			bool head = (lane == 0) || (prev != k);
-			unsigned heads = __ballot_sync(full, head);
-			if (head && valid && !quirk) {
-				unsigned later = heads & ~((2u << lane) - 1u);
-				int len = (later ? __ffs(later) - 1 : 32) - lane;
-				if (p + len > n) len = n - p;
-				atomicAdd(reinterpret_cast<int *>(buckets + k) + 2, len);
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			const int p = p0 + u * stride;
+			if (p >= nround) break;                    /* warp-uniform: nround and the strides are multiples of 32 */
+			bool listed = false, valid = p < n;
+			const uint32_t k = kc[u];
+			bool quirk = false;
+			if (valid) {
+				if (table_out) {
+					m3dreg_hash_element h;
+					h.index_of_point = (int)vv[u];
+					h.index_of_bucket = (int)k;
+					table_out[p] = h;
+				}
+				quirk = has_quirk && k == k1;
+				bool run_start = (p == 0) || (kp[u] != k);
+				bool run_end = (p == n - 1) || (kn[u] != k);
+				int *bp = reinterpret_cast<int *>(buckets + k);
+				if (run_start && !quirk) bp[0] = p;
+				if (run_end) { bp[1] = p + 1; listed = !quirk; }
 			}
-		}
-		if (cell_list) {   /* compact list of the searchable buckets (order irrelevant): one atomic per warp */
-			unsigned m = __ballot_sync(full, listed);
-			if (m) {
-				unsigned int base = 0;
-				if (lane == 0) base = atomicAdd(cell_count, (unsigned int)__popc(m));
-				base = __shfl_sync(full, base, 0);
-				if (listed) cell_list[base + __popc(m & ((1u << lane) - 1u))] = k;
+			{   /* number_of_points: one atomic per piece of a run inside this warp */
+				uint32_t prev = __shfl_up_sync(full, k, 1);
+				bool head = (lane == 0) || (prev != k);
+				unsigned heads = __ballot_sync(full, head);
+				if (head && valid && !quirk) {
+					unsigned later = heads & ~((2u << lane) - 1u);
+					int len = (later ? __ffs(later) - 1 : 32) - lane;
+					if (p + len > n) len = n - p;
+					atomicAdd(reinterpret_cast<int *>(buckets + k) + 2, len);
+				}
+			}
+			if (cell_list) {   /* compact list of the searchable buckets (order irrelevant): one atomic per warp */
+				unsigned m = __ballot_sync(full, listed);
+				if (m) {
+					unsigned int base = 0;
+					if (lane == 0) base = atomicAdd(cell_count, (unsigned int)__popc(m));
+					base = __shfl_sync(full, base, 0);
+					if (listed) cell_list[base + __popc(m & ((1u << lane) - 1u))] = k;
+				}
 			}
 		}
 	}
