@@ -153,13 +153,22 @@ def cpu_baseline(first, second, pose_init, pose2, res, dof, budget_s=20.0, max_i
 
 
 def run_reference(args, rank, world, out):
-    """Reference arm: the reference's own kernels driven the way cudaWrapper.cpp / gpu6DSLAM.cpp drive them."""
+    """Reference arm: the reference's own kernels driven the way cudaWrapper.cpp / gpu6DSLAM.cpp drive them.
+
+    The reference is single-threaded (one ROS spin loop, main.cpp:431-436), so its host glue — the per-iteration CPU
+    transform of both clouds (gpu6DSLAM.cpp:635-663), the label counting and observation assembly (gpu6DSLAM.cpp:323-398)
+    — runs on ONE thread here, whatever the box or the launcher.  The line carries a per-stage breakdown: host stages by
+    wall clock, the reference's device calls by wall clock around each call (every one of them ends in
+    cudaDeviceSynchronize or a blocking copy), so the kernel-versus-kernel ratios can be read off next to the whole-step
+    ratio."""
     if rank != 0:
         return
     pkg = importlib.import_module("mandala-mapping_b200")
+    import ctypes as C
     import oracle
     first, second, pose_init, pose2, _, res = make_pair(pkg, args.workload, args.seed)
-    n_pts = len(first) + len(second)
+    n1, n2 = len(first), len(second)
+    n_pts = n1 + n2
     dof = args.dof
     use_ref = oracle.ref_available()
     kind = "reference"
@@ -174,21 +183,37 @@ def run_reference(args, rank, world, out):
             use_ref = False
     if not use_ref:
         kind = "port"
+    threads_before = oracle.lib().orc_num_threads()
+    oracle.lib().orc_set_num_threads(1)
     prm = oracle.default_params(res, dof=dof)
     pose = pose_init.copy()
     weights = (10.0, 1.0, 10.0, 10.0)
+    host_ms = {"euler round trips + CPU transform of both clouds (gpu6DSLAM.cpp:276-307,635-663)": 0.0,
+               "label counts + observation assembly (gpu6DSLAM.cpp:323-398)": 0.0}
+    hk = list(host_ms)
+    nb_last = [0]
+    nc_last = [0]
 
-    def step(pose):
+    def step(pose, timed):
         # gpu6DSLAM.cpp:276-307: Euler round trips + CPU transform of BOTH clouds every iteration
+        t0 = time.perf_counter()
         o1, t1 = oracle.matrix4_to_euler(pose)
         p1 = oracle.euler_to_matrix(o1, t1)
         fg = oracle.transform_cloud(first, p1)
         sg = oracle.transform_cloud(second, oracle.euler_to_matrix(*oracle.matrix4_to_euler(pose2)))
+        t1c = time.perf_counter()
         if use_ref:
-            nn, *_ = refwrap.nn_search_host(fg, sg, res, res, 1.0, 100, 100, export=False)     # cudaWrapper.cpp:344-424
+            nn, gp, *_ = refwrap.nn_search_host(fg, sg, res, res, 1.0, 100, 100, export=False)     # cudaWrapper.cpp:344-424
         else:
-            nn, *_ = oracle.semantic_nn(fg, sg, res, res, 1.0, 100, 100)
+            nn, gp, *_ = oracle.semantic_nn(fg, sg, res, res, 1.0, 100, 100)
+        nb_last[0] = int(gp["number_of_buckets"][0])
+        t2 = time.perf_counter()
         obs = oracle.build_observations(fg, first, sg, nn, weights)                              # gpu6DSLAM.cpp:323-398
+        nc_last[0] = len(obs)
+        t3 = time.perf_counter()
+        if timed:
+            host_ms[hk[0]] += 1e3 * (t1c - t0)
+            host_ms[hk[1]] += 1e3 * (t3 - t2)
         pose6 = [t1[0], t1[1], t1[2], o1[0], o1[1], o1[2]]
         if len(obs) > 100:
             if use_ref:
@@ -203,24 +228,40 @@ def run_reference(args, rank, world, out):
     steps = args.steps if use_ref else min(args.steps, 3)
     warm = args.warmup if use_ref else min(args.warmup, 1)
     for _ in range(warm):
-        pose = step(pose)
+        pose = step(pose, False)
+    if use_ref:
+        oracle.ref().ref_get_stage_ms(None, None, C.c_int(1))
     t0 = time.perf_counter()
     for _ in range(steps):
-        pose = step(pose)
+        pose = step(pose, True)
     dt = time.perf_counter() - t0
+    stage_ms = {k: v / steps for k, v in host_ms.items()}
+    if use_ref:
+        ms = (C.c_double * 8)()
+        calls = (C.c_int * 2)()
+        oracle.ref().ref_get_stage_ms(ms, calls, C.c_int(1))
+        names = ["cudaMalloc + H2D of both 40-B clouds (cudaWrapper.cpp:360-372)", "cudaCalculateGridParams (lesson_16.cu:23-106)",
+                 "cudaMalloc x3 + cudaCalculateGrid (lesson_16.cu:200-243)", "cudaSemanticNearestNeighborSearch (lesson_16.cu:531-738)",
+                 "D2H of nn + cudaFree x5 (cudaWrapper.cpp:406-420)", "cudaMalloc x4 + H2D of the observations (cudaWrapper.cpp:523-536)",
+                 "fill_A_l_cuda (lesson_16.cu:355-439)", "Solve_ATPA_ATPl_x: AtP + 2x DGEMM + potrf/potrs + handles + frees (CCUDAAXBSolverWrapper.cpp:407-539)"]
+        for k in range(8):
+            stage_ms[names[k]] = ms[k] / steps
+    oracle.lib().orc_set_num_threads(threads_before)
     value = n_pts * steps / dt
-    cores = oracle.lib().orc_num_threads()
     line = {
         "impl": "reference", "metric": "points/sec per ICP iteration", "value": value, "unit": "points/s", "n_gpus": 1,
         "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 geometry / f64 normal equations", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][3], "mode": "icp", "dof": dof,
+        "config": {"workload": WORKLOADS[args.workload][3], "mode": "icp", "dof": dof, "n_first": n1, "n_second": n2,
+                   "buckets": nb_last[0], "correspondences": nc_last[0], "search_radius_m": res, "bucket_m": res, "max_inner": 100, "max_outer": 100,
+                   "l2_policy": "n/a (every device buffer is allocated, filled over PCIe and freed inside each call)", "parallelism": "pairs1",
                    "reference_path": ("verbatim reference CUDA kernels (lesson_16.cu, CCUDAAXBSolverWrapper.cpp compiled for sm_100a) through the "
-                                      "reference's per-call malloc/H2D/D2H/free pattern + its per-iteration CPU transform and observation assembly "
-                                      "(the reference has NO CPU implementation of this path)") if use_ref else
-                                     "CPU oracle port (reference kernels unavailable on this box)"},
-        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": kind,
-                         "sample": f"{steps} full iterations of the same pair, host glue on {cores} threads"},
+                                      "reference's per-call malloc/H2D/D2H/free pattern + its per-iteration CPU transform and observation assembly on ONE "
+                                      "host thread, as upstream (the reference has NO CPU implementation of this path)") if use_ref else
+                                     "CPU oracle port (reference kernels unavailable on this box), one thread"},
+        "stage_ms": stage_ms,
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": 1, "kind": kind,
+                         "sample": f"{steps} full iterations of the same pair, host glue on 1 thread (the reference is single-threaded)"},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), file=out, flush=True)

@@ -2054,17 +2054,19 @@ __global__ void k_zero_f64(double *p, int n)
  * coordinate SUM per bucket; the normal equations are then a reduction over buckets:
  *     N += cnt * A^T W A,   rhs += A^T W (cnt*mu_g - sum q),   A = -[I | J(mu_l)].
  * Layout: acc[b*12 ..] = {sum p'(3), sum p'p'^T(6), sum p_local(3)} -> finalised in place to
- *         {mu_g(3), mu_l(3), W(6: xx,xy,xz,yy,yz,zz)}; W.xx == 0 marks an unusable bucket.  qacc[b*4..] = {cnt, sum q(3)}. */
+ *         {mu_g(3), mu_l(3), W(6: xx,xy,xz,yy,yz,zz)}; W.xx == 0 marks an unusable bucket.
+ *         qacc[b*4..] = {cnt, sum (q - cell centre)(3) in 2^-40 m} as int64.
+ * Deterministic: the bucket statistics are reduced in a fixed order by one warp per bucket, the query sums are integers. */
 constexpr int kNdtMinPoints = 5;
 constexpr double kNdtRegRel = 0.05;
 
-__global__ void k_ndt_zero(double *__restrict__ acc, double *__restrict__ qacc, const m3dreg_grid_params *__restrict__ gp, int zero_acc)
+__global__ void k_ndt_zero(double *__restrict__ acc, long long *__restrict__ qacc, const m3dreg_grid_params *__restrict__ gp, int zero_acc)
 {
 	pdl_enter();
 	long long nb = gp->number_of_buckets;
 	long long total = nb * (zero_acc ? 16 : 4);
 	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-		if (i < nb * 4) qacc[i] = 0.0;
+		if (i < nb * 4) qacc[i] = 0;
 		else acc[i - nb * 4] = 0.0;
 	}
 }
@@ -2103,35 +2105,68 @@ __device__ __forceinline__ void warp_segmented_sum(uint32_t key, double (&v)[NV]
 	}
 }
 
-__global__ void __launch_bounds__(256) k_ndt_accumulate_points(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int n,
+/* forward declaration (defined below) */
+__device__ __host__ inline bool sym3_inverse(const double *S, double *W);
+
+/* Per-bucket statistics of the gridded cloud, ONE WARP PER SEARCHABLE BUCKET (the compact list the grid build left
+ * behind): lane l adds the bucket's sorted positions begin + l, begin + l + 32, ... in fp64 relative to the cell centre,
+ * a butterfly adds the lanes, lane 0 finalises (mean, covariance + eps I, inverse) in place.  No atomics: the result does
+ * not depend on scheduling (round 1 added run pieces with fp64 atomicAdd: not reproducible run to run).
+ * acc must be zero for every bucket on entry (k_ndt_zero): buckets that are not listed, or have fewer than
+ * kNdtMinPoints points, stay unusable (W.xx == 0). */
+__global__ void __launch_bounds__(256) k_ndt_bucket_stats(const uint32_t *__restrict__ vals, const m3dreg_bucket *__restrict__ buckets,
+		const uint32_t *__restrict__ cell_list, const unsigned int *__restrict__ cell_count,
 		const float4 *__restrict__ g_xyzl, const float4 *__restrict__ l_xyzl, const m3dreg_grid_params *__restrict__ gp,
 		double *__restrict__ acc)
 {
 	pdl_enter();
 	if (gp->number_of_buckets <= 0) return;
-	int nround = (n + 31) & ~31;
-	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
-		uint32_t key = 0xFFFFFFFFu;
+	const int lane = threadIdx.x & 31;
+	const unsigned int ncells = *cell_count, nwarps = gridDim.x * (blockDim.x >> 5);
+	const double res = (double)gp->resolution_X;
+	const double eps = (kNdtRegRel * res) * (kNdtRegRel * res);
+	for (unsigned int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < ncells; t += nwarps) {
+		const uint32_t cell = __ldg(cell_list + t);
+		const int *bp = reinterpret_cast<const int *>(buckets + cell);
+		const int begin = __ldg(bp), n = __ldg(bp + 2);
+		if (n < kNdtMinPoints || begin < 0) continue;      /* warp-uniform */
+		double cx, cy, cz;
+		cell_centre(cell, gp, cx, cy, cz);
 		double v[12];
 #pragma unroll
 		for (int i = 0; i < 12; i++) v[i] = 0.0;
-		if (p < n) {
-			key = __ldg(keys + p);
-			uint32_t idx = __ldg(vals + p);
-			float4 g = __ldg(g_xyzl + idx), l = __ldg(l_xyzl + idx);
-			double cx, cy, cz;
-			cell_centre(key, gp, cx, cy, cz);
-			double x = (double)g.x - cx, y = (double)g.y - cy, z = (double)g.z - cz;
-			v[0] = x; v[1] = y; v[2] = z;
-			v[3] = x * x; v[4] = x * y; v[5] = x * z; v[6] = y * y; v[7] = y * z; v[8] = z * z;
-			v[9] = l.x; v[10] = l.y; v[11] = l.z;
+		for (int k0 = lane; k0 < n; k0 += 64) {            /* two points per lane and trip in flight */
+			const int k1 = k0 + 32;
+			const uint32_t i0 = __ldg(vals + begin + k0), i1 = k1 < n ? __ldg(vals + begin + k1) : i0;
+			const float4 g0 = __ldg(g_xyzl + i0), l0 = __ldg(l_xyzl + i0), g1 = __ldg(g_xyzl + i1), l1 = __ldg(l_xyzl + i1);
+			{
+				const double x = (double)g0.x - cx, y = (double)g0.y - cy, z = (double)g0.z - cz;
+				v[0] += x; v[1] += y; v[2] += z;
+				v[3] += x * x; v[4] += x * y; v[5] += x * z; v[6] += y * y; v[7] += y * z; v[8] += z * z;
+				v[9] += l0.x; v[10] += l0.y; v[11] += l0.z;
+			}
+			if (k1 < n) {
+				const double x = (double)g1.x - cx, y = (double)g1.y - cy, z = (double)g1.z - cz;
+				v[0] += x; v[1] += y; v[2] += z;
+				v[3] += x * x; v[4] += x * y; v[5] += x * z; v[6] += y * y; v[7] += y * z; v[8] += z * z;
+				v[9] += l1.x; v[10] += l1.y; v[11] += l1.z;
+			}
 		}
-		bool head;
-		warp_segmented_sum<12>(key, v, head);
-		if (head && key != 0xFFFFFFFFu) {
-			double *a = acc + (size_t)key * 12;
 #pragma unroll
-			for (int i = 0; i < 12; i++) atomicAdd(a + i, v[i]);
+		for (int i = 0; i < 12; i++) v[i] = warp_sum(v[i]);
+		if (lane == 0) {
+			double *a = acc + (size_t)cell * 12;
+			const double inv = 1.0 / n, d = 1.0 / (n - 1);
+			const double m[3] = {v[0] * inv, v[1] * inv, v[2] * inv};
+			double S[6], W[6];
+			S[0] = (v[3] - n * m[0] * m[0]) * d + eps; S[1] = (v[4] - n * m[0] * m[1]) * d; S[2] = (v[5] - n * m[0] * m[2]) * d;
+			S[3] = (v[6] - n * m[1] * m[1]) * d + eps; S[4] = (v[7] - n * m[1] * m[2]) * d; S[5] = (v[8] - n * m[2] * m[2]) * d + eps;
+			if (sym3_inverse(S, W)) {
+				a[0] = m[0] + cx; a[1] = m[1] + cy; a[2] = m[2] + cz;
+				a[3] = v[9] * inv; a[4] = v[10] * inv; a[5] = v[11] * inv;
+#pragma unroll
+				for (int i = 0; i < 6; i++) a[6 + i] = W[i];
+			}
 		}
 	}
 }
@@ -2148,35 +2183,14 @@ __device__ __host__ inline bool sym3_inverse(const double *S, double *W)
 	return true;
 }
 
-__global__ void k_ndt_finalize_buckets(const m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp,
-		double *__restrict__ acc)
-{
-	pdl_enter();
-	long long nb = gp->number_of_buckets;
-	double res = (double)gp->resolution_X;
-	double eps = (kNdtRegRel * res) * (kNdtRegRel * res);
-	for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (long long)gridDim.x * blockDim.x) {
-		int n = buckets[b].number_of_points;
-		double *a = acc + (size_t)b * 12;
-		if (n < kNdtMinPoints) { a[6] = 0.0; continue; }
-		double s[3] = {a[0], a[1], a[2]}, ss[6] = {a[3], a[4], a[5], a[6], a[7], a[8]}, sl[3] = {a[9], a[10], a[11]};
-		double inv = 1.0 / n, d = 1.0 / (n - 1);
-		double m[3] = {s[0] * inv, s[1] * inv, s[2] * inv};
-		double S[6], W[6];
-		S[0] = (ss[0] - n * m[0] * m[0]) * d + eps; S[1] = (ss[1] - n * m[0] * m[1]) * d; S[2] = (ss[2] - n * m[0] * m[2]) * d;
-		S[3] = (ss[3] - n * m[1] * m[1]) * d + eps; S[4] = (ss[4] - n * m[1] * m[2]) * d; S[5] = (ss[5] - n * m[2] * m[2]) * d + eps;
-		if (!sym3_inverse(S, W)) { a[6] = 0.0; continue; }
-		double cx, cy, cz;
-		cell_centre((uint32_t)b, gp, cx, cy, cz);
-		a[0] = m[0] + cx; a[1] = m[1] + cy; a[2] = m[2] + cz;
-		a[3] = sl[0] * inv; a[4] = sl[1] * inv; a[5] = sl[2] * inv;
-#pragma unroll
-		for (int i = 0; i < 6; i++) a[6 + i] = W[i];
-	}
-}
+/* Queries per bucket: a count and the coordinate sum RELATIVE TO THE CELL CENTRE in 2^-40 m fixed point, added with
+ * 64-bit INTEGER atomics — integer addition is associative, so the sums do not depend on the order the warps arrive in
+ * (fp64 atomics did).  |q - centre| < 1.5 res per axis and at most 2^20 queries of a bucket fit 63 bits for res <= 4 m;
+ * the quantum (9e-13 m) is far below the float coordinates' own resolution.  qacc[b*4..] = {count, sx, sy, sz} as int64. */
+constexpr double kNdtFixScale = 1099511627776.0;      /* 2^40 */
 
 __global__ void __launch_bounds__(256) k_ndt_accumulate_queries(const float4 *__restrict__ q_xyzl, int n2,
-		const m3dreg_grid_params *__restrict__ gp, const double *__restrict__ acc, double *__restrict__ qacc)
+		const m3dreg_grid_params *__restrict__ gp, const double *__restrict__ acc, long long *__restrict__ qacc)
 {
 	pdl_enter();
 	long long nb = gp->number_of_buckets;
@@ -2185,9 +2199,11 @@ __global__ void __launch_bounds__(256) k_ndt_accumulate_queries(const float4 *__
 	float rx = gp->resolution_X, ry = gp->resolution_Y, rz = gp->resolution_Z;
 	int nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z;
 	int nround = (n2 + 31) & ~31;
+	const unsigned full = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
 		uint32_t key = 0xFFFFFFFFu;
-		double v[4] = {0.0, 0.0, 0.0, 0.0};
+		long long v[4] = {0, 0, 0, 0};
 		if (i < n2) {
 			float4 p = __ldg(q_xyzl + i);
 			bool inside = !(p.x < mnx || p.x > gp->bounding_box_max_X) && !(p.y < mny || p.y > gp->bounding_box_max_Y) &&
@@ -2196,21 +2212,39 @@ __global__ void __launch_bounds__(256) k_ndt_accumulate_queries(const float4 *__
 				int h = cell_of(p.x, mnx, rx) * nby * nbz + cell_of(p.y, mny, ry) * nbz + cell_of(p.z, mnz, rz);
 				if (h >= 0 && (long long)h < nb && __ldg(acc + (size_t)h * 12 + 6) > 0.0) {
 					key = (uint32_t)h;
-					v[0] = 1.0; v[1] = p.x; v[2] = p.y; v[3] = p.z;
+					double cx, cy, cz;
+					cell_centre(key, gp, cx, cy, cz);
+					v[0] = 1;
+					v[1] = __double2ll_rn(((double)p.x - cx) * kNdtFixScale);
+					v[2] = __double2ll_rn(((double)p.y - cy) * kNdtFixScale);
+					v[3] = __double2ll_rn(((double)p.z - cz) * kNdtFixScale);
 				}
 			}
 		}
-		bool head;
-		warp_segmented_sum<4>(key, v, head);
-		if (head && key != 0xFFFFFFFFu) {
-			double *a = qacc + (size_t)key * 4;
+		/* runs of equal keys inside the warp are added up first (integer: any order gives the same sum) */
+		uint32_t prev = __shfl_up_sync(full, key, 1);
+		bool is_head = (lane == 0) || (prev != key);
+		unsigned heads = __ballot_sync(full, is_head);
+		int seg = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
 #pragma unroll
-			for (int k = 0; k < 4; k++) atomicAdd(a + k, v[k]);
+		for (int o = 1; o < 32; o <<= 1) {
+			int s2 = __shfl_down_sync(full, seg, o);
+			bool take = (lane + o < 32) && (s2 == seg);
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				long long t = __shfl_down_sync(full, v[k], o);
+				if (take) v[k] += t;
+			}
+		}
+		if (is_head && key != 0xFFFFFFFFu) {
+			unsigned long long *a = reinterpret_cast<unsigned long long *>(qacc + (size_t)key * 4);
+#pragma unroll
+			for (int k = 0; k < 4; k++) atomicAdd(a + k, (unsigned long long)v[k]);
 		}
 	}
 }
 
-__global__ void __launch_bounds__(kNeqThreads) k_ndt_normal_equations(const double *__restrict__ acc, const double *__restrict__ qacc,
+__global__ void __launch_bounds__(kNeqThreads) k_ndt_normal_equations(const double *__restrict__ acc, const long long *__restrict__ qacc,
 		const m3dreg_grid_params *__restrict__ gp, double *__restrict__ partials, unsigned int *__restrict__ ticket, FinalizeArgs fin)
 {
 	pdl_enter();
@@ -2232,9 +2266,14 @@ __global__ void __launch_bounds__(kNeqThreads) k_ndt_normal_equations(const doub
 	for (int k = 0; k < kPartialCols; k++) sum[k] = 0.0;
 	for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (long long)gridDim.x * blockDim.x) {
 		const double *a = acc + (size_t)b * 12;
-		const double *qa = qacc + (size_t)b * 4;
-		double cnt = qa[0];
+		const long long *qa = qacc + (size_t)b * 4;
+		const double cnt = (double)qa[0];
 		if (!(a[6] > 0.0) || !(cnt > 0.0)) continue;
+		double ccx, ccy, ccz;
+		cell_centre((uint32_t)b, gp, ccx, ccy, ccz);
+		/* sum of the bucket's queries = count x centre + fixed-point sum of the offsets */
+		const double sqx = cnt * ccx + (double)qa[1] / kNdtFixScale, sqy = cnt * ccy + (double)qa[2] / kNdtFixScale,
+				sqz = cnt * ccz + (double)qa[3] / kNdtFixScale;
 		double A[3][6];
 #pragma unroll
 		for (int r = 0; r < 3; r++)
@@ -2244,7 +2283,7 @@ __global__ void __launch_bounds__(kNeqThreads) k_ndt_normal_equations(const doub
 				A[r][3 + c] = -(C[r][c][0] * a[3] + C[r][c][1] * a[4] + C[r][c][2] * a[5]);
 			}
 		double W[3][3] = {{a[6], a[7], a[8]}, {a[7], a[9], a[10]}, {a[8], a[10], a[11]}};
-		double sl[3] = {cnt * a[0] - qa[1], cnt * a[1] - qa[2], cnt * a[2] - qa[3]};
+		double sl[3] = {cnt * a[0] - sqx, cnt * a[1] - sqy, cnt * a[2] - sqz};
 		int k = 0;
 #pragma unroll
 		for (int i = 0; i < 6; i++) {

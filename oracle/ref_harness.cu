@@ -23,6 +23,25 @@
 
 typedef lidar_pointcloud::PointXYZIRNLRGB ref_point_t;
 
+/* Per-stage wall-clock of the reference's own call sequence (every reference function ends in cudaDeviceSynchronize or a
+ * blocking copy, so host time around a call IS its device time plus its malloc / launch overhead — what a caller pays):
+ *   0 malloc + H2D of both clouds        1 cudaCalculateGridParams      2 mallocs + cudaCalculateGrid
+ *   3 cudaSemanticNearestNeighborSearch  4 D2H of nn + frees            5 malloc + H2D of the observations
+ *   6 fill_A_l_cuda[_4DOF]               7 Solve_ATPA_ATPl_x (AtP, 2x DGEMM, potrf/potrs incl. handle creation) + frees */
+static double g_stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+static int g_stage_calls[2] = {0, 0};
+struct StageClock {
+	std::chrono::steady_clock::time_point t;
+	StageClock() : t(std::chrono::steady_clock::now()) {}
+	void lap(int stage)
+	{
+		cudaDeviceSynchronize();
+		auto n = std::chrono::steady_clock::now();
+		g_stage_ms[stage] += std::chrono::duration<double, std::milli>(n - t).count();
+		t = n;
+	}
+};
+
 #define REF_CHECK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { rc = (int)e__; goto done; } } while (0)
 
 static int ref_threads_for_device(int dev)
@@ -44,6 +63,14 @@ int ref_device_count(void)
 
 int ref_sizeof_point(void) { return (int)sizeof(ref_point_t); }
 int ref_sizeof_grid_params(void) { return (int)sizeof(gridParameters); }
+
+/* accumulated stage times (ms) since the last reset; calls_out[0] = NN calls, [1] = registerLS calls */
+void ref_get_stage_ms(double *ms_out, int *calls_out, int reset)
+{
+	for (int k = 0; k < 8; k++) { if (ms_out) ms_out[k] = g_stage_ms[k]; if (reset) g_stage_ms[k] = 0.0; }
+	if (calls_out) { calls_out[0] = g_stage_calls[0]; calls_out[1] = g_stage_calls[1]; }
+	if (reset) g_stage_calls[0] = g_stage_calls[1] = 0;
+}
 
 int ref_warm_up(int dev)
 {
@@ -73,18 +100,24 @@ int ref_nn_search_host(const void *first, int n1, const void *second, int n2,
 	memset(&p, 0, sizeof(p));
 	cudaGetDevice(&dev);
 	int threads = ref_threads_for_device(dev);
+	StageClock clk;
+	g_stage_calls[0]++;
 
 	REF_CHECK(cudaMalloc((void **)&d_first, (size_t)n1 * sizeof(ref_point_t)));
 	REF_CHECK(cudaMemcpy(d_first, first, (size_t)n1 * sizeof(ref_point_t), cudaMemcpyHostToDevice));
 	REF_CHECK(cudaMalloc((void **)&d_second, (size_t)n2 * sizeof(ref_point_t)));
 	REF_CHECK(cudaMemcpy(d_second, second, (size_t)n2 * sizeof(ref_point_t), cudaMemcpyHostToDevice));
+	clk.lap(0);
 	REF_CHECK(cudaCalculateGridParams(d_first, n1, bucket_size, bucket_size, bucket_size, bbox_extension, p));
+	clk.lap(1);
 	REF_CHECK(cudaMalloc((void **)&d_table, (size_t)n1 * sizeof(hashElement)));
 	REF_CHECK(cudaMalloc((void **)&d_buckets, (size_t)p.number_of_buckets * sizeof(bucket)));
 	REF_CHECK(cudaMalloc((void **)&d_nn, (size_t)n2 * sizeof(int)));
 	REF_CHECK(cudaCalculateGrid(threads, d_first, d_buckets, d_table, n1, p));
+	clk.lap(2);
 	REF_CHECK(cudaSemanticNearestNeighborSearch(threads, d_first, n1, d_second, n2, d_table, d_buckets, p,
 			search_radius, max_inner, max_outer, d_nn));
+	clk.lap(3);
 	REF_CHECK(cudaMemcpy(nn_out, d_nn, (size_t)n2 * sizeof(int), cudaMemcpyDeviceToHost));
 	if (params_out) memcpy(params_out, &p, sizeof(p));
 	if (table_out) REF_CHECK(cudaMemcpy(table_out, d_table, (size_t)n1 * sizeof(hashElement), cudaMemcpyDeviceToHost));
@@ -94,6 +127,7 @@ int ref_nn_search_host(const void *first, int n1, const void *second, int n2,
 	}
 done:
 	cudaFree(d_first); cudaFree(d_second); cudaFree(d_table); cudaFree(d_buckets); cudaFree(d_nn);
+	clk.lap(4);
 	return rc;
 }
 
@@ -191,15 +225,19 @@ int ref_register_ls_host(const void *obs, int n_obs, double *pose6, int dof, dou
 	cudaGetDevice(&dev);
 	int threads = ref_threads_for_device(dev);
 	if (dof != 6 && dof != 4) return -3;
+	StageClock clk;
+	g_stage_calls[1]++;
 	REF_CHECK(cudaMalloc((void **)&d_A, (size_t)n_obs * 3 * dof * sizeof(double)));
 	REF_CHECK(cudaMalloc((void **)&d_P, (size_t)n_obs * 3 * sizeof(double)));
 	REF_CHECK(cudaMalloc((void **)&d_l, (size_t)n_obs * 3 * sizeof(double)));
 	REF_CHECK(cudaMalloc((void **)&d_obs, (size_t)n_obs * sizeof(obs_nn_t)));
 	REF_CHECK(cudaMemcpy(d_obs, obs, (size_t)n_obs * sizeof(obs_nn_t), cudaMemcpyHostToDevice));
+	clk.lap(5);
 	if (dof == 6)
 		REF_CHECK(fill_A_l_cuda(threads, d_A, pose6[0], pose6[1], pose6[2], pose6[3], pose6[4], pose6[5], d_obs, n_obs, d_P, d_l));
 	else
 		REF_CHECK(fill_A_l_4DOFcuda(threads, d_A, pose6[0], pose6[1], pose6[2], pose6[3], pose6[4], pose6[5], d_obs, n_obs, d_P, d_l));
+	clk.lap(6);
 	{
 		CCUDA_AX_B_SolverWrapper *wr = new CCUDA_AX_B_SolverWrapper(false, dev);
 		CCUDA_AX_B_SolverWrapper::CCUDA_AX_B_SolverWrapper_error e =
@@ -215,6 +253,7 @@ int ref_register_ls_host(const void *obs, int n_obs, double *pose6, int dof, dou
 	if (x_out) memcpy(x_out, x, sizeof(double) * dof);
 done:
 	cudaFree(d_A); cudaFree(d_P); cudaFree(d_l); cudaFree(d_obs);
+	clk.lap(7);
 	return rc;
 }
 

@@ -75,3 +75,41 @@ def test_ndt_sweep_matches_oracle(pkg, oracle, ctx, synth):
     assert (np.abs(neq_d[:, :27] - neq_o[:, :27]) <= 1e-9 * scale).all()
     assert np.array_equal(status_d, status_o)
     assert np.abs(poses_d - poses_o).max() < 1e-6
+
+
+def test_ndt_matches_independent_numpy_fixture(pkg, ctx, synth):
+    """The CUDA NDT path against the numpy / scipy statement of the definition (tests/golden/ndt/make_ndt_golden.py), which
+    shares no code with the kernels or the oracle: normal equations of one fused iteration and its solution."""
+    import os
+    import torch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ndt", "ndt_planes.npz"))
+
+    def pts(xyz):
+        p = np.zeros(len(xyz), dtype=synth.POINT_DTYPE)
+        p["x"], p["y"], p["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+        p["normal_z"] = 1.0
+        return p
+    ctx.scan_clear()
+    ctx.scan_upload(0, pts(g["local"]))
+    ctx.scan_upload(1, pts(g["queries"]))
+    p6 = g["pose6"]
+    pose = pkg.euler_to_matrix(np.float32(p6[3:]), np.float32(p6[:3])).reshape(4, 4)
+    prm = pkg.default_params(float(g["res"]), dof=6, mode=pkg.MODE_NDT)
+    ctx.icp_begin(0, 1, pose, np.eye(4, dtype=np.float32), prm)
+    ctx.icp_step(1)
+    d = torch.zeros(28, dtype=torch.float64, device="cuda")
+    ctx.icp_copy_neq(d)
+    _, st = ctx.icp_end()
+    neq = d.cpu().numpy()
+    assert st.last_status == 0 and int(neq[27]) == int(g["n_obs"]) == st.n_obs_last
+    scale = np.abs(g["neq28"][:27]).max()
+    # float32 pose (Euler angles rounded to float, matrix entries rounded to float): ~1e-7 relative on the angle-dependent entries
+    assert (np.abs(neq[:27] - g["neq28"][:27]) <= 2e-5 * scale).all(), np.abs(neq[:27] - g["neq28"][:27]).max() / scale
+    assert np.allclose(np.array(st.x_last), g["x"], rtol=2e-3, atol=2e-6)
+    # deterministic: a second run gives the same bits (bucket statistics reduced in a fixed order, integer query sums)
+    ctx.icp_begin(0, 1, pose, np.eye(4, dtype=np.float32), prm)
+    ctx.icp_step(1)
+    d2 = torch.zeros(28, dtype=torch.float64, device="cuda")
+    ctx.icp_copy_neq(d2)
+    ctx.icp_end()
+    assert np.array_equal(d2.cpu().numpy(), neq)

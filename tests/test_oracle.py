@@ -326,3 +326,26 @@ def test_ndt_converges(oracle, synth):
     assert np.abs(pose[:3, 3] - p_true[:3, 3]).max() < 5e-3
     o, _ = oracle.matrix4_to_euler(pose)
     assert np.abs(o).max() < 2e-3
+
+
+def _points_from_xyz(synth, xyz):
+    pts = np.zeros(len(xyz), dtype=synth.POINT_DTYPE)
+    pts["x"], pts["y"], pts["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    pts["normal_z"] = 1.0
+    return pts
+
+
+def test_ndt_oracle_matches_independent_numpy_fixture(oracle, synth):
+    """NDT has no reference implementation; tests/golden/ndt/make_ndt_golden.py states its definition a third time with numpy
+    / scipy library routines only (np.cov, np.linalg.inv, scipy Rotation, finite-difference Jacobian).  The oracle must
+    reproduce that fixture, so that oracle and CUDA kernels are not only checked against each other."""
+    g = np.load(os.path.join(HERE, "golden", "ndt", "ndt_planes.npz"))
+    fg, fl, q = _points_from_xyz(synth, g["glob"]), _points_from_xyz(synth, g["local"]), _points_from_xyz(synth, g["queries"])
+    gp = oracle.grid_params(fg, float(g["res"]), ext=float(g["ext"]))
+    buckets, table = oracle.build_grid(fg, gp)
+    _, neq = oracle.ndt_normal_equations(fg, fl, q, table, buckets, gp, g["pose6"])
+    assert int(neq[27]) == int(g["n_obs"])
+    scale = np.abs(g["neq28"][:27]).max()
+    assert (np.abs(neq[:27] - g["neq28"][:27]) <= 1e-7 * scale).all()      # finite-difference Jacobian in the fixture: ~1e-9
+    st, x = oracle.solve_packed(neq, 6)
+    assert st == 0 and np.allclose(x, g["x"], rtol=1e-6, atol=1e-10)
