@@ -12,7 +12,16 @@
  * m3dreg::Affine3f / Vector3f below are minimal stand-ins used by this repository's own tests.
  *
  * Beyond the reference surface the shim exposes the device-resident fused loop (registerPair / scan store), which is
- * what a patched gpu6DSLAM::registerLastArrivedScan calls instead of one NN + one registerLS call per iteration.
+ * what a patched gpu6DSLAM::registerLastArrivedScan calls instead of one NN + one registerLS call per iteration, and the
+ * multi-GPU Jacobi sweep (registerAll -> m3dreg_slam_sweep).
+ *
+ * Two ways to use it:
+ *   - alone, as `class CCudaWrapper` (default), in a harness that only needs the registration surface;
+ *   - NEXT TO the reference's own cudaWrapper.h — whose CCudaWrapper also carries the pre-registration methods
+ *     removeNoiseNaive / downsampling / classify / findBestYaw (src/gpu6DSLAM.cpp:63,71,75,137,756) that are not on this
+ *     path — by compiling with -DM3DREG_SHIM_CLASS=CM3dRegWrapper -DM3DREG_SHIM_NO_OBSERVATIONS: the class then has its own
+ *     name and the header does not redefine observations_t; its template methods accept the reference's observations_t
+ *     and obs_nn_t as they are (same field names, 28-byte layout checked at compile time).
  */
 #ifndef M3DREG_CUDA_WRAPPER_SHIM_HPP_
 #define M3DREG_CUDA_WRAPPER_SHIM_HPP_
@@ -65,15 +74,21 @@ struct observations_tmpl {
 	Affine m_pose;
 	double om = 0, fi = 0, ka = 0, tx = 0, ty = 0, tz = 0;
 };
+#ifndef M3DREG_SHIM_NO_OBSERVATIONS
 typedef observations_tmpl<> observations_t;
+#endif
 
-class CCudaWrapper {
+#ifndef M3DREG_SHIM_CLASS
+#define M3DREG_SHIM_CLASS CCudaWrapper
+#endif
+
+class M3DREG_SHIM_CLASS {
 public:
 	/* ref: src/cudaWrapper.cpp:4-18 — the context is created lazily by warmUpGPU, like the reference picks its device there */
-	CCudaWrapper() : threads(0), threadsNV(0), cuda_device(0), ctx_(nullptr) {}
-	~CCudaWrapper() { if (ctx_) m3dreg_destroy(ctx_); }
-	CCudaWrapper(const CCudaWrapper &) = delete;
-	CCudaWrapper &operator=(const CCudaWrapper &) = delete;
+	M3DREG_SHIM_CLASS() : threads(0), threadsNV(0), cuda_device(0), ctx_(nullptr) {}
+	~M3DREG_SHIM_CLASS() { if (ctx_) m3dreg_destroy(ctx_); }
+	M3DREG_SHIM_CLASS(const M3DREG_SHIM_CLASS &) = delete;
+	M3DREG_SHIM_CLASS &operator=(const M3DREG_SHIM_CLASS &) = delete;
 
 	/* ref: src/cudaWrapper.cpp:36-44 */
 	void warmUpGPU(int cudaDevice)
@@ -175,6 +190,40 @@ public:
 		throw_on_cuda_error(st, __FILE__, __LINE__);
 		for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) pose_first(r, c) = a[r * 4 + c];
 		return (stats ? stats : &local)->last_status == 0;
+	}
+
+	/* ref: gpu6DSLAM::registerAll(cudaWrapper, radius, bucket, number_of_last_EOZ) (src/gpu6DSLAM.cpp:424-597) as ONE call:
+	 * scans 0..poses.size()-1 must have been uploaded (uploadScan); the poses (any container of Affine) are updated in
+	 * place.  With a communicator attached (attachNccl, one wrapper per GPU / rank, the same poses on every rank) the
+	 * pairs are sharded over the ranks and the normal-equation blocks all-reduced inside the library. */
+	template <class AffineVec>
+	int registerAll(AffineVec &poses, const m3dreg_reg_params &params, float distance_threshold, size_t number_of_last_EOZ,
+			std::vector<int> *status = nullptr, m3dreg_sweep_stats *stats = nullptr)
+	{
+		const int n = (int)poses.size();
+		if (n == 0 || (size_t)n < number_of_last_EOZ) return 0;                    /* ref: src/gpu6DSLAM.cpp:428 */
+		std::vector<float> flat((size_t)n * 16);
+		for (int k = 0; k < n; k++)
+			for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++)
+				flat[(size_t)k * 16 + r * 4 + c] = (r < 3) ? poses[k](r, c) : (c == 3 ? 1.0f : 0.0f);
+		m3dreg_slam_params sp;
+		sp.reg = params;
+		sp.distance_threshold = distance_threshold;
+		sp.first_optimised = n - (int)number_of_last_EOZ;
+		std::vector<int> st_local((size_t)n, 0);
+		int st = m3dreg_slam_sweep(context(), n, flat.data(), &sp, st_local.data(), stats);
+		throw_on_cuda_error(st, __FILE__, __LINE__);
+		for (int k = 0; k < n; k++)
+			for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) poses[k](r, c) = flat[(size_t)k * 16 + r * 4 + c];
+		int solved = 0;
+		for (int k = sp.first_optimised; k < n; k++) solved += st_local[(size_t)k] == 0 ? 1 : 0;
+		if (status) *status = st_local;
+		return solved;
+	}
+	/* existing ncclComm_t of the host application (or 0 / world 1 to detach); see also m3dreg_nccl_init */
+	void attachNccl(void *nccl_comm, int rank, int world)
+	{
+		throw_on_cuda_error(m3dreg_nccl_attach(context(), nccl_comm, rank, world), __FILE__, __LINE__);
 	}
 
 	m3dreg_ctx *context()

@@ -121,6 +121,8 @@ struct m3dreg_ctx {
 	DevBuf<m3dreg_obs_nn> obs;
 	DevBuf<double> partials, ndt_acc;
 	DevBuf<long long> ndt_qacc;                      /* per bucket {count, fixed-point coordinate sums} of the NDT query pass */
+	DevBuf<long long> ndt_iacc;                      /* per bucket 12 fixed-point sums of the gridded cloud (NDT statistics) */
+	float act_local_mag = 1.0f;                      /* largest |coordinate| of the gridded scan in its local frame (NDT fixed-point scale) */
 	DevBuf<m3dreg_hash_element> table;
 	DevBuf<float> d_poses1;      /* sweep: round-tripped poses, 16 floats per scan */
 	DevBuf<double> d_pose6;      /* sweep: tx,ty,tz,om,fi,ka per scan             */
@@ -341,6 +343,7 @@ int ensure_buckets(m3dreg_ctx *c, size_t cap, bool ndt)
 	if (ndt) {
 		if ((e = c->ndt_acc.ensure(c->buckets.cap * 12))) return e;
 		if ((e = c->ndt_qacc.ensure(c->buckets.cap * 4))) return e;
+		if ((e = c->ndt_iacc.ensure(c->buckets.cap * 12))) return e;
 	}
 	return 0;
 }
@@ -641,17 +644,32 @@ bool valid_params(const m3dreg_reg_params *p)
 }
 
 /* NDT: per-bucket statistics of the gridded cloud (once per grid) and the query pass + bucket reduction (per pair). */
-void ndt_bucket_stats(m3dreg_ctx *c, const float4 *lx, int n1)
+/* fixed-point scales: |p - centre| <= res / 2 (+ rounding), |local| <= local_mag; up to 2^22 points per bucket */
+NdtScales ndt_scales(float res, float local_mag)
 {
-	(void)n1;
+	double p = 1.0;
+	while (p * 4.0 < (double)res) p *= 2.0;
+	double q = 1.0;
+	while (q < (double)local_mag) q *= 2.0;
+	NdtScales sc;
+	sc.s1 = 274877906944.0 / p;            /* 2^38 / p        */
+	sc.s2 = 274877906944.0 / (p * p);
+	sc.sl = 549755813888.0 / q;            /* 2^39 / q        */
+	return sc;
+}
+
+void ndt_bucket_stats(m3dreg_ctx *c, const float4 *lx, int n1, const m3dreg_reg_params *prm, float local_mag)
+{
 	int cur = c->last_sorted;
-	LAUNCH(c, k_ndt_zero, grid_for(c, (long long)c->buckets.cap * 16, 256), 256, c->ndt_acc.p, c->ndt_qacc.p, c->gp, 1);
-	LAUNCH(c, k_ndt_bucket_stats, c->sm_count * 8, 256, c->vals[cur].p, c->buckets.p, c->cell_list.p, c->cell_count, c->g_xyzl.p, lx, c->gp, c->ndt_acc.p);
+	const NdtScales sc = ndt_scales(prm->bucket_size, local_mag);
+	LAUNCH(c, k_ndt_zero, grid_for(c, (long long)c->buckets.cap * 16, 256), 256, c->ndt_iacc.p, c->ndt_qacc.p, c->gp, 1);
+	LAUNCH(c, k_ndt_accumulate_points, grid_for(c, n1, 256), 256, c->keys[cur].p, c->vals[cur].p, n1, c->g_xyzl.p, lx, c->gp, c->ndt_iacc.p, sc);
+	LAUNCH(c, k_ndt_finalize_buckets, grid_for(c, (long long)c->buckets.cap, 256), 256, c->buckets.p, c->gp, c->ndt_iacc.p, c->ndt_acc.p, sc);
 }
 
 void ndt_queries_and_reduce(m3dreg_ctx *c, int n2, const FinalizeArgs &fin, bool zero_qacc)
 {
-	if (zero_qacc) LAUNCH(c, k_ndt_zero, grid_for(c, (long long)c->buckets.cap * 4, 256), 256, c->ndt_acc.p, c->ndt_qacc.p, c->gp, 0);
+	if (zero_qacc) LAUNCH(c, k_ndt_zero, grid_for(c, (long long)c->buckets.cap * 4, 256), 256, c->ndt_iacc.p, c->ndt_qacc.p, c->gp, 0);
 	LAUNCH(c, k_ndt_accumulate_queries, grid_for(c, n2, 256), 256, c->q_xyzl.p, n2, c->gp, c->ndt_acc.p, c->ndt_qacc.p);
 	LAUNCH(c, k_ndt_normal_equations, grid_for(c, (long long)c->buckets.cap, kNeqThreads, 2), kNeqThreads, c->ndt_acc.p, c->ndt_qacc.p, c->gp,
 			c->partials.p, c->ticket, fin);
@@ -699,7 +717,7 @@ void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int
 	fin.ps = c->ps; fin.neq_out = c->neq_out_ext; fin.accumulate = 0; fin.solve = 1; fin.dof = prm->dof;
 	fin.obs_threshold = prm->obs_threshold; fin.pose6_in = nullptr; fin.bounds_reset = c->bounds;
 	if (ndt) {
-		ndt_bucket_stats(c, lx, n1);
+		ndt_bucket_stats(c, lx, n1, prm, c->act_local_mag);
 		if (prof) { cudaEventRecord(c->pev[2], c->stream); cudaEventRecord(c->pev[3], c->stream); }
 		fin.label_counts_reset = nullptr;
 		ndt_queries_and_reduce(c, n2, fin, false);
@@ -834,7 +852,7 @@ void m3dreg_destroy(m3dreg_ctx *c)
 	c->q_xyzl.release(); c->q_nrm.release(); c->l_xyzl.release(); c->l_nrm.release();
 	for (int k = 0; k < 2; k++) { c->keys[k].release(); c->vals[k].release(); }
 	c->hist.release(); c->buckets.release(); c->nn.release(); c->obs_rec.release(); c->cell_list.release(); c->aos_a.release(); c->aos_b.release();
-	c->obs.release(); c->partials.release(); c->ndt_acc.release(); c->ndt_qacc.release(); c->table.release(); c->d_poses1.release(); c->d_pose6.release(); c->d_sweep_status.release();
+	c->obs.release(); c->partials.release(); c->ndt_acc.release(); c->ndt_qacc.release(); c->ndt_iacc.release(); c->table.release(); c->d_poses1.release(); c->d_pose6.release(); c->d_sweep_status.release();
 	c->d_segs.release(); c->d_seg_of_chunk.release(); c->d_seg_counts.release();
 	if (c->h_sweep) cudaFreeHost(c->h_sweep);
 	if (c->ps) cudaFree(c->ps);   /* base of the small block */
@@ -1227,6 +1245,8 @@ static int icp_begin_internal(m3dreg_ctx *c, const float4 *lx, const float4 *ln,
 	 * axis for the pose changes of the loop. */
 	if ((e = ensure_buckets(c, (size_t)bucket_capacity_for(box.diag, prm), prm->mode == M3DREG_MODE_NDT))) return e;
 	const int sort_bits = planned_sort_bits(box.mn, box.mx, pose_first, prm, 4);
+	c->act_local_mag = 1.0f;
+	for (int k = 0; k < 3; k++) c->act_local_mag = fmaxf(c->act_local_mag, fmaxf(fabsf(box.mn[k]), fabsf(box.mx[k])));
 	LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
 	c->act_lx = lx; c->act_ln = ln; c->act_n1 = n1; c->act_n2 = n2; c->act_sort_bits = sort_bits; c->act_prm = *prm;
 	c->active = true;
@@ -1551,7 +1571,11 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 			} else {
 				build_grid_mega(c, A.xyzl, A.nrm, A.n, pose_i, prm, ndt);
 			}
-			if (ndt) ndt_bucket_stats(c, A.xyzl, A.n);
+			if (ndt) {
+				float mag = 1.0f;
+				for (int k = 0; k < 3; k++) mag = fmaxf(mag, fmaxf(fabsf(A.bb_min[k]), fabsf(A.bb_max[k])));
+				ndt_bucket_stats(c, A.xyzl, A.n, prm, mag);
+			}
 			cur_i = i;
 		}
 		FinalizeArgs fin = {};

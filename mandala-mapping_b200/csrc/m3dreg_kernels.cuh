@@ -2053,21 +2053,21 @@ __global__ void k_zero_f64(double *p, int n)
  * All queries that fall into a bucket share its (mu, W, Jacobian), so the query pass only needs a COUNT and a
  * coordinate SUM per bucket; the normal equations are then a reduction over buckets:
  *     N += cnt * A^T W A,   rhs += A^T W (cnt*mu_g - sum q),   A = -[I | J(mu_l)].
- * Layout: acc[b*12 ..] = {sum p'(3), sum p'p'^T(6), sum p_local(3)} -> finalised in place to
- *         {mu_g(3), mu_l(3), W(6: xx,xy,xz,yy,yz,zz)}; W.xx == 0 marks an unusable bucket.
+ * Layout: iacc[b*12 ..] = {sum p'(3), sum p'p'^T(6), sum p_local(3)} as fixed-point int64 -> finalised into
+ *         acc[b*12 ..] = {mu_g(3), mu_l(3), W(6: xx,xy,xz,yy,yz,zz)}; W.xx == 0 marks an unusable bucket.
  *         qacc[b*4..] = {cnt, sum (q - cell centre)(3) in 2^-40 m} as int64.
- * Deterministic: the bucket statistics are reduced in a fixed order by one warp per bucket, the query sums are integers. */
+ * Deterministic: every sum that is accumulated with atomics is an INTEGER. */
 constexpr int kNdtMinPoints = 5;
 constexpr double kNdtRegRel = 0.05;
 
-__global__ void k_ndt_zero(double *__restrict__ acc, long long *__restrict__ qacc, const m3dreg_grid_params *__restrict__ gp, int zero_acc)
+__global__ void k_ndt_zero(long long *__restrict__ iacc, long long *__restrict__ qacc, const m3dreg_grid_params *__restrict__ gp, int zero_acc)
 {
 	pdl_enter();
 	long long nb = gp->number_of_buckets;
 	long long total = nb * (zero_acc ? 16 : 4);
 	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
 		if (i < nb * 4) qacc[i] = 0;
-		else acc[i - nb * 4] = 0.0;
+		else iacc[i - nb * 4] = 0;
 	}
 }
 
@@ -2105,68 +2105,60 @@ __device__ __forceinline__ void warp_segmented_sum(uint32_t key, double (&v)[NV]
 	}
 }
 
-/* forward declaration (defined below) */
-__device__ __host__ inline bool sym3_inverse(const double *S, double *W);
+/* Fixed-point scales of the NDT sums (chosen on the host so that 2^22 points of one bucket cannot overflow 63 bits):
+ * s1 for coordinates relative to the cell centre, s2 for their products, sl for local coordinates. */
+struct NdtScales { double s1, s2, sl; };
 
-/* Per-bucket statistics of the gridded cloud, ONE WARP PER SEARCHABLE BUCKET (the compact list the grid build left
- * behind): lane l adds the bucket's sorted positions begin + l, begin + l + 32, ... in fp64 relative to the cell centre,
- * a butterfly adds the lanes, lane 0 finalises (mean, covariance + eps I, inverse) in place.  No atomics: the result does
- * not depend on scheduling (round 1 added run pieces with fp64 atomicAdd: not reproducible run to run).
- * acc must be zero for every bucket on entry (k_ndt_zero): buckets that are not listed, or have fewer than
- * kNdtMinPoints points, stay unusable (W.xx == 0). */
-__global__ void __launch_bounds__(256) k_ndt_bucket_stats(const uint32_t *__restrict__ vals, const m3dreg_bucket *__restrict__ buckets,
-		const uint32_t *__restrict__ cell_list, const unsigned int *__restrict__ cell_count,
+/* Per-bucket sums of the gridded cloud, one thread per SORTED position: coordinates relative to the cell centre, their
+ * products and the local coordinates as 64-bit FIXED-POINT integers; runs of equal keys inside a warp are added with
+ * shuffles, one integer atomic per run piece and sum.  Integer addition is associative: the sums — hence everything
+ * downstream — do not depend on scheduling (round 1 used fp64 atomicAdd: not reproducible run to run), and the work is
+ * spread evenly whatever the bucket sizes (a warp per bucket took 700 us on the 1 M-point scan: one bucket near the
+ * sensor holds 20 000 points).  iacc[b*12..] = {sum p'(3), sum p'p'^T(6), sum p_local(3)}. */
+__global__ void __launch_bounds__(256) k_ndt_accumulate_points(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int n,
 		const float4 *__restrict__ g_xyzl, const float4 *__restrict__ l_xyzl, const m3dreg_grid_params *__restrict__ gp,
-		double *__restrict__ acc)
+		long long *__restrict__ iacc, NdtScales sc)
 {
 	pdl_enter();
 	if (gp->number_of_buckets <= 0) return;
+	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
-	const unsigned int ncells = *cell_count, nwarps = gridDim.x * (blockDim.x >> 5);
-	const double res = (double)gp->resolution_X;
-	const double eps = (kNdtRegRel * res) * (kNdtRegRel * res);
-	for (unsigned int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < ncells; t += nwarps) {
-		const uint32_t cell = __ldg(cell_list + t);
-		const int *bp = reinterpret_cast<const int *>(buckets + cell);
-		const int begin = __ldg(bp), n = __ldg(bp + 2);
-		if (n < kNdtMinPoints || begin < 0) continue;      /* warp-uniform */
-		double cx, cy, cz;
-		cell_centre(cell, gp, cx, cy, cz);
-		double v[12];
+	int nround = (n + 31) & ~31;
+	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
+		uint32_t key = 0xFFFFFFFFu;
+		long long v[12];
 #pragma unroll
-		for (int i = 0; i < 12; i++) v[i] = 0.0;
-		for (int k0 = lane; k0 < n; k0 += 64) {            /* two points per lane and trip in flight */
-			const int k1 = k0 + 32;
-			const uint32_t i0 = __ldg(vals + begin + k0), i1 = k1 < n ? __ldg(vals + begin + k1) : i0;
-			const float4 g0 = __ldg(g_xyzl + i0), l0 = __ldg(l_xyzl + i0), g1 = __ldg(g_xyzl + i1), l1 = __ldg(l_xyzl + i1);
-			{
-				const double x = (double)g0.x - cx, y = (double)g0.y - cy, z = (double)g0.z - cz;
-				v[0] += x; v[1] += y; v[2] += z;
-				v[3] += x * x; v[4] += x * y; v[5] += x * z; v[6] += y * y; v[7] += y * z; v[8] += z * z;
-				v[9] += l0.x; v[10] += l0.y; v[11] += l0.z;
-			}
-			if (k1 < n) {
-				const double x = (double)g1.x - cx, y = (double)g1.y - cy, z = (double)g1.z - cz;
-				v[0] += x; v[1] += y; v[2] += z;
-				v[3] += x * x; v[4] += x * y; v[5] += x * z; v[6] += y * y; v[7] += y * z; v[8] += z * z;
-				v[9] += l1.x; v[10] += l1.y; v[11] += l1.z;
+		for (int i = 0; i < 12; i++) v[i] = 0;
+		if (p < n) {
+			key = __ldg(keys + p);
+			uint32_t idx = __ldg(vals + p);
+			float4 g = __ldg(g_xyzl + idx), l = __ldg(l_xyzl + idx);
+			double cx, cy, cz;
+			cell_centre(key, gp, cx, cy, cz);
+			double x = (double)g.x - cx, y = (double)g.y - cy, z = (double)g.z - cz;
+			v[0] = __double2ll_rn(x * sc.s1); v[1] = __double2ll_rn(y * sc.s1); v[2] = __double2ll_rn(z * sc.s1);
+			v[3] = __double2ll_rn(x * x * sc.s2); v[4] = __double2ll_rn(x * y * sc.s2); v[5] = __double2ll_rn(x * z * sc.s2);
+			v[6] = __double2ll_rn(y * y * sc.s2); v[7] = __double2ll_rn(y * z * sc.s2); v[8] = __double2ll_rn(z * z * sc.s2);
+			v[9] = __double2ll_rn((double)l.x * sc.sl); v[10] = __double2ll_rn((double)l.y * sc.sl); v[11] = __double2ll_rn((double)l.z * sc.sl);
+		}
+		uint32_t prev = __shfl_up_sync(full, key, 1);
+		bool is_head = (lane == 0) || (prev != key);
+		unsigned heads = __ballot_sync(full, is_head);
+		int seg = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			int s2 = __shfl_down_sync(full, seg, o);
+			bool take = (lane + o < 32) && (s2 == seg);
+#pragma unroll
+			for (int i = 0; i < 12; i++) {
+				long long t = __shfl_down_sync(full, v[i], o);
+				if (take) v[i] += t;
 			}
 		}
+		if (is_head && key != 0xFFFFFFFFu) {
+			unsigned long long *a = reinterpret_cast<unsigned long long *>(iacc + (size_t)key * 12);
 #pragma unroll
-		for (int i = 0; i < 12; i++) v[i] = warp_sum(v[i]);
-		if (lane == 0) {
-			double *a = acc + (size_t)cell * 12;
-			const double inv = 1.0 / n, d = 1.0 / (n - 1);
-			const double m[3] = {v[0] * inv, v[1] * inv, v[2] * inv};
-			double S[6], W[6];
-			S[0] = (v[3] - n * m[0] * m[0]) * d + eps; S[1] = (v[4] - n * m[0] * m[1]) * d; S[2] = (v[5] - n * m[0] * m[2]) * d;
-			S[3] = (v[6] - n * m[1] * m[1]) * d + eps; S[4] = (v[7] - n * m[1] * m[2]) * d; S[5] = (v[8] - n * m[2] * m[2]) * d + eps;
-			if (sym3_inverse(S, W)) {
-				a[0] = m[0] + cx; a[1] = m[1] + cy; a[2] = m[2] + cz;
-				a[3] = v[9] * inv; a[4] = v[10] * inv; a[5] = v[11] * inv;
-#pragma unroll
-				for (int i = 0; i < 6; i++) a[6 + i] = W[i];
-			}
+			for (int i = 0; i < 12; i++) atomicAdd(a + i, (unsigned long long)v[i]);
 		}
 	}
 }
@@ -2181,6 +2173,37 @@ __device__ __host__ inline bool sym3_inverse(const double *S, double *W)
 	W[0] = c00 * id; W[1] = c01 * id; W[2] = c02 * id;
 	W[3] = (a * f - c * c) * id; W[4] = (b * c - a * e) * id; W[5] = (a * d - b * b) * id;
 	return true;
+}
+
+__global__ void k_ndt_finalize_buckets(const m3dreg_bucket *__restrict__ buckets, const m3dreg_grid_params *__restrict__ gp,
+		const long long *__restrict__ iacc, double *__restrict__ acc, NdtScales sc)
+{
+	pdl_enter();
+	long long nb = gp->number_of_buckets;
+	double res = (double)gp->resolution_X;
+	double eps = (kNdtRegRel * res) * (kNdtRegRel * res);
+	for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (long long)gridDim.x * blockDim.x) {
+		int n = buckets[b].number_of_points;
+		double *a = acc + (size_t)b * 12;
+		a[6] = 0.0;                                  /* unusable until proven otherwise */
+		if (n < kNdtMinPoints) continue;
+		const long long *ia = iacc + (size_t)b * 12;
+		double s[3] = {(double)ia[0] / sc.s1, (double)ia[1] / sc.s1, (double)ia[2] / sc.s1};
+		double ss[6] = {(double)ia[3] / sc.s2, (double)ia[4] / sc.s2, (double)ia[5] / sc.s2, (double)ia[6] / sc.s2, (double)ia[7] / sc.s2, (double)ia[8] / sc.s2};
+		double sl[3] = {(double)ia[9] / sc.sl, (double)ia[10] / sc.sl, (double)ia[11] / sc.sl};
+		double inv = 1.0 / n, d = 1.0 / (n - 1);
+		double m[3] = {s[0] * inv, s[1] * inv, s[2] * inv};
+		double S[6], W[6];
+		S[0] = (ss[0] - n * m[0] * m[0]) * d + eps; S[1] = (ss[1] - n * m[0] * m[1]) * d; S[2] = (ss[2] - n * m[0] * m[2]) * d;
+		S[3] = (ss[3] - n * m[1] * m[1]) * d + eps; S[4] = (ss[4] - n * m[1] * m[2]) * d; S[5] = (ss[5] - n * m[2] * m[2]) * d + eps;
+		if (!sym3_inverse(S, W)) continue;
+		double cx, cy, cz;
+		cell_centre((uint32_t)b, gp, cx, cy, cz);
+		a[0] = m[0] + cx; a[1] = m[1] + cy; a[2] = m[2] + cz;
+		a[3] = sl[0] * inv; a[4] = sl[1] * inv; a[5] = sl[2] * inv;
+#pragma unroll
+		for (int i = 0; i < 6; i++) a[6 + i] = W[i];
+	}
 }
 
 /* Queries per bucket: a count and the coordinate sum RELATIVE TO THE CELL CENTRE in 2^-40 m fixed point, added with

@@ -86,6 +86,12 @@ def ndt_normal_equations(local, pose6, queries, res, ext):
 def main():
     rng = np.random.default_rng(20240611)
     local = planes(rng, 3000, np.array([-2.0, -1.5, 0.0]))
+    # Two identical points below everything else in x, y and z: they define the box minimum and share the first bucket.
+    # The reference's bucket table has a first-element quirk (lesson_16.cu:148-158: if sorted element 0 is alone in its bucket,
+    # the NEXT occupied bucket is lost), and the point that defines the minimum sits exactly `ext` from it, i.e. on a cell
+    # boundary when ext == res — one ulp of difference in the transform would decide whether the quirk fires.  A pair of
+    # duplicates takes that sensitivity out of the fixture (it is a property of the reference's grid, not of NDT).
+    local = np.vstack([np.array([[-3.0, -2.5, -0.5], [-3.0, -2.5, -0.5]], dtype=np.float32), local])
     queries = planes(rng, 2000, np.array([-1.97, -1.52, 0.01]))
     pose6 = np.array([0.04, -0.03, 0.02, 0.006, -0.004, 0.012])
     res, ext = 1.0, 1.0

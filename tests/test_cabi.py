@@ -95,3 +95,54 @@ def test_cpp_shim_compiles_and_links(pkg):
     if not torch.cuda.is_available():
         r = subprocess.run([exe, "/dev/null", "/dev/null", "/dev/null", "0.5", "1", "6", "/dev/null"], capture_output=True, text=True)
         assert r.returncode != 0
+
+
+def test_cpp_shim_coexists_with_reference_wrapper(pkg, tmp_path):
+    """INTEGRATION.md recipe: the shim next to the reference's own cudaWrapper.h (whose CCudaWrapper keeps the
+    pre-registration methods).  A stand-in for that header (a CCudaWrapper with removeNoiseNaive / classify, the
+    reference's observations_t / obs_nn_t) is included BEFORE the shim compiled under another class name; the call sites of
+    gpu6DSLAM.cpp:313,406,575 and the sweep compile against it with the reference's own types."""
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("g++ not available")
+    src = tmp_path / "coexist.cpp"
+    src.write_text(r'''
+#include <vector>
+#include <cstdint>
+// --- stand-in for the reference's cudaWrapper.h + lesson_16.h (include/cudaWrapper.h:14-105, include/lesson_16.h:48-57) ---
+struct obs_nn_t { float x_diff, y_diff, z_diff, x0, y0, z0, P; };
+struct Aff { float m[16]; float &operator()(int r, int c) { return m[r * 4 + c]; } float operator()(int r, int c) const { return m[r * 4 + c]; } };
+struct observations_t { std::vector<obs_nn_t> vobs_nn; Aff m_pose; double om, fi, ka, tx, ty, tz; };
+struct Pt { float x, y, z, intensity; uint16_t ring; float normal_x, normal_y, normal_z; int32_t label; float rgb; };
+struct Cloud { std::vector<Pt> points; size_t size() const { return points.size(); } };
+class CCudaWrapper { public: void removeNoiseNaive(Cloud &, int) {} void classify(Cloud &) {} };
+// --- the shim under its own name ---
+#define M3DREG_SHIM_CLASS CM3dRegWrapper
+#define M3DREG_SHIM_NO_OBSERVATIONS
+#include "cuda_wrapper_shim.hpp"
+int main()
+{
+	CCudaWrapper pre;            // the reference's wrapper keeps the pre-registration path
+	CM3dRegWrapper reg;          // the registration path goes through libm3dreg.so
+	Cloud a, b;
+	pre.classify(a);
+	std::vector<int> nn(b.size());
+	observations_t obs;
+	obs.om = obs.fi = obs.ka = obs.tx = obs.ty = obs.tz = 0;
+	std::vector<Aff> poses;
+	try {
+		reg.semanticNearestNeighbourhoodSearch(a, b, 1.0f, 1.0f, 1.0f, 100, 100, nn);
+		reg.registerLS_4DOF(obs);
+		m3dreg_reg_params p = {1.0f, 1.0f, 1.0f, 100, 100, 100, {10, 1, 10, 10}, 4, M3DREG_MODE_ICP};
+		reg.registerAll(poses, p, 10.0f, 3);
+	} catch (const m3dreg::system_error &) { return 3; }
+	return 0;
+}
+''')
+    exe = tmp_path / "coexist"
+    inc = os.path.join(pkg.ROOT, "include")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I", inc, str(src), "-o", str(exe), pkg.LIB_PATH,
+                           "-Wl,-rpath," + os.path.dirname(pkg.LIB_PATH)])
+    rc = subprocess.run([str(exe)]).returncode
+    assert rc in (0, 3)          # 3 = no GPU here: the shim's exception path, never a fallback
