@@ -1769,6 +1769,11 @@ struct ObsFromRec {  /* fused path: the search's per-query records + the queries
 #pragma unroll
 		for (int k = 0; k < 12; k++) r[k] = __ldg(m + k);
 	}
+	__device__ __forceinline__ void prefetch(int i) const      /* the next trip's two streams into L2 while this trip computes */
+	{
+		asm volatile("prefetch.global.L2 [%0];" :: "l"(rec + i));
+		asm volatile("prefetch.global.L2 [%0];" :: "l"(q_xyzl + i));
+	}
 	__device__ __forceinline__ bool load(int i, Raw &raw) const
 	{
 		raw.p0 = __ldg(rec + i); raw.p2 = __ldg(q_xyzl + i);
@@ -1794,6 +1799,7 @@ struct ObsFromList { /* stage-level path: the reference's obs_nn_t array */
 	const m3dreg_obs_nn *obs;
 	struct Raw { float v[7]; };
 	__device__ __forceinline__ void prepare() {}
+	__device__ __forceinline__ void prefetch(int) const {}
 	__device__ __forceinline__ bool load(int i, Raw &r) const
 	{
 		const float *o = reinterpret_cast<const float *>(obs + i);
@@ -1907,6 +1913,8 @@ __global__ void __launch_bounds__(kNeqThreads) k_normal_equations(const Src src_
 			typename Src::Raw raw[kNeqInFlight];
 #pragma unroll
 			for (int k = 0; k < kNeqInFlight; k++) { int i = i0 + k * stride; tok[k] = i < n && src.load(i, raw[k]); }
+#pragma unroll
+			for (int k = 0; k < kNeqInFlight; k++) { int i = i0 + (kNeqInFlight + k) * stride; if (i < n) src.prefetch(i); }
 #pragma unroll
 			for (int k = 0; k < kNeqInFlight; k++) {
 				if (tok[k]) {

@@ -3,7 +3,7 @@
 
 Same method names, argument order/meaning and error behaviour as the reference so the parity tests read like
 calls the reference's own host code (src/gpu6DSLAM.cpp:313,405-406) would make.  The C++ equivalent for the
-real m3d pipeline is ``csrc/cuda_wrapper_shim.hpp``.
+real m3d pipeline is ``include/cuda_wrapper_shim.hpp`` (repository root).
 """
 from __future__ import annotations
 
