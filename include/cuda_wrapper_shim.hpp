@@ -17,9 +17,8 @@
  *
  * Two ways to use it:
  *   - alone, as `class CCudaWrapper` (default), in a harness that only needs the registration surface;
- *   - NEXT TO the reference's own cudaWrapper.h — whose CCudaWrapper also carries the pre-registration methods
- *     removeNoiseNaive / downsampling / classify / findBestYaw (src/gpu6DSLAM.cpp:63,71,75,137,756) that are not on this
- *     path — by compiling with -DM3DREG_SHIM_CLASS=CM3dRegWrapper -DM3DREG_SHIM_NO_OBSERVATIONS: the class then has its own
+ *   - NEXT TO the reference's own cudaWrapper.h (a staged migration: some call sites still on the reference's class) by
+ *     compiling with -DM3DREG_SHIM_CLASS=CM3dRegWrapper -DM3DREG_SHIM_NO_OBSERVATIONS: the class then has its own
  *     name and the header does not redefine observations_t; its template methods accept the reference's observations_t
  *     and obs_nn_t as they are (same field names, 28-byte layout checked at compile time).
  */
@@ -121,6 +120,73 @@ public:
 				search_radius, bucket_size, bounding_box_extension, max_number_considered_in_INNER_bucket,
 				max_number_considered_in_OUTER_bucket, nearest_neighbour_indexes.data());
 		throw_on_cuda_error(st, __FILE__, __LINE__);
+	}
+
+	/* ---- pre-registration steps (every incoming scan, src/gpu6DSLAM.cpp:63-85) ------------------------------------
+	 * ref: src/cudaWrapper.cpp:118-179 — the cloud is replaced by its survivors, original order kept */
+	template <class Cloud>
+	void removeNoiseNaive(Cloud &point_cloud, float resolution, float bounding_box_extension, int number_of_points_in_bucket_threshold)
+	{
+		static_assert(sizeof(point_cloud.points[0]) == sizeof(m3dreg_point), "point type must be the 40-byte PointXYZIRNLRGB");
+		const int n = (int)point_cloud.points.size();
+		if (n == 0) return;
+		int kept = 0;
+		m3dreg_point *p = reinterpret_cast<m3dreg_point *>(point_cloud.points.data());
+		throw_on_cuda_error(m3dreg_remove_noise_host(context(), p, n, resolution, bounding_box_extension,
+				number_of_points_in_bucket_threshold, p, &kept, nullptr), __FILE__, __LINE__);
+		shrink(point_cloud, kept);
+	}
+	/* ref: src/cudaWrapper.cpp:181-262 */
+	template <class Cloud>
+	void downsampling(Cloud &point_cloud, float resolution, float bounding_box_extension)
+	{
+		static_assert(sizeof(point_cloud.points[0]) == sizeof(m3dreg_point), "point type must be the 40-byte PointXYZIRNLRGB");
+		const int n = (int)point_cloud.points.size();
+		if (n == 0) return;
+		int kept = 0;
+		m3dreg_point *p = reinterpret_cast<m3dreg_point *>(point_cloud.points.data());
+		throw_on_cuda_error(m3dreg_downsample_host(context(), p, n, resolution, bounding_box_extension, p, &kept, nullptr), __FILE__, __LINE__);
+		shrink(point_cloud, kept);
+	}
+	/* ref: src/cudaWrapper.cpp:264-342 — normals and labels rewritten in place */
+	template <class Cloud>
+	void classify(Cloud &point_cloud, float normal_vectors_search_radius, float curvature_threshold, float ground_Z_coordinate_threshold,
+			int number_of_points_needed_for_plane_threshold, float bounding_box_extension, int max_number_considered_in_INNER_bucket,
+			int max_number_considered_in_OUTER_bucket, float viewpointX, float viewpointY, float viewpointZ)
+	{
+		static_assert(sizeof(point_cloud.points[0]) == sizeof(m3dreg_point), "point type must be the 40-byte PointXYZIRNLRGB");
+		const int n = (int)point_cloud.points.size();
+		if (n == 0) return;
+		throw_on_cuda_error(m3dreg_classify_host(context(), reinterpret_cast<m3dreg_point *>(point_cloud.points.data()), n,
+				normal_vectors_search_radius, curvature_threshold, ground_Z_coordinate_threshold, number_of_points_needed_for_plane_threshold,
+				bounding_box_extension, max_number_considered_in_INNER_bucket, max_number_considered_in_OUTER_bucket,
+				viewpointX, viewpointY, viewpointZ, nullptr, nullptr), __FILE__, __LINE__);
+	}
+	/* ref: src/cudaWrapper.cpp:662-836 — myaw receives the rotation about Z with the most matches (untouched when no angle
+	 * matches anything, as upstream).  `first_transform_inverse` is passed in by the caller: upstream inverts an
+	 * Eigen::Affine3f, which this header does not depend on (Eigen callers pass first_transform.inverse()). */
+	template <class Cloud, class Affine>
+	void findBestYaw(Cloud &first_point_cloud, const Affine &first_transform_inverse, Cloud &second_point_cloud, const Affine &second_transform,
+			float bucket_size, float bounding_box_extension, float search_radius, int max_number_considered_in_INNER_bucket,
+			int max_number_considered_in_OUTER_bucket, float angle_start, float angle_finish, float angle_step, Affine &myaw,
+			float *best_angle_deg = nullptr)
+	{
+		float m1[12], m2[12];
+		for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) { m1[r * 4 + c] = first_transform_inverse(r, c); m2[r * 4 + c] = second_transform(r, c); }
+		float best = angle_start;
+		int best_n = 0;
+		throw_on_cuda_error(m3dreg_find_best_yaw_host(context(),
+				reinterpret_cast<const m3dreg_point *>(first_point_cloud.points.data()), (int)first_point_cloud.points.size(),
+				reinterpret_cast<const m3dreg_point *>(second_point_cloud.points.data()), (int)second_point_cloud.points.size(),
+				m2, m1, bucket_size, bounding_box_extension, search_radius, max_number_considered_in_INNER_bucket,
+				max_number_considered_in_OUTER_bucket, angle_start, angle_finish, angle_step, &best, &best_n, nullptr, 0), __FILE__, __LINE__);
+		if (best_angle_deg) *best_angle_deg = best;
+		if (best_n > 0) {
+			const float rad = (float)((double)best * 3.14159265358979323846 / 180.0);
+			float of[3] = {0.0f, 0.0f, rad}, t[3] = {0.0f, 0.0f, 0.0f}, a[16];
+			m3dreg_euler_to_matrix(of, t, a);
+			for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) myaw(r, c) = a[r * 4 + c];
+		}
 	}
 
 	/* ref: src/cudaWrapper.cpp:427-468 (double[16] column-major variant) */
@@ -237,6 +303,16 @@ public:
 	int cuda_device;
 
 private:
+	/* keep the first `kept` points (pcl::PointCloud keeps width / height beside the vector: unorganised cloud of `kept` points) */
+	template <class Cloud>
+	static auto shrink(Cloud &c, int kept) -> decltype(c.width = 0u, void())
+	{
+		c.points.resize((size_t)kept);
+		c.width = (unsigned)kept; c.height = 1;
+	}
+	template <class Cloud>
+	static void shrink(Cloud &c, long kept) { c.points.resize((size_t)kept); }
+
 	template <class Obs>
 	bool register_ls(Obs &obs, int dof)
 	{

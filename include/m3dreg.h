@@ -344,6 +344,49 @@ int m3dreg_slam_copy_neq(m3dreg_ctx *ctx, double *neq_out, int n_scans);
 int m3dreg_slam_plan(const float *poses, int n_scans, const int *sizes, float distance_threshold, int first_optimised,
 		int world, int *pair_i, int *pair_j, int *owner, int cap);
 
+/* ---- pre-registration steps on the registration path's own grid ---------------------
+ * Every incoming scan passes through these before it is registered (src/gpu6DSLAM.cpp:63-85); they build the same
+ * regular grid (bounds -> keys -> stable sort -> dense table) and produce the normals / labels the semantic search keys
+ * on.  HOST clouds in, HOST clouds out, synchronous — as the reference's wrapper methods. */
+
+/* ref: CCudaWrapper::removeNoiseNaive(cloud, resolution, bounding_box_extension, number_of_points_in_bucket_threshold)
+ * (src/cudaWrapper.cpp:118-179) = cudaCalculateGridParams + cudaCalculateGrid + cudaRemoveNoiseNaive
+ * (src/lesson_16.cu:740-787): a point stays iff its bucket holds MORE than `threshold` points.  The survivors are
+ * written to `out` (capacity n) in their original order, their number to *n_out; markers_out (n bytes, 0/1, may be
+ * NULL) receives the reference's d_markers.  `out` may alias `cloud`. */
+int m3dreg_remove_noise_host(m3dreg_ctx *ctx, const m3dreg_point *cloud, int n, float resolution, float bounding_box_extension,
+		int number_of_points_in_bucket_threshold, m3dreg_point *out, int *n_out, unsigned char *markers_out);
+
+/* ref: CCudaWrapper::downsampling(cloud, resolution, bounding_box_extension) (src/cudaWrapper.cpp:181-262) =
+ * grid + cudaDownSample (src/lesson_16.cu:789-815): the first point (smallest original index) of every bucket that
+ * has an index_begin stays. */
+int m3dreg_downsample_host(m3dreg_ctx *ctx, const m3dreg_point *cloud, int n, float resolution, float bounding_box_extension,
+		m3dreg_point *out, int *n_out, unsigned char *markers_out);
+
+/* ref: CCudaWrapper::classify(cloud, normal_vectors_search_radius, curvature_threshold, ground_Z_coordinate_threshold,
+ * number_of_points_needed_for_plane_threshold, bounding_box_extension, max_INNER, max_OUTER, viewpoint)
+ * (src/cudaWrapper.cpp:264-342) = grid with cubic buckets of the search radius + cudaSemanticLabelingPlaneEdges +
+ * cudaSemanticLabelingFloorCeiling (src/lesson_16.cu:817-1239): normal_x/y/z and label of every point are rewritten
+ * in place.  mean_out (3 floats per SORTED position, may be NULL) receives the reference's d_mean for parity checks,
+ * table_out (n records, may be NULL) the sorted table the positions refer to. */
+int m3dreg_classify_host(m3dreg_ctx *ctx, m3dreg_point *cloud, int n, float normal_vectors_search_radius, float curvature_threshold,
+		float ground_Z_coordinate_threshold, int number_of_points_needed_for_plane_threshold, float bounding_box_extension,
+		int max_number_considered_in_INNER_bucket, int max_number_considered_in_OUTER_bucket,
+		float viewpointX, float viewpointY, float viewpointZ, float *mean_out, m3dreg_hash_element *table_out);
+
+/* ref: CCudaWrapper::findBestYaw(first, m_first, second, m_second, bucket_size, bounding_box_extension, search_radius,
+ * max_INNER, max_OUTER, angle_start, angle_finish, angle_step, myaw_out) (src/cudaWrapper.cpp:662-836;
+ * src/lesson_16.cu:1241-1384): the second cloud is brought into the first one's frame (second_transform3x4, then
+ * first_transform_inverse3x4: row-major 3x4, may be NULL = identity), and for every angle a = start, start + step, ...
+ * <= finish (degrees, float accumulation as upstream) rotated about Z, searched against the grid of the first cloud
+ * and the matched queries counted; the angle with the most matches wins (strictly more: the first maximum).
+ * The grid and the candidate sets of the first cloud are built ONCE (upstream rebuilds nothing either, but copies the
+ * second cloud and launches per angle with a device-wide sync each).  counts_out (may be NULL): matches per angle. */
+int m3dreg_find_best_yaw_host(m3dreg_ctx *ctx, const m3dreg_point *first, int n1, const m3dreg_point *second, int n2,
+		const float *second_transform3x4, const float *first_transform_inverse3x4,
+		float bucket_size, float bounding_box_extension, float search_radius, int max_inner, int max_outer,
+		float angle_start, float angle_finish, float angle_step, float *best_angle_out, int *best_count_out, int *counts_out, int counts_cap);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

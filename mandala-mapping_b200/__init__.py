@@ -48,6 +48,7 @@ EXPORTS = [
     "m3dreg_set_profiling", "m3dreg_get_stage_ms", "m3dreg_set_pruning", "m3dreg_get_nn_evaluations", "m3dreg_get_nn_fallbacks",
     "m3dreg_get_grid_phase_ns", "m3dreg_slam_sweep", "m3dreg_slam_copy_neq", "m3dreg_slam_plan", "m3dreg_nccl_get_unique_id",
     "m3dreg_nccl_init", "m3dreg_nccl_attach",
+    "m3dreg_remove_noise_host", "m3dreg_downsample_host", "m3dreg_classify_host", "m3dreg_find_best_yaw_host",
 ]
 
 
@@ -229,6 +230,52 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(lib().m3dreg_launch_count(self._h))
+
+    # -- pre-registration steps (host clouds, as CCudaWrapper::removeNoiseNaive / downsampling / classify / findBestYaw) ----
+    def remove_noise(self, cloud: np.ndarray, resolution: float, ext: float, threshold: int):
+        """-> (filtered cloud, markers): a point stays iff its bucket holds more than `threshold` points."""
+        n = len(cloud)
+        out = np.zeros(n, dtype=POINT_DTYPE); markers = np.zeros(n, dtype=np.uint8); kept = C.c_int(0)
+        _check(lib().m3dreg_remove_noise_host(self._h, _p(cloud), C.c_int(n), C.c_float(resolution), C.c_float(ext), C.c_int(threshold),
+                                              _p(out), C.byref(kept), _p(markers)), "m3dreg_remove_noise_host")
+        return out[:kept.value].copy(), markers
+
+    def downsample(self, cloud: np.ndarray, resolution: float, ext: float):
+        """-> (one point per occupied bucket, markers)."""
+        n = len(cloud)
+        out = np.zeros(n, dtype=POINT_DTYPE); markers = np.zeros(n, dtype=np.uint8); kept = C.c_int(0)
+        _check(lib().m3dreg_downsample_host(self._h, _p(cloud), C.c_int(n), C.c_float(resolution), C.c_float(ext),
+                                            _p(out), C.byref(kept), _p(markers)), "m3dreg_downsample_host")
+        return out[:kept.value].copy(), markers
+
+    def classify(self, cloud: np.ndarray, radius: float, curvature_threshold: float, ground_z: float, plane_points: int, ext: float,
+                 max_inner: int, max_outer: int, viewpoint=(0.0, 0.0, 0.0), want_debug: bool = False):
+        """Normals + plane/edge/ceiling/ground labels written into a COPY of `cloud` (returned).  want_debug also returns the
+        reference's d_mean (3 floats per sorted position) and the sorted table those positions refer to."""
+        out = np.ascontiguousarray(cloud).copy()
+        n = len(out)
+        mean = np.zeros((n, 3), dtype=np.float32) if want_debug else None
+        table = np.zeros(n, dtype=HASH_DTYPE) if want_debug else None
+        _check(lib().m3dreg_classify_host(self._h, _p(out), C.c_int(n), C.c_float(radius), C.c_float(curvature_threshold), C.c_float(ground_z),
+                                          C.c_int(plane_points), C.c_float(ext), C.c_int(max_inner), C.c_int(max_outer),
+                                          C.c_float(viewpoint[0]), C.c_float(viewpoint[1]), C.c_float(viewpoint[2]), _p(mean), _p(table)),
+               "m3dreg_classify_host")
+        return (out, mean, table) if want_debug else out
+
+    def find_best_yaw(self, first: np.ndarray, second: np.ndarray, second_transform=None, first_transform_inverse=None, bucket: float = 1.0,
+                      ext: float = 1.0, radius: float = 1.0, max_inner: int = 100, max_outer: int = 100,
+                      angle_start: float = -30.0, angle_finish: float = 30.0, angle_step: float = 0.5):
+        """-> (best angle in degrees, its match count, matches per angle)."""
+        def m34(m):
+            return None if m is None else np.ascontiguousarray(np.asarray(m, dtype=np.float32).reshape(-1)[:12])
+        a, b = m34(second_transform), m34(first_transform_inverse)
+        cap = int((angle_finish - angle_start) / angle_step) + 8
+        counts = np.full(cap, -1, dtype=np.int32); best = C.c_float(0.0); best_n = C.c_int(0)
+        _check(lib().m3dreg_find_best_yaw_host(self._h, _p(first), C.c_int(len(first)), _p(second), C.c_int(len(second)), _p(a), _p(b),
+                                               C.c_float(bucket), C.c_float(ext), C.c_float(radius), C.c_int(max_inner), C.c_int(max_outer),
+                                               C.c_float(angle_start), C.c_float(angle_finish), C.c_float(angle_step),
+                                               C.byref(best), C.byref(best_n), _p(counts), C.c_int(cap)), "m3dreg_find_best_yaw_host")
+        return float(best.value), int(best_n.value), counts[counts >= 0].copy()
 
     # -- stage level (device pointers: torch CUDA tensors or raw addresses) ------------------------------
     def calculate_grid_params(self, d_cloud, n, rx, ry=None, rz=None, ext=1.0) -> np.ndarray:

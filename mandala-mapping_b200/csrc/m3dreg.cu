@@ -18,6 +18,7 @@
 #include "m3dreg_kernels.cuh"
 #include "grid_build.cuh"
 #include "nn_hull.cuh"
+#include "preproc.cuh"
 
 using namespace m3d;
 
@@ -117,7 +118,9 @@ struct m3dreg_ctx {
 	                                                  * PDL-chained kernels — measured slower on B200 at every size, kept for A/B runs */
 	int nn_v7 = 0;                                   /* env M3DREG_NN_V7=1: round 1's k_nn_search_grid instead of k_nn_search_hull (A/B runs) */
 	cudaError_t launch_err = cudaSuccess;            /* first failed kernel launch since the last report */
-	DevBuf<m3dreg_point> aos_a, aos_b;
+	DevBuf<m3dreg_point> aos_a, aos_b, pp_aos;       /* pp_*: pre-registration steps (preproc_host.inl) */
+	DevBuf<unsigned char> pp_markers;
+	DevBuf<int> pp_tiles;
 	DevBuf<m3dreg_obs_nn> obs;
 	DevBuf<double> partials, ndt_acc;
 	DevBuf<long long> ndt_qacc;                      /* per bucket {count, fixed-point coordinate sums} of the NDT query pass */
@@ -155,6 +158,12 @@ struct m3dreg_ctx {
 	int use_pdl = 1;             /* programmatic dependent launch for every kernel (env M3DREG_NO_PDL=1 disables) */
 	int nn_per_thread = 0;       /* test switch (env M3DREG_NN_PER_THREAD=1): k_nn_search instead of k_nn_search_grid */
 	NNTuning nn_tune = {16, 128, 8};   /* heuristics of k_nn_search_grid (env M3DREG_NN_RHO_DIV / _HULL_MIN / _HULL_RATIO override) */
+	/* The pairs of a registerAll sweep are scans up to the pair gate (10 m) apart: a good part of the queries has no partner
+	 * inside the search radius and pays every doubling of the round radius up to it.  A larger first radius and larger
+	 * shared hulls suit that regime — measured on B200: 100 HDL-32E scans x 65 536 points 91.4 -> 74 ms per sweep, 12
+	 * rotating-SICK scans x 1 M points 22.7 -> 19.6 ms — while the same-viewpoint pair loops are faster with the values above
+	 * (1 M-point pair 116 vs 145 us).  Any values give the exact answer.  Env M3DREG_NN_SWEEP_RHO_DIV / _HULL_MIN / _HULL_RATIO. */
+	NNTuning nn_tune_sweep = {8, 512, 32};
 	double *scratch = nullptr;   /* 64 doubles */
 	float *mats = nullptr;       /* 32 floats  */
 	HostSmall *h = nullptr;      /* pinned */
@@ -802,6 +811,9 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	{ const char *e = getenv("M3DREG_NN_RHO_DIV"); if (e && atoi(e) > 0) c->nn_tune.rho_div = atoi(e); }
 	{ const char *e = getenv("M3DREG_NN_HULL_MIN"); if (e && atoi(e) > 0) c->nn_tune.hull_min = atoi(e); }
 	{ const char *e = getenv("M3DREG_NN_HULL_RATIO"); if (e && atoi(e) > 0) c->nn_tune.hull_ratio = atoi(e); }
+	{ const char *e = getenv("M3DREG_NN_SWEEP_RHO_DIV"); if (e && atoi(e) > 0) c->nn_tune_sweep.rho_div = atoi(e); }
+	{ const char *e = getenv("M3DREG_NN_SWEEP_HULL_MIN"); if (e && atoi(e) > 0) c->nn_tune_sweep.hull_min = atoi(e); }
+	{ const char *e = getenv("M3DREG_NN_SWEEP_HULL_RATIO"); if (e && atoi(e) > 0) c->nn_tune_sweep.hull_ratio = atoi(e); }
 	cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
 	if (e != cudaSuccess) { delete c; return (int)e; }
 	c->stream = c->own_stream;
@@ -854,6 +866,7 @@ void m3dreg_destroy(m3dreg_ctx *c)
 	c->hist.release(); c->buckets.release(); c->nn.release(); c->obs_rec.release(); c->cell_list.release(); c->aos_a.release(); c->aos_b.release();
 	c->obs.release(); c->partials.release(); c->ndt_acc.release(); c->ndt_qacc.release(); c->ndt_iacc.release(); c->table.release(); c->d_poses1.release(); c->d_pose6.release(); c->d_sweep_status.release();
 	c->d_segs.release(); c->d_seg_of_chunk.release(); c->d_seg_counts.release();
+	c->pp_aos.release(); c->pp_markers.release(); c->pp_tiles.release();
 	if (c->h_sweep) cudaFreeHost(c->h_sweep);
 	if (c->ps) cudaFree(c->ps);   /* base of the small block */
 	if (c->h) cudaFreeHost(c->h);
@@ -1594,8 +1607,13 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 		const SweepSeg *segs = c->d_segs.p + bt.seg0;
 		LAUNCH(c, k_transform_segments, n_chunks, kSegChunk, segs, bt.nseg, c->d_seg_of_chunk.p, c->d_poses1.p, c->q_xyzl.p, c->q_nrm.p);
 		const float res3[3] = {prm->bucket_size, prm->bucket_size, prm->bucket_size};
-		launch_nn(c, nullptr, (int)bt.total, c->vals[c->last_sorted].p, A.n, c->buckets.p, res3, prm->search_radius, prm->max_inner, prm->max_outer, 1,
-				nullptr, c->obs_rec.p, A.xyzl, c->d_seg_counts.p, c->d_seg_of_chunk.p);
+		{
+			const NNTuning pair_tune = c->nn_tune;
+			c->nn_tune = c->nn_tune_sweep;
+			launch_nn(c, nullptr, (int)bt.total, c->vals[c->last_sorted].p, A.n, c->buckets.p, res3, prm->search_radius, prm->max_inner, prm->max_outer, 1,
+					nullptr, c->obs_rec.p, A.xyzl, c->d_seg_counts.p, c->d_seg_of_chunk.p);
+			c->nn_tune = pair_tune;
+		}
 		ObsFromRec src = {};
 		src.rec = c->obs_rec.p; src.q_xyzl = c->q_xyzl.p; src.m = pose_i;
 		src.label_counts = c->d_seg_counts.p; src.seg_of_chunk = c->d_seg_of_chunk.p; src.n_segs = bt.nseg;
@@ -1634,3 +1652,4 @@ int m3dreg_sweep_solve(m3dreg_ctx *c, const double *d_neq, int n_scans, int scan
 } /* extern "C" */
 
 #include "slam_host.inl"
+#include "preproc_host.inl"

@@ -237,3 +237,63 @@ def register_all_sweep(scans, poses, params: RegParams, pair_thr=10.0):
     lib().orc_register_all_sweep(_ptr(allp), _ptr(off), C.c_int(len(scans)), _ptr(poses), C.byref(params),
                                  C.c_float(pair_thr), _ptr(neq), _ptr(status))
     return poses.reshape(-1, 4, 4), neq, status
+
+
+# -- pre-registration steps ------------------------------------------------------
+def _m34(m):
+    return None if m is None else np.ascontiguousarray(np.asarray(m, dtype=np.float32).reshape(-1)[:12])
+
+
+def _optr(a):
+    return None if a is None else _ptr(a)
+
+
+def remove_noise(cloud, res, ext, threshold):
+    """-> (filtered cloud, markers) as CCudaWrapper::removeNoiseNaive (cudaWrapper.cpp:118-179)."""
+    markers = np.zeros(len(cloud), dtype=np.uint8)
+    lib().orc_remove_noise_markers(_ptr(cloud), C.c_int(len(cloud)), C.c_float(res), C.c_float(ext), C.c_int(threshold), _ptr(markers))
+    return np.ascontiguousarray(cloud[markers != 0]), markers
+
+
+def downsample(cloud, res, ext):
+    markers = np.zeros(len(cloud), dtype=np.uint8)
+    lib().orc_downsample_markers(_ptr(cloud), C.c_int(len(cloud)), C.c_float(res), C.c_float(ext), _ptr(markers))
+    return np.ascontiguousarray(cloud[markers != 0]), markers
+
+
+def classify(cloud, radius, curvature_threshold, ground_z, plane_points, ext, max_inner, max_outer, viewpoint=(0.0, 0.0, 0.0)):
+    """-> (classified copy, d_mean per sorted position, sorted table) as CCudaWrapper::classify (cudaWrapper.cpp:264-342)."""
+    out = np.ascontiguousarray(cloud).copy()
+    mean = np.zeros((len(out), 3), dtype=np.float32)
+    table = np.zeros(len(out), dtype=HASH_DTYPE)
+    lib().orc_classify(_ptr(out), C.c_int(len(out)), C.c_float(radius), C.c_float(curvature_threshold), C.c_float(ground_z),
+                       C.c_int(plane_points), C.c_float(ext), C.c_int(max_inner), C.c_int(max_outer),
+                       C.c_float(viewpoint[0]), C.c_float(viewpoint[1]), C.c_float(viewpoint[2]), _ptr(mean), _ptr(table))
+    return out, mean, table
+
+
+def yaw_matrices(angle_start, angle_finish, angle_step):
+    """Angles (float accumulation as the reference's loop, cudaWrapper.cpp:761) and their row-major 3x4 yaw matrices
+    (AngleAxis product = quaternion path = euler_to_matrix(0, 0, rad))."""
+    angles, mats = [], []
+    a = np.float32(angle_start)
+    while a <= np.float32(angle_finish):
+        rad = np.float32(float(a) * np.pi / 180.0)
+        m = euler_to_matrix(np.array([0.0, 0.0, rad], dtype=np.float32), np.zeros(3, dtype=np.float32))
+        angles.append(float(a)); mats.append(np.asarray(m, dtype=np.float32).reshape(-1)[:12].copy())
+        a = np.float32(a + np.float32(angle_step))
+    return np.array(angles, dtype=np.float32), np.ascontiguousarray(np.stack(mats))
+
+
+def find_best_yaw(first, second, second_transform=None, first_transform_inverse=None, bucket=1.0, ext=1.0, radius=1.0,
+                  max_inner=100, max_outer=100, angle_start=-30.0, angle_finish=30.0, angle_step=0.5):
+    """-> (best angle, its count, counts per angle) as CCudaWrapper::findBestYaw (cudaWrapper.cpp:662-836)."""
+    angles, mats = yaw_matrices(angle_start, angle_finish, angle_step)
+    counts = np.zeros(len(angles), dtype=np.int32)
+    L = lib()
+    L.orc_find_best_yaw.restype = C.c_int
+    a, b = _m34(second_transform), _m34(first_transform_inverse)
+    best = L.orc_find_best_yaw(_ptr(first), C.c_int(len(first)), _ptr(second), C.c_int(len(second)), _optr(a), _optr(b),
+                               C.c_float(bucket), C.c_float(ext), C.c_float(radius), C.c_int(max_inner), C.c_int(max_outer),
+                               _ptr(mats), C.c_int(len(angles)), _ptr(counts))
+    return (float(angles[best]) if best >= 0 else float(angle_start)), (int(counts[best]) if best >= 0 else 0), counts

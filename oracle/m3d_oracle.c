@@ -808,3 +808,325 @@ int orc_register_all_sweep(const orc_point *scans, const int64_t *off, int n_sca
 	free(newp); free(pc1); free(pc2); free(nn);
 	return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Pre-registration steps.  CW = src/cudaWrapper.cpp, L16 = src/lesson_16.cu,
+ * SVD = src/cuda_SVD.cu.  Every step starts with the grid of the cloud itself with cubic buckets
+ * (cudaCalculateGridParams + cudaCalculateGrid, e.g. CW:131-141).
+ * --------------------------------------------------------------------------------------------- */
+
+static void grid_of(const orc_point *c, int n, float res, float ext, orc_grid_params *gp, orc_bucket **buckets, orc_hash_element **table)
+{
+	orc_grid_params_compute(c, n, res, res, res, ext, gp);
+	int64_t nb = gp->number_of_buckets > 0 ? gp->number_of_buckets : 1;
+	*buckets = (orc_bucket *)malloc((size_t)nb * sizeof(orc_bucket));
+	*table = (orc_hash_element *)malloc((size_t)(n > 0 ? n : 1) * sizeof(orc_hash_element));
+	orc_build_grid(c, n, gp, *buckets, *table);
+}
+
+/* CCudaWrapper::removeNoiseNaive (CW:118-179): kernel_setAllPointsToRemove + kernel_markPointsToRemain (L16:740-766) —
+ * a point stays iff the bucket of ITS coordinates holds more than `threshold` points (the dense table's count, so the
+ * points of the first-element quirk bucket, whose count stays 0, are dropped). */
+void orc_remove_noise_markers(const orc_point *c, int n, float res, float ext, int threshold, uint8_t *markers)
+{
+	orc_grid_params gp; orc_bucket *b; orc_hash_element *t;
+	grid_of(c, n, res, ext, &gp, &b, &t);
+#pragma omp parallel for schedule(static)
+	for (int i = 0; i < n; i++) {
+		int32_t key = bucket_key(c[i].x, c[i].y, c[i].z, &gp, 0, 0, 0);
+		markers[i] = (key >= 0 && (int64_t)key < gp.number_of_buckets && b[key].number_of_points > threshold) ? 1 : 0;
+	}
+	free(b); free(t);
+}
+
+/* CCudaWrapper::downsampling (CW:181-262): kernel_markFirstPointInBuckets (L16:789-801) — the first sorted point of
+ * every bucket with an index_begin. */
+void orc_downsample_markers(const orc_point *c, int n, float res, float ext, uint8_t *markers)
+{
+	orc_grid_params gp; orc_bucket *b; orc_hash_element *t;
+	grid_of(c, n, res, ext, &gp, &b, &t);
+	memset(markers, 0, (size_t)n);
+	for (int64_t k = 0; k < gp.number_of_buckets; k++)
+		if (b[k].index_begin != -1) markers[t[b[k].index_begin].index_of_point] = 1;
+	free(b); free(t);
+}
+
+/* ---- the 3x3 decomposition upstream uses (SVD:29-380, Nathan Lay's closed-form SVD): eigen-decomposition of A^T A by
+ * the trigonometric cubic solution, null vectors by a pivoted LDU, U = A V.  Restated for the oracle with the same
+ * storage convention: matrices are 9 doubles, element (row r, column c) at [3*c + r]; U + 3*k is the k-th vector. ---- */
+static void svd_ata3(double *AA, const double *A)      /* SVD:29-42 */
+{
+	AA[0] = A[0] * A[0] + A[1] * A[1] + A[2] * A[2];
+	AA[3] = A[0] * A[3] + A[1] * A[4] + A[2] * A[5];
+	AA[6] = A[0] * A[6] + A[1] * A[7] + A[2] * A[8];
+	AA[1] = AA[3];
+	AA[4] = A[3] * A[3] + A[4] * A[4] + A[5] * A[5];
+	AA[7] = A[3] * A[6] + A[4] * A[7] + A[5] * A[8];
+	AA[2] = AA[6];
+	AA[5] = AA[7];
+	AA[8] = A[6] * A[6] + A[7] * A[7] + A[8] * A[8];
+}
+
+static void svd_solvecubic(double *c)                  /* SVD:44-82: roots of x^3 + c2 x^2 + c1 x + c0 */
+{
+	const double sq3d2 = 0.86602540378443864676, c2d3 = c[2] / 3, c2sq = c[2] * c[2], Q = (3 * c[1] - c2sq) / 9,
+			R = (c[2] * (9 * c[1] - 2 * c2sq) - 27 * c[0]) / 54;
+	if (Q < 0) {
+		double tmp = 2 * sqrt(-Q), t = acos(R / sqrt(-Q * Q * Q)) / 3, cost = tmp * cos(t), sint = tmp * sin(t);
+		c[0] = cost - c2d3;
+		cost = -0.5 * cost - c2d3;
+		sint = sq3d2 * sint;
+		c[1] = cost - sint;
+		c[2] = cost + sint;
+	} else {
+		double tmp = cbrt(R);
+		c[0] = -c2d3 + 2 * tmp;
+		c[1] = c[2] = -c2d3 - tmp;
+	}
+}
+
+static void svd_sort3(double *x)                       /* SVD:84-106: descending */
+{
+	double tmp;
+	if (x[0] < x[1]) { tmp = x[0]; x[0] = x[1]; x[1] = tmp; }
+	if (x[1] < x[2]) {
+		if (x[0] < x[2]) { tmp = x[2]; x[2] = x[1]; x[1] = x[0]; x[0] = tmp; }
+		else { tmp = x[1]; x[1] = x[2]; x[2] = tmp; }
+	}
+}
+
+static void svd_ldu3(double *A, int *P)                /* SVD:108-141: row-pivoted LDU in place */
+{
+	P[1] = 1; P[2] = 2;
+	P[0] = fabs(A[3]) > fabs(A[0]) ? (fabs(A[6]) > fabs(A[3]) ? 2 : 1) : (fabs(A[6]) > fabs(A[0]) ? 2 : 0);
+	P[P[0]] = 0;
+	if (fabs(A[3 * P[2] + 1]) > fabs(A[3 * P[1] + 1])) { int tmp = P[1]; P[1] = P[2]; P[2] = tmp; }
+	if (A[3 * P[0]] != 0) {
+		A[3 * P[1]] = A[3 * P[1]] / A[3 * P[0]];
+		A[3 * P[2]] = A[3 * P[2]] / A[3 * P[0]];
+		A[3 * P[0] + 1] = A[3 * P[0] + 1] / A[3 * P[0]];
+		A[3 * P[0] + 2] = A[3 * P[0] + 2] / A[3 * P[0]];
+	}
+	A[3 * P[1] + 1] = A[3 * P[1] + 1] - A[3 * P[0] + 1] * A[3 * P[1]] * A[3 * P[0]];
+	if (A[3 * P[1] + 1] != 0) {
+		A[3 * P[2] + 1] = (A[3 * P[2] + 1] - A[3 * P[0] + 1] * A[3 * P[2]] * A[3 * P[0]]) / A[3 * P[1] + 1];
+		A[3 * P[1] + 2] = (A[3 * P[1] + 2] - A[3 * P[0] + 2] * A[3 * P[1]] * A[3 * P[0]]) / A[3 * P[1] + 1];
+	}
+	A[3 * P[2] + 2] = A[3 * P[2] + 2] - A[3 * P[0] + 2] * A[3 * P[2]] * A[3 * P[0]] - A[3 * P[1] + 2] * A[3 * P[2] + 1] * A[3 * P[1] + 1];
+}
+
+static void svd_ldubsolve3(double *x, const double *y, const double *LDU, const int *P)      /* SVD:143-148 */
+{
+	x[P[2]] = y[2];
+	x[P[1]] = y[1] - LDU[3 * P[2] + 1] * x[P[2]];
+	x[P[0]] = y[0] - LDU[3 * P[2]] * x[P[2]] - LDU[3 * P[1]] * x[P[1]];
+}
+
+static void svd_cross(double *z, const double *x, const double *y)                          /* SVD:150-155 */
+{
+	z[0] = x[1] * y[2] - x[2] * y[1];
+	z[1] = -(x[0] * y[2] - x[2] * y[0]);
+	z[2] = x[0] * y[1] - x[1] * y[0];
+}
+
+static void svd_matvec3(double *y, const double *A, const double *x)                        /* SVD:157-162 */
+{
+	y[0] = A[0] * x[0] + A[3] * x[1] + A[6] * x[2];
+	y[1] = A[1] * x[0] + A[4] * x[1] + A[7] * x[2];
+	y[2] = A[2] * x[0] + A[5] * x[1] + A[8] * x[2];
+}
+
+static void svd_unit3(double *x)                                                             /* SVD:179-185 */
+{
+	double tmp = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+	x[0] /= tmp; x[1] /= tmp; x[2] /= tmp;
+}
+
+static int svd_nearest_zero(const double *LDU, const int *P, int first_system)              /* SVD:253-256, 283-286 */
+{
+	double d0 = fabs(LDU[3 * P[0]]), d1 = fabs(LDU[3 * P[1] + 1]), d2 = fabs(LDU[3 * P[2] + 2]);
+	if (first_system) return d1 < d0 ? (d2 < d1 ? 2 : 1) : (d2 < d0 ? 2 : 0);
+	return d0 < d2 ? (d0 < d1 ? 0 : 1) : (d1 < d2 ? 1 : 2);
+}
+
+/* gpuSVD (SVD:187-380).  NOTE the index expressions LDU[P[k]][k] upstream address element [3*P[k] + k] of the flat
+ * array, restated as such. */
+static void svd3(const double *A, double *U, double *S9, double *V)
+{
+	const double thr = 1e-10;
+	int P[3], k;
+	double y[3], AA[9], LDU[9], S[3];
+	svd_ata3(AA, A);
+	S[2] = -AA[0] - AA[4] - AA[8];
+	S[1] = AA[0] * AA[4] + AA[8] * AA[0] + AA[8] * AA[4] - AA[7] * AA[5] - AA[6] * AA[2] - AA[3] * AA[1];
+	S[0] = AA[7] * AA[5] * AA[0] + AA[6] * AA[2] * AA[4] + AA[3] * AA[1] * AA[8] - AA[0] * AA[4] * AA[8] - AA[3] * AA[7] * AA[2] -
+			AA[6] * AA[1] * AA[5];
+	svd_solvecubic(S);
+	if (S[0] < 0) S[0] = 0;
+	if (S[1] < 0) S[1] = 0;
+	if (S[2] < 0) S[2] = 0;
+	svd_sort3(S);
+	memcpy(LDU, AA, sizeof(LDU));
+	LDU[0] -= S[0]; LDU[4] -= S[0]; LDU[8] -= S[0];
+	svd_ldu3(LDU, P);
+	y[0] = y[1] = y[2] = 0;
+	y[svd_nearest_zero(LDU, P, 1)] = 1;
+	svd_ldubsolve3(V, y, LDU, P);
+	memcpy(LDU, AA, sizeof(LDU));
+	LDU[0] -= S[2]; LDU[4] -= S[2]; LDU[8] -= S[2];
+	svd_ldu3(LDU, P);
+	y[0] = y[1] = y[2] = 0;
+	y[svd_nearest_zero(LDU, P, 0)] = 1;
+	svd_ldubsolve3(V + 6, y, LDU, P);
+	svd_cross(V + 3, V + 6, V);
+	k = (S[0] > thr) + (S[1] > thr) + (S[2] > thr);
+	switch (k) {
+	case 0:
+		memcpy(U, V, 9 * sizeof(double));
+		break;
+	case 1:
+		svd_matvec3(U, A, V);
+		y[0] = y[1] = y[2] = 0;
+		k = fabs(U[0]) < fabs(U[2]) ? (fabs(U[0]) < fabs(U[1]) ? 0 : 1) : (fabs(U[1]) < fabs(U[2]) ? 1 : 2);
+		y[k] = 1;
+		svd_cross(U + 3, y, U);
+		svd_cross(U + 6, U, U + 3);
+		break;
+	case 2:
+		svd_matvec3(U, A, V);
+		svd_matvec3(U + 3, A, V + 3);
+		svd_cross(U + 6, U, U + 3);
+		break;
+	default:
+		svd_matvec3(U, A, V);
+		svd_matvec3(U + 3, A, V + 3);
+		svd_matvec3(U + 6, A, V + 6);
+		break;
+	}
+	svd_unit3(V); svd_unit3(V + 3); svd_unit3(V + 6);
+	svd_unit3(U); svd_unit3(U + 3); svd_unit3(U + 6);
+	memset(S9, 0, 9 * sizeof(double));
+	S9[0] = sqrt(S[0]); S9[4] = sqrt(S[1]); S9[8] = sqrt(S[2]);
+}
+
+/* one sweep over the 27-neighbourhood of sorted position `pos` (L16:858-941 and L16:989-1060): sweep 0 accumulates the
+ * float coordinate sums, sweep 1 the covariance about `mean` (float differences, float products, double sums). */
+static int classify_sweep(const orc_point *c, int n, const orc_hash_element *t, const orc_bucket *b, const orc_grid_params *gp,
+		int key, float x, float y, float z, float radius, int max_in, int max_out, int sweep, float *sum3, const float *mean, double *cov9)
+{
+	const int nby = gp->number_of_buckets_Y, nbz = gp->number_of_buckets_Z, nbx = gp->number_of_buckets_X;
+	const int ix = key / (nby * nbz), iy = (key % (nby * nbz)) / nbz, iz = (key % (nby * nbz)) % nbz;
+	const int sx = ix == 0 ? 0 : -1, sy = iy == 0 ? 0 : -1, sz = iz == 0 ? 0 : -1;
+	const int stx = ix == nbx - 1 ? 1 : 2, sty = iy == nby - 1 ? 1 : 2, stz = iz == nbz - 1 ? 1 : 2;
+	int cnt = 0;
+	for (int i = sx; i < stx; i++)
+	for (int j = sy; j < sty; j++)
+	for (int k = sz; k < stz; k++) {
+		const int nbk = key + i * nby * nbz + j * nbz + k;
+		if (nbk < 0 || (int64_t)nbk >= gp->number_of_buckets) continue;
+		const int npts = b[nbk].number_of_points;
+		if (npts <= 0) continue;
+		const int cap = nbk == key ? max_in : max_out;
+		if (cap <= 0) continue;
+		int iter = 1;
+		if (cap < npts) { iter = npts / cap; if (iter <= 0) iter = 1; }
+		for (int l = b[nbk].index_begin; l < b[nbk].index_end; l += iter) {
+			if (l < 0 || l >= n) continue;
+			const orc_point *q = &c[t[l].index_of_point];
+			const float dx = x - q->x, dy = y - q->y, dz = z - q->z;
+			const float dist = sqrtf(fmaf(dz, dz, fmaf(dx, dx, dy * dy)));      /* SASS of the reference build: (dy*dy) then fma dx, fma dz */
+			if (!(dist <= radius)) continue;
+			if (sweep == 0) { sum3[0] += q->x; sum3[1] += q->y; sum3[2] += q->z; }
+			else {
+				const float ex = mean[0] - q->x, ey = mean[1] - q->y, ez = mean[2] - q->z;
+				cov9[0] += (double)(ex * ex); cov9[1] += (double)(ex * ey); cov9[2] += (double)(ex * ez);
+				cov9[3] += (double)(ey * ex); cov9[4] += (double)(ey * ey); cov9[5] += (double)(ey * ez);
+				cov9[6] += (double)(ez * ex); cov9[7] += (double)(ez * ey); cov9[8] += (double)(ez * ez);
+			}
+			cnt++;
+		}
+	}
+	return cnt;
+}
+
+/* CCudaWrapper::classify (CW:264-342): grid with cubic buckets of the search radius, cudaSemanticLabelingPlaneEdges
+ * (L16:817-1194: step1 mean, step2 covariance + SVD + plane test, flip towards the viewpoint), then
+ * cudaSemanticLabelingFloorCeiling (L16:1196-1239).  In place.  mean_out: 3 floats per SORTED position (d_mean). */
+void orc_classify(orc_point *c, int n, float radius, float curvature_threshold, float ground_z, int plane_points, float ext,
+		int max_in, int max_out, float vx, float vy, float vz, float *mean_out, orc_hash_element *table_out)
+{
+	orc_grid_params gp; orc_bucket *b; orc_hash_element *t;
+	grid_of(c, n, radius, ext, &gp, &b, &t);
+	float *mean = (float *)calloc((size_t)(n > 0 ? n : 1) * 3, sizeof(float));
+	for (int i = 0; i < n; i++) { c[i].normal_x = 0.0f; c[i].normal_y = 0.0f; c[i].normal_z = 0.0f; }      /* L16:831-833 */
+#pragma omp parallel for schedule(dynamic, 256)
+	for (int pos = 0; pos < n; pos++) {                                       /* step 1, L16:817-957 */
+		const int key = t[pos].index_of_bucket, idx = t[pos].index_of_point;
+		if (!(key >= 0 && (int64_t)key < gp.number_of_buckets) || !(idx >= 0 && idx < n)) continue;
+		float s[3] = {0.0f, 0.0f, 0.0f};
+		const int cnt = classify_sweep(c, n, t, b, &gp, key, c[idx].x, c[idx].y, c[idx].z, radius, max_in, max_out, 0, s, 0, 0);
+		if (cnt >= 3) { mean[3 * pos] = s[0] / (float)cnt; mean[3 * pos + 1] = s[1] / (float)cnt; mean[3 * pos + 2] = s[2] / (float)cnt; }
+	}
+#pragma omp parallel for schedule(dynamic, 256)
+	for (int pos = 0; pos < n; pos++) {                                       /* step 2, L16:959-1110 */
+		const int key = t[pos].index_of_bucket, idx = t[pos].index_of_point;
+		if (!(key >= 0 && (int64_t)key < gp.number_of_buckets) || !(idx >= 0 && idx < n)) continue;
+		orc_point *p = &c[idx];
+		p->label = 1;                                                          /* LABEL_EDGE */
+		const float *m = mean + 3 * pos;
+		if (!(m[0] != 0.0f && m[1] != 0.0f && m[2] != 0.0f)) continue;
+		double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+		const int cnt = classify_sweep(c, n, t, b, &gp, key, p->x, p->y, p->z, radius, max_in, max_out, 1, 0, m, cov);
+		if (cnt >= plane_points) {
+			for (int k = 0; k < 9; k++) cov[k] /= cnt;
+			double U[9], V[9], SS[9];
+			svd3(cov, U, SS, V);
+			const double nx = (float)(U[1] * U[5] - U[2] * U[4]), ny = (float)(-(U[0] * U[5] - U[2] * U[3])), nz = (float)(U[0] * U[4] - U[1] * U[3]);
+			const double len = sqrt(nx * nx + ny * ny + nz * nz);
+			if (len != 0) {
+				p->normal_x = (float)(nx / len); p->normal_y = (float)(ny / len); p->normal_z = (float)(nz / len);
+				if (SS[4] / SS[8] > (double)curvature_threshold) p->label = 0;    /* LABEL_PLANE */
+			}
+		}
+	}
+	for (int i = 0; i < n; i++) {
+		orc_point *p = &c[i];
+		/* kernel_flipNormalsTowardsViewpoint (L16:1112-1133); float expression, nvcc contracts it as fma(nz,dz, fma(ny,dy, nx*dx)) */
+		const float d = fmaf(p->normal_z, vz - p->z, fmaf(p->normal_y, vy - p->y, p->normal_x * (vx - p->x)));
+		if ((double)d < 0.0) { p->normal_x = -p->normal_x; p->normal_y = -p->normal_y; p->normal_z = -p->normal_z; }
+		/* kernel_semanticLabelingFloorCeiling (L16:1196-1219) */
+		if (p->label == 0 && ((double)p->normal_z > 0.7 || (double)p->normal_z < -0.7)) p->label = p->z < ground_z ? 3 : 2;
+	}
+	if (mean_out) memcpy(mean_out, mean, (size_t)n * 3 * sizeof(float));
+	if (table_out) memcpy(table_out, t, (size_t)n * sizeof(orc_hash_element));
+	free(mean); free(b); free(t);
+}
+
+/* CCudaWrapper::findBestYaw (CW:662-836): second cloud into the first one's frame (two device transforms), grid of the
+ * first cloud, then per angle: rotate about Z out of place, semantic NN, count the matched queries
+ * (cudaCountNumberOfSemanticNearestNeighbours, L16:1241-1298); strictly more matches win.  Matrices row-major 3x4
+ * (rows of a 4x4 also fine: 12 floats are read); NULL = identity.  Returns the index of the best angle or -1. */
+int orc_find_best_yaw(const orc_point *first, int n1, const orc_point *second, int n2, const float *second_m, const float *first_inv_m,
+		float bucket, float ext, float radius, int max_in, int max_out, const float *yaw_mats, int n_angles, int32_t *counts_out)
+{
+	orc_point *s = (orc_point *)malloc((size_t)n2 * sizeof(orc_point)), *r = (orc_point *)malloc((size_t)n2 * sizeof(orc_point));
+	int32_t *nn = (int32_t *)malloc((size_t)n2 * sizeof(int32_t));
+	memcpy(s, second, (size_t)n2 * sizeof(orc_point));
+	for (int k = 0; k < 2; k++) {
+		const float *m = k == 0 ? second_m : first_inv_m;
+		if (m) { orc_transform_cloud(s, r, n2, m); memcpy(s, r, (size_t)n2 * sizeof(orc_point)); }
+	}
+	orc_grid_params gp; orc_bucket *b; orc_hash_element *t;
+	grid_of(first, n1, bucket, ext, &gp, &b, &t);
+	int best = -1, best_n = 0;
+	for (int a = 0; a < n_angles; a++) {
+		orc_transform_cloud(s, r, n2, yaw_mats + 12 * (size_t)a);
+		orc_nn_search(first, n1, r, n2, t, b, &gp, radius, max_in, max_out, nn);
+		int cnt = 0;
+		for (int i = 0; i < n2; i++) cnt += nn[i] >= 0 ? 1 : 0;
+		if (counts_out) counts_out[a] = cnt;
+		if (cnt > best_n) { best_n = cnt; best = a; }
+	}
+	free(s); free(r); free(nn); free(b); free(t);
+	return best;
+}

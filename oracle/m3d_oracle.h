@@ -105,6 +105,14 @@ int  orc_register_all_sweep(const orc_point *scans_local, const int64_t *offsets
 		float *poses4x4, const orc_reg_params *prm, float pair_distance_threshold,
 		double *neq_out /* n_scans*28 or NULL */, int32_t *status_out /* n_scans or NULL */);
 
+/* pre-registration steps --------------------------------------------------------- */
+void orc_remove_noise_markers(const orc_point *cloud, int n, float res, float ext, int threshold, uint8_t *markers);
+void orc_downsample_markers(const orc_point *cloud, int n, float res, float ext, uint8_t *markers);
+void orc_classify(orc_point *cloud, int n, float radius, float curvature_threshold, float ground_z, int plane_points, float ext,
+		int max_in, int max_out, float vx, float vy, float vz, float *mean_out, orc_hash_element *table_out);
+int  orc_find_best_yaw(const orc_point *first, int n1, const orc_point *second, int n2, const float *second_m, const float *first_inv_m,
+		float bucket, float ext, float radius, int max_in, int max_out, const float *yaw_mats, int n_angles, int32_t *counts_out);
+
 #ifdef __cplusplus
 }
 #endif

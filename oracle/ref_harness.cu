@@ -257,4 +257,126 @@ done:
 	return rc;
 }
 
+
+/* ---- pre-registration steps: the reference's own kernels behind the call sequences of
+ * CCudaWrapper::removeNoiseNaive / downsampling / classify / findBestYaw (cudaWrapper.cpp:118-342, 662-836) ---- */
+
+/* mode 0: removeNoiseNaive (threshold used), mode 1: downsampling.  markers_out: n bytes (the reference's bool d_markers). */
+static int ref_mark_host(int mode, const void *cloud, int n, float resolution, float ext, int threshold, unsigned char *markers_out)
+{
+	int rc = 0, dev = 0;
+	ref_point_t *d_cloud = 0;
+	hashElement *d_table = 0;
+	bucket *d_buckets = 0;
+	bool *d_markers = 0;
+	gridParameters p;
+	memset(&p, 0, sizeof(p));
+	cudaGetDevice(&dev);
+	int threads = ref_threads_for_device(dev);
+	REF_CHECK(cudaMalloc((void **)&d_cloud, (size_t)n * sizeof(ref_point_t)));
+	REF_CHECK(cudaMemcpy(d_cloud, cloud, (size_t)n * sizeof(ref_point_t), cudaMemcpyHostToDevice));
+	REF_CHECK(cudaCalculateGridParams(d_cloud, n, resolution, resolution, resolution, ext, p));
+	REF_CHECK(cudaMalloc((void **)&d_table, (size_t)n * sizeof(hashElement)));
+	REF_CHECK(cudaMalloc((void **)&d_buckets, (size_t)p.number_of_buckets * sizeof(bucket)));
+	REF_CHECK(cudaCalculateGrid(threads, d_cloud, d_buckets, d_table, n, p));
+	REF_CHECK(cudaMalloc((void **)&d_markers, (size_t)n * sizeof(bool)));
+	if (mode == 0) REF_CHECK(cudaRemoveNoiseNaive(threads, d_markers, d_cloud, d_table, d_buckets, p, n, threshold));
+	else REF_CHECK(cudaDownSample(threads, d_markers, d_table, d_buckets, p, n));
+	REF_CHECK(cudaMemcpy(markers_out, d_markers, (size_t)n * sizeof(bool), cudaMemcpyDeviceToHost));
+done:
+	cudaFree(d_cloud); cudaFree(d_table); cudaFree(d_buckets); cudaFree(d_markers);
+	return rc;
+}
+
+int ref_remove_noise_host(const void *cloud, int n, float resolution, float ext, int threshold, unsigned char *markers_out)
+{
+	return ref_mark_host(0, cloud, n, resolution, ext, threshold, markers_out);
+}
+
+int ref_downsample_host(const void *cloud, int n, float resolution, float ext, unsigned char *markers_out)
+{
+	return ref_mark_host(1, cloud, n, resolution, ext, 0, markers_out);
+}
+
+/* CCudaWrapper::classify (cudaWrapper.cpp:264-342) in place on a host cloud.  The grid and the two labelling kernels run
+ * with threadsNV = maxThreadsPerBlock / 4 (cudaWrapper.cpp:85), the floor/ceiling pass with threads.  Optional exports:
+ * mean_out = d_mean (3 floats per SORTED position), table_out = the sorted table (n records). */
+int ref_classify_host(void *cloud, int n, float radius, float curvature_threshold, float ground_z, int plane_points, float ext,
+		int max_inner, int max_outer, float vx, float vy, float vz, float *mean_out, void *table_out)
+{
+	int rc = 0, dev = 0;
+	ref_point_t *d_cloud = 0;
+	hashElement *d_table = 0;
+	bucket *d_buckets = 0;
+	simple_point3D *d_mean = 0;
+	gridParameters p;
+	memset(&p, 0, sizeof(p));
+	cudaGetDevice(&dev);
+	int threads = ref_threads_for_device(dev), threadsNV = threads / 4;
+	REF_CHECK(cudaMalloc((void **)&d_cloud, (size_t)n * sizeof(ref_point_t)));
+	REF_CHECK(cudaMemcpy(d_cloud, cloud, (size_t)n * sizeof(ref_point_t), cudaMemcpyHostToDevice));
+	REF_CHECK(cudaCalculateGridParams(d_cloud, n, radius, radius, radius, ext, p));
+	REF_CHECK(cudaMalloc((void **)&d_table, (size_t)n * sizeof(hashElement)));
+	REF_CHECK(cudaMalloc((void **)&d_buckets, (size_t)p.number_of_buckets * sizeof(bucket)));
+	REF_CHECK(cudaCalculateGrid(threadsNV, d_cloud, d_buckets, d_table, n, p));
+	REF_CHECK(cudaMalloc((void **)&d_mean, (size_t)n * sizeof(simple_point3D)));
+	REF_CHECK(cudaMemset(d_mean, 0, (size_t)n * sizeof(simple_point3D)));      /* upstream leaves rows of invalid positions unset */
+	REF_CHECK(cudaSemanticLabelingPlaneEdges(threadsNV, d_cloud, n, d_table, d_buckets, d_mean, p, radius, max_inner, max_outer,
+			curvature_threshold, plane_points, vx, vy, vz));
+	REF_CHECK(cudaSemanticLabelingFloorCeiling(threads, d_cloud, n, ground_z));
+	REF_CHECK(cudaMemcpy(cloud, d_cloud, (size_t)n * sizeof(ref_point_t), cudaMemcpyDeviceToHost));
+	if (mean_out) REF_CHECK(cudaMemcpy(mean_out, d_mean, (size_t)n * sizeof(simple_point3D), cudaMemcpyDeviceToHost));
+	if (table_out) REF_CHECK(cudaMemcpy(table_out, d_table, (size_t)n * sizeof(hashElement), cudaMemcpyDeviceToHost));
+done:
+	cudaFree(d_cloud); cudaFree(d_table); cudaFree(d_buckets); cudaFree(d_mean);
+	return rc;
+}
+
+/* CCudaWrapper::findBestYaw (cudaWrapper.cpp:662-836) without Eigen: the caller supplies the matrices upstream takes from
+ * Eigen — second_transform and first_transform.inverse() as row-major 3x4 (NULL = skip that transform) and ONE row-major
+ * 3x4 yaw matrix per angle (yaw_mats: n_angles x 12).  counts_out: matched queries per angle
+ * (cudaCountNumberOfSemanticNearestNeighbours).  Returns the index of the winning angle in *best_out (strict >). */
+int ref_find_best_yaw_host(const void *first, int n1, const void *second, int n2, const float *second_m, const float *first_inv_m,
+		float bucket_size, float ext, float search_radius, int max_inner, int max_outer,
+		const float *yaw_mats, int n_angles, int *counts_out, int *best_out)
+{
+	int rc = 0, dev = 0;
+	ref_point_t *d_first = 0, *d_second = 0, *d_rot = 0;
+	hashElement *d_table = 0;
+	bucket *d_buckets = 0;
+	int *d_nn = 0;
+	gridParameters p;
+	memset(&p, 0, sizeof(p));
+	cudaGetDevice(&dev);
+	int threads = ref_threads_for_device(dev);
+	int best = -1, best_n = 0;
+	REF_CHECK(cudaMalloc((void **)&d_first, (size_t)n1 * sizeof(ref_point_t)));
+	REF_CHECK(cudaMemcpy(d_first, first, (size_t)n1 * sizeof(ref_point_t), cudaMemcpyHostToDevice));
+	REF_CHECK(cudaMalloc((void **)&d_second, (size_t)n2 * sizeof(ref_point_t)));
+	REF_CHECK(cudaMemcpy(d_second, second, (size_t)n2 * sizeof(ref_point_t), cudaMemcpyHostToDevice));
+	for (int k = 0; k < 2; k++) {
+		const float *m = k == 0 ? second_m : first_inv_m;
+		if (m) REF_CHECK(cudaTransformPointCloud(threads, d_second, n2, m[0], m[4], m[8], m[1], m[5], m[9], m[2], m[6], m[10], m[3], m[7], m[11]));
+	}
+	REF_CHECK(cudaMalloc((void **)&d_rot, (size_t)n2 * sizeof(ref_point_t)));
+	REF_CHECK(cudaCalculateGridParams(d_first, n1, bucket_size, bucket_size, bucket_size, ext, p));
+	REF_CHECK(cudaMalloc((void **)&d_table, (size_t)n1 * sizeof(hashElement)));
+	REF_CHECK(cudaMalloc((void **)&d_buckets, (size_t)p.number_of_buckets * sizeof(bucket)));
+	REF_CHECK(cudaMalloc((void **)&d_nn, (size_t)n2 * sizeof(int)));
+	REF_CHECK(cudaCalculateGrid(threads, d_first, d_buckets, d_table, n1, p));
+	for (int a = 0; a < n_angles; a++) {
+		const float *m = yaw_mats + 12 * (size_t)a;
+		int number_of_nn = 0;
+		REF_CHECK(cudaTransformPointCloud(threads, d_second, n2, d_rot, n2, m[0], m[4], m[8], m[1], m[5], m[9], m[2], m[6], m[10], m[3], m[7], m[11]));
+		REF_CHECK(cudaCountNumberOfSemanticNearestNeighbours(threads, d_first, n1, d_rot, n2, d_table, d_buckets, p, search_radius,
+				max_inner, max_outer, d_nn, number_of_nn));
+		if (counts_out) counts_out[a] = number_of_nn;
+		if (number_of_nn > best_n) { best_n = number_of_nn; best = a; }
+	}
+	if (best_out) *best_out = best;
+done:
+	cudaFree(d_first); cudaFree(d_second); cudaFree(d_rot); cudaFree(d_table); cudaFree(d_buckets); cudaFree(d_nn);
+	return rc;
+}
+
 } /* extern "C" */

@@ -60,3 +60,43 @@ def register_ls_host(obs, pose6, dof):
     x = np.zeros(6)
     st = oracle.ref().ref_register_ls_host(_ptr(obs), C.c_int(len(obs)), _ptr(p), C.c_int(dof), _ptr(x))
     return st, p, x[:dof]
+
+
+# -- pre-registration steps: the reference's kernels behind the call sequences of cudaWrapper.cpp:118-342, 662-836 --
+def remove_noise_host(cloud, res, ext, threshold):
+    markers = np.zeros(len(cloud), dtype=np.uint8)
+    st = oracle.ref().ref_remove_noise_host(_ptr(cloud), C.c_int(len(cloud)), C.c_float(res), C.c_float(ext), C.c_int(threshold), _ptr(markers))
+    assert st == 0, st
+    return markers
+
+
+def downsample_host(cloud, res, ext):
+    markers = np.zeros(len(cloud), dtype=np.uint8)
+    st = oracle.ref().ref_downsample_host(_ptr(cloud), C.c_int(len(cloud)), C.c_float(res), C.c_float(ext), _ptr(markers))
+    assert st == 0, st
+    return markers
+
+
+def classify_host(cloud, radius, curvature_threshold, ground_z, plane_points, ext, max_inner, max_outer, viewpoint=(0.0, 0.0, 0.0)):
+    out = np.ascontiguousarray(cloud).copy()
+    mean = np.zeros((len(out), 3), dtype=np.float32)
+    table = np.zeros(len(out), dtype=oracle.HASH_DTYPE)
+    st = oracle.ref().ref_classify_host(_ptr(out), C.c_int(len(out)), C.c_float(radius), C.c_float(curvature_threshold), C.c_float(ground_z),
+                                        C.c_int(plane_points), C.c_float(ext), C.c_int(max_inner), C.c_int(max_outer),
+                                        C.c_float(viewpoint[0]), C.c_float(viewpoint[1]), C.c_float(viewpoint[2]), _ptr(mean), _ptr(table))
+    assert st == 0, st
+    return out, mean, table
+
+
+def find_best_yaw_host(first, second, second_transform, first_transform_inverse, bucket, ext, radius, max_inner, max_outer,
+                       angle_start, angle_finish, angle_step):
+    angles, mats = oracle.yaw_matrices(angle_start, angle_finish, angle_step)
+    counts = np.zeros(len(angles), dtype=np.int32)
+    best = C.c_int(-1)
+    a = None if second_transform is None else np.ascontiguousarray(np.asarray(second_transform, dtype=np.float32).reshape(-1)[:12])
+    b = None if first_transform_inverse is None else np.ascontiguousarray(np.asarray(first_transform_inverse, dtype=np.float32).reshape(-1)[:12])
+    st = oracle.ref().ref_find_best_yaw_host(_ptr(first), C.c_int(len(first)), _ptr(second), C.c_int(len(second)), _ptr(a), _ptr(b),
+                                             C.c_float(bucket), C.c_float(ext), C.c_float(radius), C.c_int(max_inner), C.c_int(max_outer),
+                                             _ptr(mats), C.c_int(len(angles)), _ptr(counts), C.byref(best))
+    assert st == 0, st
+    return (float(angles[best.value]) if best.value >= 0 else float(angle_start)), counts
