@@ -42,6 +42,7 @@ extern "C" {
 #define M3DREG_E_SIZE_MISMATCH   (-7)   /* ref: cudaWrapper.cpp:354 silently returns; we report it    */
 #define M3DREG_E_NO_NCCL         (-8)   /* multi-GPU sweep without NCCL in the process / without a communicator */
 #define M3DREG_E_NCCL            (-9)   /* an NCCL call returned an error                            */
+#define M3DREG_E_IO              (-10)  /* a file could not be read / written / parsed (m3dreg_node.h) */
 
 /* ---- labels (ref: include/lesson_16.h:9-12) --------------------------------------------- */
 #define M3DREG_LABEL_PLANE   0

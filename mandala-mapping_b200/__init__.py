@@ -50,6 +50,15 @@ EXPORTS = [
     "m3dreg_nccl_init", "m3dreg_nccl_attach",
     "m3dreg_remove_noise_host", "m3dreg_downsample_host", "m3dreg_classify_host", "m3dreg_find_best_yaw_host",
 ]
+#: every symbol include/m3dreg_node.h declares
+NODE_EXPORTS = [
+    "m3dreg_pcd_write_binary", "m3dreg_pcd_read", "m3dreg_model_create", "m3dreg_model_destroy", "m3dreg_model_load", "m3dreg_model_save",
+    "m3dreg_model_set_algorithm_name", "m3dreg_model_set_dataset_path", "m3dreg_model_get_dataset_path", "m3dreg_model_set_affine",
+    "m3dreg_model_get_affine", "m3dreg_model_set_cloud_name", "m3dreg_model_get_cloud_name", "m3dreg_model_scan_count", "m3dreg_model_scan_id",
+    "m3dreg_model_full_cloud_path", "m3dreg_node_default_params", "m3dreg_node_create", "m3dreg_node_destroy",
+    "m3dreg_node_register_single_scan", "m3dreg_node_scan_count", "m3dreg_node_get_pose", "m3dreg_node_scan_size", "m3dreg_node_get_scan",
+    "m3dreg_node_scan_id", "m3dreg_node_metascan", "m3dreg_node_register_all", "m3dreg_node_load_map", "m3dreg_node_set_initial_pose",
+]
 
 
 class RegParams(C.Structure):
@@ -119,7 +128,7 @@ def sources() -> list[str]:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a into libm3dreg.so, in-tree (nvcc cross-compiles without a GPU)."""
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "m3dreg.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "m3dreg.h"), os.path.join(ROOT, "include", "m3dreg_node.h")]
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
     if force or stale:
         cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
@@ -152,8 +161,9 @@ def lib() -> C.CDLL:
         L.m3dreg_get_stream.restype = C.c_void_p
         L.m3dreg_launch_count.restype = C.c_int64
         L.m3dreg_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
-        for name in EXPORTS:
+        for name in EXPORTS + NODE_EXPORTS:
             getattr(L, name)
+        L.m3dreg_model_create.restype = C.c_void_p
         _lib = L
     return _lib
 
@@ -483,3 +493,181 @@ def euler_to_matrix(omfika, xyz):
 
 
 from .wrapper import CCudaWrapper, Observations  # noqa: E402,F401
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# include/m3dreg_node.h: persistence formats and the per-scan driver (class gpu6DSLAM without ROS / PCL / Eigen / Boost)
+# ---------------------------------------------------------------------------------------------------------------------
+def pcd_write_binary(path: str, cloud: np.ndarray):
+    """pcl::io::savePCDFileBinary for the 40-byte point type (packed 38-byte records, see formats_host.inl)."""
+    _check(lib().m3dreg_pcd_write_binary(str(path).encode(), _p(np.ascontiguousarray(cloud)), C.c_int(len(cloud))), "m3dreg_pcd_write_binary")
+
+
+def pcd_read(path: str) -> np.ndarray:
+    n = C.c_int(0)
+    _check(lib().m3dreg_pcd_read(str(path).encode(), None, C.c_int(0), C.byref(n)), "m3dreg_pcd_read")
+    out = np.zeros(n.value, dtype=POINT_DTYPE)
+    if n.value:
+        _check(lib().m3dreg_pcd_read(str(path).encode(), _p(out), C.c_int(n.value), C.byref(n)), "m3dreg_pcd_read")
+    return out
+
+
+class Model:
+    """class data_model (include/data_model.hpp): the XML pose model."""
+
+    def __init__(self):
+        self._h = C.c_void_p(lib().m3dreg_model_create())
+
+    def close(self):
+        if self._h:
+            lib().m3dreg_model_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load(self, path):
+        return lib().m3dreg_model_load(self._h, str(path).encode()) == 0
+
+    def save(self, path):
+        _check(lib().m3dreg_model_save(self._h, str(path).encode()), "m3dreg_model_save")
+
+    def set_algorithm_name(self, name):
+        lib().m3dreg_model_set_algorithm_name(self._h, name.encode())
+
+    def set_dataset_path(self, path):
+        lib().m3dreg_model_set_dataset_path(self._h, path.encode())
+
+    def _str(self, fn, *args):
+        buf = C.create_string_buffer(4096)
+        st = fn(self._h, *args, buf, C.c_int(4096))
+        return None if st < 0 else buf.value.decode()
+
+    def dataset_path(self):
+        return self._str(lib().m3dreg_model_get_dataset_path)
+
+    def set_affine(self, scan_id, m):
+        lib().m3dreg_model_set_affine(self._h, scan_id.encode(), _p(np.ascontiguousarray(m, dtype=np.float32).reshape(16)))
+
+    def affine(self, scan_id):
+        m = np.zeros(16, dtype=np.float32)
+        return m.reshape(4, 4) if lib().m3dreg_model_get_affine(self._h, scan_id.encode(), _p(m)) == 0 else None
+
+    def set_cloud_name(self, scan_id, fn):
+        lib().m3dreg_model_set_cloud_name(self._h, scan_id.encode(), fn.encode())
+
+    def cloud_name(self, scan_id):
+        return self._str(lib().m3dreg_model_get_cloud_name, scan_id.encode())
+
+    def scan_ids(self):
+        n = lib().m3dreg_model_scan_count(self._h)
+        return [self._str(lib().m3dreg_model_scan_id, C.c_int(k)) for k in range(max(n, 0))]
+
+    def full_cloud_path(self, scan_id):
+        return self._str(lib().m3dreg_model_full_cloud_path, scan_id.encode())
+
+
+class NodeParams(C.Structure):
+    """m3dreg_node_params (include/m3dreg_node.h) = the public parameter members of class gpu6DSLAM."""
+    _fields_ = [("noise_removal_resolution", C.c_float), ("noise_removal_number_of_points_in_bucket_threshold", C.c_int32),
+                ("noise_removal_bounding_box_extension", C.c_float), ("downsampling_resolution", C.c_float),
+                ("semantic_classification_normal_vectors_search_radius", C.c_float), ("semantic_classification_curvature_threshold", C.c_float),
+                ("semantic_classification_ground_Z_coordinate_threshold", C.c_float),
+                ("semantic_classification_number_of_points_needed_for_plane_threshold", C.c_int32),
+                ("semantic_classification_max_number_considered_in_INNER_bucket", C.c_int32),
+                ("semantic_classification_max_number_considered_in_OUTER_bucket", C.c_int32),
+                ("semantic_classification_bounding_box_extension", C.c_float),
+                ("slam_registerLastArrivedScan_distance_threshold", C.c_float), ("slam_registerAll_distance_threshold", C.c_float),
+                ("slam_number_of_observations_threshold", C.c_int32),
+                ("slam_search_radius_step", C.c_float * 3), ("slam_bucket_size_step", C.c_float * 3),
+                ("slam_registerLastArrivedScan_number_of_iterations_step", C.c_int32 * 3), ("slam_registerAll_number_of_iterations_step", C.c_int32 * 3),
+                ("slam_search_radius_register_all", C.c_float), ("slam_bucket_size_step_register_all", C.c_float),
+                ("slam_bounding_box_extension", C.c_float), ("slam_max_number_considered_in_INNER_bucket", C.c_int32),
+                ("slam_max_number_considered_in_OUTER_bucket", C.c_int32), ("slam_observation_weight", C.c_float * 4),
+                ("findBestYaw_start_angle", C.c_float), ("findBestYaw_finish_angle", C.c_float), ("findBestYaw_step_angle", C.c_float),
+                ("findBestYaw_bucket_size", C.c_float), ("findBestYaw_bounding_box_extension", C.c_float), ("findBestYaw_search_radius", C.c_float),
+                ("findBestYaw_max_number_considered_in_INNER_bucket", C.c_int32), ("findBestYaw_max_number_considered_in_OUTER_bucket", C.c_int32),
+                ("viewpoint", C.c_float * 3), ("cutoff_z_min", C.c_float), ("cutoff_z_max", C.c_float), ("cutoff_xy2_min", C.c_float),
+                ("number_of_last_scans_in_sweeps", C.c_int32), ("dof", C.c_int32), ("use_find_best_yaw", C.c_int32), ("write_files", C.c_int32)]
+
+
+class NodeScanStats(C.Structure):
+    _fields_ = [("n_raw", C.c_int32), ("n_after_cutoff", C.c_int32), ("n_after_noise_removal", C.c_int32), ("n_after_downsampling", C.c_int32),
+                ("pair_iterations", C.c_int32), ("pair_last_status", C.c_int32), ("sweeps", C.c_int32), ("sweep_solved_last", C.c_int32),
+                ("yaw_deg", C.c_float), ("preprocess_ms", C.c_float), ("register_ms", C.c_float)]
+
+
+def node_default_params() -> NodeParams:
+    p = NodeParams()
+    lib().m3dreg_node_default_params(C.byref(p))
+    return p
+
+
+class Node:
+    """class gpu6DSLAM (include/gpu6DSLAM.h) replayed without ROS: registerSingleScan, getMetascan, registerAll, loadmapfromfile."""
+
+    def __init__(self, ctx: "Context", params: NodeParams | None = None, root_folder: str | None = None):
+        self._h = C.c_void_p()
+        self.ctx = ctx
+        _check(lib().m3dreg_node_create(C.byref(self._h), ctx._h, C.byref(params) if params is not None else None,
+                                        root_folder.encode() if root_folder else None), "m3dreg_node_create")
+
+    def close(self):
+        if self._h:
+            lib().m3dreg_node_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def register_single_scan(self, cloud: np.ndarray, mtf: np.ndarray, iso_time: str) -> NodeScanStats:
+        st = NodeScanStats()
+        _check(lib().m3dreg_node_register_single_scan(self._h, _p(np.ascontiguousarray(cloud)), C.c_int(len(cloud)),
+                                                      _p(np.ascontiguousarray(mtf, dtype=np.float32).reshape(16)), iso_time.encode(), C.byref(st)),
+               "m3dreg_node_register_single_scan")
+        return st
+
+    def __len__(self):
+        return int(lib().m3dreg_node_scan_count(self._h))
+
+    def pose(self, i: int):
+        """-> (registered, tf) row-major 4x4"""
+        r = np.zeros(16, dtype=np.float32); t = np.zeros(16, dtype=np.float32)
+        _check(lib().m3dreg_node_get_pose(self._h, C.c_int(i), _p(r), _p(t)), "m3dreg_node_get_pose")
+        return r.reshape(4, 4), t.reshape(4, 4)
+
+    def scan(self, i: int) -> np.ndarray:
+        n = _check(lib().m3dreg_node_scan_size(self._h, C.c_int(i)), "m3dreg_node_scan_size", allow=range(1, 1 << 31))
+        out = np.zeros(n, dtype=POINT_DTYPE)
+        _check(lib().m3dreg_node_get_scan(self._h, C.c_int(i), _p(out), C.c_int(n)), "m3dreg_node_get_scan")
+        return out
+
+    def scan_id(self, i: int) -> str:
+        buf = C.create_string_buffer(512)
+        lib().m3dreg_node_scan_id(self._h, C.c_int(i), buf, C.c_int(512))
+        return buf.value.decode()
+
+    def metascan(self) -> np.ndarray:
+        n = C.c_int(0)
+        _check(lib().m3dreg_node_metascan(self._h, None, C.c_int(0), C.byref(n)), "m3dreg_node_metascan")
+        out = np.zeros(n.value, dtype=POINT_DTYPE)
+        if n.value:
+            _check(lib().m3dreg_node_metascan(self._h, _p(out), C.c_int(n.value), C.byref(n)), "m3dreg_node_metascan")
+        return out
+
+    def register_all(self) -> int:
+        solved = C.c_int(0)
+        _check(lib().m3dreg_node_register_all(self._h, C.byref(solved)), "m3dreg_node_register_all")
+        return int(solved.value)
+
+    def load_map(self, xml_path: str):
+        _check(lib().m3dreg_node_load_map(self._h, str(xml_path).encode()), "m3dreg_node_load_map")
+
+    def set_initial_pose(self, pose: np.ndarray):
+        _check(lib().m3dreg_node_set_initial_pose(self._h, _p(np.ascontiguousarray(pose, dtype=np.float32).reshape(16))), "m3dreg_node_set_initial_pose")

@@ -783,6 +783,7 @@ const char *m3dreg_status_string(int status)
 	case M3DREG_E_SIZE_MISMATCH: return "size mismatch";
 	case M3DREG_E_NO_NCCL: return "NCCL not available (libnccl.so.2 not found) or no communicator attached";
 	case M3DREG_E_NCCL: return "NCCL call failed";
+	case M3DREG_E_IO: return "file could not be read, written or parsed";
 	default: break;
 	}
 	if (status > 0) return cudaGetErrorString((cudaError_t)status);
@@ -1653,3 +1654,6 @@ int m3dreg_sweep_solve(m3dreg_ctx *c, const double *d_neq, int n_scans, int scan
 
 #include "slam_host.inl"
 #include "preproc_host.inl"
+#include "../../include/m3dreg_node.h"
+#include "formats_host.inl"
+#include "node_host.inl"

@@ -227,15 +227,15 @@ def icp_iteration(first_local, second_global, pose, params: RegParams, want_nn=F
     return st, pose.reshape(4, 4), int(n_obs.value), x, nn
 
 
-def register_all_sweep(scans, poses, params: RegParams, pair_thr=10.0):
+def register_all_sweep(scans, poses, params: RegParams, pair_thr=10.0, first_optimised=0):
     off = np.zeros(len(scans) + 1, dtype=np.int64)
     off[1:] = np.cumsum([len(s) for s in scans])
     allp = _synth.concat_points(scans)
     poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(len(scans), 16).copy()
     neq = np.zeros((len(scans), 28))
     status = np.zeros(len(scans), dtype=np.int32)
-    lib().orc_register_all_sweep(_ptr(allp), _ptr(off), C.c_int(len(scans)), _ptr(poses), C.byref(params),
-                                 C.c_float(pair_thr), _ptr(neq), _ptr(status))
+    lib().orc_register_all_sweep_last(_ptr(allp), _ptr(off), C.c_int(len(scans)), _ptr(poses), C.byref(params),
+                                      C.c_float(pair_thr), C.c_int(first_optimised), _ptr(neq), _ptr(status))
     return poses.reshape(-1, 4, 4), neq, status
 
 

@@ -745,13 +745,27 @@ static void pack_neq(const double *N6, const double *b6, double count, double *o
 int orc_register_all_sweep(const orc_point *scans, const int64_t *off, int n_scans,
 		float *poses, const orc_reg_params *prm, float pair_thr, double *neq_out, int32_t *status_out)
 {
+	return orc_register_all_sweep_last(scans, off, n_scans, poses, prm, pair_thr, 0, neq_out, status_out);
+}
+
+/* registerAll(cudaWrapper, radius, bucket, number_of_last_EOZ) (SL:424-597): only scans first_optimised .. n_scans-1
+ * (= the last number_of_last_EOZ) are optimised, the earlier ones keep their pose and serve as neighbours (SL:430-432). */
+int orc_register_all_sweep_last(const orc_point *scans, const int64_t *off, int n_scans,
+		float *poses, const orc_reg_params *prm, float pair_thr, int first_optimised, double *neq_out, int32_t *status_out)
+{
 	float *newp = (float *)malloc((size_t)n_scans * 16 * sizeof(float));
+	memcpy(newp, poses, (size_t)n_scans * 16 * sizeof(float));
+	if (first_optimised < 0) first_optimised = 0;
+	for (int i = 0; i < first_optimised && i < n_scans; i++) {
+		if (status_out) status_out[i] = 0;
+		if (neq_out) memset(neq_out + 28 * (size_t)i, 0, 28 * sizeof(double));
+	}
 	int64_t maxn = 0;
 	for (int i = 0; i < n_scans; i++) if (off[i + 1] - off[i] > maxn) maxn = off[i + 1] - off[i];
 	orc_point *pc1 = (orc_point *)malloc((size_t)maxn * sizeof(orc_point));
 	orc_point *pc2 = (orc_point *)malloc((size_t)maxn * sizeof(orc_point));
 	int32_t *nn = (int32_t *)malloc((size_t)maxn * sizeof(int32_t));
-	for (int i = 0; i < n_scans; i++) {
+	for (int i = first_optimised; i < n_scans; i++) {
 		int n1 = (int)(off[i + 1] - off[i]);
 		float of1[3], t1[3], pose1[16];
 		orc_matrix4_to_euler(poses + 16 * i, of1, t1);

@@ -104,6 +104,9 @@ int  orc_icp_iteration(const orc_point *first_local, int n_first, const orc_poin
 int  orc_register_all_sweep(const orc_point *scans_local, const int64_t *offsets, int n_scans,
 		float *poses4x4, const orc_reg_params *prm, float pair_distance_threshold,
 		double *neq_out /* n_scans*28 or NULL */, int32_t *status_out /* n_scans or NULL */);
+int  orc_register_all_sweep_last(const orc_point *scans_local, const int64_t *offsets, int n_scans,
+		float *poses4x4, const orc_reg_params *prm, float pair_distance_threshold, int first_optimised,
+		double *neq_out, int32_t *status_out);
 
 /* pre-registration steps --------------------------------------------------------- */
 void orc_remove_noise_markers(const orc_point *cloud, int n, float res, float ext, int threshold, uint8_t *markers);

@@ -11,8 +11,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
-    text = open(os.path.join(ROOT, "include", "m3dreg.h")).read()
+def _declared(header="m3dreg.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(m3dreg_[a-z0-9_]+)\s*\(", text)))
 
@@ -25,6 +25,8 @@ def test_header_symbols_exported(pkg):
     out = subprocess.check_output(["nm", "-D", "--defined-only", pkg.LIB_PATH]).decode()
     exported = set(re.findall(r" T (m3dreg_[a-z0-9_]+)", out))
     assert set(names) <= exported
+    node_names = _declared("m3dreg_node.h")            # the callers / formats either side of the path
+    assert sorted(pkg.NODE_EXPORTS) == node_names and set(node_names) <= exported
     L = pkg.lib()
     assert L.m3dreg_version() == 100
     assert L.m3dreg_status_string(-3).decode().startswith("normal equations")
@@ -48,6 +50,21 @@ int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(m3dreg_po
         subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
         vals = [int(v) for v in subprocess.check_output([os.path.join(d, "t")]).split()]
     assert vals == [40, 8, 12, 64, 40, 28, 48, 20, 32]
+    # the node's parameter block: the Python mirror has the header's size, and the defaults are the reference's
+    src2 = r'''
+#include <stdio.h>
+#include "m3dreg_node.h"
+int main(void){ printf("%zu %zu\n", sizeof(m3dreg_node_params), sizeof(m3dreg_node_scan_stats)); return 0; }
+'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src2)
+        subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
+        vals = [int(v) for v in subprocess.check_output([os.path.join(d, "t")]).split()]
+    assert vals == [C.sizeof(pkg.NodeParams), C.sizeof(pkg.NodeScanStats)]
+    p = pkg.node_default_params()
+    assert (p.noise_removal_resolution, p.downsampling_resolution, p.slam_number_of_observations_threshold) == (0.5, np.float32(0.3), 100)
+    assert list(p.slam_search_radius_step) == [2.5, 2.0, 1.0] and list(p.slam_registerLastArrivedScan_number_of_iterations_step) == [30, 30, 30]
+    assert list(p.slam_observation_weight) == [10.0, 1.0, 10.0, 10.0] and p.dof == 4 and list(p.viewpoint) == [0.0, 0.0, 2.0]
 
 
 def test_no_cpu_fallback(pkg):
