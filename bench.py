@@ -49,7 +49,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    """SM clock + throttle reasons DURING the timed region: NVML polled from a thread every millisecond (the timed region
+    of a default run is a few milliseconds — a 100 ms nvidia-smi poll cannot see it), plus one reading right before and
+    right after.  nvidia-smi is only the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -58,8 +60,59 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.thread = None
+        self.nvml = None
+        self.handle = None
+        self.samples = []          # (sm MHz, reasons bitmask)
+        self.edge = []             # readings right before / right after
+        self.stop_flag = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            uuid = None
+            try:
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+            except Exception:
+                uuid = None
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if isinstance(uuid, str) else uuid) if uuid else None
+            except Exception:
+                self.handle = None
+            if self.handle is None:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
+
+    def _read(self):
+        n = self.nvml
+        mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            reasons = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            try:
+                reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            except Exception:
+                reasons = 0
+        return float(mhz), int(reasons)
 
     def start(self):
+        if self.nvml:
+            try:
+                self.edge.append(self._read())
+            except Exception:
+                self.nvml = None
+        if self.nvml:
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append(self._read())
+                    except Exception:
+                        break
+                    time.sleep(0.001)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -73,8 +126,31 @@ class ClockSampler:
         self.thread.start()
 
     def stop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.nvml:
+            self.stop_flag = True
+            try:
+                self.edge.append(self._read())
+            except Exception:
+                pass
+            if self.thread:
+                self.thread.join(timeout=1.0)
+            n = self.nvml
+            bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                    "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                    "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                    "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4))}
+            allr = self.samples + self.edge
+            reasons = sorted(k for k, b in bits.items() if any(r & b for _, r in allr))
+            try:
+                mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+            except Exception:
+                mx = None
+            sm = [m for m, _ in (self.samples or self.edge)]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(self.samples),
+                    "sm_mhz_before_after": [m for m, _ in self.edge], "source": "NVML polled every ms during the timed region", "reasons": reasons}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither NVML nor nvidia-smi available"]}
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -82,7 +158,6 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
@@ -95,7 +170,7 @@ class ClockSampler:
                 if f[3 + k].lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100", "reasons": sorted(reasons)}
 
 
 def ncu_traffic(kernel, workload):
@@ -544,8 +619,18 @@ def main():
     stage_names = ["box pass (transform in registers + bounding box)", "grid (keys, radix sort, bucket table, candidate sets)",
                    "semantic NN (k_nn_search_hull)", "normal equations + solve"]
     dom = int(np.argmax(stage_ms))
-    nn_ms = float(stage_ms[2])
-    nn_bytes = nn_alg_bytes(n1, n2, nb)
+    if args.mode == "icp":
+        # the dominant kernel of the ICP iteration is the semantic search: ONE launch per iteration = the whole stage
+        roof_kernel, roof_stage = "k_nn_search_hull", 2
+        nn_bytes = nn_alg_bytes(n1, n2, nb)
+    else:
+        # NDT (no reference implementation): no search kernel runs; report the stage that dominates, with SURVEY 8d's stage bytes
+        # (grid: 20*N1 + 12*B plus the 12*N1 coordinates the per-bucket statistics read; queries: 16*N2; reduction: 4*N2 + 40*Nc)
+        roof_stage = dom
+        roof_kernel = ["k_transform_soa<true>", "k_grid_head + k_radix_scan/scatter + k_finalize_grid + k_ndt_accumulate_points + k_ndt_finalize_buckets",
+                       "k_ndt_accumulate_queries", "k_ndt_accumulate_queries + k_ndt_normal_equations"][dom]
+        nn_bytes = [48 * n1, 32 * n1 + 12 * nb, 16 * n2, 20 * n2 + 40 * nc][dom]
+    nn_ms = float(stage_ms[roof_stage])
     nn_gbs = nn_bytes / (nn_ms * 1e-3) / 1e9
     iter_bytes = alg_bytes(n1, n2, nb, nc)
     iter_gbs = iter_bytes / (ms_per_step * 1e-3) / 1e9
@@ -575,6 +660,26 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * (n1 + n2) * e2e_steps / float(te.item())
+
+    # ---------------- the reference's schedule from the initial perturbation (gpu6DSLAM.cpp:159-172) ----------------
+    # The timed steps above run after the warm-up iterations, i.e. on a nearly aligned pair (the search's best case).  This
+    # record times the three steps of registerLastArrivedScan as upstream runs them: 30 iterations each at radius = bucket =
+    # 2.5 / 2.0 / 1.0 m, 4-DOF, starting from the SURVEY 8d perturbation: unconverged correspondences and larger buckets.
+    schedule = None
+    if args.mode == "icp" and world == 1:
+        try:
+            pose_s = np.ascontiguousarray(pose_init, dtype=np.float32).copy()
+            schedule = {"dof": 4, "steps": []}
+            for rb in (2.5, 2.0, 1.0):
+                sp = pkg.default_params(rb, dof=4)
+                pose_w, _ = ctx.icp_pair(0, 1, pose_s, pose2, sp, 1)          # buffers for this bucket size: outside the timed call
+                pose_s, sst = ctx.icp_pair(0, 1, pose_s, pose2, sp, 30)
+                schedule["steps"].append({"radius_m": rb, "bucket_m": rb, "iterations": int(sst.iterations_run), "us_per_iteration": float(sst.device_ms) * 1e3 / max(int(sst.iterations_run), 1),
+                                          "buckets": int(sst.n_buckets_last), "correspondences": int(sst.n_obs_last),
+                                          "translation_error_m": float(np.abs(pose_s[:3, 3] - pose_true[:3, 3]).max())})
+            schedule["total_ms"] = float(sum(s["us_per_iteration"] * s["iterations"] for s in schedule["steps"]) / 1e3)
+        except Exception as ex:  # pragma: no cover
+            schedule = {"failed": repr(ex)}
 
     ctx.close()
     slam_out = {}
@@ -608,7 +713,7 @@ def main():
             "launches_per_step": launches / args.steps,
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "k_nn_search_hull", "achieved": nn_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": nn_gbs / peak_gbs,
+                "bound": "hbm", "kernel": roof_kernel, "achieved": nn_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": nn_gbs / peak_gbs,
                 "traffic": ncu_traffic("k_nn_search_hull", args.workload) if args.mode == "icp" else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": nn_bytes, "launch_ms": nn_ms,
                 "dominant_stage": stage_names[dom],
                 "nn_candidate_evaluations_per_query": evals_per_query,
@@ -621,6 +726,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": 40 * (n1 + n2), "d2h_bytes_per_step": 4 * n2 + 64,
                     "steps": e2e_steps, "call": "m3dreg_icp_iteration_host (both 40-B clouds H2D from pinned memory, nn + pose D2H, every step)"},
             "cpu_baseline": cpu,
+            "schedule": schedule,
             "slam": slam_out or None,
             "result": {"status": int(st.last_status), "translation_error_m": float(np.abs(pose_out[:3, 3] - pose_true[:3, 3]).max())},
         }
