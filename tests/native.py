@@ -42,6 +42,21 @@ def build_shim_host(force: bool = False) -> str:
     return SHIM_EXE
 
 
+def build_shim_program(name: str, force: bool = False) -> str:
+    """Any tests/csrc/<name>.cpp over the shim, linked against the product library (plain g++, no CUDA headers)."""
+    root = os.path.dirname(_HERE)
+    inc = os.path.join(root, "include")
+    libdir = os.path.join(root, "mandala-mapping_b200")
+    src, exe = os.path.join(_HERE, "csrc", name + ".cpp"), os.path.join(_HERE, "_build", name)
+    deps = [src, os.path.join(inc, "cuda_wrapper_shim.hpp"), os.path.join(inc, "m3dreg.h"), os.path.join(libdir, "libm3dreg.so")]
+    stale = (not os.path.exists(exe)) or any(os.path.getmtime(f) > os.path.getmtime(exe) for f in deps)
+    if force or stale:
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-ffp-contract=off", "-I", inc, "-o", exe, src,
+                               "-L", libdir, "-lm3dreg", "-Wl,-rpath," + libdir])
+    return exe
+
+
 EMUL_SO = os.path.join(_HERE, "_build", "libnn_emul.so")
 EMUL_SRC = os.path.join(_HERE, "csrc", "nn_emul.cpp")
 
