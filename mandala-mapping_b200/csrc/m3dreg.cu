@@ -156,6 +156,7 @@ struct m3dreg_ctx {
 	int nn_blocks_per_sm[2] = {0, 0};             /* resident blocks per SM of k_nn_search_hull<false|true> (occupancy API, once) */
 	unsigned long long *eval_counter = nullptr;   /* candidates staged by the NN search (warp-level), diagnostic */
 	int use_pdl = 1;             /* programmatic dependent launch for every kernel (env M3DREG_NO_PDL=1 disables) */
+	int nn_diag = 0;             /* env M3DREG_NN_DIAG=1: per-chunk time stamps of the profiling search kernel (tools/nn_tail.py) */
 	int nn_per_thread = 0;       /* test switch (env M3DREG_NN_PER_THREAD=1): k_nn_search instead of k_nn_search_grid */
 	NNTuning nn_tune = {16, 128, 8};   /* heuristics of k_nn_search_grid (env M3DREG_NN_RHO_DIV / _HULL_MIN / _HULL_RATIO override) */
 	/* The pairs of a registerAll sweep are scans up to the pair gate (10 m) apart: a good part of the queries has no partner
@@ -536,6 +537,7 @@ void launch_nn(m3dreg_ctx *c, const uint32_t *q_perm, int n2, const uint32_t *va
 		a.nn_out = nn_out; a.obs_rec = obs_rec; a.src_xyzl = src_xyzl; a.label_counts = label_counts;
 		a.eval_counter = c->profiling ? c->eval_counter : nullptr; a.seg_of_chunk = seg_of_chunk;
 		a.work = c->nn_work;
+		if (c->profiling && c->nn_diag) { cudaMemsetAsync(c->gb_dbg, 0, 16 * sizeof(unsigned long long), c->stream); a.diag = c->gb_dbg; }
 		/* persistent warps: one wave of resident blocks, chunks of 32 queries handed out by an atomic counter */
 		const int pi = c->profiling ? 1 : 0;
 		if (c->nn_blocks_per_sm[pi] <= 0) {
@@ -812,6 +814,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	{ const char *e = getenv("M3DREG_NN_RHO_DIV"); if (e && atoi(e) > 0) c->nn_tune.rho_div = atoi(e); }
 	{ const char *e = getenv("M3DREG_NN_HULL_MIN"); if (e && atoi(e) > 0) c->nn_tune.hull_min = atoi(e); }
 	{ const char *e = getenv("M3DREG_NN_HULL_RATIO"); if (e && atoi(e) > 0) c->nn_tune.hull_ratio = atoi(e); }
+	{ const char *e = getenv("M3DREG_NN_DIAG"); if (e) c->nn_diag = atoi(e) != 0 ? 1 : 0; }
 	{ const char *e = getenv("M3DREG_NN_SWEEP_RHO_DIV"); if (e && atoi(e) > 0) c->nn_tune_sweep.rho_div = atoi(e); }
 	{ const char *e = getenv("M3DREG_NN_SWEEP_HULL_MIN"); if (e && atoi(e) > 0) c->nn_tune_sweep.hull_min = atoi(e); }
 	{ const char *e = getenv("M3DREG_NN_SWEEP_HULL_RATIO"); if (e && atoi(e) > 0) c->nn_tune_sweep.hull_ratio = atoi(e); }

@@ -74,6 +74,10 @@ struct NNHullArgs {
 	unsigned long long *eval_counter;
 	const int *seg_of_chunk;
 	unsigned int *work;         /* [0] next chunk of 32 queries, [1] warps that ran out of work: both zero between launches */
+	/* profiling build with M3DREG_NN_DIAG=1 only (tools/nn_tail.py): [0] ~(earliest start), [1] latest chunk end, [2] sum of warp exits,
+	 * [3] warps, [4] longest chunk (ns), [5] sum of chunk times, [6] chunks, [7] chunks > 20 us, [8] chunks > 50 us, [9] time in chunks
+	 * that searched per lane, [10] such chunks */
+	unsigned long long *diag;
 };
 
 /* the lane's conservative box of fine columns for dist <= tau (nn_query()'s box), clamped to its 27-neighbourhood */
@@ -168,6 +172,9 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 	chunk = __shfl_sync(full, chunk, 0);
 	if (chunk >= n_chunks) break;
 	const int qi = (chunk << 5) + lane;
+	unsigned long long t_chunk = 0;
+	bool chunk_fell_back = false;
+	if (COUNT && a.diag) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_chunk)); if (lane == 0) atomicMax(a.diag, ~t_chunk); }
 
 	unsigned int evals = 0;
 	int best_l = kNNNone, best_j = -1, label = -1;                     /* best_j: the winner's slot in the candidate set (-1: found by nn_query()) */
@@ -190,6 +197,7 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 	if (!nn_columns_usable(nbx, nby, nbz)) {                            /* warp-uniform */
 		if (active) { const int2 fr = nnh_query_fallback(&a, qx, qy, qz, label, qi); best_l = fr.x; evals += (unsigned int)fr.y; }
 		active = false;
+		if (COUNT) chunk_fell_back = true;
 	}
 
 	unsigned todo = __ballot_sync(full, active);
@@ -228,6 +236,7 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 						}
 						if (unsettled) { const int2 fr = nnh_query_fallback(&a, qx, qy, qz, label, qi); best_l = fr.x; best_j = -1; evals += (unsigned int)fr.y; }
 						unsettled = false;
+						if (COUNT) chunk_fell_back = true;
 						break;
 					}
 				}
@@ -452,7 +461,22 @@ __global__ void __launch_bounds__(kNNHThreads, M3D_NNH_MINBLOCKS) k_nn_search_hu
 			if (m && lane == Lb) atomicAdd(&lc[Lb], (unsigned long long)__popc(m));
 		}
 	}
+	if (COUNT && a.diag && lane == 0) {
+		unsigned long long t1;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		const unsigned long long dt = t1 - t_chunk;
+		atomicMax(a.diag + 4, dt); atomicAdd(a.diag + 5, dt); atomicAdd(a.diag + 6, 1ull);
+		if (dt > 20000ull) atomicAdd(a.diag + 7, 1ull);
+		if (dt > 50000ull) atomicAdd(a.diag + 8, 1ull);
+		if (chunk_fell_back) { atomicAdd(a.diag + 9, dt); atomicAdd(a.diag + 10, 1ull); }
+		atomicMax(a.diag + 1, t1);
+	}
 	}      /* persistent loop */
+	if (COUNT && a.diag && lane == 0) {
+		unsigned long long t1;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		atomicAdd(a.diag + 2, t1 - ~a.diag[0]); atomicAdd(a.diag + 3, 1ull);
+	}
 	/* the last warp to run out of work re-arms the counters for the next launch */
 	if (lane == 0) {
 		const unsigned int total_warps = gridDim.x * kNNHWarps;

@@ -51,14 +51,14 @@ int main(int argc, char **argv)
 		cudaWrapper.downsampling(pc, 0.3f, 0.3f);
 		cudaWrapper.classify(pc, 1.0f, 10.0f, 1.0f, 15, 1.0f, 100, 100, 0.0f, 0.0f, 0.0f);
 		if (pc.width != pc.points.size() || pc.height != 1) { std::fprintf(stderr, "width/height not maintained\n"); return 3; }
-		FILE *f = std::fopen(argv[5], "wb");
+		FILE *f = std::fopen(argv[4], "wb");
 		std::fwrite(pc.points.data(), sizeof(m3dreg_point), pc.points.size(), f);
 		std::fclose(f);
 		/* findBestYaw with the defaults of include/gpu6DSLAM.h:212-219 on a coarser angle grid */
 		m3dreg::Affine3f first_inv, second_tf, myaw;
 		float best = 0.0f;
 		cudaWrapper.findBestYaw(first, first_inv, other, second_tf, 1.0f, 1.0f, 0.3f, 50, 50, -12.0f, 12.0f, 1.5f, myaw, &best);
-		f = std::fopen(argv[4], "wb");
+		f = std::fopen(argv[5], "wb");
 		std::fwrite(&best, sizeof(float), 1, f);
 		std::fwrite(myaw.m, sizeof(float), 12, f);
 		std::fclose(f);
