@@ -307,7 +307,9 @@ int m3dreg_sweep_solve(m3dreg_ctx *ctx, const double *d_neq, int n_scans, int sc
  * context (m3dreg_scan_upload, slots 0..n_scans-1).  Every rank calls m3dreg_slam_sweep with the SAME poses:
  *   1. pair gate: (i, j), i in [first_optimised, n_scans), j != i, |t_i - t_j| < distance_threshold
  *      (slam_registerAll_distance_threshold, include/gpu6DSLAM.h:180; src/gpu6DSLAM.cpp:464-469);
- *   2. deterministic partition of the pairs over the ranks (whole groups of equal i, heavy groups split);
+ *   2. deterministic partition of the pairs over the ranks (whole groups of equal i, heavy groups split), balanced by point
+ *      counts in the first sweep and by the MEASURED device time of every group from then on (a second all-reduce of
+ *      n_scans doubles per sweep carries the measurements);
  *   3. m3dreg_sweep_accumulate of the rank's pairs into n_scans x 28 doubles on the device;
  *   4. ONE ncclAllReduce (sum, double) of that block over NVLink / NVSwitch, on the context's stream;
  *   5. gate on obs_threshold, Cholesky, pose update, Euler round trip of scans [first_optimised, n_scans) on every rank
@@ -344,6 +346,11 @@ int m3dreg_slam_copy_neq(m3dreg_ctx *ctx, double *neq_out, int n_scans);
  * rank that owns each.  Returns the number of pairs (or < 0); arrays may be NULL to only count.  sizes: points per scan. */
 int m3dreg_slam_plan(const float *poses, int n_scans, const int *sizes, float distance_threshold, int first_optimised,
 		int world, int *pair_i, int *pair_j, int *owner, int cap);
+/* The plan m3dreg_slam_sweep uses from its SECOND sweep on (multi-GPU only): instead of point counts the groups are
+ * balanced by the device time per pair the previous sweep measured for every scan's group (cost_per_pair, n_scans doubles,
+ * ms; <= 0 = not measured: the mean of the measured ones).  The measurement is all-reduced, so every rank plans alike. */
+int m3dreg_slam_plan_measured(const float *poses, int n_scans, const int *sizes, float distance_threshold, int first_optimised,
+		int world, const double *cost_per_pair, int *pair_i, int *pair_j, int *owner, int cap);
 
 /* ---- pre-registration steps on the registration path's own grid ---------------------
  * Every incoming scan passes through these before it is registered (src/gpu6DSLAM.cpp:63-85); they build the same

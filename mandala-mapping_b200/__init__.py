@@ -46,7 +46,7 @@ EXPORTS = [
     "m3dreg_export_last_grid", "m3dreg_export_last_nn", "m3dreg_sweep_zero", "m3dreg_sweep_accumulate",
     "m3dreg_sweep_solve", "m3dreg_icp_begin", "m3dreg_icp_step", "m3dreg_icp_end", "m3dreg_icp_copy_neq", "m3dreg_icp_set_neq_out",
     "m3dreg_set_profiling", "m3dreg_get_stage_ms", "m3dreg_set_pruning", "m3dreg_get_nn_evaluations", "m3dreg_get_nn_fallbacks",
-    "m3dreg_get_grid_phase_ns", "m3dreg_slam_sweep", "m3dreg_slam_copy_neq", "m3dreg_slam_plan", "m3dreg_nccl_get_unique_id",
+    "m3dreg_get_grid_phase_ns", "m3dreg_slam_sweep", "m3dreg_slam_copy_neq", "m3dreg_slam_plan", "m3dreg_slam_plan_measured", "m3dreg_nccl_get_unique_id",
     "m3dreg_nccl_init", "m3dreg_nccl_attach",
     "m3dreg_remove_noise_host", "m3dreg_downsample_host", "m3dreg_classify_host", "m3dreg_find_best_yaw_host",
 ]
@@ -98,6 +98,22 @@ def slam_plan(poses, sizes, distance_threshold: float = 10.0, first_optimised: i
     if rc < 0:
         raise M3dRegError(rc, "m3dreg_slam_plan")
     return pi[:cnt], pj[:cnt], ow[:cnt]
+
+
+def slam_plan_measured(poses, sizes, cost_per_pair, distance_threshold: float = 10.0, first_optimised: int = 0, world: int = 1):
+    """The plan of a sweep balanced by measured device time per pair of every scan's group (m3dreg_slam_plan_measured)."""
+    poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, 16)
+    sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+    cpp = np.ascontiguousarray(cost_per_pair, dtype=np.float64)
+    n = len(poses)
+    pi, pj = slam_plan(poses, sizes, distance_threshold, first_optimised, 1)[:2]
+    ow = np.zeros(max(len(pi), 1), dtype=np.int32)
+    pi2, pj2 = np.zeros_like(ow), np.zeros_like(ow)
+    rc = lib().m3dreg_slam_plan_measured(_p(poses), C.c_int(n), _p(sizes), C.c_float(distance_threshold), C.c_int(first_optimised), C.c_int(world),
+                                         _p(cpp), _p(pi2), _p(pj2), _p(ow), C.c_int(len(ow)))
+    if rc < 0:
+        raise M3dRegError(rc, "m3dreg_slam_plan_measured")
+    return pi2[:rc], pj2[:rc], ow[:rc]
 
 
 def nccl_unique_id() -> np.ndarray:

@@ -131,6 +131,16 @@ struct m3dreg_ctx {
 	DevBuf<double> d_pose6;      /* sweep: tx,ty,tz,om,fi,ka per scan             */
 	DevBuf<int> d_sweep_status;  /* sweep: per-scan solve status                  */
 	DevBuf<double> d_neq;        /* m3dreg_slam_sweep: n_scans x 28 normal-equation blocks (the all-reduce buffer) */
+	/* multi-GPU sweeps: measured device time of every scan's group of pairs (ms, %globaltimer stamps at the group boundaries),
+	 * all-reduced after the sweep; the NEXT sweep's partition balances these instead of point counts (the cost of a pair
+	 * depends on how much the two scans overlap, which point counts do not show) */
+	DevBuf<double> d_group_ms;
+	unsigned long long *stamp_last = nullptr;
+	std::vector<double> slam_group_ms, slam_cost_per_pair, slam_cost_per_pair_used;
+	/* m3dreg_slam_sweep sizes the sweep's buffers for the WHOLE pair list, not for this rank's share: the share changes from
+	 * sweep to sweep under the measured-cost partition, and a buffer that grows synchronises (and re-pins host memory) */
+	size_t sweep_reserve_segs = 0, sweep_reserve_second = 0, sweep_reserve_first = 0;
+	long long sweep_reserve_cap = 0;
 	void *nccl_comm = nullptr;   /* ncclComm_t of this rank (m3dreg_nccl_init / m3dreg_nccl_attach), 0 = single GPU */
 	bool nccl_owned = false;
 	int nccl_rank = 0, nccl_world = 0;
@@ -842,6 +852,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	c->grid_bar = (unsigned int *)take(16);
 	c->gb_dbg = (unsigned long long *)take(32 * sizeof(unsigned long long));
 	c->nn_work = (unsigned int *)take(16);
+	c->stamp_last = (unsigned long long *)take(16);
 	c->eval_counter = (unsigned long long *)take(16);
 	c->mats = (float *)take(32 * sizeof(float));
 	e = cudaMallocHost((void **)&c->h, sizeof(HostSmall));
@@ -870,7 +881,7 @@ void m3dreg_destroy(m3dreg_ctx *c)
 	c->hist.release(); c->buckets.release(); c->nn.release(); c->obs_rec.release(); c->cell_list.release(); c->aos_a.release(); c->aos_b.release();
 	c->obs.release(); c->partials.release(); c->ndt_acc.release(); c->ndt_qacc.release(); c->ndt_iacc.release(); c->table.release(); c->d_poses1.release(); c->d_pose6.release(); c->d_sweep_status.release();
 	c->d_segs.release(); c->d_seg_of_chunk.release(); c->d_seg_counts.release();
-	c->pp_aos.release(); c->pp_markers.release(); c->pp_tiles.release();
+	c->pp_aos.release(); c->pp_markers.release(); c->pp_tiles.release(); c->d_group_ms.release();
 	if (c->h_sweep) cudaFreeHost(c->h_sweep);
 	if (c->ps) cudaFree(c->ps);   /* base of the small block */
 	if (c->h) cudaFreeHost(c->h);
@@ -1203,6 +1214,7 @@ int m3dreg_scan_upload(m3dreg_ctx *c, int slot, const m3dreg_point *src, int n, 
 	}
 	LAUNCH(c, k_unpack_points, (n + 255) / 256, 256, d_src, n, s.xyzl, s.nrm);
 	s.n = n;
+	c->slam_cost_per_pair.clear();
 	c->active = false;
 	c->last_valid = false;
 	return presort_scan(c, s, d_src);
@@ -1221,6 +1233,7 @@ int m3dreg_scan_clear(m3dreg_ctx *c)
 	CK(cudaStreamSynchronize(c->stream));
 	for (auto &s : c->scans) s.release();
 	c->scans.clear();
+	c->slam_cost_per_pair.clear();      /* measured pair costs belong to the scans that are gone */
 	return 0;
 }
 
@@ -1486,8 +1499,28 @@ static int ensure_sweep_staging(m3dreg_ctx *c, size_t bytes)
 	return 0;
 }
 
+__global__ void k_group_stamp(double *__restrict__ group_ms, int finished_group, unsigned long long *__restrict__ last)
+{
+	pdl_enter();
+	if (threadIdx.x != 0) return;
+	unsigned long long now;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+	if (finished_group >= 0) group_ms[finished_group] += (double)(now - *last) * 1.0e-6;
+	*last = now;
+}
+
+static int sweep_accumulate_impl(m3dreg_ctx *c, int n_pairs, const int *pair_i, const int *pair_j, const float *poses, int n_scans,
+		const m3dreg_reg_params *prm, double *d_neq, double *d_group_ms);
+
 int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const int *pair_j, const float *poses, int n_scans,
 		const m3dreg_reg_params *prm, double *d_neq)
+{
+	return sweep_accumulate_impl(c, n_pairs, pair_i, pair_j, poses, n_scans, prm, d_neq, nullptr);
+}
+
+/* d_group_ms (n_scans doubles on the device, may be 0): += the device time of every scan's group of pairs */
+static int sweep_accumulate_impl(m3dreg_ctx *c, int n_pairs, const int *pair_i, const int *pair_j, const float *poses, int n_scans,
+		const m3dreg_reg_params *prm, double *d_neq, double *d_group_ms)
 {
 	if (!c || n_pairs < 0 || (n_pairs && (!pair_i || !pair_j)) || !poses || n_scans <= 0 || !valid_params(prm) || !d_neq)
 		return M3DREG_E_INVALID_ARG;
@@ -1544,6 +1577,10 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 		if (bt.total > max_second) max_second = bt.total;
 		batches.push_back(bt);
 	}
+	if (c->sweep_reserve_second > max_second) max_second = c->sweep_reserve_second;
+	if (c->sweep_reserve_first > max_first) max_first = c->sweep_reserve_first;
+	if (c->sweep_reserve_cap > max_cap) max_cap = c->sweep_reserve_cap;
+	const size_t seg_slots = all_segs.size() > c->sweep_reserve_segs ? all_segs.size() : c->sweep_reserve_segs;
 	if ((e = c->d_poses1.ensure((size_t)n_scans * 16))) return e;
 	if ((e = c->d_pose6.ensure((size_t)n_scans * 6))) return e;
 	if (max_first) {
@@ -1553,13 +1590,13 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 		if ((e = ensure_buckets(c, (size_t)max_cap, ndt))) return e;
 	}
 	if (!ndt) {
-		if ((e = c->d_segs.ensure(all_segs.size() + 1))) return e;
+		if ((e = c->d_segs.ensure(seg_slots + 1))) return e;
 		if ((e = c->d_seg_counts.ensure(4 * kMaxSegs))) return e;
 		if ((e = c->d_seg_of_chunk.ensure(max_second / kSegChunk + 1))) return e;
 	}
 	const size_t bytes_p1 = (size_t)n_scans * 16 * sizeof(float), bytes_p6 = (size_t)n_scans * 6 * sizeof(double),
 			bytes_segs = all_segs.size() * sizeof(SweepSeg);
-	if ((e = ensure_sweep_staging(c, bytes_p6 + bytes_p1 + bytes_segs + 64))) return e;
+	if ((e = ensure_sweep_staging(c, bytes_p6 + bytes_p1 + seg_slots * sizeof(SweepSeg) + 64))) return e;
 	/* the previous sweep's uploads have completed: every sweep ends with check_flags (one synchronisation per sweep) */
 	double *h_p6 = static_cast<double *>(c->h_sweep);
 	float *h_p1 = reinterpret_cast<float *>(static_cast<char *>(c->h_sweep) + bytes_p6);
@@ -1581,6 +1618,7 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 		const Scan &A = c->scans[(size_t)i];
 		const float *pose_i = c->d_poses1.p + 16 * (size_t)i;
 		if (i != cur_i) {
+			if (d_group_ms) LAUNCH(c, k_group_stamp, 1, 32, d_group_ms, cur_i, c->stamp_last);
 			LAUNCH(c, k_reset_bounds, 1, 32, c->bounds);
 			if (!c->grid_mega) {
 				LAUNCH(c, k_transform_soa<true>, box_pass_blocks(c, A.n), 512, A.xyzl, A.nrm, A.n, pose_i, ndt ? c->g_xyzl.p : (float4 *)nullptr, (float4 *)nullptr, c->bounds);
@@ -1626,6 +1664,7 @@ int m3dreg_sweep_accumulate(m3dreg_ctx *c, int n_pairs, const int *pair_i, const
 		LAUNCH(c, k_normal_equations<ObsFromRec>, grid_for(c, (long long)bt.total, kNeqThreads, 2), kNeqThreads, src, (int)bt.total, c->partials.p, c->ticket, fin);
 		c->last_n_first = A.n; c->last_n_second = all_segs[(size_t)(bt.seg0 + bt.nseg - 1)].n; c->last_valid = true; c->last_nn_valid = false; c->nn_pending = false;
 	}
+	if (d_group_ms && cur_i >= 0) LAUNCH(c, k_group_stamp, 1, 32, d_group_ms, cur_i, c->stamp_last);
 	int f = check_flags(c);
 	if (f) return f;
 	return launch_status(c);

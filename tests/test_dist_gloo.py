@@ -136,3 +136,25 @@ def test_cpp_plan_equals_python_plan(pkg):
         a, b, ow = pkg.slam_plan(poses, sizes, thr, n - 3, 2)
         keep = pi >= n - 3
         assert np.array_equal(a, pi[keep]) and np.array_equal(b, pj[keep])
+
+
+def test_measured_cost_plan_balances_what_point_counts_cannot(pkg):
+    """m3dreg_slam_plan_measured: equal-sized scans whose groups cost very different device time (overlap differs) are
+    balanced by the measured time; every pair keeps exactly one owner and groups stay whole unless heavier than a share."""
+    synth = pkg.synth
+    truth = synth.loop_trajectory(40, 1.0)
+    sizes = np.full(40, 65536, dtype=np.int32)
+    rng = np.random.default_rng(3)
+    cpp = rng.uniform(0.01, 0.05, 40)
+    cpp[5] = 0.0                                              # one group not measured: takes the mean of the others
+    for world in (2, 4, 8):
+        pi, pj, ow = pkg.slam_plan_measured(truth, sizes, cpp, 10.0, 0, world)
+        pi0, pj0, ow0 = pkg.slam_plan(truth, sizes, 10.0, 0, world)
+        assert np.array_equal(pi, pi0) and np.array_equal(pj, pj0) and ow.min() >= 0 and ow.max() < world
+        eff = np.where(cpp > 0, cpp, cpp[cpp > 0].mean())
+        load = np.array([eff[pi[ow == r]].sum() for r in range(world)])
+        load0 = np.array([eff[pi[ow0 == r]].sum() for r in range(world)])
+        assert load.max() / load.mean() < 1.06, (world, load)
+        assert load.max() <= load0.max() + 1e-12            # never worse than the point-count plan under the measured costs
+        for i in np.unique(pi):                              # groups stay whole (none is heavier than 1.25 shares here)
+            assert len(np.unique(ow[pi == i])) == 1

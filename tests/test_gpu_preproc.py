@@ -128,3 +128,49 @@ def test_yaw_sweep_counts_identical(ctx, synth, oracle, ref):
         assert np.array_equal(counts, counts_o)
         assert best == best_r == best_o and best_n == int(counts.max())
         assert abs(best - 7.5) <= 1.5
+
+
+def test_preproc_edge_cases_and_argument_errors(pkg, ctx, synth, oracle):
+    """One point, coincident points, a cloud in a single bucket, zero survivors; invalid arguments report, never crash."""
+    import ctypes as C
+    one = synth.random_cloud(1, seed=70)
+    out, m = ctx.remove_noise(one, 0.5, 1.0, 0)
+    assert m.tolist() == oracle.remove_noise(one, 0.5, 1.0, 0)[1].tolist() and len(out) == int(m.sum())
+    out, m = ctx.downsample(one, 0.3, 0.3)
+    assert m.tolist() == [1] and len(out) == 1
+    got = ctx.classify(one, **CLS)
+    assert got["label"][0] == 1 and got["normal_x"][0] == 0 and got["normal_z"][0] == 0            # fewer than three neighbours: edge, no normal
+    same = synth.random_cloud(300, seed=71)
+    same["x"], same["y"], same["z"] = 1.25, -0.5, 0.75                                             # 300 coincident points
+    out, m = ctx.remove_noise(same, 0.5, 1.0, 3)
+    assert m.all() and len(out) == 300
+    out, m = ctx.downsample(same, 0.3, 0.3)
+    assert m.sum() == 1 and m[0] == 1                                                               # the smallest original index of the bucket stays
+    got = ctx.classify(same, **CLS)
+    want, _, _ = oracle.classify(same, **CLS)
+    assert np.array_equal(got["label"], want["label"])                                             # zero covariance: edge everywhere
+    sparse = synth.random_cloud(500, seed=72, extent=(40, 40, 10))
+    out, m = ctx.remove_noise(sparse, 0.5, 1.0, 5)
+    assert np.array_equal(m, oracle.remove_noise(sparse, 0.5, 1.0, 5)[1]) and len(out) == int(m.sum())
+    out, m = ctx.remove_noise(sparse, 0.5, 1.0, 1000)
+    assert len(out) == 0 and not m.any()                                                            # nothing survives
+    # argument errors through the raw C ABI
+    L = pkg.lib()
+    kept = C.c_int(0)
+    buf = np.zeros(4, dtype=pkg.POINT_DTYPE)
+    assert L.m3dreg_remove_noise_host(ctx._h, None, C.c_int(4), C.c_float(0.5), C.c_float(1.0), C.c_int(3), pkg._p(buf), C.byref(kept), None) == pkg.E_INVALID_ARG
+    assert L.m3dreg_remove_noise_host(ctx._h, pkg._p(buf), C.c_int(0), C.c_float(0.5), C.c_float(1.0), C.c_int(3), pkg._p(buf), C.byref(kept), None) == pkg.E_INVALID_ARG
+    assert L.m3dreg_downsample_host(ctx._h, pkg._p(buf), C.c_int(4), C.c_float(0.0), C.c_float(1.0), pkg._p(buf), C.byref(kept), None) == pkg.E_INVALID_ARG
+    assert L.m3dreg_classify_host(ctx._h, pkg._p(buf), C.c_int(4), C.c_float(-1.0), C.c_float(10.0), C.c_float(1.0), C.c_int(15), C.c_float(1.0),
+                                  C.c_int(100), C.c_int(100), C.c_float(0), C.c_float(0), C.c_float(0), None, None) == pkg.E_INVALID_ARG
+    best = C.c_float(0)
+    assert L.m3dreg_find_best_yaw_host(ctx._h, pkg._p(buf), C.c_int(4), pkg._p(buf), C.c_int(4), None, None, C.c_float(1.0), C.c_float(1.0), C.c_float(0.3),
+                                       C.c_int(50), C.c_int(50), C.c_float(-3.0), C.c_float(3.0), C.c_float(0.0), C.byref(best), None, None, C.c_int(0)) == pkg.E_INVALID_ARG
+    # a grid that does not fit int32 is refused (upstream overflows silently, lesson_16.cu:80)
+    huge = synth.random_cloud(64, seed=73, extent=(3000, 3000, 3000))
+    with pytest.raises(pkg.M3dRegError) as ei:
+        ctx.remove_noise(huge, 0.001, 1.0, 0)
+    assert ei.value.status == pkg.E_TOO_MANY_BUCKETS
+    # the context is still usable afterwards
+    out, m = ctx.downsample(sparse, 1.0, 1.0)
+    assert np.array_equal(m, oracle.downsample(sparse, 1.0, 1.0)[1])
