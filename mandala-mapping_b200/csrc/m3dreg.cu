@@ -1541,7 +1541,22 @@ static int sweep_accumulate_impl(m3dreg_ctx *c, int n_pairs, const int *pair_i, 
 	 * synchronisation, no allocation (round 1 synchronised per scan and per batch). */
 	std::vector<int> order((size_t)n_pairs);
 	for (int p = 0; p < n_pairs; p++) order[(size_t)p] = p;
-	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pair_i[a] < pair_i[b]; });
+	/* Inside a group the FARTHEST neighbours come first.  Queries of a distant neighbour mostly have no partner inside the
+	 * search radius and pay every round of the search (chunks of 90-280 us where the mean is 36 us), and the search hands
+	 * its chunks out in query order: with the neighbours in index order the distant ones sat at the end of the launch and
+	 * 38 % of it was tail (mean warp out of work at 262 of 420 us, tools/nn_tail_sweep.py).  Longest first needs no
+	 * measurement here — the distance between the poses is the proxy.  Env M3DREG_SWEEP_INDEX_ORDER=1: index order (A/B). */
+	std::vector<float> far((size_t)n_pairs, 0.0f);
+	if (!getenv("M3DREG_SWEEP_INDEX_ORDER"))
+		for (int p = 0; p < n_pairs; p++) {
+			const float *a = poses + 16 * (size_t)pair_i[p], *b = poses + 16 * (size_t)pair_j[p];
+			const float dx = a[3] - b[3], dy = a[7] - b[7], dz = a[11] - b[11];
+			far[(size_t)p] = dx * dx + dy * dy + dz * dz;
+		}
+	std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+		if (pair_i[a] != pair_i[b]) return pair_i[a] < pair_i[b];
+		return far[(size_t)a] > far[(size_t)b];
+	});
 	const size_t kBatchQueries = (size_t)8 << 20;       /* queries per batch (incl. padding): 8 Mi x 36 B of query state */
 	struct Batch { int i, seg0, nseg, j_single; size_t total; };
 	std::vector<Batch> batches;
