@@ -196,6 +196,15 @@ struct m3dreg_ctx {
 	int last_n_first = 0, last_n_second = 0, last_sorted = 0;
 	bool last_valid = false, last_nn_valid = true;
 	double *neq_out_ext = nullptr;                /* m3dreg_icp_set_neq_out: extra destination of the fused loop's block */
+	/* CUDA-graph replay of the fused iteration (m3dreg_icp_step): the ten PDL-chained launches of one iteration are captured
+	 * once per loop (every kernel argument is a device pointer or a constant of the loop: the pose lives on the device) and
+	 * replayed per step — one driver call instead of ten.  Up to two instantiations, keyed by the extra normal-equation
+	 * destination (a multi-GPU caller alternates two buffers).  Env M3DREG_NO_GRAPH=1: plain launches. */
+	struct IterGraph { cudaGraphExec_t exec = nullptr; double *neq_out = nullptr; int launches = 0; unsigned long long age = 0; };
+	IterGraph it_graph[2];
+	unsigned long long it_graph_clock = 0;
+	bool it_graph_failed = false;
+	int use_graph = 1;
 	bool nn_pending = false;                      /* obs_rec (query order) is newer than nn (caller order) */
 	const uint32_t *nn_pending_perm = nullptr;
 };
@@ -719,6 +728,15 @@ void stage_events_collect(m3dreg_ctx *c)
 /* One registerLastArrivedScan iteration, fully on the device, nothing read back: box pass, key pass, sort passes, bucket
  * table, candidate sets, search, moment reduction + solve (PDL-chained launches).  first local cloud = (lx, ln), queries
  * already in q_*. */
+void drop_iteration_graphs(m3dreg_ctx *c)
+{
+	for (auto &g : c->it_graph) {
+		if (g.exec) cudaGraphExecDestroy(g.exec);
+		g = m3dreg_ctx::IterGraph();
+	}
+	c->it_graph_failed = false;
+}
+
 void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, int n2,
 		const m3dreg_reg_params *prm, int sort_bits)
 {
@@ -824,6 +842,7 @@ int m3dreg_create(m3dreg_ctx **out, int cuda_device)
 	{ const char *e = getenv("M3DREG_NN_RHO_DIV"); if (e && atoi(e) > 0) c->nn_tune.rho_div = atoi(e); }
 	{ const char *e = getenv("M3DREG_NN_HULL_MIN"); if (e && atoi(e) > 0) c->nn_tune.hull_min = atoi(e); }
 	{ const char *e = getenv("M3DREG_NN_HULL_RATIO"); if (e && atoi(e) > 0) c->nn_tune.hull_ratio = atoi(e); }
+	{ const char *e = getenv("M3DREG_NO_GRAPH"); if (e && atoi(e) != 0) c->use_graph = 0; }
 	{ const char *e = getenv("M3DREG_NN_DIAG"); if (e) c->nn_diag = atoi(e) != 0 ? 1 : 0; }
 	{ const char *e = getenv("M3DREG_NN_SWEEP_RHO_DIV"); if (e && atoi(e) > 0) c->nn_tune_sweep.rho_div = atoi(e); }
 	{ const char *e = getenv("M3DREG_NN_SWEEP_HULL_MIN"); if (e && atoi(e) > 0) c->nn_tune_sweep.hull_min = atoi(e); }
@@ -869,6 +888,7 @@ void m3dreg_destroy(m3dreg_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->dev);
 	if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+	drop_iteration_graphs(c);
 	m3dreg_nccl_attach(c, nullptr, 0, 1);      /* destroys a communicator this context created */
 	c->d_neq.release();
 	if (c->ev2) cudaEventDestroy(c->ev2);
@@ -906,7 +926,7 @@ int m3dreg_set_stream(m3dreg_ctx *c, void *s)
 	if (!c) return M3DREG_E_INVALID_ARG;
 	CK(cudaStreamSynchronize(c->stream));
 	c->stream = s ? (cudaStream_t)s : c->own_stream;
-	return 0;
+	return 0;      /* captured iteration graphs stay valid: a graph is launched into whatever stream is current */
 }
 
 void *m3dreg_get_stream(m3dreg_ctx *c) { return c ? (void *)c->stream : nullptr; }
@@ -1268,6 +1288,7 @@ static int icp_begin_internal(m3dreg_ctx *c, const float4 *lx, const float4 *ln,
 	CK(cudaMemsetAsync(c->label_counts, 0, 4 * sizeof(unsigned long long), c->stream));
 	CK(cudaMemsetAsync(c->flags, 0, FLAG_COUNT * sizeof(int), c->stream));
 	CK(cudaMemsetAsync(c->ticket, 0, sizeof(unsigned int), c->stream));
+	drop_iteration_graphs(c);      /* a new loop: other clouds, sizes, parameters */
 	LAUNCH(c, k_pose_prepare, 1, 32, c->ps);
 	/* Nothing is read back to plan the loop (round 1 transformed the cloud once and synchronised to size the table):
 	 * the bucket table holds the grid of this scan under ANY pose (its extent never exceeds the local box's diagonal), and
@@ -1281,6 +1302,46 @@ static int icp_begin_internal(m3dreg_ctx *c, const float4 *lx, const float4 *ln,
 	c->act_lx = lx; c->act_ln = ln; c->act_n1 = n1; c->act_n2 = n2; c->act_sort_bits = sort_bits; c->act_prm = *prm;
 	c->active = true;
 	return 0;
+}
+
+/* `iterations` fused iterations of the active loop: graph replay (see m3dreg_ctx::it_graph) or plain launches */
+static int run_iterations(m3dreg_ctx *c, int iterations)
+{
+	int it = 0;
+	if (c->use_graph && !c->profiling && !c->it_graph_failed && iterations > 0) {
+		m3dreg_ctx::IterGraph *g = nullptr;
+		for (auto &cand : c->it_graph) if (cand.exec && cand.neq_out == c->neq_out_ext) g = &cand;
+		if (!g) {      /* capture one iteration (nothing runs while capturing) */
+			m3dreg_ctx::IterGraph *slot = &c->it_graph[0];
+			for (auto &cand : c->it_graph) if (!cand.exec || cand.age < slot->age) { slot = &cand; if (!cand.exec) break; }
+			if (slot->exec) { cudaGraphExecDestroy(slot->exec); *slot = m3dreg_ctx::IterGraph(); }
+			const int64_t launches_before = c->launches;
+			cudaGraph_t graph = nullptr;
+			if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+				icp_iteration_device(c, c->act_lx, c->act_ln, c->act_n1, c->act_n2, &c->act_prm, c->act_sort_bits);
+				const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+				cudaGraphExec_t exec = nullptr;
+				if (ce == cudaSuccess && graph && c->launch_err == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+					slot->exec = exec; slot->neq_out = c->neq_out_ext; slot->launches = (int)(c->launches - launches_before);
+					g = slot;
+				}
+				if (graph) cudaGraphDestroy(graph);
+			}
+			c->launches = launches_before;
+			if (!g) { cudaGetLastError(); c->launch_err = cudaSuccess; c->it_graph_failed = true; }      /* this loop runs on plain launches */
+		}
+		if (g) {
+			g->age = ++c->it_graph_clock;
+			for (; it < iterations; it++) {
+				const cudaError_t ce = cudaGraphLaunch(g->exec, c->stream);
+				if (ce != cudaSuccess) return (int)ce;
+				c->launches += g->launches;
+			}
+		}
+	}
+	for (; it < iterations; it++)
+		icp_iteration_device(c, c->act_lx, c->act_ln, c->act_n1, c->act_n2, &c->act_prm, c->act_sort_bits);
+	return (int)cudaGetLastError();
 }
 
 static int icp_end_internal(m3dreg_ctx *c, float *pose_first_out, m3dreg_icp_stats *stats, float ms)
@@ -1300,7 +1361,7 @@ static int icp_loop(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, i
 	int e = icp_begin_internal(c, lx, ln, n1, n2, pose_first, prm, box);
 	if (e) return e;
 	CK(cudaEventRecord(c->ev0, c->stream));
-	for (int it = 0; it < iterations; it++) icp_iteration_device(c, lx, ln, n1, n2, prm, c->act_sort_bits);
+	if ((e = run_iterations(c, iterations))) return e;
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(cudaEventSynchronize(c->ev1));
 	float ms = 0.0f;
@@ -1340,9 +1401,7 @@ int m3dreg_icp_step(m3dreg_ctx *c, int iterations)
 	if (!c || iterations < 0) return M3DREG_E_INVALID_ARG;
 	if (!c->active) return M3DREG_E_BAD_SLOT;
 	CK(cudaSetDevice(c->dev));
-	for (int it = 0; it < iterations; it++)
-		icp_iteration_device(c, c->act_lx, c->act_ln, c->act_n1, c->act_n2, &c->act_prm, c->act_sort_bits);
-	return (int)cudaGetLastError();
+	return run_iterations(c, iterations);
 }
 
 int m3dreg_icp_end(m3dreg_ctx *c, float *pose_first_out, m3dreg_icp_stats *stats)
