@@ -356,10 +356,12 @@ def slam_record(pkg, which, args, rank, world, local_rank):
     else:
         n_scans, kind, kw, res, modes, dof = args.slam_c5_scans, "sick", {}, 1.0, ["icp", "ndt"], 6
         desc = (f"C5 shape: registerAll over {n_scans} synthetic rotating-SICK scans x 1 048 576 points, 1.0 m buckets, 10 m pair gate, "
-                "ICP and NDT sweeps alternating (BASELINE's 1000 scans do not fit a bench run: the scans are numpy ray casts, 2.4 s each)")
+                "ICP and NDT sweeps alternating (BASELINE's 1000 scans do not fit a bench run: the scans are numpy ray casts, 2.4 s each, "
+                "spread over worker processes)")
     t0 = time.perf_counter()
     mine = [k for k in range(n_scans) if k % world == rank]
-    scans, truth, init = pkg.synth.slam_scans(n_scans, kind=kind, seed=42, spacing=1.0, only=mine, **kw)
+    gen_workers = max(1, min(args.slam_gen_workers, (os.cpu_count() or 1) // max(1, world)))
+    scans, truth, init = pkg.synth.slam_scans(n_scans, kind=kind, seed=42, spacing=1.0, only=mine, workers=gen_workers, **kw)
     ctx = pkg.Context(local_rank)
     npts = len(scans[mine[0]])
     if world > 1:
@@ -470,6 +472,7 @@ def main():
     ap.add_argument("--slam-scans", type=int, default=100)
     ap.add_argument("--slam-c5-scans", type=int, default=16)
     ap.add_argument("--slam-sweeps", type=int, default=6)
+    ap.add_argument("--slam-gen-workers", type=int, default=16, help="processes that ray-cast the synthetic scans (per rank; capped by the host's cores)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

@@ -302,18 +302,70 @@ def loop_trajectory(n_scans: int, spacing: float = 1.0, size=(25.0, 15.0), corne
     return poses
 
 
+def _scan_job(job):
+    """One scan of slam_scans()."""
+    kind, pose, seed, kw = job
+    return {"hdl32": hdl32_scan, "sick": rotating_sick_scan}[kind](pose, seed=seed, **kw)
+
+
+_WORKER_CODE = """
+import importlib.util, json, sys
+import numpy as np
+spec = importlib.util.spec_from_file_location("m3d_synth_worker", sys.argv[1])
+synth = importlib.util.module_from_spec(spec); spec.loader.exec_module(synth)
+job = json.load(open(sys.argv[2]))
+truth = synth.loop_trajectory(job["n_scans"], job["spacing"])
+for k in job["scans"]:
+    sc = synth._scan_job((job["kind"], truth[k], job["seed"] + k, job["kw"]))
+    np.save(job["dir"] + "/scan_%d.npy" % k, sc)
+"""
+
+
+def _scans_by_workers(todo, n_scans, kind, seed, spacing, kw, workers):
+    """Generate the scans `todo` with `workers` plain child processes (python -c, this file loaded by path, results as
+    .npy files in a temporary directory): independent of how the caller's main module was started."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    made = {}
+    with tempfile.TemporaryDirectory(prefix="m3d_scans_") as d:
+        procs = []
+        for w in range(workers):
+            share = todo[w::workers]
+            if not share:
+                continue
+            jf = os.path.join(d, "job_%d.json" % w)
+            with open(jf, "w") as f:
+                json.dump({"n_scans": n_scans, "spacing": spacing, "kind": kind, "seed": seed, "kw": kw, "scans": share, "dir": d}, f)
+            procs.append(subprocess.Popen([sys.executable, "-c", _WORKER_CODE, os.path.abspath(__file__), jf]))
+        for p in procs:
+            if p.wait() != 0:
+                raise RuntimeError("scan generation worker failed")
+        for k in todo:
+            made[k] = np.load(os.path.join(d, "scan_%d.npy" % k))
+    return made
+
+
 def slam_scans(n_scans: int, kind: str = "hdl32", seed: int = 42, spacing: float = 1.0,
-               drift_sigma_t: float = 0.05, drift_sigma_r: float = 0.01, only=None, **kw):
+               drift_sigma_t: float = 0.05, drift_sigma_r: float = 0.01, only=None, workers: int = 1, **kw):
     """Multi-scan data set (C4/C5): scans in their local frames, true poses, drifted initial poses.
     only: iterable of scan indices to generate (the others are None) — poses are always complete, so that the ranks of a
-    multi-GPU job can each generate a share of the scans and exchange them."""
-    gen = {"hdl32": hdl32_scan, "sick": rotating_sick_scan}[kind]
+    multi-GPU job can each generate a share of the scans and exchange them.
+    workers > 1: the scans (independent numpy ray casts, seed + k each) are generated by that many child processes —
+    same arrays as the serial path."""
     truth = loop_trajectory(n_scans, spacing)
     rng = np.random.Generator(np.random.PCG64(seed + 1000))
     want = None if only is None else set(int(k) for k in only)
+    todo = [k for k in range(n_scans) if want is None or k in want]
+    if workers > 1 and len(todo) > 1:
+        made = _scans_by_workers(todo, n_scans, kind, seed, spacing, kw, min(workers, len(todo)))
+    else:
+        made = {k: _scan_job((kind, truth[k], seed + k, kw)) for k in todo}
     scans, init = [], np.zeros((n_scans, 4, 4), dtype=np.float32)
     for k in range(n_scans):
-        scans.append(gen(truth[k], seed=seed + k, **kw) if (want is None or k in want) else None)
+        scans.append(made.get(k))
         dt = rng.normal(0, drift_sigma_t, 3)
         dr = rng.normal(0, drift_sigma_r, 3)
         yaw = math.atan2(truth[k][1, 0], truth[k][0, 0])
