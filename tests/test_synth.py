@@ -42,3 +42,14 @@ def test_pair_and_trajectory(synth):
     d = np.linalg.norm(tr[1:, :3, 3] - tr[:-1, :3, 3], axis=1)
     assert np.all(d < 1.0 + 1e-6) and np.all(d > 0.9)          # unit spacing along the loop (chords on arcs)
     assert np.abs(tr[:, 0, 3]).max() <= 12.5 + 1e-9 and np.abs(tr[:, 1, 3]).max() <= 7.5 + 1e-9
+
+
+def test_slam_scans_by_worker_processes_match_the_serial_path(synth):
+    """bench.py spreads the ray casts of a multi-scan set over child processes: same scans, same poses."""
+    a, ta, ia = synth.slam_scans(5, kind="hdl32", seed=7, n_azimuth=64)
+    b, tb, ib = synth.slam_scans(5, kind="hdl32", seed=7, n_azimuth=64, workers=3, only=[0, 2, 3])
+    assert np.array_equal(ta, tb) and np.array_equal(ia, ib)
+    assert b[1] is None and b[4] is None
+    for k in (0, 2, 3):
+        assert b[k].dtype == a[k].dtype and b[k].dtype.itemsize == 40
+        assert b[k].tobytes() == a[k].tobytes()
