@@ -136,7 +136,24 @@ struct m3dreg_ctx {
 	 * depends on how much the two scans overlap, which point counts do not show) */
 	DevBuf<double> d_group_ms;
 	unsigned long long *stamp_last = nullptr;
-	std::vector<double> slam_group_ms, slam_cost_per_pair, slam_cost_per_pair_used;
+	std::vector<double> slam_group_ms, slam_cost_per_pair_used;
+	/* measured cost per pair of every scan's group, kept per sweep KIND (mode, bucket size, search radius): an NDT sweep costs
+	 * a fifth of an ICP sweep and spreads differently over the scans, and drivers alternate them (C5) — each kind plans with
+	 * its own last measurement.  Four kinds are remembered (least recently used replaced). */
+	struct SlamCosts { int mode = -1; float bucket = 0.0f, radius = 0.0f; unsigned long long age = 0; std::vector<double> per_pair; };
+	SlamCosts slam_costs[4];
+	unsigned long long slam_costs_clock = 0;
+	SlamCosts &slam_costs_for(const m3dreg_reg_params &r)
+	{
+		SlamCosts *lru = &slam_costs[0];
+		for (auto &k : slam_costs) {
+			if (k.mode == r.mode && k.bucket == r.bucket_size && k.radius == r.search_radius) { k.age = ++slam_costs_clock; return k; }
+			if (k.age < lru->age) lru = &k;
+		}
+		lru->mode = r.mode; lru->bucket = r.bucket_size; lru->radius = r.search_radius; lru->per_pair.clear(); lru->age = ++slam_costs_clock;
+		return *lru;
+	}
+	void slam_costs_clear() { for (auto &k : slam_costs) { k.mode = -1; k.per_pair.clear(); k.age = 0; } }
 	/* m3dreg_slam_sweep sizes the sweep's buffers for the WHOLE pair list, not for this rank's share: the share changes from
 	 * sweep to sweep under the measured-cost partition, and a buffer that grows synchronises (and re-pins host memory) */
 	size_t sweep_reserve_segs = 0, sweep_reserve_second = 0, sweep_reserve_first = 0;
@@ -1234,7 +1251,7 @@ int m3dreg_scan_upload(m3dreg_ctx *c, int slot, const m3dreg_point *src, int n, 
 	}
 	LAUNCH(c, k_unpack_points, (n + 255) / 256, 256, d_src, n, s.xyzl, s.nrm);
 	s.n = n;
-	c->slam_cost_per_pair.clear();
+	c->slam_costs_clear();
 	c->active = false;
 	c->last_valid = false;
 	return presort_scan(c, s, d_src);
@@ -1253,7 +1270,7 @@ int m3dreg_scan_clear(m3dreg_ctx *c)
 	CK(cudaStreamSynchronize(c->stream));
 	for (auto &s : c->scans) s.release();
 	c->scans.clear();
-	c->slam_cost_per_pair.clear();      /* measured pair costs belong to the scans that are gone */
+	c->slam_costs_clear();      /* measured pair costs belong to the scans that are gone */
 	return 0;
 }
 

@@ -249,9 +249,10 @@ int m3dreg_slam_sweep(m3dreg_ctx *c, int n_scans, float *poses, const m3dreg_sla
 	}
 	std::vector<int> pi, pj, owner, mi, mj;
 	slam_gate_pairs(poses, n_scans, sp->distance_threshold, first_opt, pi, pj);
-	const bool have_costs = world > 1 && c->slam_cost_per_pair.size() == (size_t)n_scans && !getenv("M3DREG_SLAM_STATIC_PARTITION");
-	slam_partition(pi, pj, sizes.data(), world, owner, have_costs ? c->slam_cost_per_pair.data() : nullptr);
-	if (have_costs) c->slam_cost_per_pair_used = c->slam_cost_per_pair;
+	m3dreg_ctx::SlamCosts &costs = c->slam_costs_for(sp->reg);      /* this kind of sweep's last measurement */
+	const bool have_costs = world > 1 && costs.per_pair.size() == (size_t)n_scans && !getenv("M3DREG_SLAM_STATIC_PARTITION");
+	slam_partition(pi, pj, sizes.data(), world, owner, have_costs ? costs.per_pair.data() : nullptr);
+	if (have_costs) c->slam_cost_per_pair_used = costs.per_pair;
 	long long my_points = 0, all_points = 0;
 	for (size_t k = 0; k < pi.size(); k++) {
 		const long long pts = (long long)sizes[(size_t)pi[k]] + sizes[(size_t)pj[k]];
@@ -311,9 +312,9 @@ int m3dreg_slam_sweep(m3dreg_ctx *c, int n_scans, float *poses, const m3dreg_sla
 	if (world > 1) {
 		std::vector<int> cnt((size_t)n_scans, 0);
 		for (size_t k = 0; k < pi.size(); k++) cnt[(size_t)pi[k]]++;
-		c->slam_cost_per_pair.assign((size_t)n_scans, 0.0);
+		costs.per_pair.assign((size_t)n_scans, 0.0);
 		for (int s = 0; s < n_scans; s++)
-			if (cnt[(size_t)s] > 0 && c->slam_group_ms[(size_t)s] > 0.0) c->slam_cost_per_pair[(size_t)s] = c->slam_group_ms[(size_t)s] / (double)cnt[(size_t)s];
+			if (cnt[(size_t)s] > 0 && c->slam_group_ms[(size_t)s] > 0.0) costs.per_pair[(size_t)s] = c->slam_group_ms[(size_t)s] / (double)cnt[(size_t)s];
 	}
 	if (getenv("M3DREG_SLAM_DEBUG")) {      /* how well did the plan predict this rank's share? */
 		float ms_acc = 0.0f;
