@@ -96,6 +96,14 @@ struct m3dreg_ctx {
 	cudaStream_t own_stream = nullptr;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	/* host-buffer iteration (m3dreg_icp_iteration_host): the two clouds go up on a copy stream of their own; the second one
+	 * (the queries) is only waited for after the grid of the first has been built, so box pass, sort and candidate sets run
+	 * under its transfer.  q_deferred_* = the unpack of the queries that icp_iteration_device issues at that point. */
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
+	cudaEvent_t q_deferred_ev = nullptr;
+	const m3dreg_point *q_deferred_aos = nullptr;
+	int q_deferred_n = 0;
 	int64_t launches = 0;
 	int prune = 1;               /* exact bucket pruning in the NN search (0 only for the equivalence test) */
 
@@ -769,6 +777,11 @@ void icp_iteration_device(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int
 		if (prof) cudaEventRecord(c->pev[1], c->stream);      /* the transform is part of the grid launch */
 		build_grid_mega(c, lx, ln, n1, c->ps->pose1, prm, ndt);
 	}
+	if (c->q_deferred_ev) {      /* host-buffer call: the queries' upload was left running under the grid build */
+		cudaStreamWaitEvent(c->stream, c->q_deferred_ev, 0);
+		LAUNCH(c, k_unpack_points, (c->q_deferred_n + 255) / 256, 256, c->q_deferred_aos, c->q_deferred_n, c->q_xyzl.p, c->q_nrm.p);
+		c->q_deferred_ev = nullptr;
+	}
 	FinalizeArgs fin = {};
 	fin.ps = c->ps; fin.neq_out = c->neq_out_ext; fin.accumulate = 0; fin.solve = 1; fin.dof = prm->dof;
 	fin.obs_threshold = prm->obs_threshold; fin.pose6_in = nullptr; fin.bounds_reset = c->bounds;
@@ -923,6 +936,8 @@ void m3dreg_destroy(m3dreg_ctx *c)
 	if (c->ps) cudaFree(c->ps);   /* base of the small block */
 	if (c->h) cudaFreeHost(c->h);
 	for (int k = 0; k <= M3DREG_STAGE_COUNT; k++) if (c->pev[k]) cudaEventDestroy(c->pev[k]);
+	for (auto &ev : c->ev_copy) if (ev) cudaEventDestroy(ev);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -1299,14 +1314,12 @@ static int icp_begin_internal(m3dreg_ctx *c, const float4 *lx, const float4 *ln,
 {
 	int e;
 	if ((e = ensure_candidates(c, (size_t)n1, prm->max_inner, prm->max_outer))) return e;
-	memset(&c->h->ps, 0, sizeof(PoseState));
-	memcpy(c->h->ps.m, pose_first, 16 * sizeof(float));
-	CK(cudaMemcpyAsync(c->ps, &c->h->ps, sizeof(PoseState), cudaMemcpyHostToDevice, c->stream));
-	CK(cudaMemsetAsync(c->label_counts, 0, 4 * sizeof(unsigned long long), c->stream));
-	CK(cudaMemsetAsync(c->flags, 0, FLAG_COUNT * sizeof(int), c->stream));
-	CK(cudaMemsetAsync(c->ticket, 0, sizeof(unsigned int), c->stream));
+	static_assert(sizeof(PoseState) % sizeof(unsigned int) == 0, "k_pose_init clears the state word by word");
 	drop_iteration_graphs(c);      /* a new loop: other clouds, sizes, parameters */
-	LAUNCH(c, k_pose_prepare, 1, 32, c->ps);
+	Pose16 p16;
+	memcpy(p16.m, pose_first, 16 * sizeof(float));
+	/* state, label counters, flags and ticket cleared, pose in (as a kernel argument: no copy-engine traffic), first Euler round trip */
+	LAUNCH(c, k_pose_init, 1, 32, c->ps, p16, c->label_counts, c->flags, c->ticket);
 	/* Nothing is read back to plan the loop (round 1 transformed the cloud once and synchronised to size the table):
 	 * the bucket table holds the grid of this scan under ANY pose (its extent never exceeds the local box's diagonal), and
 	 * the number of sort passes follows from the local box rotated by the initial pose plus a margin of four cells per
@@ -1325,7 +1338,9 @@ static int icp_begin_internal(m3dreg_ctx *c, const float4 *lx, const float4 *ln,
 static int run_iterations(m3dreg_ctx *c, int iterations)
 {
 	int it = 0;
-	if (c->use_graph && !c->profiling && !c->it_graph_failed && iterations > 0) {
+	/* capturing and instantiating the graph costs about as much host time as three iterations of plain launches, and a
+	 * deferred query upload (host-buffer call, one iteration) must not be baked into a graph */
+	if (c->use_graph && !c->profiling && !c->it_graph_failed && iterations >= 4 && !c->q_deferred_ev) {
 		m3dreg_ctx::IterGraph *g = nullptr;
 		for (auto &cand : c->it_graph) if (cand.exec && cand.neq_out == c->neq_out_ext) g = &cand;
 		if (!g) {      /* capture one iteration (nothing runs while capturing) */
@@ -1496,15 +1511,35 @@ int m3dreg_icp_iteration_host(m3dreg_ctx *c, const m3dreg_point *first_local, in
 	if ((e = c->l_nrm.ensure((size_t)n1))) return e;
 	if ((e = ensure_first(c, (size_t)n1))) return e;
 	if ((e = ensure_second(c, (size_t)n2))) return e;
-	CK(cudaMemcpyAsync(c->aos_a.p, first_local, (size_t)n1 * sizeof(m3dreg_point), cudaMemcpyHostToDevice, c->stream));
-	CK(cudaMemcpyAsync(c->aos_b.p, second_global, (size_t)n2 * sizeof(m3dreg_point), cudaMemcpyHostToDevice, c->stream));
+	if (!c->copy_stream) {
+		CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+		for (auto &ev : c->ev_copy) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+	}
+	/* uploads on the copy stream, ordered after whatever the registration stream still does with the staging buffers
+	 * (env M3DREG_HOST_OVERLAP=0: on the registration stream itself, i.e. nothing runs under the transfers — A/B runs) */
+	static const bool overlap = !(getenv("M3DREG_HOST_OVERLAP") && atoi(getenv("M3DREG_HOST_OVERLAP")) == 0);
+	cudaStream_t cs = overlap ? c->copy_stream : c->stream;
+	CK(cudaEventRecord(c->ev_copy[0], c->stream));
+	CK(cudaStreamWaitEvent(cs, c->ev_copy[0], 0));
+	CK(cudaMemcpyAsync(c->aos_a.p, first_local, (size_t)n1 * sizeof(m3dreg_point), cudaMemcpyHostToDevice, cs));
+	CK(cudaEventRecord(c->ev_copy[1], cs));
+	CK(cudaMemcpyAsync(c->aos_b.p, second_global, (size_t)n2 * sizeof(m3dreg_point), cudaMemcpyHostToDevice, cs));
+	CK(cudaEventRecord(c->ev_copy[2], cs));
+	CK(cudaStreamWaitEvent(c->stream, c->ev_copy[1], 0));
 	LAUNCH(c, k_unpack_points, (n1 + 255) / 256, 256, c->aos_a.p, n1, c->l_xyzl.p, c->l_nrm.p);
-	LAUNCH(c, k_unpack_points, (n2 + 255) / 256, 256, c->aos_b.p, n2, c->q_xyzl.p, c->q_nrm.p);
 	c->act_perm = nullptr;
 	LocalBox box;
-	if ((e = local_box_aos(c, c->aos_a.p, n1, &box))) return e;
-	e = icp_loop(c, c->l_xyzl.p, c->l_nrm.p, n1, n2, pose_first, prm, 1, stats, box);
+	e = local_box_aos(c, c->aos_a.p, n1, &box);
+	if (!e) {
+		/* the queries are unpacked by the iteration itself, after the grid of the first cloud is built (icp_iteration_device) */
+		c->q_deferred_ev = c->ev_copy[2]; c->q_deferred_aos = c->aos_b.p; c->q_deferred_n = n2;
+		e = icp_loop(c, c->l_xyzl.p, c->l_nrm.p, n1, n2, pose_first, prm, 1, stats, box);
+	}
 	c->active = false;
+	if (c->q_deferred_ev || e) {      /* not consumed (error path): the caller's buffers must not be read after the return */
+		c->q_deferred_ev = nullptr;
+		cudaStreamSynchronize(c->copy_stream);
+	}
 	if (e) return e;
 	if (nn_out) {
 		if (prm->mode == M3DREG_MODE_NDT) CK(cudaMemsetAsync(c->nn.p, 0xFF, (size_t)n2 * sizeof(int), c->stream));

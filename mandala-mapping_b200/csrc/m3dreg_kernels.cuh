@@ -1615,6 +1615,26 @@ __global__ void k_pose_prepare(PoseState *ps)
 	if (blockIdx.x == 0 && threadIdx.x < 32) pose_prepare_warp(ps, threadIdx.x, nullptr);
 }
 
+/* Start of a fused loop: the pose state is cleared and the caller's pose arrives as a KERNEL ARGUMENT — a host-to-device
+ * copy of 300 bytes would queue on the copy engine behind whatever upload is running (the host-buffer iteration keeps the
+ * second cloud's 42 MB in flight at that moment) — then the first iteration's Euler round trip. */
+struct Pose16 { float m[16]; };
+__global__ void k_pose_init(PoseState *ps, const Pose16 pose, unsigned long long *label_counts, int *flags, unsigned int *ticket)
+{
+	pdl_enter();
+	if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+	const int lane = threadIdx.x;
+	if (lane < 4) label_counts[lane] = 0ull;
+	if (lane < FLAG_COUNT) flags[lane] = 0;
+	if (lane == 0) *ticket = 0u;
+	unsigned int *w = reinterpret_cast<unsigned int *>(ps);
+	for (int k = lane; k < (int)(sizeof(PoseState) / sizeof(unsigned int)); k += 32) w[k] = 0u;
+	__syncwarp();
+	if (lane < 16) ps->m[lane] = pose.m[lane];
+	__syncwarp();
+	pose_prepare_warp(ps, lane, nullptr);
+}
+
 /* ---- warp-cooperative versions of the serial tail ------------------------------------------------------------
  * The last block's tail (6x6 system, Cholesky, pose update, two Euler conversions) is a chain of ~20 double
  * precision transcendental calls when one thread runs it; here the calls that do not depend on each other are
