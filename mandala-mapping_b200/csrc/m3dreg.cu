@@ -14,6 +14,7 @@
 #include <cstring>
 #include <cstdio>
 #include <algorithm>
+#include <chrono>
 
 #include "m3dreg_kernels.cuh"
 #include "grid_build.cuh"
@@ -1387,18 +1388,35 @@ static int icp_end_internal(m3dreg_ctx *c, float *pose_first_out, m3dreg_icp_sta
 	return (int)cudaGetLastError();
 }
 
+/* env M3DREG_HOST_TRACE=1: host time stamps of the host-buffer iteration's steps on stderr (tools/e2e_probe.py) */
+static bool host_trace_on()
+{
+	static const bool on = getenv("M3DREG_HOST_TRACE") && atoi(getenv("M3DREG_HOST_TRACE")) != 0;
+	return on;
+}
+static double host_now_us()
+{
+	return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+#define HOST_TRACE(label) do { if (host_trace_on()) fprintf(stderr, "[m3dreg host trace] %-34s %12.1f us\n", label, host_now_us()); } while (0)
+
 static int icp_loop(m3dreg_ctx *c, const float4 *lx, const float4 *ln, int n1, int n2, float *pose_first,
 		const m3dreg_reg_params *prm, int iterations, m3dreg_icp_stats *stats, const LocalBox &box)
 {
 	int e = icp_begin_internal(c, lx, ln, n1, n2, pose_first, prm, box);
 	if (e) return e;
 	CK(cudaEventRecord(c->ev0, c->stream));
+	HOST_TRACE("loop: begin enqueued");
 	if ((e = run_iterations(c, iterations))) return e;
 	CK(cudaEventRecord(c->ev1, c->stream));
+	HOST_TRACE("loop: iterations enqueued");
 	CK(cudaEventSynchronize(c->ev1));
+	HOST_TRACE("loop: iterations done");
 	float ms = 0.0f;
 	cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-	return icp_end_internal(c, pose_first, stats, ms);
+	e = icp_end_internal(c, pose_first, stats, ms);
+	HOST_TRACE("loop: state read back");
+	return e;
 }
 
 static int stage_queries(m3dreg_ctx *c, int second_slot, const float *pose_second)
@@ -1517,6 +1535,7 @@ int m3dreg_icp_iteration_host(m3dreg_ctx *c, const m3dreg_point *first_local, in
 	}
 	/* uploads on the copy stream, ordered after whatever the registration stream still does with the staging buffers
 	 * (env M3DREG_HOST_OVERLAP=0: on the registration stream itself, i.e. nothing runs under the transfers — A/B runs) */
+	HOST_TRACE("host iteration: entry");
 	static const bool overlap = !(getenv("M3DREG_HOST_OVERLAP") && atoi(getenv("M3DREG_HOST_OVERLAP")) == 0);
 	cudaStream_t cs = overlap ? c->copy_stream : c->stream;
 	CK(cudaEventRecord(c->ev_copy[0], c->stream));
@@ -1529,7 +1548,9 @@ int m3dreg_icp_iteration_host(m3dreg_ctx *c, const m3dreg_point *first_local, in
 	LAUNCH(c, k_unpack_points, (n1 + 255) / 256, 256, c->aos_a.p, n1, c->l_xyzl.p, c->l_nrm.p);
 	c->act_perm = nullptr;
 	LocalBox box;
+	HOST_TRACE("host iteration: copies enqueued");
 	e = local_box_aos(c, c->aos_a.p, n1, &box);
+	HOST_TRACE("host iteration: local box known");
 	if (!e) {
 		/* the queries are unpacked by the iteration itself, after the grid of the first cloud is built (icp_iteration_device) */
 		c->q_deferred_ev = c->ev_copy[2]; c->q_deferred_aos = c->aos_b.p; c->q_deferred_n = n2;
@@ -1547,6 +1568,7 @@ int m3dreg_icp_iteration_host(m3dreg_ctx *c, const m3dreg_point *first_local, in
 		CK(cudaMemcpyAsync(nn_out, c->nn.p, (size_t)n2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
 	}
+	HOST_TRACE("host iteration: nn read back");
 	return (int)cudaGetLastError();
 }
 

@@ -29,3 +29,6 @@ print("bare D2H of nn: %.3f ms" % t(lambda: h_nn.copy_(dn, non_blocking=True)))
 print("m3dreg_icp_iteration_host (nn out): %.3f ms" % t(lambda: bench._e2e_call(ctx, pkg, h_first, n1, h_second, n2, pose, prm, h_nn)))
 st = bench._e2e_call(ctx, pkg, h_first, n1, h_second, n2, pose, prm, h_nn)
 print("device_ms of the iteration inside the call: %.3f" % st.device_ms)
+if os.environ.get("M3DREG_HOST_TRACE"):
+    print("-- one traced call (stderr)")
+    bench._e2e_call(ctx, pkg, h_first, n1, h_second, n2, pose, prm, h_nn)
