@@ -274,7 +274,9 @@ int m3dreg_get_stage_ms(m3dreg_ctx *ctx, float *ms_out, int *iterations_out);
 
 /* Same iteration, but through HOST clouds every call the way the reference crosses the
  * boundary (both 40-B clouds H2D, nn + pose D2H): first is in its LOCAL frame, second already
- * in the global frame.  nn_out may be NULL. */
+ * in the global frame.  nn_out may be NULL.  The uploads run on an internal copy stream and the
+ * first cloud's grid is built under the second upload; the call synchronises before returning
+ * (the caller's buffers are free again, pose_first / stats / nn_out are final). */
 int m3dreg_icp_iteration_host(m3dreg_ctx *ctx,
 		const m3dreg_point *first_local, int n_first, const m3dreg_point *second_global, int n_second,
 		float *pose_first, const m3dreg_reg_params *params, int *nn_out, m3dreg_icp_stats *stats);
